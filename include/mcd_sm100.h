@@ -1,0 +1,201 @@
+/*
+ * mcd_sm100.h — C-ABI of libmcd_sm100.so, the B200 (sm_100a) kernel library behind the
+ * Maximum-Classifier-Discrepancy (MCD) training / inference step of
+ * LittleWat/multichannel-semseg-with-uda.
+ *
+ * The reference has no FFI: every op below replaces a stock PyTorch call made by the reference's
+ * nn.Modules (file:line cited per entry point, paths relative to the reference checkout).  The
+ * host-side mirror of those modules (multichannel-semseg-with-uda_b200/{models,loss.py}) binds
+ * these symbols with ctypes (mcd_b200/abi.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative MCD_E_* code on failure; the message is
+ *     available from mcd_last_error() (thread-local).  Nothing throws across the ABI.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the library allocates no
+ *     persistent device memory: outputs and workspaces are supplied by the caller.
+ *   - `stream` is a cudaStream_t passed as void*; `device` is the CUDA ordinal the pointers live on
+ *     (the call is re-entrant and may come from PyTorch's autograd worker thread).
+ *   - "nhwc" tensors are bf16, channel count C must be a multiple of 8 (16-byte TMA stride rule);
+ *     "planar" tensors are NCHW-contiguous.  Image geometry is (N, H, W).
+ *   - conv weights are consumed in a packed bf16 form produced by mcd_pack_weight():
+ *         [rows][taps][kc_pad]   kc_pad = round_up(reduce-channels, 64)
+ *     fprop : rows = Cout, taps in (r,s) order, reduce-channels = Cin
+ *     dgrad : rows = Cin,  taps flipped,        reduce-channels = Cout
+ */
+#ifndef MCD_SM100_H
+#define MCD_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCD_ABI_VERSION 3
+
+enum {
+  MCD_OK = 0,
+  MCD_E_INVALID = -1,   /* bad argument / unsupported shape            */
+  MCD_E_CUDA = -2,      /* a CUDA runtime / driver call failed          */
+  MCD_E_WORKSPACE = -3, /* caller workspace too small                   */
+  MCD_E_ARCH = -4       /* device is not sm_100                         */
+};
+
+/* conv algorithm selector */
+enum {
+  MCD_ALGO_AUTO = 0,   /* tcgen05 implicit GEMM when the shape allows it, else direct */
+  MCD_ALGO_DIRECT = 1, /* smem-tiled CUDA-core kernel (any shape; cross-check + thin layers) */
+  MCD_ALGO_UMMA = 2    /* tcgen05/TMEM/TMA implicit GEMM; MCD_E_INVALID if shape unsupported */
+};
+
+/* output layout of mcd_conv2d_fprop */
+enum {
+  MCD_OUT_NHWC_BF16 = 0, /* [N,Ho,Wo,Cout] bf16, Cout % 8 == 0 */
+  MCD_OUT_PLANAR_F32 = 1 /* [N,Cout,Ho,Wo] fp32 (score maps: seg / decoder heads, any Cout) */
+};
+
+/* Geometry of one convolution (nn.Conv2d semantics: models/drn.py:21-23,126-128,195-205). */
+typedef struct mcd_conv_geom {
+  int32_t N, H, W;     /* input image geometry                       */
+  int32_t Cin, Cout;   /* logical channel counts                      */
+  int32_t Cin_s;       /* channel stride of the nhwc input  (>= Cin, % 8 == 0) */
+  int32_t Cout_s;      /* channel stride of the nhwc output / dy (>= Cout, % 8 == 0) */
+  int32_t R, S;        /* filter size                                 */
+  int32_t stride, dil, pad;
+  int32_t Ho, Wo;      /* output geometry                             */
+} mcd_conv_geom;
+
+const char* mcd_last_error(void);
+int mcd_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t mcd_launch_count(void);
+/* 0 if `device` is an sm_100 part, MCD_E_ARCH otherwise. */
+int mcd_check_device(int device);
+
+/* ---- layout ----------------------------------------------------------------------------- */
+/* NCHW fp32 -> NHWC bf16 with channel stride Cs (zero fill of channels >= C).  Replaces the
+ * implicit layout of `Variable(...).cuda()` inputs (adapt_trainer.py:156-160). */
+int mcd_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cs,
+                              int device, void* stream);
+/* NHWC bf16 (channel stride Cs) -> NCHW fp32 (first C channels). */
+int mcd_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cs,
+                              int device, void* stream);
+/* fp32 OIHW nn.Conv2d weight -> packed bf16.  mode 0 = fprop, 1 = dgrad (see header comment).
+ * dst holds rows*R*S*kc_pad bf16 where rows = (mode ? Cin : Cout), kc_pad = round_up(mode ? Cout : Cin, 64). */
+int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int mode,
+                    int device, void* stream);
+
+/* ---- convolution (nn.Conv2d: models/drn.py:21-23,126-131,171-205; dilated_fcn.py:226-232,632-658,821-823) */
+/* y = conv(x, w) (+ bias).  If `stats` != NULL (fp32 [2*Cout], caller-zeroed) the kernel also
+ * accumulates per-channel sum and sum of squares of y for train-mode BatchNorm. */
+int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias, void* y,
+                     int y_layout, float* stats, const mcd_conv_geom* g, int algo, int device,
+                     void* stream);
+/* dx = conv_transpose(dy, w): gradient wrt the nhwc input.  w_packed is the mode-1 pack. */
+int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc,
+                     const mcd_conv_geom* g, int algo, int device, void* stream);
+/* dw (fp32 OIHW, overwritten) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).
+ * workspace: mcd_conv2d_wgrad_workspace() bytes. */
+size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo);
+int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, float* dbias,
+                     void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int algo,
+                     int device, void* stream);
+
+/* ---- BatchNorm2d (+ReLU, +residual)  (nn.BatchNorm2d defaults eps 1e-5 momentum 0.1:
+ *      models/drn.py:34-59,129-131,167-169,199-204; --fix_bn: models/model_util.py:305-310) -------- */
+/* per-channel sum / sum-of-squares of an nhwc tensor into caller-zeroed stats[2*C]. */
+int mcd_bn_stats(const void* y_nhwc, float* stats, int64_t P, int C, int Cs, int device, void* stream);
+/* training: mean/var from stats (count = P), writes scale/shift (fp32 [C] each), save_mean,
+ * save_rstd, and updates running_mean / running_var (unbiased) with `momentum`.
+ * eval (training == 0): scale/shift from running stats, save_* = running mean / rstd.
+ * num_batches_tracked (int64 scalar, may be NULL) is incremented in training mode. */
+int mcd_bn_finalize(const float* stats, int64_t P, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps,
+                    int training, float* scale, float* shift, float* save_mean, float* save_rstd,
+                    int64_t* num_batches_tracked, int C, int device, void* stream);
+/* z = act(scale*y + shift + residual'), residual' = res (identity) or rscale*res + rshift
+ * (downsample branch, models/drn.py:53-56); res / rscale may be NULL; relu = 0/1. */
+int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, const void* res_nhwc,
+                 const float* rscale, const float* rshift, int relu, void* z_nhwc, int64_t P, int C,
+                 int Cs, int device, void* stream);
+/* backward reductions: g = dz * (relu ? z > 0 : 1);
+ *   sums[0:C]  = sum g, sums[C:2C] = sum g * xhat(y)   [, sums[2C:3C] = sum g * xhat(res) if res_mean]
+ * sums is caller-zeroed fp32 [3*C]. */
+int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc,
+                      const float* mean, const float* rstd, const void* res_nhwc,
+                      const float* res_mean, const float* res_rstd, int relu, float* sums, int64_t P,
+                      int C, int Cs, int device, void* stream);
+/* dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat))  (training) or gamma*rstd*g (eval);
+ * optional second branch dres with its own gamma/mean/rstd (downsample BN) or, when
+ * res_gamma == NULL and dres != NULL, the identity residual gradient dres = g.
+ * dgamma/dbeta (fp32 [C]) are written from sums. */
+int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc, const float* gamma,
+                     const float* mean, const float* rstd, const float* sums, int training, int relu,
+                     void* dy_nhwc, float* dgamma, float* dbeta, const void* res_nhwc,
+                     const float* res_gamma, const float* res_mean, const float* res_rstd,
+                     int res_training, void* dres_nhwc, float* dres_gamma, float* dres_beta,
+                     int64_t P, int C, int Cs, int device, void* stream);
+
+/* ---- classifier heads --------------------------------------------------------------------- */
+/* Depthwise ConvTranspose2d(C,C,16,stride 8,pad 4,groups C,bias=False)
+ * (dilated_fcn.py:357-366,465-470,479-491).  x,x2: planar fp32 [N,C,h,w]; w,w2: fp32 [C,1,16,16];
+ * out: planar bf16 [N,C,8h,8w].  out = up_w(x) (+ up_w2(x2) when x2 != NULL; if w2 == NULL the
+ * same weight is used, i.e. AddFusion up(x1+x2)). */
+int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const float* w2, void* out,
+                       int N, int C, int h, int w_, int device, void* stream);
+/* dx (planar fp32 [N,C,h,w], overwritten) and dw (fp32 [C,256], overwritten) from dout (planar bf16). */
+int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* dx, float* dw, int N,
+                       int C, int h, int w_, int device, void* stream);
+/* nn.Upsample(scale_factor=s, mode='bilinear'), align_corners=False (dilated_fcn.py:676,817-819).
+ * x planar fp32 [N,C,h,w] -> out planar bf16 (out_f32 == 0) or fp32 [N,C,s*h,s*w]. */
+int mcd_bilinear_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s,
+                        int device, void* stream);
+int mcd_bilinear_up_bwd(const void* dout, int dout_f32, float* dx, int N, int C, int h, int w_,
+                        int s, int device, void* stream);
+
+/* ---- per-pixel losses (loss.py:7-13,93-100,131-138; dilated_fcn.py:712,958; util.py:44-48) - */
+/* CrossEntropyLoss2d: log_softmax(dim=1) + NLLLoss2d(weight, mean, ignore_index).
+ * logits planar bf16 [N,C,H,W]; target int64 [N,H,W]; weight fp32 [C] or NULL.
+ * acc (fp32 [4], caller-zeroed): acc[0] += sum w*nll, acc[1] += sum w, acc[2] += #bad labels. */
+int mcd_ce2d_fwd(const void* logits, const int64_t* target, const float* weight,
+                 int64_t ignore_index, float* acc, int N, int C, int H, int W, int device,
+                 void* stream);
+/* dlogits (planar bf16) = gscale[0] * w[y]*(softmax - onehot) / acc[1]; gscale is a device fp32 scalar
+ * (the upstream gradient). */
+int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
+                 int64_t ignore_index, const float* acc, const float* gscale, void* dlogits, int N,
+                 int C, int H, int W, int device, void* stream);
+/* Diff2d: mean |softmax(a) - softmax(b)| over N*C*H*W.  acc[0] += sum |.| */
+int mcd_diff2d_fwd(const void* a, const void* b, float* acc, int N, int C, int H, int W, int device,
+                   void* stream);
+int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, void* da, void* db, int N,
+                   int C, int H, int W, int device, void* stream);
+/* F.mse_loss(pred, target) with pred planar bf16, target planar fp32: acc[0] += sum (p-t)^2 */
+int mcd_mse_fwd(const void* pred, const float* target, float* acc, int64_t numel, int device,
+                void* stream);
+int mcd_mse_bwd(const void* pred, const float* target, const float* gscale, void* dpred,
+                int64_t numel, int device, void* stream);
+/* boundary head: p = (sigmoid(h1)+sigmoid(h2)+sigmoid(h3))/3 (dilated_fcn.py:913-923) followed by
+ * bce2d (loss.py:131-138).  h* planar bf16 [numel]; target fp32 in {0,1}.
+ * tsum (fp32[1], caller-zeroed) receives sum(target) from mcd_bce_target_sum first. */
+int mcd_sum_f32(const float* x, float* acc, int64_t numel, int device, void* stream);
+int mcd_sigmoid3_bce_fwd(const void* h1, const void* h2, const void* h3, const float* target,
+                         const float* tsum, float* acc, void* p_out, int64_t numel, int device,
+                         void* stream);
+int mcd_sigmoid3_bce_bwd(const void* h1, const void* h2, const void* h3, const float* target,
+                         const float* tsum, const float* gscale, void* dh1, void* dh2, void* dh3,
+                         int64_t numel, int device, void* stream);
+/* Testers: argmax over channels [0, C_arg) (first max wins, like torch.max) + entropy partial
+ * acc[0] += sum_c p*log(p+1e-6) over all C channels (adapt_tester.py:104-124, util.py:44-48). */
+int mcd_argmax_entropy(const void* logits, int64_t* labels, float* acc, int N, int C, int C_arg,
+                       int H, int W, int device, void* stream);
+
+/* ---- optimiser (models/model_util.py:289-302: SGD momentum / weight decay, torch semantics) - */
+int mcd_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t numel, float lr,
+                 float momentum, float weight_decay, int first_step, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCD_SM100_H */

@@ -1,0 +1,307 @@
+// bn.cu — BatchNorm2d (+ReLU, +residual) forward / backward on NHWC bf16 activations.
+// Reference semantics: nn.BatchNorm2d(eps=1e-5, momentum=0.1, affine, track_running_stats) as used by
+// models/drn.py:34-59 (BasicBlock), :129-131, :199-204 and dilated_fcn.py:632-644 (CBR); eval / --fix_bn
+// (models/model_util.py:305-310) uses the running statistics.
+// All kernels are single-pass, 16-byte vectorised and HBM-bound.
+#include "common.cuh"
+
+namespace mcd {
+
+// ---- per-channel reductions ------------------------------------------------------------------
+// MODE 0: stats      : acc0 = sum y, acc1 = sum y^2
+// MODE 1: bwd reduce : g = dz * (z > 0 | !relu); acc0 = sum g, acc1 = sum g*xhat(y), acc2 = sum g*xhat(res)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
+                 const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ res,
+                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                 const float* __restrict__ res_mean, const float* __restrict__ res_rstd, int relu,
+                 float* __restrict__ out, int64_t P, int C, int Cs) {
+  extern __shared__ float sh[];  // 3 * Cs
+  const int vpr = Cs >> 3;                 // 16-byte vectors per pixel row
+  const int rpi = 256 / vpr;               // pixel rows per block iteration
+  const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
+  const bool active = pr < rpi;
+  for (int i = threadIdx.x; i < 3 * Cs; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  float a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a0[k] = a1[k] = a2[k] = 0.f;
+  float mu[8], rs[8], mu2[8], rs2[8];
+  const int c0 = cv * 8;
+  if (MODE == 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = min(c0 + k, C - 1);
+      mu[k] = mean[c]; rs[k] = rstd[c];
+      mu2[k] = res_mean ? res_mean[c] : 0.f; rs2[k] = res_mean ? res_rstd[c] : 0.f;
+    }
+  }
+  if (active) {
+    for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += (int64_t)gridDim.x * rpi) {
+      const int64_t off = p * Cs + c0;
+      float fy[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + off), fy);
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0[k] += fy[k]; a1[k] = fmaf(fy[k], fy[k], a1[k]); }
+      } else {
+        float fd[8], fz[8], fr[8];
+        unpack8(*reinterpret_cast<const uint4*>(dz + off), fd);
+        if (relu) unpack8(*reinterpret_cast<const uint4*>(z + off), fz);
+        if (res_mean) unpack8(*reinterpret_cast<const uint4*>(res + off), fr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float g = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
+          a0[k] += g;
+          a1[k] = fmaf(g, (fy[k] - mu[k]) * rs[k], a1[k]);
+          if (res_mean) a2[k] = fmaf(g, (fr[k] - mu2[k]) * rs2[k], a2[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sh[c0 + k], a0[k]);
+      atomicAdd(&sh[Cs + c0 + k], a1[k]);
+      if (MODE == 1 && res_mean) atomicAdd(&sh[2 * Cs + c0 + k], a2[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    atomicAdd(out + c, sh[c]);
+    atomicAdd(out + C + c, sh[Cs + c]);
+    if (MODE == 1 && res_mean) atomicAdd(out + 2 * C + c, sh[2 * Cs + c]);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, double invP, double unbias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, int training, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_rstd, int64_t* __restrict__ nbt,
+                                   int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c == 0 && training && nbt) *nbt += 1;
+  float mean, var;
+  if (training) {
+    double m = (double)stats[c] * invP;
+    double v = (double)stats[C + c] * invP - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m; var = (float)v;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(v * unbias);
+    }
+  } else {
+    mean = running_mean[c]; var = running_var[c];
+  }
+  float rstd = rsqrtf(var + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * rstd;
+  shift[c] = b - mean * g * rstd;
+  save_mean[c] = mean;
+  save_rstd[c] = rstd;
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
+                __nv_bfloat16* __restrict__ z, int64_t nvec, int vpr) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) * 8;
+    float f[8], sc[8], sf[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + c0));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+    *reinterpret_cast<float4*>(sf) = __ldg(reinterpret_cast<const float4*>(shift + c0));
+    *reinterpret_cast<float4*>(sf + 4) = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
+    if (res) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + i * 8), r);
+      if (rscale) {
+        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(rscale + c0));
+        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(rscale + c0 + 4));
+        *reinterpret_cast<float4*>(sf) = __ldg(reinterpret_cast<const float4*>(rshift + c0));
+        *reinterpret_cast<float4*>(sf + 4) = __ldg(reinterpret_cast<const float4*>(rshift + c0 + 4));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], sc[k], sf[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += r[k];
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    *reinterpret_cast<uint4*>(z + i * 8) = pack8(f);
+  }
+}
+
+struct BwdBranch {
+  const float* gamma; const float* mean; const float* rstd;
+  int training;
+};
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
+                    const __nv_bfloat16* __restrict__ y, BwdBranch b1, const float* __restrict__ sums,
+                    int relu, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, const __nv_bfloat16* __restrict__ res, BwdBranch b2,
+                    __nv_bfloat16* __restrict__ dres, float* __restrict__ dres_gamma,
+                    float* __restrict__ dres_beta, float invP, int64_t nvec, int vpr, int C) {
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dgamma) dgamma[c] = sums[C + c];
+      if (dbeta) dbeta[c] = sums[c];
+      if (dres_gamma) dres_gamma[c] = sums[2 * C + c];
+      if (dres_beta) dres_beta[c] = sums[c];
+    }
+  }
+  const bool has_res_bn = dres && b2.gamma;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) * 8;
+    float fd[8], fz[8], fy[8], g[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dz + i * 8), fd);
+    if (relu) unpack8(*reinterpret_cast<const uint4*>(z + i * 8), fz);
+    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), fy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
+      const float gm = __ldg(b1.gamma + c), rs = __ldg(b1.rstd + c);
+      if (b1.training) {
+        const float xh = (fy[k] - __ldg(b1.mean + c)) * rs;
+        o[k] = gm * rs * (g[k] - __ldg(sums + c) * invP - xh * __ldg(sums + C + c) * invP);
+      } else {
+        o[k] = gm * rs * g[k];
+      }
+    }
+    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+    if (dres) {
+      if (has_res_bn) {
+        float fr[8];
+        unpack8(*reinterpret_cast<const uint4*>(res + i * 8), fr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 + k;
+          const float gm = __ldg(b2.gamma + c), rs = __ldg(b2.rstd + c);
+          if (b2.training) {
+            const float xh = (fr[k] - __ldg(b2.mean + c)) * rs;
+            o[k] = gm * rs * (g[k] - __ldg(sums + c) * invP - xh * __ldg(sums + 2 * C + c) * invP);
+          } else {
+            o[k] = gm * rs * g[k];
+          }
+        }
+        *reinterpret_cast<uint4*>(dres + i * 8) = pack8(o);
+      } else {
+        *reinterpret_cast<uint4*>(dres + i * 8) = pack8(g);
+      }
+    }
+  }
+}
+
+int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaStream_t st) {
+  int vpr = Cs / 8, rpi = 256 / vpr;
+  int grid = (int)min64((P + rpi * 4 - 1) / (rpi * 4), 148 * 8);
+  grid = max(grid, 1);
+  bn_reduce_kernel<0><<<grid, 256, 3 * Cs * sizeof(float), st>>>(
+      (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stats, P,
+      C, Cs);
+  return check_launch("bn_stats");
+}
+
+}  // namespace mcd
+
+using namespace mcd;
+
+extern "C" {
+
+int mcd_bn_stats(const void* y_nhwc, float* stats, int64_t P, int C, int Cs, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(y_nhwc && stats && P > 0 && C > 0, "bn_stats: bad arguments");
+  MCD_REQUIRE(Cs >= C && Cs % 8 == 0 && Cs <= 2048, "bn_stats: channel stride %d unsupported", Cs);
+  return bn_stats_launch(y_nhwc, stats, P, C, Cs, (cudaStream_t)stream);
+}
+
+int mcd_bn_finalize(const float* stats, int64_t P, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps,
+                    int training, float* scale, float* shift, float* save_mean, float* save_rstd,
+                    int64_t* num_batches_tracked, int C, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(scale && shift && save_mean && save_rstd && C > 0, "bn_finalize: bad arguments");
+  MCD_REQUIRE(training ? (stats != nullptr && P > 0) : (running_mean && running_var),
+              "bn_finalize: missing statistics for mode training=%d", training);
+  double invP = training ? 1.0 / (double)P : 0.0;
+  double unbias = (training && P > 1) ? (double)P / (double)(P - 1) : 1.0;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      stats, invP, unbias, gamma, beta, running_mean, running_var, momentum, eps, training, scale,
+      shift, save_mean, save_rstd, num_batches_tracked, C);
+  return check_launch("bn_finalize");
+}
+
+int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, const void* res_nhwc,
+                 const float* rscale, const float* rshift, int relu, void* z_nhwc, int64_t P, int C,
+                 int Cs, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(y_nhwc && scale && shift && z_nhwc && P > 0, "bn_apply: bad arguments");
+  MCD_REQUIRE(Cs == C && C % 8 == 0, "bn_apply: needs dense channels, C %% 8 == 0 (C=%d Cs=%d)", C, Cs);
+  MCD_REQUIRE(!rscale || (res_nhwc && rshift), "bn_apply: residual affine without residual");
+  int64_t nvec = P * (Cs / 8);
+  int grid = (int)min64((nvec + 255) / 256, 148 * 16);
+  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y_nhwc, scale, shift, (const __nv_bfloat16*)res_nhwc, rscale, rshift, relu,
+      (__nv_bfloat16*)z_nhwc, nvec, Cs / 8);
+  return check_launch("bn_apply");
+}
+
+int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc,
+                      const float* mean, const float* rstd, const void* res_nhwc,
+                      const float* res_mean, const float* res_rstd, int relu, float* sums, int64_t P,
+                      int C, int Cs, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(dz_nhwc && y_nhwc && mean && rstd && sums && P > 0, "bn_bwd_reduce: bad arguments");
+  MCD_REQUIRE(!relu || z_nhwc, "bn_bwd_reduce: relu needs z");
+  MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_bwd_reduce: needs dense channels (C=%d Cs=%d)", C, Cs);
+  MCD_REQUIRE(!res_mean || (res_nhwc && res_rstd), "bn_bwd_reduce: residual stats without residual");
+  int vpr = Cs / 8, rpi = 256 / vpr;
+  int grid = (int)min64((P + rpi * 4 - 1) / (rpi * 4), 148 * 8);
+  grid = max(grid, 1);
+  bn_reduce_kernel<1><<<grid, 256, 3 * Cs * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y_nhwc, (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc,
+      (const __nv_bfloat16*)res_nhwc, mean, rstd, res_mean, res_rstd, relu, sums, P, C, Cs);
+  return check_launch("bn_bwd_reduce");
+}
+
+int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc, const float* gamma,
+                     const float* mean, const float* rstd, const float* sums, int training, int relu,
+                     void* dy_nhwc, float* dgamma, float* dbeta, const void* res_nhwc,
+                     const float* res_gamma, const float* res_mean, const float* res_rstd,
+                     int res_training, void* dres_nhwc, float* dres_gamma, float* dres_beta,
+                     int64_t P, int C, int Cs, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(dz_nhwc && y_nhwc && gamma && mean && rstd && sums && dy_nhwc && P > 0,
+              "bn_bwd_apply: bad arguments");
+  MCD_REQUIRE(!relu || z_nhwc, "bn_bwd_apply: relu needs z");
+  MCD_REQUIRE(Cs == C && C % 8 == 0, "bn_bwd_apply: needs dense channels (C=%d Cs=%d)", C, Cs);
+  MCD_REQUIRE(!res_gamma || (res_nhwc && res_mean && res_rstd && dres_nhwc),
+              "bn_bwd_apply: incomplete residual branch");
+  BwdBranch b1{gamma, mean, rstd, training};
+  BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
+  int64_t nvec = P * (Cs / 8);
+  int grid = (int)min64((nvec + 255) / 256, 148 * 16);
+  bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc, (const __nv_bfloat16*)y_nhwc, b1, sums,
+      relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, (const __nv_bfloat16*)res_nhwc, b2,
+      (__nv_bfloat16*)dres_nhwc, dres_gamma, dres_beta, (float)(1.0 / (double)P), nvec, Cs / 8, C);
+  return check_launch("bn_bwd_apply");
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+// common.cuh — shared helpers for libmcd_sm100 (error plumbing, launch accounting, bf16 utils).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/mcd_sm100.h"
+
+namespace mcd {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+// RAII-free guard: select the device for this call; every entry point starts with it.
+inline int enter(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    return MCD_E_CUDA;
+  }
+  return MCD_OK;
+}
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return MCD_E_CUDA;
+  }
+  count_launch();
+  return MCD_OK;
+}
+
+#define MCD_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::mcd::set_error(__VA_ARGS__);      \
+      return MCD_E_INVALID;               \
+    }                                     \
+  } while (0)
+
+#define MCD_ENTER(device)                 \
+  do {                                    \
+    int _rc = ::mcd::enter(device);       \
+    if (_rc != MCD_OK) return _rc;        \
+  } while (0)
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// unpack 8 bf16 (one 16-byte vector) to floats
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem32[wid] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (wid == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    r = lane < nw ? smem32[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+}  // namespace mcd

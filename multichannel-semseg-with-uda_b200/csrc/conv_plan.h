@@ -1,0 +1,92 @@
+// conv_plan.h — host-side lowering of one nn.Conv2d (fprop / dgrad) to "tap problems":
+// a dense gather-GEMM over a tile-space pixel grid, shared by the direct and the tcgen05 kernels.
+//
+//   out[n, ht*omul+oh0, wt*omul+ow0, row] = sum_t sum_kc src[n, ht*smul+dh_t, wt*smul+dw_t, kc]
+//                                                      * w_packed[row][wk_t][kc]
+//
+// fprop  stride s : one problem, smul = s, omul = 1, dh = r*dil - pad, wk = r*S+s.
+// dgrad  stride 1 : one problem over dy with the flipped-tap pack (mcd_pack_weight mode 1).
+// dgrad  stride 2 : four problems, one per output parity class (ph,pw); only the taps whose source
+//                   row (h + pad - r*dil)/2 is an integer contribute (models/drn.py:175-180 strided
+//                   convs: layer2, layer3.0, layer4.0 and their 1x1 downsample branches).
+#pragma once
+#include <stdint.h>
+
+namespace mcd {
+
+constexpr int kMaxTaps = 49;
+
+struct Tap {
+  int16_t dh, dw;   // source offset in source-grid pixels (after smul scaling of the tile coord)
+  int16_t wk;       // tap slot inside the packed weight row
+  int16_t map;      // tcgen05 path: which parity tensor map (0..3); direct path: unused
+  int16_t mdh, mdw; // tcgen05 path: offset inside the parity sub-grid
+  int16_t pad0, pad1;
+};
+
+struct TapProblem {
+  int N;
+  int Hs, Ws;          // source geometry
+  int Cs_src;          // source channel stride
+  int Kc;              // reduce channels actually present in the source (<= Cs_src)
+  int kc_pad;          // padded reduce channels per tap in the packed weights
+  int T_total;         // taps per packed weight row
+  int Ht, Wt;          // tile-space grid
+  int smul;            // source multiplier (direct kernel)
+  int omul, oh0, ow0;  // output placement
+  int Hd, Wd;          // destination geometry
+  int Cd_s;            // destination channel stride (nhwc) / channel count (planar)
+  int rows;            // GEMM-N: produced channels
+  int ntaps;
+  Tap taps[kMaxTaps];
+};
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+// fprop: returns 1 problem
+inline void plan_fprop(const mcd_conv_geom& g, TapProblem& p) {
+  p.N = g.N; p.Hs = g.H; p.Ws = g.W; p.Cs_src = g.Cin_s; p.Kc = g.Cin;
+  p.kc_pad = (g.Cin + 63) / 64 * 64; p.T_total = g.R * g.S;
+  p.Ht = g.Ho; p.Wt = g.Wo; p.smul = g.stride; p.omul = 1; p.oh0 = 0; p.ow0 = 0;
+  p.Hd = g.Ho; p.Wd = g.Wo; p.Cd_s = g.Cout_s; p.rows = g.Cout; p.ntaps = 0;
+  for (int r = 0; r < g.R; ++r)
+    for (int s = 0; s < g.S; ++s) {
+      Tap& t = p.taps[p.ntaps++];
+      t.dh = (int16_t)(r * g.dil - g.pad); t.dw = (int16_t)(s * g.dil - g.pad);
+      t.wk = (int16_t)(r * g.S + s);
+      // parity decomposition for stride 2: source row = stride*ht + dh = stride*(ht + floor(dh/stride)) + (dh mod stride)
+      int ph = posmod(t.dh, g.stride), pw = posmod(t.dw, g.stride);
+      t.map = (int16_t)(ph * g.stride + pw);
+      t.mdh = (int16_t)floordiv(t.dh, g.stride); t.mdw = (int16_t)floordiv(t.dw, g.stride);
+      t.pad0 = t.pad1 = 0;
+    }
+}
+
+// dgrad: returns the number of problems written to p[] (1 for stride 1, stride^2 for stride 2);
+// problems with ntaps == 0 mean "that parity class of dx is identically zero".
+inline int plan_dgrad(const mcd_conv_geom& g, TapProblem* p) {
+  int st = g.stride, np = 0;
+  for (int ph = 0; ph < st; ++ph)
+    for (int pw = 0; pw < st; ++pw) {
+      TapProblem& q = p[np++];
+      q.N = g.N; q.Hs = g.Ho; q.Ws = g.Wo; q.Cs_src = g.Cout_s; q.Kc = g.Cout;
+      q.kc_pad = (g.Cout + 63) / 64 * 64; q.T_total = g.R * g.S;
+      q.Ht = (g.H - ph + st - 1) / st; q.Wt = (g.W - pw + st - 1) / st;
+      q.smul = 1; q.omul = st; q.oh0 = ph; q.ow0 = pw;
+      q.Hd = g.H; q.Wd = g.W; q.Cd_s = g.Cin_s; q.rows = g.Cin; q.ntaps = 0;
+      for (int r = 0; r < g.R; ++r)
+        for (int s = 0; s < g.S; ++s) {
+          int nh = ph + g.pad - r * g.dil, nw = pw + g.pad - s * g.dil;
+          if (posmod(nh, st) != 0 || posmod(nw, st) != 0) continue;
+          Tap& t = q.taps[q.ntaps++];
+          t.dh = (int16_t)floordiv(nh, st); t.dw = (int16_t)floordiv(nw, st);
+          // mode-1 pack stores tap (r,s) at slot (R-1-r)*S + (S-1-s)
+          t.wk = (int16_t)((g.R - 1 - r) * g.S + (g.S - 1 - s));
+          t.map = 0; t.mdh = t.dh; t.mdw = t.dw; t.pad0 = t.pad1 = 0;
+        }
+    }
+  return np;
+}
+
+}  // namespace mcd

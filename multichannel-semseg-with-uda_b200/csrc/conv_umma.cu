@@ -1,0 +1,568 @@
+// conv_umma.cu — tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a.
+//
+//   fprop / dgrad ("tap problem" of conv_plan.h):
+//     D[128 pixels, BN channels] = sum over taps, 64-channel chunks  A_tap[128 x 64] * W_tap[BN x 64]^T
+//     A_tap is ONE 4-D TMA box {64 ch, TW, TH, 1 image} of the NHWC activations, shifted by the tap's
+//     (dh, dw); out-of-image coordinates are zero-filled by TMA, which implements the padding
+//     (models/drn.py:21-23 conv3x3 padding=dilation).  Strided convs read parity sub-grids of the
+//     image through up to 4 tensor maps.  Both operands are K-major, 128B-swizzled.
+//   wgrad:
+//     dW_tap[128 co, BN ci] = sum over 64-pixel tiles  dY[pix x co]^T * X_tap[pix x ci]
+//     both operands MN-major (channels contiguous), split over pixel ranges into a workspace that
+//     wgrad_reduce sums into the fp32 OIHW gradient.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "common.cuh"
+#include "conv_plan.h"
+#include "umma_ptx.cuh"
+
+namespace mcd {
+
+using namespace ptx;
+
+constexpr int kThreads = 192;
+
+struct UmmaMaps {
+  CUtensorMap a[4];  // activation maps (parity sub-grids for strided problems)
+  CUtensorMap b;     // fprop: packed weights; wgrad: dY
+};
+
+struct FpropArgs {
+  int N, Ht, Wt, TH, TW, tiles_h, tiles_w;
+  int kchunks, ntaps, kc_pad;
+  int rows;               // produced channels
+  int omul, oh0, ow0, Hd, Wd, Cd_s;
+  int planar;
+  const float* bias;
+  float* stats;
+  void* out;
+  Tap taps[kMaxTaps];
+};
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int A_BYTES = 128 * 128;          // 128 pixels x 64 ch bf16
+  static constexpr int B_BYTES = BN * 128;           // BN rows x 64 ch bf16
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
+  using Cfg = FpropCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
+  const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
+  const int n_img = mt;
+  const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = a.ntaps * a.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < a.ntaps; ++t) {
+        const Tap tap = a.taps[t];
+        const CUtensorMap* amap = &maps.a[tap.map];
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
+          tma_load_2d(sb, &maps.b, &full_bar[stage], tap.wk * a.kc_pad + kc * 64, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc_bf16(128, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint64_t adesc = smem_desc_sw128(sa, 0, 1024);
+        const uint64_t bdesc = smem_desc_sw128(sb, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-channel chunk: +32 bytes each
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                    (kb | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (kb == kblocks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ---- epilogue: thread = one output pixel (TMEM lane), loop over 32-channel column chunks ----
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ht = th0 + m / a.TW, wt = tw0 + m % a.TW;
+    const bool pvalid = ht < a.Ht && wt < a.Wt;
+    const int hd = ht * a.omul + a.oh0, wd = wt * a.omul + a.ow0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ncover = a.planar ? a.rows : a.Cd_s;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= ncover) break;   // warp-uniform
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int c = n0 + c0 + j;
+          v[j] += (c < a.rows) ? __ldg(a.bias + c) : 0.f;
+        }
+      }
+      if (pvalid) {
+        if (a.planar) {
+          float* o = reinterpret_cast<float*>(a.out);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int c = n0 + c0 + j;
+            if (c < a.rows) o[(((int64_t)n_img * a.rows + c) * a.Hd + hd) * a.Wd + wd] = v[j];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) +
+                             (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0 + c0;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            int c = n0 + c0 + j8 * 8;
+            if (c < a.Cd_s) {
+              float f[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
+              *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
+            }
+          }
+        }
+      }
+      if (a.stats) {
+        // column sums over the 32 pixels of this warp: butterfly transpose-reduce, lane j ends up
+        // holding column j.
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { float x = pvalid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const bool up = (lane & step) != 0;
+#pragma unroll
+          for (int i = 0; i < step; ++i) {
+            float send1 = up ? s1[i] : s1[i + step];
+            float keep1 = up ? s1[i + step] : s1[i];
+            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
+            float send2 = up ? s2[i] : s2[i + step];
+            float keep2 = up ? s2[i + step] : s2[i];
+            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+          }
+        }
+        int c = n0 + c0 + lane;
+        if (c < a.rows) {
+          atomicAdd(a.stats + c, s1[0]);
+          atomicAdd(a.stats + a.rows + c, s2[0]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad
+struct WgradArgs {
+  int N, tiles_h, tiles_w, TH, TW;   // 64-pixel tiles over the dY grid
+  int ntiles;                        // N * tiles_h * tiles_w
+  int ksplit;                        // pixel-tile ranges
+  int T;                             // taps
+  int CoutP, CinP;                   // padded workspace dims (multiples of 128 / BN)
+  float* ws;                         // [ksplit][T][CoutP][CinP]
+  Tap taps[kMaxTaps];
+};
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int KPIX = 64;
+  static constexpr int A_BYTES = 2 * KPIX * 128;             // two 64-co atoms
+  static constexpr int B_BYTES = (BN / 64) * KPIX * 128;     // BN/64 ci atoms
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = BN;
+};
+
+// grid: x = co tile (128), y = ci tile (BN), z = tap * ksplit + split
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ WgradArgs a) {
+  using Cfg = WgradCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BN;
+  const int t = blockIdx.z / a.ksplit, split = blockIdx.z % a.ksplit;
+  const int per = (a.ntiles + a.ksplit - 1) / a.ksplit;
+  const int tile_beg = split * per;
+  const int tile_end = min(tile_beg + per, a.ntiles);
+  const int ksteps = max(tile_end - tile_beg, 0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const Tap tap = a.taps[t];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const CUtensorMap* xmap = &maps.a[tap.map];
+      for (int ks = 0; ks < ksteps; ++ks) {
+        int tile = tile_beg + ks;
+        const int tw_i = tile % a.tiles_w; tile /= a.tiles_w;
+        const int th_i = tile % a.tiles_h; tile /= a.tiles_h;
+        const int n_img = tile;
+        const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          tma_load_4d(sa + i * Cfg::KPIX * 128, &maps.b, &full_bar[stage], co0 + i * 64, tw0, th0, n_img);
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i)
+          tma_load_4d(sb + i * Cfg::KPIX * 128, xmap, &full_bar[stage], ci0 + i * 64, tw0 + tap.mdw,
+                      th0 + tap.mdh, n_img);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc_bf16(128, BN, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        // MN-major, 128B swizzle: LBO = bytes between 64-channel atoms, SBO = 8 pixel rows
+        const uint64_t adesc = smem_desc_sw128(sa, Cfg::KPIX * 128, 1024);
+        const uint64_t bdesc = smem_desc_sw128(sb, Cfg::KPIX * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < Cfg::KPIX / 16; ++k)   // 16 pixel rows = 2048 bytes per UMMA_K step
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
+                    (ks | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        if (ks == ksteps - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    float* o = a.ws + (((int64_t)split * a.T + t) * a.CoutP + co) * a.CinP + ci0;
+    if (ksteps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (ksteps > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// dw[co][ci][r][s] = sum_split ws[split][t][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit,
+                                    int T, int CoutP, int CinP, int Cout, int Cin) {
+  int64_t total = (int64_t)Cout * Cin * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int ci = (int)(i % Cin);
+    int co = (int)((i / Cin) % Cout);
+    int t = (int)(i / ((int64_t)Cin * Cout));
+    float s = 0.f;
+    for (int k = 0; k < ksplit; ++k) s += ws[(((int64_t)k * T + t) * CoutP + co) * CinP + ci];
+    dw[((int64_t)co * Cin + ci) * T + t] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D map over an NHWC bf16 tensor viewed through a (ph,pw) parity sub-grid with step `st`.
+static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int Cs,
+                          int st, int ph, int pw, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
+  int Wsub = (W - pw + st - 1) / st, Hsub = (H - ph + st - 1) / st;
+  if (Wsub <= 0 || Hsub <= 0) { Wsub = max(Wsub, 1); Hsub = max(Hsub, 1); }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wsub, (cuuint64_t)Hsub, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)st * Cs * 2, (cuuint64_t)st * W * Cs * 2,
+                           (cuuint64_t)H * W * Cs * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const char* p = reinterpret_cast<const char*>(base) + ((int64_t)ph * W + pw) * Cs * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(p), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act N=%d H=%d W=%d C=%d Cs=%d st=%d box=%dx%d) failed: %d", N, H,
+              W, C, Cs, st, box_w, box_h, (int)r);
+    return MCD_E_CUDA;
+  }
+  return MCD_OK;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t kdim, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights rows=%d k=%lld) failed: %d", rows, (long long)kdim, (int)r);
+    return MCD_E_CUDA;
+  }
+  return MCD_OK;
+}
+
+// spatial tile of `npix` pixels minimising padded area; ties -> wider tile
+static void pick_tile(int Ht, int Wt, int npix, int* TH, int* TW) {
+  int64_t best = -1;
+  for (int tw = npix; tw >= 1; tw >>= 1) {
+    int th = npix / tw;
+    if (tw > 256 || th > 256) continue;
+    int64_t area = (int64_t)((Ht + th - 1) / th) * th * ((Wt + tw - 1) / tw) * tw;
+    if (best < 0 || area < best) { best = area; *TH = th; *TW = tw; }
+  }
+}
+
+bool umma_problem_supported(const TapProblem& p) {
+  if (p.smul != 1 && p.smul != 2) return false;
+  if (p.Cs_src % 8 != 0) return false;
+  if (p.ntaps > kMaxTaps) return false;
+  return true;
+}
+
+template <int BN>
+static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
+  using Cfg = FpropCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("fprop smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    attr_set = true;
+  }
+  conv_umma_fprop_kernel<BN><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  return check_launch("conv_umma_fprop");
+}
+
+// src: activations for this problem; for strided fprop the parity maps are built over (Hs, Ws).
+int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
+                        float* stats, const TapProblem& p, cudaStream_t st) {
+  if (p.ntaps == 0) return MCD_OK;
+  if (!umma_problem_supported(p)) { set_error("umma fprop: unsupported problem"); return MCD_E_INVALID; }
+  FpropArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = p.N; a.Ht = p.Ht; a.Wt = p.Wt;
+  pick_tile(p.Ht, p.Wt, 128, &a.TH, &a.TW);
+  a.tiles_h = (p.Ht + a.TH - 1) / a.TH; a.tiles_w = (p.Wt + a.TW - 1) / a.TW;
+  a.kchunks = (p.Kc + 63) / 64; a.ntaps = p.ntaps; a.kc_pad = p.kc_pad;
+  a.rows = p.rows; a.omul = p.omul; a.oh0 = p.oh0; a.ow0 = p.ow0; a.Hd = p.Hd; a.Wd = p.Wd;
+  a.Cd_s = p.Cd_s; a.planar = planar; a.bias = bias; a.stats = stats; a.out = out;
+  for (int t = 0; t < p.ntaps; ++t) a.taps[t] = p.taps[t];
+
+  UmmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int stp = p.smul;
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < p.ntaps; ++t) used[p.taps[t].map] = true;
+  for (int ph = 0; ph < stp; ++ph)
+    for (int pw = 0; pw < stp; ++pw) {
+      int id = ph * stp + pw;
+      if (!used[id]) continue;
+      int rc = encode_act_map(&maps.a[id], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, stp, ph, pw, a.TW, a.TH);
+      if (rc != MCD_OK) return rc;
+    }
+  if (!used[0]) maps.a[0] = maps.a[p.taps[0].map];  // keep the prefetch target valid
+
+  int ncover = planar ? p.rows : p.Cd_s;
+  int BN = ncover > 128 ? 256 : (ncover > 64 ? 128 : 64);
+  int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, BN);
+  if (rc != MCD_OK) return rc;
+  dim3 grid((unsigned)(p.N * a.tiles_h * a.tiles_w), (unsigned)((ncover + BN - 1) / BN));
+  if (BN == 256) return launch_fprop_bn<256>(maps, a, grid, st);
+  if (BN == 128) return launch_fprop_bn<128>(maps, a, grid, st);
+  return launch_fprop_bn<64>(maps, a, grid, st);
+}
+
+static int wgrad_bn(const mcd_conv_geom& g) { return g.Cin > 128 ? 256 : (g.Cin > 64 ? 128 : 64); }
+
+static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
+                        int* ntiles, int* ksplit) {
+  *BN = wgrad_bn(g);
+  *CoutP = round_up(g.Cout, 128);
+  *CinP = round_up(g.Cin, *BN);
+  pick_tile(g.Ho, g.Wo, 64, TH, TW);
+  *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
+  int base = (*CoutP / 128) * (*CinP / *BN) * g.R * g.S;
+  int ks = (2 * 148 + base - 1) / base;
+  ks = max(1, min(ks, *ntiles));
+  ks = min(ks, 64);
+  *ksplit = ks;
+}
+
+size_t umma_wgrad_workspace(const mcd_conv_geom& g) {
+  int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
+  wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
+  return sizeof(float) * (size_t)ksplit * g.R * g.S * CoutP * CinP;
+}
+
+template <int BN>
+static int launch_wgrad_bn(const UmmaMaps& maps, const WgradArgs& a, dim3 grid, cudaStream_t st) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("wgrad smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    attr_set = true;
+  }
+  conv_umma_wgrad_kernel<BN><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  return check_launch("conv_umma_wgrad");
+}
+
+int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+               const mcd_conv_geom& g, cudaStream_t st) {
+  if (g.stride != 1 && g.stride != 2) { set_error("umma wgrad: stride %d unsupported", g.stride); return MCD_E_INVALID; }
+  if (g.R * g.S > kMaxTaps) { set_error("umma wgrad: too many taps"); return MCD_E_INVALID; }
+  int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
+  wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
+  size_t need = sizeof(float) * (size_t)ksplit * g.R * g.S * CoutP * CinP;
+  if (ws_bytes < need || !ws) { set_error("umma wgrad: workspace %zu < %zu", ws_bytes, need); return MCD_E_WORKSPACE; }
+
+  TapProblem p;
+  plan_fprop(g, p);
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = g.N; a.TH = TH; a.TW = TW;
+  a.tiles_h = (g.Ho + TH - 1) / TH; a.tiles_w = (g.Wo + TW - 1) / TW;
+  a.ntiles = ntiles; a.ksplit = ksplit; a.T = g.R * g.S; a.CoutP = CoutP; a.CinP = CinP;
+  a.ws = reinterpret_cast<float*>(ws);
+  for (int t = 0; t < p.ntaps; ++t) a.taps[t] = p.taps[t];
+
+  UmmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < p.ntaps; ++t) used[p.taps[t].map] = true;
+  for (int ph = 0; ph < g.stride; ++ph)
+    for (int pw = 0; pw < g.stride; ++pw) {
+      int id = ph * g.stride + pw;
+      if (!used[id]) continue;
+      int rc = encode_act_map(&maps.a[id], x, g.N, g.H, g.W, g.Cin, g.Cin_s, g.stride, ph, pw, TW, TH);
+      if (rc != MCD_OK) return rc;
+    }
+  if (!used[0]) maps.a[0] = maps.a[p.taps[0].map];
+  int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, TW, TH);
+  if (rc != MCD_OK) return rc;
+
+  dim3 grid((unsigned)(CoutP / 128), (unsigned)(CinP / BN), (unsigned)(a.T * ksplit));
+  if (BN == 256) rc = launch_wgrad_bn<256>(maps, a, grid, st);
+  else if (BN == 128) rc = launch_wgrad_bn<128>(maps, a, grid, st);
+  else rc = launch_wgrad_bn<64>(maps, a, grid, st);
+  if (rc != MCD_OK) return rc;
+
+  int64_t total = (int64_t)g.Cout * g.Cin * a.T;
+  int rgrid = (int)min64((total + 255) / 256, 148 * 8);
+  wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout, g.Cin);
+  return check_launch("wgrad_reduce");
+}
+
+}  // namespace mcd

@@ -1,0 +1,274 @@
+// heads.cu — classifier-head upsampling: the learned depthwise ConvTranspose2d(C,C,16,s8,p4,groups=C)
+// of DRNSegPixelClassifier / FusionDRNSegPixelClassifier / ScoreFusionDRNSegPixelClassifier
+// (models/dilated_fcn.py:357-366,465-470,479-491) and nn.Upsample(bilinear, align_corners=False) of the
+// multitask decoders (models/dilated_fcn.py:676,817-819).  Low-res score maps are planar fp32, the
+// full-resolution outputs planar bf16 (or fp32 for regression targets); all kernels are HBM-bound
+// on the full-resolution tensor and read / write it exactly once.
+#include "common.cuh"
+
+namespace mcd {
+
+// ---- depthwise deconv 16x16 stride 8 pad 4 ------------------------------------------------------
+// out[oh][ow] = sum_{a,b in {0,1}} x[ih0-a][iw0-b] * w[kh0+8a][kw0+8b],  ih0 = (oh+4)>>3, kh0 = (oh+4)&7
+// grid: (N*C, ceil(H/8)); block 256; each thread produces 8 consecutive ow (one 16-byte store).
+__global__ void __launch_bounds__(256)
+deconv16s8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ x2, const float* __restrict__ w2,
+                      __nv_bfloat16* __restrict__ out, int C, int h, int wd) {
+  __shared__ float sw[2][256];
+  const int nc = blockIdx.x, c = nc % C;
+  const int H = h * 8, W = wd * 8;
+  sw[0][threadIdx.x] = w[c * 256 + threadIdx.x];
+  sw[1][threadIdx.x] = x2 ? (w2 ? w2 : w)[c * 256 + threadIdx.x] : 0.f;
+  __syncthreads();
+  const float* xp = x + (int64_t)nc * h * wd;
+  const float* xp2 = x2 ? x2 + (int64_t)nc * h * wd : nullptr;
+  __nv_bfloat16* op = out + (int64_t)nc * H * W;
+  const int oh_beg = blockIdx.y * 8, oh_end = min(oh_beg + 8, H);
+  const int items = (oh_end - oh_beg) * wd;  // one item = 8 consecutive output columns
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int oh = oh_beg + it / wd, j = it % wd;
+    const int ih0 = (oh + 4) >> 3, kh0 = (oh + 4) & 7;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ow = j * 8 + k;
+      const int iw0 = (ow + 4) >> 3, kw0 = (ow + 4) & 7;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int ih = ih0 - a;
+        if (ih < 0 || ih >= h) continue;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int iw = iw0 - b;
+          if (iw < 0 || iw >= wd) continue;
+          const int widx = (kh0 + 8 * a) * 16 + kw0 + 8 * b;
+          acc = fmaf(xp[ih * wd + iw], sw[0][widx], acc);
+          if (xp2) acc = fmaf(xp2[ih * wd + iw], sw[1][widx], acc);
+        }
+      }
+      f[k] = acc;
+    }
+    *reinterpret_cast<uint4*>(op + (int64_t)oh * W + j * 8) = pack8(f);
+  }
+}
+
+// dx[ih][iw] = sum_{kh,kw} dout[8ih-4+kh][8iw-4+kw] * w[kh][kw]
+// grid: (N*C, h); block 128: thread t handles iw = t, t+128, ...
+__global__ void __launch_bounds__(128)
+deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ w,
+                         float* __restrict__ dx, int C, int h, int wd) {
+  __shared__ float sw[256];
+  const int nc = blockIdx.x, c = nc % C, ih = blockIdx.y;
+  const int H = h * 8, W = wd * 8;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sw[i] = w[c * 256 + i];
+  __syncthreads();
+  const __nv_bfloat16* dp = dout + (int64_t)nc * H * W;
+  for (int iw = threadIdx.x; iw < wd; iw += blockDim.x) {
+    float acc = 0.f;
+    for (int kh = 0; kh < 16; ++kh) {
+      const int oh = 8 * ih - 4 + kh;
+      if (oh < 0 || oh >= H) continue;
+      const int ow0 = 8 * iw - 4;  // multiple of 4 -> 8-byte aligned groups of 4
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const int ow = ow0 + 4 * k4;
+        if (ow < 0 || ow + 3 >= W) continue;  // W % 8 == 0 and ow % 4 == 0: group fully in or out
+        const uint2 v = *reinterpret_cast<const uint2*>(dp + (int64_t)oh * W + ow);
+        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const float2 p0 = __bfloat1622float2(pv[0]), p1 = __bfloat1622float2(pv[1]);
+        const float* ww = &sw[kh * 16 + 4 * k4];
+        acc = fmaf(p0.x, ww[0], acc); acc = fmaf(p0.y, ww[1], acc);
+        acc = fmaf(p1.x, ww[2], acc); acc = fmaf(p1.y, ww[3], acc);
+      }
+    }
+    dx[(int64_t)nc * h * wd + ih * wd + iw] = acc;
+  }
+}
+
+// dw[c][kh][kw] = sum_{n,ih,iw} x[n,c,ih,iw] * dout[n,c,8ih-4+kh,8iw-4+kw]
+// grid: (C, 16 kh); block 256 = 16 kw x 16 position lanes.
+__global__ void __launch_bounds__(256)
+deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ x,
+                         float* __restrict__ dw, int N, int C, int h, int wd) {
+  __shared__ float red[16][17];
+  const int c = blockIdx.x, kh = blockIdx.y;
+  const int kw = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int H = h * 8, W = wd * 8;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const __nv_bfloat16* dp = dout + ((int64_t)n * C + c) * H * W;
+    const float* xp = x + ((int64_t)n * C + c) * h * wd;
+    for (int ih = 0; ih < h; ++ih) {
+      const int oh = 8 * ih - 4 + kh;
+      if (oh < 0 || oh >= H) continue;
+      for (int iw = pl; iw < wd; iw += 16) {
+        const int ow = 8 * iw - 4 + kw;
+        if (ow < 0 || ow >= W) continue;
+        acc = fmaf(xp[ih * wd + iw], bf2f(dp[(int64_t)oh * W + ow]), acc);
+      }
+    }
+  }
+  red[pl][kw] = acc;
+  __syncthreads();
+  if (pl == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += red[k][kw];
+    dw[c * 256 + kh * 16 + kw] = s;
+  }
+}
+
+// ---- bilinear upsample, align_corners=False ------------------------------------------------------
+__device__ __forceinline__ void bil_src(int o, int s, int in, int* i0, int* i1, float* lam) {
+  float src = (o + 0.5f) / (float)s - 0.5f;
+  if (src < 0.f) src = 0.f;
+  int a = (int)src;
+  if (a > in - 1) a = in - 1;
+  *i0 = a;
+  *i1 = a + (a < in - 1 ? 1 : 0);
+  *lam = src - (float)a;
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256)
+bilinear_fwd_kernel(const float* __restrict__ x, void* __restrict__ out, int h, int wd, int s,
+                    int64_t total8) {
+  const int H = h * s, W = wd * s;
+  const int w8 = W >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % w8);
+    const int oh = (int)((i / w8) % H);
+    const int64_t nc = i / ((int64_t)w8 * H);
+    int h0, h1; float lh;
+    bil_src(oh, s, h, &h0, &h1, &lh);
+    const float* r0 = x + (nc * h + h0) * wd;
+    const float* r1 = x + (nc * h + h1) * wd;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int w0, w1; float lw;
+      bil_src(j * 8 + k, s, wd, &w0, &w1, &lw);
+      const float top = r0[w0] + lw * (r0[w1] - r0[w0]);
+      const float bot = r1[w0] + lw * (r1[w1] - r1[w0]);
+      f[k] = top + lh * (bot - top);
+    }
+    const int64_t o = (nc * H + oh) * (int64_t)W + j * 8;
+    if (OUT_F32) {
+      float* op = reinterpret_cast<float*>(out) + o;
+      *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pack8(f);
+    }
+  }
+}
+
+// separable gather: block = one (n*c, ih) low-res row.
+//   col[ow] = sum_{oh} wh(oh, ih) * dout[oh][ow]     (coalesced along ow)
+//   dx[iw]  = sum_{ow} ww(ow, iw) * col[ow]
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+bilinear_bwd_kernel(const void* __restrict__ dout, float* __restrict__ dx, int h, int wd, int s) {
+  extern __shared__ float col[];  // W floats
+  const int H = h * s, W = wd * s;
+  const int64_t nc = blockIdx.x;
+  const int ih = blockIdx.y;
+  const int oh_lo = max(0, s * (ih - 1)), oh_hi = min(H - 1, s * (ih + 2) - 1);
+  for (int ow = threadIdx.x; ow < W; ow += blockDim.x) {
+    float acc = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int h0, h1; float lh;
+      bil_src(oh, s, h, &h0, &h1, &lh);
+      float wgt = (h0 == ih ? 1.f - lh : 0.f) + (h1 == ih ? lh : 0.f);
+      if (wgt == 0.f) continue;
+      const int64_t o = (nc * H + oh) * (int64_t)W + ow;
+      float v = IN_F32 ? reinterpret_cast<const float*>(dout)[o]
+                       : bf2f(reinterpret_cast<const __nv_bfloat16*>(dout)[o]);
+      acc = fmaf(wgt, v, acc);
+    }
+    col[ow] = acc;
+  }
+  __syncthreads();
+  for (int iw = threadIdx.x; iw < wd; iw += blockDim.x) {
+    const int ow_lo = max(0, s * (iw - 1)), ow_hi = min(W - 1, s * (iw + 2) - 1);
+    float acc = 0.f;
+    for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+      int w0, w1; float lw;
+      bil_src(ow, s, wd, &w0, &w1, &lw);
+      float wgt = (w0 == iw ? 1.f - lw : 0.f) + (w1 == iw ? lw : 0.f);
+      acc = fmaf(wgt, col[ow], acc);
+    }
+    dx[(nc * h + ih) * wd + iw] = acc;
+  }
+}
+
+}  // namespace mcd
+
+using namespace mcd;
+
+extern "C" {
+
+int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const float* w2, void* out,
+                       int N, int C, int h, int w_, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && w && out && N > 0 && C > 0 && h > 0 && w_ > 0, "deconv16s8_fwd: bad arguments");
+  dim3 grid((unsigned)(N * C), (unsigned)h);
+  deconv16s8_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, x2, w2, (__nv_bfloat16*)out, C,
+                                                                 h, w_);
+  return check_launch("deconv16s8_fwd");
+}
+
+int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* dx, float* dw, int N,
+                       int C, int h, int w_, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(dout && w && N > 0 && C > 0 && h > 0 && w_ > 0, "deconv16s8_bwd: bad arguments");
+  MCD_REQUIRE(!dw || x, "deconv16s8_bwd: dw needs x");
+  if (dx) {
+    dim3 grid((unsigned)(N * C), (unsigned)h);
+    deconv16s8_bwd_dx_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, w, dx,
+                                                                      C, h, w_);
+    int rc = check_launch("deconv16s8_bwd_dx");
+    if (rc != MCD_OK) return rc;
+  }
+  if (dw) {
+    dim3 grid((unsigned)C, 16);
+    deconv16s8_bwd_dw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, x, dw,
+                                                                      N, C, h, w_);
+    return check_launch("deconv16s8_bwd_dw");
+  }
+  return MCD_OK;
+}
+
+int mcd_bilinear_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s,
+                        int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && out && N > 0 && C > 0 && h > 0 && w_ > 0, "bilinear_up_fwd: bad arguments");
+  MCD_REQUIRE(s == 2 || s == 4 || s == 8, "bilinear_up_fwd: scale %d unsupported (2/4/8)", s);
+  MCD_REQUIRE((w_ * s) % 8 == 0, "bilinear_up_fwd: output width must be a multiple of 8");
+  int64_t total8 = (int64_t)N * C * h * s * (w_ * s / 8);
+  int grid = (int)min64((total8 + 255) / 256, 148 * 16);
+  if (out_f32)
+    bilinear_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, h, w_, s, total8);
+  else
+    bilinear_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, h, w_, s, total8);
+  return check_launch("bilinear_up_fwd");
+}
+
+int mcd_bilinear_up_bwd(const void* dout, int dout_f32, float* dx, int N, int C, int h, int w_,
+                        int s, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(dout && dx && N > 0 && C > 0 && h > 0 && w_ > 0, "bilinear_up_bwd: bad arguments");
+  MCD_REQUIRE(s == 2 || s == 4 || s == 8, "bilinear_up_bwd: scale %d unsupported (2/4/8)", s);
+  dim3 grid((unsigned)(N * C), (unsigned)h);
+  size_t smem = sizeof(float) * (size_t)w_ * s;
+  if (dout_f32)
+    bilinear_bwd_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, dx, h, w_, s);
+  else
+    bilinear_bwd_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, dx, h, w_, s);
+  return check_launch("bilinear_up_bwd");
+}
+
+}  // extern "C"

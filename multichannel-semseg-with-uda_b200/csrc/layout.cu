@@ -1,0 +1,120 @@
+// layout.cu — boundary conversions between the reference's NCHW fp32 / OIHW fp32 tensors and the
+// library's NHWC bf16 activations and packed bf16 weights.
+#include "common.cuh"
+
+namespace mcd {
+
+// one thread = one pixel x 8-channel group; lanes walk pixels so plane reads are coalesced.
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src,
+                                             __nv_bfloat16* __restrict__ dst, int N, int C, int HW,
+                                             int Cs) {
+  int groups = Cs >> 3;
+  int64_t total = (int64_t)N * HW * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i % ((int64_t)N * HW);
+    int g = (int)(i / ((int64_t)N * HW));
+    int n = (int)(pix / HW);
+    int hw = (int)(pix % HW);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = g * 8 + k;
+      f[k] = c < C ? src[((int64_t)n * C + c) * HW + hw] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(dst + pix * Cs + g * 8) = pack8(f);
+  }
+}
+
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src,
+                                             float* __restrict__ dst, int N, int C, int HW, int Cs) {
+  int groups = (C + 7) >> 3;
+  int64_t total = (int64_t)N * HW * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i % ((int64_t)N * HW);
+    int g = (int)(i / ((int64_t)N * HW));
+    int n = (int)(pix / HW);
+    int hw = (int)(pix % HW);
+    uint4 v = *reinterpret_cast<const uint4*>(src + pix * Cs + g * 8);
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int c = g * 8 + k;
+      if (c < C) dst[((int64_t)n * C + c) * HW + hw] = f[k];
+    }
+  }
+}
+
+// mode 0: dst[co][r*S+s][kc]            = w[co][kc][r][s]                 (kc < Cin, else 0)
+// mode 1: dst[ci][(R-1-r)*S+(S-1-s)][kc] = w[kc][ci][r][s]                 (kc < Cout, else 0)
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+                                   int Cout, int Cin, int R, int S, int mode, int rows, int kc_pad) {
+  int T = R * S;
+  int64_t total = (int64_t)rows * T * kc_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int kc = (int)(i % kc_pad);
+    int t = (int)((i / kc_pad) % T);
+    int row = (int)(i / ((int64_t)kc_pad * T));
+    float v = 0.f;
+    if (mode == 0) {
+      if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S];
+    } else {
+      if (kc < Cout) {
+        int r = R - 1 - t / S, s = S - 1 - t % S;
+        v = w[(((int64_t)kc * Cin + row) * R + r) * S + s];
+      }
+    }
+    dst[i] = f2bf(v);
+  }
+}
+
+}  // namespace mcd
+
+using namespace mcd;
+
+extern "C" {
+
+int mcd_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cs,
+                              int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nchw->nhwc: bad arguments");
+  MCD_REQUIRE(Cs >= C && Cs % 8 == 0, "nchw->nhwc: channel stride %d must be >= C=%d and %% 8 == 0",
+              Cs, C);
+  int64_t total = (int64_t)N * H * W * (Cs / 8);
+  int grid = (int)min64((total + 255) / 256, 148 * 16);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      src, (__nv_bfloat16*)dst, N, C, H * W, Cs);
+  return check_launch("nchw_f32_to_nhwc_bf16");
+}
+
+int mcd_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cs,
+                              int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nhwc->nchw: bad arguments");
+  MCD_REQUIRE(Cs >= C && Cs % 8 == 0, "nhwc->nchw: channel stride %d must be >= C=%d and %% 8 == 0",
+              Cs, C);
+  int64_t total = (int64_t)N * H * W * ((C + 7) / 8);
+  int grid = (int)min64((total + 255) / 256, 148 * 16);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, dst, N, C, H * W, Cs);
+  return check_launch("nhwc_bf16_to_nchw_f32");
+}
+
+int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int mode,
+                    int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(w_oihw && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, "pack_weight: bad arguments");
+  MCD_REQUIRE(mode == 0 || mode == 1, "pack_weight: mode must be 0 (fprop) or 1 (dgrad)");
+  int rows = mode ? Cin : Cout;
+  int kc_pad = round_up(mode ? Cout : Cin, 64);
+  int64_t total = (int64_t)rows * R * S * kc_pad;
+  int grid = (int)min64((total + 255) / 256, 148 * 16);
+  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
+                                                              R, S, mode, rows, kc_pad);
+  return check_launch("pack_weight");
+}
+
+}  // extern "C"

@@ -1,0 +1,434 @@
+// loss.cu — fused per-pixel losses on planar (NCHW) bf16 logits.
+//   CrossEntropyLoss2d = log_softmax(dim=1) + NLLLoss2d(weight, mean)        loss.py:7-13
+//   Diff2d             = mean |softmax(a) - softmax(b)|                      loss.py:93-100
+//   F.mse_loss (HHA regression)                              models/dilated_fcn.py:712,958
+//   sigmoid-average boundary head + bce2d       models/dilated_fcn.py:913-923, loss.py:131-138
+//   tester argmax + calc_entropy                      adapt_tester.py:104-124, util.py:44-48
+// One thread owns two horizontally adjacent pixels (4-byte bf16x2 loads, 128 B per warp and channel
+// plane); channel loops re-read the logits from L1/L2, so DRAM sees each logit once per kernel.
+#include "common.cuh"
+
+namespace mcd {
+
+__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// max and sum-exp over channels for a pixel pair
+__device__ __forceinline__ void softmax_stats(const __nv_bfloat16* base, int C, int64_t HW, float2* mx,
+                                              float2* se) {
+  float2 m = make_float2(-INFINITY, -INFINITY);
+  for (int c = 0; c < C; ++c) {
+    float2 v = ld2(base + c * HW);
+    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y);
+  }
+  float2 s = make_float2(0.f, 0.f);
+  for (int c = 0; c < C; ++c) {
+    float2 v = ld2(base + c * HW);
+    s.x += __expf(v.x - m.x); s.y += __expf(v.y - m.y);
+  }
+  *mx = m; *se = s;
+}
+
+struct LabelInfo { float w; int y; bool bad; };
+__device__ __forceinline__ LabelInfo read_label(const int64_t* target, int64_t idx, const float* weight,
+                                                int64_t ignore_index, int C) {
+  LabelInfo li;
+  int64_t y = target[idx];
+  li.bad = false; li.w = 0.f; li.y = -1;
+  if (y == ignore_index) return li;
+  if (y < 0 || y >= C) { li.bad = true; return li; }
+  li.y = (int)y;
+  li.w = weight ? weight[y] : 1.f;
+  return li;
+}
+
+// grid-stride over pixel pairs; npairs = N*H*W/2 (W even)
+__global__ void __launch_bounds__(256)
+ce2d_fwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+                const float* __restrict__ weight, int64_t ignore_index, float* __restrict__ acc, int C,
+                int64_t HW, int64_t npairs) {
+  __shared__ float red[32];
+  float lsum = 0.f, wsum = 0.f, bad = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const __nv_bfloat16* base = logits + n * C * HW + hw;
+    float2 m, s;
+    softmax_stats(base, C, HW, &m, &s);
+    LabelInfo l0 = read_label(target, pix, weight, ignore_index, C);
+    LabelInfo l1 = read_label(target, pix + 1, weight, ignore_index, C);
+    if (l0.y >= 0) { float xy = bf2f(base[l0.y * HW]); lsum += l0.w * (m.x + __logf(s.x) - xy); wsum += l0.w; }
+    if (l1.y >= 0) { float xy = bf2f(base[l1.y * HW + 1]); lsum += l1.w * (m.y + __logf(s.y) - xy); wsum += l1.w; }
+    bad += (l0.bad ? 1.f : 0.f) + (l1.bad ? 1.f : 0.f);
+  }
+  float r0 = block_sum(lsum, red), r1 = block_sum(wsum, red), r2 = block_sum(bad, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + 0, r0); atomicAdd(acc + 1, r1);
+    if (r2 != 0.f) atomicAdd(acc + 2, r2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce2d_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+                const float* __restrict__ weight, int64_t ignore_index, const float* __restrict__ acc,
+                const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dlogits, int C,
+                int64_t HW, int64_t npairs) {
+  const float wtot = acc[1];
+  const float coef = wtot > 0.f ? gscale[0] / wtot : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const __nv_bfloat16* base = logits + n * C * HW + hw;
+    __nv_bfloat16* dbase = dlogits + n * C * HW + hw;
+    float2 m, s;
+    softmax_stats(base, C, HW, &m, &s);
+    LabelInfo l0 = read_label(target, pix, weight, ignore_index, C);
+    LabelInfo l1 = read_label(target, pix + 1, weight, ignore_index, C);
+    const float k0 = coef * l0.w / s.x, k1 = coef * l1.w / s.y;
+    for (int c = 0; c < C; ++c) {
+      float2 v = ld2(base + c * HW);
+      float g0 = k0 * __expf(v.x - m.x) - (c == l0.y ? coef * l0.w : 0.f);
+      float g1 = k1 * __expf(v.y - m.y) - (c == l1.y ? coef * l1.w : 0.f);
+      st2(dbase + c * HW, g0, g1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+diff2d_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                  float* __restrict__ acc, int C, int64_t HW, int64_t npairs) {
+  __shared__ float red[32];
+  float lsum = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const __nv_bfloat16* pa = a + n * C * HW + hw;
+    const __nv_bfloat16* pb = b + n * C * HW + hw;
+    float2 ma, sa, mb, sb;
+    softmax_stats(pa, C, HW, &ma, &sa);
+    softmax_stats(pb, C, HW, &mb, &sb);
+    const float ia0 = 1.f / sa.x, ia1 = 1.f / sa.y, ib0 = 1.f / sb.x, ib1 = 1.f / sb.y;
+    for (int c = 0; c < C; ++c) {
+      float2 va = ld2(pa + c * HW), vb = ld2(pb + c * HW);
+      lsum += fabsf(__expf(va.x - ma.x) * ia0 - __expf(vb.x - mb.x) * ib0);
+      lsum += fabsf(__expf(va.y - ma.y) * ia1 - __expf(vb.y - mb.y) * ib1);
+    }
+  }
+  float r = block_sum(lsum, red);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(256)
+diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                  const float* __restrict__ gscale, __nv_bfloat16* __restrict__ da,
+                  __nv_bfloat16* __restrict__ db, float inv_numel, int C, int64_t HW, int64_t npairs) {
+  const float coef = gscale[0] * inv_numel;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const int64_t off = n * C * HW + hw;
+    const __nv_bfloat16* pa = a + off;
+    const __nv_bfloat16* pb = b + off;
+    float2 ma, sa, mb, sb;
+    softmax_stats(pa, C, HW, &ma, &sa);
+    softmax_stats(pb, C, HW, &mb, &sb);
+    const float ia0 = 1.f / sa.x, ia1 = 1.f / sa.y, ib0 = 1.f / sb.x, ib1 = 1.f / sb.y;
+    // dot products  sum_c sign_c * p_c  for both distributions
+    float da0 = 0.f, da1 = 0.f, db0 = 0.f, db1 = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float2 va = ld2(pa + c * HW), vb = ld2(pb + c * HW);
+      float pa0 = __expf(va.x - ma.x) * ia0, pb0 = __expf(vb.x - mb.x) * ib0;
+      float pa1 = __expf(va.y - ma.y) * ia1, pb1 = __expf(vb.y - mb.y) * ib1;
+      float s0 = sgn(pa0 - pb0), s1 = sgn(pa1 - pb1);
+      da0 += s0 * pa0; db0 += s0 * pb0; da1 += s1 * pa1; db1 += s1 * pb1;
+    }
+    for (int c = 0; c < C; ++c) {
+      float2 va = ld2(pa + c * HW), vb = ld2(pb + c * HW);
+      float pa0 = __expf(va.x - ma.x) * ia0, pb0 = __expf(vb.x - mb.x) * ib0;
+      float pa1 = __expf(va.y - ma.y) * ia1, pb1 = __expf(vb.y - mb.y) * ib1;
+      float s0 = sgn(pa0 - pb0), s1 = sgn(pa1 - pb1);
+      st2(da + off + c * HW, coef * pa0 * (s0 - da0), coef * pa1 * (s1 - da1));
+      st2(db + off + c * HW, coef * pb0 * (db0 - s0), coef * pb1 * (db1 - s1));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mse_fwd_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target,
+               float* __restrict__ acc, int64_t numel) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float d = bf2f(pred[i]) - target[i];
+    s = fmaf(d, d, s);
+  }
+  float r = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+__global__ void __launch_bounds__(256)
+mse_bwd_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target,
+               const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dpred, float inv_numel,
+               int64_t numel) {
+  const float coef = 2.f * gscale[0] * inv_numel;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dpred[i] = f2bf(coef * (bf2f(pred[i]) - target[i]));
+}
+
+__global__ void __launch_bounds__(256)
+sum_f32_kernel(const float* __restrict__ x, float* __restrict__ acc, int64_t numel) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x)
+    s += x[i];
+  float r = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+__device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + __expf(-v)); }
+
+__global__ void __launch_bounds__(256)
+sigmoid3_bce_fwd_kernel(const __nv_bfloat16* __restrict__ h1, const __nv_bfloat16* __restrict__ h2,
+                        const __nv_bfloat16* __restrict__ h3, const float* __restrict__ target,
+                        const float* __restrict__ tsum, float* __restrict__ acc,
+                        __nv_bfloat16* __restrict__ p_out, int64_t numel) {
+  __shared__ float red[32];
+  const float beta = 1.f - tsum[0] / (float)numel;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float p = (sigmoidf(bf2f(h1[i])) + sigmoidf(bf2f(h2[i])) + sigmoidf(bf2f(h3[i]))) * (1.f / 3.f);
+    if (p_out) p_out[i] = f2bf(p);
+    if (target) {
+      float t = target[i];
+      float w = 1.f - beta + (2.f * beta - 1.f) * t;
+      float lp = fmaxf(__logf(p), -100.f), lq = fmaxf(__logf(1.f - p), -100.f);
+      s -= w * (t * lp + (1.f - t) * lq);
+    }
+  }
+  if (acc) {
+    float r = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(acc, r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sigmoid3_bce_bwd_kernel(const __nv_bfloat16* __restrict__ h1, const __nv_bfloat16* __restrict__ h2,
+                        const __nv_bfloat16* __restrict__ h3, const float* __restrict__ target,
+                        const float* __restrict__ tsum, const float* __restrict__ gscale,
+                        __nv_bfloat16* __restrict__ dh1, __nv_bfloat16* __restrict__ dh2,
+                        __nv_bfloat16* __restrict__ dh3, int64_t numel) {
+  const float beta = 1.f - tsum[0] / (float)numel;
+  const float coef = gscale[0] / (float)numel;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float s1 = sigmoidf(bf2f(h1[i])), s2 = sigmoidf(bf2f(h2[i])), s3 = sigmoidf(bf2f(h3[i]));
+    float p = (s1 + s2 + s3) * (1.f / 3.f);
+    float t = target[i];
+    float w = 1.f - beta + (2.f * beta - 1.f) * t;
+    // F.binary_cross_entropy backward: w * (p - t) / max(p*(1-p), 1e-12)
+    float dp = coef * w * (p - t) / fmaxf(p * (1.f - p), 1e-12f) * (1.f / 3.f);
+    dh1[i] = f2bf(dp * s1 * (1.f - s1));
+    dh2[i] = f2bf(dp * s2 * (1.f - s2));
+    dh3[i] = f2bf(dp * s3 * (1.f - s3));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+argmax_entropy_kernel(const __nv_bfloat16* __restrict__ logits, int64_t* __restrict__ labels,
+                      float* __restrict__ acc, int C, int C_arg, int64_t HW, int64_t npairs) {
+  __shared__ float red[32];
+  float esum = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const __nv_bfloat16* base = logits + n * C * HW + hw;
+    float2 m, s;
+    softmax_stats(base, C, HW, &m, &s);
+    float b0 = -INFINITY, b1 = -INFINITY;
+    int a0 = 0, a1 = 0;
+    const float i0 = 1.f / s.x, i1 = 1.f / s.y;
+    for (int c = 0; c < C; ++c) {
+      float2 v = ld2(base + c * HW);
+      if (c < C_arg) {
+        if (v.x > b0) { b0 = v.x; a0 = c; }
+        if (v.y > b1) { b1 = v.y; a1 = c; }
+      }
+      float p0 = __expf(v.x - m.x) * i0, p1 = __expf(v.y - m.y) * i1;
+      esum += p0 * __logf(p0 + 1e-6f) + p1 * __logf(p1 + 1e-6f);
+    }
+    if (labels) { labels[pix] = a0; labels[pix + 1] = a1; }
+  }
+  if (acc) {
+    float r = block_sum(esum, red);
+    if (threadIdx.x == 0) atomicAdd(acc, r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                int64_t numel, float lr, float momentum, float wd, int first) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float d = fmaf(wd, p[i], g[i]);
+    float b = d;
+    if (momentum != 0.f) {
+      b = first ? d : fmaf(momentum, buf[i], d);
+      buf[i] = b;
+    }
+    p[i] -= lr * b;
+  }
+}
+
+static inline int grid_for(int64_t items) {
+  return (int)max64(1, min64((items + 255) / 256, 148 * 16));
+}
+
+}  // namespace mcd
+
+using namespace mcd;
+
+#define MCD_CHECK_PLANAR(name)                                                                   \
+  MCD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, name ": bad sizes");                             \
+  MCD_REQUIRE(W % 2 == 0, name ": W must be even (pixel-pair vectorisation), got %d", W)
+
+extern "C" {
+
+int mcd_ce2d_fwd(const void* logits, const int64_t* target, const float* weight,
+                 int64_t ignore_index, float* acc, int N, int C, int H, int W, int device,
+                 void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(logits && target && acc, "ce2d_fwd: null pointer");
+  MCD_CHECK_PLANAR("ce2d_fwd");
+  int64_t npairs = (int64_t)N * H * W / 2;
+  ce2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, C, (int64_t)H * W, npairs);
+  return check_launch("ce2d_fwd");
+}
+
+int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
+                 int64_t ignore_index, const float* acc, const float* gscale, void* dlogits, int N,
+                 int C, int H, int W, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(logits && target && acc && gscale && dlogits, "ce2d_bwd: null pointer");
+  MCD_CHECK_PLANAR("ce2d_bwd");
+  int64_t npairs = (int64_t)N * H * W / 2;
+  ce2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, gscale, (__nv_bfloat16*)dlogits,
+      C, (int64_t)H * W, npairs);
+  return check_launch("ce2d_bwd");
+}
+
+int mcd_diff2d_fwd(const void* a, const void* b, float* acc, int N, int C, int H, int W, int device,
+                   void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(a && b && acc, "diff2d_fwd: null pointer");
+  MCD_CHECK_PLANAR("diff2d_fwd");
+  int64_t npairs = (int64_t)N * H * W / 2;
+  diff2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, C, (int64_t)H * W, npairs);
+  return check_launch("diff2d_fwd");
+}
+
+int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, void* da, void* db, int N,
+                   int C, int H, int W, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(a && b && gscale && da && db, "diff2d_bwd: null pointer");
+  MCD_CHECK_PLANAR("diff2d_bwd");
+  int64_t npairs = (int64_t)N * H * W / 2;
+  float inv = (float)(1.0 / ((double)N * C * H * W));
+  diff2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (__nv_bfloat16*)da, (__nv_bfloat16*)db,
+      inv, C, (int64_t)H * W, npairs);
+  return check_launch("diff2d_bwd");
+}
+
+int mcd_mse_fwd(const void* pred, const float* target, float* acc, int64_t numel, int device,
+                void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(pred && target && acc && numel > 0, "mse_fwd: bad arguments");
+  mse_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)pred, target,
+                                                                     acc, numel);
+  return check_launch("mse_fwd");
+}
+
+int mcd_mse_bwd(const void* pred, const float* target, const float* gscale, void* dpred,
+                int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(pred && target && gscale && dpred && numel > 0, "mse_bwd: bad arguments");
+  mse_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)pred, target, gscale, (__nv_bfloat16*)dpred, (float)(1.0 / (double)numel),
+      numel);
+  return check_launch("mse_bwd");
+}
+
+int mcd_sum_f32(const float* x, float* acc, int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && acc && numel > 0, "sum_f32: bad arguments");
+  sum_f32_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x, acc, numel);
+  return check_launch("sum_f32");
+}
+
+int mcd_sigmoid3_bce_fwd(const void* h1, const void* h2, const void* h3, const float* target,
+                         const float* tsum, float* acc, void* p_out, int64_t numel, int device,
+                         void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(h1 && h2 && h3 && numel > 0, "sigmoid3_bce_fwd: bad arguments");
+  MCD_REQUIRE(!target || (tsum && acc), "sigmoid3_bce_fwd: target needs tsum and acc");
+  MCD_REQUIRE(target || p_out, "sigmoid3_bce_fwd: nothing to compute");
+  sigmoid3_bce_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)h1, (const __nv_bfloat16*)h2, (const __nv_bfloat16*)h3, target, tsum,
+      target ? acc : nullptr, (__nv_bfloat16*)p_out, numel);
+  return check_launch("sigmoid3_bce_fwd");
+}
+
+int mcd_sigmoid3_bce_bwd(const void* h1, const void* h2, const void* h3, const float* target,
+                         const float* tsum, const float* gscale, void* dh1, void* dh2, void* dh3,
+                         int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(h1 && h2 && h3 && target && tsum && gscale && dh1 && dh2 && dh3 && numel > 0,
+              "sigmoid3_bce_bwd: bad arguments");
+  sigmoid3_bce_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)h1, (const __nv_bfloat16*)h2, (const __nv_bfloat16*)h3, target, tsum, gscale,
+      (__nv_bfloat16*)dh1, (__nv_bfloat16*)dh2, (__nv_bfloat16*)dh3, numel);
+  return check_launch("sigmoid3_bce_bwd");
+}
+
+int mcd_argmax_entropy(const void* logits, int64_t* labels, float* acc, int N, int C, int C_arg,
+                       int H, int W, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(logits && (labels || acc), "argmax_entropy: null pointer");
+  MCD_CHECK_PLANAR("argmax_entropy");
+  MCD_REQUIRE(C_arg >= 1 && C_arg <= C, "argmax_entropy: C_arg=%d out of range", C_arg);
+  int64_t npairs = (int64_t)N * H * W / 2;
+  argmax_entropy_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)logits, labels, acc, C, C_arg, (int64_t)H * W, npairs);
+  return check_launch("argmax_entropy");
+}
+
+int mcd_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t numel, float lr,
+                 float momentum, float weight_decay, int first_step, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(param && grad && numel > 0, "sgd_step: bad arguments");
+  MCD_REQUIRE(momentum == 0.f || momentum_buf, "sgd_step: momentum needs a buffer");
+  sgd_step_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, numel,
+                                                                      lr, momentum, weight_decay,
+                                                                      first_step);
+  return check_launch("sgd_step");
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""Per-pixel losses of the MCD step on libmcd_sm100 (drop-in for the reference's loss.py).
+
+  CrossEntropyLoss2d(weight, size_average, ignore_index)(inputs[B,C,H,W], targets[B,H,W] int64)   loss.py:7-13
+  Diff2d()(inputs1, inputs2) = mean |softmax - softmax|                                          loss.py:93-100
+  bce2d(input, target)   class-balanced binary cross entropy                                     loss.py:131-138
+  get_prob_distance_criterion(name, n_class)                                                     loss.py:192-210
+
+Each criterion is ONE fused forward kernel and ONE fused backward kernel over the full-resolution
+logits (softmax is never materialised).  Other divergences of the reference (jsd, symkl, ...) are not on
+the default `--d_loss diff` path (argmyparse.py:131) and raise NotImplementedError.
+Extra entry points used by the multitask decoders: mse_loss, sigmoid3_mean, sigmoid3_bce2d.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from mcd_b200 import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+_CHECK_LABELS = os.environ.get("MCD_CHECK_LABELS", "0") == "1"
+
+
+def _logits(x):
+    """full-resolution predictions are bf16 NCHW-contiguous; convert anything else (differentiably)."""
+    if x.dtype != BF16:
+        x = x.to(BF16)
+    return x.contiguous()
+
+
+def _gscale(go):
+    return go.reshape(1).to(F32).contiguous()
+
+
+class _CE2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, weight, ignore_index, size_average):
+        acc = ops.ce2d_fwd(logits, target, weight, ignore_index)
+        if _CHECK_LABELS and float(acc[2]) != 0:
+            raise IndexError("CrossEntropyLoss2d: %d target labels outside [0, %d) and != ignore_index" %
+                             (int(acc[2]), logits.shape[1]))
+        ctx.save_for_backward(logits, target, weight, acc)
+        ctx.ignore_index, ctx.size_average = ignore_index, size_average
+        return acc[0] / acc[1] if size_average else acc[0].clone()
+
+    @staticmethod
+    def backward(ctx, go):
+        logits, target, weight, acc = ctx.saved_tensors
+        if not ctx.size_average:
+            acc = torch.ones_like(acc)
+        d = ops.ce2d_bwd(logits, target, weight, ctx.ignore_index, acc, _gscale(go))
+        return d, None, None, None, None
+
+
+class CrossEntropyLoss2d(nn.Module):
+    def __init__(self, weight=None, size_average=True, ignore_index=-100):
+        super().__init__()
+        self.register_buffer("weight", None if weight is None else weight.detach().to(F32).contiguous())
+        self.size_average = size_average
+        self.ignore_index = ignore_index
+
+    def forward(self, inputs, targets):
+        logits = _logits(inputs)
+        if targets.dtype != torch.int64:
+            targets = targets.long()
+        w = self.weight
+        if w is not None and w.device != logits.device:
+            w = w.to(logits.device)
+        return _CE2dFn.apply(logits, targets.contiguous(), w, self.ignore_index, self.size_average)
+
+
+class _Diff2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        acc = ops.diff2d_fwd(a, b)
+        ctx.save_for_backward(a, b)
+        return acc[0] / float(a.numel())
+
+    @staticmethod
+    def backward(ctx, go):
+        a, b = ctx.saved_tensors
+        da, db = ops.diff2d_bwd(a, b, _gscale(go))
+        return da, db
+
+
+class Diff2d(nn.Module):
+    def __init__(self, weight=None, size_average=True):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, inputs1, inputs2):
+        return _Diff2dFn.apply(_logits(inputs1), _logits(inputs2))
+
+
+class _MSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        acc = ops.mse_fwd(pred, target)
+        ctx.save_for_backward(pred, target)
+        return acc[0] / float(pred.numel())
+
+    @staticmethod
+    def backward(ctx, go):
+        pred, target = ctx.saved_tensors
+        return ops.mse_bwd(pred, target, _gscale(go)), None
+
+
+def mse_loss(pred, target):
+    """F.mse_loss(pred, target) for the HHA regression head (reference models/dilated_fcn.py:712,958)."""
+    return _MSEFn.apply(_logits(pred), target.to(F32).contiguous())
+
+
+class _Sigmoid3BCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h1, h2, h3, target):
+        tsum = ops.sum_f32(target)
+        acc, _ = ops.sigmoid3_bce_fwd(h1, h2, h3, target, tsum)
+        ctx.save_for_backward(h1, h2, h3, target, tsum)
+        return acc[0] / float(h1.numel())
+
+    @staticmethod
+    def backward(ctx, go):
+        h1, h2, h3, target, tsum = ctx.saved_tensors
+        d1, d2, d3 = ops.sigmoid3_bce_bwd(h1, h2, h3, target, tsum, _gscale(go))
+        return d1, d2, d3, None
+
+
+def sigmoid3_bce2d(h1, h2, h3, target):
+    """bce2d((sigmoid(h1)+sigmoid(h2)+sigmoid(h3))/3, target) fused (reference models/dilated_fcn.py:913-923,
+    1002-1004 + loss.py:131-138)."""
+    assert not target.requires_grad, "nn criterions don't compute the gradient w.r.t. targets"
+    return _Sigmoid3BCEFn.apply(_logits(h1), _logits(h2), _logits(h3), target.to(F32).contiguous())
+
+
+def sigmoid3_mean(h1, h2, h3):
+    """(sigmoid(h1)+sigmoid(h2)+sigmoid(h3))/3 as a bf16 probability map (inference / testers)."""
+    with torch.no_grad():
+        _, p = ops.sigmoid3_bce_fwd(_logits(h1), _logits(h2), _logits(h3), want_p=True)
+    return p
+
+
+def bce2d(input, target):
+    """Class-balanced BCE on a probability map (reference loss.py:131-138).  The MCD decoders call the fused
+    `sigmoid3_bce2d` instead; a bare probability input has no kernel on the hot path."""
+    raise NotImplementedError("use loss.sigmoid3_bce2d(h1, h2, h3, target): the boundary head fuses the "
+                              "sigmoid average with bce2d")
+
+
+def get_prob_distance_criterion(criterion_name, n_class=None):
+    if criterion_name == 'diff':
+        return Diff2d()
+    if criterion_name in ("jsd", "symkl", "nmlsymkl", "mysymkl", "spatial_jsd", "mis_symkl"):
+        raise NotImplementedError("d_loss=%s is outside the libmcd_sm100 hot-path scope (default is 'diff')"
+                                  % criterion_name)
+    raise NotImplementedError()

@@ -1,0 +1,237 @@
+"""autograd Functions and nn.Module building blocks over libmcd_sm100.
+
+The modules subclass the stock torch containers (`nn.Conv2d`, `nn.BatchNorm2d`, `nn.ConvTranspose2d`)
+only so that parameters, buffers, initialisation and state_dict keys are byte-compatible with the
+reference's checkpoints (adapt_trainer.py:232-245, adapt_tester.py:79-83); their `forward` never calls
+a stock torch kernel - it launches the library's kernels through `ops`.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _as_nhwc_grad(dy):
+    """Gradients arriving from autograd for an nhwc activation: make them nhwc bf16 again."""
+    if ops.is_nhwc(dy):
+        return dy
+    if dy.dtype == BF16 and dy.shape[1] % 8 == 0:
+        return dy.contiguous(memory_format=torch.channels_last)
+    return ops.to_nhwc(dy)
+
+
+# ---------------------------------------------------------------------------------------------
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod, planar, want_stats):
+        g = mod.geom(x.shape)
+        y, stats = ops.conv_fprop(x, mod.packed(0), bias, g, planar=planar, want_stats=want_stats)
+        ctx.mod, ctx.g, ctx.planar = mod, g, planar
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x)
+        if stats is None:
+            stats = torch.empty(0, dtype=F32, device=x.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        (x,) = ctx.saved_tensors
+        g, mod = ctx.g, ctx.mod
+        dy = ops.to_nhwc(dy) if ctx.planar else _as_nhwc_grad(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv_dgrad(dy, mod.packed(1), g)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.conv_wgrad(x, dy, g, want_dbias=ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw, db, None, None, None
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d parameter container whose forward is the library's implicit-GEMM convolution.
+
+    Input / output are bf16 channels_last activations (`planar_out=True`: fp32 NCHW score map).
+    """
+
+    def __init__(self, *args, planar_out=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert self.groups == 1 and self.padding_mode == "zeros"
+        assert self.kernel_size[0] == self.kernel_size[1] and self.stride[0] == self.stride[1]
+        assert self.dilation[0] == self.dilation[1] and self.padding[0] == self.padding[1]
+        self.planar_out = planar_out
+        self._packs = {}
+        self._geoms = {}
+
+    def geom(self, x_shape):
+        key = tuple(x_shape)
+        g = self._geoms.get(key)
+        if g is None:
+            g = ops.conv_geom(x_shape, self.in_channels, self.out_channels, self.kernel_size[0],
+                              self.kernel_size[1], self.stride[0], self.dilation[0], self.padding[0])
+            self._geoms[key] = g
+        return g
+
+    def packed(self, mode):
+        """bf16 packed shadow of the fp32 master weight, refreshed when the parameter changes."""
+        w = self.weight
+        tag = (w._version, w.data_ptr())
+        hit = self._packs.get(mode)
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.pack_weight(w, mode))
+            self._packs[mode] = hit
+        return hit[1]
+
+    def conv_raw(self, x, want_stats=False):
+        x = ops.to_nhwc(x)
+        if x.shape[1] < self.in_channels:
+            raise ValueError("Conv2d expected >= %d input channels, got %d" % (self.in_channels, x.shape[1]))
+        y, stats = _ConvFn.apply(x, self.weight, self.bias, self, self.planar_out, want_stats)
+        return y, (stats if want_stats else None)
+
+    def forward(self, x):
+        return self.conv_raw(x)[0]
+
+
+# ---------------------------------------------------------------------------------------------
+class _BNActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, res, res_stats, res_gamma, res_beta, bn, res_bn, relu):
+        n, c, h, w = y.shape
+        count = n * h * w
+        training = bn.training
+        aff = ops.bn_finalize(stats if training else None, count, gamma, beta, bn.running_mean,
+                              bn.running_var, bn.momentum, bn.eps, training,
+                              bn.num_batches_tracked if training else None)
+        res_aff = None
+        if res_bn is not None:
+            res_aff = ops.bn_finalize(res_stats if res_bn.training else None, count, res_gamma, res_beta,
+                                      res_bn.running_mean, res_bn.running_var, res_bn.momentum,
+                                      res_bn.eps, res_bn.training,
+                                      res_bn.num_batches_tracked if res_bn.training else None)
+        z = ops.bn_apply(y, aff, res, res_aff, relu)
+        ctx.relu, ctx.training = relu, training
+        ctx.res_training = res_bn.training if res_bn is not None else False
+        ctx.has_res, ctx.has_res_bn = res is not None, res_bn is not None
+        ctx.save_for_backward(y, z, gamma, aff, res if res_bn is not None else None, res_gamma, res_aff)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, z, gamma, aff, res, res_gamma, res_aff = ctx.saved_tensors
+        dz = _as_nhwc_grad(dz)
+        want_dres = ctx.has_res and ctx.needs_input_grad[4]
+        dy, dgamma, dbeta, dres, dres_gamma, dres_beta = ops.bn_bwd(
+            dz, z, y, gamma, aff, ctx.training, ctx.relu, res=res, res_gamma=res_gamma, res_aff=res_aff,
+            res_training=ctx.res_training, want_dres=want_dres)
+        if not want_dres:
+            dres = None
+        return dy, None, dgamma, dbeta, dres, None, dres_gamma, dres_beta, None, None, None
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d container (eps/momentum/affine/running stats as in models/drn.py:34,129,202).
+
+    `fused(y, stats, ...)` = normalise (+ residual) (+ ReLU) in one pass; statistics come from the
+    producing convolution's epilogue.  `.training = False` (eval() or fix_batchnorm_when_training,
+    models/model_util.py:305-310) switches to the running statistics.
+    """
+
+    def fused(self, y, stats, relu=True, res=None, res_stats=None, res_bn=None):
+        assert self.affine and self.track_running_stats
+        if res_bn is not None:
+            return _BNActFn.apply(y, stats, self.weight, self.bias, res, res_stats, res_bn.weight,
+                                  res_bn.bias, self, res_bn, relu)
+        return _BNActFn.apply(y, stats, self.weight, self.bias, res, None, None, None, self, None, relu)
+
+    def forward(self, x):
+        x = ops.to_nhwc(x)
+        stats = ops.bn_stats(x, self.num_features) if self.training else None
+        return self.fused(x, stats, relu=False)
+
+
+def conv_bn_act(conv, bn, x, relu=True, res=None, res_conv=None, res_bn=None):
+    """z = act(bn(conv(x)) + residual); residual = res (identity) or res_bn(res_conv(x_res))."""
+    y, stats = conv.conv_raw(x, want_stats=bn.training)
+    if res_conv is not None:
+        ry, rstats = res_conv.conv_raw(res, want_stats=res_bn.training)
+        return bn.fused(y, stats, relu=relu, res=ry, res_stats=rstats, res_bn=res_bn)
+    return bn.fused(y, stats, relu=relu, res=res)
+
+
+class ConvBNReLU(nn.Sequential):
+    """`nn.Sequential(conv, bn, relu)` of models/drn.py:126-131,195-205 executed as one fused unit."""
+
+    def forward(self, x):
+        mods = list(self.children())
+        i = 0
+        while i < len(mods):
+            conv, bn = mods[i], mods[i + 1]
+            x = conv_bn_act(conv, bn, x, relu=True)
+            i += 3
+        return x
+
+
+# ---------------------------------------------------------------------------------------------
+class _Deconv16s8Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, x2, w2):
+        out = ops.deconv16s8_fwd(x, w, x2, w2)
+        ctx.save_for_backward(x, w, x2, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, x2, w2 = ctx.saved_tensors
+        dout = dout.contiguous()
+        need = ctx.needs_input_grad
+        dx = dw = dx2 = dw2 = None
+        if need[0] or need[1]:
+            dx, dw = ops.deconv16s8_bwd(dout, x, w, want_dx=need[0], want_dw=need[1])
+        if x2 is not None and (need[2] or need[3]):
+            dx2, dw2 = ops.deconv16s8_bwd(dout, x2, w2, want_dx=need[2], want_dw=need[3])
+        return dx, dw, dx2, dw2
+
+
+def _planar_f32(x):
+    if x.dtype != F32:
+        x = x.float()
+    return x.contiguous()
+
+
+class DepthwiseDeconv16s8(nn.ConvTranspose2d):
+    """ConvTranspose2d(C, C, 16, stride=8, padding=4, groups=C, bias=False): the *learned* upsampling of
+    the MCD heads (models/dilated_fcn.py:357-360).  fp32 planar score map in, bf16 planar logits out."""
+
+    def __init__(self, n_class):
+        super().__init__(n_class, n_class, 16, stride=8, padding=4, output_padding=0, groups=n_class,
+                         bias=False)
+
+    def forward(self, x, x2=None, other=None):
+        x = _planar_f32(x)
+        if x2 is None:
+            return _Deconv16s8Fn.apply(x, self.weight, None, None)
+        return _Deconv16s8Fn.apply(x, self.weight, _planar_f32(x2), other.weight)
+
+
+class _BilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, out_f32):
+        ctx.s = s
+        return ops.bilinear_up_fwd(x, s, out_f32)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return ops.bilinear_up_bwd(dout.contiguous(), ctx.s), None, None
+
+
+class BilinearUpsample(nn.Module):
+    """nn.Upsample(scale_factor=s, mode='bilinear') (align_corners=False), models/dilated_fcn.py:676,817-819."""
+
+    def __init__(self, scale_factor, out_f32=False):
+        super().__init__()
+        self.scale_factor, self.out_f32 = int(scale_factor), out_f32
+
+    def forward(self, x):
+        return _BilinearFn.apply(_planar_f32(x), self.scale_factor, self.out_f32)

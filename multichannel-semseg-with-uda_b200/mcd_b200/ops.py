@@ -1,0 +1,315 @@
+"""Tensor-level wrappers over the C-ABI: validate, allocate outputs with torch, pass raw pointers.
+
+PyTorch is plumbing here (device memory, streams); every computation is a libmcd_sm100 kernel.
+Activations are bf16 NHWC buffers exposed as logical-NCHW `channels_last` tensors; score maps and
+full-resolution logits are ordinary contiguous NCHW ("planar") tensors.
+"""
+import ctypes
+
+import torch
+
+from . import abi
+from .abi import ConvGeom
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+_algo = abi.ALGO_AUTO
+
+
+def set_conv_algo(algo):
+    """ALGO_AUTO (tcgen05 where supported), ALGO_DIRECT (CUDA-core cross-check) or ALGO_UMMA."""
+    global _algo
+    prev, _algo = _algo, int(algo)
+    return prev
+
+
+def get_conv_algo():
+    return _algo
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise abi.McdError("libmcd_sm100 ops need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+# ---- layout ------------------------------------------------------------------------------------
+def is_nhwc(t):
+    return (t.dim() == 4 and t.dtype == BF16 and t.shape[1] % 8 == 0
+            and t.permute(0, 2, 3, 1).is_contiguous())
+
+
+def nhwc_empty(n, c, h, w, device):
+    """bf16 [n,h,w,c] buffer viewed as logical NCHW (channels_last strides)."""
+    return torch.empty((n, h, w, c), dtype=BF16, device=device).permute(0, 3, 1, 2)
+
+
+def to_nhwc(x):
+    """NCHW fp32 (any C) -> channels_last bf16 with C padded to a multiple of 8 (zero fill)."""
+    if is_nhwc(x):
+        return x
+    if x.dtype != F32:
+        x = x.float()
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    cs = round_up(c, 8)
+    out = nhwc_empty(n, cs, h, w, x.device)
+    abi.check(abi.lib().mcd_nchw_f32_to_nhwc_bf16(_p(x), _p(out), n, c, h, w, cs, _dev(x), _stream(x)),
+              "nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def to_nchw_f32(x, c=None):
+    """channels_last bf16 -> contiguous NCHW fp32 (first c channels)."""
+    assert is_nhwc(x)
+    n, cs, h, w = x.shape
+    c = cs if c is None else c
+    out = torch.empty((n, c, h, w), dtype=F32, device=x.device)
+    abi.check(abi.lib().mcd_nhwc_bf16_to_nchw_f32(_p(x), _p(out), n, c, h, w, cs, _dev(x), _stream(x)),
+              "nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def pack_weight(w, mode):
+    """fp32 OIHW -> packed bf16 [rows][R*S][kc_pad] (mode 0 fprop / 1 dgrad)."""
+    w = w.detach()
+    assert w.dtype == F32 and w.is_contiguous()
+    co, ci, r, s = w.shape
+    rows, kc = (ci, co) if mode else (co, ci)
+    out = torch.empty((rows, r * s, round_up(kc, 64)), dtype=BF16, device=w.device)
+    abi.check(abi.lib().mcd_pack_weight(_p(w), _p(out), co, ci, r, s, mode, _dev(w), _stream(w)),
+              "pack_weight")
+    return out
+
+
+# ---- convolution -------------------------------------------------------------------------------
+def conv_geom(x_shape, cin, cout, r, s, stride, dil, pad, cout_s=None):
+    n, cin_s, h, w = x_shape
+    ho = (h + 2 * pad - dil * (r - 1) - 1) // stride + 1
+    wo = (w + 2 * pad - dil * (s - 1) - 1) // stride + 1
+    return ConvGeom(n, h, w, cin, cout, cin_s, cout_s if cout_s else round_up(cout, 8), r, s, stride,
+                    dil, pad, ho, wo)
+
+
+def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
+    """returns (y, stats) - y nhwc bf16 [N,Cout_s,Ho,Wo] or planar fp32 [N,Cout,Ho,Wo]."""
+    assert is_nhwc(x) and x.shape[1] == g.Cin_s
+    if planar:
+        y = torch.empty((g.N, g.Cout, g.Ho, g.Wo), dtype=F32, device=x.device)
+    else:
+        y = nhwc_empty(g.N, g.Cout_s, g.Ho, g.Wo, x.device)
+    stats = torch.zeros(2 * g.Cout, dtype=F32, device=x.device) if want_stats else None
+    abi.check(abi.lib().mcd_conv2d_fprop(
+        _p(x), _p(w_packed), _p(bias), _p(y), abi.OUT_PLANAR_F32 if planar else abi.OUT_NHWC_BF16,
+        _p(stats), ctypes.byref(g), _algo if algo is None else algo, _dev(x), _stream(x)), "conv2d_fprop")
+    return y, stats
+
+
+def conv_dgrad(dy, w_packed_dgrad, g, algo=None):
+    assert is_nhwc(dy) and dy.shape[1] == g.Cout_s
+    dx = nhwc_empty(g.N, g.Cin_s, g.H, g.W, dy.device)
+    abi.check(abi.lib().mcd_conv2d_dgrad(_p(dy), _p(w_packed_dgrad), _p(dx), ctypes.byref(g),
+                                         _algo if algo is None else algo, _dev(dy), _stream(dy)),
+              "conv2d_dgrad")
+    return dx
+
+
+def conv_wgrad(x, dy, g, want_dbias=False, algo=None):
+    assert is_nhwc(x) and is_nhwc(dy)
+    algo = _algo if algo is None else algo
+    dw = torch.empty((g.Cout, g.Cin, g.R, g.S), dtype=F32, device=x.device)
+    db = torch.empty(g.Cout, dtype=F32, device=x.device) if want_dbias else None
+    nbytes = int(abi.lib().mcd_conv2d_wgrad_workspace(ctypes.byref(g), algo))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    abi.check(abi.lib().mcd_conv2d_wgrad(_p(x), _p(dy), _p(dw), _p(db), _p(ws), nbytes,
+                                         ctypes.byref(g), algo, _dev(x), _stream(x)), "conv2d_wgrad")
+    return dw, db
+
+
+# ---- batch norm --------------------------------------------------------------------------------
+def bn_stats(y, c):
+    n, cs, h, w = y.shape
+    stats = torch.zeros(2 * c, dtype=F32, device=y.device)
+    abi.check(abi.lib().mcd_bn_stats(_p(y), _p(stats), n * h * w, c, cs, _dev(y), _stream(y)), "bn_stats")
+    return stats
+
+
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, training,
+                num_batches_tracked=None):
+    c = gamma.numel()
+    out = torch.empty((4, c), dtype=F32, device=gamma.device)  # scale, shift, mean, rstd
+    abi.check(abi.lib().mcd_bn_finalize(
+        _p(stats), count, _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(momentum),
+        float(eps), int(training), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+        _p(num_batches_tracked), c, _dev(gamma),
+        _stream(gamma)), "bn_finalize")
+    return out
+
+
+def bn_apply(y, aff, res, res_aff, relu):
+    n, c, h, w = y.shape
+    z = nhwc_empty(n, c, h, w, y.device)
+    abi.check(abi.lib().mcd_bn_apply(
+        _p(y), _p(aff[0]), _p(aff[1]), _p(res), _p(res_aff[0]) if res_aff is not None else None,
+        _p(res_aff[1]) if res_aff is not None else None, int(relu), _p(z), n * h * w, c, c, _dev(y),
+        _stream(y)), "bn_apply")
+    return z
+
+
+def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_aff=None,
+           res_training=False, want_dres=False):
+    """returns dy, dgamma, dbeta, dres, dres_gamma, dres_beta"""
+    n, c, h, w = y.shape
+    count = n * h * w
+    dev, st = _dev(y), _stream(y)
+    has_res_bn = res_gamma is not None
+    sums = torch.zeros(3 * c, dtype=F32, device=y.device)
+    abi.check(abi.lib().mcd_bn_bwd_reduce(
+        _p(dz), _p(z), _p(y), _p(aff[2]), _p(aff[3]), _p(res) if has_res_bn else None,
+        _p(res_aff[2]) if has_res_bn else None, _p(res_aff[3]) if has_res_bn else None, int(relu),
+        _p(sums), count, c, c, dev, st), "bn_bwd_reduce")
+    dy = nhwc_empty(n, c, h, w, y.device)
+    dgb = torch.empty((4, c), dtype=F32, device=y.device)
+    dres = nhwc_empty(n, c, h, w, y.device) if (want_dres or has_res_bn) else None
+    abi.check(abi.lib().mcd_bn_bwd_apply(
+        _p(dz), _p(z), _p(y), _p(gamma), _p(aff[2]), _p(aff[3]), _p(sums), int(training), int(relu),
+        _p(dy), _p(dgb[0]), _p(dgb[1]), _p(res) if has_res_bn else None,
+        _p(res_gamma) if has_res_bn else None, _p(res_aff[2]) if has_res_bn else None,
+        _p(res_aff[3]) if has_res_bn else None, int(res_training), _p(dres),
+        _p(dgb[2]) if has_res_bn else None, _p(dgb[3]) if has_res_bn else None, count, c, c, dev, st),
+        "bn_bwd_apply")
+    return dy, dgb[0], dgb[1], dres, (dgb[2] if has_res_bn else None), (dgb[3] if has_res_bn else None)
+
+
+# ---- heads -------------------------------------------------------------------------------------
+def deconv16s8_fwd(x, w, x2=None, w2=None):
+    n, c, h, wd = x.shape
+    out = torch.empty((n, c, 8 * h, 8 * wd), dtype=BF16, device=x.device)
+    abi.check(abi.lib().mcd_deconv16s8_fwd(_p(x), _p(w), _p(x2), _p(w2), _p(out), n, c, h, wd, _dev(x),
+                                           _stream(x)), "deconv16s8_fwd")
+    return out
+
+
+def deconv16s8_bwd(dout, x, w, want_dx=True, want_dw=True):
+    n, c, h, wd = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.empty_like(w) if want_dw else None
+    abi.check(abi.lib().mcd_deconv16s8_bwd(_p(dout), _p(x), _p(w), _p(dx), _p(dw), n, c, h, wd, _dev(x),
+                                           _stream(x)), "deconv16s8_bwd")
+    return dx, dw
+
+
+def bilinear_up_fwd(x, s, out_f32=False):
+    n, c, h, wd = x.shape
+    out = torch.empty((n, c, s * h, s * wd), dtype=F32 if out_f32 else BF16, device=x.device)
+    abi.check(abi.lib().mcd_bilinear_up_fwd(_p(x), _p(out), int(out_f32), n, c, h, wd, s, _dev(x),
+                                            _stream(x)), "bilinear_up_fwd")
+    return out
+
+
+def bilinear_up_bwd(dout, s):
+    n, c, hh, ww = dout.shape
+    dx = torch.empty((n, c, hh // s, ww // s), dtype=F32, device=dout.device)
+    abi.check(abi.lib().mcd_bilinear_up_bwd(_p(dout), int(dout.dtype == F32), _p(dx), n, c, hh // s,
+                                            ww // s, s, _dev(dout), _stream(dout)), "bilinear_up_bwd")
+    return dx
+
+
+# ---- losses ------------------------------------------------------------------------------------
+def ce2d_fwd(logits, target, weight, ignore_index):
+    n, c, h, w = logits.shape
+    acc = torch.zeros(4, dtype=F32, device=logits.device)
+    abi.check(abi.lib().mcd_ce2d_fwd(_p(logits), _p(target), _p(weight), int(ignore_index), _p(acc), n, c,
+                                     h, w, _dev(logits), _stream(logits)), "ce2d_fwd")
+    return acc
+
+
+def ce2d_bwd(logits, target, weight, ignore_index, acc, gscale):
+    n, c, h, w = logits.shape
+    d = torch.empty_like(logits)
+    abi.check(abi.lib().mcd_ce2d_bwd(_p(logits), _p(target), _p(weight), int(ignore_index), _p(acc),
+                                     _p(gscale), _p(d), n, c, h, w, _dev(logits), _stream(logits)),
+              "ce2d_bwd")
+    return d
+
+
+def diff2d_fwd(a, b):
+    n, c, h, w = a.shape
+    acc = torch.zeros(1, dtype=F32, device=a.device)
+    abi.check(abi.lib().mcd_diff2d_fwd(_p(a), _p(b), _p(acc), n, c, h, w, _dev(a), _stream(a)), "diff2d_fwd")
+    return acc
+
+
+def diff2d_bwd(a, b, gscale):
+    n, c, h, w = a.shape
+    da, db = torch.empty_like(a), torch.empty_like(b)
+    abi.check(abi.lib().mcd_diff2d_bwd(_p(a), _p(b), _p(gscale), _p(da), _p(db), n, c, h, w, _dev(a),
+                                       _stream(a)), "diff2d_bwd")
+    return da, db
+
+
+def mse_fwd(pred, target):
+    acc = torch.zeros(1, dtype=F32, device=pred.device)
+    abi.check(abi.lib().mcd_mse_fwd(_p(pred), _p(target), _p(acc), pred.numel(), _dev(pred), _stream(pred)),
+              "mse_fwd")
+    return acc
+
+
+def mse_bwd(pred, target, gscale):
+    d = torch.empty_like(pred)
+    abi.check(abi.lib().mcd_mse_bwd(_p(pred), _p(target), _p(gscale), _p(d), pred.numel(), _dev(pred),
+                                    _stream(pred)), "mse_bwd")
+    return d
+
+
+def sum_f32(x):
+    acc = torch.zeros(1, dtype=F32, device=x.device)
+    abi.check(abi.lib().mcd_sum_f32(_p(x), _p(acc), x.numel(), _dev(x), _stream(x)), "sum_f32")
+    return acc
+
+
+def sigmoid3_bce_fwd(h1, h2, h3, target=None, tsum=None, want_p=False):
+    acc = torch.zeros(1, dtype=F32, device=h1.device) if target is not None else None
+    p = torch.empty_like(h1) if want_p else None
+    abi.check(abi.lib().mcd_sigmoid3_bce_fwd(_p(h1), _p(h2), _p(h3), _p(target), _p(tsum), _p(acc), _p(p),
+                                             h1.numel(), _dev(h1), _stream(h1)), "sigmoid3_bce_fwd")
+    return acc, p
+
+
+def sigmoid3_bce_bwd(h1, h2, h3, target, tsum, gscale):
+    d1, d2, d3 = torch.empty_like(h1), torch.empty_like(h2), torch.empty_like(h3)
+    abi.check(abi.lib().mcd_sigmoid3_bce_bwd(_p(h1), _p(h2), _p(h3), _p(target), _p(tsum), _p(gscale),
+                                             _p(d1), _p(d2), _p(d3), h1.numel(), _dev(h1), _stream(h1)),
+              "sigmoid3_bce_bwd")
+    return d1, d2, d3
+
+
+def argmax_entropy(logits, c_arg=None, want_labels=True, want_entropy=True):
+    """labels int64 [N,H,W] = argmax over channels [0,c_arg); entropy = -mean(p*log(p+1e-6))."""
+    n, c, h, w = logits.shape
+    c_arg = c if c_arg is None else c_arg
+    labels = torch.empty((n, h, w), dtype=torch.int64, device=logits.device) if want_labels else None
+    acc = torch.zeros(1, dtype=F32, device=logits.device) if want_entropy else None
+    abi.check(abi.lib().mcd_argmax_entropy(_p(logits), _p(labels), _p(acc), n, c, c_arg, h, w, _dev(logits),
+                                           _stream(logits)), "argmax_entropy")
+    ent = (-acc[0] / float(n * c * h * w)) if want_entropy else None
+    return labels, ent
+
+
+def sgd_step(param, grad, buf, lr, momentum, weight_decay, first_step):
+    abi.check(abi.lib().mcd_sgd_step(_p(param), _p(grad), _p(buf), param.numel(), float(lr),
+                                     float(momentum), float(weight_decay), int(first_step), _dev(param),
+                                     _stream(param)), "sgd_step")

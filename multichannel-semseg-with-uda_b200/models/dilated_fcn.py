@@ -1,0 +1,295 @@
+"""Segmentation wrappers over DRN for the MCD step, on libmcd_sm100 kernels.
+
+Mirrors the hot classes of the reference's models/dilated_fcn.py with identical constructor signatures,
+module names (=> state_dict keys) and call signatures:
+
+  DRNSegBase (:217-250)                       generator G: DRN trunk + 1x1 `seg` conv -> [B,n_class,H/8,W/8]
+  DRNSegPixelClassifier (:340-366)            head F: learned depthwise 16x16/s8 deconv -> [B,n_class,H,W]
+  FusionDRNSegPixelClassifier (:431-470)      MFNet AddFusion head     up(x1 + x2)
+  ScoreFusionDRNSegPixelClassifier (:473-491) MFNet ScoreAddFusion head up1(x1) + up2(x2)
+  MultiTaskEncoder (:554-566), MultiTaskEncoderReturningMultipleFeaturemaps (:569-629)
+  CBR (:632-644), ThreeLayerDecoder (:647-658)
+  MCDMultiTaskDecoder (:661-739), MCDTripleMultiTaskDecoder (:790-1024)
+
+Score maps (n_class / depth / boundary channels at 1/8, 1/4, 1/2 resolution) are fp32 NCHW tensors, the
+full-resolution predictions bf16 NCHW tensors; trunk activations are bf16 channels_last.
+Everything else in the reference file (DRNSeg, ver2 heads, FuseDRNSegBase, domain classifiers, the
+vendored fyu/drn CLI, shortcut / seg2bd options) is outside SURVEY.md section 8 and raises NotImplementedError.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn import Parameter
+
+import loss as _loss
+from mcd_b200 import ops
+from mcd_b200.nn import (BatchNorm2d, BilinearUpsample, Conv2d, DepthwiseDeconv16s8, conv_bn_act)
+from models import drn
+from models.fusion import AddFusion, get_fusion_model
+
+
+def _he_init(conv):
+    import math
+    fan = conv.kernel_size[0] * conv.kernel_size[1] * conv.out_channels
+    conv.weight.data.normal_(0, math.sqrt(2. / fan))
+    conv.bias.data.zero_()
+
+
+def _trunk(model_name, pretrained, input_ch):
+    factory = drn.__dict__.get(model_name)
+    if factory is None:
+        raise NotImplementedError("%s: only drn_d_22 / drn_d_38 are built on libmcd_sm100" % model_name)
+    return factory(pretrained=pretrained, num_classes=1000, input_ch=input_ch)
+
+
+class DRNSegBase(nn.Module):
+    def __init__(self, model_name, n_class, pretrained=True, input_ch=3, ver="ver1"):
+        super().__init__()
+        if ver != "ver1":
+            raise NotImplementedError("ver2 heads are outside the libmcd_sm100 hot-path scope")
+        model = _trunk(model_name, pretrained, input_ch)
+        self.base = nn.Sequential(*list(model.children())[:-2])
+        self.ver = ver
+        self.seg = Conv2d(model.out_dim, n_class, kernel_size=1, bias=True, planar_out=True)
+        _he_init(self.seg)
+
+    def forward(self, x):
+        return self.seg(self.base(x))
+
+    def optim_parameters(self, memo=None):
+        for param in self.base.parameters():
+            yield param
+        for param in self.seg.parameters():
+            yield param
+
+
+class DRNSegPixelClassifier(nn.Module):
+    def __init__(self, n_class, use_torch_up=False, dropout=False, ver="ver1"):
+        super().__init__()
+        if ver != "ver1" or use_torch_up:
+            raise NotImplementedError("ver2 / UpsamplingBilinear2d heads are outside the hot-path scope")
+        self.dropout = dropout
+        self.ver = ver
+        self.up = DepthwiseDeconv16s8(n_class)
+
+    def forward(self, x):
+        return self.up(x)
+
+
+class FusionDRNSegPixelClassifier(nn.Module):
+    def __init__(self, fusion_type, n_class, use_torch_up=False, ver="ver1"):
+        super().__init__()
+        if ver != "ver1" or use_torch_up:
+            raise NotImplementedError("ver2 / UpsamplingBilinear2d heads are outside the hot-path scope")
+        self.fusion = get_fusion_model(fusion_type, n_class)
+        self.ver = ver
+        self.up = DepthwiseDeconv16s8(n_class)
+
+    def forward(self, x1, x2):
+        return self.up(self.fusion(x1, x2))
+
+
+class ScoreFusionDRNSegPixelClassifier(nn.Module):
+    def __init__(self, fusion_type, n_class):
+        super().__init__()
+        self.fusion = get_fusion_model(fusion_type, n_class)
+        self.up1 = DepthwiseDeconv16s8(n_class)
+        self.up2 = DepthwiseDeconv16s8(n_class)
+
+    def forward(self, x1, x2):
+        if isinstance(self.fusion, AddFusion):
+            # up1(x1) + up2(x2) in ONE pass over the full-resolution tensor (no operand materialised)
+            return self.up1(x1, x2, self.up2)
+        return self.fusion(self.up1(x1), self.up2(x2))
+
+
+# ---- multitask encoder / decoders -----------------------------------------------------------------
+class MultiTaskEncoder(nn.Module):
+    def __init__(self, model_name, pretrained=True, input_ch=3):
+        super().__init__()
+        model = _trunk(model_name, pretrained, input_ch)
+        self.base = nn.Sequential(*list(model.children())[:-2])
+
+    def forward(self, x):
+        return self.base(x)
+
+
+class MultiTaskEncoderReturningMultipleFeaturemaps(nn.Module):
+    """returns {'h0'..'h8'}: h2 32@1/2, h3 64@1/4, h8 512@1/8 feed the triple-task decoder."""
+
+    def __init__(self, model_name, pretrained=True, input_ch=3):
+        super().__init__()
+        model = _trunk(model_name, pretrained, input_ch)
+        for i in range(9):
+            setattr(self, "main_layer%d" % i, getattr(model, "layer%d" % i))
+        self.up = BilinearUpsample(8)  # parameter-free, unused in forward (as in the reference)
+
+    def forward(self, x):
+        out = {}
+        for i in range(9):
+            x = getattr(self, "main_layer%d" % i)(x)
+            out["h%d" % i] = x
+        return out
+
+
+class CBR(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True):
+        super().__init__()
+        self.conv = Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                           dilation=dilation, groups=groups, bias=bias)
+        self.bn = BatchNorm2d(out_channels)
+
+    def forward(self, x):
+        return conv_bn_act(self.conv, self.bn, x, relu=True)
+
+
+class ThreeLayerDecoder(nn.Module):
+    def __init__(self, output_ch, input_ch=512):
+        super().__init__()
+        self.cbr1 = CBR(input_ch, 512, kernel_size=3, padding=1)
+        self.cbr2 = CBR(512, 512, kernel_size=1)
+        self.conv3 = Conv2d(512, output_ch, kernel_size=1, planar_out=True)
+
+    def forward(self, x):
+        return self.conv3(self.cbr2(self.cbr1(x)))
+
+
+def _scalar_param():
+    p = Parameter(torch.Tensor(1))
+    p.data.fill_(1)
+    return p
+
+
+def _weighted(s, value):
+    """learned log-variance task weighting exp(-s) * L + s (reference :1008-1014)."""
+    return torch.exp(-s) * value + s
+
+
+class MCDMultiTaskDecoder(nn.Module):
+    def __init__(self, n_class, depth_ch, semseg_criterion=None, discrepancy_criterion=None):
+        super().__init__()
+        self.s_semsegcls = _scalar_param()
+        self.s_deprgr = _scalar_param()
+        self.semsegcls_dec1 = ThreeLayerDecoder(n_class)
+        self.semsegcls_dec2 = ThreeLayerDecoder(n_class)
+        self.deprgr_dec = ThreeLayerDecoder(depth_ch)
+        self.semseg_criterion = semseg_criterion
+        self.discrepancy_criterion = discrepancy_criterion
+        self.upsample = BilinearUpsample(8)
+
+    def semseg_forward(self, x):
+        return self.upsample(self.semsegcls_dec1(x)), self.upsample(self.semsegcls_dec2(x))
+
+    def depth_forward(self, x):
+        return self.upsample(self.deprgr_dec(x))
+
+    def forward(self, x):
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x)
+        return pred_semseg1, pred_semseg2, self.depth_forward(x)
+
+    def get_cls_descrepancy(self, x):
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x)
+        return self.discrepancy_criterion(pred_semseg1, pred_semseg2)
+
+    def get_semseg_loss(self, x, gt_semseg, separately_returning=False):
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x)
+        loss1 = self.semseg_criterion(pred_semseg1, gt_semseg)
+        loss2 = self.semseg_criterion(pred_semseg2, gt_semseg)
+        return (loss1, loss2) if separately_returning else loss1 + loss2
+
+    def get_depth_loss(self, x, gt_dep):
+        return _loss.mse_loss(self.depth_forward(x), gt_dep)
+
+    def get_loss(self, x, gt_semseg, gt_dep, separately_returning=False):
+        l1, l2 = self.get_semseg_loss(x, gt_semseg, separately_returning=True)
+        semseg_loss = (_weighted(self.s_semsegcls, l1) + _weighted(self.s_semsegcls, l2)) / 2
+        depreg_loss = _weighted(self.s_deprgr, self.get_depth_loss(x, gt_dep))
+        if separately_returning:
+            return semseg_loss, depreg_loss
+        return semseg_loss + depreg_loss
+
+    def get_task_weights(self):
+        std_semseg = np.sqrt(np.exp(2 * self.s_semsegcls.data.cpu().numpy()))
+        std_depth = np.sqrt(np.exp(2 * self.s_deprgr.data.cpu().numpy()))
+        return std_semseg, std_depth
+
+
+class MCDTripleMultiTaskDecoder(nn.Module):
+    """semantic segmentation (two MCD classifiers) + HHA regression + boundary detection."""
+
+    def __init__(self, n_class, depth_ch, semseg_criterion=None, discrepancy_criterion=None,
+                 semseg_shortcut=False, depth_shortcut=False, add_pred_seg_boundary_loss=False,
+                 use_seg2bd_conv=False):
+        super().__init__()
+        if semseg_shortcut or depth_shortcut or add_pred_seg_boundary_loss or use_seg2bd_conv:
+            raise NotImplementedError("shortcut / pred-seg-boundary / seg2bd options are default-off in the "
+                                      "reference trainer and outside the libmcd_sm100 hot-path scope")
+        self.s_semsegcls = _scalar_param()
+        self.s_deprgr = _scalar_param()
+        self.s_boundary = _scalar_param()
+        self.semsegcls_dec1 = ThreeLayerDecoder(n_class)
+        self.semsegcls_dec2 = ThreeLayerDecoder(n_class)
+        self.deprgr_dec = ThreeLayerDecoder(depth_ch)
+        self.nmlrgr_dec = ThreeLayerDecoder(depth_ch)  # constructed, never used (reference :813)
+        self.semseg_criterion = semseg_criterion
+        self.discrepancy_criterion = discrepancy_criterion
+        self.upsample1 = BilinearUpsample(2)
+        self.upsample2 = BilinearUpsample(4)
+        self.upsample3 = BilinearUpsample(8)
+        self.conv1 = Conv2d(32, 1, kernel_size=1, stride=1, padding=0, planar_out=True)
+        self.conv2 = Conv2d(64, 1, kernel_size=1, stride=1, padding=0, planar_out=True)
+        self.conv3 = Conv2d(512, 1, kernel_size=1, stride=1, padding=0, planar_out=True)
+        self.semseg_shortcut = semseg_shortcut
+        self.depth_shortcut = depth_shortcut
+        self.add_pred_seg_boundary_loss = add_pred_seg_boundary_loss
+        self.use_seg2bd_conv = use_seg2bd_conv
+
+    def semseg_forward(self, x_dic):
+        h8 = x_dic["h8"]
+        return self.upsample3(self.semsegcls_dec1(h8)), self.upsample3(self.semsegcls_dec2(h8))
+
+    def depth_forward(self, x_dic):
+        return self.upsample3(self.deprgr_dec(x_dic["h8"]))
+
+    def _boundary_maps(self, x_dic):
+        return (self.upsample1(self.conv1(x_dic["h2"])), self.upsample2(self.conv2(x_dic["h3"])),
+                self.upsample3(self.conv3(x_dic["h8"])))
+
+    def boundary_forward(self, x_dic):
+        return _loss.sigmoid3_mean(*self._boundary_maps(x_dic))
+
+    def forward(self, x_dic):
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x_dic)
+        return pred_semseg1, pred_semseg2, self.depth_forward(x_dic), self.boundary_forward(x_dic)
+
+    def get_cls_descrepancy(self, x_dic):
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x_dic)
+        return self.discrepancy_criterion(pred_semseg1, pred_semseg2)
+
+    def get_semseg_loss(self, x_dic, gt_semseg, separately_returning=False):
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x_dic)
+        loss1 = self.semseg_criterion(pred_semseg1, gt_semseg)
+        loss2 = self.semseg_criterion(pred_semseg2, gt_semseg)
+        return (loss1, loss2) if separately_returning else loss1 + loss2
+
+    def get_depth_loss(self, x_dic, gt_dep):
+        return _loss.mse_loss(self.depth_forward(x_dic), gt_dep)
+
+    def get_boundary_loss(self, x_dic, gt_boundary):
+        # sigmoid-average + bce2d fused: the averaged probability map is never materialised
+        return _loss.sigmoid3_bce2d(*self._boundary_maps(x_dic), gt_boundary)
+
+    def get_loss(self, x, gt_semseg, gt_dep, gt_boundary, separately_returning=False):
+        l1, l2 = self.get_semseg_loss(x, gt_semseg, separately_returning=True)
+        semseg_loss = (_weighted(self.s_semsegcls, l1) + _weighted(self.s_semsegcls, l2)) / 2
+        depreg_loss = _weighted(self.s_deprgr, self.get_depth_loss(x, gt_dep))
+        boundary_loss = _weighted(self.s_boundary, self.get_boundary_loss(x, gt_boundary))
+        if separately_returning:
+            return semseg_loss, depreg_loss, boundary_loss
+        return semseg_loss + depreg_loss + boundary_loss
+
+    def get_task_weights(self):
+        std_semseg = np.sqrt(np.exp(2 * self.s_semsegcls.data.cpu().numpy()))
+        std_depth = np.sqrt(np.exp(2 * self.s_deprgr.data.cpu().numpy()))
+        return std_semseg, std_depth

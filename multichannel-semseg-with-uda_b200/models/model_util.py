@@ -1,0 +1,113 @@
+"""Model / optimiser factories of the MCD step (drop-in for the reference's models/model_util.py).
+
+Same function names, argument meaning and error behaviour as the reference (file:line below) for the DRN
+branches that are on the hot path; every other `net_name` raises NotImplementedError like the reference does
+for unknown names.  `is_data_parallel=True` is refused: the reference's single-process nn.DataParallel
+(models/model_util.py:283-284) is replaced by one process per GPU with NCCL gradient all-reduce
+(mcd_b200/parallel.py).
+"""
+import torch
+from torch import nn
+from torch.nn.modules.batchnorm import _BatchNorm
+
+_DRN_NAMES = ("drn_d_22", "drn_d_38")
+
+
+def _check_drn(net_name):
+    if "drn" not in net_name:
+        raise NotImplementedError("Only FCN (Including Dilated FCN), SegNet, PSPNet UNet are supported!")
+    if net_name not in _DRN_NAMES:
+        raise NotImplementedError("libmcd_sm100 builds %s only (got %s)" % (", ".join(_DRN_NAMES), net_name))
+
+
+def _no_data_parallel(flag):
+    if flag:
+        raise NotImplementedError("nn.DataParallel is replaced by one process per GPU: launch with torchrun "
+                                  "and wrap the models with mcd_b200.parallel.GradSync")
+
+
+def get_models(net_name, input_ch, n_class, res="50", method="MCD", is_data_parallel=False):
+    """(model_g, model_f1, model_f2) for method "MCD"; (model_g_3ch, model_g_1ch, model_f1, model_f2) for
+    "MCD-MFNet-AddFusion" / "MCD-MFNet-ScoreAddFusion" (reference models/model_util.py:160-286)."""
+    from models.dilated_fcn import (DRNSegBase, DRNSegPixelClassifier, FusionDRNSegPixelClassifier,
+                                    ScoreFusionDRNSegPixelClassifier)
+    if method == "MCD":
+        _check_drn(net_name)
+        model_list = [DRNSegBase(model_name=net_name, n_class=n_class, input_ch=input_ch),
+                      DRNSegPixelClassifier(n_class=n_class), DRNSegPixelClassifier(n_class=n_class)]
+    elif "MFNet" in method:
+        assert input_ch in [4, 6]
+        if "drn" not in net_name:
+            raise NotImplementedError("Only Dilated FCN is supported!")
+        _check_drn(net_name)
+        fusion_type = method.split("-")[-1]
+        head = ScoreFusionDRNSegPixelClassifier if "score" in method.lower() else FusionDRNSegPixelClassifier
+        model_list = [DRNSegBase(model_name=net_name, n_class=n_class, input_ch=3),
+                      DRNSegBase(model_name=net_name, n_class=n_class, input_ch=input_ch - 3),
+                      head(fusion_type=fusion_type, n_class=n_class),
+                      head(fusion_type=fusion_type, n_class=n_class)]
+    else:
+        # the reference *returns* (does not raise) the exception object here (models/model_util.py:281)
+        return NotImplementedError("Sorry... Only MCD is supported!")
+    _no_data_parallel(is_data_parallel)
+    return model_list
+
+
+def get_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
+                         is_data_parallel=False, is_src_only=False):
+    """(model_enc, model_dec): RGB encoder + seg/HHA MCD decoder (reference models/model_util.py:81-99)."""
+    from models.dilated_fcn import MCDMultiTaskDecoder, MultiTaskEncoder
+    _check_drn(net_name)
+    if is_src_only:
+        raise NotImplementedError("source-only decoders are outside the libmcd_sm100 hot-path scope")
+    model_enc = MultiTaskEncoder(model_name=net_name, input_ch=3)  # RGB is 3 channel
+    model_dec = MCDMultiTaskDecoder(n_class=n_class, depth_ch=input_ch - 3, semseg_criterion=semseg_criterion,
+                                    discrepancy_criterion=discrepancy_criterion)
+    _no_data_parallel(is_data_parallel)
+    return model_enc, model_dec
+
+
+def get_triple_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
+                                is_data_parallel=False, semseg_shortcut=False, depth_shortcut=False,
+                                add_pred_seg_boundary_loss=False, is_src_only=False, use_seg2bd_conv=False):
+    """(model_enc, model_dec): RGB encoder returning h0..h8 + seg/HHA/boundary MCD decoder; `input_ch` is
+    ignored exactly as in the reference (models/model_util.py:102-130)."""
+    from models.dilated_fcn import MCDTripleMultiTaskDecoder, MultiTaskEncoderReturningMultipleFeaturemaps
+    _check_drn(net_name)
+    if is_src_only:
+        raise NotImplementedError("source-only decoders are outside the libmcd_sm100 hot-path scope")
+    model_enc = MultiTaskEncoderReturningMultipleFeaturemaps(model_name=net_name, input_ch=3)
+    model_dec = MCDTripleMultiTaskDecoder(n_class=n_class, depth_ch=3, semseg_criterion=semseg_criterion,
+                                          discrepancy_criterion=discrepancy_criterion,
+                                          semseg_shortcut=semseg_shortcut, depth_shortcut=depth_shortcut,
+                                          add_pred_seg_boundary_loss=add_pred_seg_boundary_loss,
+                                          use_seg2bd_conv=use_seg2bd_conv)
+    _no_data_parallel(is_data_parallel)
+    return model_enc, model_dec
+
+
+def get_optimizer(model_parameters, opt, lr, momentum, weight_decay):
+    """torch.optim stays the optimiser (reference models/model_util.py:289-302)."""
+    params = filter(lambda p: p.requires_grad, model_parameters)
+    if opt == "sgd":
+        return torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
+    if opt == "adadelta":
+        return torch.optim.Adadelta(params, lr=lr, weight_decay=weight_decay)
+    if opt == "adam":
+        return torch.optim.Adam(params, lr=lr, betas=[0.5, 0.999], weight_decay=weight_decay)
+    raise NotImplementedError("Only (Momentum) SGD, Adadelta, Adam are supported!")
+
+
+def fix_batchnorm_when_training(model):
+    """--fix_bn: BatchNorm layers keep using their running statistics (reference :305-310)."""
+    if issubclass(type(model), _BatchNorm):
+        model.training = False
+    for module in model.children():
+        fix_batchnorm_when_training(module)
+
+
+def fix_dropout_when_training(model):
+    if type(model) in [nn.Dropout, nn.Dropout2d, nn.Dropout3d, nn.AlphaDropout]:
+        model.training = False
+    for module in model.children():
+        fix_dropout_when_training(module)

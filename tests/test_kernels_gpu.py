@@ -1,0 +1,306 @@
+"""Per-kernel parity of libmcd_sm100 (through the C-ABI) against plain PyTorch fp32 ops on the same
+bf16-rounded inputs.  Tolerances: bf16 outputs |err| <= 1e-2 * max|ref| (2^-8 rounding + accumulation
+order), fp32 reductions 2e-3 relative, integer outputs bit-exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _ops():
+    from mcd_b200 import abi, ops
+    return abi, ops
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def bf16_round(t):
+    return t.to(BF16).float()
+
+
+CONV_SHAPES = [
+    # N, H, W, Cin, Cout, k, stride, dil, pad
+    (2, 20, 24, 64, 64, 3, 1, 1, 1),
+    (1, 15, 20, 128, 256, 3, 1, 2, 2),
+    (2, 12, 16, 256, 512, 3, 1, 4, 4),
+    (1, 16, 16, 512, 512, 3, 1, 1, 1),
+    (1, 16, 24, 128, 256, 1, 1, 1, 0),
+    (2, 32, 40, 6, 16, 7, 1, 1, 3),
+    (2, 32, 40, 16, 16, 3, 1, 1, 1),
+    (2, 32, 40, 16, 32, 3, 2, 1, 1),
+    (2, 30, 40, 32, 64, 3, 2, 1, 1),
+    (2, 30, 40, 32, 64, 1, 2, 1, 0),
+    (1, 31, 37, 64, 128, 3, 2, 1, 1),   # odd sizes
+]
+
+
+def _conv_case(dev, shape, seed=0):
+    n, h, w, cin, cout, k, stride, dil, pad = shape
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g)).to(dev)
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) * (2.0 / (k * k * cin)) ** 0.5).to(dev)
+    return x, wt
+
+
+@pytest.mark.parametrize("algo_name", ["direct", "umma"])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_fprop(cuda_dev, shape, algo_name):
+    abi, ops = _ops()
+    algo = abi.ALGO_DIRECT if algo_name == "direct" else abi.ALGO_UMMA
+    n, h, w, cin, cout, k, stride, dil, pad = shape
+    x, wt = _conv_case(cuda_dev, shape)
+    ref = F.conv2d(x, wt, None, stride, pad, dil)
+    xn = ops.to_nhwc(x)
+    g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
+    y, stats = ops.conv_fprop(xn, ops.pack_weight(wt, 0), None, g, want_stats=True, algo=algo)
+    torch.cuda.synchronize()
+    got = ops.to_nchw_f32(y, cout)
+    assert rel_err(got, ref) < 1e-2
+    # fused BatchNorm statistics
+    s_ref = torch.cat([ref.sum((0, 2, 3)), (ref * ref).sum((0, 2, 3))])
+    assert float((stats - s_ref).abs().max() / (s_ref.abs().max() + 1e-6)) < 1e-2
+
+
+@pytest.mark.parametrize("algo_name", ["direct", "umma"])
+def test_conv_fprop_planar_bias(cuda_dev, algo_name):
+    abi, ops = _ops()
+    algo = abi.ALGO_DIRECT if algo_name == "direct" else abi.ALGO_UMMA
+    shape = (2, 15, 20, 512, 41, 1, 1, 1, 0)
+    x, wt = _conv_case(cuda_dev, shape, seed=3)
+    bias = torch.randn(41, device=cuda_dev)
+    ref = F.conv2d(x, wt, bias)
+    xn = ops.to_nhwc(x)
+    g = ops.conv_geom(xn.shape, 512, 41, 1, 1, 1, 1, 0)
+    y, _ = ops.conv_fprop(xn, ops.pack_weight(wt, 0), bias, g, planar=True, algo=algo)
+    assert y.shape == ref.shape and y.dtype == F32
+    assert rel_err(y, ref) < 2e-3
+
+
+@pytest.mark.parametrize("algo_name", ["direct", "umma"])
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad_wgrad(cuda_dev, shape, algo_name):
+    abi, ops = _ops()
+    algo = abi.ALGO_DIRECT if algo_name == "direct" else abi.ALGO_UMMA
+    n, h, w, cin, cout, k, stride, dil, pad = shape
+    x, wt = _conv_case(cuda_dev, shape, seed=1)
+    x.requires_grad_(True)
+    wt.requires_grad_(True)
+    ref = F.conv2d(x, wt, None, stride, pad, dil)
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    dy = bf16_round(torch.randn(ref.shape, generator=gen)).to(cuda_dev)
+    dx_ref, dw_ref = torch.autograd.grad(ref, (x, wt), dy)
+    xn, dyn = ops.to_nhwc(x.detach()), ops.to_nhwc(dy)
+    g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
+    dx = ops.conv_dgrad(dyn, ops.pack_weight(wt.detach(), 1), g, algo=algo)
+    dw, db = ops.conv_wgrad(xn, dyn, g, want_dbias=True, algo=algo)
+    torch.cuda.synchronize()
+    assert rel_err(ops.to_nchw_f32(dx, cin), dx_ref) < 1e-2
+    assert rel_err(dw, dw_ref) < 5e-3
+    assert rel_err(db, dy.sum((0, 2, 3))) < 5e-3
+
+
+def test_layout_roundtrip(cuda_dev):
+    abi, ops = _ops()
+    x = bf16_round(torch.randn(2, 6, 9, 10)).to(cuda_dev)
+    xn = ops.to_nhwc(x)
+    assert xn.shape == (2, 8, 9, 10) and ops.is_nhwc(xn)
+    assert torch.equal(xn[:, :6].float(), x) and float(xn[:, 6:].abs().max()) == 0.0
+    assert torch.equal(ops.to_nchw_f32(xn, 6), x)
+
+
+@pytest.mark.parametrize("mode", ["plain", "identity", "downsample"])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act_fwd_bwd(cuda_dev, mode, training):
+    abi, ops = _ops()
+    from mcd_b200.nn import BatchNorm2d
+    torch.manual_seed(0)
+    n, c, h, w = 2, 64, 12, 10
+    y = bf16_round(torch.randn(n, c, h, w) * 2 + 0.5).to(cuda_dev)
+    r = bf16_round(torch.randn(n, c, h, w)).to(cuda_dev)
+    bn, bn2 = BatchNorm2d(c).to(cuda_dev), BatchNorm2d(c).to(cuda_dev)
+    rbn, rbn2 = torch.nn.BatchNorm2d(c).to(cuda_dev), torch.nn.BatchNorm2d(c).to(cuda_dev)
+    for m in (bn, rbn):
+        m.weight.data = torch.linspace(0.5, 1.5, c, device=cuda_dev)
+        m.bias.data = torch.linspace(-0.2, 0.2, c, device=cuda_dev)
+        m.running_var.data.fill_(2.0)
+    for m in (bn2, rbn2):
+        m.weight.data = torch.linspace(1.2, 0.7, c, device=cuda_dev)
+        m.running_mean.data.fill_(0.1)
+    for m in (bn, bn2, rbn, rbn2):
+        m.train(training)
+    # reference
+    yr, rr = y.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    out = rbn(yr)
+    if mode == "identity":
+        out = out + rr
+    elif mode == "downsample":
+        out = out + rbn2(rr)
+    out = F.relu(out)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    dz = bf16_round(torch.randn(out.shape, generator=gen)).to(cuda_dev)
+    out.backward(dz)
+    # ours
+    yn = ops.to_nhwc(y).requires_grad_(True)
+    rn = ops.to_nhwc(r).requires_grad_(True)
+    st = ops.bn_stats(yn.detach(), c) if training else None
+    if mode == "plain":
+        z = bn.fused(yn, st, relu=True)
+    elif mode == "identity":
+        z = bn.fused(yn, st, relu=True, res=rn)
+    else:
+        rst = ops.bn_stats(rn.detach(), c) if training else None
+        z = bn.fused(yn, st, relu=True, res=rn, res_stats=rst, res_bn=bn2)
+    z.backward(ops.to_nhwc(dz))
+    torch.cuda.synchronize()
+    assert rel_err(ops.to_nchw_f32(z.detach()), out) < 1e-2
+    assert rel_err(ops.to_nchw_f32(yn.grad), yr.grad) < 1.5e-2
+    assert rel_err(bn.weight.grad, rbn.weight.grad) < 1e-2
+    assert rel_err(bn.bias.grad, rbn.bias.grad) < 1e-2
+    if mode != "plain":
+        assert rel_err(ops.to_nchw_f32(rn.grad), rr.grad) < 1.5e-2
+    if mode == "downsample":
+        assert rel_err(bn2.weight.grad, rbn2.weight.grad) < 1e-2
+    if training:
+        assert rel_err(bn.running_mean, rbn.running_mean) < 1e-3
+        assert rel_err(bn.running_var, rbn.running_var) < 1e-3
+        assert int(bn.num_batches_tracked) == 1
+
+
+def test_deconv16s8(cuda_dev):
+    abi, ops = _ops()
+    torch.manual_seed(1)
+    n, c, h, w = 2, 41, 6, 10
+    x = torch.randn(n, c, h, w, device=cuda_dev)
+    x2 = torch.randn(n, c, h, w, device=cuda_dev)
+    wt = torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1
+    wt2 = torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    ref = F.conv_transpose2d(xr, wr, None, stride=8, padding=4, groups=c)
+    out = ops.deconv16s8_fwd(x, wt)
+    assert out.shape == ref.shape and rel_err(out, ref) < 6e-3
+    ref2 = ref + F.conv_transpose2d(x2, wt2, None, stride=8, padding=4, groups=c)
+    assert rel_err(ops.deconv16s8_fwd(x, wt, x2, wt2), ref2) < 6e-3
+    dout = bf16_round(torch.randn(ref.shape, device=cuda_dev))
+    dx_ref, dw_ref = torch.autograd.grad(ref, (xr, wr), dout)
+    dx, dw = ops.deconv16s8_bwd(dout.to(BF16), x, wt)
+    assert rel_err(dx, dx_ref) < 2e-3 and rel_err(dw, dw_ref) < 2e-3
+
+
+@pytest.mark.parametrize("s", [2, 4, 8])
+def test_bilinear(cuda_dev, s):
+    abi, ops = _ops()
+    torch.manual_seed(2)
+    x = torch.randn(2, 3, 6, 8, device=cuda_dev)
+    xr = x.clone().requires_grad_(True)
+    ref = F.interpolate(xr, scale_factor=s, mode="bilinear", align_corners=False)
+    out32 = ops.bilinear_up_fwd(x, s, out_f32=True)
+    assert rel_err(out32, ref) < 1e-5
+    assert rel_err(ops.bilinear_up_fwd(x, s), ref) < 6e-3
+    dout = torch.randn_like(ref)
+    (dx_ref,) = torch.autograd.grad(ref, xr, dout)
+    assert rel_err(ops.bilinear_up_bwd(dout, s), dx_ref) < 1e-4
+    assert rel_err(ops.bilinear_up_bwd(bf16_round(dout).to(BF16), s),
+                   torch.autograd.grad(ref, xr, bf16_round(dout))[0]) < 1e-4
+
+
+def test_ce2d(cuda_dev):
+    from loss import CrossEntropyLoss2d
+    torch.manual_seed(3)
+    n, c, h, w = 2, 41, 16, 24
+    logits = bf16_round(torch.randn(n, c, h, w) * 3).to(cuda_dev)
+    target = torch.randint(0, c, (n, h, w), device=cuda_dev)
+    target[0, 0, :5] = -100
+    weight = torch.ones(c, device=cuda_dev)
+    weight[c - 1] = 0
+    weight[3] = 2.5
+    lr = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr, target, weight, ignore_index=-100)
+    (ref * 1.7).backward()
+    lo = logits.to(BF16).requires_grad_(True)
+    got = CrossEntropyLoss2d(weight)(lo, target)
+    (got * 1.7).backward()
+    assert abs(float(got) - float(ref)) / abs(float(ref)) < 1e-4
+    assert rel_err(lo.grad, lr.grad) < 1e-2
+    # rows with ignore_index / zero weight get exactly zero gradient
+    assert float(lo.grad[0, :, 0, :5].abs().max()) == 0.0
+    assert float(lo.grad.permute(0, 2, 3, 1)[target == c - 1].abs().max()) == 0.0
+
+
+def test_diff2d(cuda_dev):
+    from loss import Diff2d
+    torch.manual_seed(4)
+    a = bf16_round(torch.randn(2, 41, 16, 24) * 2).to(cuda_dev)
+    b = bf16_round(torch.randn(2, 41, 16, 24) * 2).to(cuda_dev)
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.mean(torch.abs(F.softmax(ar, 1) - F.softmax(br, 1)))
+    (-ref).backward()
+    ao, bo = a.to(BF16).requires_grad_(True), b.to(BF16).requires_grad_(True)
+    got = Diff2d()(ao, bo)
+    (-got).backward()
+    assert abs(float(got) - float(ref)) / float(ref) < 1e-4
+    assert rel_err(ao.grad, ar.grad) < 1e-2 and rel_err(bo.grad, br.grad) < 1e-2
+
+
+def test_mse_and_boundary_bce(cuda_dev):
+    import loss as L
+    torch.manual_seed(5)
+    p = bf16_round(torch.randn(2, 3, 16, 24)).to(cuda_dev)
+    t = torch.randn(2, 3, 16, 24, device=cuda_dev)
+    pr = p.clone().requires_grad_(True)
+    ref = F.mse_loss(pr, t)
+    ref.backward()
+    po = p.to(BF16).requires_grad_(True)
+    got = L.mse_loss(po, t)
+    got.backward()
+    assert abs(float(got) - float(ref)) / float(ref) < 1e-4 and rel_err(po.grad, pr.grad) < 1e-2
+
+    hs = [bf16_round(torch.randn(2, 1, 16, 24) * 2).to(cuda_dev) for _ in range(3)]
+    tgt = (torch.rand(2, 1, 16, 24, device=cuda_dev) < 0.1).float()
+    hr = [h.clone().requires_grad_(True) for h in hs]
+    prob = (torch.sigmoid(hr[0]) + torch.sigmoid(hr[1]) + torch.sigmoid(hr[2])) / 3
+    beta = 1 - torch.mean(tgt)
+    wts = 1 - beta + (2 * beta - 1) * tgt
+    ref = F.binary_cross_entropy(prob, tgt, wts)
+    ref.backward()
+    ho = [h.to(BF16).requires_grad_(True) for h in hs]
+    got = L.sigmoid3_bce2d(ho[0], ho[1], ho[2], tgt)
+    got.backward()
+    assert abs(float(got) - float(ref)) / float(ref) < 1e-4
+    for a_, b_ in zip(ho, hr):
+        assert rel_err(a_.grad, b_.grad) < 1e-2
+    assert rel_err(L.sigmoid3_mean(*[h.to(BF16) for h in hs]), prob) < 6e-3
+
+
+def test_argmax_entropy_bit_exact(cuda_dev):
+    import util
+    torch.manual_seed(6)
+    logits = (torch.randn(2, 41, 16, 24) * 3).to(BF16).to(cuda_dev)
+    logits[0, 7, 0, 0] = logits[0, 3, 0, 0] = 50.0   # tie: first index wins, like torch.max
+    logits[1, 40, 2, 2] = 60.0                        # background channel is excluded from argmax
+    ref = logits[:, :40].float().max(1)[1]
+    got = util.predict_labels(logits, 40)
+    assert got.dtype == torch.int64 and torch.equal(got, ref)
+    p = F.softmax(logits.float(), 1)
+    ent_ref = -torch.mean(p * torch.log(p + 1e-6))
+    assert abs(float(util.calc_entropy(logits)) - float(ent_ref)) / float(ent_ref) < 1e-3
+
+
+def test_sgd_step(cuda_dev):
+    abi, ops = _ops()
+    torch.manual_seed(7)
+    p = torch.randn(1000, device=cuda_dev)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=1e-3, momentum=0.9, weight_decay=2e-5)
+    buf = torch.zeros_like(p)
+    for it in range(3):
+        g = torch.randn(1000, device=cuda_dev)
+        pr.grad = g.clone()
+        opt.step()
+        ops.sgd_step(p, g, buf, 1e-3, 0.9, 2e-5, it == 0)
+    assert rel_err(p, pr.detach()) < 1e-6
