@@ -206,7 +206,7 @@ sigmoid3_bce_fwd_kernel(const __nv_bfloat16* __restrict__ h1, const __nv_bfloat1
                         const float* __restrict__ tsum, float* __restrict__ acc,
                         __nv_bfloat16* __restrict__ p_out, int64_t numel) {
   __shared__ float red[32];
-  const float beta = 1.f - tsum[0] / (float)numel;
+  const float beta = tsum ? 1.f - tsum[0] / (float)numel : 0.f;
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
        i += (int64_t)gridDim.x * blockDim.x) {

@@ -52,10 +52,19 @@ class _CE2dFn(torch.autograd.Function):
         return d, None, None, None, None
 
 
+class _NLLState(nn.Module):
+    """holds the class-weight buffer under the reference's key `nll_loss.weight` (the multitask decoders
+    register their criterion as a sub-module, so that key is part of their checkpoints)."""
+
+    def __init__(self, weight):
+        super().__init__()
+        self.register_buffer("weight", None if weight is None else weight.detach().to(F32).contiguous())
+
+
 class CrossEntropyLoss2d(nn.Module):
     def __init__(self, weight=None, size_average=True, ignore_index=-100):
         super().__init__()
-        self.register_buffer("weight", None if weight is None else weight.detach().to(F32).contiguous())
+        self.nll_loss = _NLLState(weight)
         self.size_average = size_average
         self.ignore_index = ignore_index
 
@@ -63,7 +72,7 @@ class CrossEntropyLoss2d(nn.Module):
         logits = _logits(inputs)
         if targets.dtype != torch.int64:
             targets = targets.long()
-        w = self.weight
+        w = self.nll_loss.weight
         if w is not None and w.device != logits.device:
             w = w.to(logits.device)
         return _CE2dFn.apply(logits, targets.contiguous(), w, self.ignore_index, self.size_average)

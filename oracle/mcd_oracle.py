@@ -1,0 +1,440 @@
+"""ORACLE - TEST INFRASTRUCTURE ONLY.  Never imported by the product path.
+
+A plain fp32 restatement (stock torch.nn.functional ops, NCHW, no custom kernels) of the reference's MCD hot
+path, written functionally over state_dicts that use the REFERENCE's key names.  It is what the CUDA path is
+compared against in tests/, in __graft_entry__.smoke() and what bench.py times as `cpu_baseline` /
+`--impl reference`.
+
+The arithmetic of the reference lives in a third-party dependency that is not under /root/reference:
+PyTorch (pinned `torch-0.4.1` CPU wheel, requirements.txt:7).  The oracle therefore calls the same torch
+operators the reference's modules call, from the same call sites:
+
+  conv / BN / ReLU / residual      models/drn.py:21-23,26-59,126-131,171-205
+  seg 1x1 conv                     models/dilated_fcn.py:226-232,243
+  depthwise deconv heads           models/dilated_fcn.py:357-366,465-470,479-491
+  decoders, bilinear upsample      models/dilated_fcn.py:632-658,661-739,790-1019
+  CrossEntropyLoss2d / Diff2d / bce2d   loss.py:7-13,93-100,131-138
+  class weights, entropy           util.py:99-111,44-48
+  MCD phases A / B / C x num_k     adapt_trainer.py:162-212, adapt_mfnet_trainer.py:181-235,
+                                   adapt_triple_multitask_trainer.py:202-287
+  SGD(momentum, weight decay)      models/model_util.py:289-302 (torch.optim.SGD semantics)
+
+Pinning: tests/golden/make_golden.py imports the real reference modules (py3-patched throw-away copy) in the
+build container, runs them on seeded inputs with `fill_state_dict_` weights and stores the outputs under
+tests/golden/; tests/test_oracle_golden.py checks this file against those vectors.  The reference's own
+tests (test/test_loss.py) do not touch this path, so those golden vectors are the pin.
+"""
+import math
+import zlib
+
+import torch
+import torch.nn.functional as F
+
+LAYERS = {"drn_d_22": [1, 1, 2, 2, 2, 2, 1, 1], "drn_d_38": [1, 1, 3, 4, 6, 3, 1, 1]}
+CHANNELS = (16, 32, 64, 128, 256, 512, 512, 512)
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+# ------------------------------------------------------------------------------------------------
+# architecture description (models/drn.py:103-205): a list of stages; each stage is a list of units
+#   ("cbr", key_conv, key_bn, stride, dil)                               conv3x3/7x7 + BN + ReLU
+#   ("block", prefix, stride, dil1, dil2, has_downsample)                 BasicBlock
+def trunk_spec(name="drn_d_38", prefix="base."):
+    layers = LAYERS[name]
+    spec = [[("cbr", "%s0.0" % prefix, "%s0.1" % prefix, 1, 1, 3)]]          # 7x7 pad 3
+    inplanes = CHANNELS[0]
+
+    def conv_stack(idx, ch, convs, stride=1, dil=1):
+        nonlocal inplanes
+        units = []
+        for j in range(convs):
+            units.append(("cbr", "%s%d.%d" % (prefix, idx, 3 * j), "%s%d.%d" % (prefix, idx, 3 * j + 1),
+                          stride if j == 0 else 1, dil, dil))
+            inplanes = ch
+        return units
+
+    def block_stack(idx, planes, blocks, stride=1, dilation=1, new_level=True):
+        nonlocal inplanes
+        units = []
+        ds = stride != 1 or inplanes != planes
+        d0 = (1, 1) if dilation == 1 else ((dilation // 2 if new_level else dilation), dilation)
+        units.append(("block", "%s%d.0" % (prefix, idx), stride, d0[0], d0[1], ds))
+        inplanes = planes
+        for b in range(1, blocks):
+            units.append(("block", "%s%d.%d" % (prefix, idx, b), 1, dilation, dilation, False))
+        return units
+
+    spec.append(conv_stack(1, CHANNELS[0], layers[0], stride=1))
+    spec.append(conv_stack(2, CHANNELS[1], layers[1], stride=2))
+    spec.append(block_stack(3, CHANNELS[2], layers[2], stride=2))
+    spec.append(block_stack(4, CHANNELS[3], layers[3], stride=2))
+    spec.append(block_stack(5, CHANNELS[4], layers[4], dilation=2, new_level=False))
+    spec.append(block_stack(6, CHANNELS[5], layers[5], dilation=4, new_level=False))
+    spec.append(conv_stack(7, CHANNELS[6], layers[6], dil=2))
+    spec.append(conv_stack(8, CHANNELS[7], layers[7], dil=1))
+    return spec
+
+
+def _bn(sd, key, x, train):
+    if train:
+        sd[key + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, sd[key + ".running_mean"], sd[key + ".running_var"], sd[key + ".weight"],
+                        sd[key + ".bias"], train, BN_MOMENTUM, BN_EPS)
+
+
+def _bn_train_flag(train, fix_bn):
+    return train and not fix_bn
+
+
+def trunk_forward(sd, x, name="drn_d_38", prefix="base.", train=True, fix_bn=False, taps=None):
+    """returns [h0..h8]; `taps` (dict) collects every conv output / unit output by key."""
+    bn_train = _bn_train_flag(train, fix_bn)
+    outs = []
+    for stage in trunk_spec(name, prefix):
+        for unit in stage:
+            if unit[0] == "cbr":
+                _, kc, kb, stride, dil, pad = unit
+                y = F.conv2d(x, sd[kc + ".weight"], None, stride, pad, dil)
+                x = F.relu(_bn(sd, kb, y, bn_train))
+                if taps is not None:
+                    taps[kc + ":conv"] = y
+                    taps[kc + ":out"] = x
+            else:
+                _, p, stride, d1, d2, ds = unit
+                y1 = F.conv2d(x, sd[p + ".conv1.weight"], None, stride, d1, d1)
+                o = F.relu(_bn(sd, p + ".bn1", y1, bn_train))
+                y2 = F.conv2d(o, sd[p + ".conv2.weight"], None, 1, d2, d2)
+                o = _bn(sd, p + ".bn2", y2, bn_train)
+                res = x
+                if ds:
+                    res = _bn(sd, p + ".downsample.1",
+                              F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0, 1), bn_train)
+                x = F.relu(o + res)
+                if taps is not None:
+                    taps[p + ".conv1:conv"] = y1
+                    taps[p + ".conv2:conv"] = y2
+                    taps[p + ":out"] = x
+        outs.append(x)
+    return outs
+
+
+def seg_base_forward(sd, x, name="drn_d_38", train=True, fix_bn=False, taps=None):
+    """DRNSegBase.forward: trunk + 1x1 seg conv (models/dilated_fcn.py:238-244)."""
+    h = trunk_forward(sd, x, name, "base.", train, fix_bn, taps)[-1]
+    return F.conv2d(h, sd["seg.weight"], sd["seg.bias"])
+
+
+def up_head(w, x):
+    """ConvTranspose2d(C,C,16,stride=8,padding=4,groups=C,bias=False) (models/dilated_fcn.py:357-366)."""
+    return F.conv_transpose2d(x, w, None, stride=8, padding=4, groups=x.shape[1])
+
+
+def head_forward(sd, feats, kind="single"):
+    """kind: 'single' DRNSegPixelClassifier, 'add' FusionDRNSegPixelClassifier(AddFusion),
+    'scoreadd' ScoreFusionDRNSegPixelClassifier."""
+    if kind == "single":
+        return up_head(sd["up.weight"], feats)
+    if kind == "add":
+        return up_head(sd["up.weight"], feats[0] + feats[1])
+    return up_head(sd["up1.weight"], feats[0]) + up_head(sd["up2.weight"], feats[1])
+
+
+def bilinear_up(x, s):
+    return F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+
+
+def three_layer_decoder(sd, p, x, train=True, fix_bn=False):
+    """ThreeLayerDecoder: CBR 3x3 -> CBR 1x1 -> conv 1x1, all with bias (models/dilated_fcn.py:632-658)."""
+    bn_train = _bn_train_flag(train, fix_bn)
+    x = F.relu(_bn(sd, p + ".cbr1.bn", F.conv2d(x, sd[p + ".cbr1.conv.weight"], sd[p + ".cbr1.conv.bias"],
+                                                padding=1), bn_train))
+    x = F.relu(_bn(sd, p + ".cbr2.bn", F.conv2d(x, sd[p + ".cbr2.conv.weight"], sd[p + ".cbr2.conv.bias"]),
+                   bn_train))
+    return F.conv2d(x, sd[p + ".conv3.weight"], sd[p + ".conv3.bias"])
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+def class_weight(n_class, add_bg_loss=False):
+    w = torch.ones(n_class)
+    if not add_bg_loss:
+        w[n_class - 1] = 0
+    return w
+
+
+def ce2d(logits, target, weight=None, ignore_index=-100):
+    return F.nll_loss(F.log_softmax(logits, dim=1), target, weight, ignore_index=ignore_index)
+
+
+def diff2d(a, b):
+    return torch.mean(torch.abs(F.softmax(a, dim=1) - F.softmax(b, dim=1)))
+
+
+def bce2d(p, t):
+    beta = 1 - torch.mean(t)
+    w = 1 - beta + (2 * beta - 1) * t
+    return F.binary_cross_entropy(p, t, w)
+
+
+def calc_entropy(logits):
+    p = F.softmax(logits, dim=1)
+    return -torch.mean(p * torch.log(p + 1e-6))
+
+
+def predict_labels(logits, n_valid):
+    return logits[:, :n_valid].max(1)[1]
+
+
+# ------------------------------------------------------------------------------------------------
+# triple-task decoder (models/dilated_fcn.py:790-1019), default flags
+def triple_semseg(sd, hd, train=True, fix_bn=False):
+    return (bilinear_up(three_layer_decoder(sd, "semsegcls_dec1", hd["h8"], train, fix_bn), 8),
+            bilinear_up(three_layer_decoder(sd, "semsegcls_dec2", hd["h8"], train, fix_bn), 8))
+
+
+def triple_depth(sd, hd, train=True, fix_bn=False):
+    return bilinear_up(three_layer_decoder(sd, "deprgr_dec", hd["h8"], train, fix_bn), 8)
+
+
+def triple_boundary(sd, hd):
+    h1 = bilinear_up(F.conv2d(hd["h2"], sd["conv1.weight"], sd["conv1.bias"]), 2)
+    h2 = bilinear_up(F.conv2d(hd["h3"], sd["conv2.weight"], sd["conv2.bias"]), 4)
+    h3 = bilinear_up(F.conv2d(hd["h8"], sd["conv3.weight"], sd["conv3.bias"]), 8)
+    return (torch.sigmoid(h1) + torch.sigmoid(h2) + torch.sigmoid(h3)) / 3
+
+
+def _uw(s, value):
+    return torch.exp(-s) * value + s
+
+
+def triple_get_loss(sd, hd, gt_semseg, gt_dep, gt_bd, weight, train=True):
+    s1, s2 = triple_semseg(sd, hd, train)
+    l1, l2 = ce2d(s1, gt_semseg, weight), ce2d(s2, gt_semseg, weight)
+    semseg = (_uw(sd["s_semsegcls"], l1) + _uw(sd["s_semsegcls"], l2)) / 2
+    dep = _uw(sd["s_deprgr"], F.mse_loss(triple_depth(sd, hd, train), gt_dep))
+    bd = _uw(sd["s_boundary"], bce2d(triple_boundary(sd, hd), gt_bd))
+    return semseg, dep, bd
+
+
+def encoder_dict(sd, x, name="drn_d_38", train=True, fix_bn=False):
+    hs = trunk_forward(sd, x, name, "main_layer", train, fix_bn)
+    return {"h%d" % i: h for i, h in enumerate(hs)}
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter creation with the reference's initialisation distributions
+def _he_normal(shape, gen):
+    fan = shape[2] * shape[3] * shape[0]
+    return torch.randn(shape, generator=gen) * math.sqrt(2.0 / fan)
+
+
+def _bn_state(sd, key, c):
+    sd[key + ".weight"] = torch.ones(c)
+    sd[key + ".bias"] = torch.zeros(c)
+    sd[key + ".running_mean"] = torch.zeros(c)
+    sd[key + ".running_var"] = torch.ones(c)
+    sd[key + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+
+
+def init_trunk(name="drn_d_38", input_ch=3, prefix="base.", gen=None):
+    """He-normal convs, BN gamma=1 beta=0 (models/drn.py:163-169); 4-6 channel first conv duplicates the RGB
+    filters (models/drn.py:285-288)."""
+    gen = gen or torch.Generator().manual_seed(0)
+    sd = {}
+    cin = 3
+    for stage in trunk_spec(name, prefix):
+        for unit in stage:
+            if unit[0] == "cbr":
+                _, kc, kb, stride, dil, pad = unit
+                idx = int(kc[len(prefix):].split(".")[0])
+                cout = CHANNELS[0] if idx == 0 else (CHANNELS[0] if idx == 1 else
+                                                     CHANNELS[1] if idx == 2 else CHANNELS[idx - 1])
+                k = 7 if idx == 0 else 3
+                sd[kc + ".weight"] = _he_normal((cout, cin, k, k), gen)
+                _bn_state(sd, kb, cout)
+                cin = cout
+            else:
+                _, p, stride, d1, d2, ds = unit
+                idx = int(p[len(prefix):].split(".")[0])
+                planes = CHANNELS[idx - 1]
+                sd[p + ".conv1.weight"] = _he_normal((planes, cin, 3, 3), gen)
+                _bn_state(sd, p + ".bn1", planes)
+                sd[p + ".conv2.weight"] = _he_normal((planes, planes, 3, 3), gen)
+                _bn_state(sd, p + ".bn2", planes)
+                if ds:
+                    sd[p + ".downsample.0.weight"] = _he_normal((planes, cin, 1, 1), gen)
+                    _bn_state(sd, p + ".downsample.1", planes)
+                cin = planes
+    if input_ch != 3:
+        w3 = sd[prefix + "0.0.weight"]
+        if input_ch == 1:
+            sd[prefix + "0.0.weight"] = w3[:, 0:1].clone()
+        else:
+            sd[prefix + "0.0.weight"] = torch.cat([w3, w3[:, 0:input_ch - 3]], 1)
+    return sd
+
+
+def _default_conv(sd, key, cout, cin, k, gen, bias=True):
+    """nn.Conv2d default init: kaiming_uniform(a=sqrt(5)) = U(+-1/sqrt(fan_in)) for weight and bias."""
+    bound = 1.0 / math.sqrt(cin * k * k)
+    sd[key + ".weight"] = (torch.rand((cout, cin, k, k), generator=gen) * 2 - 1) * bound
+    if bias:
+        sd[key + ".bias"] = (torch.rand(cout, generator=gen) * 2 - 1) * bound
+
+
+def init_seg_base(name="drn_d_38", input_ch=6, n_class=41, gen=None):
+    gen = gen or torch.Generator().manual_seed(0)
+    sd = init_trunk(name, input_ch, "base.", gen)
+    sd["seg.weight"] = _he_normal((n_class, 512, 1, 1), gen)
+    sd["seg.bias"] = torch.zeros(n_class)
+    return sd
+
+
+def init_head(n_class=41, kind="single", gen=None):
+    """nn.ConvTranspose2d default init (weight [C,1,16,16]: fan_in = 256 -> U(+-1/16))."""
+    gen = gen or torch.Generator().manual_seed(1)
+    keys = ["up.weight"] if kind in ("single", "add") else ["up1.weight", "up2.weight"]
+    return {k: (torch.rand((n_class, 1, 16, 16), generator=gen) * 2 - 1) / 16.0 for k in keys}
+
+
+def init_three_layer_decoder(sd, p, out_ch, gen):
+    _default_conv(sd, p + ".cbr1.conv", 512, 512, 3, gen)
+    _bn_state(sd, p + ".cbr1.bn", 512)
+    _default_conv(sd, p + ".cbr2.conv", 512, 512, 1, gen)
+    _bn_state(sd, p + ".cbr2.bn", 512)
+    _default_conv(sd, p + ".conv3", out_ch, 512, 1, gen)
+
+
+def init_triple_decoder(n_class=41, depth_ch=3, gen=None):
+    gen = gen or torch.Generator().manual_seed(2)
+    sd = {"s_semsegcls": torch.ones(1), "s_deprgr": torch.ones(1), "s_boundary": torch.ones(1)}
+    init_three_layer_decoder(sd, "semsegcls_dec1", n_class, gen)
+    init_three_layer_decoder(sd, "semsegcls_dec2", n_class, gen)
+    init_three_layer_decoder(sd, "deprgr_dec", depth_ch, gen)
+    init_three_layer_decoder(sd, "nmlrgr_dec", depth_ch, gen)
+    _default_conv(sd, "conv1", 1, 32, 1, gen)
+    _default_conv(sd, "conv2", 1, 64, 1, gen)
+    _default_conv(sd, "conv3", 1, 512, 1, gen)
+    return sd
+
+
+def fill_state_dict_(sd, seed=0):
+    """Deterministic, key-addressed refill used to give the reference modules, the oracle and the CUDA modules
+    IDENTICAL non-trivial weights without shipping them: every tensor is regenerated from crc32(key)."""
+    for key in sorted(sd):
+        t = sd[key]
+        if not torch.is_floating_point(t):
+            continue
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(key.encode()))
+        if key.endswith("running_var"):
+            v = torch.rand(t.shape, generator=g) + 0.5
+        elif key.endswith("running_mean") or key.endswith(".bias"):
+            v = torch.randn(t.shape, generator=g) * 0.1
+        elif t.dim() == 1 and key.endswith(".weight"):       # BN gamma
+            v = torch.rand(t.shape, generator=g) + 0.5
+        elif t.dim() == 4:
+            fan_in = t.shape[1] * t.shape[2] * t.shape[3]
+            v = torch.randn(t.shape, generator=g) * math.sqrt(2.0 / fan_in)
+        else:                                                # task-uncertainty scalars
+            v = torch.rand(t.shape, generator=g) + 0.5
+        t.copy_(v.to(t.dtype))
+    return sd
+
+
+def to_device(sd, dev):
+    return {k: v.to(dev) for k, v in sd.items()}
+
+
+def trainable(sd):
+    """names of the tensors torch.optim would update (nn.Parameters of the reference modules)."""
+    return [k for k, v in sd.items() if torch.is_floating_point(v) and not k.endswith("running_mean")
+            and not k.endswith("running_var")]
+
+
+# ------------------------------------------------------------------------------------------------
+# SGD exactly as torch.optim.SGD(momentum, weight_decay) (dampening 0, no nesterov)
+class SGD:
+    def __init__(self, lr=1e-3, momentum=0.9, weight_decay=2e-5):
+        self.lr, self.momentum, self.wd = lr, momentum, weight_decay
+        self.buf = {}
+
+    def step(self, sd, grads):
+        with torch.no_grad():
+            for k, g in grads.items():
+                if g is None:
+                    continue
+                d = g + self.wd * sd[k] if self.wd else g
+                if self.momentum:
+                    b = self.buf.get((id(sd), k))
+                    b = d.clone() if b is None else b.mul_(self.momentum).add_(d)
+                    self.buf[(id(sd), k)] = b
+                    d = b
+                sd[k].add_(d, alpha=-self.lr)
+
+
+def _grads(loss, sds):
+    """d loss / d params for a list of state dicts; returns one {key: grad} per dict."""
+    names, leaves = [], []
+    for i, sd in enumerate(sds):
+        for k in trainable(sd):
+            names.append((i, k))
+            leaves.append(sd[k])
+    gs = torch.autograd.grad(loss, leaves, allow_unused=True)
+    out = [dict() for _ in sds]
+    for (i, k), g in zip(names, gs):
+        out[i][k] = g
+    return out
+
+
+def _req(sds, flag=True):
+    for sd in sds:
+        for k in trainable(sd):
+            sd[k].requires_grad_(flag)
+
+
+def mcd_step_early(G, F1, F2, src, lbl, tgt, weight, opt_g, opt_f, num_k=4, num_multiply_d_loss=1.0,
+                   name="drn_d_38", record=None):
+    """One iteration of adapt_trainer.py:162-212 (phase A, B, num_k x C).  G/F1/F2 are state dicts and are
+    updated in place; returns (c_loss, d_loss) like the trainer's running numbers.  `record` (dict) receives
+    intermediate tensors for parity tests."""
+    _req([G, F1, F2])
+    # ---- A: source supervised, updates G, F1, F2 (adapt_trainer.py:163-185)
+    feat = seg_base_forward(G, src, name)
+    o1, o2 = head_forward(F1, feat), head_forward(F2, feat)
+    loss = ce2d(o1, lbl, weight) + ce2d(o2, lbl, weight)
+    gg, g1, g2 = _grads(loss, [G, F1, F2])
+    if record is not None:
+        record.update(A_feat=feat.detach(), A_out1=o1.detach(), A_loss=loss.detach(),
+                      A_grad_g=gg, A_grad_f1=g1)
+    c_loss = float(loss)
+    opt_g.step(G, gg)
+    opt_f.step(F1, g1)
+    if F2 is not F1:
+        opt_f.step(F2, g2)
+    # ---- B: classifiers maximise the discrepancy on target (adapt_trainer.py:187-200)
+    feat = seg_base_forward(G, src, name)
+    o1, o2 = head_forward(F1, feat), head_forward(F2, feat)
+    loss = ce2d(o1, lbl, weight) + ce2d(o2, lbl, weight)
+    feat_t = seg_base_forward(G, tgt, name)
+    t1, t2 = head_forward(F1, feat_t), head_forward(F2, feat_t)
+    loss = loss - diff2d(t1, t2)
+    _, g1, g2 = _grads(loss, [G, F1, F2])
+    if record is not None:
+        record.update(B_loss=loss.detach(), B_grad_f1=g1)
+    opt_f.step(F1, g1)
+    if F2 is not F1:
+        opt_f.step(F2, g2)
+    # ---- C x num_k: generator minimises the discrepancy (adapt_trainer.py:204-212)
+    for i in range(num_k):
+        feat_t = seg_base_forward(G, tgt, name)
+        t1, t2 = head_forward(F1, feat_t), head_forward(F2, feat_t)
+        loss = diff2d(t1, t2) * num_multiply_d_loss
+        gg, _, _ = _grads(loss, [G, F1, F2])
+        if record is not None:
+            record.setdefault("C_losses", []).append(float(loss))
+            if i == 0:
+                record.update(C0_grad_g=gg)
+        opt_g.step(G, gg)
+    _req([G, F1, F2], False)
+    d_loss = float(loss) / num_k
+    return c_loss, d_loss

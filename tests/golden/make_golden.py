@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""Generate the golden vectors that pin oracle/mcd_oracle.py to the REAL reference implementation.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It stages a throw-away py3-patched copy of the reference under /tmp (four one-line Python-2-isms, SURVEY.md
+section 8c; nothing of the reference is written into this repository), imports the reference's own modules
+(models/model_util.py factories, loss.py criteria), gives them deterministic weights with
+oracle.fill_state_dict_ (regenerable from the key names, so no weights are shipped), replays the reference's
+trainer / tester loop bodies on seeded synthetic inputs with torch.optim.SGD, and stores the resulting losses,
+activations, gradient norms and updated-weight checksums in tests/golden/*.npz.
+"""
+import os
+import shutil
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import mcd_oracle as O  # noqa: E402
+
+REF = "/root/reference"
+STAGE = "/tmp/mcd_ref_py3"
+SIZE = (96, 128)
+N_CLASS = 41
+
+
+def stage_reference():
+    if os.path.exists(STAGE):
+        shutil.rmtree(STAGE)
+    shutil.copytree(REF, STAGE, ignore=shutil.ignore_patterns("*.png", "*.jpg", "docs", "sample_img", "_static"))
+
+    def patch(rel, pairs):
+        p = os.path.join(STAGE, rel)
+        s = open(p).read()
+        for a, b in pairs:
+            assert a in s, (rel, a)
+            s = s.replace(a, b)
+        open(p, "w").write(s)
+
+    patch("loss.py", [("print prob1", "print(prob1)")])
+    patch("models/dilated_fcn.py", [("cuda(async=True)", "cuda(non_blocking=True)"),
+                                    ("\nimport drn\n", "\nfrom models import drn\n")])
+    patch("models/drn.py", [("gen.next()", "next(gen)")])
+    sys.path.insert(0, STAGE)
+    import models.drn as drn
+    for name in ("drn_d_22", "drn_d_38"):
+        orig = getattr(drn, name)
+        setattr(drn, name, (lambda f: lambda pretrained=False, **kw: f(pretrained=False, **kw))(orig))
+
+
+def filled(module, seed):
+    # the multitask decoders register their criterion as a sub-module, so its class-weight buffer
+    # (`semseg_criterion.nll_loss.weight`) shows up in state_dict(): keep that one as configured.
+    sd = {k: v for k, v in module.state_dict().items() if "criterion" not in k}
+    O.fill_state_dict_(sd, seed)
+    module.load_state_dict(sd, strict=False)
+    return module
+
+
+def inputs(seed, n=2, ch=6, size=SIZE):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(n, ch, *size, generator=g)
+    tgt = torch.randn(n, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (n, *size), generator=g)
+    return src, tgt, lbl
+
+
+def norms(named_grads):
+    keys = sorted(named_grads)
+    return keys, np.array([float(named_grads[k].norm()) if named_grads[k] is not None else -1.0 for k in keys],
+                          dtype=np.float64)
+
+
+def summarize(sd):
+    keys = sorted(k for k in sd if torch.is_floating_point(sd[k]))
+    return keys, np.array([[float(sd[k].double().sum()), float(sd[k].double().norm())] for k in keys])
+
+
+def golden_early_fusion():
+    """adapt_trainer.py:151-215 replayed verbatim (python-3 spellings) on synthetic tensors."""
+    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+    from models.model_util import get_models, get_optimizer
+    from util import get_class_weight_from_file
+    model_g, model_f1, model_f2 = get_models(net_name="drn_d_38", res="50", input_ch=6, n_class=N_CLASS,
+                                             method="MCD", is_data_parallel=False)
+    filled(model_g, 11), filled(model_f1, 12), filled(model_f2, 13)
+    optimizer_g = get_optimizer(model_g.parameters(), lr=1e-3, momentum=0.9, opt="sgd", weight_decay=2e-5)
+    optimizer_f = get_optimizer(list(model_f1.parameters()) + list(model_f2.parameters()), opt="sgd", lr=1e-3,
+                                momentum=0.9, weight_decay=2e-5)
+    weight = get_class_weight_from_file(n_class=N_CLASS, weight_filename=None, add_bg_loss=False)
+    criterion = CrossEntropyLoss2d(weight)
+    criterion_d = get_prob_distance_criterion("diff")
+    model_g.train(), model_f1.train(), model_f2.train()
+    src_imgs, tgt_imgs, src_lbls = inputs(101)
+    num_k, out = 4, {}
+
+    # phase A
+    optimizer_g.zero_grad(), optimizer_f.zero_grad()
+    outputs = model_g(src_imgs)
+    outputs1, outputs2 = model_f1(outputs), model_f2(outputs)
+    loss = criterion(outputs1, src_lbls) + criterion(outputs2, src_lbls)
+    loss.backward()
+    out["A_loss"] = float(loss)
+    out["A_feat"] = outputs.detach().numpy()
+    out["A_out1_sub"] = outputs1.detach()[:, :, ::8, ::8].numpy()
+    gk, gv = norms({k: p.grad for k, p in model_g.named_parameters()})
+    out["A_grad_g_keys"], out["A_grad_g_norms"] = np.array(gk), gv
+    out["A_grad_up1"] = model_f1.up.weight.grad.numpy().copy()
+    out["A_grad_seg_bias"] = model_g.seg.bias.grad.numpy().copy()
+    optimizer_g.step(), optimizer_f.step()
+    # phase B
+    optimizer_g.zero_grad(), optimizer_f.zero_grad()
+    outputs = model_g(src_imgs)
+    outputs1, outputs2 = model_f1(outputs), model_f2(outputs)
+    loss = criterion(outputs1, src_lbls) + criterion(outputs2, src_lbls)
+    outputs = model_g(tgt_imgs)
+    outputs1, outputs2 = model_f1(outputs), model_f2(outputs)
+    loss = loss - criterion_d(outputs1, outputs2)
+    loss.backward()
+    out["B_loss"] = float(loss)
+    out["B_grad_up1"] = model_f1.up.weight.grad.numpy().copy()
+    optimizer_f.step()
+    # phase C
+    c_losses = []
+    for i in range(num_k):
+        optimizer_g.zero_grad()
+        outputs = model_g(tgt_imgs)
+        outputs1, outputs2 = model_f1(outputs), model_f2(outputs)
+        loss = criterion_d(outputs1, outputs2) * 1.0
+        loss.backward()
+        if i == 0:
+            gk, gv = norms({k: p.grad for k, p in model_g.named_parameters()})
+            out["C0_grad_g_norms"] = gv
+        c_losses.append(float(loss))
+        optimizer_g.step()
+    out["C_losses"] = np.array(c_losses)
+    sk, sv = summarize(model_g.state_dict())
+    out["final_g_keys"], out["final_g_sums"] = np.array(sk), sv
+    out["final_up1"] = model_f1.up.weight.detach().numpy().copy()
+    # tester (adapt_tester.py:104-124): eval forward, argmax without the background channel, entropy
+    from util import calc_entropy
+    model_g.eval(), model_f1.eval()
+    with torch.no_grad():
+        o = model_f1(model_g(tgt_imgs[:1]))
+    out["test_labels"] = o[0, :N_CLASS - 1].max(0)[1].numpy()
+    out["test_entropy"] = float(calc_entropy(o))
+    np.savez_compressed(os.path.join(HERE, "early_fusion.npz"), **out)
+    print("early_fusion: A %.6f B %.6f C %s" % (out["A_loss"], out["B_loss"], c_losses))
+
+
+def golden_mfnet():
+    from loss import CrossEntropyLoss2d, Diff2d
+    from models.model_util import get_models
+    from util import get_class_weight_from_file
+    out = {}
+    for tag, method in (("add", "MCD-MFNet-AddFusion"), ("scoreadd", "MCD-MFNet-ScoreAddFusion")):
+        g3, g1, f1, f2 = get_models(net_name="drn_d_38", res="50", input_ch=6, n_class=N_CLASS, method=method)
+        filled(g3, 21), filled(g1, 22), filled(f1, 23), filled(f2, 24)
+        for m in (g3, g1, f1, f2):
+            m.train()
+        src, tgt, lbl = inputs(202, size=(64, 96))
+        crit = CrossEntropyLoss2d(get_class_weight_from_file(n_class=N_CLASS))
+        # adapt_mfnet_trainer.py:186-192 forward pattern + the B-phase loss (CE on src - Diff2d on tgt)
+        o3, o1 = g3(src[:, :3, :, :]), g1(src[:, 3:, :, :])
+        p1, p2 = f1(o3, o1), f2(o3, o1)
+        loss = crit(p1, lbl) + crit(p2, lbl)
+        t3, t1 = g3(tgt[:, :3, :, :]), g1(tgt[:, 3:, :, :])
+        q1, q2 = f1(t3, t1), f2(t3, t1)
+        d = Diff2d()(q1, q2)
+        (loss - d).backward()
+        out[tag + "_ce"], out[tag + "_diff"] = float(loss), float(d)
+        out[tag + "_feat3"] = o3.detach().numpy()
+        out[tag + "_p1_sub"] = p1.detach()[:, :, ::8, ::8].numpy()
+        gk, gv = norms({k: p.grad for k, p in g1.named_parameters()})
+        out[tag + "_grad_g1_keys"], out[tag + "_grad_g1_norms"] = np.array(gk), gv
+        for k, p in f1.named_parameters():
+            out[tag + "_grad_f1_" + k] = p.grad.numpy().copy()
+        print("mfnet %s: ce %.6f diff %.6f" % (tag, float(loss), float(d)))
+    np.savez_compressed(os.path.join(HERE, "mfnet.npz"), **out)
+
+
+def golden_triple():
+    from loss import CrossEntropyLoss2d, Diff2d
+    from models.model_util import get_triple_multitask_models
+    from util import calc_entropy, get_class_weight_from_file
+    crit = CrossEntropyLoss2d(get_class_weight_from_file(n_class=N_CLASS))
+    enc, dec = get_triple_multitask_models(net_name="drn_d_38", input_ch=6, n_class=N_CLASS,
+                                           semseg_criterion=crit, discrepancy_criterion=Diff2d())
+    filled(enc, 31), filled(dec, 32)
+    enc.train(), dec.train()
+    g = torch.Generator().manual_seed(303)
+    size = (64, 96)
+    src = torch.randn(2, 7, *size, generator=g)
+    src[:, 6] = (torch.rand(2, *size, generator=g) < 0.1).float()
+    tgt = torch.randn(2, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (2, *size), generator=g)
+    # adapt_triple_multitask_trainer.py:194-248 (phase A)
+    src_rgbs, src_depths, src_boundary = src[:, :3], src[:, 3:-1], src[:, -1:]
+    tgt_rgbs, tgt_depths = tgt[:, :3], tgt[:, 3:]
+    src_fet, tgt_fet = enc(src_rgbs), enc(tgt_rgbs)
+    semseg, dep, bd = dec.get_loss(src_fet, lbl, src_depths, src_boundary, separately_returning=True)
+    tgt_dep = dec.get_depth_loss(tgt_fet, tgt_depths)
+    disc = dec.get_cls_descrepancy(tgt_fet)
+    total = semseg + dep + bd + tgt_dep - disc
+    total.backward()
+    out = dict(semseg=float(semseg), dep=float(dep), bd=float(bd), tgt_dep=float(tgt_dep), disc=float(disc))
+    out["h8_sub"] = src_fet["h8"].detach()[:, ::16].numpy()
+    gk, gv = norms({k: p.grad for k, p in enc.named_parameters()})
+    out["grad_enc_keys"], out["grad_enc_norms"] = np.array(gk), gv
+    gk, gv = norms({k: p.grad for k, p in dec.named_parameters()})
+    out["grad_dec_keys"], out["grad_dec_norms"] = np.array(gk), gv
+    # tester (adapt_triple_multitask_tester.py:117-142)
+    enc.eval(), dec.eval()
+    with torch.no_grad():
+        s1, s2, depth, boundary = dec(enc(tgt_rgbs[:1]))
+    out["test_labels"] = s1[0, :N_CLASS - 1].max(0)[1].numpy()
+    out["test_entropy"] = float(calc_entropy(s1))
+    out["test_depth_sub"] = depth[:, :, ::8, ::8].numpy()
+    out["test_boundary_sub"] = boundary[:, :, ::8, ::8].numpy()
+    np.savez_compressed(os.path.join(HERE, "triple.npz"), **out)
+    print("triple:", {k: v for k, v in out.items() if isinstance(v, float)})
+
+
+def golden_losses():
+    from loss import CrossEntropyLoss2d, Diff2d, bce2d
+    g = torch.Generator().manual_seed(404)
+    a = (torch.randn(2, N_CLASS, 12, 16, generator=g) * 3).requires_grad_(True)
+    b = (torch.randn(2, N_CLASS, 12, 16, generator=g) * 3).requires_grad_(True)
+    t = torch.randint(0, N_CLASS, (2, 12, 16), generator=g)
+    t[0, 0, :4] = -100
+    w = torch.ones(N_CLASS)
+    w[N_CLASS - 1] = 0
+    w[5] = 2.0
+    ce = CrossEntropyLoss2d(w)(a, t)
+    df = Diff2d()(a, b)
+    (ce + df).backward()
+    p = torch.rand(2, 1, 12, 16, generator=g).clamp(0.01, 0.99).requires_grad_(True)
+    tb = (torch.rand(2, 1, 12, 16, generator=g) < 0.2).float()
+    bc = bce2d(p, tb)
+    bc.backward()
+    np.savez_compressed(os.path.join(HERE, "losses.npz"), a=a.detach().numpy(), b=b.detach().numpy(), t=t.numpy(),
+                        w=w.numpy(), ce=float(ce), diff=float(df), da=a.grad.numpy(), db=b.grad.numpy(),
+                        p=p.detach().numpy(), tb=tb.numpy(), bce=float(bc), dp=p.grad.numpy())
+    print("losses: ce %.6f diff %.6f bce %.6f" % (float(ce), float(df), float(bc)))
+
+
+if __name__ == "__main__":
+    warnings.simplefilter("ignore")
+    torch.set_num_threads(8)
+    stage_reference()
+    golden_losses()
+    golden_early_fusion()
+    golden_mfnet()
+    golden_triple()

@@ -1,0 +1,146 @@
+"""Pin the oracle (oracle/mcd_oracle.py) to the real reference: every golden vector under tests/golden/ was
+produced by tests/golden/make_golden.py running the reference's own modules.  Both sides are fp32 torch CPU
+ops on identical weights (fill_state_dict_), so agreement is expected to ~1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mcd_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+N_CLASS = 41
+
+
+def close(a, b, rtol=2e-4, atol=1e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a - b).max() if a.size else 0.0
+    assert err <= atol + rtol * np.abs(b).max(), (err, np.abs(b).max())
+
+
+def _inputs(seed, n=2, ch=6, size=(96, 128)):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(n, ch, *size, generator=g)
+    tgt = torch.randn(n, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (n, *size), generator=g)
+    return src, tgt, lbl
+
+
+def _norms(keys, grads):
+    return np.array([float(grads[k].norm()) if grads.get(k) is not None else -1.0 for k in keys])
+
+
+def test_losses_match_reference():
+    z = np.load(os.path.join(GOLD, "losses.npz"))
+    a = torch.tensor(z["a"], requires_grad=True)
+    b = torch.tensor(z["b"], requires_grad=True)
+    t, w = torch.tensor(z["t"]), torch.tensor(z["w"])
+    ce, df = O.ce2d(a, t, w), O.diff2d(a, b)
+    (ce + df).backward()
+    close(float(ce), z["ce"]), close(float(df), z["diff"])
+    close(a.grad.numpy(), z["da"]), close(b.grad.numpy(), z["db"])
+    p = torch.tensor(z["p"], requires_grad=True)
+    bc = O.bce2d(p, torch.tensor(z["tb"]))
+    bc.backward()
+    close(float(bc), z["bce"]), close(p.grad.numpy(), z["dp"])
+
+
+def test_state_dict_keys_match_reference():
+    z = np.load(os.path.join(GOLD, "early_fusion.npz"))
+    G = O.init_seg_base("drn_d_38", 6, N_CLASS)
+    assert sorted(k for k in G if torch.is_floating_point(G[k])) == list(z["final_g_keys"])
+    assert sorted(O.trainable(G)) == list(z["A_grad_g_keys"])
+
+
+@pytest.mark.timeout(900)
+def test_early_fusion_iteration_matches_reference():
+    z = np.load(os.path.join(GOLD, "early_fusion.npz"))
+    G = O.fill_state_dict_(O.init_seg_base("drn_d_38", 6, N_CLASS), 11)
+    F1 = O.fill_state_dict_(O.init_head(N_CLASS), 12)
+    F2 = O.fill_state_dict_(O.init_head(N_CLASS), 13)
+    src, tgt, lbl = _inputs(101)
+    rec = {}
+    c_loss, d_loss = O.mcd_step_early(G, F1, F2, src, lbl, tgt, O.class_weight(N_CLASS), O.SGD(), O.SGD(),
+                                      num_k=4, record=rec)
+    close(float(rec["A_loss"]), z["A_loss"])
+    close(rec["A_feat"].numpy(), z["A_feat"])
+    close(rec["A_out1"][:, :, ::8, ::8].numpy(), z["A_out1_sub"])
+    close(_norms(list(z["A_grad_g_keys"]), rec["A_grad_g"]), z["A_grad_g_norms"], rtol=1e-3)
+    close(rec["A_grad_f1"]["up.weight"].numpy(), z["A_grad_up1"])
+    close(rec["A_grad_g"]["seg.bias"].numpy(), z["A_grad_seg_bias"])
+    close(float(rec["B_loss"]), z["B_loss"])
+    close(rec["B_grad_f1"]["up.weight"].numpy(), z["B_grad_up1"])
+    close(np.array(rec["C_losses"]), z["C_losses"], rtol=1e-3)
+    close(_norms(list(z["A_grad_g_keys"]), rec["C0_grad_g"]), z["C0_grad_g_norms"], rtol=2e-3)
+    sums = np.array([[float(G[k].double().sum()), float(G[k].double().norm())] for k in z["final_g_keys"]])
+    close(sums[:, 1], z["final_g_sums"][:, 1], rtol=1e-5)
+    close(sums[:, 0], z["final_g_sums"][:, 0], rtol=1e-4, atol=1e-3)
+    close(F1["up.weight"].numpy(), z["final_up1"])
+    assert abs(c_loss - float(z["A_loss"])) < 1e-4 and abs(d_loss - z["C_losses"][-1] / 4) < 1e-6
+    # tester path: eval-mode forward, argmax without background, entropy (adapt_tester.py:104-124)
+    with torch.no_grad():
+        o = O.head_forward(F1, O.seg_base_forward(G, tgt[:1], train=False))
+    labels = O.predict_labels(o, N_CLASS - 1)[0].numpy()
+    assert (labels == z["test_labels"]).mean() > 0.999
+    close(float(O.calc_entropy(o)), z["test_entropy"], rtol=1e-3)
+
+
+@pytest.mark.parametrize("tag,kind", [("add", "add"), ("scoreadd", "scoreadd")])
+def test_mfnet_heads_match_reference(tag, kind):
+    z = np.load(os.path.join(GOLD, "mfnet.npz"))
+    G3 = O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 21)
+    G1 = O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 22)
+    F1 = O.fill_state_dict_(O.init_head(N_CLASS, kind), 23)
+    F2 = O.fill_state_dict_(O.init_head(N_CLASS, kind), 24)
+    src, tgt, lbl = _inputs(202, size=(64, 96))
+    w = O.class_weight(N_CLASS)
+    O._req([G3, G1, F1, F2])
+    o3, o1 = O.seg_base_forward(G3, src[:, :3]), O.seg_base_forward(G1, src[:, 3:])
+    p1, p2 = O.head_forward(F1, (o3, o1), kind), O.head_forward(F2, (o3, o1), kind)
+    ce = O.ce2d(p1, lbl, w) + O.ce2d(p2, lbl, w)
+    t3, t1 = O.seg_base_forward(G3, tgt[:, :3]), O.seg_base_forward(G1, tgt[:, 3:])
+    d = O.diff2d(O.head_forward(F1, (t3, t1), kind), O.head_forward(F2, (t3, t1), kind))
+    _, gg1, gf1, _ = O._grads(ce - d, [G3, G1, F1, F2])
+    close(float(ce), z[tag + "_ce"]), close(float(d), z[tag + "_diff"], rtol=1e-3)
+    close(o3.detach().numpy(), z[tag + "_feat3"])
+    close(p1.detach()[:, :, ::8, ::8].numpy(), z[tag + "_p1_sub"])
+    close(_norms(list(z[tag + "_grad_g1_keys"]), gg1), z[tag + "_grad_g1_norms"], rtol=2e-3)
+    for k, g in gf1.items():
+        close(g.numpy(), z[tag + "_grad_f1_" + k], rtol=1e-3)
+
+
+def test_triple_multitask_matches_reference():
+    z = np.load(os.path.join(GOLD, "triple.npz"))
+    E = O.fill_state_dict_(O.init_trunk("drn_d_38", 3, "main_layer"), 31)
+    D = O.fill_state_dict_(O.init_triple_decoder(N_CLASS, 3), 32)
+    g = torch.Generator().manual_seed(303)
+    size = (64, 96)
+    src = torch.randn(2, 7, *size, generator=g)
+    src[:, 6] = (torch.rand(2, *size, generator=g) < 0.1).float()
+    tgt = torch.randn(2, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (2, *size), generator=g)
+    w = O.class_weight(N_CLASS)
+    O._req([E, D])
+    src_f, tgt_f = O.encoder_dict(E, src[:, :3]), O.encoder_dict(E, tgt[:, :3])
+    semseg, dep, bd = O.triple_get_loss(D, src_f, lbl, src[:, 3:-1], src[:, -1:], w)
+    tgt_dep = torch.nn.functional.mse_loss(O.triple_depth(D, tgt_f), tgt[:, 3:])
+    disc = O.diff2d(*O.triple_semseg(D, tgt_f))
+    ge, gd = O._grads(semseg + dep + bd + tgt_dep - disc, [E, D])
+    for name, v in (("semseg", semseg), ("dep", dep), ("bd", bd), ("tgt_dep", tgt_dep), ("disc", disc)):
+        close(float(v), z[name], rtol=5e-4)
+    close(src_f["h8"].detach()[:, ::16].numpy(), z["h8_sub"])
+    close(_norms(list(z["grad_enc_keys"]), ge), z["grad_enc_norms"], rtol=2e-3)
+    gd_n = _norms(list(z["grad_dec_keys"]), gd)
+    close(gd_n, z["grad_dec_norms"], rtol=2e-3)
+    assert (z["grad_dec_norms"] < 0).sum() == 10  # nmlrgr_dec never receives a gradient (reference :813)
+    O._req([E, D], False)
+    with torch.no_grad():
+        f = O.encoder_dict(E, tgt[:1, :3], train=False)
+        s1, _ = O.triple_semseg(D, f, train=False)
+        depth, boundary = O.triple_depth(D, f, train=False), O.triple_boundary(D, f)
+    assert (O.predict_labels(s1, N_CLASS - 1)[0].numpy() == z["test_labels"]).mean() > 0.999
+    close(float(O.calc_entropy(s1)), z["test_entropy"], rtol=1e-3)
+    close(depth[:, :, ::8, ::8].numpy(), z["test_depth_sub"])
+    close(boundary[:, :, ::8, ::8].numpy(), z["test_boundary_sub"])
