@@ -34,8 +34,13 @@ def _gscale(go):
 
 class _CE2dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, weight, ignore_index, size_average):
+    def forward(ctx, logits, target, weight, ignore_index, size_average, dist_group=False):
         acc = ops.ce2d_fwd(logits, target, weight, ignore_index)
+        if dist_group is not False and size_average:
+            # data parallel: the normaliser sum_i w[y_i] is global (what nn.DataParallel computes on the
+            # gathered outputs); the numerator stays local so that SUM-all-reduced gradients are exact.
+            import torch.distributed as dist
+            dist.all_reduce(acc[1:2], op=dist.ReduceOp.SUM, group=dist_group)
         if _CHECK_LABELS and float(acc[2]) != 0:
             raise IndexError("CrossEntropyLoss2d: %d target labels outside [0, %d) and != ignore_index" %
                              (int(acc[2]), logits.shape[1]))
@@ -49,7 +54,7 @@ class _CE2dFn(torch.autograd.Function):
         if not ctx.size_average:
             acc = torch.ones_like(acc)
         d = ops.ce2d_bwd(logits, target, weight, ctx.ignore_index, acc, _gscale(go))
-        return d, None, None, None, None
+        return d, None, None, None, None, None
 
 
 class _NLLState(nn.Module):
@@ -67,6 +72,12 @@ class CrossEntropyLoss2d(nn.Module):
         self.nll_loss = _NLLState(weight)
         self.size_average = size_average
         self.ignore_index = ignore_index
+        self._dist_group = False
+
+    def set_process_group(self, group=None):
+        """data-parallel runs: normalise by the GLOBAL sum of class weights (mcd_b200/parallel.py)."""
+        import torch.distributed as dist
+        self._dist_group = group if (dist.is_initialized() and dist.get_world_size(group) > 1) else False
 
     def forward(self, inputs, targets):
         logits = _logits(inputs)
@@ -75,7 +86,8 @@ class CrossEntropyLoss2d(nn.Module):
         w = self.nll_loss.weight
         if w is not None and w.device != logits.device:
             w = w.to(logits.device)
-        return _CE2dFn.apply(logits, targets.contiguous(), w, self.ignore_index, self.size_average)
+        return _CE2dFn.apply(logits, targets.contiguous(), w, self.ignore_index, self.size_average,
+                             self._dist_group)
 
 
 class _Diff2dFn(torch.autograd.Function):

@@ -313,3 +313,59 @@ def sgd_step(param, grad, buf, lr, momentum, weight_decay, first_step):
     abi.check(abi.lib().mcd_sgd_step(_p(param), _p(grad), _p(buf), param.numel(), float(lr),
                                      float(momentum), float(weight_decay), int(first_step), _dev(param),
                                      _stream(param)), "sgd_step")
+
+
+# ---- measurement hook (bench.py roofline) ---------------------------------------------------------
+class ConvProfiler:
+    """Records a CUDA-event pair on the launching stream around every convolution call made while active and
+    groups durations / algorithmic FLOPs (2 * N*Ho*Wo * Cout * Cin * R*S) by kernel family."""
+    active = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        ConvProfiler.active = self
+        return self
+
+    def __exit__(self, *a):
+        ConvProfiler.active = None
+
+    def summary(self):
+        fam = {}
+        for name, flop, e0, e1 in self.records:
+            f = fam.setdefault(name, {"ms": 0.0, "flop": 0.0, "n": 0})
+            f["ms"] += e0.elapsed_time(e1)
+            f["flop"] += flop
+            f["n"] += 1
+        return fam
+
+
+def _profiled(name, g, fn):
+    prof = ConvProfiler.active
+    if prof is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    flop = 2.0 * g.N * g.Ho * g.Wo * g.Cout * g.Cin * g.R * g.S
+    prof.records.append((name, flop, e0, e1))
+    return out
+
+
+_conv_fprop_raw, _conv_dgrad_raw, _conv_wgrad_raw = conv_fprop, conv_dgrad, conv_wgrad
+
+
+def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):  # noqa: F811
+    return _profiled("conv_fprop_kernel (forward)", g,
+                     lambda: _conv_fprop_raw(x, w_packed, bias, g, planar, want_stats, algo))
+
+
+def conv_dgrad(dy, w_packed_dgrad, g, algo=None):  # noqa: F811
+    return _profiled("conv_fprop_kernel (dgrad)", g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo))
+
+
+def conv_wgrad(x, dy, g, want_dbias=False, algo=None):  # noqa: F811
+    return _profiled("conv_wgrad_kernel (+split-K reduce)", g,
+                     lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo))

@@ -1,0 +1,133 @@
+"""Data-parallel plumbing: one process per GPU, NCCL all-reduce of gradients over NVLink/NVSwitch.
+
+Replaces the reference's single-process nn.DataParallel (models/model_util.py:283-284).  The MCD path shards
+over independent source/target image pairs; the only exchange is the gradient all-reduce before each
+optimiser step, plus a 4-float all-reduce of the cross-entropy normaliser so that the
+loss keeps DataParallel's global `sum w` semantics.
+
+GradSync keeps the gradients of one optimiser in flat fp32 buffers ("buckets", filled in reverse parameter
+order = the order backward produces them).  `param.grad` are views into the buckets, so
+  * zeroing is one memset per bucket,
+  * a bucket is all-reduced (SUM) on a side stream as soon as autograd has accumulated its last gradient,
+    overlapping the remaining dgrad / wgrad kernels,
+  * no gather / scatter copies are needed.
+With world_size == 1 (or no process group) it only provides the flat zeroing.
+Works with any torch.distributed backend (tests run it on gloo with CPU tensors).
+"""
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    __slots__ = ("flat", "params", "pending", "work", "event")
+
+    def __init__(self, flat, params):
+        self.flat, self.params = flat, params
+        self.pending, self.work, self.event = 0, None, None
+
+
+class GradSync:
+    def __init__(self, params, process_group=None, bucket_mb=25):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = 1
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size(process_group)
+        self.armed = False
+        self.buckets = []
+        self._by_param = {}
+        cap = int(bucket_mb * (1 << 20) / 4)
+        cur, cur_n = [], 0
+        for p in reversed(self.params):
+            if cur and cur_n + p.numel() > cap:
+                self._make_bucket(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self._make_bucket(cur)
+        self.cuda = bool(self.params) and self.params[0].is_cuda
+        self.comm_stream = torch.cuda.Stream(self.params[0].device) if (self.cuda and self.world > 1) else None
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    def _make_bucket(self, params):
+        n = sum(p.numel() for p in params)
+        flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+        b = _Bucket(flat, list(params))
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            self._by_param[p] = b
+            off += p.numel()
+        self.buckets.append(b)
+
+    # ---------------------------------------------------------------------------------------------
+    def zero_and_arm(self, armed=True):
+        """zero the flat gradients (re-attaching the views if something replaced .grad) and arm the hooks."""
+        for b in self.buckets:
+            b.flat.zero_()
+            off = 0
+            for p in b.params:
+                g = p.grad
+                if g is None or g.data_ptr() != b.flat.data_ptr() + off * b.flat.element_size():
+                    p.grad = b.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            b.pending, b.work, b.event = len(b.params), None, None
+        self.armed = armed and self.world > 1
+
+    def disarm(self):
+        self.armed = False
+
+    def _on_grad_ready(self, p):
+        if not self.armed:
+            return
+        b = self._by_param[p]
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(b.flat.device))
+            with torch.cuda.stream(self.comm_stream):
+                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def wait(self):
+        """all buckets reduced and visible to the compute stream (call before optimizer.step())."""
+        if not self.armed:
+            return
+        for b in self.buckets:
+            if b.pending > 0:          # parameters that received no gradient this phase (e.g. unused decoders)
+                self._launch(b)
+                b.pending = 0
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()
+                b.work = None
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.buckets[0].flat.device).wait_stream(self.comm_stream)
+        self.armed = False
+
+
+def init_from_env(backend=None):
+    """torchrun entry: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend or ("nccl" if torch.cuda.is_available() else "gloo"),
+                                rank=rank, world_size=world)
+    return rank, local, world
+
+
+def allreduce_sum_(t, group=None):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t

@@ -1,0 +1,100 @@
+"""The MCD iteration (phase A, B, num_k x C) as one callable, mirroring the reference's inline loop bodies
+(adapt_trainer.py:162-212, adapt_mfnet_trainer.py:181-235) over the drop-in modules.
+
+Differences from the reference loop that do NOT change any result (SURVEY.md section 8a16 "legal savings"):
+  * phase B back-propagates only into the classifiers: the reference also back-propagates through G and then
+    throws those gradients away (`optimizer_g.zero_grad()` at adapt_trainer.py:205 before any use), which is
+    ~1 TFLOP of dead work per image pair.  `exact_reference_backward=True` restores the dead work.
+  * gradients live in flat per-optimizer buffers (one memset instead of ~250 zero_grad kernels); with
+    world_size > 1 the buffers are all-reduced with NCCL in buckets overlapped with wgrad (parallel.GradSync).
+  * losses stay on the device; `.item()` is the caller's choice (the reference syncs every phase).
+"""
+import torch
+
+from . import parallel
+
+
+class MCDStep:
+    """method 'MCD' (early fusion): models = (model_g, model_f1, model_f2);
+    method 'MFNet': models = (model_g_3ch, model_g_1ch, model_f1, model_f2)."""
+
+    def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
+                 num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
+                 bucket_mb=25):
+        from models.model_util import get_optimizer
+        self.mfnet = len(models) == 4
+        self.gens = list(models[:-2])
+        self.f1, self.f2 = models[-2], models[-1]
+        self.criterion, self.criterion_d = criterion, criterion_d
+        self.num_k, self.mult = num_k, num_multiply_d_loss
+        self.exact = exact_reference_backward
+        g_params = [p for m in self.gens for p in m.parameters() if p.requires_grad]
+        f_params = [p for p in self.f1.parameters() if p.requires_grad]
+        if self.f2 is not self.f1:
+            f_params += [p for p in self.f2.parameters() if p.requires_grad]
+        self.optimizer_g = get_optimizer(g_params, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.optimizer_f = get_optimizer(f_params, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        self.sync_g = parallel.GradSync(g_params, process_group, bucket_mb)
+        self.sync_f = parallel.GradSync(f_params, process_group, bucket_mb)
+        self.world = self.sync_g.world
+        if self.world > 1 and hasattr(criterion, "set_process_group"):
+            criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
+
+    # -- forward helpers -------------------------------------------------------------------------
+    def _gen(self, x):
+        if not self.mfnet:
+            return (self.gens[0](x),)
+        # adapt_mfnet_trainer.py:186-187: RGB stream and HHA stream
+        return self.gens[0](x[:, :3]), self.gens[1](x[:, 3:])
+
+    def _heads(self, feats):
+        return self.f1(*feats), self.f2(*feats)
+
+    def _disc(self, o1, o2):
+        d = self.criterion_d(o1, o2)
+        return d / self.world if self.world > 1 else d   # SUM all-reduce of gradients => global mean
+
+    def __call__(self, src_imgs, src_lbls, tgt_imgs):
+        crit = self.criterion
+        # ---- A: source supervised; updates G, F1, F2
+        self.sync_g.zero_and_arm(), self.sync_f.zero_and_arm()
+        o1, o2 = self._heads(self._gen(src_imgs))
+        loss = crit(o1, src_lbls) + crit(o2, src_lbls)
+        loss.backward()
+        c_loss = loss.detach()
+        self.sync_g.wait(), self.sync_f.wait()
+        self.optimizer_g.step(), self.optimizer_f.step()
+        # ---- B: classifiers maximise the discrepancy on target; only optimizer_f steps
+        self.sync_f.zero_and_arm()
+        if self.exact:
+            self.sync_g.zero_and_arm(armed=False)
+            feats_s, feats_t = self._gen(src_imgs), self._gen(tgt_imgs)
+        else:
+            with torch.no_grad():
+                feats_s, feats_t = self._gen(src_imgs), self._gen(tgt_imgs)
+        o1, o2 = self._heads(feats_s)
+        loss = crit(o1, src_lbls) + crit(o2, src_lbls)
+        t1, t2 = self._heads(feats_t)
+        loss = loss - self._disc(t1, t2)
+        loss.backward()
+        self.sync_f.wait()
+        self.optimizer_f.step()
+        # ---- C x num_k: generator minimises the discrepancy; only optimizer_g steps
+        #      (classifier gradients of this phase are zeroed before use at adapt_trainer.py:163-164, so unless
+        #       exact_reference_backward is set they are not computed at all)
+        self.sync_f.disarm()
+        if not self.exact:
+            for p in self.sync_f.params:
+                p.requires_grad_(False)
+        for _ in range(self.num_k):
+            self.sync_g.zero_and_arm()
+            t1, t2 = self._heads(self._gen(tgt_imgs))
+            loss = self._disc(t1, t2) * self.mult
+            loss.backward()
+            self.sync_g.wait()
+            self.optimizer_g.step()
+        if not self.exact:
+            for p in self.sync_f.params:
+                p.requires_grad_(True)
+        d_loss = loss.detach() * (self.world / self.num_k)
+        return c_loss, d_loss

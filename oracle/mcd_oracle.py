@@ -75,6 +75,52 @@ def trunk_spec(name="drn_d_38", prefix="base."):
     return spec
 
 
+# ------------------------------------------------------------------------------------------------
+# storage emulation: `with storage(torch.bfloat16):` makes the oracle round tensors to the CUDA path's STORAGE
+# precision at the CUDA path's storage points (network input, conv weights, conv outputs, unit outputs,
+# full-resolution logits; gradients of the same tensors on the way back) while all arithmetic stays fp32.
+# DRN-D-38 with train-mode BatchNorm at random weights amplifies any perturbation by ~1.2x per layer, so two
+# correct implementations with different storage precision drift apart by ~20 % after 41 layers; this mode
+# separates that inherent drift from kernel errors (see DESIGN.md "numerics").
+_STORAGE = None
+
+
+class storage:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _STORAGE
+        self.prev, _STORAGE = _STORAGE, self.dtype
+
+    def __exit__(self, *a):
+        global _STORAGE
+        _STORAGE = self.prev
+
+
+class _Round(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype, fwd, bwd):
+        ctx.dtype, ctx.bwd = dtype, bwd
+        return x.to(dtype).to(x.dtype) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(ctx.dtype).to(g.dtype) if ctx.bwd else g), None, None, None
+
+
+def _q(x):      # stored activation: value and its gradient are rounded
+    return x if _STORAGE is None else _Round.apply(x, _STORAGE, True, True)
+
+
+def _qw(w):     # packed weight shadow: rounded copy, fp32 gradient
+    return w if _STORAGE is None else _Round.apply(w, _STORAGE, True, False)
+
+
+def _qg(x):     # fp32 score map whose incoming gradient is stored rounded
+    return x if _STORAGE is None else _Round.apply(x, _STORAGE, False, True)
+
+
 def _bn(sd, key, x, train):
     if train:
         sd[key + ".num_batches_tracked"] += 1
@@ -86,34 +132,45 @@ def _bn_train_flag(train, fix_bn):
     return train and not fix_bn
 
 
+def unit_forward(sd, unit, x, bn_train=True, taps=None):
+    """one DRN unit of trunk_spec(): conv+BN+ReLU (models/drn.py:195-205) or BasicBlock (models/drn.py:43-59)."""
+    if unit[0] == "cbr":
+        _, kc, kb, stride, dil, pad = unit
+        y = _q(F.conv2d(x, _qw(sd[kc + ".weight"]), None, stride, pad, dil))
+        out = _q(F.relu(_bn(sd, kb, y, bn_train)))
+        if taps is not None:
+            taps[kc + ":conv"] = y
+            taps[kc + ":out"] = out
+        return out
+    _, p, stride, d1, d2, ds = unit
+    y1 = _q(F.conv2d(x, _qw(sd[p + ".conv1.weight"]), None, stride, d1, d1))
+    o = _q(F.relu(_bn(sd, p + ".bn1", y1, bn_train)))
+    y2 = _q(F.conv2d(o, _qw(sd[p + ".conv2.weight"]), None, 1, d2, d2))
+    o = _bn(sd, p + ".bn2", y2, bn_train)
+    res = x
+    if ds:
+        yd = _q(F.conv2d(x, _qw(sd[p + ".downsample.0.weight"]), None, stride, 0, 1))
+        res = _bn(sd, p + ".downsample.1", yd, bn_train)
+    out = _q(F.relu(o + res))
+    if taps is not None:
+        taps[p + ".conv1:conv"] = y1
+        taps[p + ".conv2:conv"] = y2
+        taps[p + ":out"] = out
+    return out
+
+
+def unit_key(unit):
+    return (unit[1] if unit[0] == "cbr" else unit[1]) + ":out"
+
+
 def trunk_forward(sd, x, name="drn_d_38", prefix="base.", train=True, fix_bn=False, taps=None):
     """returns [h0..h8]; `taps` (dict) collects every conv output / unit output by key."""
     bn_train = _bn_train_flag(train, fix_bn)
     outs = []
+    x = _q(x)
     for stage in trunk_spec(name, prefix):
         for unit in stage:
-            if unit[0] == "cbr":
-                _, kc, kb, stride, dil, pad = unit
-                y = F.conv2d(x, sd[kc + ".weight"], None, stride, pad, dil)
-                x = F.relu(_bn(sd, kb, y, bn_train))
-                if taps is not None:
-                    taps[kc + ":conv"] = y
-                    taps[kc + ":out"] = x
-            else:
-                _, p, stride, d1, d2, ds = unit
-                y1 = F.conv2d(x, sd[p + ".conv1.weight"], None, stride, d1, d1)
-                o = F.relu(_bn(sd, p + ".bn1", y1, bn_train))
-                y2 = F.conv2d(o, sd[p + ".conv2.weight"], None, 1, d2, d2)
-                o = _bn(sd, p + ".bn2", y2, bn_train)
-                res = x
-                if ds:
-                    res = _bn(sd, p + ".downsample.1",
-                              F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0, 1), bn_train)
-                x = F.relu(o + res)
-                if taps is not None:
-                    taps[p + ".conv1:conv"] = y1
-                    taps[p + ".conv2:conv"] = y2
-                    taps[p + ":out"] = x
+            x = unit_forward(sd, unit, x, bn_train, taps)
         outs.append(x)
     return outs
 
@@ -121,12 +178,12 @@ def trunk_forward(sd, x, name="drn_d_38", prefix="base.", train=True, fix_bn=Fal
 def seg_base_forward(sd, x, name="drn_d_38", train=True, fix_bn=False, taps=None):
     """DRNSegBase.forward: trunk + 1x1 seg conv (models/dilated_fcn.py:238-244)."""
     h = trunk_forward(sd, x, name, "base.", train, fix_bn, taps)[-1]
-    return F.conv2d(h, sd["seg.weight"], sd["seg.bias"])
+    return _qg(F.conv2d(h, _qw(sd["seg.weight"]), sd["seg.bias"]))
 
 
 def up_head(w, x):
     """ConvTranspose2d(C,C,16,stride=8,padding=4,groups=C,bias=False) (models/dilated_fcn.py:357-366)."""
-    return F.conv_transpose2d(x, w, None, stride=8, padding=4, groups=x.shape[1])
+    return _q(F.conv_transpose2d(x, w, None, stride=8, padding=4, groups=x.shape[1]))
 
 
 def head_forward(sd, feats, kind="single"):
@@ -140,17 +197,17 @@ def head_forward(sd, feats, kind="single"):
 
 
 def bilinear_up(x, s):
-    return F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+    return _q(F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False))
 
 
 def three_layer_decoder(sd, p, x, train=True, fix_bn=False):
     """ThreeLayerDecoder: CBR 3x3 -> CBR 1x1 -> conv 1x1, all with bias (models/dilated_fcn.py:632-658)."""
     bn_train = _bn_train_flag(train, fix_bn)
-    x = F.relu(_bn(sd, p + ".cbr1.bn", F.conv2d(x, sd[p + ".cbr1.conv.weight"], sd[p + ".cbr1.conv.bias"],
-                                                padding=1), bn_train))
-    x = F.relu(_bn(sd, p + ".cbr2.bn", F.conv2d(x, sd[p + ".cbr2.conv.weight"], sd[p + ".cbr2.conv.bias"]),
-                   bn_train))
-    return F.conv2d(x, sd[p + ".conv3.weight"], sd[p + ".conv3.bias"])
+    y = _q(F.conv2d(x, _qw(sd[p + ".cbr1.conv.weight"]), sd[p + ".cbr1.conv.bias"], padding=1))
+    x = _q(F.relu(_bn(sd, p + ".cbr1.bn", y, bn_train)))
+    y = _q(F.conv2d(x, _qw(sd[p + ".cbr2.conv.weight"]), sd[p + ".cbr2.conv.bias"]))
+    x = _q(F.relu(_bn(sd, p + ".cbr2.bn", y, bn_train)))
+    return _qg(F.conv2d(x, _qw(sd[p + ".conv3.weight"]), sd[p + ".conv3.bias"]))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,9 +254,9 @@ def triple_depth(sd, hd, train=True, fix_bn=False):
 
 
 def triple_boundary(sd, hd):
-    h1 = bilinear_up(F.conv2d(hd["h2"], sd["conv1.weight"], sd["conv1.bias"]), 2)
-    h2 = bilinear_up(F.conv2d(hd["h3"], sd["conv2.weight"], sd["conv2.bias"]), 4)
-    h3 = bilinear_up(F.conv2d(hd["h8"], sd["conv3.weight"], sd["conv3.bias"]), 8)
+    h1 = bilinear_up(_qg(F.conv2d(hd["h2"], _qw(sd["conv1.weight"]), sd["conv1.bias"])), 2)
+    h2 = bilinear_up(_qg(F.conv2d(hd["h3"], _qw(sd["conv2.weight"]), sd["conv2.bias"])), 4)
+    h3 = bilinear_up(_qg(F.conv2d(hd["h8"], _qw(sd["conv3.weight"]), sd["conv3.bias"])), 8)
     return (torch.sigmoid(h1) + torch.sigmoid(h2) + torch.sigmoid(h3)) / 3
 
 
