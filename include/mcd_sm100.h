@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 3
+#define MCD_ABI_VERSION 4
 
 enum {
   MCD_OK = 0,
@@ -85,6 +85,15 @@ int mcd_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, 
  * dst holds rows*R*S*kc_pad bf16 where rows = (mode ? Cin : Cout), kc_pad = round_up(mode ? Cout : Cin, 64). */
 int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int mode,
                     int device, void* stream);
+
+/* Row-packed pack for thin-channel convolutions (channel stride Cs in {8,16}, S*Cs <= 64, dilation 1):
+ * dst[rows][R][64] with k = s*Cs + c.  mode 0 = fprop (rows = Cout, Cs = Cin_s), 1 = dgrad (rows = Cin,
+ * Cs = Cout_s, flipped filter).  Which pack a convolution wants: mcd_conv2d_pack_kind(). */
+int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs,
+                         int mode, int device, void* stream);
+/* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows() layout for (geometry, pass, algo);
+ * pass: 0 = fprop, 1 = dgrad. */
+int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
 
 /* ---- convolution (nn.Conv2d: models/drn.py:21-23,126-131,171-205; dilated_fcn.py:226-232,632-658,821-823) */
 /* y = conv(x, w) (+ bias).  If `stats` != NULL (fp32 [2*Cout], caller-zeroed) the kernel also

@@ -60,7 +60,10 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
   int planar = y_layout == MCD_OUT_PLANAR_F32;
   bool umma = use_umma(algo, umma_problem_supported(p), &rc);
   if (rc != MCD_OK) return rc;
-  if (umma) return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, p, st);
+  if (umma) {
+    if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p);   // w_packed is then the mcd_pack_weight_rows layout
+    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, p, st);
+  }
   rc = launch_direct_problem(x_nhwc, w_packed, bias, y, planar, p, st);
   if (rc != MCD_OK) return rc;
   if (stats) {
@@ -80,6 +83,10 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
   cudaStream_t st = (cudaStream_t)stream;
   TapProblem p[4];
   int np = plan_dgrad(*g, p);
+  if (algo != MCD_ALGO_DIRECT && packed_dgrad_ok(*g) && umma_problem_supported(p[0])) {
+    plan_dgrad_packed(*g, p[0]);                          // w_packed_dgrad: mcd_pack_weight_rows mode 1
+    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, p[0], st);
+  }
   bool any_empty = false;
   for (int i = 0; i < np; ++i) any_empty |= (p[i].ntaps == 0);
   if (any_empty) {
@@ -95,6 +102,12 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
     if (rc != MCD_OK) return rc;
   }
   return MCD_OK;
+}
+
+int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo) {
+  if (!g || algo == MCD_ALGO_DIRECT) return 0;
+  if (g->stride > 2) return 0;
+  return pass == 0 ? (packed_fprop_ok(*g) ? 1 : 0) : (packed_dgrad_ok(*g) ? 1 : 0);
 }
 
 size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo) {

@@ -37,6 +37,7 @@ struct TapProblem {
   int Hd, Wd;          // destination geometry
   int Cd_s;            // destination channel stride (nhwc) / channel count (planar)
   int rows;            // GEMM-N: produced channels
+  int packed;          // 1: row-packed thin-channel problem (one "tap" = one filter row, see plan_*_packed)
   int ntaps;
   Tap taps[kMaxTaps];
 };
@@ -49,7 +50,7 @@ inline void plan_fprop(const mcd_conv_geom& g, TapProblem& p) {
   p.N = g.N; p.Hs = g.H; p.Ws = g.W; p.Cs_src = g.Cin_s; p.Kc = g.Cin;
   p.kc_pad = (g.Cin + 63) / 64 * 64; p.T_total = g.R * g.S;
   p.Ht = g.Ho; p.Wt = g.Wo; p.smul = g.stride; p.omul = 1; p.oh0 = 0; p.ow0 = 0;
-  p.Hd = g.Ho; p.Wd = g.Wo; p.Cd_s = g.Cout_s; p.rows = g.Cout; p.ntaps = 0;
+  p.Hd = g.Ho; p.Wd = g.Wo; p.Cd_s = g.Cout_s; p.rows = g.Cout; p.ntaps = 0; p.packed = 0;
   for (int r = 0; r < g.R; ++r)
     for (int s = 0; s < g.S; ++s) {
       Tap& t = p.taps[p.ntaps++];
@@ -74,7 +75,7 @@ inline int plan_dgrad(const mcd_conv_geom& g, TapProblem* p) {
       q.kc_pad = (g.Cout + 63) / 64 * 64; q.T_total = g.R * g.S;
       q.Ht = (g.H - ph + st - 1) / st; q.Wt = (g.W - pw + st - 1) / st;
       q.smul = 1; q.omul = st; q.oh0 = ph; q.ow0 = pw;
-      q.Hd = g.H; q.Wd = g.W; q.Cd_s = g.Cin_s; q.rows = g.Cin; q.ntaps = 0;
+      q.Hd = g.H; q.Wd = g.W; q.Cd_s = g.Cin_s; q.rows = g.Cin; q.ntaps = 0; q.packed = 0;
       for (int r = 0; r < g.R; ++r)
         for (int s = 0; s < g.S; ++s) {
           int nh = ph + g.pad - r * g.dil, nw = pw + g.pad - s * g.dil;
@@ -87,6 +88,44 @@ inline int plan_dgrad(const mcd_conv_geom& g, TapProblem* p) {
         }
     }
   return np;
+}
+
+// ---- row-packed thin-channel problems ---------------------------------------------------------------
+// For Cs_src in {8,16} and dilation 1 the S taps of one filter row read S*Cs_src CONTIGUOUS bf16 of the NHWC
+// image (pixels w*stride-pad .. +S-1), at most 64 elements.  One 64-element window per output pixel is then one
+// K=64 chunk: layer0 (7x7, 6->16 ch: 7 chunks instead of 49), layer1 (3x3, 16->16: 3 instead of 9), layer2
+// (3x3 stride 2, 16->32) and the dgrad of layer1 (models/drn.py:126-136).  The window is fetched by a 3-D TMA
+// map {W*Cs elements, rows, N} whose inner coordinate is an ELEMENT offset, so image-border windows are
+// zero-filled by TMA exactly like the padded convolution.
+//   tap t = filter row r:  dh/mdh/map as usual (row parity for stride 2), mdw = window start in PIXELS
+//   relative to wt*smul, wk = r.  Packed weights: [rows][R][64] with k = s*Cs_src + c.
+inline bool packed_fprop_ok(const mcd_conv_geom& g) {
+  return g.dil == 1 && (g.Cin_s == 8 || g.Cin_s == 16) && g.S * g.Cin_s <= 64 && g.stride <= 2 && g.R <= kMaxTaps;
+}
+inline void plan_fprop_packed(const mcd_conv_geom& g, TapProblem& p) {
+  p.N = g.N; p.Hs = g.H; p.Ws = g.W; p.Cs_src = g.Cin_s; p.Kc = 64; p.kc_pad = 64; p.T_total = g.R;
+  p.Ht = g.Ho; p.Wt = g.Wo; p.smul = g.stride; p.omul = 1; p.oh0 = 0; p.ow0 = 0;
+  p.Hd = g.Ho; p.Wd = g.Wo; p.Cd_s = g.Cout_s; p.rows = g.Cout; p.ntaps = 0; p.packed = 1;
+  for (int r = 0; r < g.R; ++r) {
+    Tap& t = p.taps[p.ntaps++];
+    t.dh = (int16_t)(r - g.pad); t.dw = (int16_t)(-g.pad); t.wk = (int16_t)r;
+    t.map = (int16_t)posmod(t.dh, g.stride);
+    t.mdh = (int16_t)floordiv(t.dh, g.stride); t.mdw = t.dw; t.pad0 = t.pad1 = 0;
+  }
+}
+// dgrad of a stride-1 conv whose dy is thin: windows over dy, flipped filter rows.
+inline bool packed_dgrad_ok(const mcd_conv_geom& g) {
+  return g.dil == 1 && g.stride == 1 && (g.Cout_s == 8 || g.Cout_s == 16) && g.S * g.Cout_s <= 64;
+}
+inline void plan_dgrad_packed(const mcd_conv_geom& g, TapProblem& q) {
+  q.N = g.N; q.Hs = g.Ho; q.Ws = g.Wo; q.Cs_src = g.Cout_s; q.Kc = 64; q.kc_pad = 64; q.T_total = g.R;
+  q.Ht = g.H; q.Wt = g.W; q.smul = 1; q.omul = 1; q.oh0 = 0; q.ow0 = 0;
+  q.Hd = g.H; q.Wd = g.W; q.Cd_s = g.Cin_s; q.rows = g.Cin; q.ntaps = 0; q.packed = 1;
+  for (int rp = 0; rp < g.R; ++rp) {          // rp = R-1-r
+    Tap& t = q.taps[q.ntaps++];
+    t.dh = (int16_t)(rp - (g.R - 1 - g.pad)); t.dw = (int16_t)(-(g.S - 1 - g.pad)); t.wk = (int16_t)rp;
+    t.map = 0; t.mdh = t.dh; t.mdw = t.dw; t.pad0 = t.pad1 = 0;
+  }
 }
 
 }  // namespace mcd

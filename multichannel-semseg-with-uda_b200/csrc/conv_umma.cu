@@ -34,6 +34,8 @@ struct FpropArgs {
   int rows;               // produced channels
   int omul, oh0, ow0, Hd, Wd, Cd_s;
   int planar;
+  int packed;             // row-packed thin-channel mode: A = TWp window loads of THp rows each
+  int cs_src, smul;       // packed: source channel stride, W stride of the convolution
   const float* bias;
   float* stats;
   void* out;
@@ -45,13 +47,14 @@ struct FpropCfg {
   static constexpr int A_BYTES = 128 * 128;          // 128 pixels x 64 ch bf16
   static constexpr int B_BYTES = BN * 128;           // BN rows x 64 ch bf16
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 4));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int MIN_CTAS = BN <= 32 ? 2 : 1;   // thin tiles: overlap prologue/epilogue across CTAs
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, FpropCfg<BN>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
   using Cfg = FpropCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -98,7 +101,14 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
+          if (a.packed) {
+            // TW columns x TH rows, column-major in the tile: one {64 elements, TH rows} window box per column
+            for (int j = 0; j < a.TW; ++j)
+              tma_load_3d(sa + j * a.TH * 128, amap, &full_bar[stage],
+                          ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
+          } else {
+            tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
+          }
           tma_load_2d(sb, &maps.b, &full_bar[stage], tap.wk * a.kc_pad + kc * 64, n0);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -129,7 +139,8 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     // ---- epilogue: thread = one output pixel (TMEM lane), loop over 32-channel column chunks ----
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int ht = th0 + m / a.TW, wt = tw0 + m % a.TW;
+    const int ht = a.packed ? th0 + m % a.TH : th0 + m / a.TW;
+    const int wt = a.packed ? tw0 + m / a.TH : tw0 + m % a.TW;
     const bool pvalid = ht < a.Ht && wt < a.Wt;
     const int hd = ht * a.omul + a.oh0, wd = wt * a.omul + a.ow0;
     mbar_wait(tmem_full_bar, 0);
@@ -212,6 +223,7 @@ struct WgradArgs {
   int ksplit;                        // pixel-tile ranges
   int T;                             // taps
   int CoutP, CinP;                   // padded workspace dims (multiples of 128 / BN)
+  int packed, cs_src, smul;          // row-packed thin-channel mode (tap = filter row, K-window loads)
   float* ws;                         // [ksplit][T][CoutP][CinP]
   Tap taps[kMaxTaps];
 };
@@ -276,13 +288,25 @@ conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        if (a.packed) {
+          // pixel order inside the tile is column-major (TW columns of TH rows) for both operands
+          for (int j = 0; j < a.TW; ++j) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-          tma_load_4d(sa + i * Cfg::KPIX * 128, &maps.b, &full_bar[stage], co0 + i * 64, tw0, th0, n_img);
+            for (int i = 0; i < 2; ++i)
+              tma_load_4d(sa + i * Cfg::KPIX * 128 + j * a.TH * 128, &maps.b, &full_bar[stage],
+                          co0 + i * 64, tw0 + j, th0, n_img);
+            tma_load_3d(sb + j * a.TH * 128, xmap, &full_bar[stage],
+                        ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
+          }
+        } else {
 #pragma unroll
-        for (int i = 0; i < BN / 64; ++i)
-          tma_load_4d(sb + i * Cfg::KPIX * 128, xmap, &full_bar[stage], ci0 + i * 64, tw0 + tap.mdw,
-                      th0 + tap.mdh, n_img);
+          for (int i = 0; i < 2; ++i)
+            tma_load_4d(sa + i * Cfg::KPIX * 128, &maps.b, &full_bar[stage], co0 + i * 64, tw0, th0, n_img);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+            tma_load_4d(sb + i * Cfg::KPIX * 128, xmap, &full_bar[stage], ci0 + i * 64, tw0 + tap.mdw,
+                        th0 + tap.mdh, n_img);
+        }
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -351,6 +375,22 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+// packed: ws[split][r][co][s*Cs + c]  ->  dw[co][c][r][s]
+__global__ void wgrad_reduce_packed_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit,
+                                           int R, int S, int Cs, int CoutP, int Cout, int Cin) {
+  int64_t total = (int64_t)Cout * Cin * R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int sx = (int)(i % S);
+    int r = (int)((i / S) % R);
+    int c = (int)((i / ((int64_t)S * R)) % Cin);
+    int co = (int)(i / ((int64_t)S * R * Cin));
+    float acc = 0.f;
+    for (int k = 0; k < ksplit; ++k) acc += ws[(((int64_t)k * R + r) * CoutP + co) * 64 + sx * Cs + c];
+    dw[i] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 
@@ -393,6 +433,39 @@ static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W,
     return MCD_E_CUDA;
   }
   return MCD_OK;
+}
+
+// 3-D map {W*Cs elements, rows of parity ph (step st), N} for the row-packed window loads
+static int encode_rows_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cs, int st, int ph,
+                           int box_h) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
+  int Hsub = (H - ph + st - 1) / st;
+  if (Hsub <= 0) Hsub = 1;
+  cuuint64_t dims[3] = {(cuuint64_t)W * Cs, (cuuint64_t)Hsub, (cuuint64_t)N};
+  cuuint64_t strides[2] = {(cuuint64_t)st * W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const char* p = reinterpret_cast<const char*>(base) + (int64_t)ph * W * Cs * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<char*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rows N=%d H=%d W=%d Cs=%d st=%d box_h=%d) failed: %d", N, H, W, Cs, st,
+              box_h, (int)r);
+    return MCD_E_CUDA;
+  }
+  return MCD_OK;
+}
+
+// packed tiles: TW columns of TH rows, TH >= 8 so that every column box starts on a 1024-byte swizzle atom
+static void pick_tile_packed(int Ht, int Wt, int npix, int* TH, int* TW) {
+  int64_t best = -1;
+  for (int th = npix; th >= 8; th >>= 1) {
+    int tw = npix / th;
+    int64_t area = (int64_t)((Ht + th - 1) / th) * th * ((Wt + tw - 1) / tw) * tw;
+    if (best < 0 || area < best) { best = area; *TH = th; *TW = tw; }
+  }
 }
 
 static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t kdim, int box_rows) {
@@ -452,7 +525,9 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   FpropArgs a;
   memset(&a, 0, sizeof(a));
   a.N = p.N; a.Ht = p.Ht; a.Wt = p.Wt;
-  pick_tile(p.Ht, p.Wt, 128, &a.TH, &a.TW);
+  a.packed = p.packed; a.cs_src = p.Cs_src; a.smul = p.smul;
+  if (p.packed) pick_tile_packed(p.Ht, p.Wt, 128, &a.TH, &a.TW);
+  else pick_tile(p.Ht, p.Wt, 128, &a.TH, &a.TW);
   a.tiles_h = (p.Ht + a.TH - 1) / a.TH; a.tiles_w = (p.Wt + a.TW - 1) / a.TW;
   a.kchunks = (p.Kc + 63) / 64; a.ntaps = p.ntaps; a.kc_pad = p.kc_pad;
   a.rows = p.rows; a.omul = p.omul; a.oh0 = p.oh0; a.ow0 = p.ow0; a.Hd = p.Hd; a.Wd = p.Wd;
@@ -464,35 +539,47 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   int stp = p.smul;
   bool used[4] = {false, false, false, false};
   for (int t = 0; t < p.ntaps; ++t) used[p.taps[t].map] = true;
-  for (int ph = 0; ph < stp; ++ph)
-    for (int pw = 0; pw < stp; ++pw) {
-      int id = ph * stp + pw;
-      if (!used[id]) continue;
-      int rc = encode_act_map(&maps.a[id], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, stp, ph, pw, a.TW, a.TH);
+  if (p.packed) {
+    for (int ph = 0; ph < stp; ++ph) {
+      if (!used[ph]) continue;
+      int rc = encode_rows_map(&maps.a[ph], src, p.N, p.Hs, p.Ws, p.Cs_src, stp, ph, a.TH);
       if (rc != MCD_OK) return rc;
     }
+  } else {
+    for (int ph = 0; ph < stp; ++ph)
+      for (int pw = 0; pw < stp; ++pw) {
+        int id = ph * stp + pw;
+        if (!used[id]) continue;
+        int rc = encode_act_map(&maps.a[id], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, stp, ph, pw, a.TW, a.TH);
+        if (rc != MCD_OK) return rc;
+      }
+  }
   if (!used[0]) maps.a[0] = maps.a[p.taps[0].map];  // keep the prefetch target valid
 
   int ncover = planar ? p.rows : p.Cd_s;
-  int BN = ncover > 128 ? 256 : (ncover > 64 ? 128 : 64);
+  int BN = ncover > 128 ? 256 : (ncover > 64 ? 128 : (ncover > 32 ? 64 : (ncover > 16 ? 32 : 16)));
   int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, BN);
   if (rc != MCD_OK) return rc;
   dim3 grid((unsigned)(p.N * a.tiles_h * a.tiles_w), (unsigned)((ncover + BN - 1) / BN));
   if (BN == 256) return launch_fprop_bn<256>(maps, a, grid, st);
   if (BN == 128) return launch_fprop_bn<128>(maps, a, grid, st);
-  return launch_fprop_bn<64>(maps, a, grid, st);
+  if (BN == 64) return launch_fprop_bn<64>(maps, a, grid, st);
+  if (BN == 32) return launch_fprop_bn<32>(maps, a, grid, st);
+  return launch_fprop_bn<16>(maps, a, grid, st);
 }
 
 static int wgrad_bn(const mcd_conv_geom& g) { return g.Cin > 128 ? 256 : (g.Cin > 64 ? 128 : 64); }
 
 static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
                         int* ntiles, int* ksplit) {
-  *BN = wgrad_bn(g);
+  const bool packed = packed_fprop_ok(g);
+  *BN = packed ? 64 : wgrad_bn(g);
   *CoutP = round_up(g.Cout, 128);
-  *CinP = round_up(g.Cin, *BN);
-  pick_tile(g.Ho, g.Wo, 64, TH, TW);
+  *CinP = packed ? 64 : round_up(g.Cin, *BN);
+  if (packed) pick_tile_packed(g.Ho, g.Wo, 64, TH, TW);
+  else pick_tile(g.Ho, g.Wo, 64, TH, TW);
   *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
-  int base = (*CoutP / 128) * (*CinP / *BN) * g.R * g.S;
+  int base = (*CoutP / 128) * (*CinP / *BN) * g.R * (packed ? 1 : g.S);
   int ks = (2 * 148 + base - 1) / base;
   ks = max(1, min(ks, *ntiles));
   ks = min(ks, 64);
@@ -502,7 +589,7 @@ static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, 
 size_t umma_wgrad_workspace(const mcd_conv_geom& g) {
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
-  return sizeof(float) * (size_t)ksplit * g.R * g.S * CoutP * CinP;
+  return sizeof(float) * (size_t)ksplit * g.R * (packed_fprop_ok(g) ? 1 : g.S) * CoutP * CinP;
 }
 
 template <int BN>
@@ -525,16 +612,19 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   if (g.R * g.S > kMaxTaps) { set_error("umma wgrad: too many taps"); return MCD_E_INVALID; }
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
-  size_t need = sizeof(float) * (size_t)ksplit * g.R * g.S * CoutP * CinP;
+  const bool packed = packed_fprop_ok(g);
+  size_t need = sizeof(float) * (size_t)ksplit * g.R * (packed ? 1 : g.S) * CoutP * CinP;
   if (ws_bytes < need || !ws) { set_error("umma wgrad: workspace %zu < %zu", ws_bytes, need); return MCD_E_WORKSPACE; }
 
   TapProblem p;
-  plan_fprop(g, p);
+  if (packed) plan_fprop_packed(g, p);
+  else plan_fprop(g, p);
   WgradArgs a;
   memset(&a, 0, sizeof(a));
   a.N = g.N; a.TH = TH; a.TW = TW;
   a.tiles_h = (g.Ho + TH - 1) / TH; a.tiles_w = (g.Wo + TW - 1) / TW;
-  a.ntiles = ntiles; a.ksplit = ksplit; a.T = g.R * g.S; a.CoutP = CoutP; a.CinP = CinP;
+  a.ntiles = ntiles; a.ksplit = ksplit; a.T = p.ntaps; a.CoutP = CoutP; a.CinP = CinP;
+  a.packed = packed; a.cs_src = g.Cin_s; a.smul = g.stride;
   a.ws = reinterpret_cast<float*>(ws);
   for (int t = 0; t < p.ntaps; ++t) a.taps[t] = p.taps[t];
 
@@ -542,15 +632,24 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   memset(&maps, 0, sizeof(maps));
   bool used[4] = {false, false, false, false};
   for (int t = 0; t < p.ntaps; ++t) used[p.taps[t].map] = true;
-  for (int ph = 0; ph < g.stride; ++ph)
-    for (int pw = 0; pw < g.stride; ++pw) {
-      int id = ph * g.stride + pw;
-      if (!used[id]) continue;
-      int rc = encode_act_map(&maps.a[id], x, g.N, g.H, g.W, g.Cin, g.Cin_s, g.stride, ph, pw, TW, TH);
+  if (packed) {
+    for (int ph = 0; ph < g.stride; ++ph) {
+      if (!used[ph]) continue;
+      int rc = encode_rows_map(&maps.a[ph], x, g.N, g.H, g.W, g.Cin_s, g.stride, ph, TH);
       if (rc != MCD_OK) return rc;
     }
+  } else {
+    for (int ph = 0; ph < g.stride; ++ph)
+      for (int pw = 0; pw < g.stride; ++pw) {
+        int id = ph * g.stride + pw;
+        if (!used[id]) continue;
+        int rc = encode_act_map(&maps.a[id], x, g.N, g.H, g.W, g.Cin, g.Cin_s, g.stride, ph, pw, TW, TH);
+        if (rc != MCD_OK) return rc;
+      }
+  }
   if (!used[0]) maps.a[0] = maps.a[p.taps[0].map];
-  int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, TW, TH);
+  // dY map: packed mode loads one column (box width 1) at a time to get column-major pixel order
+  int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, packed ? 1 : TW, TH);
   if (rc != MCD_OK) return rc;
 
   dim3 grid((unsigned)(CoutP / 128), (unsigned)(CinP / BN), (unsigned)(a.T * ksplit));
@@ -559,9 +658,12 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   else rc = launch_wgrad_bn<64>(maps, a, grid, st);
   if (rc != MCD_OK) return rc;
 
-  int64_t total = (int64_t)g.Cout * g.Cin * a.T;
+  int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
   int rgrid = (int)min64((total + 255) / 256, 148 * 8);
-  wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout, g.Cin);
+  if (packed)
+    wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, g.R, g.S, g.Cin_s, CoutP, g.Cout, g.Cin);
+  else
+    wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout, g.Cin);
   return check_launch("wgrad_reduce");
 }
 

@@ -71,6 +71,30 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// row-packed variants (conv_plan.h): dst[row][r][k], k = s*Cs + c, 64 elements per filter row
+// mode 0: row = co, value w[co][c][r][s]            (c < Cin)
+// mode 1: row = ci, value w[c][ci][R-1-r][S-1-s]    (c < Cout)   - flipped filter for dgrad
+__global__ void pack_weight_rows_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+                                        int Cout, int Cin, int R, int S, int Cs, int mode, int rows) {
+  int64_t total = (int64_t)rows * R * 64;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % 64);
+    int r = (int)((i / 64) % R);
+    int row = (int)(i / (64 * (int64_t)R));
+    int s = k / Cs, c = k % Cs;
+    float v = 0.f;
+    if (s < S) {
+      if (mode == 0) {
+        if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s];
+      } else {
+        if (c < Cout) v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
+      }
+    }
+    dst[i] = f2bf(v);
+  }
+}
+
 }  // namespace mcd
 
 using namespace mcd;
@@ -115,6 +139,21 @@ int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, in
   pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
                                                               R, S, mode, rows, kc_pad);
   return check_launch("pack_weight");
+}
+
+int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs,
+                         int mode, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(w_oihw && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, "pack_weight_rows: bad arguments");
+  MCD_REQUIRE(mode == 0 || mode == 1, "pack_weight_rows: mode must be 0 (fprop) or 1 (dgrad)");
+  MCD_REQUIRE((Cs == 8 || Cs == 16) && S * Cs <= 64 && Cs >= (mode ? Cout : Cin),
+              "pack_weight_rows: channel stride %d / S=%d not packable", Cs, S);
+  int rows = mode ? Cin : Cout;
+  int64_t total = (int64_t)rows * R * 64;
+  int grid = (int)min64((total + 255) / 256, 148 * 16);
+  pack_weight_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
+                                                                   R, S, Cs, mode, rows);
+  return check_launch("pack_weight_rows");
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, mod, planar, want_stats):
         g = mod.geom(x.shape)
-        y, stats = ops.conv_fprop(x, mod.packed(0), bias, g, planar=planar, want_stats=want_stats)
+        y, stats = ops.conv_fprop(x, mod.packed(0, g), bias, g, planar=planar, want_stats=want_stats)
         ctx.mod, ctx.g, ctx.planar = mod, g, planar
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x)
@@ -43,7 +43,7 @@ class _ConvFn(torch.autograd.Function):
         dy = ops.to_nhwc(dy) if ctx.planar else _as_nhwc_grad(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.conv_dgrad(dy, mod.packed(1), g)
+            dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = ops.conv_wgrad(x, dy, g, want_dbias=ctx.has_bias and ctx.needs_input_grad[2])
         return dx, dw, db, None, None, None
@@ -73,14 +73,16 @@ class Conv2d(nn.Conv2d):
             self._geoms[key] = g
         return g
 
-    def packed(self, mode):
-        """bf16 packed shadow of the fp32 master weight, refreshed when the parameter changes."""
+    def packed(self, mode, g):
+        """bf16 packed shadow of the fp32 master weight (layout chosen by the library for geometry `g`),
+        refreshed when the parameter changes (optimizer step, load_state_dict, .to())."""
         w = self.weight
         tag = (w._version, w.data_ptr())
-        hit = self._packs.get(mode)
+        key = ops.pack_key(g, mode)
+        hit = self._packs.get(key)
         if hit is None or hit[0] != tag:
-            hit = (tag, ops.pack_weight(w, mode))
-            self._packs[mode] = hit
+            hit = (tag, ops.pack_weight_for(w, g, mode))
+            self._packs[key] = hit
         return hit[1]
 
     def conv_raw(self, x, want_stats=False):

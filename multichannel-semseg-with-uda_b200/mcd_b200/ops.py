@@ -95,6 +95,29 @@ def pack_weight(w, mode):
     return out
 
 
+def pack_weight_for(w, g, mode, algo=None):
+    """the packed bf16 weight the kernels want for geometry `g` (mode 0 fprop / 1 dgrad): the standard
+    [rows][taps][kc_pad] pack or, for thin-channel layers on the tcgen05 path, the row-packed [rows][R][64]."""
+    algo = _algo if algo is None else algo
+    kind = int(abi.lib().mcd_conv2d_pack_kind(ctypes.byref(g), mode, algo))
+    if kind == 0:
+        return pack_weight(w, mode)
+    w = w.detach()
+    assert w.dtype == F32 and w.is_contiguous()
+    co, ci, r, s = w.shape
+    rows, cs = (ci, g.Cout_s) if mode else (co, g.Cin_s)
+    out = torch.empty((rows, r, 64), dtype=BF16, device=w.device)
+    abi.check(abi.lib().mcd_pack_weight_rows(_p(w), _p(out), co, ci, r, s, cs, mode, _dev(w), _stream(w)),
+              "pack_weight_rows")
+    return out
+
+
+def pack_key(g, mode, algo=None):
+    algo = _algo if algo is None else algo
+    kind = int(abi.lib().mcd_conv2d_pack_kind(ctypes.byref(g), mode, algo))
+    return (mode, kind, (g.Cout_s if mode else g.Cin_s) if kind else 0)
+
+
 # ---- convolution -------------------------------------------------------------------------------
 def conv_geom(x_shape, cin, cout, r, s, stride, dil, pad, cout_s=None):
     n, cin_s, h, w = x_shape

@@ -37,6 +37,9 @@ CONV_SHAPES = [
     (2, 30, 40, 32, 64, 3, 2, 1, 1),
     (2, 30, 40, 32, 64, 1, 2, 1, 0),
     (1, 31, 37, 64, 128, 3, 2, 1, 1),   # odd sizes
+    (1, 33, 45, 3, 16, 7, 1, 1, 3),     # RGB-only first conv, ragged tiles (row-packed path)
+    (2, 24, 40, 16, 16, 3, 1, 1, 1),
+    (1, 37, 50, 16, 32, 3, 2, 1, 1),    # row-packed stride 2, odd sizes
 ]
 
 
@@ -58,7 +61,7 @@ def test_conv_fprop(cuda_dev, shape, algo_name):
     ref = F.conv2d(x, wt, None, stride, pad, dil)
     xn = ops.to_nhwc(x)
     g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
-    y, stats = ops.conv_fprop(xn, ops.pack_weight(wt, 0), None, g, want_stats=True, algo=algo)
+    y, stats = ops.conv_fprop(xn, ops.pack_weight_for(wt, g, 0, algo), None, g, want_stats=True, algo=algo)
     torch.cuda.synchronize()
     got = ops.to_nchw_f32(y, cout)
     assert rel_err(got, ref) < 1e-2
@@ -77,7 +80,7 @@ def test_conv_fprop_planar_bias(cuda_dev, algo_name):
     ref = F.conv2d(x, wt, bias)
     xn = ops.to_nhwc(x)
     g = ops.conv_geom(xn.shape, 512, 41, 1, 1, 1, 1, 0)
-    y, _ = ops.conv_fprop(xn, ops.pack_weight(wt, 0), bias, g, planar=True, algo=algo)
+    y, _ = ops.conv_fprop(xn, ops.pack_weight_for(wt, g, 0, algo), bias, g, planar=True, algo=algo)
     assert y.shape == ref.shape and y.dtype == F32
     assert rel_err(y, ref) < 2e-3
 
@@ -97,7 +100,7 @@ def test_conv_dgrad_wgrad(cuda_dev, shape, algo_name):
     dx_ref, dw_ref = torch.autograd.grad(ref, (x, wt), dy)
     xn, dyn = ops.to_nhwc(x.detach()), ops.to_nhwc(dy)
     g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
-    dx = ops.conv_dgrad(dyn, ops.pack_weight(wt.detach(), 1), g, algo=algo)
+    dx = ops.conv_dgrad(dyn, ops.pack_weight_for(wt.detach(), g, 1, algo), g, algo=algo)
     dw, db = ops.conv_wgrad(xn, dyn, g, want_dbias=True, algo=algo)
     torch.cuda.synchronize()
     assert rel_err(ops.to_nchw_f32(dx, cin), dx_ref) < 1e-2
