@@ -87,27 +87,29 @@ deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
   }
 }
 
-// dw[c][kh][kw] = sum_{n,ih,iw} x[n,c,ih,iw] * dout[n,c,8ih-4+kh,8iw-4+kw]
-// grid: (C, 16 kh); block 256 = 16 kw x 16 position lanes.
+// dw[c][kh][kw] += sum_{(n,ih) in this block's chunk} sum_iw x[n,c,ih,iw] * dout[n,c,8ih-4+kh,8iw-4+kw]
+// grid: (C*16 [c,kh], nsplit chunks of (n,ih) rows); block 256 = 16 kw x 16 iw lanes; dw is pre-zeroed.
 __global__ void __launch_bounds__(256)
 deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ x,
                          float* __restrict__ dw, int N, int C, int h, int wd) {
   __shared__ float red[16][17];
-  const int c = blockIdx.x, kh = blockIdx.y;
+  const int c = blockIdx.x >> 4, kh = blockIdx.x & 15;
   const int kw = threadIdx.x & 15, pl = threadIdx.x >> 4;
   const int H = h * 8, W = wd * 8;
+  const int rows = N * h;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r_beg = blockIdx.y * per, r_end = min(r_beg + per, rows);
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const __nv_bfloat16* dp = dout + ((int64_t)n * C + c) * H * W;
-    const float* xp = x + ((int64_t)n * C + c) * h * wd;
-    for (int ih = 0; ih < h; ++ih) {
-      const int oh = 8 * ih - 4 + kh;
-      if (oh < 0 || oh >= H) continue;
-      for (int iw = pl; iw < wd; iw += 16) {
-        const int ow = 8 * iw - 4 + kw;
-        if (ow < 0 || ow >= W) continue;
-        acc = fmaf(xp[ih * wd + iw], bf2f(dp[(int64_t)oh * W + ow]), acc);
-      }
+  for (int rr = r_beg; rr < r_end; ++rr) {
+    const int n = rr / h, ih = rr % h;
+    const int oh = 8 * ih - 4 + kh;
+    if (oh < 0 || oh >= H) continue;
+    const __nv_bfloat16* dp = dout + (((int64_t)n * C + c) * H + oh) * W;
+    const float* xp = x + (((int64_t)n * C + c) * h + ih) * wd;
+    for (int iw = pl; iw < wd; iw += 16) {
+      const int ow = 8 * iw - 4 + kw;
+      if (ow < 0 || ow >= W) continue;
+      acc = fmaf(xp[iw], bf2f(dp[ow]), acc);
     }
   }
   red[pl][kw] = acc;
@@ -116,7 +118,7 @@ deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) s += red[k][kw];
-    dw[c * 256 + kh * 16 + kw] = s;
+    atomicAdd(dw + c * 256 + kh * 16 + kw, s);
   }
 }
 
@@ -234,7 +236,10 @@ int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* 
     if (rc != MCD_OK) return rc;
   }
   if (dw) {
-    dim3 grid((unsigned)C, 16);
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 256, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("deconv dw memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    int nsplit = min(N * h, 32);
+    dim3 grid((unsigned)(C * 16), (unsigned)nsplit);
     deconv16s8_bwd_dw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, x, dw,
                                                                       N, C, h, w_);
     return check_launch("deconv16s8_bwd_dw");

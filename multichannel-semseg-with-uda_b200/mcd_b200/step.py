@@ -40,6 +40,37 @@ class MCDStep:
         if self.world > 1 and hasattr(criterion, "set_process_group"):
             criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
 
+    # -- CUDA-graph execution ---------------------------------------------------------------------
+    def capture(self, src_imgs, src_lbls, tgt_imgs, warmup=2):
+        """Capture the whole iteration (forward, backward, optimizer steps, weight re-packing) in ONE CUDA
+        graph: the ~3500 kernel launches of an iteration are then replayed without any host work.  Inputs are
+        copied into static buffers by `replay`."""
+        from . import abi
+        assert self.world == 1, "graph capture is single-GPU (NCCL side-stream overlap is launched eagerly)"
+        dev = src_imgs.device
+        self._static = (src_imgs.clone(), src_lbls.clone(), tgt_imgs.clone())
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self(*self._static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = abi.launch_count()
+        with torch.cuda.graph(self.graph):
+            self._static_out = self(*self._static)
+        self.launches_per_replay = abi.launch_count() - n0
+        return self
+
+    def replay(self, src_imgs, src_lbls, tgt_imgs):
+        s, l, t = self._static
+        s.copy_(src_imgs, non_blocking=True)
+        l.copy_(src_lbls, non_blocking=True)
+        t.copy_(tgt_imgs, non_blocking=True)
+        self.graph.replay()
+        return self._static_out
+
     # -- forward helpers -------------------------------------------------------------------------
     def _gen(self, x):
         if not self.mfnet:

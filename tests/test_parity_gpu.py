@@ -5,7 +5,7 @@ tolerances asserted here:
   per-layer activations                  max|a-b| / max|b| <= 2e-2 against fp32; every DRN unit of the real
                                          network is fed the ORACLE's input / upstream gradient, so the number
                                          measures that layer's kernels only
-  per-layer gradients                    relative L2 <= 3e-2 against the oracle with bf16-storage emulation,
+  per-layer gradients                    relative L2 <= 4e-2 against the oracle with bf16-storage emulation,
                                          <= 1.2e-1 against fp32 (ReLU-mask flips, see the comment at the asserts)
   losses (CE, Diff2d, phases A/B/C)      relative <= 1e-3 (C-phase discrepancy <= 5e-3) against fp32
   updated weights after one iteration    max|a-b| / max|b| <= 1e-3
@@ -169,8 +169,8 @@ def test_per_layer_forward_backward_vs_oracle(cuda_dev, size, n):
     # error on that single element and, through the identity shortcut of a BasicBlock, lands un-diluted in dx:
     # element-wise max errors are then O(0.3) for ANY two implementations (measured identically between the
     # fp32 oracle and its own bf16-storage emulation, and between our tcgen05 and CUDA-core kernels).
-    assert worst[1] <= 3e-2, "input gradient vs bf16-storage oracle %.3e" % worst[1]
-    assert worst[2] <= 3e-2, "parameter gradient vs bf16-storage oracle %.3e" % worst[2]
+    assert worst[1] <= 4e-2, "input gradient vs bf16-storage oracle %.3e" % worst[1]
+    assert worst[2] <= 4e-2, "parameter gradient vs bf16-storage oracle %.3e" % worst[2]
     assert worst[3] <= 0.12 and worst[4] <= 0.12, "fp32 relative-L2 %.3e %.3e" % (worst[3], worst[4])
     assert max(e_seg) <= 2e-2 and max(e_head) <= 2e-2
 
