@@ -7,55 +7,64 @@
 
 namespace mcd {
 
+// Thread layout shared by all kernels: a thread owns ONE 16-byte channel vector (8 channels) and walks over
+// pixel rows, so per-channel coefficients live in registers and a warp reads 512 contiguous bytes.
+//   vpr = Cs/8 vectors per pixel row, rpi = 256/vpr pixel rows per block iteration.
+
 // ---- per-channel reductions ------------------------------------------------------------------
 // MODE 0: stats      : acc0 = sum y, acc1 = sum y^2
 // MODE 1: bwd reduce : g = dz * (z > 0 | !relu); acc0 = sum g, acc1 = sum g*xhat(y), acc2 = sum g*xhat(res)
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
                  const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ res,
                  const float* __restrict__ mean, const float* __restrict__ rstd,
                  const float* __restrict__ res_mean, const float* __restrict__ res_rstd, int relu,
                  float* __restrict__ out, int64_t P, int C, int Cs) {
   extern __shared__ float sh[];  // 3 * Cs
-  const int vpr = Cs >> 3;                 // 16-byte vectors per pixel row
-  const int rpi = 256 / vpr;               // pixel rows per block iteration
+  const int vpr = Cs >> 3;
+  const int rpi = 256 / vpr;
   const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
   const bool active = pr < rpi;
+  const bool dual = MODE == 1 && res_mean != nullptr;
   for (int i = threadIdx.x; i < 3 * Cs; i += 256) sh[i] = 0.f;
   __syncthreads();
   float a0[8], a1[8], a2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a0[k] = a1[k] = a2[k] = 0.f;
-  float mu[8], rs[8], mu2[8], rs2[8];
   const int c0 = cv * 8;
-  if (MODE == 1) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      int c = min(c0 + k, C - 1);
-      mu[k] = mean[c]; rs[k] = rstd[c];
-      mu2[k] = res_mean ? res_mean[c] : 0.f; rs2[k] = res_mean ? res_rstd[c] : 0.f;
-    }
-  }
   if (active) {
-    for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += (int64_t)gridDim.x * rpi) {
+    float mu[8], rs[8], mu2[8], rs2[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int c = min(c0 + k, C - 1);
+        mu[k] = mean[c]; rs[k] = rstd[c];
+        mu2[k] = dual ? res_mean[c] : 0.f; rs2[k] = dual ? res_rstd[c] : 0.f;
+      }
+    }
+    const int64_t step = (int64_t)gridDim.x * rpi;
+    for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
       const int64_t off = p * Cs + c0;
       float fy[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + off), fy);
+      const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
       if (MODE == 0) {
+        unpack8(vy, fy);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a0[k] += fy[k]; a1[k] = fmaf(fy[k], fy[k], a1[k]); }
       } else {
+        const uint4 vd = *reinterpret_cast<const uint4*>(dz + off);
+        uint4 vz = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
+        if (relu) vz = *reinterpret_cast<const uint4*>(z + off);
+        if (dual) vr = *reinterpret_cast<const uint4*>(res + off);
         float fd[8], fz[8], fr[8];
-        unpack8(*reinterpret_cast<const uint4*>(dz + off), fd);
-        if (relu) unpack8(*reinterpret_cast<const uint4*>(z + off), fz);
-        if (res_mean) unpack8(*reinterpret_cast<const uint4*>(res + off), fr);
+        unpack8(vy, fy); unpack8(vd, fd); unpack8(vz, fz); unpack8(vr, fr);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float g = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
+          const float g = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
           a0[k] += g;
           a1[k] = fmaf(g, (fy[k] - mu[k]) * rs[k], a1[k]);
-          if (res_mean) a2[k] = fmaf(g, (fr[k] - mu2[k]) * rs2[k], a2[k]);
+          if (dual) a2[k] = fmaf(g, (fr[k] - mu2[k]) * rs2[k], a2[k]);
         }
       }
     }
@@ -63,14 +72,14 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
     for (int k = 0; k < 8; ++k) {
       atomicAdd(&sh[c0 + k], a0[k]);
       atomicAdd(&sh[Cs + c0 + k], a1[k]);
-      if (MODE == 1 && res_mean) atomicAdd(&sh[2 * Cs + c0 + k], a2[k]);
+      if (dual) atomicAdd(&sh[2 * Cs + c0 + k], a2[k]);
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += 256) {
     atomicAdd(out + c, sh[c]);
     atomicAdd(out + C + c, sh[Cs + c]);
-    if (MODE == 1 && res_mean) atomicAdd(out + 2 * C + c, sh[2 * Cs + c]);
+    if (dual) atomicAdd(out + 2 * C + c, sh[2 * Cs + c]);
   }
 }
 
@@ -105,42 +114,40 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, double invP,
   save_rstd[c] = rstd;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
-                __nv_bfloat16* __restrict__ z, int64_t nvec, int vpr) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vpr) * 8;
-    float f[8], sc[8], sf[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
-    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + c0));
-    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
-    *reinterpret_cast<float4*>(sf) = __ldg(reinterpret_cast<const float4*>(shift + c0));
-    *reinterpret_cast<float4*>(sf + 4) = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+                __nv_bfloat16* __restrict__ z, int64_t P, int Cs) {
+  const int vpr = Cs >> 3;
+  const int rpi = 256 / vpr;
+  const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
+  if (pr >= rpi) return;
+  const int c0 = cv * 8;
+  float sc[8], sf[8], rc[8], rf[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = scale[c0 + k]; sf[k] = shift[c0 + k];
+    rc[k] = rscale ? rscale[c0 + k] : 1.f; rf[k] = rscale ? rshift[c0 + k] : 0.f;
+  }
+  const int64_t step = (int64_t)gridDim.x * rpi;
+  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
+    const int64_t off = p * Cs + c0;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + off), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
     if (res) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + i * 8), r);
-      if (rscale) {
-        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(rscale + c0));
-        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(rscale + c0 + 4));
-        *reinterpret_cast<float4*>(sf) = __ldg(reinterpret_cast<const float4*>(rshift + c0));
-        *reinterpret_cast<float4*>(sf + 4) = __ldg(reinterpret_cast<const float4*>(rshift + c0 + 4));
+      unpack8(*reinterpret_cast<const uint4*>(res + off), r);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], sc[k], sf[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += r[k];
-      }
+      for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], rc[k], rf[k]);
     }
     if (relu) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
     }
-    *reinterpret_cast<uint4*>(z + i * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(z + off) = pack8(f);
   }
 }
 
@@ -149,13 +156,29 @@ struct BwdBranch {
   int training;
 };
 
-__global__ void __launch_bounds__(256)
+// dy = A*g + B*y + K with per-channel A = gamma*rstd, B = -A*m2*rstd, K = -A*m1 - B*mean  (training;
+// m1 = sum(g)/P, m2 = sum(g*xhat)/P) or B = K = 0 (eval).
+__device__ __forceinline__ void bwd_coeffs(const BwdBranch& b, const float* sums, int sum_off, int C, int c,
+                                           float invP, float* A, float* B, float* K) {
+  const float a = b.gamma[c] * b.rstd[c];
+  *A = a;
+  if (b.training) {
+    const float m1 = sums[c] * invP, m2 = sums[sum_off + c] * invP;
+    const float bb = -a * m2 * b.rstd[c];
+    *B = bb;
+    *K = -a * m1 - bb * b.mean[c];
+  } else {
+    *B = 0.f; *K = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                     const __nv_bfloat16* __restrict__ y, BwdBranch b1, const float* __restrict__ sums,
                     int relu, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, const __nv_bfloat16* __restrict__ res, BwdBranch b2,
                     __nv_bfloat16* __restrict__ dres, float* __restrict__ dres_gamma,
-                    float* __restrict__ dres_beta, float invP, int64_t nvec, int vpr, int C) {
+                    float* __restrict__ dres_beta, float invP, int64_t P, int Cs, int C) {
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (dgamma) dgamma[c] = sums[C + c];
@@ -164,54 +187,55 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       if (dres_beta) dres_beta[c] = sums[c];
     }
   }
+  const int vpr = Cs >> 3;
+  const int rpi = 256 / vpr;
+  const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
+  if (pr >= rpi) return;
+  const int c0 = cv * 8;
   const bool has_res_bn = dres && b2.gamma;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vpr) * 8;
+  float A1[8], B1[8], K1[8], A2[8], B2[8], K2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    bwd_coeffs(b1, sums, C, C, c0 + k, invP, &A1[k], &B1[k], &K1[k]);
+    if (has_res_bn) bwd_coeffs(b2, sums, 2 * C, C, c0 + k, invP, &A2[k], &B2[k], &K2[k]);
+    else { A2[k] = B2[k] = K2[k] = 0.f; }
+  }
+  const int64_t step = (int64_t)gridDim.x * rpi;
+  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
+    const int64_t off = p * Cs + c0;
     float fd[8], fz[8], fy[8], g[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(dz + i * 8), fd);
-    if (relu) unpack8(*reinterpret_cast<const uint4*>(z + i * 8), fz);
-    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), fy);
+    unpack8(*reinterpret_cast<const uint4*>(dz + off), fd);
+    unpack8(*reinterpret_cast<const uint4*>(y + off), fy);
+    if (relu) unpack8(*reinterpret_cast<const uint4*>(z + off), fz);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
       g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
-      const float gm = __ldg(b1.gamma + c), rs = __ldg(b1.rstd + c);
-      if (b1.training) {
-        const float xh = (fy[k] - __ldg(b1.mean + c)) * rs;
-        o[k] = gm * rs * (g[k] - __ldg(sums + c) * invP - xh * __ldg(sums + C + c) * invP);
-      } else {
-        o[k] = gm * rs * g[k];
-      }
+      o[k] = fmaf(A1[k], g[k], fmaf(B1[k], fy[k], K1[k]));
     }
-    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+    *reinterpret_cast<uint4*>(dy + off) = pack8(o);
     if (dres) {
       if (has_res_bn) {
         float fr[8];
-        unpack8(*reinterpret_cast<const uint4*>(res + i * 8), fr);
+        unpack8(*reinterpret_cast<const uint4*>(res + off), fr);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int c = c0 + k;
-          const float gm = __ldg(b2.gamma + c), rs = __ldg(b2.rstd + c);
-          if (b2.training) {
-            const float xh = (fr[k] - __ldg(b2.mean + c)) * rs;
-            o[k] = gm * rs * (g[k] - __ldg(sums + c) * invP - xh * __ldg(sums + 2 * C + c) * invP);
-          } else {
-            o[k] = gm * rs * g[k];
-          }
-        }
-        *reinterpret_cast<uint4*>(dres + i * 8) = pack8(o);
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(A2[k], g[k], fmaf(B2[k], fr[k], K2[k]));
+        *reinterpret_cast<uint4*>(dres + off) = pack8(o);
       } else {
-        *reinterpret_cast<uint4*>(dres + i * 8) = pack8(g);
+        *reinterpret_cast<uint4*>(dres + off) = pack8(g);
       }
     }
   }
 }
 
+static inline int rows_grid(int64_t P, int Cs, int rows_per_thread, int max_blocks) {
+  int rpi = 256 / (Cs / 8);
+  int64_t g = (P + (int64_t)rpi * rows_per_thread - 1) / ((int64_t)rpi * rows_per_thread);
+  if (g < 1) g = 1;
+  return (int)(g < max_blocks ? g : max_blocks);
+}
+
 int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaStream_t st) {
-  int vpr = Cs / 8, rpi = 256 / vpr;
-  int grid = (int)min64((P + rpi * 4 - 1) / (rpi * 4), 148 * 8);
-  grid = max(grid, 1);
+  int grid = rows_grid(P, Cs, 8, 148 * 2);
   bn_reduce_kernel<0><<<grid, 256, 3 * Cs * sizeof(float), st>>>(
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stats, P,
       C, Cs);
@@ -254,11 +278,11 @@ int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, con
   MCD_REQUIRE(y_nhwc && scale && shift && z_nhwc && P > 0, "bn_apply: bad arguments");
   MCD_REQUIRE(Cs == C && C % 8 == 0, "bn_apply: needs dense channels, C %% 8 == 0 (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!rscale || (res_nhwc && rshift), "bn_apply: residual affine without residual");
-  int64_t nvec = P * (Cs / 8);
-  int grid = (int)min64((nvec + 255) / 256, 148 * 16);
+  MCD_REQUIRE(Cs <= 2048, "bn_apply: channel stride %d unsupported", Cs);
+  int grid = rows_grid(P, Cs, 4, 148 * 8);
   bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, scale, shift, (const __nv_bfloat16*)res_nhwc, rscale, rshift, relu,
-      (__nv_bfloat16*)z_nhwc, nvec, Cs / 8);
+      (__nv_bfloat16*)z_nhwc, P, Cs);
   return check_launch("bn_apply");
 }
 
@@ -271,9 +295,7 @@ int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhw
   MCD_REQUIRE(!relu || z_nhwc, "bn_bwd_reduce: relu needs z");
   MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_bwd_reduce: needs dense channels (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!res_mean || (res_nhwc && res_rstd), "bn_bwd_reduce: residual stats without residual");
-  int vpr = Cs / 8, rpi = 256 / vpr;
-  int grid = (int)min64((P + rpi * 4 - 1) / (rpi * 4), 148 * 8);
-  grid = max(grid, 1);
+  int grid = rows_grid(P, Cs, 8, 148 * 2);
   bn_reduce_kernel<1><<<grid, 256, 3 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc,
       (const __nv_bfloat16*)res_nhwc, mean, rstd, res_mean, res_rstd, relu, sums, P, C, Cs);
@@ -295,12 +317,12 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
               "bn_bwd_apply: incomplete residual branch");
   BwdBranch b1{gamma, mean, rstd, training};
   BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
-  int64_t nvec = P * (Cs / 8);
-  int grid = (int)min64((nvec + 255) / 256, 148 * 16);
+  MCD_REQUIRE(Cs <= 2048, "bn_bwd_apply: channel stride %d unsupported", Cs);
+  int grid = rows_grid(P, Cs, 4, 148 * 8);
   bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc, (const __nv_bfloat16*)y_nhwc, b1, sums,
       relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, (const __nv_bfloat16*)res_nhwc, b2,
-      (__nv_bfloat16*)dres_nhwc, dres_gamma, dres_beta, (float)(1.0 / (double)P), nvec, Cs / 8, C);
+      (__nv_bfloat16*)dres_nhwc, dres_gamma, dres_beta, (float)(1.0 / (double)P), P, Cs, C);
   return check_launch("bn_bwd_apply");
 }
 

@@ -361,18 +361,26 @@ conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
 }
 
 // dw[co][ci][r][s] = sum_split ws[split][t][co][ci]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit,
-                                    int T, int CoutP, int CinP, int Cout, int Cin) {
-  int64_t total = (int64_t)Cout * Cin * T;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int ci = (int)(i % Cin);
-    int co = (int)((i / Cin) % Cout);
-    int t = (int)(i / ((int64_t)Cin * Cout));
-    float s = 0.f;
-    for (int k = 0; k < ksplit; ++k) s += ws[(((int64_t)k * T + t) * CoutP + co) * CinP + ci];
-    dw[((int64_t)co * Cin + ci) * T + t] = s;
+// block = one co x 64 ci: coalesced reads along ci, transpose through smem, contiguous 64*T-float write.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit, int T, int CoutP,
+                    int CinP, int Cout, int Cin) {
+  extern __shared__ float tile[];  // [64][T]
+  const int co = blockIdx.x, ci0 = blockIdx.y * 64;
+  const int nci = min(64, Cin - ci0);
+  for (int idx = threadIdx.x; idx < 64 * T; idx += blockDim.x) {
+    const int t = idx >> 6, cil = idx & 63;
+    float acc = 0.f;
+    if (cil < nci) {
+      const float* p = ws + ((int64_t)t * CoutP + co) * CinP + ci0 + cil;
+      const int64_t kstride = (int64_t)T * CoutP * CinP;
+      for (int k = 0; k < ksplit; ++k) acc += p[k * kstride];
+    }
+    tile[cil * T + t] = acc;
   }
+  __syncthreads();
+  float* o = dw + ((int64_t)co * Cin + ci0) * T;
+  for (int j = threadIdx.x; j < nci * T; j += blockDim.x) o[j] = tile[j];
 }
 
 // packed: ws[split][r][co][s*Cs + c]  ->  dw[co][c][r][s]
@@ -663,7 +671,11 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   if (packed)
     wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, g.R, g.S, g.Cin_s, CoutP, g.Cout, g.Cin);
   else
-    wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout, g.Cin);
+  {
+    dim3 rg((unsigned)g.Cout, (unsigned)((g.Cin + 63) / 64));
+    wgrad_reduce_kernel<<<rg, 256, sizeof(float) * 64 * a.T, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout,
+                                                                   g.Cin);
+  }
   return check_launch("wgrad_reduce");
 }
 
