@@ -118,7 +118,8 @@ int mcd_bn_stats(const void* y_nhwc, float* stats, int64_t P, int C, int Cs, int
 /* training: mean/var from stats (count = P), writes scale/shift (fp32 [C] each), save_mean,
  * save_rstd, and updates running_mean / running_var (unbiased) with `momentum`.
  * eval (training == 0): scale/shift from running stats, save_* = running mean / rstd.
- * num_batches_tracked (int64 scalar, may be NULL) is incremented in training mode. */
+ * num_batches_tracked (int64 scalar, may be NULL) is incremented by `training` in training mode
+ * (training = k > 1 folds k identical batches: pass momentum' = 1-(1-momentum)^k). */
 int mcd_bn_finalize(const float* stats, int64_t P, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float momentum, float eps,
                     int training, float* scale, float* shift, float* save_mean, float* save_rstd,

@@ -92,7 +92,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, double invP,
                                    int C) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (c == 0 && training && nbt) *nbt += 1;
+  if (c == 0 && training && nbt) *nbt += training;   // training = number of (identical) batches folded in
   float mean, var;
   if (training) {
     double m = (double)stats[c] * invP;

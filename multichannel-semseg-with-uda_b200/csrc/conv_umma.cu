@@ -360,6 +360,123 @@ conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad of the row-packed thin-channel layers (layer0/1/2: Cout <= 64, R <= 7 filter rows).
+// One CTA owns a range of 64-pixel tiles and ALL filter rows: per tile it loads the dY tile once (A, one
+// 64-channel atom, MN-major) and the R shifted K-windows of X (B_r), and issues R accumulating MMAs
+// (M=64 co, N=64 window elements) into R TMEM accumulators.  8 TMA issues + 4R MMAs per tile instead of
+// 3 TMA issues per (tile, row) in the generic kernel; the producer lane is no longer the bottleneck.
+struct WgradRowsArgs {
+  int tiles_h, tiles_w, TH, TW, ntiles, nsplit;
+  int R, cs_src, smul, stages, tmem_cols;
+  float* ws;                         // [nsplit][R][64 co][64 k]
+  Tap taps[8];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_wgrad_rows_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ WgradRowsArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int stage_bytes = (1 + a.R) * 8192;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + a.stages;
+  uint64_t* tmem_full_bar = empty_bar + a.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int per = (a.ntiles + a.nsplit - 1) / a.nsplit;
+  const int tile_beg = split * per;
+  const int ksteps = max(min(tile_beg + per, a.ntiles) - tile_beg, 0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int tw_i = tile_beg % a.tiles_w, th_i = (tile_beg / a.tiles_w) % a.tiles_h,
+          n_img = tile_beg / (a.tiles_w * a.tiles_h);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], stage_bytes);
+        for (int j = 0; j < a.TW; ++j) {
+          tma_load_4d(sa + j * a.TH * 128, &maps.b, &full_bar[stage], 0, tw0 + j, th0, n_img);
+          for (int r = 0; r < a.R; ++r)
+            tma_load_3d(sa + (1 + r) * 8192 + j * a.TH * 128, &maps.a[a.taps[r].map], &full_bar[stage],
+                        ((tw0 + j) * a.smul + a.taps[r].mdw) * a.cs_src, th0 + a.taps[r].mdh, n_img);
+        }
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        if (++tw_i == a.tiles_w) { tw_i = 0; if (++th_i == a.tiles_h) { th_i = 0; ++n_img; } }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc_bf16(64, 64, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t adesc = smem_desc_sw128(sa, 8192, 1024);
+        for (int r = 0; r < a.R; ++r) {
+          const uint64_t bdesc = smem_desc_sw128(sa + (1 + r) * 8192, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 64 pixels = 4 x UMMA_K(16) rows of 128 bytes
+            umma_bf16(tmem_base + (uint32_t)(r * 64), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128),
+                      idesc, (ks | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (ks == ksteps - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // M = 64 accumulators live in lanes 0..15 of each 32-lane TMEM sub-partition: row = 16*q + lane
+    const int q = warp & 3;
+    const int co = q * 16 + lane;
+    if (ksteps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    for (int r = 0; r < a.R; ++r) {
+      float* o = a.ws + (((int64_t)split * a.R + r) * 64 + co) * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        if (ksteps > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 64 + c0), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (lane < 16) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
 // dw[co][ci][r][s] = sum_split ws[split][t][co][ci]
 // block = one co x 64 ci: coalesced reads along ci, transpose through smem, contiguous 64*T-float write.
 __global__ void __launch_bounds__(256)
@@ -588,13 +705,76 @@ static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, 
   else pick_tile(g.Ho, g.Wo, 64, TH, TW);
   *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
   int base = (*CoutP / 128) * (*CinP / *BN) * g.R * (packed ? 1 : g.S);
-  int ks = (2 * 148 + base - 1) / base;
+  int ks = (2 * 148) / base;               // at most two full waves of CTAs
   ks = max(1, min(ks, *ntiles));
   ks = min(ks, 64);
   *ksplit = ks;
 }
 
+static bool wgrad_rows_ok(const mcd_conv_geom& g) {
+  return packed_fprop_ok(g) && g.Cout <= 64 && g.R <= 7;
+}
+
+static void wgrad_rows_shape(const mcd_conv_geom& g, int* TH, int* TW, int* ntiles, int* nsplit) {
+  // a single 64-row column per tile halves the TMA issues; accept up to 10 % padded rows for it
+  if (((g.Ho + 63) / 64) * 64 * 10 <= g.Ho * 11) { *TH = 64; *TW = 1; }
+  else pick_tile_packed(g.Ho, g.Wo, 64, TH, TW);
+  *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
+  *nsplit = max(1, min(*ntiles, 148));
+}
+
+static int umma_wgrad_rows(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                           const mcd_conv_geom& g, cudaStream_t st) {
+  int TH, TW, ntiles, nsplit;
+  wgrad_rows_shape(g, &TH, &TW, &ntiles, &nsplit);
+  size_t need = sizeof(float) * (size_t)nsplit * g.R * 64 * 64;
+  if (ws_bytes < need || !ws) { set_error("umma wgrad: workspace %zu < %zu", ws_bytes, need); return MCD_E_WORKSPACE; }
+  TapProblem p;
+  plan_fprop_packed(g, p);
+  WgradRowsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.TH = TH; a.TW = TW; a.tiles_h = (g.Ho + TH - 1) / TH; a.tiles_w = (g.Wo + TW - 1) / TW;
+  a.ntiles = ntiles; a.nsplit = nsplit; a.R = g.R; a.cs_src = g.Cin_s; a.smul = g.stride;
+  const int stage_bytes = (1 + g.R) * 8192;
+  a.stages = min(8, (200 * 1024) / stage_bytes);
+  a.tmem_cols = g.R * 64 <= 64 ? 64 : (g.R * 64 <= 128 ? 128 : (g.R * 64 <= 256 ? 256 : 512));
+  a.ws = reinterpret_cast<float*>(ws);
+  for (int r = 0; r < g.R; ++r) a.taps[r] = p.taps[r];
+  UmmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool used[2] = {false, false};
+  for (int r = 0; r < g.R; ++r) used[p.taps[r].map] = true;
+  for (int ph = 0; ph < g.stride; ++ph) {
+    if (!used[ph]) continue;
+    int rc = encode_rows_map(&maps.a[ph], x, g.N, g.H, g.W, g.Cin_s, g.stride, ph, TH);
+    if (rc != MCD_OK) return rc;
+  }
+  if (!used[0]) maps.a[0] = maps.a[p.taps[0].map];
+  int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, 1, TH);
+  if (rc != MCD_OK) return rc;
+  const int smem_bytes = a.stages * stage_bytes + 1024 + 256;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_rows_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { set_error("wgrad rows smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    attr_bytes = smem_bytes;
+  }
+  conv_umma_wgrad_rows_kernel<<<nsplit, kThreads, smem_bytes, st>>>(maps, a);
+  rc = check_launch("conv_umma_wgrad_rows");
+  if (rc != MCD_OK) return rc;
+  int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
+  int rgrid = (int)min64((total + 255) / 256, 148 * 8);
+  wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, nsplit, g.R, g.S, g.Cin_s, 64, g.Cout, g.Cin);
+  return check_launch("wgrad_reduce");
+}
+
 size_t umma_wgrad_workspace(const mcd_conv_geom& g) {
+  if (wgrad_rows_ok(g)) {
+    int TH, TW, ntiles, nsplit;
+    wgrad_rows_shape(g, &TH, &TW, &ntiles, &nsplit);
+    return sizeof(float) * (size_t)nsplit * g.R * 64 * 64;
+  }
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
   return sizeof(float) * (size_t)ksplit * g.R * (packed_fprop_ok(g) ? 1 : g.S) * CoutP * CinP;
@@ -618,6 +798,7 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
                const mcd_conv_geom& g, cudaStream_t st) {
   if (g.stride != 1 && g.stride != 2) { set_error("umma wgrad: stride %d unsupported", g.stride); return MCD_E_INVALID; }
   if (g.R * g.S > kMaxTaps) { set_error("umma wgrad: too many taps"); return MCD_E_INVALID; }
+  if (wgrad_rows_ok(g)) return umma_wgrad_rows(x, dy, dw, ws, ws_bytes, g, st);
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
   const bool packed = packed_fprop_ok(g);

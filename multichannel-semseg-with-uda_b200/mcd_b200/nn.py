@@ -12,6 +12,32 @@ from . import ops
 
 BF16, F32 = torch.bfloat16, torch.float32
 
+# number of identical forward passes one BatchNorm forward stands for (MCDStep re-uses the phase-B target
+# forward for the first phase-C step): the running statistics then take that many momentum updates at once.
+_bn_repeat = 1
+
+
+class bn_update_repeat:
+    def __init__(self, k):
+        self.k = int(k)
+
+    def __enter__(self):
+        global _bn_repeat
+        self.prev, _bn_repeat = _bn_repeat, self.k
+
+    def __exit__(self, *a):
+        global _bn_repeat
+        _bn_repeat = self.prev
+
+
+def _bn_finalize(bn, stats, count, gamma, beta):
+    if not bn.training:
+        return ops.bn_finalize(None, count, gamma, beta, bn.running_mean, bn.running_var, bn.momentum, bn.eps, 0)
+    k = _bn_repeat
+    momentum = bn.momentum if k == 1 else 1.0 - (1.0 - bn.momentum) ** k
+    return ops.bn_finalize(stats, count, gamma, beta, bn.running_mean, bn.running_var, momentum, bn.eps, k,
+                           bn.num_batches_tracked)
+
 
 def _as_nhwc_grad(dy):
     """Gradients arriving from autograd for an nhwc activation: make them nhwc bf16 again."""
@@ -103,15 +129,10 @@ class _BNActFn(torch.autograd.Function):
         n, c, h, w = y.shape
         count = n * h * w
         training = bn.training
-        aff = ops.bn_finalize(stats if training else None, count, gamma, beta, bn.running_mean,
-                              bn.running_var, bn.momentum, bn.eps, training,
-                              bn.num_batches_tracked if training else None)
+        aff = _bn_finalize(bn, stats, count, gamma, beta)
         res_aff = None
         if res_bn is not None:
-            res_aff = ops.bn_finalize(res_stats if res_bn.training else None, count, res_gamma, res_beta,
-                                      res_bn.running_mean, res_bn.running_var, res_bn.momentum,
-                                      res_bn.eps, res_bn.training,
-                                      res_bn.num_batches_tracked if res_bn.training else None)
+            res_aff = _bn_finalize(res_bn, res_stats, count, res_gamma, res_beta)
         z = ops.bn_apply(y, aff, res, res_aff, relu)
         ctx.relu, ctx.training = relu, training
         ctx.res_training = res_bn.training if res_bn is not None else False

@@ -20,7 +20,7 @@ class MCDStep:
 
     def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
                  num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
-                 bucket_mb=25):
+                 bucket_mb=25, reuse_target_forward=True):
         from models.model_util import get_optimizer
         self.mfnet = len(models) == 4
         self.gens = list(models[:-2])
@@ -28,6 +28,10 @@ class MCDStep:
         self.criterion, self.criterion_d = criterion, criterion_d
         self.num_k, self.mult = num_k, num_multiply_d_loss
         self.exact = exact_reference_backward
+        # G is not updated between the phase-B target forward and the first phase-C forward (only optimizer_f
+        # steps in between, adapt_trainer.py:195-207), so both forwards are the same computation: run it once,
+        # keep its autograd graph for the C[0] backward and let BatchNorm take both momentum updates at once.
+        self.reuse_t = reuse_target_forward and not exact_reference_backward
         g_params = [p for m in self.gens for p in m.parameters() if p.requires_grad]
         f_params = [p for p in self.f1.parameters() if p.requires_grad]
         if self.f2 is not self.f1:
@@ -100,9 +104,19 @@ class MCDStep:
         if self.exact:
             self.sync_g.zero_and_arm(armed=False)
             feats_s, feats_t = self._gen(src_imgs), self._gen(tgt_imgs)
+            feats_t_graph = None
         else:
             with torch.no_grad():
-                feats_s, feats_t = self._gen(src_imgs), self._gen(tgt_imgs)
+                feats_s = self._gen(src_imgs)
+            if self.reuse_t:
+                from .nn import bn_update_repeat
+                with bn_update_repeat(2):
+                    feats_t_graph = self._gen(tgt_imgs)
+                feats_t = tuple(f.detach() for f in feats_t_graph)
+            else:
+                feats_t_graph = None
+                with torch.no_grad():
+                    feats_t = self._gen(tgt_imgs)
         o1, o2 = self._heads(feats_s)
         loss = crit(o1, src_lbls) + crit(o2, src_lbls)
         t1, t2 = self._heads(feats_t)
@@ -117,9 +131,11 @@ class MCDStep:
         if not self.exact:
             for p in self.sync_f.params:
                 p.requires_grad_(False)
-        for _ in range(self.num_k):
+        for k in range(self.num_k):
             self.sync_g.zero_and_arm()
-            t1, t2 = self._heads(self._gen(tgt_imgs))
+            feats = feats_t_graph if (k == 0 and feats_t_graph is not None) else self._gen(tgt_imgs)
+            feats_t_graph = None
+            t1, t2 = self._heads(feats)
             loss = self._disc(t1, t2) * self.mult
             loss.backward()
             self.sync_g.wait()

@@ -336,3 +336,42 @@ def test_tester_argmax_entropy_vs_oracle(cuda_dev):
     assert agree >= 0.99 and agree16 >= 0.99, (agree, agree16)
     assert agree >= agree_oo - 0.003
     assert abs(ent - ent_o) / abs(ent_o) <= 1e-2
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
+    """mcd_b200.step.MCDStep (dead phase-B backward skipped, phase-B target forward re-used for C[0] with folded
+    BatchNorm updates, optional CUDA-graph replay) produces the reference iteration's results."""
+    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+    from mcd_b200.step import MCDStep
+    dev, size, n = cuda_dev, (240, 320), 2
+    G, F1, F2 = _state(dev)
+    models = _models(dev)
+    for m, sd in zip(models, (G, F1, F2)):
+        _load(m, sd)
+        m.train()
+    src, tgt, lbl = _inputs(9, n, size, dev)
+    w = O.class_weight(N_CLASS).to(dev)
+    step = MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=4)
+    iters = 2
+    og, of = O.SGD(), O.SGD()
+    for _ in range(iters):
+        c_o, d_o = O.mcd_step_early(G, F1, F2, src, lbl, tgt, w, og, of, num_k=4)
+    if graph:
+        # capture() runs one warm-up iteration eagerly, then replays: 1 eager + 1 replay = 2 iterations
+        step.capture(src, lbl, tgt, warmup=0)          # capture itself does not execute
+        step(src, lbl, tgt)
+        c, d = step.replay(src, lbl, tgt)
+    else:
+        for _ in range(iters):
+            c, d = step(src, lbl, tgt)
+    torch.cuda.synchronize()
+    assert abs(float(c) - c_o) / abs(c_o) <= 1e-3
+    assert abs(float(d) - d_o) / abs(d_o) <= 5e-3
+    werr = max(nerr(p, G[k]) for k, p in models[0].named_parameters())
+    assert werr <= 2e-3, werr
+    assert nerr(models[1].up.weight, F1["up.weight"]) <= 2e-3
+    # BatchNorm bookkeeping: 7 forward passes per iteration (A, B-src, B-tgt == C0 folded, C1..C3)
+    assert int(models[0].base[5][2].bn2.num_batches_tracked) == 7 * iters == int(G["base.5.2.bn2.num_batches_tracked"])
+    assert nerr(models[0].base[5][2].bn2.running_var, G["base.5.2.bn2.running_var"]) <= 2e-2
+    assert nerr(models[0].base[0][1].running_mean, G["base.0.1.running_mean"]) <= 2e-2
