@@ -375,3 +375,119 @@ def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
     assert int(models[0].base[5][2].bn2.num_batches_tracked) == 7 * iters == int(G["base.5.2.bn2.num_batches_tracked"])
     assert nerr(models[0].base[5][2].bn2.running_var, G["base.5.2.bn2.running_var"]) <= 2e-2
     assert nerr(models[0].base[0][1].running_mean, G["base.0.1.running_mean"]) <= 2e-2
+
+
+# ---- config 3: MFNet two-stream heads (adapt_mfnet_trainer.py:181-235) -------------------------------------
+@pytest.mark.parametrize("method,kind", [("MCD-MFNet-AddFusion", "add"), ("MCD-MFNet-ScoreAddFusion", "scoreadd")])
+def test_mfnet_step_vs_oracle(cuda_dev, method, kind):
+    from loss import CrossEntropyLoss2d, Diff2d
+    dev, size, n = cuda_dev, (240, 320), 2
+    G3 = O.to_device(O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 21), dev)
+    G1 = O.to_device(O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 22), dev)
+    F1 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS, kind), 23), dev)
+    F2 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS, kind), 24), dev)
+    g3, g1, f1, f2 = _models(dev, method)
+    for m, sd in ((g3, G3), (g1, G1), (f1, F1), (f2, F2)):
+        _load(m, sd)
+        m.train()
+    src, tgt, lbl = _inputs(31, n, size, dev)
+    w = O.class_weight(N_CLASS).to(dev)
+    # oracle: B-phase objective CE(src) - Diff2d(tgt) exercises both streams, both heads, both criteria
+    O._req([G3, G1, F1, F2])
+    o3, o1 = O.seg_base_forward(G3, src[:, :3]), O.seg_base_forward(G1, src[:, 3:])
+    p1, p2 = O.head_forward(F1, (o3, o1), kind), O.head_forward(F2, (o3, o1), kind)
+    ce_o = O.ce2d(p1, lbl, w) + O.ce2d(p2, lbl, w)
+    t3, t1 = O.seg_base_forward(G3, tgt[:, :3]), O.seg_base_forward(G1, tgt[:, 3:])
+    d_o = O.diff2d(O.head_forward(F1, (t3, t1), kind), O.head_forward(F2, (t3, t1), kind))
+    _, _, gF1, _ = O._grads(ce_o - d_o, [G3, G1, F1, F2])
+    # ours, written like the trainer
+    outputs_3ch, outputs_1ch = g3(src[:, :3, :, :]), g1(src[:, 3:, :, :])
+    outputs1, outputs2 = f1(outputs_3ch, outputs_1ch), f2(outputs_3ch, outputs_1ch)
+    crit = CrossEntropyLoss2d(w)
+    ce = crit(outputs1, lbl) + crit(outputs2, lbl)
+    t3_, t1_ = g3(tgt[:, :3, :, :]), g1(tgt[:, 3:, :, :])
+    d = Diff2d()(f1(t3_, t1_), f2(t3_, t1_))
+    (ce - d).backward()
+    torch.cuda.synchronize()
+    assert outputs1.shape == (n, N_CLASS, *size)
+    assert abs(float(ce) - float(ce_o)) / abs(float(ce_o)) <= 1e-3
+    assert abs(float(d) - float(d_o)) / abs(float(d_o)) <= 1e-2
+    # head parameters: dW = sum x (x) dout inherits the ~20 % end-to-end drift of the 41-layer features x
+    for k, p in f1.named_parameters():
+        e = float((p.grad - gF1[k]).norm() / gF1[k].norm())
+        assert e <= 0.25, (k, e)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for m in (g3, g1) for p in m.parameters())
+    # the fused ScoreAdd head equals up1(x1) + up2(x2) on identical inputs
+    with torch.no_grad():
+        ref = O.head_forward(F1, (o3.detach(), o1.detach()), kind)
+        got = f1(o3.detach(), o1.detach())
+    assert nerr(got, ref) <= 8e-3
+
+
+# ---- config 4 / 5: triple multitask (adapt_triple_multitask_trainer.py:194-287, tester :117-142) ------------
+def test_triple_multitask_vs_oracle(cuda_dev):
+    import util
+    from loss import CrossEntropyLoss2d, Diff2d
+    from models.model_util import get_triple_multitask_models
+    dev, size, n = cuda_dev, (240, 320), 2
+    E = O.to_device(O.fill_state_dict_(O.init_trunk("drn_d_38", 3, "main_layer"), 31), dev)
+    D = O.to_device(O.fill_state_dict_(O.init_triple_decoder(N_CLASS, 3), 32), dev)
+    w = O.class_weight(N_CLASS).to(dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model_enc, model_dec = get_triple_multitask_models("drn_d_38", 6, N_CLASS,
+                                                           semseg_criterion=CrossEntropyLoss2d(w),
+                                                           discrepancy_criterion=Diff2d())
+    model_enc, model_dec = model_enc.to(dev).train(), model_dec.to(dev).train()
+    _load(model_enc, E)
+    model_dec.load_state_dict({k: v.clone() for k, v in D.items()}, strict=False)   # criterion buffer stays
+    g = torch.Generator().manual_seed(303)
+    src = torch.randn(n, 7, *size, generator=g)
+    src[:, 6] = (torch.rand(n, *size, generator=g) < 0.1).float()
+    tgt = torch.randn(n, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (n, *size), generator=g)
+    src, tgt, lbl = src.to(dev), tgt.to(dev), lbl.to(dev)
+    # oracle (phase A objective + discrepancy)
+    O._req([E, D])
+    src_f, tgt_f = O.encoder_dict(E, src[:, :3]), O.encoder_dict(E, tgt[:, :3])
+    semseg_o, dep_o, bd_o = O.triple_get_loss(D, src_f, lbl, src[:, 3:-1], src[:, -1:], w)
+    tdep_o = torch.nn.functional.mse_loss(O.triple_depth(D, tgt_f), tgt[:, 3:])
+    disc_o = O.diff2d(*O.triple_semseg(D, tgt_f))
+    gE, gD = O._grads(semseg_o + dep_o + bd_o + tdep_o - disc_o, [E, D])
+    # ours, written like the trainer
+    src_rgbs, src_depths, src_boundary = src[:, :3, :, :], src[:, 3:-1, :, :], src[:, -1:, :, :]
+    tgt_rgbs, tgt_depths = tgt[:, :3, :, :], tgt[:, 3:, :, :]
+    src_fet, tgt_fet = model_enc(src_rgbs), model_enc(tgt_rgbs)
+    assert sorted(src_fet) == ["h%d" % i for i in range(9)] and src_fet["h2"].shape[1:] == (32, 120, 160)
+    semseg, dep, bd = model_dec.get_loss(src_fet, lbl, src_depths, src_boundary, separately_returning=True)
+    tdep = model_dec.get_depth_loss(tgt_fet, tgt_depths)
+    disc = model_dec.get_cls_descrepancy(tgt_fet)
+    (semseg + dep + bd + tdep - disc).backward()
+    torch.cuda.synchronize()
+    for name, a, b in (("semseg", semseg, semseg_o), ("depth", dep, dep_o), ("boundary", bd, bd_o),
+                       ("tgt_depth", tdep, tdep_o)):
+        assert abs(float(a) - float(b)) / abs(float(b)) <= 5e-3, (name, float(a), float(b))
+    assert abs(float(disc) - float(disc_o)) / abs(float(disc_o)) <= 2e-2
+    # decoder-side gradients (short path): uncertainty scalars, boundary convs, last decoder layers
+    for k in ("s_semsegcls", "s_deprgr", "s_boundary", "conv3.bias", "conv1.weight", "deprgr_dec.conv3.weight",
+              "semsegcls_dec1.conv3.bias"):
+        p = dict(model_dec.named_parameters())[k]
+        e = float((p.grad - gD[k]).norm() / (gD[k].norm() + 1e-20))
+        assert e <= 8e-2, (k, e)
+    assert model_dec.nmlrgr_dec.conv3.weight.grad is None        # never used (reference :813)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model_enc.parameters())
+    # tester: forward, argmax without background, entropy, depth and boundary maps
+    model_enc.eval(), model_dec.eval()
+    O._req([E, D], False)
+    with torch.no_grad():
+        semseg1, semseg2, depth, boundary = model_dec(model_enc(tgt_rgbs[:1]))
+        f = O.encoder_dict(E, tgt[:1, :3], train=False)
+        s1_o, _ = O.triple_semseg(D, f, train=False)
+        depth_o, bd_map_o = O.triple_depth(D, f, train=False), O.triple_boundary(D, f)
+    assert semseg1.shape == (1, N_CLASS, *size) and depth.shape == (1, 3, *size) and boundary.shape == (1, 1, *size)
+    agree = float((util.predict_labels(semseg1, N_CLASS - 1) == O.predict_labels(s1_o, N_CLASS - 1)).float().mean())
+    assert agree >= 0.98, agree
+    # eval mode on un-calibrated random running statistics is ill-conditioned for the deep h8 branch: compare the
+    # probability maps on average, the shallow-branch-dominated structure must agree
+    assert float((boundary.float() - bd_map_o).abs().mean()) <= 2e-2
+    assert float((depth.float() - depth_o).pow(2).mean().sqrt() / depth_o.pow(2).mean().sqrt()) <= 0.3
