@@ -15,34 +15,33 @@ namespace mcd {
 // MODE 0: stats      : acc0 = sum y, acc1 = sum y^2
 // MODE 1: bwd reduce : g = dz * (z > 0 | !relu); acc0 = sum g, acc1 = sum g*xhat(y), acc2 = sum g*xhat(res)
 template <int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
                  const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ res,
                  const float* __restrict__ mean, const float* __restrict__ rstd,
                  const float* __restrict__ res_mean, const float* __restrict__ res_rstd, int relu,
                  float* __restrict__ out, int64_t P, int C, int Cs) {
-  extern __shared__ float sh[];  // 3 * Cs
+  extern __shared__ float sh[];  // 3 * Cs accumulators + 4 * Cs coefficients (mean, rstd, res_mean, res_rstd)
+  float* co = sh + 3 * Cs;
   const int vpr = Cs >> 3;
   const int rpi = 256 / vpr;
   const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
   const bool active = pr < rpi;
   const bool dual = MODE == 1 && res_mean != nullptr;
   for (int i = threadIdx.x; i < 3 * Cs; i += 256) sh[i] = 0.f;
+  if (MODE == 1) {
+    for (int c = threadIdx.x; c < Cs; c += 256) {
+      const int cc = min(c, C - 1);
+      co[c] = mean[cc]; co[Cs + c] = rstd[cc];
+      co[2 * Cs + c] = dual ? res_mean[cc] : 0.f; co[3 * Cs + c] = dual ? res_rstd[cc] : 0.f;
+    }
+  }
   __syncthreads();
   float a0[8], a1[8], a2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a0[k] = a1[k] = a2[k] = 0.f;
   const int c0 = cv * 8;
   if (active) {
-    float mu[8], rs[8], mu2[8], rs2[8];
-    if (MODE == 1) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        int c = min(c0 + k, C - 1);
-        mu[k] = mean[c]; rs[k] = rstd[c];
-        mu2[k] = dual ? res_mean[c] : 0.f; rs2[k] = dual ? res_rstd[c] : 0.f;
-      }
-    }
     const int64_t step = (int64_t)gridDim.x * rpi;
     for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
       const int64_t off = p * Cs + c0;
@@ -57,14 +56,21 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
         uint4 vz = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
         if (relu) vz = *reinterpret_cast<const uint4*>(z + off);
         if (dual) vr = *reinterpret_cast<const uint4*>(res + off);
-        float fd[8], fz[8], fr[8];
-        unpack8(vy, fy); unpack8(vd, fd); unpack8(vz, fz); unpack8(vr, fr);
+        float fd[8], fz[8];
+        unpack8(vy, fy); unpack8(vd, fd); unpack8(vz, fz);
+        float g[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float g = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
-          a0[k] += g;
-          a1[k] = fmaf(g, (fy[k] - mu[k]) * rs[k], a1[k]);
-          if (dual) a2[k] = fmaf(g, (fr[k] - mu2[k]) * rs2[k], a2[k]);
+          g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
+          a0[k] += g[k];
+          a1[k] = fmaf(g[k], (fy[k] - co[c0 + k]) * co[Cs + c0 + k], a1[k]);
+        }
+        if (dual) {
+          float fr[8];
+          unpack8(vr, fr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            a2[k] = fmaf(g[k], (fr[k] - co[2 * Cs + c0 + k]) * co[3 * Cs + c0 + k], a2[k]);
         }
       }
     }
@@ -114,34 +120,37 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, double invP,
   save_rstd[c] = rstd;
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
                 __nv_bfloat16* __restrict__ z, int64_t P, int Cs) {
+  extern __shared__ float co[];  // scale, shift, rscale, rshift : 4 * Cs
+  for (int c = threadIdx.x; c < Cs; c += 256) {
+    co[c] = scale[c]; co[Cs + c] = shift[c];
+    co[2 * Cs + c] = rscale ? rscale[c] : 1.f; co[3 * Cs + c] = rscale ? rshift[c] : 0.f;
+  }
+  __syncthreads();
   const int vpr = Cs >> 3;
   const int rpi = 256 / vpr;
   const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
   if (pr >= rpi) return;
   const int c0 = cv * 8;
-  float sc[8], sf[8], rc[8], rf[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    sc[k] = scale[c0 + k]; sf[k] = shift[c0 + k];
-    rc[k] = rscale ? rscale[c0 + k] : 1.f; rf[k] = rscale ? rshift[c0 + k] : 0.f;
-  }
   const int64_t step = (int64_t)gridDim.x * rpi;
   for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
     const int64_t off = p * Cs + c0;
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + off), f);
+    const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
+    uint4 vr = make_uint4(0, 0, 0, 0);
+    if (res) vr = *reinterpret_cast<const uint4*>(res + off);
+    unpack8(vy, f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], co[c0 + k], co[Cs + c0 + k]);
     if (res) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + off), r);
+      unpack8(vr, r);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], rc[k], rf[k]);
+      for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], co[2 * Cs + c0 + k], co[3 * Cs + c0 + k]);
     }
     if (relu) {
 #pragma unroll
@@ -172,13 +181,14 @@ __device__ __forceinline__ void bwd_coeffs(const BwdBranch& b, const float* sums
   }
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                     const __nv_bfloat16* __restrict__ y, BwdBranch b1, const float* __restrict__ sums,
                     int relu, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, const __nv_bfloat16* __restrict__ res, BwdBranch b2,
                     __nv_bfloat16* __restrict__ dres, float* __restrict__ dres_gamma,
                     float* __restrict__ dres_beta, float invP, int64_t P, int Cs, int C) {
+  extern __shared__ float co[];  // A1, B1, K1, A2, B2, K2 : 6 * Cs
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (dgamma) dgamma[c] = sums[C + c];
@@ -187,38 +197,45 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       if (dres_beta) dres_beta[c] = sums[c];
     }
   }
+  const bool has_res_bn = dres && b2.gamma;
+  for (int c = threadIdx.x; c < Cs; c += 256) {
+    float A = 0.f, B = 0.f, K = 0.f, A2 = 0.f, B2 = 0.f, K2 = 0.f;
+    if (c < C) {
+      bwd_coeffs(b1, sums, C, C, c, invP, &A, &B, &K);
+      if (has_res_bn) bwd_coeffs(b2, sums, 2 * C, C, c, invP, &A2, &B2, &K2);
+    }
+    co[c] = A; co[Cs + c] = B; co[2 * Cs + c] = K;
+    co[3 * Cs + c] = A2; co[4 * Cs + c] = B2; co[5 * Cs + c] = K2;
+  }
+  __syncthreads();
   const int vpr = Cs >> 3;
   const int rpi = 256 / vpr;
   const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
   if (pr >= rpi) return;
   const int c0 = cv * 8;
-  const bool has_res_bn = dres && b2.gamma;
-  float A1[8], B1[8], K1[8], A2[8], B2[8], K2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    bwd_coeffs(b1, sums, C, C, c0 + k, invP, &A1[k], &B1[k], &K1[k]);
-    if (has_res_bn) bwd_coeffs(b2, sums, 2 * C, C, c0 + k, invP, &A2[k], &B2[k], &K2[k]);
-    else { A2[k] = B2[k] = K2[k] = 0.f; }
-  }
   const int64_t step = (int64_t)gridDim.x * rpi;
   for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
     const int64_t off = p * Cs + c0;
+    const uint4 vd = *reinterpret_cast<const uint4*>(dz + off);
+    const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
+    uint4 vz = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
+    if (relu) vz = *reinterpret_cast<const uint4*>(z + off);
+    if (has_res_bn) vr = *reinterpret_cast<const uint4*>(res + off);
     float fd[8], fz[8], fy[8], g[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(dz + off), fd);
-    unpack8(*reinterpret_cast<const uint4*>(y + off), fy);
-    if (relu) unpack8(*reinterpret_cast<const uint4*>(z + off), fz);
+    unpack8(vd, fd); unpack8(vy, fy); unpack8(vz, fz);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
-      o[k] = fmaf(A1[k], g[k], fmaf(B1[k], fy[k], K1[k]));
+      o[k] = fmaf(co[c0 + k], g[k], fmaf(co[Cs + c0 + k], fy[k], co[2 * Cs + c0 + k]));
     }
     *reinterpret_cast<uint4*>(dy + off) = pack8(o);
     if (dres) {
       if (has_res_bn) {
         float fr[8];
-        unpack8(*reinterpret_cast<const uint4*>(res + off), fr);
+        unpack8(vr, fr);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf(A2[k], g[k], fmaf(B2[k], fr[k], K2[k]));
+        for (int k = 0; k < 8; ++k)
+          o[k] = fmaf(co[3 * Cs + c0 + k], g[k], fmaf(co[4 * Cs + c0 + k], fr[k], co[5 * Cs + c0 + k]));
         *reinterpret_cast<uint4*>(dres + off) = pack8(o);
       } else {
         *reinterpret_cast<uint4*>(dres + off) = pack8(g);
@@ -235,8 +252,8 @@ static inline int rows_grid(int64_t P, int Cs, int rows_per_thread, int max_bloc
 }
 
 int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaStream_t st) {
-  int grid = rows_grid(P, Cs, 8, 148 * 2);
-  bn_reduce_kernel<0><<<grid, 256, 3 * Cs * sizeof(float), st>>>(
+  int grid = rows_grid(P, Cs, 8, 148 * 3);
+  bn_reduce_kernel<0><<<grid, 256, 7 * Cs * sizeof(float), st>>>(
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stats, P,
       C, Cs);
   return check_launch("bn_stats");
@@ -280,7 +297,7 @@ int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, con
   MCD_REQUIRE(!rscale || (res_nhwc && rshift), "bn_apply: residual affine without residual");
   MCD_REQUIRE(Cs <= 2048, "bn_apply: channel stride %d unsupported", Cs);
   int grid = rows_grid(P, Cs, 4, 148 * 8);
-  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  bn_apply_kernel<<<grid, 256, 4 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, scale, shift, (const __nv_bfloat16*)res_nhwc, rscale, rshift, relu,
       (__nv_bfloat16*)z_nhwc, P, Cs);
   return check_launch("bn_apply");
@@ -295,8 +312,8 @@ int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhw
   MCD_REQUIRE(!relu || z_nhwc, "bn_bwd_reduce: relu needs z");
   MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_bwd_reduce: needs dense channels (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!res_mean || (res_nhwc && res_rstd), "bn_bwd_reduce: residual stats without residual");
-  int grid = rows_grid(P, Cs, 8, 148 * 2);
-  bn_reduce_kernel<1><<<grid, 256, 3 * Cs * sizeof(float), (cudaStream_t)stream>>>(
+  int grid = rows_grid(P, Cs, 8, 148 * 3);
+  bn_reduce_kernel<1><<<grid, 256, 7 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc,
       (const __nv_bfloat16*)res_nhwc, mean, rstd, res_mean, res_rstd, relu, sums, P, C, Cs);
   return check_launch("bn_bwd_reduce");
@@ -319,7 +336,7 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
   BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
   MCD_REQUIRE(Cs <= 2048, "bn_bwd_apply: channel stride %d unsupported", Cs);
   int grid = rows_grid(P, Cs, 4, 148 * 8);
-  bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  bn_bwd_apply_kernel<<<grid, 256, 6 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc, (const __nv_bfloat16*)y_nhwc, b1, sums,
       relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, (const __nv_bfloat16*)res_nhwc, b2,
       (__nv_bfloat16*)dres_nhwc, dres_gamma, dres_beta, (float)(1.0 / (double)P), P, Cs, C);

@@ -583,13 +583,20 @@ static int encode_rows_map(CUtensorMap* m, const void* base, int N, int H, int W
   return MCD_OK;
 }
 
-// packed tiles: TW columns of TH rows, TH >= 8 so that every column box starts on a 1024-byte swizzle atom
+// packed tiles: TW columns of TH rows, TH >= 8 so that every column box starts on a 1024-byte swizzle atom.
+// Every column costs one TMA issue per K chunk and the thin layers are TMA-issue-bound, so the tallest tile whose
+// padded area is within 10 % of the best one wins.
 static void pick_tile_packed(int Ht, int Wt, int npix, int* TH, int* TW) {
   int64_t best = -1;
   for (int th = npix; th >= 8; th >>= 1) {
     int tw = npix / th;
     int64_t area = (int64_t)((Ht + th - 1) / th) * th * ((Wt + tw - 1) / tw) * tw;
-    if (best < 0 || area < best) { best = area; *TH = th; *TW = tw; }
+    if (best < 0 || area < best) best = area;
+  }
+  for (int th = npix; th >= 8; th >>= 1) {
+    int tw = npix / th;
+    int64_t area = (int64_t)((Ht + th - 1) / th) * th * ((Wt + tw - 1) / tw) * tw;
+    if (area * 10 <= best * 11) { *TH = th; *TW = tw; return; }
   }
 }
 
@@ -716,9 +723,7 @@ static bool wgrad_rows_ok(const mcd_conv_geom& g) {
 }
 
 static void wgrad_rows_shape(const mcd_conv_geom& g, int* TH, int* TW, int* ntiles, int* nsplit) {
-  // a single 64-row column per tile halves the TMA issues; accept up to 10 % padded rows for it
-  if (((g.Ho + 63) / 64) * 64 * 10 <= g.Ho * 11) { *TH = 64; *TW = 1; }
-  else pick_tile_packed(g.Ho, g.Wo, 64, TH, TW);
+  pick_tile_packed(g.Ho, g.Wo, 64, TH, TW);
   *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
   *nsplit = max(1, min(*ntiles, 148));
 }

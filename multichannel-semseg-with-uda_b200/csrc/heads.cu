@@ -10,47 +10,69 @@ namespace mcd {
 
 // ---- depthwise deconv 16x16 stride 8 pad 4 ------------------------------------------------------
 // out[oh][ow] = sum_{a,b in {0,1}} x[ih0-a][iw0-b] * w[kh0+8a][kw0+8b],  ih0 = (oh+4)>>3, kh0 = (oh+4)&7
-// grid: (N*C, ceil(H/8)); block 256; each thread produces 8 consecutive ow (one 16-byte store).
+// "cell row" i (0..h) = the 8 output rows oh = 8i-4 .. 8i+3 that read x[i] (filter rows kh0) and x[i-1]
+// (filter rows kh0+8).  One thread owns a cell (i, j): it loads the 6 neighbouring inputs once and emits 8 rows
+// of 8 consecutive output columns (one 16-byte store per row) with broadcast LDS.128 weight reads.
+// grid: (N*C, ceil((h+1)/cells_per_block)); block 256.
 __global__ void __launch_bounds__(256)
 deconv16s8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ x2, const float* __restrict__ w2,
-                      __nv_bfloat16* __restrict__ out, int C, int h, int wd) {
-  __shared__ float sw[2][256];
+                      __nv_bfloat16* __restrict__ out, int C, int h, int wd, int cells_per_block) {
+  __shared__ __align__(16) float sw[2][256];
   const int nc = blockIdx.x, c = nc % C;
   const int H = h * 8, W = wd * 8;
   sw[0][threadIdx.x] = w[c * 256 + threadIdx.x];
   sw[1][threadIdx.x] = x2 ? (w2 ? w2 : w)[c * 256 + threadIdx.x] : 0.f;
   __syncthreads();
-  const float* xp = x + (int64_t)nc * h * wd;
-  const float* xp2 = x2 ? x2 + (int64_t)nc * h * wd : nullptr;
+  const int ninputs = x2 ? 2 : 1;
   __nv_bfloat16* op = out + (int64_t)nc * H * W;
-  const int oh_beg = blockIdx.y * 8, oh_end = min(oh_beg + 8, H);
-  const int items = (oh_end - oh_beg) * wd;  // one item = 8 consecutive output columns
+  const int items = cells_per_block * wd;
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int oh = oh_beg + it / wd, j = it % wd;
-    const int ih0 = (oh + 4) >> 3, kh0 = (oh + 4) & 7;
-    float f[8];
+    const int i = blockIdx.y * cells_per_block + it / wd, j = it % wd;
+    if (i > h) continue;
+    float xa[2][3], xb[2][3];   // [input][column j-1, j, j+1] of rows i (a) and i-1 (b)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int ow = j * 8 + k;
-      const int iw0 = (ow + 4) >> 3, kw0 = (ow + 4) & 7;
-      float acc = 0.f;
+    for (int q = 0; q < 2; ++q) {
+      const float* xp = (q == 0 ? x : x2);
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        const int ih = ih0 - a;
-        if (ih < 0 || ih >= h) continue;
+      for (int d = 0; d < 3; ++d) {
+        const int col = j - 1 + d;
+        const bool cok = q < ninputs && col >= 0 && col < wd;
+        xa[q][d] = (cok && i < h) ? xp[((int64_t)nc * h + i) * wd + col] : 0.f;
+        xb[q][d] = (cok && i >= 1) ? xp[((int64_t)nc * h + i - 1) * wd + col] : 0.f;
+      }
+    }
+#pragma unroll 2
+    for (int kh0 = 0; kh0 < 8; ++kh0) {
+      const int oh = 8 * i - 4 + kh0;
+      if (oh < 0 || oh >= H) continue;
+      float f[8];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int iw = iw0 - b;
-          if (iw < 0 || iw >= wd) continue;
-          const int widx = (kh0 + 8 * a) * 16 + kw0 + 8 * b;
-          acc = fmaf(xp[ih * wd + iw], sw[0][widx], acc);
-          if (xp2) acc = fmaf(xp2[ih * wd + iw], sw[1][widx], acc);
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      for (int q = 0; q < ninputs; ++q) {
+        float wa[16], wb[16];   // filter rows kh0 and kh0+8
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          *reinterpret_cast<float4*>(wa + 4 * v) = *reinterpret_cast<const float4*>(&sw[q][kh0 * 16 + 4 * v]);
+          *reinterpret_cast<float4*>(wb + 4 * v) = *reinterpret_cast<const float4*>(&sw[q][(kh0 + 8) * 16 + 4 * v]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {     // ow = 8j+k: iw0 = j, kw0 = k+4
+          f[k] = fmaf(xa[q][1], wa[k + 4], f[k]);
+          f[k] = fmaf(xa[q][0], wa[k + 12], f[k]);
+          f[k] = fmaf(xb[q][1], wb[k + 4], f[k]);
+          f[k] = fmaf(xb[q][0], wb[k + 12], f[k]);
+        }
+#pragma unroll
+        for (int k = 4; k < 8; ++k) {     // ow = 8j+k: iw0 = j+1, kw0 = k-4
+          f[k] = fmaf(xa[q][2], wa[k - 4], f[k]);
+          f[k] = fmaf(xa[q][1], wa[k + 4], f[k]);
+          f[k] = fmaf(xb[q][2], wb[k - 4], f[k]);
+          f[k] = fmaf(xb[q][1], wb[k + 4], f[k]);
         }
       }
-      f[k] = acc;
+      *reinterpret_cast<uint4*>(op + (int64_t)oh * W + j * 8) = pack8(f);
     }
-    *reinterpret_cast<uint4*>(op + (int64_t)oh * W + j * 8) = pack8(f);
   }
 }
 
@@ -217,9 +239,10 @@ int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const fl
                        int N, int C, int h, int w_, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(x && w && out && N > 0 && C > 0 && h > 0 && w_ > 0, "deconv16s8_fwd: bad arguments");
-  dim3 grid((unsigned)(N * C), (unsigned)h);
+  int cells = w_ >= 256 ? 1 : 256 / w_;
+  dim3 grid((unsigned)(N * C), (unsigned)((h + 1 + cells - 1) / cells));
   deconv16s8_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, x2, w2, (__nv_bfloat16*)out, C,
-                                                                 h, w_);
+                                                                 h, w_, cells);
   return check_launch("deconv16s8_fwd");
 }
 
