@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 4
+#define MCD_ABI_VERSION 5
 
 enum {
   MCD_OK = 0,
@@ -124,6 +124,16 @@ int mcd_bn_finalize(const float* stats, int64_t P, const float* gamma, const flo
                     float* running_mean, float* running_var, float momentum, float eps,
                     int training, float* scale, float* shift, float* save_mean, float* save_rstd,
                     int64_t* num_batches_tracked, int C, int device, void* stream);
+/* Fused forward: mcd_bn_finalize (for the main and, when res_save_mean_rstd != NULL, the residual/downsample
+ * BatchNorm) + mcd_bn_apply in ONE launch.  save_mean_rstd: fp32 [2*C] out (mean, rstd) for the backward.
+ * res_nhwc with res_save_mean_rstd == NULL is an identity residual. */
+int mcd_bn_forward(const void* y_nhwc, const float* stats, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                   float eps, int training, float* save_mean_rstd, const void* res_nhwc,
+                   const float* res_stats, const float* res_gamma, const float* res_beta,
+                   float* res_running_mean, float* res_running_var, int64_t* res_num_batches_tracked,
+                   float res_momentum, float res_eps, int res_training, float* res_save_mean_rstd, int relu,
+                   void* z_nhwc, int64_t P, int C, int Cs, int device, void* stream);
 /* z = act(scale*y + shift + residual'), residual' = res (identity) or rscale*res + rshift
  * (downsample branch, models/drn.py:53-56); res / rscale may be NULL; relu = 0/1. */
 int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, const void* res_nhwc,

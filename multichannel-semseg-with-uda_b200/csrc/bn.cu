@@ -160,6 +160,86 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
   }
 }
 
+// ---- fused forward: finalize (statistics -> scale/shift, running-stat update) + apply in ONE launch --------
+struct BnParams {
+  const float* stats;          // [2C] sum / sum of squares (training) or NULL
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; int64_t* nbt;
+  float* save;                 // [2C] out: mean, rstd (consumed by the backward kernels)
+  float momentum, eps;
+  int training;                // 0 eval, k >= 1: k identical batches folded (momentum already adjusted)
+};
+
+__device__ __forceinline__ void bn_coeffs(const BnParams& b, int c, int C, double invP, double unbias,
+                                          bool writer, float* scale, float* shift) {
+  float mean, var;
+  if (b.training) {
+    double m = (double)b.stats[c] * invP;
+    double v = (double)b.stats[C + c] * invP - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m; var = (float)v;
+    if (writer && b.running_mean) {
+      b.running_mean[c] = (1.f - b.momentum) * b.running_mean[c] + b.momentum * mean;
+      b.running_var[c] = (1.f - b.momentum) * b.running_var[c] + b.momentum * (float)(v * unbias);
+    }
+  } else {
+    mean = b.running_mean[c]; var = b.running_var[c];
+  }
+  const float rstd = rsqrtf(var + b.eps);
+  const float g = b.gamma ? b.gamma[c] : 1.f, be = b.beta ? b.beta[c] : 0.f;
+  *scale = g * rstd;
+  *shift = be - mean * g * rstd;
+  if (writer) { b.save[c] = mean; b.save[C + c] = rstd; }
+}
+
+__global__ void __launch_bounds__(256, 4)
+bn_forward_kernel(const __nv_bfloat16* __restrict__ y, BnParams b1, const __nv_bfloat16* __restrict__ res,
+                  BnParams b2, int has_res_bn, int relu, __nv_bfloat16* __restrict__ z, int64_t P, int C, int Cs,
+                  double invP, double unbias) {
+  extern __shared__ float co[];  // scale, shift, rscale, rshift : 4 * Cs
+  const bool writer = blockIdx.x == 0;   // exactly one block updates running stats / saves mean, rstd
+  for (int c = threadIdx.x; c < Cs; c += 256) {
+    float sc = 0.f, sf = 0.f, rc = 1.f, rf = 0.f;
+    if (c < C) {
+      bn_coeffs(b1, c, C, invP, unbias, writer, &sc, &sf);
+      if (has_res_bn) bn_coeffs(b2, c, C, invP, unbias, writer, &rc, &rf);
+    }
+    co[c] = sc; co[Cs + c] = sf; co[2 * Cs + c] = rc; co[3 * Cs + c] = rf;
+  }
+  if (writer && threadIdx.x == 0) {
+    if (b1.training && b1.nbt) *b1.nbt += b1.training;
+    if (has_res_bn && b2.training && b2.nbt) *b2.nbt += b2.training;
+  }
+  __syncthreads();
+  const int vpr = Cs >> 3;
+  const int rpi = 256 / vpr;
+  const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
+  if (pr >= rpi) return;
+  const int c0 = cv * 8;
+  const int64_t step = (int64_t)gridDim.x * rpi;
+  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
+    const int64_t off = p * Cs + c0;
+    float f[8];
+    const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
+    uint4 vr = make_uint4(0, 0, 0, 0);
+    if (res) vr = *reinterpret_cast<const uint4*>(res + off);
+    unpack8(vy, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], co[c0 + k], co[Cs + c0 + k]);
+    if (res) {
+      float r[8];
+      unpack8(vr, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], co[2 * Cs + c0 + k], co[3 * Cs + c0 + k]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    }
+    *reinterpret_cast<uint4*>(z + off) = pack8(f);
+  }
+}
+
 struct BwdBranch {
   const float* gamma; const float* mean; const float* rstd;
   int training;
@@ -286,6 +366,32 @@ int mcd_bn_finalize(const float* stats, int64_t P, const float* gamma, const flo
       stats, invP, unbias, gamma, beta, running_mean, running_var, momentum, eps, training, scale,
       shift, save_mean, save_rstd, num_batches_tracked, C);
   return check_launch("bn_finalize");
+}
+
+int mcd_bn_forward(const void* y_nhwc, const float* stats, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                   float eps, int training, float* save_mean_rstd, const void* res_nhwc,
+                   const float* res_stats, const float* res_gamma, const float* res_beta,
+                   float* res_running_mean, float* res_running_var, int64_t* res_num_batches_tracked,
+                   float res_momentum, float res_eps, int res_training, float* res_save_mean_rstd, int relu,
+                   void* z_nhwc, int64_t P, int C, int Cs, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(y_nhwc && z_nhwc && save_mean_rstd && P > 0 && C > 0, "bn_forward: bad arguments");
+  MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_forward: needs dense channels, C %% 8 == 0 (C=%d Cs=%d)", C, Cs);
+  MCD_REQUIRE(training ? stats != nullptr : (running_mean && running_var), "bn_forward: missing statistics");
+  const int has_res_bn = res_save_mean_rstd != nullptr;
+  MCD_REQUIRE(!has_res_bn || (res_nhwc && (res_training ? res_stats != nullptr : (res_running_mean && res_running_var))),
+              "bn_forward: incomplete residual BatchNorm");
+  BnParams b1{stats, gamma, beta, running_mean, running_var, num_batches_tracked, save_mean_rstd, momentum, eps, training};
+  BnParams b2{res_stats, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked,
+              res_save_mean_rstd, res_momentum, res_eps, res_training};
+  double invP = 1.0 / (double)P;
+  double unbias = P > 1 ? (double)P / (double)(P - 1) : 1.0;
+  int grid = rows_grid(P, Cs, 4, 148 * 8);
+  bn_forward_kernel<<<grid, 256, 4 * Cs * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y_nhwc, b1, (const __nv_bfloat16*)res_nhwc, b2, has_res_bn, relu,
+      (__nv_bfloat16*)z_nhwc, P, C, Cs, invP, unbias);
+  return check_launch("bn_forward");
 }
 
 int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, const void* res_nhwc,

@@ -30,15 +30,6 @@ class bn_update_repeat:
         _bn_repeat = self.prev
 
 
-def _bn_finalize(bn, stats, count, gamma, beta):
-    if not bn.training:
-        return ops.bn_finalize(None, count, gamma, beta, bn.running_mean, bn.running_var, bn.momentum, bn.eps, 0)
-    k = _bn_repeat
-    momentum = bn.momentum if k == 1 else 1.0 - (1.0 - bn.momentum) ** k
-    return ops.bn_finalize(stats, count, gamma, beta, bn.running_mean, bn.running_var, momentum, bn.eps, k,
-                           bn.num_batches_tracked)
-
-
 def _as_nhwc_grad(dy):
     """Gradients arriving from autograd for an nhwc activation: make them nhwc bf16 again."""
     if ops.is_nhwc(dy):
@@ -126,14 +117,9 @@ class Conv2d(nn.Conv2d):
 class _BNActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, stats, gamma, beta, res, res_stats, res_gamma, res_beta, bn, res_bn, relu):
-        n, c, h, w = y.shape
-        count = n * h * w
         training = bn.training
-        aff = _bn_finalize(bn, stats, count, gamma, beta)
-        res_aff = None
-        if res_bn is not None:
-            res_aff = _bn_finalize(res_bn, res_stats, count, res_gamma, res_beta)
-        z = ops.bn_apply(y, aff, res, res_aff, relu)
+        z, aff, res_aff = ops.bn_forward(y, stats, bn, relu, res=res, res_stats=res_stats, res_bn=res_bn,
+                                         repeat=_bn_repeat)
         ctx.relu, ctx.training = relu, training
         ctx.res_training = res_bn.training if res_bn is not None else False
         ctx.has_res, ctx.has_res_bn = res is not None, res_bn is not None

@@ -46,6 +46,43 @@ def round_up(a, b):
     return (a + b - 1) // b * b
 
 
+# ---- zero-initialised fp32 scratch (BatchNorm statistics, loss accumulators) -------------------------
+class ZeroArena:
+    """One device buffer that is zeroed ONCE per iteration (`begin`) and handed out in slices: replaces the
+    several hundred tiny `torch.zeros` fill kernels of an MCD iteration by a single memset."""
+
+    def __init__(self, device, nfloats=1 << 20):
+        self.buf = torch.zeros(nfloats, dtype=F32, device=device)
+        self.pos = 0
+
+    def begin(self):
+        self.buf.zero_()
+        self.pos = 0
+
+    def take(self, n):
+        n_al = (n + 31) // 32 * 32
+        if self.pos + n_al > self.buf.numel():
+            return torch.zeros(n, dtype=F32, device=self.buf.device)
+        v = self.buf[self.pos:self.pos + n]
+        self.pos += n_al
+        return v
+
+
+_arena = None
+
+
+def set_arena(arena):
+    global _arena
+    prev, _arena = _arena, arena
+    return prev
+
+
+def zeros_f32(n, device):
+    if _arena is not None and _arena.buf.device == device:
+        return _arena.take(n)
+    return torch.zeros(n, dtype=F32, device=device)
+
+
 # ---- layout ------------------------------------------------------------------------------------
 def is_nhwc(t):
     return (t.dim() == 4 and t.dtype == BF16 and t.shape[1] % 8 == 0
@@ -134,7 +171,7 @@ def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
         y = torch.empty((g.N, g.Cout, g.Ho, g.Wo), dtype=F32, device=x.device)
     else:
         y = nhwc_empty(g.N, g.Cout_s, g.Ho, g.Wo, x.device)
-    stats = torch.zeros(2 * g.Cout, dtype=F32, device=x.device) if want_stats else None
+    stats = zeros_f32(2 * g.Cout, x.device) if want_stats else None
     abi.check(abi.lib().mcd_conv2d_fprop(
         _p(x), _p(w_packed), _p(bias), _p(y), abi.OUT_PLANAR_F32 if planar else abi.OUT_NHWC_BF16,
         _p(stats), ctypes.byref(g), _algo if algo is None else algo, _dev(x), _stream(x)), "conv2d_fprop")
@@ -182,6 +219,33 @@ def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, 
     return out
 
 
+def bn_forward(y, stats, bn, relu, res=None, res_stats=None, res_bn=None, repeat=1):
+    """fused finalize + normalise (+residual / downsample BatchNorm) (+ReLU).  `bn` / `res_bn` are nn.BatchNorm2d
+    modules (parameters, running buffers, momentum, eps, .training).  Returns z, save[2,C], res_save[2,C]|None;
+    save rows are (mean, rstd) for the backward."""
+    n, c, h, w = y.shape
+
+    def mom(m):
+        return m.momentum if repeat == 1 else 1.0 - (1.0 - m.momentum) ** repeat
+
+    z = nhwc_empty(n, c, h, w, y.device)
+    save = torch.empty((2, c), dtype=F32, device=y.device)
+    rsave = torch.empty((2, c), dtype=F32, device=y.device) if res_bn is not None else None
+    tr = repeat if bn.training else 0
+    rtr = (repeat if res_bn.training else 0) if res_bn is not None else 0
+    abi.check(abi.lib().mcd_bn_forward(
+        _p(y), _p(stats) if tr else None, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
+        _p(bn.num_batches_tracked) if tr else None, float(mom(bn)), float(bn.eps), tr, _p(save), _p(res),
+        (_p(res_stats) if rtr else None) if res_bn is not None else None,
+        _p(res_bn.weight) if res_bn is not None else None, _p(res_bn.bias) if res_bn is not None else None,
+        _p(res_bn.running_mean) if res_bn is not None else None,
+        _p(res_bn.running_var) if res_bn is not None else None,
+        (_p(res_bn.num_batches_tracked) if rtr else None) if res_bn is not None else None,
+        float(mom(res_bn)) if res_bn is not None else 0.0, float(res_bn.eps) if res_bn is not None else 0.0,
+        rtr, _p(rsave), int(relu), _p(z), n * h * w, c, c, _dev(y), _stream(y)), "bn_forward")
+    return z, save, rsave
+
+
 def bn_apply(y, aff, res, res_aff, relu):
     n, c, h, w = y.shape
     z = nhwc_empty(n, c, h, w, y.device)
@@ -194,12 +258,17 @@ def bn_apply(y, aff, res, res_aff, relu):
 
 def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_aff=None,
            res_training=False, want_dres=False):
-    """returns dy, dgamma, dbeta, dres, dres_gamma, dres_beta"""
+    """returns dy, dgamma, dbeta, dres, dres_gamma, dres_beta.  `aff` / `res_aff`: either the [4,C] tensor of
+    bn_finalize (scale, shift, mean, rstd) or the [2,C] (mean, rstd) tensor of bn_forward."""
+    if aff.shape[0] == 2:
+        aff = (None, None, aff[0], aff[1])
+    if res_aff is not None and res_aff.shape[0] == 2:
+        res_aff = (None, None, res_aff[0], res_aff[1])
     n, c, h, w = y.shape
     count = n * h * w
     dev, st = _dev(y), _stream(y)
     has_res_bn = res_gamma is not None
-    sums = torch.zeros(3 * c, dtype=F32, device=y.device)
+    sums = zeros_f32(3 * c, y.device)
     abi.check(abi.lib().mcd_bn_bwd_reduce(
         _p(dz), _p(z), _p(y), _p(aff[2]), _p(aff[3]), _p(res) if has_res_bn else None,
         _p(res_aff[2]) if has_res_bn else None, _p(res_aff[3]) if has_res_bn else None, int(relu),
@@ -254,7 +323,7 @@ def bilinear_up_bwd(dout, s):
 # ---- losses ------------------------------------------------------------------------------------
 def ce2d_fwd(logits, target, weight, ignore_index):
     n, c, h, w = logits.shape
-    acc = torch.zeros(4, dtype=F32, device=logits.device)
+    acc = zeros_f32(4, logits.device)
     abi.check(abi.lib().mcd_ce2d_fwd(_p(logits), _p(target), _p(weight), int(ignore_index), _p(acc), n, c,
                                      h, w, _dev(logits), _stream(logits)), "ce2d_fwd")
     return acc
@@ -271,7 +340,7 @@ def ce2d_bwd(logits, target, weight, ignore_index, acc, gscale):
 
 def diff2d_fwd(a, b):
     n, c, h, w = a.shape
-    acc = torch.zeros(1, dtype=F32, device=a.device)
+    acc = zeros_f32(1, a.device)
     abi.check(abi.lib().mcd_diff2d_fwd(_p(a), _p(b), _p(acc), n, c, h, w, _dev(a), _stream(a)), "diff2d_fwd")
     return acc
 

@@ -11,7 +11,9 @@ order = the order backward produces them).  `param.grad` are views into the buck
   * a bucket is all-reduced (SUM) on a side stream as soon as autograd has accumulated its last gradient,
     overlapping the remaining dgrad / wgrad kernels,
   * no gather / scatter copies are needed.
-With world_size == 1 (or no process group) it only provides the flat zeroing.
+With world_size == 1 (or no process group) nothing is exchanged: `zero_and_arm` simply drops the gradients
+(`p.grad = None`), so autograd hands each freshly computed gradient to the parameter without an accumulation
+kernel and nothing needs zeroing.
 Works with any torch.distributed backend (tests run it on gloo with CPU tensors).
 """
 import torch
@@ -36,6 +38,10 @@ class GradSync:
         self.armed = False
         self.buckets = []
         self._by_param = {}
+        self.flat = self.world > 1
+        if not self.flat:
+            self.cuda, self.comm_stream = bool(self.params) and self.params[0].is_cuda, None
+            return
         cap = int(bucket_mb * (1 << 20) / 4)
         cur, cur_n = [], 0
         for p in reversed(self.params):
@@ -66,6 +72,10 @@ class GradSync:
     # ---------------------------------------------------------------------------------------------
     def zero_and_arm(self, armed=True):
         """zero the flat gradients (re-attaching the views if something replaced .grad) and arm the hooks."""
+        if not self.flat:
+            for p in self.params:
+                p.grad = None
+            return
         for b in self.buckets:
             b.flat.zero_()
             off = 0

@@ -40,6 +40,7 @@ class MCDStep:
         self.optimizer_f = get_optimizer(f_params, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.sync_g = parallel.GradSync(g_params, process_group, bucket_mb)
         self.sync_f = parallel.GradSync(f_params, process_group, bucket_mb)
+        self._arena = None
         self.world = self.sync_g.world
         if self.world > 1 and hasattr(criterion, "set_process_group"):
             criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
@@ -91,6 +92,17 @@ class MCDStep:
 
     def __call__(self, src_imgs, src_lbls, tgt_imgs):
         crit = self.criterion
+        from . import ops
+        if self._arena is None or self._arena.buf.device != src_imgs.device:
+            self._arena = ops.ZeroArena(src_imgs.device)
+        prev_arena = ops.set_arena(self._arena)
+        try:
+            self._arena.begin()            # ONE memset for all BatchNorm-statistic / loss accumulators
+            return self._iteration(crit, src_imgs, src_lbls, tgt_imgs)
+        finally:
+            ops.set_arena(prev_arena)
+
+    def _iteration(self, crit, src_imgs, src_lbls, tgt_imgs):
         # ---- A: source supervised; updates G, F1, F2
         self.sync_g.zero_and_arm(), self.sync_f.zero_and_arm()
         o1, o2 = self._heads(self._gen(src_imgs))

@@ -20,10 +20,10 @@ for (c, dil) in ((512, 4), (256, 2)):
         y, stats = ops.conv_fprop(x, wf, None, g, want_stats=True)
         dx = ops.conv_dgrad(y, wd, g)
         dw, _ = ops.conv_wgrad(x, y, g)
-    aff = ops.bn_finalize(stats, 8 * 60 * 80, torch.ones(c, device=dev), torch.zeros(c, device=dev),
-                          torch.zeros(c, device=dev), torch.ones(c, device=dev), 0.1, 1e-5, 1)
+    bn = torch.nn.BatchNorm2d(c).to(dev).train()
     for _ in range(2):
-        z = ops.bn_apply(y, aff, x, None, True)
-        ops.bn_bwd(dx, z, y, torch.ones(c, device=dev), aff, True, True, want_dres=True)
+        _, stats = ops.conv_fprop(x, wf, None, g, want_stats=True)
+        z, save, _ = ops.bn_forward(y, stats, bn, True, res=x)
+        ops.bn_bwd(dx, z, y, bn.weight, save, True, True, want_dres=True)
 torch.cuda.synchronize()
 print("done")
