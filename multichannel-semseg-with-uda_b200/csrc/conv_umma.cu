@@ -30,6 +30,7 @@ struct UmmaMaps {
 
 struct FpropArgs {
   int N, Ht, Wt, TH, TW, tiles_h, tiles_w;
+  int tiles_m, tiles_n;   // tiles_m = N * tiles_h * tiles_w pixel tiles, tiles_n = channel tiles of BN
   int kchunks, ntaps, kc_pad;
   int rows;               // produced channels
   int omul, oh0, ow0, Hd, Wd, Cd_s;
@@ -49,10 +50,14 @@ struct FpropCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 4));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int MIN_CTAS = BN <= 32 ? 2 : 1;   // thin tiles: overlap prologue/epilogue across CTAs
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // one accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;              // double-buffered (power of two, <= 512)
+  static constexpr int MIN_CTAS = BN <= 32 ? 2 : 1;           // thin tiles: two CTAs per SM
 };
 
+// Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
+// boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
+// registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, FpropCfg<BN>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
@@ -62,24 +67,18 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                                              ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int mt = blockIdx.x;
-  const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
-  const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
-  const int n_img = mt;
-  const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
-  const int n0 = blockIdx.y * BN;
+  const int total_tiles = a.tiles_m * a.tiles_n;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -93,120 +92,149 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < a.ntaps; ++t) {
-        const Tap tap = a.taps[t];
-        const CUtensorMap* amap = &maps.a[tap.map];
-        for (int kc = 0; kc < a.kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (a.packed) {
-            // TW columns x TH rows, column-major in the tile: one {64 elements, TH rows} window box per column
-            for (int j = 0; j < a.TW; ++j)
-              tma_load_3d(sa + j * a.TH * 128, amap, &full_bar[stage],
-                          ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
-          } else {
-            tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt = tile / a.tiles_n;
+        const int n0 = (tile % a.tiles_n) * BN;
+        const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
+        const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
+        const int n_img = mt;
+        const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+        for (int t = 0; t < a.ntaps; ++t) {
+          const Tap tap = a.taps[t];
+          const CUtensorMap* amap = &maps.a[tap.map];
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (a.packed) {
+              // TW columns x TH rows, column-major in the tile: one {64 elements, TH rows} window box per column
+              for (int j = 0; j < a.TW; ++j)
+                tma_load_3d(sa + j * a.TH * 128, amap, &full_bar[stage],
+                            ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
+            } else {
+              tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
+            }
+            tma_load_2d(sb, &maps.b, &full_bar[stage], tap.wk * a.kc_pad + kc * 64, n0);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
-          tma_load_2d(sb, &maps.b, &full_bar[stage], tap.wk * a.kc_pad + kc * 64, n0);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = instr_desc_bf16(128, BN, 0, 0);
     int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < kblocks; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        const uint64_t adesc = smem_desc_sw128(sa, 0, 1024);
-        const uint64_t bdesc = smem_desc_sw128(sb, 0, 1024);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sa, 0, 1024);
+          const uint64_t bdesc = smem_desc_sw128(sb, 0, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-channel chunk: +32 bytes each
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                    (kb | k) != 0);
-        umma_commit(&empty_bar[stage]);
-        if (kb == kblocks - 1) umma_commit(tmem_full_bar);
+          for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-channel chunk: +32 bytes each
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (kb == kblocks - 1) umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ---- epilogue: thread = one output pixel (TMEM lane), loop over 32-channel column chunks ----
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int ht = a.packed ? th0 + m % a.TH : th0 + m / a.TW;
-    const int wt = a.packed ? tw0 + m / a.TH : tw0 + m % a.TW;
-    const bool pvalid = ht < a.Ht && wt < a.Wt;
-    const int hd = ht * a.omul + a.oh0, wd = wt * a.omul + a.ow0;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int ncover = a.planar ? a.rows : a.Cd_s;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int mt = tile / a.tiles_n;
+      const int n0 = (tile % a.tiles_n) * BN;
+      const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
+      const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
+      const int n_img = mt;
+      const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+      const int ht = a.packed ? th0 + m % a.TH : th0 + m / a.TW;
+      const int wt = a.packed ? tw0 + m / a.TH : tw0 + m % a.TW;
+      const bool pvalid = ht < a.Ht && wt < a.Wt;
+      const int hd = ht * a.omul + a.oh0, wd = wt * a.omul + a.ow0;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= ncover) break;   // warp-uniform
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (a.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int c = n0 + c0 + j;
-          v[j] += (c < a.rows) ? __ldg(a.bias + c) : 0.f;
-        }
-      }
-      if (pvalid) {
-        if (a.planar) {
-          float* o = reinterpret_cast<float*>(a.out);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= ncover) break;   // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_d + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (a.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             int c = n0 + c0 + j;
-            if (c < a.rows) o[(((int64_t)n_img * a.rows + c) * a.Hd + hd) * a.Wd + wd] = v[j];
+            v[j] += (c < a.rows) ? __ldg(a.bias + c) : 0.f;
           }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) +
-                             (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0 + c0;
+        }
+        if (pvalid) {
+          if (a.planar) {
+            float* o = reinterpret_cast<float*>(a.out);
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            int c = n0 + c0 + j8 * 8;
-            if (c < a.Cd_s) {
-              float f[8];
+            for (int j = 0; j < 32; ++j) {
+              int c = n0 + c0 + j;
+              if (c < a.rows) o[(((int64_t)n_img * a.rows + c) * a.Hd + hd) * a.Wd + wd] = v[j];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) +
+                               (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0 + c0;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
-              *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
+            for (int j8 = 0; j8 < 4; ++j8) {
+              int c = n0 + c0 + j8 * 8;
+              if (c < a.Cd_s) {
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
+                *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
+              }
             }
           }
         }
-      }
-      if (a.stats) {
-        // column sums over the 32 pixels of this warp: butterfly transpose-reduce, lane j ends up
-        // holding column j.
-        float s1[32], s2[32];
+        if (a.stats) {
+          // column sums over the 32 pixels of this warp: butterfly transpose-reduce, lane j ends up
+          // holding column j.
+          float s1[32], s2[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { float x = pvalid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+          for (int j = 0; j < 32; ++j) { float x = pvalid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const bool up = (lane & step) != 0;
+          for (int step = 16; step >= 1; step >>= 1) {
+            const bool up = (lane & step) != 0;
 #pragma unroll
-          for (int i = 0; i < step; ++i) {
-            float send1 = up ? s1[i] : s1[i + step];
-            float keep1 = up ? s1[i + step] : s1[i];
-            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
-            float send2 = up ? s2[i] : s2[i + step];
-            float keep2 = up ? s2[i + step] : s2[i];
-            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+            for (int i = 0; i < step; ++i) {
+              float send1 = up ? s1[i] : s1[i + step];
+              float keep1 = up ? s1[i + step] : s1[i];
+              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
+              float send2 = up ? s2[i] : s2[i + step];
+              float keep2 = up ? s2[i + step] : s2[i];
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+            }
+          }
+          int c = n0 + c0 + lane;
+          if (c < a.rows) {
+            atomicAdd(a.stats + c, s1[0]);
+            atomicAdd(a.stats + a.rows + c, s2[0]);
           }
         }
-        int c = n0 + c0 + lane;
-        if (c < a.rows) {
-          atomicAdd(a.stats + c, s1[0]);
-          atomicAdd(a.stats + a.rows + c, s2[0]);
-        }
       }
+      // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -617,6 +645,16 @@ static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t
   return MCD_OK;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 // spatial tile of `npix` pixels minimising padded area; ties -> wider tile
 static void pick_tile(int Ht, int Wt, int npix, int* TH, int* TW) {
   int64_t best = -1;
@@ -692,7 +730,10 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   int BN = ncover > 128 ? 256 : (ncover > 64 ? 128 : (ncover > 32 ? 64 : (ncover > 16 ? 32 : 16)));
   int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, BN);
   if (rc != MCD_OK) return rc;
-  dim3 grid((unsigned)(p.N * a.tiles_h * a.tiles_w), (unsigned)((ncover + BN - 1) / BN));
+  a.tiles_m = p.N * a.tiles_h * a.tiles_w;
+  a.tiles_n = (ncover + BN - 1) / BN;
+  const int slots = sm_count() * (BN <= 32 ? 2 : 1);        // persistent CTAs: one (thin tiles: two) per SM
+  dim3 grid((unsigned)min(a.tiles_m * a.tiles_n, slots));
   if (BN == 256) return launch_fprop_bn<256>(maps, a, grid, st);
   if (BN == 128) return launch_fprop_bn<128>(maps, a, grid, st);
   if (BN == 64) return launch_fprop_bn<64>(maps, a, grid, st);
