@@ -264,10 +264,12 @@ struct WgradCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = BN;
+  static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator
 };
 
-// grid: x = co tile (128), y = ci tile (BN), z = tap * ksplit + split
+// Persistent: work item = (pixel-range split, tap, co tile of 128, ci tile of BN); CTAs walk items round-robin,
+// the smem ring runs across items and the TMEM accumulator is double-buffered so that the fp32 partial-tile store
+// of item i overlaps the MMAs of item i+1.  Consecutive items share the pixel range (dY / X tiles stay in L2).
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ WgradArgs a) {
@@ -277,22 +279,21 @@ conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                                              ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BN;
-  const int t = blockIdx.z / a.ksplit, split = blockIdx.z % a.ksplit;
+  const int n_co = a.CoutP / 128, n_ci = a.CinP / BN;
+  const int per_split = a.T * n_co * n_ci;
+  const int total_items = per_split * a.ksplit;
   const int per = (a.ntiles + a.ksplit - 1) / a.ksplit;
-  const int tile_beg = split * per;
-  const int tile_end = min(tile_beg + per, a.ntiles);
-  const int ksteps = max(tile_end - tile_beg, 0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -300,89 +301,122 @@ conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const Tap tap = a.taps[t];
+
+#define MCD_WGRAD_DECODE(item)                                              \
+  const int split = (item) / per_split;                                     \
+  int rem_ = (item) % per_split;                                            \
+  const int ci0 = (rem_ % n_ci) * BN; rem_ /= n_ci;                         \
+  const int co0 = (rem_ % n_co) * 128; rem_ /= n_co;                        \
+  const int t = rem_;                                                       \
+  const int tile_beg = split * per;                                         \
+  const int ksteps = max(min(tile_beg + per, a.ntiles) - tile_beg, 0);
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const CUtensorMap* xmap = &maps.a[tap.map];
-      for (int ks = 0; ks < ksteps; ++ks) {
-        int tile = tile_beg + ks;
-        const int tw_i = tile % a.tiles_w; tile /= a.tiles_w;
-        const int th_i = tile % a.tiles_h; tile /= a.tiles_h;
-        const int n_img = tile;
-        const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
-        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        if (a.packed) {
-          // pixel order inside the tile is column-major (TW columns of TH rows) for both operands
-          for (int j = 0; j < a.TW; ++j) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        MCD_WGRAD_DECODE(item)
+        const Tap tap = a.taps[t];
+        const CUtensorMap* xmap = &maps.a[tap.map];
+        for (int ks = 0; ks < ksteps; ++ks) {
+          int tile = tile_beg + ks;
+          const int tw_i = tile % a.tiles_w; tile /= a.tiles_w;
+          const int th_i = tile % a.tiles_h; tile /= a.tiles_h;
+          const int n_img = tile;
+          const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (a.packed) {
+            // pixel order inside the tile is column-major (TW columns of TH rows) for both operands
+            for (int j = 0; j < a.TW; ++j) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                tma_load_4d(sa + i * Cfg::KPIX * 128 + j * a.TH * 128, &maps.b, &full_bar[stage],
+                            co0 + i * 64, tw0 + j, th0, n_img);
+              tma_load_3d(sb + j * a.TH * 128, xmap, &full_bar[stage],
+                          ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
+            }
+          } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-              tma_load_4d(sa + i * Cfg::KPIX * 128 + j * a.TH * 128, &maps.b, &full_bar[stage],
-                          co0 + i * 64, tw0 + j, th0, n_img);
-            tma_load_3d(sb + j * a.TH * 128, xmap, &full_bar[stage],
-                        ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
+              tma_load_4d(sa + i * Cfg::KPIX * 128, &maps.b, &full_bar[stage], co0 + i * 64, tw0, th0, n_img);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_4d(sb + i * Cfg::KPIX * 128, xmap, &full_bar[stage], ci0 + i * 64, tw0 + tap.mdw,
+                          th0 + tap.mdh, n_img);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            tma_load_4d(sa + i * Cfg::KPIX * 128, &maps.b, &full_bar[stage], co0 + i * 64, tw0, th0, n_img);
-#pragma unroll
-          for (int i = 0; i < BN / 64; ++i)
-            tma_load_4d(sb + i * Cfg::KPIX * 128, xmap, &full_bar[stage], ci0 + i * 64, tw0 + tap.mdw,
-                        th0 + tap.mdh, n_img);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = instr_desc_bf16(128, BN, 1, 1);
     int stage = 0; uint32_t phase = 0;
-    for (int ks = 0; ks < ksteps; ++ks) {
-      mbar_wait(&full_bar[stage], phase);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      MCD_WGRAD_DECODE(item)
+      (void)ci0; (void)co0; (void)t;
+      if (ksteps == 0) continue;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        // MN-major, 128B swizzle: LBO = bytes between 64-channel atoms, SBO = 8 pixel rows
-        const uint64_t adesc = smem_desc_sw128(sa, Cfg::KPIX * 128, 1024);
-        const uint64_t bdesc = smem_desc_sw128(sb, Cfg::KPIX * 128, 1024);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          // MN-major, 128B swizzle: LBO = bytes between 64-channel atoms, SBO = 8 pixel rows
+          const uint64_t adesc = smem_desc_sw128(sa, Cfg::KPIX * 128, 1024);
+          const uint64_t bdesc = smem_desc_sw128(sb, Cfg::KPIX * 128, 1024);
 #pragma unroll
-        for (int k = 0; k < Cfg::KPIX / 16; ++k)   // 16 pixel rows = 2048 bytes per UMMA_K step
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
-                    (ks | k) != 0);
-        umma_commit(&empty_bar[stage]);
-        if (ks == ksteps - 1) umma_commit(tmem_full_bar);
+          for (int k = 0; k < Cfg::KPIX / 16; ++k)   // 16 pixel rows = 2048 bytes per UMMA_K step
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (ks | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (ks == ksteps - 1) umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
-    float* o = a.ws + (((int64_t)split * a.T + t) * a.CoutP + co) * a.CinP + ci0;
-    if (ksteps > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      MCD_WGRAD_DECODE(item)
+      const int co = co0 + q * 32 + lane;
+      float* o = a.ws + (((int64_t)split * a.T + t) * a.CoutP + co) * a.CinP + ci0;
       if (ksteps > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
       }
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        if (ksteps > 0) {
+          tmem_ld32(tmem_d + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (ksteps > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   }
+#undef MCD_WGRAD_DECODE
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -887,7 +921,8 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, packed ? 1 : TW, TH);
   if (rc != MCD_OK) return rc;
 
-  dim3 grid((unsigned)(CoutP / 128), (unsigned)(CinP / BN), (unsigned)(a.T * ksplit));
+  const int total_items = (CoutP / 128) * (CinP / BN) * a.T * ksplit;
+  dim3 grid((unsigned)min(total_items, sm_count()));
   if (BN == 256) rc = launch_wgrad_bn<256>(maps, a, grid, st);
   else if (BN == 128) rc = launch_wgrad_bn<128>(maps, a, grid, st);
   else rc = launch_wgrad_bn<64>(maps, a, grid, st);

@@ -30,6 +30,23 @@ class bn_update_repeat:
         _bn_repeat = self.prev
 
 
+_overlap_wgrad = True
+_side_streams = {}
+
+
+def _side_stream(device):
+    s = _side_streams.get(device)
+    if s is None:
+        s = _side_streams[device] = torch.cuda.Stream(device)
+    return s
+
+
+def set_overlap_wgrad(flag):
+    global _overlap_wgrad
+    prev, _overlap_wgrad = _overlap_wgrad, bool(flag)
+    return prev
+
+
 def _as_nhwc_grad(dy):
     """Gradients arriving from autograd for an nhwc activation: make them nhwc bf16 again."""
     if ops.is_nhwc(dy):
@@ -59,10 +76,26 @@ class _ConvFn(torch.autograd.Function):
         g, mod = ctx.g, ctx.mod
         dy = ops.to_nhwc(dy) if ctx.planar else _as_nhwc_grad(dy)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if need_dx and need_dw and _overlap_wgrad:
+            # dgrad and wgrad both consume dy and are independent: wgrad runs on a side stream so that its CTAs
+            # fill the SMs the other kernel's last (partial) wave of tiles leaves idle.  Every use of the side
+            # stream is preceded by side.wait_stream(main), which also makes the caching allocator's per-stream
+            # reuse of the workspace / gradient blocks safe.
+            main = torch.cuda.current_stream(dy.device)
+            side = _side_stream(dy.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
             dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = ops.conv_wgrad(x, dy, g, want_dbias=ctx.has_bias and ctx.needs_input_grad[2])
+            main.wait_stream(side)
+            return dx, dw, db, None, None, None
+        if need_dx:
+            dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
+        if need_dw:
+            dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
         return dx, dw, db, None, None, None
 
 
