@@ -224,16 +224,19 @@ def run_ours(args):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps
 
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     for _ in range(args.warmup):
         step(src_d, lbl_d, tgt_d)
     # ---- roofline instrumentation: one eager iteration with a CUDA-event pair (on the launching stream) around
     #      every convolution launch; the timed region below replays the same kernels from a CUDA graph, where
     #      individual launches cannot be bracketed.
+    from mcd_b200 import nn as mcd_nn
+    prev_overlap = mcd_nn.set_overlap_wgrad(False)   # serialise dgrad / wgrad so each family is timed alone
     prof = ops.ConvProfiler()
     with prof:
         step(src_d, lbl_d, tgt_d)
     torch.cuda.synchronize()
+    mcd_nn.set_overlap_wgrad(prev_overlap)
     fam = prof.summary()
     if use_graph:
         step.capture(src_d, lbl_d, tgt_d, warmup=1)

@@ -51,7 +51,8 @@ class MCDStep:
         graph: the ~3500 kernel launches of an iteration are then replayed without any host work.  Inputs are
         copied into static buffers by `replay`."""
         from . import abi
-        assert self.world == 1, "graph capture is single-GPU (NCCL side-stream overlap is launched eagerly)"
+        # world > 1: the NCCL bucket all-reduces (side stream, forked / joined with stream waits) and the 4-float
+        # normaliser all-reduce are captured as graph nodes too; every rank replays the same sequence.
         dev = src_imgs.device
         self._static = (src_imgs.clone(), src_lbls.clone(), tgt_imgs.clone())
         side = torch.cuda.Stream(dev)
