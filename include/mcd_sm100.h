@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 5
+#define MCD_ABI_VERSION 6
 
 enum {
   MCD_OK = 0,
@@ -104,12 +104,13 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
 /* dx = conv_transpose(dy, w): gradient wrt the nhwc input.  w_packed is the mode-1 pack. */
 int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc,
                      const mcd_conv_geom* g, int algo, int device, void* stream);
-/* dw (fp32 OIHW, overwritten) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).
+/* dw (fp32 OIHW) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).  accumulate = 0 overwrites,
+ * 1 adds to the existing contents (gradient accumulation straight into param.grad / all-reduce buckets).
  * workspace: mcd_conv2d_wgrad_workspace() bytes. */
 size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo);
 int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, float* dbias,
-                     void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int algo,
-                     int device, void* stream);
+                     void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int accumulate,
+                     int algo, int device, void* stream);
 
 /* ---- BatchNorm2d (+ReLU, +residual)  (nn.BatchNorm2d defaults eps 1e-5 momentum 0.1:
  *      models/drn.py:34-59,129-131,167-169,199-204; --fix_bn: models/model_util.py:305-310) -------- */

@@ -6,14 +6,15 @@
 namespace mcd {
 int launch_direct_problem(const void* src, const void* w, const float* bias, void* out, int planar,
                           const TapProblem& p, cudaStream_t st);
-int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& g, cudaStream_t st);
-int colsum(const void* t, float* out, int64_t P, int C, int Cs, cudaStream_t st);
+int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& g, int accumulate,
+                 cudaStream_t st);
+int colsum(const void* t, float* out, int64_t P, int C, int Cs, int accumulate, cudaStream_t st);
 bool umma_problem_supported(const TapProblem& p);
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
                         float* stats, const TapProblem& p, cudaStream_t st);
 size_t umma_wgrad_workspace(const mcd_conv_geom& g);
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-               const mcd_conv_geom& g, cudaStream_t st);
+               const mcd_conv_geom& g, int accumulate, cudaStream_t st);
 int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaStream_t st);
 
 static int validate(const mcd_conv_geom* g) {
@@ -116,8 +117,8 @@ size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo) {
 }
 
 int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, float* dbias,
-                     void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int algo,
-                     int device, void* stream) {
+                     void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int accumulate,
+                     int algo, int device, void* stream) {
   MCD_ENTER(device);
   int rc = validate(g);
   if (rc != MCD_OK) return rc;
@@ -126,10 +127,10 @@ int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, fl
   bool supported = (g->stride == 1 || g->stride == 2);
   bool umma = use_umma(algo, supported, &rc);
   if (rc != MCD_OK) return rc;
-  rc = umma ? umma_wgrad(x_nhwc, dy_nhwc, dw_oihw, workspace, workspace_bytes, *g, st)
-            : wgrad_direct(x_nhwc, dy_nhwc, dw_oihw, *g, st);
+  rc = umma ? umma_wgrad(x_nhwc, dy_nhwc, dw_oihw, workspace, workspace_bytes, *g, accumulate, st)
+            : wgrad_direct(x_nhwc, dy_nhwc, dw_oihw, *g, accumulate, st);
   if (rc != MCD_OK) return rc;
-  if (dbias) return colsum(dy_nhwc, dbias, (int64_t)g->N * g->Ho * g->Wo, g->Cout, g->Cout_s, st);
+  if (dbias) return colsum(dy_nhwc, dbias, (int64_t)g->N * g->Ho * g->Wo, g->Cout, g->Cout_s, accumulate, st);
   return MCD_OK;
 }
 

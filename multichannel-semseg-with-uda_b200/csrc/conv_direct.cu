@@ -235,9 +235,12 @@ int launch_direct_problem(const void* src, const void* w, const float* bias, voi
   return check_launch("conv_direct");
 }
 
-int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& g, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.Cout * g.Cin * g.R * g.S, st);
-  if (e != cudaSuccess) { set_error("wgrad memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& g, int accumulate,
+                 cudaStream_t st) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.Cout * g.Cin * g.R * g.S, st);
+    if (e != cudaSuccess) { set_error("wgrad memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+  }
   int64_t npix = (int64_t)g.N * g.Ho * g.Wo;
   dim3 grid((unsigned)((npix + WG_PCH - 1) / WG_PCH),
             (unsigned)(((g.Cout + DT - 1) / DT) * ((g.Cin + DT - 1) / DT)), (unsigned)(g.R * g.S));
@@ -245,9 +248,11 @@ int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& 
   return check_launch("wgrad_direct");
 }
 
-int colsum(const void* t, float* out, int64_t P, int C, int Cs, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, st);
-  if (e != cudaSuccess) { set_error("colsum memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+int colsum(const void* t, float* out, int64_t P, int C, int Cs, int accumulate, cudaStream_t st) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, st);
+    if (e != cudaSuccess) { set_error("colsum memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+  }
   dim3 grid((unsigned)min64((P + 7) / 8, 148 * 4), (unsigned)((C + 31) / 32));
   colsum_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)t, out, P, C, Cs);
   return check_launch("colsum");

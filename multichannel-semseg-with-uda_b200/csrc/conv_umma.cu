@@ -543,7 +543,7 @@ conv_umma_wgrad_rows_kernel(const __grid_constant__ UmmaMaps maps, const __grid_
 // block = one co x 64 ci: coalesced reads along ci, transpose through smem, contiguous 64*T-float write.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit, int T, int CoutP,
-                    int CinP, int Cout, int Cin) {
+                    int CinP, int Cout, int Cin, int accumulate) {
   extern __shared__ float tile[];  // [64][T]
   const int co = blockIdx.x, ci0 = blockIdx.y * 64;
   const int nci = min(64, Cin - ci0);
@@ -559,12 +559,12 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ks
   }
   __syncthreads();
   float* o = dw + ((int64_t)co * Cin + ci0) * T;
-  for (int j = threadIdx.x; j < nci * T; j += blockDim.x) o[j] = tile[j];
+  for (int j = threadIdx.x; j < nci * T; j += blockDim.x) o[j] = accumulate ? o[j] + tile[j] : tile[j];
 }
 
 // packed: ws[split][r][co][s*Cs + c]  ->  dw[co][c][r][s]
 __global__ void wgrad_reduce_packed_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit,
-                                           int R, int S, int Cs, int CoutP, int Cout, int Cin) {
+                                           int R, int S, int Cs, int CoutP, int Cout, int Cin, int accumulate) {
   int64_t total = (int64_t)Cout * Cin * R * S;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -574,7 +574,7 @@ __global__ void wgrad_reduce_packed_kernel(const float* __restrict__ ws, float* 
     int co = (int)(i / ((int64_t)S * R * Cin));
     float acc = 0.f;
     for (int k = 0; k < ksplit; ++k) acc += ws[(((int64_t)k * R + r) * CoutP + co) * 64 + sx * Cs + c];
-    dw[i] = acc;
+    dw[i] = accumulate ? dw[i] + acc : acc;
   }
 }
 
@@ -804,7 +804,7 @@ static void wgrad_rows_shape(const mcd_conv_geom& g, int* TH, int* TW, int* ntil
 }
 
 static int umma_wgrad_rows(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-                           const mcd_conv_geom& g, cudaStream_t st) {
+                           const mcd_conv_geom& g, int accumulate, cudaStream_t st) {
   int TH, TW, ntiles, nsplit;
   wgrad_rows_shape(g, &TH, &TW, &ntiles, &nsplit);
   size_t need = sizeof(float) * (size_t)nsplit * g.R * 64 * 64;
@@ -845,7 +845,8 @@ static int umma_wgrad_rows(const void* x, const void* dy, float* dw, void* ws, s
   if (rc != MCD_OK) return rc;
   int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
   int rgrid = (int)min64((total + 255) / 256, 148 * 8);
-  wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, nsplit, g.R, g.S, g.Cin_s, 64, g.Cout, g.Cin);
+  wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, nsplit, g.R, g.S, g.Cin_s, 64, g.Cout, g.Cin,
+                                                    accumulate);
   return check_launch("wgrad_reduce");
 }
 
@@ -875,10 +876,10 @@ static int launch_wgrad_bn(const UmmaMaps& maps, const WgradArgs& a, dim3 grid, 
 }
 
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-               const mcd_conv_geom& g, cudaStream_t st) {
+               const mcd_conv_geom& g, int accumulate, cudaStream_t st) {
   if (g.stride != 1 && g.stride != 2) { set_error("umma wgrad: stride %d unsupported", g.stride); return MCD_E_INVALID; }
   if (g.R * g.S > kMaxTaps) { set_error("umma wgrad: too many taps"); return MCD_E_INVALID; }
-  if (wgrad_rows_ok(g)) return umma_wgrad_rows(x, dy, dw, ws, ws_bytes, g, st);
+  if (wgrad_rows_ok(g)) return umma_wgrad_rows(x, dy, dw, ws, ws_bytes, g, accumulate, st);
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
   const bool packed = packed_fprop_ok(g);
@@ -931,12 +932,13 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
   int rgrid = (int)min64((total + 255) / 256, 148 * 8);
   if (packed)
-    wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, g.R, g.S, g.Cin_s, CoutP, g.Cout, g.Cin);
+    wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, g.R, g.S, g.Cin_s, CoutP, g.Cout, g.Cin,
+                                                      accumulate);
   else
   {
     dim3 rg((unsigned)g.Cout, (unsigned)((g.Cin + 63) / 64));
     wgrad_reduce_kernel<<<rg, 256, sizeof(float) * 64 * a.T, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout,
-                                                                   g.Cin);
+                                                                   g.Cin, accumulate);
   }
   return check_launch("wgrad_reduce");
 }

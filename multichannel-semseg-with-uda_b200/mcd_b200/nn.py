@@ -41,6 +41,33 @@ def _side_stream(device):
     return s
 
 
+class DirectGrads:
+    """Context of MCDStep's backward passes: convolution weight gradients are written by the wgrad kernels
+    directly into param.grad on the side stream (see _ConvFn.backward) instead of travelling through autograd.
+    `join()` makes the main stream wait for them and releases the operands that were kept alive."""
+
+    def __init__(self):
+        self.keep = []
+
+    def __enter__(self):
+        global _direct
+        self.prev, _direct = _direct, self
+        return self
+
+    def __exit__(self, *a):
+        global _direct
+        _direct = self.prev
+
+    def join(self, device):
+        side = _side_streams.get(device)
+        if side is not None:
+            torch.cuda.current_stream(device).wait_stream(side)
+        self.keep.clear()
+
+
+_direct = None
+
+
 def set_overlap_wgrad(flag):
     global _overlap_wgrad
     prev, _overlap_wgrad = _overlap_wgrad, bool(flag)
@@ -79,6 +106,32 @@ class _ConvFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        if need_dw and _direct is not None:
+            # direct-gradient mode (MCDStep): wgrad is enqueued on the side stream and writes straight into
+            # param.grad (or its all-reduce bucket view); nothing is returned to autograd for the weights, so no
+            # accumulation kernel runs and the main stream goes on with dgrad / BatchNorm backward while the
+            # tensor-bound wgrad kernels trail behind.  MCDStep joins the side stream before optimizer.step().
+            main = torch.cuda.current_stream(dy.device)
+            side = _side_stream(dy.device)
+            side.wait_stream(main)
+            w, b = mod.weight, mod.bias
+            acc = getattr(w, "_mcd_written", False) and w.grad is not None
+            if w.grad is None:
+                w.grad = torch.empty_like(w)
+            if want_db and b.grad is None:
+                b.grad = torch.empty_like(b)
+            with torch.cuda.stream(side):
+                ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
+                               accumulate=acc)
+            w._mcd_written = True
+            _direct.keep.append((x, dy))          # keep the operands alive until the side stream is joined
+            for p in ((w, b) if want_db else (w,)):
+                sync = getattr(p, "_mcd_sync", None)
+                if sync is not None:
+                    sync.mark_ready(p, side)
+            if need_dx:
+                dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
+            return dx, None, None, None, None, None
         if need_dx and need_dw and _overlap_wgrad:
             # dgrad and wgrad both consume dy and are independent: wgrad runs on a side stream so that its CTAs
             # fill the SMs the other kernel's last (partial) wave of tiles leaves idle.  Every use of the side

@@ -187,15 +187,20 @@ def conv_dgrad(dy, w_packed_dgrad, g, algo=None):
     return dx
 
 
-def conv_wgrad(x, dy, g, want_dbias=False, algo=None):
+def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):
+    """dw (fp32 OIHW) and optionally dbias.  `out_dw` / `out_db` (e.g. param.grad or an all-reduce bucket view)
+    are written in place - overwritten, or added to when `accumulate`."""
     assert is_nhwc(x) and is_nhwc(dy)
     algo = _algo if algo is None else algo
-    dw = torch.empty((g.Cout, g.Cin, g.R, g.S), dtype=F32, device=x.device)
-    db = torch.empty(g.Cout, dtype=F32, device=x.device) if want_dbias else None
+    dw = out_dw if out_dw is not None else torch.empty((g.Cout, g.Cin, g.R, g.S), dtype=F32, device=x.device)
+    db = None
+    if want_dbias:
+        db = out_db if out_db is not None else torch.empty(g.Cout, dtype=F32, device=x.device)
+    assert dw.is_contiguous() and dw.dtype == F32 and dw.numel() == g.Cout * g.Cin * g.R * g.S
     nbytes = int(abi.lib().mcd_conv2d_wgrad_workspace(ctypes.byref(g), algo))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
-    abi.check(abi.lib().mcd_conv2d_wgrad(_p(x), _p(dy), _p(dw), _p(db), _p(ws), nbytes,
-                                         ctypes.byref(g), algo, _dev(x), _stream(x)), "conv2d_wgrad")
+    abi.check(abi.lib().mcd_conv2d_wgrad(_p(x), _p(dy), _p(dw), _p(db), _p(ws), nbytes, ctypes.byref(g),
+                                         int(accumulate), algo, _dev(x), _stream(x)), "conv2d_wgrad")
     return dw, db
 
 
@@ -458,6 +463,6 @@ def conv_dgrad(dy, w_packed_dgrad, g, algo=None):  # noqa: F811
     return _profiled("conv_fprop_kernel (dgrad)", g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo))
 
 
-def conv_wgrad(x, dy, g, want_dbias=False, algo=None):  # noqa: F811
+def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):  # noqa: F811
     return _profiled("conv_wgrad_kernel (+split-K reduce)", g,
-                     lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo))
+                     lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo, out_dw, out_db, accumulate))

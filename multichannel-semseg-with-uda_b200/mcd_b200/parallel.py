@@ -21,11 +21,12 @@ import torch.distributed as dist
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "pending", "work", "event")
+    __slots__ = ("flat", "params", "pending", "work", "event", "streams")
 
     def __init__(self, flat, params):
         self.flat, self.params = flat, params
         self.pending, self.work, self.event = 0, None, None
+        self.streams = []
 
 
 class GradSync:
@@ -66,18 +67,22 @@ class GradSync:
         for p in params:
             p.grad = flat[off:off + p.numel()].view_as(p)
             self._by_param[p] = b
+            p._mcd_sync = self
             off += p.numel()
         self.buckets.append(b)
 
     # ---------------------------------------------------------------------------------------------
     def zero_and_arm(self, armed=True):
         """zero the flat gradients (re-attaching the views if something replaced .grad) and arm the hooks."""
+        for p in self.params:
+            p._mcd_written = False
         if not self.flat:
             for p in self.params:
                 p.grad = None
             return
         for b in self.buckets:
             b.flat.zero_()
+            b.streams = []
             off = 0
             for p in b.params:
                 g = p.grad
@@ -98,9 +103,21 @@ class GradSync:
         if b.pending == 0:
             self._launch(b)
 
+    def mark_ready(self, p, stream=None):
+        """gradient of `p` has been written into its bucket view by a kernel enqueued on `stream` (direct-gradient
+        mode of mcd_b200.nn: no autograd accumulation, hence no hook) - same bookkeeping as the hook."""
+        if not self.flat:
+            return
+        b = self._by_param[p]
+        if stream is not None and stream not in b.streams:
+            b.streams.append(stream)
+        self._on_grad_ready(p)
+
     def _launch(self, b):
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream(b.flat.device))
+            for st in b.streams:
+                self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
                 b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:

@@ -97,18 +97,26 @@ class MCDStep:
         if self._arena is None or self._arena.buf.device != src_imgs.device:
             self._arena = ops.ZeroArena(src_imgs.device)
         prev_arena = ops.set_arena(self._arena)
+        from .nn import DirectGrads
         try:
             self._arena.begin()            # ONE memset for all BatchNorm-statistic / loss accumulators
-            return self._iteration(crit, src_imgs, src_lbls, tgt_imgs)
+            with DirectGrads() as self._dg:
+                self._dev = src_imgs.device
+                return self._iteration(crit, src_imgs, src_lbls, tgt_imgs)
         finally:
             ops.set_arena(prev_arena)
+
+    def _backward(self, loss):
+        """loss.backward() + join of the side stream that carries the convolution weight gradients."""
+        loss.backward()
+        self._dg.join(self._dev)
 
     def _iteration(self, crit, src_imgs, src_lbls, tgt_imgs):
         # ---- A: source supervised; updates G, F1, F2
         self.sync_g.zero_and_arm(), self.sync_f.zero_and_arm()
         o1, o2 = self._heads(self._gen(src_imgs))
         loss = crit(o1, src_lbls) + crit(o2, src_lbls)
-        loss.backward()
+        self._backward(loss)
         c_loss = loss.detach()
         self.sync_g.wait(), self.sync_f.wait()
         self.optimizer_g.step(), self.optimizer_f.step()
@@ -134,7 +142,7 @@ class MCDStep:
         loss = crit(o1, src_lbls) + crit(o2, src_lbls)
         t1, t2 = self._heads(feats_t)
         loss = loss - self._disc(t1, t2)
-        loss.backward()
+        self._backward(loss)
         self.sync_f.wait()
         self.optimizer_f.step()
         # ---- C x num_k: generator minimises the discrepancy; only optimizer_g steps
@@ -150,7 +158,7 @@ class MCDStep:
             feats_t_graph = None
             t1, t2 = self._heads(feats)
             loss = self._disc(t1, t2) * self.mult
-            loss.backward()
+            self._backward(loss)
             self.sync_g.wait()
             self.optimizer_g.step()
         if not self.exact:
