@@ -113,13 +113,20 @@ class _ConvFn(torch.autograd.Function):
             # tensor-bound wgrad kernels trail behind.  MCDStep joins the side stream before optimizer.step().
             main = torch.cuda.current_stream(dy.device)
             side = _side_stream(dy.device)
-            side.wait_stream(main)
+            ready = torch.cuda.Event()
+            ready.record(main)                    # dy (and everything before it) is complete here
             w, b = mod.weight, mod.bias
             acc = getattr(w, "_mcd_written", False) and w.grad is not None
             if w.grad is None:
                 w.grad = torch.empty_like(w)
             if want_db and b.grad is None:
                 b.grad = torch.empty_like(b)
+            # dgrad is enqueued FIRST: it heads the critical path (dgrad -> BatchNorm backward -> next dgrad) and
+            # cannot share an SM with the persistent wgrad CTAs (both want ~190 KB of shared memory); the wgrad
+            # that follows on the side stream then overlaps the memory-bound BatchNorm kernels of the next unit.
+            if need_dx:
+                dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
+            side.wait_event(ready)
             with torch.cuda.stream(side):
                 ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
                                accumulate=acc)
@@ -129,8 +136,6 @@ class _ConvFn(torch.autograd.Function):
                 sync = getattr(p, "_mcd_sync", None)
                 if sync is not None:
                     sync.mark_ready(p, side)
-            if need_dx:
-                dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
             return dx, None, None, None, None, None
         if need_dx and need_dw and _overlap_wgrad:
             # dgrad and wgrad both consume dy and are independent: wgrad runs on a side stream so that its CTAs
