@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 6
+#define MCD_ABI_VERSION 8
 
 enum {
   MCD_OK = 0,
@@ -91,6 +91,11 @@ int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, in
  * Cs = Cout_s, flipped filter).  Which pack a convolution wants: mcd_conv2d_pack_kind(). */
 int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs,
                          int mode, int device, void* stream);
+/* Multi-tensor re-pack: one launch for all convolutions of a model (after optimizer.step()).  items_dev:
+ * device array of n_items x 8 int64 {w ptr, dst ptr, Cout, Cin, R, S, mode, Cs}; mode 0/1 = mcd_pack_weight
+ * fprop/dgrad, 2/3 = mcd_pack_weight_rows fprop/dgrad. */
+int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per_item, int device,
+                           void* stream);
 /* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows() layout for (geometry, pass, algo);
  * pass: 0 = fprop, 1 = dgrad. */
 int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
@@ -187,11 +192,13 @@ int mcd_ce2d_fwd(const void* logits, const int64_t* target, const float* weight,
 int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
                  int64_t ignore_index, const float* acc, const float* gscale, void* dlogits, int N,
                  int C, int H, int W, int device, void* stream);
-/* Diff2d: mean |softmax(a) - softmax(b)| over N*C*H*W.  acc[0] += sum |.| */
-int mcd_diff2d_fwd(const void* a, const void* b, float* acc, int N, int C, int H, int W, int device,
-                   void* stream);
-int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, void* da, void* db, int N,
-                   int C, int H, int W, int device, void* stream);
+/* Diff2d: mean |softmax(a) - softmax(b)| over N*C*H*W.  acc[0] += sum |.|
+ * stats (fp32 [N*H*W*4], may be NULL): per-pixel (max_a, 1/sumexp_a, max_b, 1/sumexp_b) written by the forward
+ * and consumed by the backward, which then skips its two statistic passes. */
+int mcd_diff2d_fwd(const void* a, const void* b, float* acc, float* stats, int N, int C, int H, int W,
+                   int device, void* stream);
+int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, const float* stats, void* da, void* db,
+                   int N, int C, int H, int W, int device, void* stream);
 /* F.mse_loss(pred, target) with pred planar bf16, target planar fp32: acc[0] += sum (p-t)^2 */
 int mcd_mse_fwd(const void* pred, const float* target, float* acc, int64_t numel, int device,
                 void* stream);

@@ -787,7 +787,7 @@ static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, 
   else pick_tile(g.Ho, g.Wo, 64, TH, TW);
   *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
   int base = (*CoutP / 128) * (*CinP / *BN) * g.R * (packed ? 1 : g.S);
-  int ks = (2 * 148) / base;               // at most two full waves of CTAs
+  int ks = sm_count() / base;               // one work item per persistent CTA; fewer splits = less partial traffic
   ks = max(1, min(ks, *ntiles));
   ks = min(ks, 64);
   *ksplit = ks;

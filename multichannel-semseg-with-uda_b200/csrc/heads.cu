@@ -109,38 +109,48 @@ deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
   }
 }
 
-// dw[c][kh][kw] += sum_{(n,ih) in this block's chunk} sum_iw x[n,c,ih,iw] * dout[n,c,8ih-4+kh,8iw-4+kw]
-// grid: (C*16 [c,kh], nsplit chunks of (n,ih) rows); block 256 = 16 kw x 16 iw lanes; dw is pre-zeroed.
+// dw[c][kh][kw] += sum_{(n,ih) rows of this block} sum_ow x[n,c,ih,iw] * dout[n,c,8ih-4+kh,ow],  ow = 8iw-4+kw
+// A lane walks ow = lane, lane+32, ...: its (ow+4)&7 = kw0 is fixed, and every dout element feeds exactly two
+// bins, (iw0 = (ow+4)>>3, kw0) and (iw0-1, kw0+8).  Output rows are read coalesced, exactly once.
+// grid: (C*16 [c,kh], nsplit chunks of (n,ih) rows); block 256 = 8 warps, one row per warp-iteration; dw pre-zeroed.
 __global__ void __launch_bounds__(256)
 deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ x,
                          float* __restrict__ dw, int N, int C, int h, int wd) {
-  __shared__ float red[16][17];
+  __shared__ float red[8][16];
   const int c = blockIdx.x >> 4, kh = blockIdx.x & 15;
-  const int kw = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = h * 8, W = wd * 8;
   const int rows = N * h;
   const int per = (rows + gridDim.y - 1) / gridDim.y;
   const int r_beg = blockIdx.y * per, r_end = min(r_beg + per, rows);
-  float acc = 0.f;
-  for (int rr = r_beg; rr < r_end; ++rr) {
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int rr = r_beg + warp; rr < r_end; rr += 8) {
     const int n = rr / h, ih = rr % h;
     const int oh = 8 * ih - 4 + kh;
     if (oh < 0 || oh >= H) continue;
     const __nv_bfloat16* dp = dout + (((int64_t)n * C + c) * H + oh) * W;
     const float* xp = x + (((int64_t)n * C + c) * h + ih) * wd;
-    for (int iw = pl; iw < wd; iw += 16) {
-      const int ow = 8 * iw - 4 + kw;
-      if (ow < 0 || ow >= W) continue;
-      acc = fmaf(xp[iw], bf2f(dp[ow]), acc);
+    for (int ow = lane; ow < W; ow += 32) {
+      const float d = bf2f(dp[ow]);
+      const int iw0 = (ow + 4) >> 3;
+      if (iw0 < wd) acc0 = fmaf(xp[iw0], d, acc0);
+      if (iw0 >= 1) acc1 = fmaf(xp[iw0 - 1], d, acc1);
     }
   }
-  red[pl][kw] = acc;
+  // lanes l, l+8, l+16, l+24 share kw0 = (l+4)&7
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 8);  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
+  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
+  if (lane < 8) {
+    const int kw0 = (lane + 4) & 7;
+    red[warp][kw0] = acc0;
+    red[warp][kw0 + 8] = acc1;
+  }
   __syncthreads();
-  if (pl == 0) {
+  if (threadIdx.x < 16) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s += red[k][kw];
-    atomicAdd(dw + c * 256 + kh * 16 + kw, s);
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    atomicAdd(dw + c * 256 + kh * 16 + threadIdx.x, s);
   }
 }
 

@@ -95,6 +95,54 @@ __global__ void pack_weight_rows_kernel(const float* __restrict__ w, __nv_bfloat
   }
 }
 
+// ---- multi-tensor re-pack: ONE launch refreshes every bf16 shadow of a model after an optimizer step ------
+// item (8 x int64 in device memory): w ptr, dst ptr, Cout, Cin, R, S, mode, cs
+//   mode 0/1: pack_weight fprop/dgrad layout   mode 2/3: pack_weight_rows fprop/dgrad layout (cs = channel stride)
+__global__ void pack_weights_multi_kernel(const int64_t* __restrict__ items) {
+  const int64_t* it = items + (int64_t)blockIdx.x * 8;
+  const float* w = reinterpret_cast<const float*>(it[0]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(it[1]);
+  const int Cout = (int)it[2], Cin = (int)it[3], R = (int)it[4], S = (int)it[5], mode = (int)it[6], Cs = (int)it[7];
+  const int T = R * S;
+  if (mode < 2) {
+    const int rows = mode ? Cin : Cout;
+    const int kc_pad = ((mode ? Cout : Cin) + 63) / 64 * 64;
+    const int64_t total = (int64_t)rows * T * kc_pad;
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
+      int kc = (int)(i % kc_pad);
+      int t = (int)((i / kc_pad) % T);
+      int row = (int)(i / ((int64_t)kc_pad * T));
+      float v = 0.f;
+      if (mode == 0) {
+        if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S];
+      } else if (kc < Cout) {
+        int r = R - 1 - t / S, s = S - 1 - t % S;
+        v = w[(((int64_t)kc * Cin + row) * R + r) * S + s];
+      }
+      dst[i] = f2bf(v);
+    }
+  } else {
+    const int m = mode - 2;
+    const int rows = m ? Cin : Cout;
+    const int64_t total = (int64_t)rows * R * 64;
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
+      int k = (int)(i % 64);
+      int r = (int)((i / 64) % R);
+      int row = (int)(i / (64 * (int64_t)R));
+      int s = k / Cs, c = k % Cs;
+      float v = 0.f;
+      if (s < S) {
+        if (m == 0) {
+          if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s];
+        } else if (c < Cout) {
+          v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
+        }
+      }
+      dst[i] = f2bf(v);
+    }
+  }
+}
+
 }  // namespace mcd
 
 using namespace mcd;
@@ -154,6 +202,16 @@ int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int 
   pack_weight_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
                                                                    R, S, Cs, mode, rows);
   return check_launch("pack_weight_rows");
+}
+
+int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per_item, int device,
+                           void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(items_dev && n_items > 0 && blocks_per_item > 0 && blocks_per_item <= 65535,
+              "pack_weights_multi: bad arguments");
+  dim3 grid((unsigned)n_items, (unsigned)blocks_per_item);
+  pack_weights_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(items_dev);
+  return check_launch("pack_weights_multi");
 }
 
 }  // extern "C"

@@ -102,7 +102,7 @@ ce2d_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restr
 
 __global__ void __launch_bounds__(256)
 diff2d_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                  float* __restrict__ acc, int C, int64_t HW, int64_t npairs) {
+                  float* __restrict__ acc, float4* __restrict__ stats, int C, int64_t HW, int64_t npairs) {
   __shared__ float red[32];
   float lsum = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
@@ -115,6 +115,10 @@ diff2d_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
     softmax_stats(pa, C, HW, &ma, &sa);
     softmax_stats(pb, C, HW, &mb, &sb);
     const float ia0 = 1.f / sa.x, ia1 = 1.f / sa.y, ib0 = 1.f / sb.x, ib1 = 1.f / sb.y;
+    if (stats) {   // per-pixel (max_a, 1/sum_a, max_b, 1/sum_b): the backward kernel skips its two statistic passes
+      stats[pix] = make_float4(ma.x, ia0, mb.x, ib0);
+      stats[pix + 1] = make_float4(ma.y, ia1, mb.y, ib1);
+    }
     for (int c = 0; c < C; ++c) {
       float2 va = ld2(pa + c * HW), vb = ld2(pb + c * HW);
       lsum += fabsf(__expf(va.x - ma.x) * ia0 - __expf(vb.x - mb.x) * ib0);
@@ -129,8 +133,9 @@ __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0
 
 __global__ void __launch_bounds__(256)
 diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                  const float* __restrict__ gscale, __nv_bfloat16* __restrict__ da,
-                  __nv_bfloat16* __restrict__ db, float inv_numel, int C, int64_t HW, int64_t npairs) {
+                  const float* __restrict__ gscale, const float4* __restrict__ stats,
+                  __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ db, float inv_numel, int C,
+                  int64_t HW, int64_t npairs) {
   const float coef = gscale[0] * inv_numel;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -139,10 +144,18 @@ diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
     const int64_t off = n * C * HW + hw;
     const __nv_bfloat16* pa = a + off;
     const __nv_bfloat16* pb = b + off;
-    float2 ma, sa, mb, sb;
-    softmax_stats(pa, C, HW, &ma, &sa);
-    softmax_stats(pb, C, HW, &mb, &sb);
-    const float ia0 = 1.f / sa.x, ia1 = 1.f / sa.y, ib0 = 1.f / sb.x, ib1 = 1.f / sb.y;
+    float2 ma, mb;
+    float ia0, ia1, ib0, ib1;
+    if (stats) {
+      const float4 s0 = stats[pix], s1 = stats[pix + 1];
+      ma = make_float2(s0.x, s1.x); mb = make_float2(s0.z, s1.z);
+      ia0 = s0.y; ia1 = s1.y; ib0 = s0.w; ib1 = s1.w;
+    } else {
+      float2 sa, sb;
+      softmax_stats(pa, C, HW, &ma, &sa);
+      softmax_stats(pb, C, HW, &mb, &sb);
+      ia0 = 1.f / sa.x; ia1 = 1.f / sa.y; ib0 = 1.f / sb.x; ib1 = 1.f / sb.y;
+    }
     // dot products  sum_c sign_c * p_c  for both distributions
     float da0 = 0.f, da1 = 0.f, db0 = 0.f, db1 = 0.f;
     for (int c = 0; c < C; ++c) {
@@ -333,27 +346,27 @@ int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
   return check_launch("ce2d_bwd");
 }
 
-int mcd_diff2d_fwd(const void* a, const void* b, float* acc, int N, int C, int H, int W, int device,
-                   void* stream) {
+int mcd_diff2d_fwd(const void* a, const void* b, float* acc, float* stats, int N, int C, int H, int W,
+                   int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(a && b && acc, "diff2d_fwd: null pointer");
   MCD_CHECK_PLANAR("diff2d_fwd");
   int64_t npairs = (int64_t)N * H * W / 2;
   diff2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, C, (int64_t)H * W, npairs);
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, (float4*)stats, C, (int64_t)H * W, npairs);
   return check_launch("diff2d_fwd");
 }
 
-int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, void* da, void* db, int N,
-                   int C, int H, int W, int device, void* stream) {
+int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, const float* stats, void* da, void* db,
+                   int N, int C, int H, int W, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(a && b && gscale && da && db, "diff2d_bwd: null pointer");
   MCD_CHECK_PLANAR("diff2d_bwd");
   int64_t npairs = (int64_t)N * H * W / 2;
   float inv = (float)(1.0 / ((double)N * C * H * W));
   diff2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (__nv_bfloat16*)da, (__nv_bfloat16*)db,
-      inv, C, (int64_t)H * W, npairs);
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (const float4*)stats, (__nv_bfloat16*)da,
+      (__nv_bfloat16*)db, inv, C, (int64_t)H * W, npairs);
   return check_launch("diff2d_bwd");
 }
 

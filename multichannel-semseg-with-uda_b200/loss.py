@@ -93,14 +93,18 @@ class CrossEntropyLoss2d(nn.Module):
 class _Diff2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
-        acc = ops.diff2d_fwd(a, b)
-        ctx.save_for_backward(a, b)
+        need_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if need_bwd:
+            acc, stats = ops.diff2d_fwd(a, b, want_stats=True)
+        else:
+            acc, stats = ops.diff2d_fwd(a, b), None
+        ctx.save_for_backward(a, b, stats)
         return acc[0] / float(a.numel())
 
     @staticmethod
     def backward(ctx, go):
-        a, b = ctx.saved_tensors
-        da, db = ops.diff2d_bwd(a, b, _gscale(go))
+        a, b, stats = ctx.saved_tensors
+        da, db = ops.diff2d_bwd(a, b, _gscale(go), stats)
         return da, db
 
 

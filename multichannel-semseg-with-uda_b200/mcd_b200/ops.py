@@ -149,6 +149,34 @@ def pack_weight_for(w, g, mode, algo=None):
     return out
 
 
+class MultiPacker:
+    """Refreshes every packed bf16 weight shadow of a set of Conv2d modules with ONE kernel launch (instead of
+    one or two launches per convolution) - called by MCDStep right after optimizer.step()."""
+
+    def __init__(self, convs):
+        rows, self.entries = [], []
+        for conv in convs:
+            w = conv.weight
+            co, ci, r, s = w.shape
+            for key, (tag, packed) in conv._packs.items():
+                mode, kind, cs = key
+                rows.append([w.data_ptr(), packed.data_ptr(), co, ci, r, s, mode + 2 * kind, cs])
+                self.entries.append((conv, key, packed))
+        self.n = len(rows)
+        self.table = torch.tensor(rows, dtype=torch.int64, device=convs[0].weight.device) if rows else None
+        self.dev = convs[0].weight.device if convs else None
+
+    def repack(self):
+        if not self.n:
+            return
+        abi.check(abi.lib().mcd_pack_weights_multi(_p(self.table), self.n, 32, self.dev.index,
+                                                   ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
+                  "pack_weights_multi")
+        for conv, key, packed in self.entries:
+            w = conv.weight
+            conv._packs[key] = ((w._version, w.data_ptr()), packed)
+
+
 def pack_key(g, mode, algo=None):
     algo = _algo if algo is None else algo
     kind = int(abi.lib().mcd_conv2d_pack_kind(ctypes.byref(g), mode, algo))
@@ -343,17 +371,19 @@ def ce2d_bwd(logits, target, weight, ignore_index, acc, gscale):
     return d
 
 
-def diff2d_fwd(a, b):
+def diff2d_fwd(a, b, want_stats=False):
     n, c, h, w = a.shape
     acc = zeros_f32(1, a.device)
-    abi.check(abi.lib().mcd_diff2d_fwd(_p(a), _p(b), _p(acc), n, c, h, w, _dev(a), _stream(a)), "diff2d_fwd")
-    return acc
+    stats = torch.empty((n, h, w, 4), dtype=F32, device=a.device) if want_stats else None
+    abi.check(abi.lib().mcd_diff2d_fwd(_p(a), _p(b), _p(acc), _p(stats), n, c, h, w, _dev(a), _stream(a)),
+              "diff2d_fwd")
+    return (acc, stats) if want_stats else acc
 
 
-def diff2d_bwd(a, b, gscale):
+def diff2d_bwd(a, b, gscale, stats=None):
     n, c, h, w = a.shape
     da, db = torch.empty_like(a), torch.empty_like(b)
-    abi.check(abi.lib().mcd_diff2d_bwd(_p(a), _p(b), _p(gscale), _p(da), _p(db), n, c, h, w, _dev(a),
+    abi.check(abi.lib().mcd_diff2d_bwd(_p(a), _p(b), _p(gscale), _p(stats), _p(da), _p(db), n, c, h, w, _dev(a),
                                        _stream(a)), "diff2d_bwd")
     return da, db
 

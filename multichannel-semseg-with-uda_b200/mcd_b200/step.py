@@ -14,6 +14,11 @@ import torch
 from . import parallel
 
 
+def ops_mod():
+    from . import ops
+    return ops
+
+
 class MCDStep:
     """method 'MCD' (early fusion): models = (model_g, model_f1, model_f2);
     method 'MFNet': models = (model_g_3ch, model_g_1ch, model_f1, model_f2)."""
@@ -41,6 +46,7 @@ class MCDStep:
         self.sync_g = parallel.GradSync(g_params, process_group, bucket_mb)
         self.sync_f = parallel.GradSync(f_params, process_group, bucket_mb)
         self._arena = None
+        self._packer_g = None
         self.world = self.sync_g.world
         if self.world > 1 and hasattr(criterion, "set_process_group"):
             criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
@@ -106,6 +112,15 @@ class MCDStep:
         finally:
             ops.set_arena(prev_arena)
 
+    def _step_g(self):
+        """optimizer_g.step() + ONE multi-tensor kernel that refreshes all packed bf16 weight shadows of G."""
+        self.optimizer_g.step()
+        if self._packer_g is None:
+            from .nn import Conv2d
+            convs = [m for g in self.gens for m in g.modules() if isinstance(m, Conv2d) and m._packs]
+            self._packer_g = ops_mod().MultiPacker(convs)
+        self._packer_g.repack()
+
     def _backward(self, loss):
         """loss.backward() + join of the side stream that carries the convolution weight gradients."""
         loss.backward()
@@ -119,7 +134,7 @@ class MCDStep:
         self._backward(loss)
         c_loss = loss.detach()
         self.sync_g.wait(), self.sync_f.wait()
-        self.optimizer_g.step(), self.optimizer_f.step()
+        self._step_g(), self.optimizer_f.step()
         # ---- B: classifiers maximise the discrepancy on target; only optimizer_f steps
         self.sync_f.zero_and_arm()
         if self.exact:
@@ -160,7 +175,7 @@ class MCDStep:
             loss = self._disc(t1, t2) * self.mult
             self._backward(loss)
             self.sync_g.wait()
-            self.optimizer_g.step()
+            self._step_g()
         if not self.exact:
             for p in self.sync_f.params:
                 p.requires_grad_(True)
