@@ -60,6 +60,8 @@ class MCDStep:
         # world > 1: the NCCL bucket all-reduces (side stream, forked / joined with stream waits) and the 4-float
         # normaliser all-reduce are captured as graph nodes too; every rank replays the same sequence.
         dev = src_imgs.device
+        if self._packer_g is None:
+            warmup = max(warmup, 1)        # lazily built host tables (weight re-pack list) need one eager iteration
         self._static = (src_imgs.clone(), src_lbls.clone(), tgt_imgs.clone())
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))

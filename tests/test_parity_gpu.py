@@ -358,9 +358,9 @@ def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
     for _ in range(iters):
         c_o, d_o = O.mcd_step_early(G, F1, F2, src, lbl, tgt, w, og, of, num_k=4)
     if graph:
-        # capture() runs one warm-up iteration eagerly, then replays: 1 eager + 1 replay = 2 iterations
-        step.capture(src, lbl, tgt, warmup=0)          # capture itself does not execute
+        # 1 eager iteration + 1 graph replay = 2 iterations (capturing does not execute anything)
         step(src, lbl, tgt)
+        step.capture(src, lbl, tgt, warmup=0)
         c, d = step.replay(src, lbl, tgt)
     else:
         for _ in range(iters):
