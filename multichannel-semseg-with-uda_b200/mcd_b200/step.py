@@ -72,7 +72,10 @@ class MCDStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = abi.launch_count()
-        with torch.cuda.graph(self.graph):
+        # capture on a HIGH-priority stream: the critical path (forward, dgrad, BatchNorm) then outranks the wgrad
+        # kernels that trail on the default-priority side stream when both compete for SMs
+        cap_stream = torch.cuda.Stream(dev, priority=-1)
+        with torch.cuda.graph(self.graph, stream=cap_stream):
             self._static_out = self(*self._static)
         self.launches_per_replay = abi.launch_count() - n0
         return self
