@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 8
+#define MCD_ABI_VERSION 9
 
 enum {
   MCD_OK = 0,
@@ -92,8 +92,9 @@ int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, in
 int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs,
                          int mode, int device, void* stream);
 /* Multi-tensor re-pack: one launch for all convolutions of a model (after optimizer.step()).  items_dev:
- * device array of n_items x 8 int64 {w ptr, dst ptr, Cout, Cin, R, S, mode, Cs}; mode 0/1 = mcd_pack_weight
- * fprop/dgrad, 2/3 = mcd_pack_weight_rows fprop/dgrad. */
+ * device array of n_items x 12 int64 {w, dst_fprop, dst_dgrad (0 = absent), Cout, Cin, R, S, kind_fprop,
+ * kind_dgrad (mcd_conv2d_pack_kind), Cs_fprop, Cs_dgrad, 0}.  The destination buffers must have been produced
+ * once by mcd_pack_weight / mcd_pack_weight_rows (their zero padding is kept). */
 int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per_item, int device,
                            void* stream);
 /* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows() layout for (geometry, pass, algo);
@@ -106,8 +107,10 @@ int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
 int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias, void* y,
                      int y_layout, float* stats, const mcd_conv_geom* g, int algo, int device,
                      void* stream);
-/* dx = conv_transpose(dy, w): gradient wrt the nhwc input.  w_packed is the mode-1 pack. */
-int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc,
+/* dx = conv_transpose(dy, w) (+ add_nhwc): gradient wrt the nhwc input.  w_packed is the mode-1 pack.
+ * add_nhwc (may be NULL): tensor of dx's geometry added in the epilogue - the gradient that reaches the same
+ * activation through the identity shortcut of a BasicBlock (models/drn.py:53-58), saving a separate add pass. */
+int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc, const void* add_nhwc,
                      const mcd_conv_geom* g, int algo, int device, void* stream);
 /* dw (fp32 OIHW) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).  accumulate = 0 overwrites,
  * 1 adds to the existing contents (gradient accumulation straight into param.grad / all-reduce buckets).

@@ -5,13 +5,13 @@
 
 namespace mcd {
 int launch_direct_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                          const TapProblem& p, cudaStream_t st);
+                          const void* addend, const TapProblem& p, cudaStream_t st);
 int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& g, int accumulate,
                  cudaStream_t st);
 int colsum(const void* t, float* out, int64_t P, int C, int Cs, int accumulate, cudaStream_t st);
 bool umma_problem_supported(const TapProblem& p);
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                        float* stats, const TapProblem& p, cudaStream_t st);
+                        float* stats, const void* addend, const TapProblem& p, cudaStream_t st);
 size_t umma_wgrad_workspace(const mcd_conv_geom& g);
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                const mcd_conv_geom& g, int accumulate, cudaStream_t st);
@@ -63,9 +63,9 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
   if (rc != MCD_OK) return rc;
   if (umma) {
     if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p);   // w_packed is then the mcd_pack_weight_rows layout
-    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, p, st);
+    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, nullptr, p, st);
   }
-  rc = launch_direct_problem(x_nhwc, w_packed, bias, y, planar, p, st);
+  rc = launch_direct_problem(x_nhwc, w_packed, bias, y, planar, nullptr, p, st);
   if (rc != MCD_OK) return rc;
   if (stats) {
     MCD_REQUIRE(!planar, "conv fprop: fused BN statistics need the nhwc output layout");
@@ -74,7 +74,7 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
   return MCD_OK;
 }
 
-int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc,
+int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc, const void* add_nhwc,
                      const mcd_conv_geom* g, int algo, int device, void* stream) {
   MCD_ENTER(device);
   int rc = validate(g);
@@ -86,20 +86,22 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
   int np = plan_dgrad(*g, p);
   if (algo != MCD_ALGO_DIRECT && packed_dgrad_ok(*g) && umma_problem_supported(p[0])) {
     plan_dgrad_packed(*g, p[0]);                          // w_packed_dgrad: mcd_pack_weight_rows mode 1
-    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, p[0], st);
+    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, add_nhwc, p[0], st);
   }
   bool any_empty = false;
   for (int i = 0; i < np; ++i) any_empty |= (p[i].ntaps == 0);
-  if (any_empty) {
-    cudaError_t e = cudaMemsetAsync(dx_nhwc, 0, (size_t)g->N * g->H * g->W * g->Cin_s * 2, st);
-    if (e != cudaSuccess) { set_error("dgrad memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+  if (any_empty) {   // parity classes without taps: dx = 0 (+ addend) there
+    const size_t bytes = (size_t)g->N * g->H * g->W * g->Cin_s * 2;
+    cudaError_t e = add_nhwc ? cudaMemcpyAsync(dx_nhwc, add_nhwc, bytes, cudaMemcpyDeviceToDevice, st)
+                             : cudaMemsetAsync(dx_nhwc, 0, bytes, st);
+    if (e != cudaSuccess) { set_error("dgrad fill: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
   }
   for (int i = 0; i < np; ++i) {
     if (p[i].ntaps == 0 || p[i].Ht <= 0 || p[i].Wt <= 0) continue;
     bool umma = use_umma(algo, umma_problem_supported(p[i]), &rc);
     if (rc != MCD_OK) return rc;
-    rc = umma ? launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, p[i], st)
-              : launch_direct_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, p[i], st);
+    rc = umma ? launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, add_nhwc, p[i], st)
+              : launch_direct_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, add_nhwc, p[i], st);
     if (rc != MCD_OK) return rc;
   }
   return MCD_OK;

@@ -40,6 +40,7 @@ struct FpropArgs {
   const float* bias;
   float* stats;
   void* out;
+  const __nv_bfloat16* addend;   // optional nhwc tensor (output geometry) added in the epilogue: residual gradient
   Tap taps[kMaxTaps];
 };
 
@@ -190,8 +191,8 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
               if (c < a.rows) o[(((int64_t)n_img * a.rows + c) * a.Hd + hd) * a.Wd + wd] = v[j];
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) +
-                               (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0 + c0;
+            const int64_t ooff = (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0 + c0;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + ooff;
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               int c = n0 + c0 + j8 * 8;
@@ -199,6 +200,12 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                 float f[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
+                if (a.addend) {
+                  float r[8];
+                  unpack8(*reinterpret_cast<const uint4*>(a.addend + ooff + j8 * 8), r);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) f[k] += r[k];
+                }
                 *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
               }
             }
@@ -723,7 +730,7 @@ static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, 
 
 // src: activations for this problem; for strided fprop the parity maps are built over (Hs, Ws).
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                        float* stats, const TapProblem& p, cudaStream_t st) {
+                        float* stats, const void* addend, const TapProblem& p, cudaStream_t st) {
   if (p.ntaps == 0) return MCD_OK;
   if (!umma_problem_supported(p)) { set_error("umma fprop: unsupported problem"); return MCD_E_INVALID; }
   FpropArgs a;
@@ -736,6 +743,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   a.kchunks = (p.Kc + 63) / 64; a.ntaps = p.ntaps; a.kc_pad = p.kc_pad;
   a.rows = p.rows; a.omul = p.omul; a.oh0 = p.oh0; a.ow0 = p.ow0; a.Hd = p.Hd; a.Wd = p.Wd;
   a.Cd_s = p.Cd_s; a.planar = planar; a.bias = bias; a.stats = stats; a.out = out;
+  a.addend = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(addend);
   for (int t = 0; t < p.ntaps; ++t) a.taps[t] = p.taps[t];
 
   UmmaMaps maps;

@@ -96,49 +96,82 @@ __global__ void pack_weight_rows_kernel(const float* __restrict__ w, __nv_bfloat
 }
 
 // ---- multi-tensor re-pack: ONE launch refreshes every bf16 shadow of a model after an optimizer step ------
-// item (8 x int64 in device memory): w ptr, dst ptr, Cout, Cin, R, S, mode, cs
-//   mode 0/1: pack_weight fprop/dgrad layout   mode 2/3: pack_weight_rows fprop/dgrad layout (cs = channel stride)
-__global__ void pack_weights_multi_kernel(const int64_t* __restrict__ items) {
-  const int64_t* it = items + (int64_t)blockIdx.x * 8;
+// item (12 x int64 in device memory): w, dst_fprop, dst_dgrad (0 = absent), Cout, Cin, R, S, kind_f, kind_d,
+// cs_f, cs_d, unused.  kind 0 = [rows][taps][kc_pad] layout, 1 = row-packed [rows][R][64] layout.
+// Standard layouts: a block transposes one 32(co) x 32(ci) x T tile through shared memory so that the fp32 OIHW
+// reads and BOTH bf16 writes are coalesced (the pad channels of the packs were zeroed when they were created and
+// are never touched again).  Row-packed layouts (three tiny stem layers) use the element-wise path.
+constexpr int PK_T_MAX = 9;
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const int64_t* __restrict__ items) {
+  __shared__ float tile[32][32 * PK_T_MAX + 1];
+  const int64_t* it = items + (int64_t)blockIdx.x * 12;
   const float* w = reinterpret_cast<const float*>(it[0]);
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(it[1]);
-  const int Cout = (int)it[2], Cin = (int)it[3], R = (int)it[4], S = (int)it[5], mode = (int)it[6], Cs = (int)it[7];
+  __nv_bfloat16* dst_f = reinterpret_cast<__nv_bfloat16*>(it[1]);
+  __nv_bfloat16* dst_d = reinterpret_cast<__nv_bfloat16*>(it[2]);
+  const int Cout = (int)it[3], Cin = (int)it[4], R = (int)it[5], S = (int)it[6];
+  const int kind_f = (int)it[7], kind_d = (int)it[8], cs_f = (int)it[9], cs_d = (int)it[10];
   const int T = R * S;
-  if (mode < 2) {
-    const int rows = mode ? Cin : Cout;
-    const int kc_pad = ((mode ? Cout : Cin) + 63) / 64 * 64;
-    const int64_t total = (int64_t)rows * T * kc_pad;
-    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
-      int kc = (int)(i % kc_pad);
-      int t = (int)((i / kc_pad) % T);
-      int row = (int)(i / ((int64_t)kc_pad * T));
-      float v = 0.f;
-      if (mode == 0) {
-        if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S];
-      } else if (kc < Cout) {
-        int r = R - 1 - t / S, s = S - 1 - t % S;
-        v = w[(((int64_t)kc * Cin + row) * R + r) * S + s];
+  const bool std_f = dst_f && kind_f == 0, std_d = dst_d && kind_d == 0;
+  if ((std_f || std_d) && T <= PK_T_MAX) {
+    const int tiles_ci = (Cin + 31) / 32, tiles_co = (Cout + 31) / 32;
+    const int kpf = (Cin + 63) / 64 * 64, kpd = (Cout + 63) / 64 * 64;
+    for (int tl = blockIdx.y; tl < tiles_ci * tiles_co; tl += gridDim.y) {
+      const int co0 = (tl / tiles_ci) * 32, ci0 = (tl % tiles_ci) * 32;
+      const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {      // co_l slowest, (ci_l, t) contiguous
+        const int co_l = idx / (nci * T), rem = idx % (nci * T);
+        if (co_l < nco) tile[co_l][rem] = w[((int64_t)(co0 + co_l) * Cin + ci0) * T + rem];
       }
-      dst[i] = f2bf(v);
-    }
-  } else {
-    const int m = mode - 2;
-    const int rows = m ? Cin : Cout;
-    const int64_t total = (int64_t)rows * R * 64;
-    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
-      int k = (int)(i % 64);
-      int r = (int)((i / 64) % R);
-      int row = (int)(i / (64 * (int64_t)R));
-      int s = k / Cs, c = k % Cs;
-      float v = 0.f;
-      if (s < S) {
-        if (m == 0) {
-          if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s];
-        } else if (c < Cout) {
-          v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
+      __syncthreads();
+      if (std_f) {
+        for (int idx = threadIdx.x; idx < nco * T * 32; idx += 256) {    // ci_l fastest
+          const int ci_l = idx & 31, t = (idx >> 5) % T, co_l = idx / (32 * T);
+          if (ci_l < nci)
+            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bf(tile[co_l][ci_l * T + t]);
         }
       }
-      dst[i] = f2bf(v);
+      if (std_d) {
+        for (int idx = threadIdx.x; idx < nci * T * 32; idx += 256) {    // co_l fastest, flipped taps
+          const int co_l = idx & 31, t = (idx >> 5) % T, ci_l = idx / (32 * T);
+          if (co_l < nco) {
+            const int tf = (R - 1 - t / S) * S + (S - 1 - t % S);
+            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bf(tile[co_l][ci_l * T + t]);
+          }
+        }
+      }
+    }
+  }
+  // element-wise paths: row-packed layouts, or filters larger than the smem tile allows
+  for (int pass = 0; pass < 2; ++pass) {
+    __nv_bfloat16* dst = pass ? dst_d : dst_f;
+    const int kind = pass ? kind_d : kind_f, Cs = pass ? cs_d : cs_f;
+    if (!dst) continue;
+    if (kind == 0 && T <= PK_T_MAX) continue;
+    const int rows = pass ? Cin : Cout;
+    if (kind == 0) {
+      const int kc_pad = ((pass ? Cout : Cin) + 63) / 64 * 64;
+      const int64_t total = (int64_t)rows * T * kc_pad;
+      for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
+        const int kc = (int)(i % kc_pad), t = (int)((i / kc_pad) % T), row = (int)(i / ((int64_t)kc_pad * T));
+        float v = 0.f;
+        if (!pass) { if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S]; }
+        else if (kc < Cout) v = w[(((int64_t)kc * Cin + row) * R + (R - 1 - t / S)) * S + (S - 1 - t % S)];
+        dst[i] = f2bf(v);
+      }
+    } else {
+      const int64_t total = (int64_t)rows * R * 64;
+      for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
+        const int k = (int)(i % 64), r = (int)((i / 64) % R), row = (int)(i / (64 * (int64_t)R));
+        const int s = k / Cs, c = k % Cs;
+        float v = 0.f;
+        if (s < S) {
+          if (!pass) { if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s]; }
+          else if (c < Cout) v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
+        }
+        dst[i] = f2bf(v);
+      }
     }
   }
 }

@@ -48,6 +48,7 @@ class DirectGrads:
 
     def __init__(self):
         self.keep = []
+        self.stash = {}      # data_ptr of a block input -> identity-shortcut gradient awaiting conv1's dgrad
 
     def __enter__(self):
         global _direct
@@ -63,6 +64,9 @@ class DirectGrads:
         if side is not None:
             torch.cuda.current_stream(device).wait_stream(side)
         self.keep.clear()
+        if self.stash:
+            self.stash.clear()
+            raise RuntimeError("mcd_b200: an identity-shortcut gradient was stashed but never consumed")
 
 
 _direct = None
@@ -124,8 +128,11 @@ class _ConvFn(torch.autograd.Function):
             # dgrad is enqueued FIRST: it heads the critical path (dgrad -> BatchNorm backward -> next dgrad) and
             # cannot share an SM with the persistent wgrad CTAs (both want ~190 KB of shared memory); the wgrad
             # that follows on the side stream then overlaps the memory-bound BatchNorm kernels of the next unit.
+            add = _direct.stash.pop(x.data_ptr(), None)      # identity-shortcut gradient of a BasicBlock
             if need_dx:
-                dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
+                dx = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add)
+            elif add is not None:
+                dx = add
             side.wait_event(ready)
             with torch.cuda.stream(side):
                 ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
@@ -214,6 +221,7 @@ class _BNActFn(torch.autograd.Function):
         ctx.relu, ctx.training = relu, training
         ctx.res_training = res_bn.training if res_bn is not None else False
         ctx.has_res, ctx.has_res_bn = res is not None, res_bn is not None
+        ctx.res_ptr = res.data_ptr() if (res is not None and res_bn is None and getattr(res, "_mcd_shortcut", False)) else None
         ctx.save_for_backward(y, z, gamma, aff, res if res_bn is not None else None, res_gamma, res_aff)
         return z
 
@@ -226,6 +234,11 @@ class _BNActFn(torch.autograd.Function):
             dz, z, y, gamma, aff, ctx.training, ctx.relu, res=res, res_gamma=res_gamma, res_aff=res_aff,
             res_training=ctx.res_training, want_dres=want_dres)
         if not want_dres:
+            dres = None
+        elif _direct is not None and not ctx.has_res_bn and ctx.res_ptr is not None:
+            # direct-gradient mode: the identity-shortcut gradient is not returned to autograd (which would add
+            # it to conv1's dgrad in a separate pass) but handed to conv1's dgrad kernel, whose epilogue adds it
+            _direct.stash[ctx.res_ptr] = dres
             dres = None
         return dy, None, dgamma, dbeta, dres, None, dres_gamma, dres_beta, None, None, None
 

@@ -158,18 +158,21 @@ class MultiPacker:
         for conv in convs:
             w = conv.weight
             co, ci, r, s = w.shape
+            slot = {0: (0, 0, 0, None), 1: (0, 0, 0, None)}      # mode -> (ptr, kind, cs, key)
             for key, (tag, packed) in conv._packs.items():
                 mode, kind, cs = key
-                rows.append([w.data_ptr(), packed.data_ptr(), co, ci, r, s, mode + 2 * kind, cs])
+                slot[mode] = (packed.data_ptr(), kind, cs, key)
                 self.entries.append((conv, key, packed))
+            rows.append([w.data_ptr(), slot[0][0], slot[1][0], co, ci, r, s, slot[0][1], slot[1][1],
+                         slot[0][2], slot[1][2], 0])
         self.n = len(rows)
-        self.table = torch.tensor(rows, dtype=torch.int64, device=convs[0].weight.device) if rows else None
         self.dev = convs[0].weight.device if convs else None
+        self.table = torch.tensor(rows, dtype=torch.int64, device=self.dev) if rows else None
 
     def repack(self):
         if not self.n:
             return
-        abi.check(abi.lib().mcd_pack_weights_multi(_p(self.table), self.n, 32, self.dev.index,
+        abi.check(abi.lib().mcd_pack_weights_multi(_p(self.table), self.n, 64, self.dev.index,
                                                    ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
                   "pack_weights_multi")
         for conv, key, packed in self.entries:
@@ -206,10 +209,13 @@ def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
     return y, stats
 
 
-def conv_dgrad(dy, w_packed_dgrad, g, algo=None):
+def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None):
+    """dx = dgrad (+ add: an nhwc tensor of dx's shape, e.g. the identity-shortcut gradient)."""
     assert is_nhwc(dy) and dy.shape[1] == g.Cout_s
     dx = nhwc_empty(g.N, g.Cin_s, g.H, g.W, dy.device)
-    abi.check(abi.lib().mcd_conv2d_dgrad(_p(dy), _p(w_packed_dgrad), _p(dx), ctypes.byref(g),
+    if add is not None:
+        assert is_nhwc(add) and tuple(add.shape) == tuple(dx.shape)
+    abi.check(abi.lib().mcd_conv2d_dgrad(_p(dy), _p(w_packed_dgrad), _p(dx), _p(add), ctypes.byref(g),
                                          _algo if algo is None else algo, _dev(dy), _stream(dy)),
               "conv2d_dgrad")
     return dx
@@ -489,8 +495,8 @@ def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
                      lambda: _conv_fprop_raw(x, w_packed, bias, g, planar, want_stats, algo))
 
 
-def conv_dgrad(dy, w_packed_dgrad, g, algo=None):  # noqa: F811
-    return _profiled("conv_fprop_kernel (dgrad)", g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo))
+def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None):  # noqa: F811
+    return _profiled("conv_fprop_kernel (dgrad)", g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add))
 
 
 def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):  # noqa: F811

@@ -47,6 +47,9 @@ class BasicBlock(nn.Module):
         if self.downsample is not None:
             ds_conv, ds_bn = self.downsample[0], self.downsample[1]
             return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x, res_conv=ds_conv, res_bn=ds_bn)
+        # identity shortcut: x feeds conv1 AND the residual add; the flag lets MCDStep fuse the shortcut gradient
+        # into conv1's dgrad epilogue (mcd_b200/nn.py, direct-gradient mode)
+        x._mcd_shortcut = True
         return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x)
 
 
