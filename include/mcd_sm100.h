@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 9
+#define MCD_ABI_VERSION 10
 
 enum {
   MCD_OK = 0,
@@ -91,13 +91,19 @@ int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, in
  * Cs = Cout_s, flipped filter).  Which pack a convolution wants: mcd_conv2d_pack_kind(). */
 int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs,
                          int mode, int device, void* stream);
+/* "Row convolution" pack for the stride-1, dilation-1 stem layers (models/drn.py:126-136: 7x7 6->16, 3x3 16->16;
+ * channel stride Cs in {8,16}, S <= 8, R <= 7, <= 32 produced channels): the smem-ready no-swizzle K-major UMMA
+ * operand dst[R][(Cs/8)*SP][NB/8][8][8] bf16 with SP = (S <= 4 ? 4 : 8) taps per row and NB = round_up(rows, 16),
+ * rows = (mode ? Cin : Cout); i.e. R*(Cs/8)*SP*NB*8 elements.  mode as for mcd_pack_weight_rows. */
+int mcd_pack_weight_rowconv(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs,
+                            int mode, int device, void* stream);
 /* Multi-tensor re-pack: one launch for all convolutions of a model (after optimizer.step()).  items_dev:
  * device array of n_items x 12 int64 {w, dst_fprop, dst_dgrad (0 = absent), Cout, Cin, R, S, kind_fprop,
  * kind_dgrad (mcd_conv2d_pack_kind), Cs_fprop, Cs_dgrad, 0}.  The destination buffers must have been produced
  * once by mcd_pack_weight / mcd_pack_weight_rows (their zero padding is kept). */
 int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per_item, int device,
                            void* stream);
-/* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows() layout for (geometry, pass, algo);
+/* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows(), 2 = mcd_pack_weight_rowconv() for (geometry, pass, algo);
  * pass: 0 = fprop, 1 = dgrad. */
 int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
 
@@ -105,13 +111,27 @@ int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
 /* y = conv(x, w) (+ bias).  If `stats` != NULL (fp32 [2*Cout], caller-zeroed) the kernel also
  * accumulates per-channel sum and sum of squares of y for train-mode BatchNorm. */
 int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias, void* y,
-                     int y_layout, float* stats, const mcd_conv_geom* g, int algo, int device,
-                     void* stream);
+                     int y_layout, float* stats, void* sk_partial, int* sk_flags, const mcd_conv_geom* g,
+                     int algo, int device, void* stream);
+/* Optional stream-K workspace of fprop (pass 0) / dgrad (pass 1): when the pixel-tile count of a layer does not
+ * fill the last wave of persistent CTAs (8 x 60x80 pixels = 300 tiles on 148 SMs), the tcgen05 kernels split the
+ * (tile, k-block) space evenly over the CTAs instead; tiles cut by a CTA boundary exchange one fp32 partial tile
+ * through `sk_partial` (returned size in bytes, contents arbitrary) and `sk_flags` (*n_flags ints, ZEROED by the
+ * caller before every call).  Returns 0 / *n_flags = 0 when the geometry does not use it; passing NULL for either
+ * pointer selects the plain tile-per-CTA schedule.  Results do not depend on the schedule beyond fp32 summation
+ * order. */
+size_t mcd_conv2d_streamk_workspace(const mcd_conv_geom* g, int pass, int y_layout, int algo, int* n_flags);
 /* dx = conv_transpose(dy, w) (+ add_nhwc): gradient wrt the nhwc input.  w_packed is the mode-1 pack.
  * add_nhwc (may be NULL): tensor of dx's geometry added in the epilogue - the gradient that reaches the same
- * activation through the identity shortcut of a BasicBlock (models/drn.py:53-58), saving a separate add pass. */
+ * activation through the identity shortcut of a BasicBlock (models/drn.py:53-58), saving a separate add pass.
+ * The backward of the BatchNorm+ReLU unit that PRODUCED the convolution's input (models/drn.py:47-49,126-131)
+ * can start in the same epilogue (each may be NULL; all nhwc tensors of dx's geometry):
+ *   relu_src_nhwc : the convolution's input x = relu(...):  dx = x > 0 ? dx : 0
+ *   bn_y_nhwc, bn_sums (fp32 [2*Cin], caller-zeroed): bn_sums += {sum dx, sum dx * bn_y} per channel, bn_y = the
+ *   input of that BatchNorm - the RAW sums mcd_bn_bwd_apply() accepts with sums_kind = 1. */
 int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc, const void* add_nhwc,
-                     const mcd_conv_geom* g, int algo, int device, void* stream);
+                     const void* relu_src_nhwc, const void* bn_y_nhwc, float* bn_sums, void* sk_partial,
+                     int* sk_flags, const mcd_conv_geom* g, int algo, int device, void* stream);
 /* dw (fp32 OIHW) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).  accumulate = 0 overwrites,
  * 1 adds to the existing contents (gradient accumulation straight into param.grad / all-reduce buckets).
  * workspace: mcd_conv2d_wgrad_workspace() bytes. */
@@ -158,13 +178,14 @@ int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhw
 /* dy = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat))  (training) or gamma*rstd*g (eval);
  * optional second branch dres with its own gamma/mean/rstd (downsample BN) or, when
  * res_gamma == NULL and dres != NULL, the identity residual gradient dres = g.
- * dgamma/dbeta (fp32 [C]) are written from sums. */
+ * dgamma/dbeta (fp32 [C]) are written from sums.  sums_kind 0: sums as produced by mcd_bn_bwd_reduce;
+ * 1: sums[C:2C] holds the raw sum g*y (mcd_conv2d_dgrad's fused epilogue; no residual BatchNorm branch). */
 int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc, const float* gamma,
                      const float* mean, const float* rstd, const float* sums, int training, int relu,
                      void* dy_nhwc, float* dgamma, float* dbeta, const void* res_nhwc,
                      const float* res_gamma, const float* res_mean, const float* res_rstd,
                      int res_training, void* dres_nhwc, float* dres_gamma, float* dres_beta,
-                     int64_t P, int C, int Cs, int device, void* stream);
+                     int sums_kind, int64_t P, int C, int Cs, int device, void* stream);
 
 /* ---- classifier heads --------------------------------------------------------------------- */
 /* Depthwise ConvTranspose2d(C,C,16,stride 8,pad 4,groups C,bias=False)

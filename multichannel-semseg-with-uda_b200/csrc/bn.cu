@@ -89,6 +89,51 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
   }
 }
 
+// dx = mask_src > 0 ? dx : 0 (in place, optional) and sums += {sum dx, sum dx * bn_y} (optional, RAW second moment):
+// the un-fused form of the dgrad epilogue extras (conv_plan.h EpiExtra) for paths that cannot fuse them.
+__global__ void __launch_bounds__(256, 3)
+bn_mask_sums_kernel(__nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ mask_src,
+                    const __nv_bfloat16* __restrict__ bn_y, float* __restrict__ sums, int64_t P, int C, int Cs) {
+  extern __shared__ float sh[];  // 2 * Cs
+  const int vpr = Cs >> 3;
+  const int rpi = 256 / vpr;
+  const int cv = threadIdx.x % vpr, pr = threadIdx.x / vpr;
+  for (int i = threadIdx.x; i < 2 * Cs; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  float a0[8], a1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a0[k] = a1[k] = 0.f;
+  const int c0 = cv * 8;
+  if (pr < rpi) {
+    const int64_t step = (int64_t)gridDim.x * rpi;
+    for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
+      const int64_t off = p * Cs + c0;
+      float g[8];
+      unpack8(*reinterpret_cast<const uint4*>(dx + off), g);
+      if (mask_src) {
+        float m[8];
+        unpack8(*reinterpret_cast<const uint4*>(mask_src + off), m);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+        *reinterpret_cast<uint4*>(dx + off) = pack8(g);
+      }
+      if (sums) {
+        float fy[8];
+        unpack8(*reinterpret_cast<const uint4*>(bn_y + off), fy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], fy[k], a1[k]); }
+      }
+    }
+    if (sums) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&sh[c0 + k], a0[k]); atomicAdd(&sh[Cs + c0 + k], a1[k]); }
+    }
+  }
+  __syncthreads();
+  if (sums)
+    for (int c = threadIdx.x; c < C; c += 256) { atomicAdd(sums + c, sh[c]); atomicAdd(sums + C + c, sh[Cs + c]); }
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, double invP, double unbias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -245,14 +290,21 @@ struct BwdBranch {
   int training;
 };
 
+// second moment of the gradient: sums hold sum(g * xhat) (kind 0) or the raw sum(g * y) (kind 1, produced by the
+// fused dgrad epilogue): sum(g * xhat) = rstd * (sum(g * y) - mean * sum(g))
+__device__ __forceinline__ float bwd_second(const BwdBranch& b, const float* sums, int sum_off, int c, int raw) {
+  const float s = sums[sum_off + c];
+  return raw ? b.rstd[c] * (s - b.mean[c] * sums[c]) : s;
+}
+
 // dy = A*g + B*y + K with per-channel A = gamma*rstd, B = -A*m2*rstd, K = -A*m1 - B*mean  (training;
 // m1 = sum(g)/P, m2 = sum(g*xhat)/P) or B = K = 0 (eval).
 __device__ __forceinline__ void bwd_coeffs(const BwdBranch& b, const float* sums, int sum_off, int C, int c,
-                                           float invP, float* A, float* B, float* K) {
+                                           float invP, int raw, float* A, float* B, float* K) {
   const float a = b.gamma[c] * b.rstd[c];
   *A = a;
   if (b.training) {
-    const float m1 = sums[c] * invP, m2 = sums[sum_off + c] * invP;
+    const float m1 = sums[c] * invP, m2 = bwd_second(b, sums, sum_off, c, raw) * invP;
     const float bb = -a * m2 * b.rstd[c];
     *B = bb;
     *K = -a * m1 - bb * b.mean[c];
@@ -267,11 +319,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
                     int relu, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, const __nv_bfloat16* __restrict__ res, BwdBranch b2,
                     __nv_bfloat16* __restrict__ dres, float* __restrict__ dres_gamma,
-                    float* __restrict__ dres_beta, float invP, int64_t P, int Cs, int C) {
+                    float* __restrict__ dres_beta, float invP, int64_t P, int Cs, int C, int raw) {
   extern __shared__ float co[];  // A1, B1, K1, A2, B2, K2 : 6 * Cs
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dgamma) dgamma[c] = sums[C + c];
+      if (dgamma) dgamma[c] = bwd_second(b1, sums, C, c, raw);
       if (dbeta) dbeta[c] = sums[c];
       if (dres_gamma) dres_gamma[c] = sums[2 * C + c];
       if (dres_beta) dres_beta[c] = sums[c];
@@ -281,8 +333,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
   for (int c = threadIdx.x; c < Cs; c += 256) {
     float A = 0.f, B = 0.f, K = 0.f, A2 = 0.f, B2 = 0.f, K2 = 0.f;
     if (c < C) {
-      bwd_coeffs(b1, sums, C, C, c, invP, &A, &B, &K);
-      if (has_res_bn) bwd_coeffs(b2, sums, 2 * C, C, c, invP, &A2, &B2, &K2);
+      bwd_coeffs(b1, sums, C, C, c, invP, raw, &A, &B, &K);
+      if (has_res_bn) bwd_coeffs(b2, sums, 2 * C, C, c, invP, 0, &A2, &B2, &K2);
     }
     co[c] = A; co[Cs + c] = B; co[2 * Cs + c] = K;
     co[3 * Cs + c] = A2; co[4 * Cs + c] = B2; co[5 * Cs + c] = K2;
@@ -337,6 +389,15 @@ int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaS
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stats, P,
       C, Cs);
   return check_launch("bn_stats");
+}
+
+int bn_mask_sums_launch(void* dx, const void* mask_src, const void* bn_y, float* sums, int64_t P, int C, int Cs,
+                        cudaStream_t st) {
+  if (Cs % 8 != 0 || Cs > 2048) { set_error("bn_mask_sums: channel stride %d unsupported", Cs); return MCD_E_INVALID; }
+  int grid = rows_grid(P, Cs, 8, 148 * 3);
+  bn_mask_sums_kernel<<<grid, 256, 2 * Cs * sizeof(float), st>>>((__nv_bfloat16*)dx, (const __nv_bfloat16*)mask_src,
+                                                                  (const __nv_bfloat16*)bn_y, sums, P, C, Cs);
+  return check_launch("bn_mask_sums");
 }
 
 }  // namespace mcd
@@ -430,7 +491,7 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
                      void* dy_nhwc, float* dgamma, float* dbeta, const void* res_nhwc,
                      const float* res_gamma, const float* res_mean, const float* res_rstd,
                      int res_training, void* dres_nhwc, float* dres_gamma, float* dres_beta,
-                     int64_t P, int C, int Cs, int device, void* stream) {
+                     int sums_kind, int64_t P, int C, int Cs, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(dz_nhwc && y_nhwc && gamma && mean && rstd && sums && dy_nhwc && P > 0,
               "bn_bwd_apply: bad arguments");
@@ -438,6 +499,8 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
   MCD_REQUIRE(Cs == C && C % 8 == 0, "bn_bwd_apply: needs dense channels (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!res_gamma || (res_nhwc && res_mean && res_rstd && dres_nhwc),
               "bn_bwd_apply: incomplete residual branch");
+  MCD_REQUIRE(sums_kind == 0 || (sums_kind == 1 && !res_gamma),
+              "bn_bwd_apply: raw sums (kind 1) are not defined for a residual BatchNorm branch");
   BwdBranch b1{gamma, mean, rstd, training};
   BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
   MCD_REQUIRE(Cs <= 2048, "bn_bwd_apply: channel stride %d unsupported", Cs);
@@ -445,7 +508,7 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
   bn_bwd_apply_kernel<<<grid, 256, 6 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc, (const __nv_bfloat16*)y_nhwc, b1, sums,
       relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, (const __nv_bfloat16*)res_nhwc, b2,
-      (__nv_bfloat16*)dres_nhwc, dres_gamma, dres_beta, (float)(1.0 / (double)P), P, Cs, C);
+      (__nv_bfloat16*)dres_nhwc, dres_gamma, dres_beta, (float)(1.0 / (double)P), P, Cs, C, sums_kind);
   return check_launch("bn_bwd_apply");
 }
 

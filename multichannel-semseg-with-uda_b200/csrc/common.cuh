@@ -54,6 +54,21 @@ inline int check_launch(const char* what) {
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
 
+// element i of the "rowconv" weight pack (conv_rows.cu): dst[r][kg = half*SP + s][n/8][n%8][c%8], n = produced
+// channel, c = half*8 + c%8 = reduce channel; mode 0: w[n][c][r][s], mode 1 (dgrad): w[c][n][R-1-r][S-1-s].
+__device__ __forceinline__ float rowconv_pack_value(const float* __restrict__ w, int64_t i, int Cout, int Cin, int R,
+                                                    int S, int HC, int SP, int NB, int mode) {
+  const int ngs = NB / 8;
+  const int c8 = (int)(i % 8), n8 = (int)((i / 8) % 8), ng = (int)((i / 64) % ngs);
+  const int kg = (int)((i / (64 * (int64_t)ngs)) % (HC * SP));
+  const int r = (int)(i / (64 * (int64_t)ngs * HC * SP));
+  const int hf = kg / SP, s = kg % SP;
+  const int n = ng * 8 + n8, c = hf * 8 + c8;
+  if (s >= S) return 0.f;
+  if (mode == 0) return (n < Cout && c < Cin) ? w[(((int64_t)n * Cin + c) * R + r) * S + s] : 0.f;
+  return (n < Cin && c < Cout) ? w[(((int64_t)c * Cin + n) * R + (R - 1 - r)) * S + (S - 1 - s)] : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,10 +11,18 @@ int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& 
 int colsum(const void* t, float* out, int64_t P, int C, int Cs, int accumulate, cudaStream_t st);
 bool umma_problem_supported(const TapProblem& p);
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                        float* stats, const void* addend, const TapProblem& p, cudaStream_t st);
+                        float* stats, const EpiExtra& ex, const TapProblem& p, cudaStream_t st);
 size_t umma_wgrad_workspace(const mcd_conv_geom& g);
+size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags);
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                const mcd_conv_geom& g, int accumulate, cudaStream_t st);
+bool rowconv_fprop_ok(const mcd_conv_geom& g);
+bool rowconv_dgrad_ok(const mcd_conv_geom& g);
+int rowconv_pack(const float* w, void* dst, int Cout, int Cin, int R, int S, int Cs, int mode, cudaStream_t st);
+int rowconv_launch(const void* src, const void* wpacked, const float* bias, void* out, int planar, float* stats,
+                   const EpiExtra& ex, const mcd_conv_geom& g, int mode, cudaStream_t st);
+int bn_mask_sums_launch(void* dx, const void* mask_src, const void* bn_y, float* sums, int64_t P, int C, int Cs,
+                        cudaStream_t st);
 int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaStream_t st);
 
 static int validate(const mcd_conv_geom* g) {
@@ -48,8 +56,8 @@ using namespace mcd;
 extern "C" {
 
 int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias, void* y,
-                     int y_layout, float* stats, const mcd_conv_geom* g, int algo, int device,
-                     void* stream) {
+                     int y_layout, float* stats, void* sk_partial, int* sk_flags, const mcd_conv_geom* g,
+                     int algo, int device, void* stream) {
   MCD_ENTER(device);
   int rc = validate(g);
   if (rc != MCD_OK) return rc;
@@ -62,8 +70,12 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
   bool umma = use_umma(algo, umma_problem_supported(p), &rc);
   if (rc != MCD_OK) return rc;
   if (umma) {
+    if (rowconv_fprop_ok(*g))                            // w_packed: mcd_pack_weight_rowconv mode 0
+      return rowconv_launch(x_nhwc, w_packed, bias, y, planar, stats, EpiExtra(), *g, 0, st);
     if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p);   // w_packed is then the mcd_pack_weight_rows layout
-    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, nullptr, p, st);
+    EpiExtra ex;
+    ex.sk_partial = sk_partial; ex.sk_flags = sk_flags;
+    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, ex, p, st);
   }
   rc = launch_direct_problem(x_nhwc, w_packed, bias, y, planar, nullptr, p, st);
   if (rc != MCD_OK) return rc;
@@ -75,21 +87,38 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
 }
 
 int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc, const void* add_nhwc,
-                     const mcd_conv_geom* g, int algo, int device, void* stream) {
+                     const void* relu_src_nhwc, const void* bn_y_nhwc, float* bn_sums, void* sk_partial,
+                     int* sk_flags, const mcd_conv_geom* g, int algo, int device, void* stream) {
   MCD_ENTER(device);
   int rc = validate(g);
   if (rc != MCD_OK) return rc;
   MCD_REQUIRE(dy_nhwc && w_packed_dgrad && dx_nhwc, "conv dgrad: null pointer");
   MCD_REQUIRE(g->stride <= 2, "conv dgrad: stride %d unsupported", g->stride);
+  MCD_REQUIRE((bn_y_nhwc != nullptr) == (bn_sums != nullptr), "conv dgrad: bn_y and bn_sums go together");
+  MCD_REQUIRE(!bn_sums || g->Cin_s == g->Cin, "conv dgrad: fused BatchNorm sums need dense channels");
   cudaStream_t st = (cudaStream_t)stream;
+  EpiExtra ex;
+  ex.addend = add_nhwc; ex.mask_src = relu_src_nhwc; ex.bn_y = bn_y_nhwc;
+  const bool post_wanted = relu_src_nhwc || bn_sums;
+  if (algo != MCD_ALGO_DIRECT && rowconv_dgrad_ok(*g))   // w_packed_dgrad: mcd_pack_weight_rowconv mode 1
+    return rowconv_launch(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, bn_sums, ex, *g, 1, st);
   TapProblem p[4];
   int np = plan_dgrad(*g, p);
   if (algo != MCD_ALGO_DIRECT && packed_dgrad_ok(*g) && umma_problem_supported(p[0])) {
     plan_dgrad_packed(*g, p[0]);                          // w_packed_dgrad: mcd_pack_weight_rows mode 1
-    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, add_nhwc, p[0], st);
+    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, bn_sums, ex, p[0], st);
   }
+  // the ReLU mask / BatchNorm sums are fused into the epilogue when every pixel of dx is produced by a tcgen05
+  // problem; otherwise one extra pass over dx applies them
+  bool fused = post_wanted && algo != MCD_ALGO_DIRECT;
   bool any_empty = false;
-  for (int i = 0; i < np; ++i) any_empty |= (p[i].ntaps == 0);
+  for (int i = 0; i < np; ++i) {
+    any_empty |= (p[i].ntaps == 0);
+    if (p[i].ntaps && !umma_problem_supported(p[i])) fused = false;
+  }
+  if (any_empty) fused = false;
+  if (!fused) { ex.mask_src = nullptr; ex.bn_y = nullptr; }
+  if (np == 1) { ex.sk_partial = sk_partial; ex.sk_flags = sk_flags; }
   if (any_empty) {   // parity classes without taps: dx = 0 (+ addend) there
     const size_t bytes = (size_t)g->N * g->H * g->W * g->Cin_s * 2;
     cudaError_t e = add_nhwc ? cudaMemcpyAsync(dx_nhwc, add_nhwc, bytes, cudaMemcpyDeviceToDevice, st)
@@ -100,17 +129,51 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
     if (p[i].ntaps == 0 || p[i].Ht <= 0 || p[i].Wt <= 0) continue;
     bool umma = use_umma(algo, umma_problem_supported(p[i]), &rc);
     if (rc != MCD_OK) return rc;
-    rc = umma ? launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, nullptr, add_nhwc, p[i], st)
+    rc = umma ? launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, fused ? bn_sums : nullptr, ex,
+                                    p[i], st)
               : launch_direct_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, add_nhwc, p[i], st);
     if (rc != MCD_OK) return rc;
   }
+  if (post_wanted && !fused)
+    return bn_mask_sums_launch(dx_nhwc, relu_src_nhwc, bn_y_nhwc, bn_sums, (int64_t)g->N * g->H * g->W, g->Cin,
+                               g->Cin_s, st);
   return MCD_OK;
 }
 
 int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo) {
   if (!g || algo == MCD_ALGO_DIRECT) return 0;
   if (g->stride > 2) return 0;
+  if (pass == 0 ? rowconv_fprop_ok(*g) : rowconv_dgrad_ok(*g)) return 2;
   return pass == 0 ? (packed_fprop_ok(*g) ? 1 : 0) : (packed_dgrad_ok(*g) ? 1 : 0);
+}
+
+int mcd_pack_weight_rowconv(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs, int mode,
+                            int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(w_oihw && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, "pack_weight_rowconv: bad arguments");
+  MCD_REQUIRE(mode == 0 || mode == 1, "pack_weight_rowconv: mode must be 0 (fprop) or 1 (dgrad)");
+  MCD_REQUIRE((Cs == 8 || Cs == 16) && S <= 8 && R <= 7 && Cs >= (mode ? Cout : Cin) && (mode ? Cin : Cout) <= 32,
+              "pack_weight_rowconv: channel stride %d / filter %dx%d not packable", Cs, R, S);
+  return rowconv_pack(w_oihw, dst, Cout, Cin, R, S, Cs, mode, (cudaStream_t)stream);
+}
+
+size_t mcd_conv2d_streamk_workspace(const mcd_conv_geom* g, int pass, int y_layout, int algo, int* n_flags) {
+  int nf = 0;
+  size_t bytes = 0;
+  if (g && algo != MCD_ALGO_DIRECT && validate(g) == MCD_OK) {
+    if (pass == 0) {
+      if (!rowconv_fprop_ok(*g) && !packed_fprop_ok(*g)) {
+        TapProblem p;
+        plan_fprop(*g, p);
+        bytes = umma_streamk_workspace(p, y_layout == MCD_OUT_PLANAR_F32, &nf);
+      }
+    } else if (g->stride == 1 && !rowconv_dgrad_ok(*g) && !packed_dgrad_ok(*g)) {
+      TapProblem p[4];
+      if (plan_dgrad(*g, p) == 1) bytes = umma_streamk_workspace(p[0], 0, &nf);
+    }
+  }
+  if (n_flags) *n_flags = nf;
+  return bytes;
 }
 
 size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo) {

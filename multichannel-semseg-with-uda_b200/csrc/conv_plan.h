@@ -16,6 +16,15 @@ namespace mcd {
 
 constexpr int kMaxTaps = 49;
 
+// optional epilogue inputs of a problem (all nhwc bf16 in the OUTPUT geometry, or null)
+struct EpiExtra {
+  const void* addend = nullptr;    // out += addend                       (identity-shortcut gradient)
+  const void* mask_src = nullptr;  // out  = mask_src > 0 ? out : 0       (ReLU backward of the producing unit)
+  const void* bn_y = nullptr;      // stats += {sum out, sum out * bn_y}  (BatchNorm backward sums)
+  void* sk_partial = nullptr;      // stream-K workspace (tcgen05 path): fp32 partial tiles ...
+  int* sk_flags = nullptr;         // ... and ready flags (zeroed by the caller); see mcd_conv2d_streamk_workspace
+};
+
 struct Tap {
   int16_t dh, dw;   // source offset in source-grid pixels (after smul scaling of the tile coord)
   int16_t wk;       // tap slot inside the packed weight row

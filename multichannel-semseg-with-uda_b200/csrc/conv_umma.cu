@@ -41,19 +41,79 @@ struct FpropArgs {
   float* stats;
   void* out;
   const __nv_bfloat16* addend;   // optional nhwc tensor (output geometry) added in the epilogue: residual gradient
+  // dgrad fused with the backward of the BatchNorm+ReLU unit that produced the convolution's input (all nhwc,
+  // output geometry): out = mask_src > 0 ? out : 0 and, with bn_y, stats += {sum out, sum out * bn_y}
+  const __nv_bfloat16* mask_src;
+  const __nv_bfloat16* bn_y;
+  // stream-K schedule (sk_units > 0): CTA i owns the (tile, k-block) units [i * sk_units, (i+1) * sk_units) of the
+  // linearised tile x k-block space, so every CTA does the same amount of MMA work whatever the tile count.  A
+  // tile cut by a CTA boundary is finished by the CTA that started it (its LAST segment): the next CTA computes
+  // the remaining k-blocks FIRST, parks the fp32 partial accumulator in sk_partial[cta] and raises sk_flags[cta].
+  int sk_units;
+  float* sk_partial;          // [gridDim.x][BN/32][128][32] fp32
+  int* sk_flags;              // [gridDim.x], zero on entry
   Tap taps[kMaxTaps];
 };
+
+// the (tile, k-block range) segments of one CTA, identical for the producer, MMA and epilogue roles.
+// Stream-K order: (1) the tail k-blocks of the tile that starts before this CTA's range (partial, parked for the
+// owner), (2) the head k-blocks of the tile that ends after the range (this CTA owns it; the partner parked the
+// rest as ITS first segment, so the merge never waits long and overlaps the remaining MMAs), (3) the whole tiles.
+struct SegIter {
+  int64_t u, u_end;        // data-parallel: tile cursor / tile count; stream-K: whole-tile cursor / end (in units)
+  int kblocks, stride, sk;
+  int head_tile, head_kb1; // stream-K: pending owned partial tile (kb 0 .. head_kb1), -1 = none
+  int tail_tile, tail_kb0; // stream-K: pending foreign partial tile (kb tail_kb0 .. kblocks), -1 = none
+  int tile, kb0, kb1;
+  __device__ __forceinline__ bool next() {
+    if (sk) {
+      if (tail_tile >= 0) { tile = tail_tile; kb0 = tail_kb0; kb1 = kblocks; tail_tile = -1; return true; }
+      if (head_tile >= 0) { tile = head_tile; kb0 = 0; kb1 = head_kb1; head_tile = -1; return true; }
+      if (u >= u_end) return false;
+      tile = (int)(u / kblocks); kb0 = 0; kb1 = kblocks;
+      u += kblocks;
+      return true;
+    }
+    if (u >= u_end) return false;
+    tile = (int)u; kb0 = 0; kb1 = kblocks;
+    u += stride;
+    return true;
+  }
+};
+
+__device__ __forceinline__ SegIter make_seg_iter(const FpropArgs& a, int total_tiles, int kblocks) {
+  SegIter it;
+  it.kblocks = kblocks; it.stride = gridDim.x; it.sk = a.sk_units > 0;
+  it.head_tile = it.tail_tile = -1; it.head_kb1 = it.tail_kb0 = 0;
+  it.tile = 0; it.kb0 = 0; it.kb1 = 0;
+  if (it.sk) {
+    const int64_t total = (int64_t)total_tiles * kblocks;
+    int64_t b = (int64_t)blockIdx.x * a.sk_units;
+    int64_t e = b + a.sk_units < total ? b + a.sk_units : total;
+    if (b >= e) { it.u = it.u_end = 0; return it; }
+    const int bt = (int)(b / kblocks), bk = (int)(b - (int64_t)bt * kblocks);
+    const int et = (int)(e / kblocks), ek = (int)(e - (int64_t)et * kblocks);
+    if (bk > 0) { it.tail_tile = bt; it.tail_kb0 = bk; b = (int64_t)(bt + 1) * kblocks; }   // host: sk_units >= kblocks
+    if (ek > 0) { it.head_tile = et; it.head_kb1 = ek; e = (int64_t)et * kblocks; }
+    it.u = b; it.u_end = e;
+  } else {
+    it.u = blockIdx.x; it.u_end = total_tiles;
+  }
+  return it;
+}
 
 template <int BN>
 struct FpropCfg {
   static constexpr int A_BYTES = 128 * 128;          // 128 pixels x 64 ch bf16
   static constexpr int B_BYTES = BN * 128;           // BN rows x 64 ch bf16
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 4));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int STAT_ROWS = 1024;             // BatchNorm partial sums staged in smem up to this many channels
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                    2 * STAT_ROWS * 4;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;              // double-buffered (power of two, <= 512)
-  static constexpr int MIN_CTAS = BN <= 32 ? 2 : 1;           // thin tiles: two CTAs per SM
+  static constexpr int MIN_CTAS = BN <= 128 ? 2 : 1;          // two CTAs per SM: their epilogues / pipelines overlap
 };
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
@@ -71,9 +131,15 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  // BatchNorm sum / sum of squares of all tiles of this (persistent) CTA are collected in shared memory and
+  // flushed with one global atomic per channel at the end (instead of 2 per channel per warp per tile)
+  float* sstat = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  const bool stat_sm = a.stats != nullptr && a.rows <= Cfg::STAT_ROWS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = a.tiles_m * a.tiles_n;
+  if (stat_sm)
+    for (int i = threadIdx.x; i < 2 * a.rows; i += kThreads) sstat[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -93,32 +159,33 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int mt = tile / a.tiles_n;
-        const int n0 = (tile % a.tiles_n) * BN;
+      SegIter it = make_seg_iter(a, total_tiles, kblocks);
+      while (it.next()) {
+        int mt = it.tile / a.tiles_n;
+        const int n0 = (it.tile % a.tiles_n) * BN;
         const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
         const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
         const int n_img = mt;
         const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
-        for (int t = 0; t < a.ntaps; ++t) {
+        int t = it.kb0 / a.kchunks, kc = it.kb0 % a.kchunks;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           const Tap tap = a.taps[t];
           const CUtensorMap* amap = &maps.a[tap.map];
-          for (int kc = 0; kc < a.kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            uint8_t* sb = sa + Cfg::A_BYTES;
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (a.packed) {
-              // TW columns x TH rows, column-major in the tile: one {64 elements, TH rows} window box per column
-              for (int j = 0; j < a.TW; ++j)
-                tma_load_3d(sa + j * a.TH * 128, amap, &full_bar[stage],
-                            ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
-            } else {
-              tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
-            }
-            tma_load_2d(sb, &maps.b, &full_bar[stage], tap.wk * a.kc_pad + kc * 64, n0);
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (a.packed) {
+            // TW columns x TH rows, column-major in the tile: one {64 elements, TH rows} window box per column
+            for (int j = 0; j < a.TW; ++j)
+              tma_load_3d(sa + j * a.TH * 128, amap, &full_bar[stage],
+                          ((tw0 + j) * a.smul + tap.mdw) * a.cs_src, th0 + tap.mdh, n_img);
+          } else {
+            tma_load_4d(sa, amap, &full_bar[stage], kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
           }
+          tma_load_2d(sb, &maps.b, &full_bar[stage], tap.wk * a.kc_pad + kc * 64, n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++kc == a.kchunks) { kc = 0; ++t; }
         }
       }
     }
@@ -126,11 +193,12 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     constexpr uint32_t idesc = instr_desc_bf16(128, BN, 0, 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    SegIter it = make_seg_iter(a, total_tiles, kblocks);
+    while (it.next()) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -140,9 +208,10 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           const uint64_t bdesc = smem_desc_sw128(sb, 0, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-channel chunk: +32 bytes each
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                      (kb != it.kb0 || k != 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (kb == kblocks - 1) umma_commit(&tmem_full_bar[acc]);
+          if (kb == it.kb1 - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -155,9 +224,12 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     const int m = q * 32 + lane;
     const int ncover = a.planar ? a.rows : a.Cd_s;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int mt = tile / a.tiles_n;
-      const int n0 = (tile % a.tiles_n) * BN;
+    SegIter it = make_seg_iter(a, total_tiles, kblocks);
+    while (it.next()) {
+      const bool sk_dump = it.kb0 > 0;             // stream-K: tail k-blocks of a tile another CTA owns
+      const bool sk_merge = it.kb1 < kblocks;      // stream-K: this CTA owns the tile, CTA+1 did the tail
+      int mt = it.tile / a.tiles_n;
+      const int n0 = (it.tile % a.tiles_n) * BN;
       const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
       const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
       const int n_img = mt;
@@ -166,15 +238,77 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       const int wt = a.packed ? tw0 + m / a.TH : tw0 + m % a.TW;
       const bool pvalid = ht < a.Ht && wt < a.Wt;
       const int hd = ht * a.omul + a.oh0, wd = wt * a.omul + a.ow0;
+      // epilogue extras (addend / ReLU mask source / BatchNorm input) of one 32-channel chunk: all loads of a chunk
+      // are issued together, and those of the first chunk before waiting for the MMAs, so that their latency
+      // overlaps the wait instead of adding up load by load
+      const bool extras = !a.planar && pvalid && !sk_dump && (a.addend || a.mask_src || a.bn_y);
+      const int64_t obase = (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0;
+      uint4 ea[4], em[4], ey[4];
+      auto prefetch = [&](int c0) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          if (n0 + c0 + j8 * 8 < a.Cd_s) {
+            const int64_t off = obase + c0 + j8 * 8;
+            if (a.addend) ea[j8] = __ldg(reinterpret_cast<const uint4*>(a.addend + off));
+            if (a.mask_src) em[j8] = __ldg(reinterpret_cast<const uint4*>(a.mask_src + off));
+            if (a.bn_y) ey[j8] = __ldg(reinterpret_cast<const uint4*>(a.bn_y + off));
+          }
+        }
+      };
+      if (extras) prefetch(0);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      if (sk_dump) {
+        // park the partial accumulator for the owner (CTA blockIdx.x - 1) and raise the flag
+        float* dst = a.sk_partial + ((int64_t)blockIdx.x * (BN / 32) * 128 + m) * 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= ncover) break;
+          float v[32];
+          tmem_ld32(tmem_d + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float4* d4 = reinterpret_cast<float4*>(dst + (int64_t)(c0 / 32) * 128 * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (m == 0) asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(a.sk_flags + blockIdx.x), "r"(1) : "memory");
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      const float* part = nullptr;
+      if (sk_merge) {
+        if (m == 0) {
+          int ready = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(ready) : "l"(a.sk_flags + blockIdx.x + 1) : "memory");
+            if (!ready) __nanosleep(64);
+          } while (!ready);
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        part = a.sk_partial + ((int64_t)(blockIdx.x + 1) * (BN / 32) * 128 + m) * 32;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= ncover) break;   // warp-uniform
+        if (extras && c0 > 0) prefetch(c0);
         float v[32];
         tmem_ld32(tmem_d + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (part) {
+          const float4* p4 = reinterpret_cast<const float4*>(part + (int64_t)(c0 / 32) * 128 * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t4 = __ldcg(p4 + j);
+            v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+          }
+        }
         if (a.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -182,6 +316,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
             v[j] += (c < a.rows) ? __ldg(a.bias + c) : 0.f;
           }
         }
+        float vy[32];                       // v * bn_y for the fused BatchNorm-backward sums
         if (pvalid) {
           if (a.planar) {
             float* o = reinterpret_cast<float*>(a.out);
@@ -202,11 +337,26 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                 for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
                 if (a.addend) {
                   float r[8];
-                  unpack8(*reinterpret_cast<const uint4*>(a.addend + ooff + j8 * 8), r);
+                  unpack8(ea[j8], r);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) f[k] += r[k];
                 }
+                if (a.mask_src) {
+                  float r[8];
+                  unpack8(em[j8], r);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) f[k] = r[k] > 0.f ? f[k] : 0.f;
+                }
+                if (a.bn_y) {
+                  float r[8];
+                  unpack8(ey[j8], r);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) { v[j8 * 8 + k] = f[k]; vy[j8 * 8 + k] = f[k] * r[k]; }
+                }
                 *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
+              } else if (a.bn_y) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { v[j8 * 8 + k] = 0.f; vy[j8 * 8 + k] = 0.f; }
               }
             }
           }
@@ -216,7 +366,11 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           // holding column j.
           float s1[32], s2[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { float x = pvalid ? v[j] : 0.f; s1[j] = x; s2[j] = x * x; }
+          for (int j = 0; j < 32; ++j) {
+            float x = pvalid ? v[j] : 0.f;
+            s1[j] = x;
+            s2[j] = a.bn_y ? (pvalid ? vy[j] : 0.f) : x * x;
+          }
 #pragma unroll
           for (int step = 16; step >= 1; step >>= 1) {
             const bool up = (lane & step) != 0;
@@ -232,8 +386,9 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           }
           int c = n0 + c0 + lane;
           if (c < a.rows) {
-            atomicAdd(a.stats + c, s1[0]);
-            atomicAdd(a.stats + a.rows + c, s2[0]);
+            float* dst = stat_sm ? sstat : a.stats;
+            atomicAdd(dst + c, s1[0]);
+            atomicAdd(dst + a.rows + c, s2[0]);
           }
         }
       }
@@ -248,6 +403,8 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (stat_sm && blockIdx.x < total_tiles)
+    for (int i = threadIdx.x; i < 2 * a.rows; i += kThreads) atomicAdd(a.stats + i, sstat[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -728,22 +885,47 @@ static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, 
   return check_launch("conv_umma_fprop");
 }
 
+static void fprop_tiling(const TapProblem& p, int planar, int* TH, int* TW, int* tiles_m, int* tiles_n, int* BN) {
+  if (p.packed) pick_tile_packed(p.Ht, p.Wt, 128, TH, TW);
+  else pick_tile(p.Ht, p.Wt, 128, TH, TW);
+  const int ncover = planar ? p.rows : p.Cd_s;
+  *BN = ncover > 128 ? 256 : (ncover > 64 ? 128 : (ncover > 32 ? 64 : (ncover > 16 ? 32 : 16)));
+  *tiles_m = p.N * ((p.Ht + *TH - 1) / *TH) * ((p.Wt + *TW - 1) / *TW);
+  *tiles_n = (ncover + *BN - 1) / *BN;
+}
+
+// stream-K pays when the data-parallel schedule would leave the last wave of tiles mostly empty
+static bool streamk_plan(int total_tiles, int kblocks, int BN, int packed, int* G, int* units) {
+  const int slots = sm_count() * (BN <= 128 ? 2 : 1);
+  if (packed || total_tiles <= slots || kblocks < 2) return false;
+  const int waves = (total_tiles + slots - 1) / slots;
+  if ((double)total_tiles / ((double)waves * slots) > 0.92) return false;
+  const int64_t U = (int64_t)total_tiles * kblocks;
+  const int64_t W = (U + slots - 1) / slots;
+  if (W < kblocks) return false;
+  *G = (int)((U + W - 1) / W);
+  *units = (int)W;
+  return true;
+}
+
 // src: activations for this problem; for strided fprop the parity maps are built over (Hs, Ws).
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                        float* stats, const void* addend, const TapProblem& p, cudaStream_t st) {
+                        float* stats, const EpiExtra& ex, const TapProblem& p, cudaStream_t st) {
   if (p.ntaps == 0) return MCD_OK;
   if (!umma_problem_supported(p)) { set_error("umma fprop: unsupported problem"); return MCD_E_INVALID; }
   FpropArgs a;
   memset(&a, 0, sizeof(a));
   a.N = p.N; a.Ht = p.Ht; a.Wt = p.Wt;
   a.packed = p.packed; a.cs_src = p.Cs_src; a.smul = p.smul;
-  if (p.packed) pick_tile_packed(p.Ht, p.Wt, 128, &a.TH, &a.TW);
-  else pick_tile(p.Ht, p.Wt, 128, &a.TH, &a.TW);
+  int bn_unused;
+  fprop_tiling(p, planar, &a.TH, &a.TW, &a.tiles_m, &a.tiles_n, &bn_unused);
   a.tiles_h = (p.Ht + a.TH - 1) / a.TH; a.tiles_w = (p.Wt + a.TW - 1) / a.TW;
   a.kchunks = (p.Kc + 63) / 64; a.ntaps = p.ntaps; a.kc_pad = p.kc_pad;
   a.rows = p.rows; a.omul = p.omul; a.oh0 = p.oh0; a.ow0 = p.ow0; a.Hd = p.Hd; a.Wd = p.Wd;
   a.Cd_s = p.Cd_s; a.planar = planar; a.bias = bias; a.stats = stats; a.out = out;
-  a.addend = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(addend);
+  a.addend = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.addend);
+  a.mask_src = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.mask_src);
+  a.bn_y = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.bn_y);
   for (int t = 0; t < p.ntaps; ++t) a.taps[t] = p.taps[t];
 
   UmmaMaps maps;
@@ -768,19 +950,36 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   }
   if (!used[0]) maps.a[0] = maps.a[p.taps[0].map];  // keep the prefetch target valid
 
-  int ncover = planar ? p.rows : p.Cd_s;
-  int BN = ncover > 128 ? 256 : (ncover > 64 ? 128 : (ncover > 32 ? 64 : (ncover > 16 ? 32 : 16)));
+  int BN, G;
+  fprop_tiling(p, planar, &a.TH, &a.TW, &a.tiles_m, &a.tiles_n, &BN);
   int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, BN);
   if (rc != MCD_OK) return rc;
-  a.tiles_m = p.N * a.tiles_h * a.tiles_w;
-  a.tiles_n = (ncover + BN - 1) / BN;
-  const int slots = sm_count() * (BN <= 32 ? 2 : 1);        // persistent CTAs: one (thin tiles: two) per SM
-  dim3 grid((unsigned)min(a.tiles_m * a.tiles_n, slots));
+  const int slots = sm_count() * (BN <= 128 ? 2 : 1);   // persistent CTAs per SM (FpropCfg::MIN_CTAS)
+  G = min(a.tiles_m * a.tiles_n, slots);
+  if (ex.sk_partial && ex.sk_flags) {
+    int units = 0, g2 = 0;
+    if (streamk_plan(a.tiles_m * a.tiles_n, a.ntaps * a.kchunks, BN, p.packed, &g2, &units)) {
+      G = g2; a.sk_units = units;
+      a.sk_partial = reinterpret_cast<float*>(ex.sk_partial); a.sk_flags = ex.sk_flags;
+    }
+  }
+  dim3 grid((unsigned)G);
   if (BN == 256) return launch_fprop_bn<256>(maps, a, grid, st);
   if (BN == 128) return launch_fprop_bn<128>(maps, a, grid, st);
   if (BN == 64) return launch_fprop_bn<64>(maps, a, grid, st);
   if (BN == 32) return launch_fprop_bn<32>(maps, a, grid, st);
   return launch_fprop_bn<16>(maps, a, grid, st);
+}
+
+// stream-K workspace of one problem: bytes of fp32 partial tiles and number of int flags (0 / 0: not used)
+size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags) {
+  *n_flags = 0;
+  if (p.ntaps == 0 || !umma_problem_supported(p)) return 0;
+  int TH, TW, tiles_m, tiles_n, BN, G = 0, units = 0;
+  fprop_tiling(p, planar, &TH, &TW, &tiles_m, &tiles_n, &BN);
+  if (!streamk_plan(tiles_m * tiles_n, p.ntaps * ((p.Kc + 63) / 64), BN, p.packed, &G, &units)) return 0;
+  *n_flags = G;
+  return (size_t)G * BN * 128 * sizeof(float);
 }
 
 static int wgrad_bn(const mcd_conv_geom& g) { return g.Cin > 128 ? 256 : (g.Cin > 64 ? 128 : 64); }

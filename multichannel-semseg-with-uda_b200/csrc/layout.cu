@@ -97,7 +97,8 @@ __global__ void pack_weight_rows_kernel(const float* __restrict__ w, __nv_bfloat
 
 // ---- multi-tensor re-pack: ONE launch refreshes every bf16 shadow of a model after an optimizer step ------
 // item (12 x int64 in device memory): w, dst_fprop, dst_dgrad (0 = absent), Cout, Cin, R, S, kind_f, kind_d,
-// cs_f, cs_d, unused.  kind 0 = [rows][taps][kc_pad] layout, 1 = row-packed [rows][R][64] layout.
+// cs_f, cs_d, unused.  kind 0 = [rows][taps][kc_pad] layout, 1 = row-packed [rows][R][64] layout, 2 = rowconv
+// layout (conv_rows.cu).
 // Standard layouts: a block transposes one 32(co) x 32(ci) x T tile through shared memory so that the fp32 OIHW
 // reads and BOTH bf16 writes are coalesced (the pad channels of the packs were zeroed when they were created and
 // are never touched again).  Row-packed layouts (three tiny stem layers) use the element-wise path.
@@ -160,6 +161,11 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
         else if (kc < Cout) v = w[(((int64_t)kc * Cin + row) * R + (R - 1 - t / S)) * S + (S - 1 - t % S)];
         dst[i] = f2bf(v);
       }
+    } else if (kind == 2) {
+      const int HC = Cs / 8, SP = S <= 4 ? 4 : 8, NB = (rows + 15) / 16 * 16;
+      const int64_t total = (int64_t)R * HC * SP * NB * 8;
+      for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x)
+        dst[i] = f2bf(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, pass));
     } else {
       const int64_t total = (int64_t)rows * R * 64;
       for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {

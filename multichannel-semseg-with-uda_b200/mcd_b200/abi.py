@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
@@ -40,10 +40,12 @@ _SIGNATURES = {
     "mcd_nhwc_bf16_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_pack_weight": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_pack_weight_rows": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_pack_weight_rowconv": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_pack_weights_multi": (c_int, [P, c_int, c_int, c_int, P]),
     "mcd_conv2d_pack_kind": (c_int, [POINTER(ConvGeom), c_int, c_int]),
-    "mcd_conv2d_fprop": (c_int, [P, P, P, P, c_int, P, POINTER(ConvGeom), c_int, c_int, P]),
-    "mcd_conv2d_dgrad": (c_int, [P, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
+    "mcd_conv2d_fprop": (c_int, [P, P, P, P, c_int, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
+    "mcd_conv2d_streamk_workspace": (c_size_t, [POINTER(ConvGeom), c_int, c_int, c_int, POINTER(c_int)]),
+    "mcd_conv2d_dgrad": (c_int, [P, P, P, P, P, P, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
     "mcd_conv2d_wgrad_workspace": (c_size_t, [POINTER(ConvGeom), c_int]),
     "mcd_conv2d_wgrad": (c_int, [P, P, P, P, P, c_size_t, POINTER(ConvGeom), c_int, c_int, c_int, P]),
     "mcd_bn_stats": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
@@ -54,7 +56,7 @@ _SIGNATURES = {
     "mcd_bn_apply": (c_int, [P, P, P, P, P, P, c_int, P, c_int64, c_int, c_int, c_int, P]),
     "mcd_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int64, c_int, c_int, c_int, P]),
     "mcd_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P,
-                                 P, c_int64, c_int, c_int, c_int, P]),
+                                 P, c_int, c_int64, c_int, c_int, c_int, P]),
     "mcd_deconv16s8_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_deconv16s8_bwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_bilinear_up_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -5,6 +5,8 @@ only so that parameters, buffers, initialisation and state_dict keys are byte-co
 reference's checkpoints (adapt_trainer.py:232-245, adapt_tester.py:79-83); their `forward` never calls
 a stock torch kernel - it launches the library's kernels through `ops`.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -49,6 +51,7 @@ class DirectGrads:
     def __init__(self):
         self.keep = []
         self.stash = {}      # data_ptr of a block input -> identity-shortcut gradient awaiting conv1's dgrad
+        self.bnsums = {}     # data_ptr of a dgrad output -> (raw BatchNorm-backward sums, data_ptr of the BN input)
 
     def __enter__(self):
         global _direct
@@ -64,12 +67,21 @@ class DirectGrads:
         if side is not None:
             torch.cuda.current_stream(device).wait_stream(side)
         self.keep.clear()
+        self.bnsums.clear()
         if self.stash:
             self.stash.clear()
             raise RuntimeError("mcd_b200: an identity-shortcut gradient was stashed but never consumed")
 
 
 _direct = None
+_fuse_bn_bwd = os.environ.get("MCD_FUSE_BN_BWD", "1") != "0"
+
+
+def set_fuse_bn_bwd(flag):
+    """fuse ReLU mask + BatchNorm-backward sums into the dgrad epilogue of sole-consumer convolutions
+    (direct-gradient mode only); off = separate reduction pass (for A/B measurements and tests)."""
+    global _fuse_bn_bwd
+    _fuse_bn_bwd = bool(flag)
 
 
 def set_overlap_wgrad(flag):
@@ -90,11 +102,15 @@ def _as_nhwc_grad(dy):
 # ---------------------------------------------------------------------------------------------
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, mod, planar, want_stats):
+    def forward(ctx, x, weight, bias, mod, planar, want_stats, bn_y):
         g = mod.geom(x.shape)
         y, stats = ops.conv_fprop(x, mod.packed(0, g), bias, g, planar=planar, want_stats=want_stats)
         ctx.mod, ctx.g, ctx.planar = mod, g, planar
         ctx.has_bias = bias is not None
+        # bn_y: x = relu(bn(bn_y)) and this convolution is x's only consumer (apart from an identity shortcut):
+        # in direct-gradient mode the dgrad epilogue then applies the ReLU mask and accumulates the BatchNorm
+        # backward sums, which removes that unit's reduction pass
+        ctx.bn_y = bn_y
         ctx.save_for_backward(x)
         if stats is None:
             stats = torch.empty(0, dtype=F32, device=x.device)
@@ -129,7 +145,10 @@ class _ConvFn(torch.autograd.Function):
             # cannot share an SM with the persistent wgrad CTAs (both want ~190 KB of shared memory); the wgrad
             # that follows on the side stream then overlaps the memory-bound BatchNorm kernels of the next unit.
             add = _direct.stash.pop(x.data_ptr(), None)      # identity-shortcut gradient of a BasicBlock
-            if need_dx:
+            if need_dx and ctx.bn_y is not None and _fuse_bn_bwd:
+                dx, sums = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add, relu_src=x, bn_y=ctx.bn_y)
+                _direct.bnsums[dx.data_ptr()] = (sums, ctx.bn_y.data_ptr(), dx)
+            elif need_dx:
                 dx = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add)
             elif add is not None:
                 dx = add
@@ -143,7 +162,7 @@ class _ConvFn(torch.autograd.Function):
                 sync = getattr(p, "_mcd_sync", None)
                 if sync is not None:
                     sync.mark_ready(p, side)
-            return dx, None, None, None, None, None
+            return dx, None, None, None, None, None, None
         if need_dx and need_dw and _overlap_wgrad:
             # dgrad and wgrad both consume dy and are independent: wgrad runs on a side stream so that its CTAs
             # fill the SMs the other kernel's last (partial) wave of tiles leaves idle.  Every use of the side
@@ -156,12 +175,12 @@ class _ConvFn(torch.autograd.Function):
                 dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
             dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
             main.wait_stream(side)
-            return dx, dw, db, None, None, None
+            return dx, dw, db, None, None, None, None
         if need_dx:
             dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
         if need_dw:
             dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class Conv2d(nn.Conv2d):
@@ -200,11 +219,16 @@ class Conv2d(nn.Conv2d):
             self._packs[key] = hit
         return hit[1]
 
-    def conv_raw(self, x, want_stats=False):
+    def conv_raw(self, x, want_stats=False, sole=False):
+        """sole=True: the caller guarantees that this convolution is the only consumer of `x` (an identity
+        shortcut of the same block aside), see _ConvFn.forward."""
+        bn_y = getattr(x, "_mcd_bn_y", None) if sole else None
         x = ops.to_nhwc(x)
         if x.shape[1] < self.in_channels:
             raise ValueError("Conv2d expected >= %d input channels, got %d" % (self.in_channels, x.shape[1]))
-        y, stats = _ConvFn.apply(x, self.weight, self.bias, self, self.planar_out, want_stats)
+        if bn_y is not None and (tuple(bn_y.shape) != tuple(x.shape) or x.shape[1] != self.in_channels):
+            bn_y = None
+        y, stats = _ConvFn.apply(x, self.weight, self.bias, self, self.planar_out, want_stats, bn_y)
         return y, (stats if want_stats else None)
 
     def forward(self, x):
@@ -230,9 +254,12 @@ class _BNActFn(torch.autograd.Function):
         y, z, gamma, aff, res, res_gamma, res_aff = ctx.saved_tensors
         dz = _as_nhwc_grad(dz)
         want_dres = ctx.has_res and ctx.needs_input_grad[4]
+        fused = _direct.bnsums.pop(dz.data_ptr(), None) if _direct is not None else None
+        if fused is not None and (fused[1] != y.data_ptr() or ctx.has_res_bn or not ctx.relu or not ctx.training):
+            raise RuntimeError("mcd_b200: fused BatchNorm-backward sums reached the wrong unit")
         dy, dgamma, dbeta, dres, dres_gamma, dres_beta = ops.bn_bwd(
             dz, z, y, gamma, aff, ctx.training, ctx.relu, res=res, res_gamma=res_gamma, res_aff=res_aff,
-            res_training=ctx.res_training, want_dres=want_dres)
+            res_training=ctx.res_training, want_dres=want_dres, raw_sums=fused[0] if fused is not None else None)
         if not want_dres:
             dres = None
         elif _direct is not None and not ctx.has_res_bn and ctx.res_ptr is not None:
@@ -256,7 +283,10 @@ class BatchNorm2d(nn.BatchNorm2d):
         if res_bn is not None:
             return _BNActFn.apply(y, stats, self.weight, self.bias, res, res_stats, res_bn.weight,
                                   res_bn.bias, self, res_bn, relu)
-        return _BNActFn.apply(y, stats, self.weight, self.bias, res, None, None, None, self, None, relu)
+        z = _BNActFn.apply(y, stats, self.weight, self.bias, res, None, None, None, self, None, relu)
+        if relu and self.training and y.shape[1] == self.num_features:
+            z._mcd_bn_y = y      # lets a sole-consumer convolution start this unit's backward in its dgrad epilogue
+        return z
 
     def forward(self, x):
         x = ops.to_nhwc(x)
@@ -264,9 +294,10 @@ class BatchNorm2d(nn.BatchNorm2d):
         return self.fused(x, stats, relu=False)
 
 
-def conv_bn_act(conv, bn, x, relu=True, res=None, res_conv=None, res_bn=None):
-    """z = act(bn(conv(x)) + residual); residual = res (identity) or res_bn(res_conv(x_res))."""
-    y, stats = conv.conv_raw(x, want_stats=bn.training)
+def conv_bn_act(conv, bn, x, relu=True, res=None, res_conv=None, res_bn=None, sole=False):
+    """z = act(bn(conv(x)) + residual); residual = res (identity) or res_bn(res_conv(x_res)).
+    sole: `conv` is the only consumer of x (Conv2d.conv_raw)."""
+    y, stats = conv.conv_raw(x, want_stats=bn.training, sole=sole)
     if res_conv is not None:
         ry, rstats = res_conv.conv_raw(res, want_stats=res_bn.training)
         return bn.fused(y, stats, relu=relu, res=ry, res_stats=rstats, res_bn=res_bn)
@@ -279,10 +310,26 @@ class ConvBNReLU(nn.Sequential):
     def forward(self, x):
         mods = list(self.children())
         i = 0
+        sole = getattr(x, "_mcd_sole", False)
         while i < len(mods):
             conv, bn = mods[i], mods[i + 1]
-            x = conv_bn_act(conv, bn, x, relu=True)
+            x = conv_bn_act(conv, bn, x, relu=True, sole=sole)
+            sole = True          # intermediate activations never leave this container
             i += 3
+        return x
+
+
+class SoleChain(nn.Sequential):
+    """nn.Sequential whose intermediate activations are read by the next child only (the DRN trunk stages,
+    reference models/dilated_fcn.py `self.base = nn.Sequential(*list(model.children())[:-2])`).  It flags them so
+    that the next stage's first convolution may fuse the producing unit's BatchNorm backward (Conv2d.conv_raw)."""
+
+    def forward(self, x):
+        mods = list(self.children())
+        for i, m in enumerate(mods):
+            x = m(x)
+            if i + 1 < len(mods):
+                x._mcd_sole = True
         return x
 
 

@@ -5,6 +5,7 @@ Activations are bf16 NHWC buffers exposed as logical-NCHW `channels_last` tensor
 full-resolution logits are ordinary contiguous NCHW ("planar") tensors.
 """
 import ctypes
+import os
 
 import torch
 
@@ -143,6 +144,12 @@ def pack_weight_for(w, g, mode, algo=None):
     assert w.dtype == F32 and w.is_contiguous()
     co, ci, r, s = w.shape
     rows, cs = (ci, g.Cout_s) if mode else (co, g.Cin_s)
+    if kind == 2:      # "row convolution" operand for the stride-1 stem layers (csrc/conv_rows.cu)
+        out = torch.empty((r, (cs // 8) * (4 if s <= 4 else 8), round_up(rows, 16) // 8, 8, 8), dtype=BF16,
+                          device=w.device)
+        abi.check(abi.lib().mcd_pack_weight_rowconv(_p(w), _p(out), co, ci, r, s, cs, mode, _dev(w), _stream(w)),
+                  "pack_weight_rowconv")
+        return out
     out = torch.empty((rows, r, 64), dtype=BF16, device=w.device)
     abi.check(abi.lib().mcd_pack_weight_rows(_p(w), _p(out), co, ci, r, s, cs, mode, _dev(w), _stream(w)),
               "pack_weight_rows")
@@ -195,30 +202,67 @@ def conv_geom(x_shape, cin, cout, r, s, stride, dil, pad, cout_s=None):
                     dil, pad, ho, wo)
 
 
+_streamk_enabled = os.environ.get("MCD_STREAMK", "0") == "1"
+_sk_cache = {}
+
+
+def set_streamk(flag):
+    """stream-K schedule of the tcgen05 fprop / dgrad kernels for layers whose tile count does not fill the last
+    wave of persistent CTAs.  OFF by default (MCD_STREAMK=1 turns it on): measured on B200 it is slower than the
+    tile-per-CTA schedule (8x60x80, 256 ch: 80 us vs 64 us) - CTAs no longer walk the weight matrix in lockstep,
+    which costs more in L2 than the empty last wave does, and concurrent streams fill that wave anyway."""
+    global _streamk_enabled
+    _streamk_enabled = bool(flag)
+
+
+def _streamk_ws(g, mode, planar, algo, device):
+    """(partial, flags) workspace tensors for mcd_conv2d_fprop / dgrad, or (None, None)."""
+    if not _streamk_enabled:
+        return None, None
+    key = (tuple(getattr(g, f) for f, _ in g._fields_), mode, planar, algo)
+    hit = _sk_cache.get(key)
+    if hit is None:
+        nf = ctypes.c_int(0)
+        nbytes = int(abi.lib().mcd_conv2d_streamk_workspace(
+            ctypes.byref(g), mode, abi.OUT_PLANAR_F32 if planar else abi.OUT_NHWC_BF16, algo, ctypes.byref(nf)))
+        hit = _sk_cache[key] = (nbytes, nf.value)
+    if not hit[0]:
+        return None, None
+    return torch.empty(hit[0], dtype=torch.uint8, device=device), zeros_f32(hit[1], device)
+
+
 def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
     """returns (y, stats) - y nhwc bf16 [N,Cout_s,Ho,Wo] or planar fp32 [N,Cout,Ho,Wo]."""
     assert is_nhwc(x) and x.shape[1] == g.Cin_s
+    algo = _algo if algo is None else algo
     if planar:
         y = torch.empty((g.N, g.Cout, g.Ho, g.Wo), dtype=F32, device=x.device)
     else:
         y = nhwc_empty(g.N, g.Cout_s, g.Ho, g.Wo, x.device)
     stats = zeros_f32(2 * g.Cout, x.device) if want_stats else None
+    skp, skf = _streamk_ws(g, 0, planar, algo, x.device)
     abi.check(abi.lib().mcd_conv2d_fprop(
         _p(x), _p(w_packed), _p(bias), _p(y), abi.OUT_PLANAR_F32 if planar else abi.OUT_NHWC_BF16,
-        _p(stats), ctypes.byref(g), _algo if algo is None else algo, _dev(x), _stream(x)), "conv2d_fprop")
+        _p(stats), _p(skp), _p(skf), ctypes.byref(g), algo, _dev(x), _stream(x)), "conv2d_fprop")
     return y, stats
 
 
-def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None):
-    """dx = dgrad (+ add: an nhwc tensor of dx's shape, e.g. the identity-shortcut gradient)."""
+def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=None):
+    """dx = dgrad (+ add: an nhwc tensor of dx's shape, e.g. the identity-shortcut gradient).
+    relu_src (the convolution's input, a ReLU output): dx is masked by relu_src > 0 in the epilogue;
+    bn_y (input of the BatchNorm that produced relu_src): also returns the fp32 [2,C] raw sums
+    {sum dx, sum dx*bn_y} for bn_bwd(..., raw_sums=...).  Returns dx or (dx, sums)."""
     assert is_nhwc(dy) and dy.shape[1] == g.Cout_s
     dx = nhwc_empty(g.N, g.Cin_s, g.H, g.W, dy.device)
-    if add is not None:
-        assert is_nhwc(add) and tuple(add.shape) == tuple(dx.shape)
-    abi.check(abi.lib().mcd_conv2d_dgrad(_p(dy), _p(w_packed_dgrad), _p(dx), _p(add), ctypes.byref(g),
-                                         _algo if algo is None else algo, _dev(dy), _stream(dy)),
-              "conv2d_dgrad")
-    return dx
+    for t in (add, relu_src, bn_y):
+        assert t is None or (is_nhwc(t) and tuple(t.shape) == tuple(dx.shape))
+    sums = zeros_f32(2 * g.Cin, dy.device) if bn_y is not None else None
+    algo = _algo if algo is None else algo
+    skp, skf = _streamk_ws(g, 1, False, algo, dy.device)
+    abi.check(abi.lib().mcd_conv2d_dgrad(_p(dy), _p(w_packed_dgrad), _p(dx), _p(add), _p(relu_src), _p(bn_y),
+                                         _p(sums), _p(skp), _p(skf), ctypes.byref(g), algo, _dev(dy),
+                                         _stream(dy)), "conv2d_dgrad")
+    return dx if bn_y is None else (dx, sums)
 
 
 def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):
@@ -296,9 +340,11 @@ def bn_apply(y, aff, res, res_aff, relu):
 
 
 def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_aff=None,
-           res_training=False, want_dres=False):
+           res_training=False, want_dres=False, raw_sums=None):
     """returns dy, dgamma, dbeta, dres, dres_gamma, dres_beta.  `aff` / `res_aff`: either the [4,C] tensor of
-    bn_finalize (scale, shift, mean, rstd) or the [2,C] (mean, rstd) tensor of bn_forward."""
+    bn_finalize (scale, shift, mean, rstd) or the [2,C] (mean, rstd) tensor of bn_forward.
+    raw_sums: the [2*C] sums of conv_dgrad(..., relu_src=z, bn_y=y) - dz is then already ReLU-masked, the reduction
+    pass is skipped and the identity-residual gradient is dz itself."""
     if aff.shape[0] == 2:
         aff = (None, None, aff[0], aff[1])
     if res_aff is not None and res_aff.shape[0] == 2:
@@ -307,6 +353,15 @@ def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_a
     count = n * h * w
     dev, st = _dev(y), _stream(y)
     has_res_bn = res_gamma is not None
+    if raw_sums is not None:
+        assert not has_res_bn
+        dy = nhwc_empty(n, c, h, w, y.device)
+        dgb = torch.empty((2, c), dtype=F32, device=y.device)
+        abi.check(abi.lib().mcd_bn_bwd_apply(
+            _p(dz), None, _p(y), _p(gamma), _p(aff[2]), _p(aff[3]), _p(raw_sums), int(training), 0,
+            _p(dy), _p(dgb[0]), _p(dgb[1]), None, None, None, None, 0, None, None, None, 1, count, c, c, dev, st),
+            "bn_bwd_apply")
+        return dy, dgb[0], dgb[1], (dz if want_dres else None), None, None
     sums = zeros_f32(3 * c, y.device)
     abi.check(abi.lib().mcd_bn_bwd_reduce(
         _p(dz), _p(z), _p(y), _p(aff[2]), _p(aff[3]), _p(res) if has_res_bn else None,
@@ -320,7 +375,7 @@ def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_a
         _p(dy), _p(dgb[0]), _p(dgb[1]), _p(res) if has_res_bn else None,
         _p(res_gamma) if has_res_bn else None, _p(res_aff[2]) if has_res_bn else None,
         _p(res_aff[3]) if has_res_bn else None, int(res_training), _p(dres),
-        _p(dgb[2]) if has_res_bn else None, _p(dgb[3]) if has_res_bn else None, count, c, c, dev, st),
+        _p(dgb[2]) if has_res_bn else None, _p(dgb[3]) if has_res_bn else None, 0, count, c, c, dev, st),
         "bn_bwd_apply")
     return dy, dgb[0], dgb[1], dres, (dgb[2] if has_res_bn else None), (dgb[3] if has_res_bn else None)
 
@@ -495,8 +550,9 @@ def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
                      lambda: _conv_fprop_raw(x, w_packed, bias, g, planar, want_stats, algo))
 
 
-def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None):  # noqa: F811
-    return _profiled("conv_fprop_kernel (dgrad)", g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add))
+def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=None):  # noqa: F811
+    return _profiled("conv_fprop_kernel (dgrad)", g,
+                     lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add, relu_src, bn_y))
 
 
 def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):  # noqa: F811

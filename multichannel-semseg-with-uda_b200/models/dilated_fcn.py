@@ -23,7 +23,7 @@ from torch.nn import Parameter
 
 import loss as _loss
 from mcd_b200 import ops
-from mcd_b200.nn import (BatchNorm2d, BilinearUpsample, Conv2d, DepthwiseDeconv16s8, conv_bn_act)
+from mcd_b200.nn import (BatchNorm2d, BilinearUpsample, Conv2d, DepthwiseDeconv16s8, SoleChain, conv_bn_act)
 from models import drn
 from models.fusion import AddFusion, get_fusion_model
 
@@ -48,7 +48,7 @@ class DRNSegBase(nn.Module):
         if ver != "ver1":
             raise NotImplementedError("ver2 heads are outside the libmcd_sm100 hot-path scope")
         model = _trunk(model_name, pretrained, input_ch)
-        self.base = nn.Sequential(*list(model.children())[:-2])
+        self.base = SoleChain(*list(model.children())[:-2])
         self.ver = ver
         self.seg = Conv2d(model.out_dim, n_class, kernel_size=1, bias=True, planar_out=True)
         _he_init(self.seg)
@@ -108,7 +108,7 @@ class MultiTaskEncoder(nn.Module):
     def __init__(self, model_name, pretrained=True, input_ch=3):
         super().__init__()
         model = _trunk(model_name, pretrained, input_ch)
-        self.base = nn.Sequential(*list(model.children())[:-2])
+        self.base = SoleChain(*list(model.children())[:-2])
 
     def forward(self, x):
         return self.base(x)

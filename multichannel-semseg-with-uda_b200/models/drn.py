@@ -39,18 +39,23 @@ class BasicBlock(nn.Module):
         self.downsample = downsample
         self.stride = stride
         self.residual = residual
+        self.inner_input = False   # True: the input is the previous block's output and nothing else reads it
 
     def forward(self, x):
-        out = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        # `sole`: conv1 is the only convolution reading x (the downsample branch would be a second one); x comes
+        # from the previous block of the same stage (DRN._make_layer sets inner_input) or is flagged by DRN.forward
+        sole = (self.inner_input or getattr(x, "_mcd_sole", False)) and self.downsample is None
+        out = conv_bn_act(self.conv1, self.bn1, x, relu=True, sole=sole)
         if not self.residual:
-            return conv_bn_act(self.conv2, self.bn2, out, relu=True)
+            return conv_bn_act(self.conv2, self.bn2, out, relu=True, sole=True)
         if self.downsample is not None:
             ds_conv, ds_bn = self.downsample[0], self.downsample[1]
-            return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x, res_conv=ds_conv, res_bn=ds_bn)
+            return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x, res_conv=ds_conv, res_bn=ds_bn,
+                               sole=True)
         # identity shortcut: x feeds conv1 AND the residual add; the flag lets MCDStep fuse the shortcut gradient
         # into conv1's dgrad epilogue (mcd_b200/nn.py, direct-gradient mode)
         x._mcd_shortcut = True
-        return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x)
+        return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x, sole=True)
 
 
 class DRN(nn.Module):
@@ -103,6 +108,8 @@ class DRN(nn.Module):
         self.inplanes = planes * block.expansion
         stack += [block(self.inplanes, planes, residual=residual, dilation=(dilation, dilation))
                   for _ in range(1, blocks)]
+        for b in stack[1:]:
+            b.inner_input = True
         return nn.Sequential(*stack)
 
     def _make_conv_layers(self, channels, convs, stride=1, dilation=1):
@@ -121,9 +128,12 @@ class DRN(nn.Module):
     def forward(self, x):
         # The ImageNet classifier forward (avgpool + fc) is outside the MCD path.
         feats = []
-        for stage in self.stages():
+        stages = self.stages()
+        for i, stage in enumerate(stages):
             x = stage(x)
             feats.append(x)
+            if not self.out_middle and i + 1 < len(stages):
+                x._mcd_sole = True     # read by the next stage only (mcd_b200.nn: fused BatchNorm backward)
         if self.out_middle:
             return x, feats[1:]
         return x

@@ -45,15 +45,15 @@ def test_conv_geom_struct_matches_header():
 
 
 def test_pack_kind_is_host_logic():
-    """mcd_conv2d_pack_kind is pure host code: thin-channel layers get the row-packed layout."""
+    """mcd_conv2d_pack_kind is pure host code: thin stem layers get the row-convolution (2) or row-packed (1) layout."""
     from mcd_b200 import abi, ops
     lib = abi.lib()
     g0 = ops.conv_geom((4, 8, 480, 640), 6, 16, 7, 7, 1, 1, 3)          # layer0
     g1 = ops.conv_geom((4, 16, 480, 640), 16, 16, 3, 3, 1, 1, 1)        # layer1
     g2 = ops.conv_geom((4, 16, 480, 640), 16, 32, 3, 3, 2, 1, 1)        # layer2 (stride 2)
     g6 = ops.conv_geom((4, 512, 60, 80), 512, 512, 3, 3, 1, 4, 4)       # layer6 (dilated)
-    assert [lib.mcd_conv2d_pack_kind(ctypes.byref(g), 0, abi.ALGO_AUTO) for g in (g0, g1, g2, g6)] == [1, 1, 1, 0]
-    assert [lib.mcd_conv2d_pack_kind(ctypes.byref(g), 1, abi.ALGO_AUTO) for g in (g0, g1, g2, g6)] == [0, 1, 0, 0]
+    assert [lib.mcd_conv2d_pack_kind(ctypes.byref(g), 0, abi.ALGO_AUTO) for g in (g0, g1, g2, g6)] == [2, 2, 1, 0]
+    assert [lib.mcd_conv2d_pack_kind(ctypes.byref(g), 1, abi.ALGO_AUTO) for g in (g0, g1, g2, g6)] == [2, 2, 0, 0]
     assert lib.mcd_conv2d_pack_kind(ctypes.byref(g0), 0, abi.ALGO_DIRECT) == 0
     assert (g2.Ho, g2.Wo) == (240, 320) and (g6.Ho, g6.Wo) == (60, 80)
     assert lib.mcd_conv2d_wgrad_workspace(ctypes.byref(g6), abi.ALGO_AUTO) > 0

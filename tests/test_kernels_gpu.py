@@ -1,6 +1,8 @@
 """Per-kernel parity of libmcd_sm100 (through the C-ABI) against plain PyTorch fp32 ops on the same
 bf16-rounded inputs.  Tolerances: bf16 outputs |err| <= 1e-2 * max|ref| (2^-8 rounding + accumulation
 order), fp32 reductions 2e-3 relative, integer outputs bit-exact."""
+import ctypes
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -40,6 +42,17 @@ CONV_SHAPES = [
     (1, 33, 45, 3, 16, 7, 1, 1, 3),     # RGB-only first conv, ragged tiles (row-packed path)
     (2, 24, 40, 16, 16, 3, 1, 1, 1),
     (1, 37, 50, 16, 32, 3, 2, 1, 1),    # row-packed stride 2, odd sizes
+    (1, 20, 24, 16, 64, 3, 1, 1, 1),    # row-packed stride 1 (more than 32 output channels)
+    (1, 9, 300, 6, 16, 7, 1, 1, 3),     # row-convolution path: several ragged 128-pixel tiles per image row
+    (2, 7, 200, 16, 16, 3, 1, 1, 1),
+    (1, 8, 130, 8, 32, 3, 1, 1, 1),
+    (1, 6, 129, 12, 24, 5, 1, 1, 2),
+]
+
+STREAMK_SHAPES = [
+    (8, 60, 80, 256, 256, 3, 1, 2, 2),  # 300 pixel tiles on 148 SMs
+    (8, 60, 80, 128, 128, 3, 1, 1, 1),  # 300 tiles on 2 x 148 CTA slots
+    (5, 60, 80, 512, 512, 3, 1, 4, 4),  # two channel tiles per pixel tile, 376 tiles
 ]
 
 
@@ -106,6 +119,91 @@ def test_conv_dgrad_wgrad(cuda_dev, shape, algo_name):
     assert rel_err(ops.to_nchw_f32(dx, cin), dx_ref) < 1e-2
     assert rel_err(dw, dw_ref) < 5e-3
     assert rel_err(db, dy.sum((0, 2, 3))) < 5e-3
+
+
+DGRAD_BN_SHAPES = [
+    (2, 20, 24, 64, 64, 3, 1, 1, 1),     # tcgen05 stride 1
+    (1, 12, 16, 256, 512, 3, 1, 4, 4),   # two channel tiles of the dx problem
+    (2, 7, 200, 16, 16, 3, 1, 1, 1),     # row-convolution path
+    (2, 30, 40, 32, 64, 3, 2, 1, 1),     # stride 2: four parity-class problems share the sums
+    (2, 30, 40, 32, 64, 1, 2, 1, 0),     # stride 2 1x1: empty parity classes -> un-fused pass
+]
+
+
+@pytest.mark.parametrize("algo_name", ["direct", "umma"])
+@pytest.mark.parametrize("shape", DGRAD_BN_SHAPES)
+def test_conv_dgrad_relu_bn_epilogue(cuda_dev, shape, algo_name):
+    """dgrad with the fused backward of the producing BatchNorm+ReLU unit: dx = (x > 0) * (dgrad + add) and the
+    raw sums {sum dx, sum dx * bn_y}; and bn_bwd(raw_sums=...) == the two-pass BatchNorm backward."""
+    abi, ops = _ops()
+    algo = abi.ALGO_DIRECT if algo_name == "direct" else abi.ALGO_UMMA
+    n, h, w, cin, cout, k, stride, dil, pad = shape
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    bn_y = bf16_round(torch.randn(n, cin, h, w, generator=gen) * 1.5 + 0.3).to(cuda_dev)
+    gamma = torch.linspace(0.5, 1.5, cin, device=cuda_dev)
+    beta = torch.linspace(-0.3, 0.3, cin, device=cuda_dev)
+    mean, var = bn_y.mean((0, 2, 3)), bn_y.var((0, 2, 3), unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    xhat = (bn_y - mean[None, :, None, None]) * rstd[None, :, None, None]
+    x = bf16_round(torch.relu(xhat * gamma[None, :, None, None] + beta[None, :, None, None]))
+    _, wt = _conv_case(cuda_dev, shape, seed=1)
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wt, None, stride, pad, dil)
+    dy = bf16_round(torch.randn(ref.shape, generator=gen)).to(cuda_dev)
+    add = bf16_round(torch.randn(x.shape, generator=gen)).to(cuda_dev)
+    (dx_ref,) = torch.autograd.grad(ref, xr, dy)
+    g_ref = (dx_ref + add) * (x > 0)
+    xn, dyn, addn, yn = ops.to_nhwc(x), ops.to_nhwc(dy), ops.to_nhwc(add), ops.to_nhwc(bn_y)
+    g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
+    dx, sums = ops.conv_dgrad(dyn, ops.pack_weight_for(wt, g, 1, algo), g, algo=algo, add=addn, relu_src=xn,
+                              bn_y=yn)
+    torch.cuda.synchronize()
+    gq = ops.to_nchw_f32(dx, cin)
+    assert rel_err(gq, g_ref) < 1e-2
+    assert float((gq[x <= 0]).abs().max()) == 0.0
+    s = sums.view(2, cin)
+    assert rel_err(s[0], g_ref.sum((0, 2, 3))) < 5e-3
+    assert rel_err(s[1], (g_ref * bn_y).sum((0, 2, 3))) < 5e-3
+    # BatchNorm backward from the raw sums vs. the two-pass form on the same (already masked) gradient
+    aff = torch.stack([mean, rstd]).contiguous()
+    two = ops.bn_bwd(dx, xn, yn, gamma, aff, True, True)
+    one = ops.bn_bwd(dx, None, yn, gamma, aff, True, True, raw_sums=sums)
+    torch.cuda.synchronize()
+    assert rel_err(one[0].float(), two[0].float()) < 1e-2
+    assert rel_err(one[1], two[1]) < 2e-3 and rel_err(one[2], two[2]) < 2e-3
+
+
+@pytest.mark.parametrize("shape", STREAMK_SHAPES)
+def test_conv_streamk_schedule(cuda_dev, shape):
+    """opt-in stream-K schedule (fp32 partial-tile exchange between neighbouring CTAs) == tile-per-CTA schedule."""
+    abi, ops = _ops()
+    n, h, w, cin, cout, k, stride, dil, pad = shape
+    x, wt = _conv_case(cuda_dev, shape, seed=5)
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    xn = ops.to_nhwc(x)
+    g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
+    dyn = ops.to_nhwc(bf16_round(torch.randn(n, cout, g.Ho, g.Wo, generator=gen)).to(cuda_dev))
+    yn = ops.to_nhwc(bf16_round(torch.randn(n, cin, h, w, generator=gen)).to(cuda_dev))
+    wf, wd = ops.pack_weight_for(wt, g, 0, abi.ALGO_UMMA), ops.pack_weight_for(wt, g, 1, abi.ALGO_UMMA)
+    nf = ctypes.c_int(0)
+    assert abi.lib().mcd_conv2d_streamk_workspace(ctypes.byref(g), 0, abi.OUT_NHWC_BF16, abi.ALGO_UMMA,
+                                                   ctypes.byref(nf)) > 0 and nf.value > 0
+    res = {}
+    try:
+        for sk in (False, True):
+            ops.set_streamk(sk)
+            y, st = ops.conv_fprop(xn, wf, None, g, want_stats=True, algo=abi.ALGO_UMMA)
+            dx, sums = ops.conv_dgrad(dyn, wd, g, algo=abi.ALGO_UMMA, add=xn, relu_src=xn, bn_y=yn)
+            torch.cuda.synchronize()
+            res[sk] = (y.float(), st, dx.float(), sums)
+    finally:
+        ops.set_streamk(False)
+    ref = F.conv2d(x, wt, None, stride, pad, dil)
+    assert rel_err(res[True][0], ref) < 1e-2
+    assert rel_err(res[True][0], res[False][0]) < 4e-3          # same bf16 outputs up to fp32 summation order
+    assert rel_err(res[True][1], res[False][1]) < 1e-3
+    assert rel_err(res[True][2], res[False][2]) < 4e-3
+    assert rel_err(res[True][3], res[False][3]) < 2e-3
 
 
 def test_layout_roundtrip(cuda_dev):
