@@ -13,6 +13,7 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_plan.h"
 #include "umma_ptx.cuh"
@@ -102,27 +103,42 @@ __device__ __forceinline__ SegIter make_seg_iter(const FpropArgs& a, int total_t
   return it;
 }
 
-template <int BN>
+// CTA pairs walk pair tiles cluster by cluster
+__device__ __forceinline__ SegIter make_pair_iter(int total_pair_tiles, int kblocks) {
+  SegIter it;
+  it.kblocks = kblocks; it.stride = gridDim.x / 2; it.sk = 0;
+  it.head_tile = it.tail_tile = -1; it.head_kb1 = it.tail_kb0 = 0;
+  it.tile = 0; it.kb0 = 0; it.kb1 = 0;
+  it.u = blockIdx.x / 2; it.u_end = total_pair_tiles;
+  return it;
+}
+
+// PAIR: two CTAs of a cluster (one TPC) run ONE 256-pixel x 256-channel tcgen05.mma.cta_group::2 tile: each CTA
+// stages its own 128 pixels (A) and HALF of the weight tile (B), so a k-block costs 32 KB of TMA writes + 32 KB of
+// operand reads per SM instead of 48 + 48 - the single-CTA 128x256 tile is shared-memory-bandwidth bound
+// (96 KB per 512 MMA cycles at 128 B/clk ~ 68 % of the tensor peak, which is what ncu shows).
+template <int BN, bool PAIR = false>
 struct FpropCfg {
   static constexpr int A_BYTES = 128 * 128;          // 128 pixels x 64 ch bf16
-  static constexpr int B_BYTES = BN * 128;           // BN rows x 64 ch bf16
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;   // rows x 64 ch bf16
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static constexpr int STAGES = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 4)));
   static constexpr int STAT_ROWS = 1024;             // BatchNorm partial sums staged in smem up to this many channels
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                     2 * STAT_ROWS * 4;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;              // double-buffered (power of two, <= 512)
-  static constexpr int MIN_CTAS = BN <= 128 ? 2 : 1;          // two CTAs per SM: their epilogues / pipelines overlap
+  static constexpr int MIN_CTAS = BN <= 32 ? 2 : 1;           // thin tiles: two CTAs per SM
 };
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
 // registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
-template <int BN>
-__global__ void __launch_bounds__(kThreads, FpropCfg<BN>::MIN_CTAS)
+template <int BN, bool PAIR>
+__global__ void __launch_bounds__(kThreads, FpropCfg<BN, PAIR>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
-  using Cfg = FpropCfg<BN>;
+  using Cfg = FpropCfg<BN, PAIR>;
+  static_assert(!PAIR || BN == 256, "CTA pairs run the 256-channel tile only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -137,7 +153,9 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   const bool stat_sm = a.stats != nullptr && a.rows <= Cfg::STAT_ROWS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = a.tiles_m * a.tiles_n;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;    // PAIR: rank 0 = leader (issues the MMAs, owns full_bar)
+  // PAIR: "tiles" are pairs of pixel tiles; CTA `rank` owns pixel tile 2 * (tile / tiles_n) + rank
+  const int total_tiles = PAIR ? ((a.tiles_m + 1) / 2) * a.tiles_n : a.tiles_m * a.tiles_n;
   if (stat_sm)
     for (int i = threadIdx.x; i < 2 * a.rows; i += kThreads) sstat[i] = 0.f;
 
@@ -145,12 +163,15 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 8 : 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -159,13 +180,13 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      SegIter it = make_seg_iter(a, total_tiles, kblocks);
+      SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
       while (it.next()) {
-        int mt = it.tile / a.tiles_n;
+        int mt = PAIR ? 2 * (it.tile / a.tiles_n) + (int)rank : it.tile / a.tiles_n;
         const int n0 = (it.tile % a.tiles_n) * BN;
         const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
         const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
-        const int n_img = mt;
+        const int n_img = mt;                      // PAIR, odd tile count: n_img == N -> TMA zero fill
         const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
         int t = it.kb0 / a.kchunks, kc = it.kb0 % a.kchunks;
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
@@ -174,6 +195,16 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if (PAIR) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_4d_pair(sa, amap, fb, kc * 64, tw0 + tap.mdw, th0 + tap.mdh, n_img);
+            tma_load_2d_pair(sb, &maps.b, fb, tap.wk * a.kc_pad + kc * 64, n0 + (int)rank * (BN / 2));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            if (++kc == a.kchunks) { kc = 0; ++t; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (a.packed) {
             // TW columns x TH rows, column-major in the tile: one {64 elements, TH rows} window box per column
@@ -190,11 +221,11 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = instr_desc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc = instr_desc_bf16(PAIR ? 256 : 128, BN, 0, 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    SegIter it = make_seg_iter(a, total_tiles, kblocks);
-    while (it.next()) {
+    SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
+    while ((!PAIR || rank == 0) && it.next()) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
@@ -206,12 +237,21 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t adesc = smem_desc_sw128(sa, 0, 1024);
           const uint64_t bdesc = smem_desc_sw128(sb, 0, 1024);
+          if (PAIR) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-channel chunk: +32 bytes each
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                      (kb != it.kb0 || k != 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (kb == it.kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                             (kb != it.kb0 || k != 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);          // frees the stage in BOTH CTAs
+            if (kb == it.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], 3);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 4 x UMMA_K(16) per 64-channel chunk: +32 bytes each
+              umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                        (kb != it.kb0 || k != 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == it.kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -224,11 +264,12 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     const int m = q * 32 + lane;
     const int ncover = a.planar ? a.rows : a.Cd_s;
     int acc = 0; uint32_t acc_phase = 0;
-    SegIter it = make_seg_iter(a, total_tiles, kblocks);
+    SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
     while (it.next()) {
       const bool sk_dump = it.kb0 > 0;             // stream-K: tail k-blocks of a tile another CTA owns
       const bool sk_merge = it.kb1 < kblocks;      // stream-K: this CTA owns the tile, CTA+1 did the tail
-      int mt = it.tile / a.tiles_n;
+      int mt = PAIR ? 2 * (it.tile / a.tiles_n) + (int)rank : it.tile / a.tiles_n;
+      const bool mt_valid = mt < a.tiles_m;
       const int n0 = (it.tile % a.tiles_n) * BN;
       const int tw_i = mt % a.tiles_w; mt /= a.tiles_w;
       const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
@@ -236,7 +277,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
       const int ht = a.packed ? th0 + m % a.TH : th0 + m / a.TW;
       const int wt = a.packed ? tw0 + m / a.TH : tw0 + m % a.TW;
-      const bool pvalid = ht < a.Ht && wt < a.Wt;
+      const bool pvalid = mt_valid && ht < a.Ht && wt < a.Wt;
       const int hd = ht * a.omul + a.oh0, wd = wt * a.omul + a.ow0;
       // epilogue extras (addend / ReLU mask source / BatchNorm input) of one 32-channel chunk: all loads of a chunk
       // are issued together, and those of the first chunk before waiting for the MMAs, so that their latency
@@ -393,17 +434,24 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         }
       }
       // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
+      // (PAIR: to the leader, whose MMAs write both CTAs' TMEM)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  if (stat_sm && blockIdx.x < total_tiles)
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer's smem / barriers stay valid until both are done
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (stat_sm && blockIdx.x < (PAIR ? 2 * total_tiles : total_tiles))
     for (int i = threadIdx.x; i < 2 * a.rows; i += kThreads) atomicAdd(a.stats + i, sstat[i]);
 }
 
@@ -876,13 +924,49 @@ static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, 
   using Cfg = FpropCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("fprop smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
     attr_set = true;
   }
-  conv_umma_fprop_kernel<BN><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  conv_umma_fprop_kernel<BN, false><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_fprop");
+}
+
+// CTA-pair variant (clusters of 2): grid = 2 * number of persistent pairs
+static int launch_fprop_pair(const UmmaMaps& maps, const FpropArgs& a, int pairs, cudaStream_t st) {
+  using Cfg = FpropCfg<256, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<256, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("fprop pair smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_fprop_kernel<256, true>, maps, a);
+  if (e != cudaSuccess) { set_error("conv_umma_fprop (CTA pairs): %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+  return check_launch("conv_umma_fprop_pair");
+}
+
+static bool g_pair_enabled = true;   // MCD_CTA_PAIRS=0 selects the single-CTA 128x256 tiles (A/B measurements)
+static bool pair_enabled() {
+  static bool init = false;
+  if (!init) {
+    const char* e = getenv("MCD_CTA_PAIRS");
+    if (e && e[0] == '0') g_pair_enabled = false;
+    init = true;
+  }
+  return g_pair_enabled;
 }
 
 static void fprop_tiling(const TapProblem& p, int planar, int* TH, int* TW, int* tiles_m, int* tiles_n, int* BN) {
@@ -896,7 +980,7 @@ static void fprop_tiling(const TapProblem& p, int planar, int* TH, int* TW, int*
 
 // stream-K pays when the data-parallel schedule would leave the last wave of tiles mostly empty
 static bool streamk_plan(int total_tiles, int kblocks, int BN, int packed, int* G, int* units) {
-  const int slots = sm_count() * (BN <= 128 ? 2 : 1);
+  const int slots = sm_count() * (BN <= 32 ? 2 : 1);
   if (packed || total_tiles <= slots || kblocks < 2) return false;
   const int waves = (total_tiles + slots - 1) / slots;
   if ((double)total_tiles / ((double)waves * slots) > 0.92) return false;
@@ -952,9 +1036,15 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
 
   int BN, G;
   fprop_tiling(p, planar, &a.TH, &a.TW, &a.tiles_m, &a.tiles_n, &BN);
-  int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, BN);
+  const bool want_sk = ex.sk_partial && ex.sk_flags;
+  const bool pair = BN == 256 && !p.packed && a.tiles_m >= 2 && !want_sk && pair_enabled();
+  int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
   if (rc != MCD_OK) return rc;
-  const int slots = sm_count() * (BN <= 128 ? 2 : 1);   // persistent CTAs per SM (FpropCfg::MIN_CTAS)
+  if (pair) {
+    const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
+    return launch_fprop_pair(maps, a, min(pair_tiles, sm_count() / 2), st);
+  }
+  const int slots = sm_count() * (BN <= 32 ? 2 : 1);    // persistent CTAs per SM (FpropCfg::MIN_CTAS)
   G = min(a.tiles_m * a.tiles_n, slots);
   if (ex.sk_partial && ex.sk_flags) {
     int units = 0, g2 = 0;

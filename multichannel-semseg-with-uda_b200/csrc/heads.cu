@@ -109,48 +109,77 @@ deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
   }
 }
 
-// dw[c][kh][kw] += sum_{(n,ih) rows of this block} sum_ow x[n,c,ih,iw] * dout[n,c,8ih-4+kh,ow],  ow = 8iw-4+kw
-// A lane walks ow = lane, lane+32, ...: its (ow+4)&7 = kw0 is fixed, and every dout element feeds exactly two
-// bins, (iw0 = (ow+4)>>3, kw0) and (iw0-1, kw0+8).  Output rows are read coalesced, exactly once.
-// grid: (C*16 [c,kh], nsplit chunks of (n,ih) rows); block 256 = 8 warps, one row per warp-iteration; dw pre-zeroed.
+// dw[c][kh][kw] = sum_{n,ih,iw} x[n,c,ih,iw] * dout[n,c,8ih-4+kh,8iw-4+kw]
+// Every dout element (oh, ow) feeds exactly four bins: with ih0 = (oh+4)>>3, kh0 = (oh+4)&7 and iw0 = (ow+4)>>3,
+// kw0 = (ow+4)&7 these are (ih0|ih0-1, kh0|kh0+8) x (iw0|iw0-1, kw0|kw0+8).  A block owns one (c, kh0): all rows
+// with that residue, i.e. both kh bins, so dout is read exactly ONCE, as 16-byte chunks (8 ow = one iw step).
+// grid: (C*8 [c,kh0], nsplit chunks of (n,ih0) rows); block 256 = 8 warps, one row per warp-iteration; dw pre-zeroed.
 __global__ void __launch_bounds__(256)
 deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ x,
                          float* __restrict__ dw, int N, int C, int h, int wd) {
-  __shared__ float red[8][16];
-  const int c = blockIdx.x >> 4, kh = blockIdx.x & 15;
+  __shared__ float red[8][32];
+  const int c = blockIdx.x >> 3, kh0 = blockIdx.x & 7;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = h * 8, W = wd * 8;
-  const int rows = N * h;
+  const int rows = N * (h + 1);
   const int per = (rows + gridDim.y - 1) / gridDim.y;
   const int r_beg = blockIdx.y * per, r_end = min(r_beg + per, rows);
-  float acc0 = 0.f, acc1 = 0.f;
+  float accA[16], accB[16];      // A: (ih0, kh0) bins kw 0..15;  B: (ih0-1, kh0+8)
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { accA[k] = 0.f; accB[k] = 0.f; }
   for (int rr = r_beg + warp; rr < r_end; rr += 8) {
-    const int n = rr / h, ih = rr % h;
-    const int oh = 8 * ih - 4 + kh;
+    const int n = rr / (h + 1), ih0 = rr % (h + 1);
+    const int oh = 8 * ih0 + kh0 - 4;
     if (oh < 0 || oh >= H) continue;
     const __nv_bfloat16* dp = dout + (((int64_t)n * C + c) * H + oh) * W;
-    const float* xp = x + (((int64_t)n * C + c) * h + ih) * wd;
-    for (int ow = lane; ow < W; ow += 32) {
-      const float d = bf2f(dp[ow]);
-      const int iw0 = (ow + 4) >> 3;
-      if (iw0 < wd) acc0 = fmaf(xp[iw0], d, acc0);
-      if (iw0 >= 1) acc1 = fmaf(xp[iw0 - 1], d, acc1);
+    const float* xa = x + (((int64_t)n * C + c) * h + ih0) * wd;     // valid if ih0 < h
+    const float* xb = xa - wd;                                       // valid if ih0 >= 1
+    const bool va = ih0 < h, vb = ih0 >= 1;
+    for (int j0 = lane; j0 < wd; j0 += 96) {
+      uint4 raw[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {          // three independent 16-byte loads per lane in flight
+        const int j = j0 + 32 * q;
+        raw[q] = (j < wd) ? __ldg(reinterpret_cast<const uint4*>(dp + j * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int j = j0 + 32 * q;
+        if (j >= wd) continue;
+        float d[8];
+        unpack8(raw[q], d);
+        const float a0 = va ? xa[j] : 0.f, am = (va && j >= 1) ? xa[j - 1] : 0.f, ap = (va && j + 1 < wd) ? xa[j + 1] : 0.f;
+        const float b0 = vb ? xb[j] : 0.f, bm = (vb && j >= 1) ? xb[j - 1] : 0.f, bp = (vb && j + 1 < wd) ? xb[j + 1] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {      // ow = 8j+k: iw0 = j, kw0 = k+4
+          accA[k + 4] = fmaf(a0, d[k], accA[k + 4]);  accA[k + 12] = fmaf(am, d[k], accA[k + 12]);
+          accB[k + 4] = fmaf(b0, d[k], accB[k + 4]);  accB[k + 12] = fmaf(bm, d[k], accB[k + 12]);
+        }
+#pragma unroll
+        for (int k = 4; k < 8; ++k) {      // ow = 8j+k: iw0 = j+1, kw0 = k-4
+          accA[k - 4] = fmaf(ap, d[k], accA[k - 4]);  accA[k + 4] = fmaf(a0, d[k], accA[k + 4]);
+          accB[k - 4] = fmaf(bp, d[k], accB[k - 4]);  accB[k + 4] = fmaf(b0, d[k], accB[k + 4]);
+        }
+      }
     }
   }
-  // lanes l, l+8, l+16, l+24 share kw0 = (l+4)&7
-  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 8);  acc1 += __shfl_xor_sync(0xffffffffu, acc1, 8);
-  acc0 += __shfl_xor_sync(0xffffffffu, acc0, 16); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 16);
-  if (lane < 8) {
-    const int kw0 = (lane + 4) & 7;
-    red[warp][kw0] = acc0;
-    red[warp][kw0 + 8] = acc1;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float va_ = accA[k], vb_ = accB[k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      va_ += __shfl_xor_sync(0xffffffffu, va_, o);
+      vb_ += __shfl_xor_sync(0xffffffffu, vb_, o);
+    }
+    if (lane == 0) { red[warp][k] = va_; red[warp][16 + k] = vb_; }
   }
   __syncthreads();
-  if (threadIdx.x < 16) {
-    float s = 0.f;
+  if (threadIdx.x < 32) {
+    float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-    atomicAdd(dw + c * 256 + kh * 16 + threadIdx.x, s);
+    for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x];
+    const int kh = threadIdx.x < 16 ? kh0 : kh0 + 8, kw = threadIdx.x & 15;
+    atomicAdd(dw + c * 256 + kh * 16 + kw, sum);
   }
 }
 
@@ -271,8 +300,8 @@ int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* 
   if (dw) {
     cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 256, (cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("deconv dw memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    int nsplit = min(N * h, 32);
-    dim3 grid((unsigned)(C * 16), (unsigned)nsplit);
+    int nsplit = min(N * (h + 1), 32);
+    dim3 grid((unsigned)(C * 8), (unsigned)nsplit);
     deconv16s8_bwd_dw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, x, dw,
                                                                       N, C, h, w_);
     return check_launch("deconv16s8_bwd_dw");

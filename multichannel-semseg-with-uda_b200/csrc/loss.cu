@@ -6,6 +6,7 @@
 //   tester argmax + calc_entropy                      adapt_tester.py:104-124, util.py:44-48
 // One thread owns two horizontally adjacent pixels (4-byte bf16x2 loads, 128 B per warp and channel
 // plane); channel loops re-read the logits from L1/L2, so DRAM sees each logit once per kernel.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace mcd {
@@ -176,6 +177,115 @@ diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
   }
 }
 
+// ---- register-resident variants (C <= kRegC): a thread loads all channels of its pixel pair ONCE (C independent
+// 4-byte loads in flight per tensor), then max / sum-exp / loss / gradients come from registers: one pass over the
+// logits with no dependent re-reads.  Used for the MCD heads (C = 41); wider heads take the multi-pass kernels.
+constexpr int kRegC = 48;
+constexpr uint32_t kNegInfPair = 0xFF80FF80u;   // two bf16 -inf: padding channels vanish in max and sum-exp
+
+__device__ __forceinline__ float lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float hi_f(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ void load_pair(const __nv_bfloat16* base, int C, int64_t HW, uint32_t (&r)[kRegC]) {
+#pragma unroll
+  for (int c = 0; c < kRegC; ++c)
+    r[c] = (c < C) ? __ldg(reinterpret_cast<const unsigned int*>(base + c * HW)) : kNegInfPair;
+}
+__device__ __forceinline__ void reg_softmax_stats(const uint32_t (&r)[kRegC], float2* mx, float2* se) {
+  float2 m = make_float2(-INFINITY, -INFINITY);
+#pragma unroll
+  for (int c = 0; c < kRegC; ++c) { m.x = fmaxf(m.x, lo_f(r[c])); m.y = fmaxf(m.y, hi_f(r[c])); }
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < kRegC; ++c) { s.x += __expf(lo_f(r[c]) - m.x); s.y += __expf(hi_f(r[c]) - m.y); }
+  *mx = m; *se = s;
+}
+
+// in place: r[c] <- half2(exp(v_lo - m.x), exp(v_hi - m.y)); returns the two sums.  One MUFU per logit - the
+// probabilities are then re-used from registers (fp16 keeps 11 bits: 5e-4 relative, below the bf16 gradients'
+// own rounding and averaged out in the loss sums) instead of being recomputed in every later pass.
+__device__ __forceinline__ float2 reg_exp_inplace(uint32_t (&r)[kRegC], float2 m) {
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < kRegC; ++c) {
+    const float e0 = __expf(lo_f(r[c]) - m.x), e1 = __expf(hi_f(r[c]) - m.y);
+    s.x += e0; s.y += e1;
+    const __half2 h = __floats2half2_rn(e0, e1);
+    r[c] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return s;
+}
+__device__ __forceinline__ float2 reg_max(const uint32_t (&r)[kRegC]) {
+  float2 m = make_float2(-INFINITY, -INFINITY);
+#pragma unroll
+  for (int c = 0; c < kRegC; ++c) { m.x = fmaxf(m.x, lo_f(r[c])); m.y = fmaxf(m.y, hi_f(r[c])); }
+  return m;
+}
+__device__ __forceinline__ float2 h2f(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+
+__global__ void __launch_bounds__(128, 3)
+ce2d_fwd_reg_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+                    const float* __restrict__ weight, int64_t ignore_index, float* __restrict__ acc, int C,
+                    int64_t HW, int64_t npairs) {
+  __shared__ float red[32];
+  float lsum = 0.f, wsum = 0.f, bad = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const __nv_bfloat16* base = logits + n * C * HW + hw;
+    uint32_t r[kRegC];
+    load_pair(base, C, HW, r);
+    LabelInfo l0 = read_label(target, pix, weight, ignore_index, C);
+    LabelInfo l1 = read_label(target, pix + 1, weight, ignore_index, C);
+    float2 m, s;
+    reg_softmax_stats(r, &m, &s);
+    float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRegC; ++c) {
+      x0 = (c == l0.y) ? lo_f(r[c]) : x0;
+      x1 = (c == l1.y) ? hi_f(r[c]) : x1;
+    }
+    if (l0.y >= 0) { lsum += l0.w * (m.x + __logf(s.x) - x0); wsum += l0.w; }
+    if (l1.y >= 0) { lsum += l1.w * (m.y + __logf(s.y) - x1); wsum += l1.w; }
+    bad += (l0.bad ? 1.f : 0.f) + (l1.bad ? 1.f : 0.f);
+  }
+  float r0 = block_sum(lsum, red), r1 = block_sum(wsum, red), r2 = block_sum(bad, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc + 0, r0); atomicAdd(acc + 1, r1);
+    if (r2 != 0.f) atomicAdd(acc + 2, r2);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+diff2d_fwd_reg_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                      float* __restrict__ acc, float4* __restrict__ stats, int C, int64_t HW, int64_t npairs) {
+  __shared__ float red[32];
+  float lsum = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    uint32_t ra[kRegC], rb[kRegC];
+    load_pair(a + n * C * HW + hw, C, HW, ra);
+    load_pair(b + n * C * HW + hw, C, HW, rb);
+    const float2 ma = reg_max(ra), mb = reg_max(rb);
+    const float2 sa = reg_exp_inplace(ra, ma), sb = reg_exp_inplace(rb, mb);
+    const float ia0 = 1.f / sa.x, ia1 = 1.f / sa.y, ib0 = 1.f / sb.x, ib1 = 1.f / sb.y;
+    if (stats) {
+      stats[pix] = make_float4(ma.x, ia0, mb.x, ib0);
+      stats[pix + 1] = make_float4(ma.y, ia1, mb.y, ib1);
+    }
+#pragma unroll
+    for (int c = 0; c < kRegC; ++c) {
+      const float2 ea = h2f(ra[c]), eb = h2f(rb[c]);
+      lsum += fabsf(ea.x * ia0 - eb.x * ib0) + fabsf(ea.y * ia1 - eb.y * ib1);
+    }
+  }
+  float r = block_sum(lsum, red);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
 __global__ void __launch_bounds__(256)
 mse_fwd_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target,
                float* __restrict__ acc, int64_t numel) {
@@ -310,6 +420,9 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
 static inline int grid_for(int64_t items) {
   return (int)max64(1, min64((items + 255) / 256, 148 * 16));
 }
+static inline int grid_reg(int64_t items) {   // 128-thread blocks, 3 per SM, a few waves
+  return (int)max64(1, min64((items + 127) / 128, 148 * 3 * 8));
+}
 
 }  // namespace mcd
 
@@ -328,8 +441,12 @@ int mcd_ce2d_fwd(const void* logits, const int64_t* target, const float* weight,
   MCD_REQUIRE(logits && target && acc, "ce2d_fwd: null pointer");
   MCD_CHECK_PLANAR("ce2d_fwd");
   int64_t npairs = (int64_t)N * H * W / 2;
-  ce2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, C, (int64_t)H * W, npairs);
+  if (C <= kRegC)
+    ce2d_fwd_reg_kernel<<<grid_reg(npairs), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, C, (int64_t)H * W, npairs);
+  else
+    ce2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, C, (int64_t)H * W, npairs);
   return check_launch("ce2d_fwd");
 }
 
@@ -341,8 +458,8 @@ int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
   MCD_CHECK_PLANAR("ce2d_bwd");
   int64_t npairs = (int64_t)N * H * W / 2;
   ce2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, gscale, (__nv_bfloat16*)dlogits,
-      C, (int64_t)H * W, npairs);
+        (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, gscale, (__nv_bfloat16*)dlogits,
+        C, (int64_t)H * W, npairs);
   return check_launch("ce2d_bwd");
 }
 
@@ -352,8 +469,12 @@ int mcd_diff2d_fwd(const void* a, const void* b, float* acc, float* stats, int N
   MCD_REQUIRE(a && b && acc, "diff2d_fwd: null pointer");
   MCD_CHECK_PLANAR("diff2d_fwd");
   int64_t npairs = (int64_t)N * H * W / 2;
-  diff2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, (float4*)stats, C, (int64_t)H * W, npairs);
+  if (C <= kRegC)
+    diff2d_fwd_reg_kernel<<<grid_reg(npairs), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, (float4*)stats, C, (int64_t)H * W, npairs);
+  else
+    diff2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, (float4*)stats, C, (int64_t)H * W, npairs);
   return check_launch("diff2d_fwd");
 }
 
@@ -365,8 +486,8 @@ int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, const floa
   int64_t npairs = (int64_t)N * H * W / 2;
   float inv = (float)(1.0 / ((double)N * C * H * W));
   diff2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (const float4*)stats, (__nv_bfloat16*)da,
-      (__nv_bfloat16*)db, inv, C, (int64_t)H * W, npairs);
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (const float4*)stats, (__nv_bfloat16*)da,
+        (__nv_bfloat16*)db, inv, C, (int64_t)H * W, npairs);
   return check_launch("diff2d_bwd");
 }
 

@@ -200,9 +200,9 @@ def test_conv_streamk_schedule(cuda_dev, shape):
         ops.set_streamk(False)
     ref = F.conv2d(x, wt, None, stride, pad, dil)
     assert rel_err(res[True][0], ref) < 1e-2
-    assert rel_err(res[True][0], res[False][0]) < 4e-3          # same bf16 outputs up to fp32 summation order
+    assert rel_err(res[True][0], res[False][0]) < 1e-2          # same up to fp32 summation order (1 bf16 ulp)
     assert rel_err(res[True][1], res[False][1]) < 1e-3
-    assert rel_err(res[True][2], res[False][2]) < 4e-3
+    assert rel_err(res[True][2], res[False][2]) < 1e-2
     assert rel_err(res[True][3], res[False][3]) < 2e-3
 
 
