@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 10
+#define MCD_ABI_VERSION 11
 
 enum {
   MCD_OK = 0,
@@ -103,6 +103,15 @@ int mcd_pack_weight_rowconv(const float* w_oihw, void* dst, int Cout, int Cin, i
  * once by mcd_pack_weight / mcd_pack_weight_rows (their zero padding is kept). */
 int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per_item, int device,
                            void* stream);
+/* Fused optimizer step of a whole model: torch.optim.SGD semantics (solvers' optimizer_g.step(), reference
+ * models/model_util.py:289-302: momentum, weight decay, dampening 0, no Nesterov) on every parameter plus the refresh
+ * of the packed bf16 shadows of the convolution weights, one launch.  items_dev: n_items x 16 int64 {param, grad,
+ * momentum_buf (0 = none; zero-initialised before the first step), dst_fprop, dst_dgrad (0 = absent / not a
+ * convolution weight), Cout, Cin, R, S, kind_fprop, kind_dgrad, Cs_fprop, Cs_dgrad, numel, 0, 0};
+ * hyper_dev: device fp32 {lr, momentum, weight_decay}, read when the kernel RUNS (CUDA-graph replays follow
+ * adjust_learning_rate()). */
+int mcd_sgd_pack_multi(const int64_t* items_dev, int n_items, const float* hyper_dev, int blocks_per_item,
+                       int device, void* stream);
 /* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows(), 2 = mcd_pack_weight_rowconv() for (geometry, pass, algo);
  * pass: 0 = fprop, 1 = dgrad. */
 int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);

@@ -182,6 +182,116 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
   }
 }
 
+// ---- fused optimizer step: SGD (momentum, weight decay) on every parameter of a model AND the refresh of the packed
+// bf16 shadows of its convolution weights, in ONE launch (torch.optim.SGD.step() is ~60 multi-tensor launches and the
+// re-pack read all weights a second time).
+// item (16 x int64): p, g, buf (0 = no momentum), dst_fprop, dst_dgrad (0 = absent), Cout, Cin, R, S, kind_f, kind_d,
+// cs_f, cs_d, numel, 0, 0.  hyper (device, fp32): lr, momentum, weight_decay - read at run time, so a captured CUDA
+// graph follows adjust_learning_rate().   d = g + wd*p ; buf = momentum*buf + d ; p -= lr*buf   (torch.optim.SGD with
+// dampening 0; buf starts as zeros, which reproduces torch's first-step "buf = d").
+__device__ __forceinline__ float sgd_update(float* p, const float* g, float* buf, int64_t i, float lr, float mom,
+                                            float wd) {
+  const float d = fmaf(wd, p[i], g[i]);
+  float b = d;
+  if (buf) { b = fmaf(mom, buf[i], d); buf[i] = b; }
+  const float w = p[i] - lr * b;
+  p[i] = w;
+  return w;
+}
+
+__global__ void __launch_bounds__(256)
+sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict__ hyper) {
+  __shared__ float tile[32][32 * PK_T_MAX + 1];
+  const int64_t* it = items + (int64_t)blockIdx.x * 16;
+  float* w = reinterpret_cast<float*>(it[0]);
+  const float* g = reinterpret_cast<const float*>(it[1]);
+  float* buf = reinterpret_cast<float*>(it[2]);
+  __nv_bfloat16* dst_f = reinterpret_cast<__nv_bfloat16*>(it[3]);
+  __nv_bfloat16* dst_d = reinterpret_cast<__nv_bfloat16*>(it[4]);
+  const int Cout = (int)it[5], Cin = (int)it[6], R = (int)it[7], S = (int)it[8];
+  const int kind_f = (int)it[9], kind_d = (int)it[10], cs_f = (int)it[11], cs_d = (int)it[12];
+  const int64_t numel = it[13];
+  const float lr = hyper[0], mom = hyper[1], wd = hyper[2];
+  const int T = R * S;
+  const bool any_pack = dst_f || dst_d;
+  if (!any_pack) {                       // BatchNorm affine parameters, biases, ...: element-wise by all blocks
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.y * blockDim.x)
+      sgd_update(w, g, buf, i, lr, mom, wd);
+    return;
+  }
+  const bool tiled = T <= PK_T_MAX && (!dst_f || kind_f == 0) && (!dst_d || kind_d == 0);
+  if (tiled) {
+    // one 32(co) x 32(ci) x T tile per iteration: update while loading, then both packs from shared memory
+    const int tiles_ci = (Cin + 31) / 32, tiles_co = (Cout + 31) / 32;
+    const int kpf = (Cin + 63) / 64 * 64, kpd = (Cout + 63) / 64 * 64;
+    for (int tl = blockIdx.y; tl < tiles_ci * tiles_co; tl += gridDim.y) {
+      const int co0 = (tl / tiles_ci) * 32, ci0 = (tl % tiles_ci) * 32;
+      const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {
+        const int co_l = idx / (nci * T), rem = idx % (nci * T);
+        if (co_l < nco) tile[co_l][rem] = sgd_update(w, g, buf, ((int64_t)(co0 + co_l) * Cin + ci0) * T + rem, lr, mom, wd);
+      }
+      __syncthreads();
+      if (dst_f) {
+        for (int idx = threadIdx.x; idx < nco * T * 32; idx += 256) {
+          const int ci_l = idx & 31, t = (idx >> 5) % T, co_l = idx / (32 * T);
+          if (ci_l < nci)
+            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bf(tile[co_l][ci_l * T + t]);
+        }
+      }
+      if (dst_d) {
+        for (int idx = threadIdx.x; idx < nci * T * 32; idx += 256) {
+          const int co_l = idx & 31, t = (idx >> 5) % T, ci_l = idx / (32 * T);
+          if (co_l < nco) {
+            const int tf = (R - 1 - t / S) * S + (S - 1 - t % S);
+            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bf(tile[co_l][ci_l * T + t]);
+          }
+        }
+      }
+    }
+    return;
+  }
+  // thin stem layers (row-packed / row-convolution packs) and large filters: tiny tensors, one block does it all
+  if (blockIdx.y != 0) return;
+  for (int64_t i = threadIdx.x; i < numel; i += blockDim.x) sgd_update(w, g, buf, i, lr, mom, wd);
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    __nv_bfloat16* dst = pass ? dst_d : dst_f;
+    const int kind = pass ? kind_d : kind_f, Cs = pass ? cs_d : cs_f;
+    if (!dst) continue;
+    const int rows = pass ? Cin : Cout;
+    if (kind == 0) {
+      const int kc_pad = ((pass ? Cout : Cin) + 63) / 64 * 64;
+      const int64_t total = (int64_t)rows * T * kc_pad;
+      for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const int kc = (int)(i % kc_pad), t = (int)((i / kc_pad) % T), row = (int)(i / ((int64_t)kc_pad * T));
+        float v = 0.f;
+        if (!pass) { if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S]; }
+        else if (kc < Cout) v = w[(((int64_t)kc * Cin + row) * R + (R - 1 - t / S)) * S + (S - 1 - t % S)];
+        dst[i] = f2bf(v);
+      }
+    } else if (kind == 2) {
+      const int HC = Cs / 8, SP = S <= 4 ? 4 : 8, NB = (rows + 15) / 16 * 16;
+      const int64_t total = (int64_t)R * HC * SP * NB * 8;
+      for (int64_t i = threadIdx.x; i < total; i += blockDim.x)
+        dst[i] = f2bf(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, pass));
+    } else {
+      const int64_t total = (int64_t)rows * R * 64;
+      for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const int k = (int)(i % 64), r = (int)((i / 64) % R), row = (int)(i / (64 * (int64_t)R));
+        const int s = k / Cs, c = k % Cs;
+        float v = 0.f;
+        if (s < S) {
+          if (!pass) { if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s]; }
+          else if (c < Cout) v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
+        }
+        dst[i] = f2bf(v);
+      }
+    }
+  }
+}
+
 }  // namespace mcd
 
 using namespace mcd;
@@ -241,6 +351,16 @@ int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int 
   pack_weight_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
                                                                    R, S, Cs, mode, rows);
   return check_launch("pack_weight_rows");
+}
+
+int mcd_sgd_pack_multi(const int64_t* items_dev, int n_items, const float* hyper_dev, int blocks_per_item,
+                       int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(items_dev && hyper_dev && n_items > 0 && blocks_per_item > 0 && blocks_per_item <= 65535,
+              "sgd_pack_multi: bad arguments");
+  dim3 grid((unsigned)n_items, (unsigned)blocks_per_item);
+  sgd_pack_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(items_dev, hyper_dev);
+  return check_launch("sgd_pack_multi");
 }
 
 int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per_item, int device,

@@ -187,6 +187,93 @@ class MultiPacker:
             conv._packs[key] = ((w._version, w.data_ptr()), packed)
 
 
+class FusedSGD:
+    """`optimizer.step()` of a torch.optim.SGD (one parameter group, dampening 0, no Nesterov) as ONE launch of
+    mcd_sgd_pack_multi, which also refreshes the packed bf16 shadows of the convolution weights (replaces
+    optimizer.step() + MultiPacker.repack()).  Momentum buffers stay in `optimizer.state[p]["momentum_buffer"]`,
+    so optimizer.state_dict() / load_state_dict() keep working; lr / momentum / weight_decay are re-read from the
+    param group on every call and live in a small device tensor (CUDA-graph replays follow changes made through
+    `refresh_hyper()`)."""
+
+    @staticmethod
+    def supports(optimizer):
+        if type(optimizer) is not torch.optim.SGD or len(optimizer.param_groups) != 1:
+            return False
+        g = optimizer.param_groups[0]
+        return (g.get("dampening", 0) == 0 and not g.get("nesterov", False) and not g.get("maximize", False)
+                and all(p.is_cuda and p.dtype == F32 and p.is_contiguous() for p in g["params"]))
+
+    def __init__(self, optimizer, convs):
+        assert FusedSGD.supports(optimizer)
+        self.opt = optimizer
+        self.group = optimizer.param_groups[0]
+        self.params = list(self.group["params"])
+        self.dev = self.params[0].device
+        self.conv_of = {c.weight: c for c in convs}
+        self.hyper_host = torch.empty(3, dtype=F32).pin_memory()
+        self.hyper = torch.zeros(3, dtype=F32, device=self.dev)
+        self._hyper_vals = None
+        self._tables = {}
+        self.refresh_hyper()
+
+    def refresh_hyper(self):
+        vals = (float(self.group["lr"]), float(self.group["momentum"]), float(self.group["weight_decay"]))
+        if vals != self._hyper_vals:
+            self.hyper_host[0], self.hyper_host[1], self.hyper_host[2] = vals
+            self.hyper.copy_(self.hyper_host, non_blocking=True)
+            self._hyper_vals = vals
+
+    def _rows(self, active):
+        rows = []
+        mom = self._hyper_vals[1] != 0.0
+        for p in active:
+            buf = 0
+            if mom:
+                st = self.opt.state[p]
+                if st.get("momentum_buffer") is None:
+                    st["momentum_buffer"] = torch.zeros_like(p)
+                buf = st["momentum_buffer"].data_ptr()
+            conv = self.conv_of.get(p)
+            slot = {0: (0, 0, 0), 1: (0, 0, 0)}
+            co = ci = r = s = 0
+            if conv is not None:
+                co, ci, r, s = p.shape
+                for key, (tag, packed) in conv._packs.items():
+                    mode, kind, cs = key
+                    slot[mode] = (packed.data_ptr(), kind, cs)
+            rows.append([p.data_ptr(), p.grad.data_ptr(), buf, slot[0][0], slot[1][0], co, ci, r, s,
+                         slot[0][1], slot[1][1], slot[0][2], slot[1][2], p.numel(), 0, 0])
+        return rows
+
+    def step(self):
+        self.refresh_hyper()
+        active = [p for p in self.params if p.grad is not None]
+        if not active:
+            return
+        for p in active:
+            g = p.grad
+            assert g.dtype == F32 and g.is_contiguous() and g.device == p.device
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in active) + \
+            tuple(pk.data_ptr() for p in active if p in self.conv_of for _, pk in self.conv_of[p]._packs.values())
+        hit = self._tables.get(key)
+        if hit is None:
+            host = torch.tensor(self._rows(active), dtype=torch.int64).pin_memory()
+            dev_t = torch.empty(host.shape, dtype=torch.int64, device=self.dev)
+            dev_t.copy_(host, non_blocking=True)
+            if len(self._tables) > 64:
+                self._tables.clear()
+            hit = self._tables[key] = (host, dev_t, len(active))
+        abi.check(abi.lib().mcd_sgd_pack_multi(_p(hit[1]), hit[2], _p(self.hyper), 64, self.dev.index,
+                                               ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
+                  "sgd_pack_multi")
+        for p in active:      # the packs were rewritten from the updated weights: keep their tags current
+            conv = self.conv_of.get(p)
+            if conv is not None:
+                tag = (p._version, p.data_ptr())
+                for k, (_, packed) in list(conv._packs.items()):
+                    conv._packs[k] = (tag, packed)
+
+
 def pack_key(g, mode, algo=None):
     algo = _algo if algo is None else algo
     kind = int(abi.lib().mcd_conv2d_pack_kind(ctypes.byref(g), mode, algo))

@@ -25,7 +25,7 @@ class MCDStep:
 
     def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
                  num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
-                 bucket_mb=25, reuse_target_forward=True):
+                 bucket_mb=25, reuse_target_forward=True, fused_sgd=True):
         from models.model_util import get_optimizer
         self.mfnet = len(models) == 4
         self.gens = list(models[:-2])
@@ -47,6 +47,8 @@ class MCDStep:
         self.sync_f = parallel.GradSync(f_params, process_group, bucket_mb)
         self._arena = None
         self._packer_g = None
+        self._fused_g = None
+        self.fused_sgd = fused_sgd     # optimizer_g.step() + weight re-pack as one kernel (plain momentum SGD only)
         self.world = self.sync_g.world
         if self.world > 1 and hasattr(criterion, "set_process_group"):
             criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
@@ -60,7 +62,7 @@ class MCDStep:
         # world > 1: the NCCL bucket all-reduces (side stream, forked / joined with stream waits) and the 4-float
         # normaliser all-reduce are captured as graph nodes too; every rank replays the same sequence.
         dev = src_imgs.device
-        if self._packer_g is None:
+        if self._packer_g is None and not self._fused_g:
             warmup = max(warmup, 1)        # lazily built host tables (weight re-pack list) need one eager iteration
         self._static = (src_imgs.clone(), src_lbls.clone(), tgt_imgs.clone())
         side = torch.cuda.Stream(dev)
@@ -118,10 +120,20 @@ class MCDStep:
             ops.set_arena(prev_arena)
 
     def _step_g(self):
-        """optimizer_g.step() + ONE multi-tensor kernel that refreshes all packed bf16 weight shadows of G."""
+        """optimizer_g.step() and the refresh of all packed bf16 weight shadows of G: ONE fused kernel when the
+        optimizer is plain momentum SGD (ops.FusedSGD), else optimizer.step() + one multi-tensor re-pack."""
+        from .nn import Conv2d
+        if self._fused_g is None:
+            convs = [m for g in self.gens for m in g.modules() if isinstance(m, Conv2d) and m._packs]
+            if self.fused_sgd and ops_mod().FusedSGD.supports(self.optimizer_g):
+                self._fused_g = ops_mod().FusedSGD(self.optimizer_g, convs)
+            else:
+                self._fused_g = False
+        if self._fused_g:
+            self._fused_g.step()
+            return
         self.optimizer_g.step()
         if self._packer_g is None:
-            from .nn import Conv2d
             convs = [m for g in self.gens for m in g.modules() if isinstance(m, Conv2d) and m._packs]
             self._packer_g = ops_mod().MultiPacker(convs)
         self._packer_g.repack()

@@ -82,3 +82,51 @@ def test_state_dict_round_trip_and_fix_bn(cuda_dev):
     assert torch.equal(before, g.base[3][0].bn1.running_mean)
     assert int(g.base[3][0].bn1.num_batches_tracked) == 0
     assert g.base[3][0].bn1.weight.grad is not None
+
+
+def test_fused_sgd_matches_torch_sgd_and_refreshes_packs():
+    """ops.FusedSGD (one mcd_sgd_pack_multi launch) == torch.optim.SGD.step() on fp32 master weights, momentum
+    buffers and BatchNorm parameters, and the packed bf16 shadows equal a fresh pack of the updated weights."""
+    import copy
+    from mcd_b200 import ops
+    from models import drn
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = drn.drn_d_22(pretrained=False, num_classes=0, input_ch=6)
+    net = torch.nn.Sequential(*[s for s in net.stages()][:4]).to(dev).train()     # stem + first residual stage
+    ref = copy.deepcopy(net)
+    x = torch.randn(2, 6, 32, 48, device=dev)
+    net(x).float().sum().backward()                      # creates the packs (fprop + dgrad) and real gradients
+    convs = [m for m in net.modules() if isinstance(m, ops_conv()) and m._packs]
+    assert convs
+    kw = dict(lr=0.05, momentum=0.9, weight_decay=1e-3)
+    opt = torch.optim.SGD(net.parameters(), **kw)
+    opt_ref = torch.optim.SGD(ref.parameters(), **kw)
+    assert ops.FusedSGD.supports(opt)
+    fused = ops.FusedSGD(opt, convs)
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    for it in range(3):
+        for p, q in zip(net.parameters(), ref.parameters()):
+            g = torch.randn(p.shape, generator=gen).to(dev)
+            p.grad, q.grad = g.clone(), g.clone()
+        if it == 2:                                       # hyper-parameters are re-read on every call
+            opt.param_groups[0]["lr"] = opt_ref.param_groups[0]["lr"] = 0.01
+        fused.step()
+        opt_ref.step()
+    torch.cuda.synchronize()
+    for (k, p), q in zip(net.named_parameters(), ref.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), k
+        assert torch.allclose(opt.state[p]["momentum_buffer"], opt_ref.state[q]["momentum_buffer"], rtol=1e-5, atol=1e-6), k
+    for conv in convs:
+        for (mode, kind, cs), (tag, packed) in conv._packs.items():
+            g = next(iter(conv._geoms.values()))
+            fresh = ops.pack_weight_for(conv.weight, g, mode)
+            if fresh.shape == packed.shape:
+                assert torch.equal(fresh, packed), (mode, kind)
+
+
+def ops_conv():
+    from mcd_b200.nn import Conv2d
+    return Conv2d
