@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 11
+#define MCD_ABI_VERSION 12
 
 enum {
   MCD_OK = 0,
@@ -115,6 +115,13 @@ int mcd_sgd_pack_multi(const int64_t* items_dev, int n_items, const float* hyper
 /* 0 = mcd_pack_weight() layout, 1 = mcd_pack_weight_rows(), 2 = mcd_pack_weight_rowconv() for (geometry, pass, algo);
  * pass: 0 = fprop, 1 = dgrad. */
 int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
+
+/* Which kernel the library launches for (geometry, pass, layout, algo); pass: 0 = fprop, 1 = dgrad, 2 = wgrad.
+ * Returns 1000 * kind + tile width BN; kind: 0 = conv_umma_fprop_kernel<BN> (one CTA per 128-pixel tile),
+ * 1 = conv_umma_fprop_kernel<256, pair> (cta_group::2, 256 x 256 tile), 2 = row-packed thin-channel mode of kind 0,
+ * 3 = conv_umma_rowconv_kernel, 4 = conv_umma_wgrad_kernel<BN>, 5 = conv_umma_wgrad_rows_kernel,
+ * 9 = CUDA-core direct kernels; -1 = invalid geometry.  Used by bench.py to attribute measured time to kernels. */
+int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int algo);
 
 /* ---- convolution (nn.Conv2d: models/drn.py:21-23,126-131,171-205; dilated_fcn.py:226-232,632-658,821-823) */
 /* y = conv(x, w) (+ bias).  If `stats` != NULL (fp32 [2*Cout], caller-zeroed) the kernel also

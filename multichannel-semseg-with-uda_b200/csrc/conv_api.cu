@@ -16,6 +16,8 @@ size_t umma_wgrad_workspace(const mcd_conv_geom& g);
 size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags);
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                const mcd_conv_geom& g, int accumulate, cudaStream_t st);
+int umma_problem_tile(const TapProblem& p, int planar, int* pair);
+int umma_wgrad_tile(const mcd_conv_geom& g, int* rows);
 bool rowconv_fprop_ok(const mcd_conv_geom& g);
 bool rowconv_dgrad_ok(const mcd_conv_geom& g);
 int rowconv_pack(const float* w, void* dst, int Cout, int Cin, int R, int S, int Cs, int mode, cudaStream_t st);
@@ -145,6 +147,28 @@ int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo) {
   if (g->stride > 2) return 0;
   if (pass == 0 ? rowconv_fprop_ok(*g) : rowconv_dgrad_ok(*g)) return 2;
   return pass == 0 ? (packed_fprop_ok(*g) ? 1 : 0) : (packed_dgrad_ok(*g) ? 1 : 0);
+}
+
+int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int algo) {
+  if (!g || validate(g) != MCD_OK) return -1;
+  if (algo == MCD_ALGO_DIRECT || g->stride > 2) return 9000;
+  if (pass == 2) {
+    int rows = 0;
+    const int bn = umma_wgrad_tile(*g, &rows);
+    return (rows ? 5000 : 4000) + bn;
+  }
+  if (pass == 0 ? rowconv_fprop_ok(*g) : rowconv_dgrad_ok(*g)) return 3000 + 16;
+  TapProblem p[4];
+  int pair = 0;
+  if (pass == 0) {
+    plan_fprop(*g, p[0]);
+    if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p[0]);
+  } else {
+    plan_dgrad(*g, p);
+    if (packed_dgrad_ok(*g)) plan_dgrad_packed(*g, p[0]);
+  }
+  const int bn = umma_problem_tile(p[0], pass == 0 && y_layout == MCD_OUT_PLANAR_F32, &pair);
+  return (p[0].packed ? 2000 : (pair ? 1000 : 0)) + bn;
 }
 
 int mcd_pack_weight_rowconv(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs, int mode,

@@ -1061,6 +1061,23 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   return launch_fprop_bn<16>(maps, a, grid, st);
 }
 
+static int wgrad_bn(const mcd_conv_geom& g);
+static bool wgrad_rows_ok(const mcd_conv_geom& g);
+// which kernel launch_umma_problem() picks for a problem: tile width BN, *pair = CTA-pair (cta_group::2) variant
+int umma_problem_tile(const TapProblem& p, int planar, int* pair) {
+  int TH, TW, tiles_m, tiles_n, BN;
+  fprop_tiling(p, planar, &TH, &TW, &tiles_m, &tiles_n, &BN);
+  *pair = BN == 256 && !p.packed && tiles_m >= 2 && pair_enabled();
+  return BN;
+}
+
+// which kernel umma_wgrad() picks: tile width BN, *rows = all-filter-rows thin-channel kernel
+int umma_wgrad_tile(const mcd_conv_geom& g, int* rows) {
+  *rows = wgrad_rows_ok(g);
+  if (*rows) return 64;
+  return packed_fprop_ok(g) ? 64 : wgrad_bn(g);
+}
+
 // stream-K workspace of one problem: bytes of fp32 partial tiles and number of int flags (0 / 0: not used)
 size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags) {
   *n_flags = 0;

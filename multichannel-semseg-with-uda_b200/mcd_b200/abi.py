@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
@@ -44,6 +44,7 @@ _SIGNATURES = {
     "mcd_sgd_pack_multi": (c_int, [P, c_int, P, c_int, c_int, P]),
     "mcd_pack_weights_multi": (c_int, [P, c_int, c_int, c_int, P]),
     "mcd_conv2d_pack_kind": (c_int, [POINTER(ConvGeom), c_int, c_int]),
+    "mcd_conv2d_kernel_id": (c_int, [POINTER(ConvGeom), c_int, c_int, c_int]),
     "mcd_conv2d_fprop": (c_int, [P, P, P, P, c_int, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
     "mcd_conv2d_streamk_workspace": (c_size_t, [POINTER(ConvGeom), c_int, c_int, c_int, POINTER(c_int)]),
     "mcd_conv2d_dgrad": (c_int, [P, P, P, P, P, P, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),

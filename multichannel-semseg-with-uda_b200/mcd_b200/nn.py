@@ -132,7 +132,8 @@ class _ConvFn(torch.autograd.Function):
             # accumulation kernel runs and the main stream goes on with dgrad / BatchNorm backward while the
             # tensor-bound wgrad kernels trail behind.  MCDStep joins the side stream before optimizer.step().
             main = torch.cuda.current_stream(dy.device)
-            side = _side_stream(dy.device)
+            # set_overlap_wgrad(False): everything on the main stream (per-kernel timing in bench.py)
+            side = _side_stream(dy.device) if _overlap_wgrad else main
             ready = torch.cuda.Event()
             ready.record(main)                    # dy (and everything before it) is complete here
             w, b = mod.weight, mod.bias

@@ -616,10 +616,26 @@ class ConvProfiler:
         return fam
 
 
-def _profiled(name, g, fn):
+_KIND_NAMES = {0: "conv_umma_fprop_kernel<%d>", 1: "conv_umma_fprop_kernel<%d,pair>",
+               2: "conv_umma_fprop_kernel<%d> (row-packed)", 3: "conv_umma_rowconv_kernel<%d>",
+               4: "conv_umma_wgrad_kernel<%d> + wgrad_reduce", 5: "conv_umma_wgrad_rows_kernel<%d> + reduce",
+               9: "conv_direct_kernel"}
+
+
+def conv_kernel_name(g, pass_, planar=False, algo=None):
+    """the kernel the library launches for this convolution (mcd_conv2d_kernel_id)."""
+    kid = abi.lib().mcd_conv2d_kernel_id(ctypes.byref(g), pass_, abi.OUT_PLANAR_F32 if planar else abi.OUT_NHWC_BF16,
+                                         abi.ALGO_AUTO if algo is None else algo)
+    kind, bn = divmod(kid, 1000)
+    name = _KIND_NAMES.get(kind, "conv?")
+    return name % bn if "%d" in name else name
+
+
+def _profiled(pass_, g, fn, planar=False, algo=None):
     prof = ConvProfiler.active
     if prof is None:
         return fn()
+    name = conv_kernel_name(g, pass_, planar, algo) + (" [fprop]", " [dgrad]", "")[pass_]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = fn()
@@ -633,15 +649,13 @@ _conv_fprop_raw, _conv_dgrad_raw, _conv_wgrad_raw = conv_fprop, conv_dgrad, conv
 
 
 def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):  # noqa: F811
-    return _profiled("conv_fprop_kernel (forward)", g,
-                     lambda: _conv_fprop_raw(x, w_packed, bias, g, planar, want_stats, algo))
+    return _profiled(0, g, lambda: _conv_fprop_raw(x, w_packed, bias, g, planar, want_stats, algo), planar, algo)
 
 
 def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=None):  # noqa: F811
-    return _profiled("conv_fprop_kernel (dgrad)", g,
-                     lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add, relu_src, bn_y))
+    return _profiled(1, g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add, relu_src, bn_y), False, algo)
 
 
 def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):  # noqa: F811
-    return _profiled("conv_wgrad_kernel (+split-K reduce)", g,
-                     lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo, out_dw, out_db, accumulate))
+    return _profiled(2, g, lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo, out_dw, out_db, accumulate), False,
+                     algo)
