@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 12
+#define MCD_ABI_VERSION 13
 
 enum {
   MCD_OK = 0,
@@ -107,7 +107,8 @@ int mcd_pack_weights_multi(const int64_t* items_dev, int n_items, int blocks_per
  * models/model_util.py:289-302: momentum, weight decay, dampening 0, no Nesterov) on every parameter plus the refresh
  * of the packed bf16 shadows of the convolution weights, one launch.  items_dev: n_items x 16 int64 {param, grad,
  * momentum_buf (0 = none; zero-initialised before the first step), dst_fprop, dst_dgrad (0 = absent / not a
- * convolution weight), Cout, Cin, R, S, kind_fprop, kind_dgrad, Cs_fprop, Cs_dgrad, numel, 0, 0};
+ * convolution weight), Cout, Cin, R, S, kind_fprop, kind_dgrad, Cs_fprop, Cs_dgrad, numel, grad_partials (0 = none; else the
+ * workspace of mcd_conv2d_wgrad(dw_oihw = NULL), `grad` is then ignored), ksplit | CoutP << 16 | CinP << 32};
  * hyper_dev: device fp32 {lr, momentum, weight_decay}, read when the kernel RUNS (CUDA-graph replays follow
  * adjust_learning_rate()). */
 int mcd_sgd_pack_multi(const int64_t* items_dev, int n_items, const float* hyper_dev, int blocks_per_item,
@@ -150,8 +151,13 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
                      int* sk_flags, const mcd_conv_geom* g, int algo, int device, void* stream);
 /* dw (fp32 OIHW) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).  accumulate = 0 overwrites,
  * 1 adds to the existing contents (gradient accumulation straight into param.grad / all-reduce buckets).
- * workspace: mcd_conv2d_wgrad_workspace() bytes. */
+ * workspace: mcd_conv2d_wgrad_workspace() bytes.
+ * dw_oihw == NULL ("partials only"): the tcgen05 kernel leaves its split partial sums in `workspace` as fp32
+ * [ksplit][R*S][CoutP][CinP] (mcd_conv2d_wgrad_partials() gives the four numbers; returns 0 for layers that have
+ * no such form) and the reduction + OIHW transpose is done by the consumer - mcd_sgd_pack_multi() reads that form
+ * directly, which removes one reduction kernel per layer and one write + read of every weight gradient. */
 size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo);
+int mcd_conv2d_wgrad_partials(const mcd_conv_geom* g, int algo, int32_t* layout4);
 int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, float* dbias,
                      void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int accumulate,
                      int algo, int device, void* stream);

@@ -18,6 +18,7 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
                const mcd_conv_geom& g, int accumulate, cudaStream_t st);
 int umma_problem_tile(const TapProblem& p, int planar, int* pair);
 int umma_wgrad_tile(const mcd_conv_geom& g, int* rows);
+bool umma_wgrad_partial_layout(const mcd_conv_geom& g, int* out4);
 bool rowconv_fprop_ok(const mcd_conv_geom& g);
 bool rowconv_dgrad_ok(const mcd_conv_geom& g);
 int rowconv_pack(const float* w, void* dst, int Cout, int Cin, int R, int S, int Cs, int mode, cudaStream_t st);
@@ -205,17 +206,26 @@ size_t mcd_conv2d_wgrad_workspace(const mcd_conv_geom* g, int algo) {
   return umma_wgrad_workspace(*g);
 }
 
+int mcd_conv2d_wgrad_partials(const mcd_conv_geom* g, int algo, int32_t* layout4) {
+  if (!g || !layout4 || algo == MCD_ALGO_DIRECT || validate(g) != MCD_OK) return 0;
+  int out[4];
+  if (!umma_wgrad_partial_layout(*g, out)) return 0;
+  for (int i = 0; i < 4; ++i) layout4[i] = out[i];
+  return 1;
+}
+
 int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, float* dbias,
                      void* workspace, size_t workspace_bytes, const mcd_conv_geom* g, int accumulate,
                      int algo, int device, void* stream) {
   MCD_ENTER(device);
   int rc = validate(g);
   if (rc != MCD_OK) return rc;
-  MCD_REQUIRE(x_nhwc && dy_nhwc && dw_oihw, "conv wgrad: null pointer");
+  MCD_REQUIRE(x_nhwc && dy_nhwc, "conv wgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   bool supported = (g->stride == 1 || g->stride == 2);
   bool umma = use_umma(algo, supported, &rc);
   if (rc != MCD_OK) return rc;
+  MCD_REQUIRE(dw_oihw || umma, "conv wgrad: dw_oihw == NULL (partial sums only) needs the tcgen05 path");
   rc = umma ? umma_wgrad(x_nhwc, dy_nhwc, dw_oihw, workspace, workspace_bytes, *g, accumulate, st)
             : wgrad_direct(x_nhwc, dy_nhwc, dw_oihw, *g, accumulate, st);
   if (rc != MCD_OK) return rc;

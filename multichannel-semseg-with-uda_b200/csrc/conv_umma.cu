@@ -117,27 +117,30 @@ __device__ __forceinline__ SegIter make_pair_iter(int total_pair_tiles, int kblo
 // stages its own 128 pixels (A) and HALF of the weight tile (B), so a k-block costs 32 KB of TMA writes + 32 KB of
 // operand reads per SM instead of 48 + 48 - the single-CTA 128x256 tile is shared-memory-bandwidth bound
 // (96 KB per 512 MMA cycles at 128 B/clk ~ 68 % of the tensor peak, which is what ncu shows).
-template <int BN, bool PAIR = false>
+// OCC = 2: half the pipeline stages so that two persistent CTAs share an SM (thin layers, BN 64 / 128): their
+// per-tile chains (TMA -> MMA -> commit -> epilogue) are latency-bound, a second CTA fills the bubbles.
+template <int BN, bool PAIR = false, int OCC = 1>
 struct FpropCfg {
   static constexpr int A_BYTES = 128 * 128;          // 128 pixels x 64 ch bf16
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;   // rows x 64 ch bf16
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 4)));
+  static constexpr int STAGES = PAIR ? 6 : (OCC == 2 ? (BN == 128 ? 3 : 4)
+                                                     : ((BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 4))));
   static constexpr int STAT_ROWS = 1024;             // BatchNorm partial sums staged in smem up to this many channels
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                     2 * STAT_ROWS * 4;
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;              // double-buffered (power of two, <= 512)
-  static constexpr int MIN_CTAS = BN <= 32 ? 2 : 1;           // thin tiles: two CTAs per SM
+  static constexpr int MIN_CTAS = (BN <= 32 || OCC == 2) ? 2 : 1;   // thin tiles: two CTAs per SM
 };
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
 // registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
-template <int BN, bool PAIR>
-__global__ void __launch_bounds__(kThreads, FpropCfg<BN, PAIR>::MIN_CTAS)
+template <int BN, bool PAIR, int OCC = 1>
+__global__ void __launch_bounds__(kThreads, FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
-  using Cfg = FpropCfg<BN, PAIR>;
+  using Cfg = FpropCfg<BN, PAIR, OCC>;
   static_assert(!PAIR || BN == 256, "CTA pairs run the 256-channel tile only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -468,13 +471,13 @@ struct WgradArgs {
   Tap taps[kMaxTaps];
 };
 
-template <int BN>
+template <int BN, int OCC = 1>
 struct WgradCfg {
   static constexpr int KPIX = 64;
   static constexpr int A_BYTES = 2 * KPIX * 128;             // two 64-co atoms
   static constexpr int B_BYTES = (BN / 64) * KPIX * 128;     // BN/64 ci atoms
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = OCC == 2 ? (BN == 128 ? 3 : 4) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;   // double-buffered accumulator
 };
@@ -482,10 +485,10 @@ struct WgradCfg {
 // Persistent: work item = (pixel-range split, tap, co tile of 128, ci tile of BN); CTAs walk items round-robin,
 // the smem ring runs across items and the TMEM accumulator is double-buffered so that the fp32 partial-tile store
 // of item i overlaps the MMAs of item i+1.  Consecutive items share the pixel range (dY / X tiles stay in L2).
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int OCC = 1>
+__global__ void __launch_bounds__(kThreads, OCC)
 conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ WgradArgs a) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, OCC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -775,18 +778,25 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ks
 }
 
 // packed: ws[split][r][co][s*Cs + c]  ->  dw[co][c][r][s]
+// 8 lanes share one output element (the splits k = lane, lane + 8, ...) and combine with shuffles: the stem layers
+// have few weights (4.7 K) but up to 148 splits, one thread per element would serialise 148 dependent loads.
 __global__ void wgrad_reduce_packed_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ksplit,
                                            int R, int S, int Cs, int CoutP, int Cout, int Cin, int accumulate) {
-  int64_t total = (int64_t)Cout * Cin * R * S;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t total = (int64_t)Cout * Cin * R * S;
+  const int sub = threadIdx.x & 7;
+  for (int64_t i0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; i0 < ((total + 31) & ~int64_t(31));
+       i0 += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int64_t i = i0 < total ? i0 : total - 1;
     int sx = (int)(i % S);
     int r = (int)((i / S) % R);
     int c = (int)((i / ((int64_t)S * R)) % Cin);
     int co = (int)(i / ((int64_t)S * R * Cin));
     float acc = 0.f;
-    for (int k = 0; k < ksplit; ++k) acc += ws[(((int64_t)k * R + r) * CoutP + co) * 64 + sx * Cs + c];
-    dw[i] = accumulate ? dw[i] + acc : acc;
+    for (int k = sub; k < ksplit; k += 8) acc += ws[(((int64_t)k * R + r) * CoutP + co) * 64 + sx * Cs + c];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0 && i0 < total) dw[i] = accumulate ? dw[i] + acc : acc;
   }
 }
 
@@ -919,18 +929,25 @@ bool umma_problem_supported(const TapProblem& p) {
   return true;
 }
 
-template <int BN>
+template <int BN, int OCC = 1>
 static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
-  using Cfg = FpropCfg<BN>;
+  using Cfg = FpropCfg<BN, false, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, false>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, false, OCC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("fprop smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
     attr_set = true;
   }
-  conv_umma_fprop_kernel<BN, false><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  conv_umma_fprop_kernel<BN, false, OCC><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_fprop");
+}
+
+// MCD_THIN_OCC2=0 keeps one persistent CTA per SM for the 64- / 128-channel tiles (A/B measurements)
+static bool thin_occ2() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCD_THIN_OCC2"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 // CTA-pair variant (clusters of 2): grid = 2 * number of persistent pairs
@@ -1044,7 +1061,8 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
     const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
     return launch_fprop_pair(maps, a, min(pair_tiles, sm_count() / 2), st);
   }
-  const int slots = sm_count() * (BN <= 32 ? 2 : 1);    // persistent CTAs per SM (FpropCfg::MIN_CTAS)
+  const bool occ2 = (BN == 64 || BN == 128) && thin_occ2() && !want_sk;
+  const int slots = sm_count() * ((BN <= 32 || occ2) ? 2 : 1);    // persistent CTAs per SM (FpropCfg::MIN_CTAS)
   G = min(a.tiles_m * a.tiles_n, slots);
   if (ex.sk_partial && ex.sk_flags) {
     int units = 0, g2 = 0;
@@ -1055,14 +1073,16 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   }
   dim3 grid((unsigned)G);
   if (BN == 256) return launch_fprop_bn<256>(maps, a, grid, st);
-  if (BN == 128) return launch_fprop_bn<128>(maps, a, grid, st);
-  if (BN == 64) return launch_fprop_bn<64>(maps, a, grid, st);
+  if (BN == 128) return occ2 ? launch_fprop_bn<128, 2>(maps, a, grid, st) : launch_fprop_bn<128>(maps, a, grid, st);
+  if (BN == 64) return occ2 ? launch_fprop_bn<64, 2>(maps, a, grid, st) : launch_fprop_bn<64>(maps, a, grid, st);
   if (BN == 32) return launch_fprop_bn<32>(maps, a, grid, st);
   return launch_fprop_bn<16>(maps, a, grid, st);
 }
 
 static int wgrad_bn(const mcd_conv_geom& g);
 static bool wgrad_rows_ok(const mcd_conv_geom& g);
+static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
+                        int* ntiles, int* ksplit);
 // which kernel launch_umma_problem() picks for a problem: tile width BN, *pair = CTA-pair (cta_group::2) variant
 int umma_problem_tile(const TapProblem& p, int planar, int* pair) {
   int TH, TW, tiles_m, tiles_n, BN;
@@ -1076,6 +1096,16 @@ int umma_wgrad_tile(const mcd_conv_geom& g, int* rows) {
   *rows = wgrad_rows_ok(g);
   if (*rows) return 64;
   return packed_fprop_ok(g) ? 64 : wgrad_bn(g);
+}
+
+// layout of the split partial sums the generic wgrad kernel leaves in its workspace: fp32 [ksplit][T][CoutP][CinP];
+// false for the layers that use other kernels (stem)
+bool umma_wgrad_partial_layout(const mcd_conv_geom& g, int* out4) {
+  if ((g.stride != 1 && g.stride != 2) || g.R * g.S > kMaxTaps || wgrad_rows_ok(g) || packed_fprop_ok(g)) return false;
+  int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
+  wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
+  out4[0] = ksplit; out4[1] = g.R * g.S; out4[2] = CoutP; out4[3] = CinP;
+  return true;
 }
 
 // stream-K workspace of one problem: bytes of fp32 partial tiles and number of int flags (0 / 0: not used)
@@ -1101,7 +1131,8 @@ static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, 
   else pick_tile(g.Ho, g.Wo, 64, TH, TW);
   *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
   int base = (*CoutP / 128) * (*CinP / *BN) * g.R * (packed ? 1 : g.S);
-  int ks = sm_count() / base;               // one work item per persistent CTA; fewer splits = less partial traffic
+  const int slots = sm_count() * ((*BN <= 128 && thin_occ2()) ? 2 : 1);
+  int ks = slots / base;                    // one work item per persistent CTA; fewer splits = less partial traffic
   ks = max(1, min(ks, *ntiles));
   ks = min(ks, 64);
   *ksplit = ks;
@@ -1158,7 +1189,7 @@ static int umma_wgrad_rows(const void* x, const void* dy, float* dw, void* ws, s
   rc = check_launch("conv_umma_wgrad_rows");
   if (rc != MCD_OK) return rc;
   int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
-  int rgrid = (int)min64((total + 255) / 256, 148 * 8);
+  int rgrid = (int)min64((total * 8 + 255) / 256, 148 * 8);
   wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, nsplit, g.R, g.S, g.Cin_s, 64, g.Cout, g.Cin,
                                                     accumulate);
   return check_launch("wgrad_reduce");
@@ -1175,17 +1206,17 @@ size_t umma_wgrad_workspace(const mcd_conv_geom& g) {
   return sizeof(float) * (size_t)ksplit * g.R * (packed_fprop_ok(g) ? 1 : g.S) * CoutP * CinP;
 }
 
-template <int BN>
+template <int BN, int OCC = 1>
 static int launch_wgrad_bn(const UmmaMaps& maps, const WgradArgs& a, dim3 grid, cudaStream_t st) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_kernel<BN, OCC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("wgrad smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
     attr_set = true;
   }
-  conv_umma_wgrad_kernel<BN><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  conv_umma_wgrad_kernel<BN, OCC><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_wgrad");
 }
 
@@ -1193,7 +1224,10 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
                const mcd_conv_geom& g, int accumulate, cudaStream_t st) {
   if (g.stride != 1 && g.stride != 2) { set_error("umma wgrad: stride %d unsupported", g.stride); return MCD_E_INVALID; }
   if (g.R * g.S > kMaxTaps) { set_error("umma wgrad: too many taps"); return MCD_E_INVALID; }
-  if (wgrad_rows_ok(g)) return umma_wgrad_rows(x, dy, dw, ws, ws_bytes, g, accumulate, st);
+  if (wgrad_rows_ok(g)) {
+    if (!dw) { set_error("umma wgrad: partial-sum output is not available for the stem layers"); return MCD_E_INVALID; }
+    return umma_wgrad_rows(x, dy, dw, ws, ws_bytes, g, accumulate, st);
+  }
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
   const bool packed = packed_fprop_ok(g);
@@ -1237,14 +1271,19 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   if (rc != MCD_OK) return rc;
 
   const int total_items = (CoutP / 128) * (CinP / BN) * a.T * ksplit;
-  dim3 grid((unsigned)min(total_items, sm_count()));
+  const bool occ2 = BN <= 128 && thin_occ2();
+  dim3 grid((unsigned)min(total_items, sm_count() * (occ2 ? 2 : 1)));
   if (BN == 256) rc = launch_wgrad_bn<256>(maps, a, grid, st);
-  else if (BN == 128) rc = launch_wgrad_bn<128>(maps, a, grid, st);
-  else rc = launch_wgrad_bn<64>(maps, a, grid, st);
+  else if (BN == 128) rc = occ2 ? launch_wgrad_bn<128, 2>(maps, a, grid, st) : launch_wgrad_bn<128>(maps, a, grid, st);
+  else rc = occ2 ? launch_wgrad_bn<64, 2>(maps, a, grid, st) : launch_wgrad_bn<64>(maps, a, grid, st);
   if (rc != MCD_OK) return rc;
 
+  if (!dw) {          // partials only: the caller reduces [ksplit][T][CoutP][CinP] itself (mcd_sgd_pack_multi)
+    if (packed) { set_error("umma wgrad: partial-sum output is not available for row-packed layers"); return MCD_E_INVALID; }
+    return MCD_OK;
+  }
   int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
-  int rgrid = (int)min64((total + 255) / 256, 148 * 8);
+  int rgrid = (int)min64((total * 8 + 255) / 256, 148 * 8);
   if (packed)
     wgrad_reduce_packed_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, ksplit, g.R, g.S, g.Cin_s, CoutP, g.Cout, g.Cin,
                                                       accumulate);

@@ -189,6 +189,16 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
 // cs_f, cs_d, numel, 0, 0.  hyper (device, fp32): lr, momentum, weight_decay - read at run time, so a captured CUDA
 // graph follows adjust_learning_rate().   d = g + wd*p ; buf = momentum*buf + d ; p -= lr*buf   (torch.optim.SGD with
 // dampening 0; buf starts as zeros, which reproduces torch's first-step "buf = d").
+__device__ __forceinline__ float sgd_update_g(float* p, float gi, float* buf, int64_t i, float lr, float mom,
+                                              float wd) {
+  const float d = fmaf(wd, p[i], gi);
+  float b = d;
+  if (buf) { b = fmaf(mom, buf[i], d); buf[i] = b; }
+  const float w = p[i] - lr * b;
+  p[i] = w;
+  return w;
+}
+
 __device__ __forceinline__ float sgd_update(float* p, const float* g, float* buf, int64_t i, float lr, float mom,
                                             float wd) {
   const float d = fmaf(wd, p[i], g[i]);
@@ -211,6 +221,9 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
   const int Cout = (int)it[5], Cin = (int)it[6], R = (int)it[7], S = (int)it[8];
   const int kind_f = (int)it[9], kind_d = (int)it[10], cs_f = (int)it[11], cs_d = (int)it[12];
   const int64_t numel = it[13];
+  // gradient still in split form (mcd_conv2d_wgrad with dw_oihw == NULL): fp32 [ksplit][T][CoutP][CinP] partial sums
+  const float* gws = reinterpret_cast<const float*>(it[14]);
+  const int ksplit = (int)(it[15] & 0xFFFF), CoutP = (int)((it[15] >> 16) & 0xFFFF), CinP = (int)((it[15] >> 32) & 0xFFFF);
   const float lr = hyper[0], mom = hyper[1], wd = hyper[2];
   const int T = R * S;
   const bool any_pack = dst_f || dst_d;
@@ -228,9 +241,29 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
       const int co0 = (tl / tiles_ci) * 32, ci0 = (tl % tiles_ci) * 32;
       const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
       __syncthreads();
-      for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {
-        const int co_l = idx / (nci * T), rem = idx % (nci * T);
-        if (co_l < nco) tile[co_l][rem] = sgd_update(w, g, buf, ((int64_t)(co0 + co_l) * Cin + ci0) * T + rem, lr, mom, wd);
+      if (gws) {
+        // reduce the split partial sums of this tile (coalesced along ci) into shared memory, OIHW order
+        const int64_t kstride = (int64_t)T * CoutP * CinP;
+        for (int idx = threadIdx.x; idx < T * 32 * 32; idx += 256) {
+          const int ci_l = idx & 31, co_l = (idx >> 5) & 31, t = idx >> 10;
+          if (ci_l < nci && co_l < nco) {
+            const float* q = gws + ((int64_t)t * CoutP + co0 + co_l) * CinP + ci0 + ci_l;
+            float acc = 0.f;
+            for (int k = 0; k < ksplit; ++k) acc += __ldcs(q + k * kstride);
+            tile[co_l][ci_l * T + t] = acc;
+          }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {
+          const int co_l = idx / (nci * T), rem = idx % (nci * T);
+          if (co_l < nco)
+            tile[co_l][rem] = sgd_update_g(w, tile[co_l][rem], buf, ((int64_t)(co0 + co_l) * Cin + ci0) * T + rem, lr, mom, wd);
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {
+          const int co_l = idx / (nci * T), rem = idx % (nci * T);
+          if (co_l < nco) tile[co_l][rem] = sgd_update(w, g, buf, ((int64_t)(co0 + co_l) * Cin + ci0) * T + rem, lr, mom, wd);
+        }
       }
       __syncthreads();
       if (dst_f) {

@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mcd_conv2d_streamk_workspace": (c_size_t, [POINTER(ConvGeom), c_int, c_int, c_int, POINTER(c_int)]),
     "mcd_conv2d_dgrad": (c_int, [P, P, P, P, P, P, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
     "mcd_conv2d_wgrad_workspace": (c_size_t, [POINTER(ConvGeom), c_int]),
+    "mcd_conv2d_wgrad_partials": (c_int, [POINTER(ConvGeom), c_int, POINTER(c_int32)]),
     "mcd_conv2d_wgrad": (c_int, [P, P, P, P, P, c_size_t, POINTER(ConvGeom), c_int, c_int, c_int, P]),
     "mcd_bn_stats": (c_int, [P, P, c_int64, c_int, c_int, c_int, P]),
     "mcd_bn_finalize": (c_int, [P, c_int64, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, c_int,

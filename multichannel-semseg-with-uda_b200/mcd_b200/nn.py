@@ -48,7 +48,8 @@ class DirectGrads:
     directly into param.grad on the side stream (see _ConvFn.backward) instead of travelling through autograd.
     `join()` makes the main stream wait for them and releases the operands that were kept alive."""
 
-    def __init__(self):
+    def __init__(self, defer=False):
+        self.defer = defer   # weight gradients may stay in split form for FusedSGD (MCDStep with fused_sgd)
         self.keep = []
         self.stash = {}      # data_ptr of a block input -> identity-shortcut gradient awaiting conv1's dgrad
         self.bnsums = {}     # data_ptr of a dgrad output -> (raw BatchNorm-backward sums, data_ptr of the BN input)
@@ -138,7 +139,12 @@ class _ConvFn(torch.autograd.Function):
             ready.record(main)                    # dy (and everything before it) is complete here
             w, b = mod.weight, mod.bias
             acc = getattr(w, "_mcd_written", False) and w.grad is not None
-            if w.grad is None:
+            defer = getattr(mod, "_mcd_defer", None) if _direct.defer else None
+            if defer is not None and defer[0] != g.key():
+                defer = None
+            if defer is not None and getattr(w, "_mcd_deferred", False):
+                raise RuntimeError("mcd_b200: a deferred weight gradient was produced twice before optimizer_g.step()")
+            if defer is None and w.grad is None:
                 w.grad = torch.empty_like(w)
             if want_db and b.grad is None:
                 b.grad = torch.empty_like(b)
@@ -155,8 +161,14 @@ class _ConvFn(torch.autograd.Function):
                 dx = add
             side.wait_event(ready)
             with torch.cuda.stream(side):
-                ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
-                               accumulate=acc)
+                if defer is not None:
+                    # split partial sums stay in the convolution's persistent workspace; FusedSGD reduces them
+                    ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_db=b.grad if want_db else None, accumulate=acc,
+                                   partials=defer[1])
+                    w._mcd_deferred = True
+                else:
+                    ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
+                                   accumulate=acc)
             w._mcd_written = True
             _direct.keep.append((x, dy))          # keep the operands alive until the side stream is joined
             for p in ((w, b) if want_db else (w,)):

@@ -203,7 +203,7 @@ class FusedSGD:
         return (g.get("dampening", 0) == 0 and not g.get("nesterov", False) and not g.get("maximize", False)
                 and all(p.is_cuda and p.dtype == F32 and p.is_contiguous() for p in g["params"]))
 
-    def __init__(self, optimizer, convs):
+    def __init__(self, optimizer, convs, defer_wgrad_reduce=False):
         assert FusedSGD.supports(optimizer)
         self.opt = optimizer
         self.group = optimizer.param_groups[0]
@@ -215,6 +215,26 @@ class FusedSGD:
         self._hyper_vals = None
         self._tables = {}
         self.refresh_hyper()
+        # deferred weight-gradient reduction: the tcgen05 wgrad kernel of these convolutions leaves its split
+        # partial sums in a persistent workspace (conv._mcd_defer) and this optimizer reads them directly - no
+        # wgrad_reduce kernel, no write + read of param.grad.  Only for convolutions with a single geometry whose
+        # packs use the standard layout (the tiled branch of sgd_pack_multi_kernel).
+        self.deferred = {}
+        if defer_wgrad_reduce:
+            for conv in convs:
+                w = conv.weight
+                if len(conv._geoms) != 1 or w.shape[2] * w.shape[3] > 9:
+                    continue
+                if any(key[1] != 0 for key in conv._packs):
+                    continue
+                g = next(iter(conv._geoms.values()))
+                lay = wgrad_partial_layout(g)
+                if lay is None:
+                    continue
+                nbytes = int(abi.lib().mcd_conv2d_wgrad_workspace(ctypes.byref(g), _algo))
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+                conv._mcd_defer = (g.key(), ws)
+                self.deferred[w] = (ws, lay)
 
     def refresh_hyper(self):
         vals = (float(self.group["lr"]), float(self.group["momentum"]), float(self.group["weight_decay"]))
@@ -241,19 +261,23 @@ class FusedSGD:
                 for key, (tag, packed) in conv._packs.items():
                     mode, kind, cs = key
                     slot[mode] = (packed.data_ptr(), kind, cs)
-            rows.append([p.data_ptr(), p.grad.data_ptr(), buf, slot[0][0], slot[1][0], co, ci, r, s,
-                         slot[0][1], slot[1][1], slot[0][2], slot[1][2], p.numel(), 0, 0])
+            gws = lay = 0
+            if getattr(p, "_mcd_deferred", False):
+                ws, (ks, _t, coutp, cinp) = self.deferred[p]
+                gws, lay = ws.data_ptr(), ks | (coutp << 16) | (cinp << 32)
+            rows.append([p.data_ptr(), p.grad.data_ptr() if p.grad is not None else 0, buf, slot[0][0], slot[1][0],
+                         co, ci, r, s, slot[0][1], slot[1][1], slot[0][2], slot[1][2], p.numel(), gws, lay])
         return rows
 
     def step(self):
         self.refresh_hyper()
-        active = [p for p in self.params if p.grad is not None]
+        active = [p for p in self.params if p.grad is not None or getattr(p, "_mcd_deferred", False)]
         if not active:
             return
         for p in active:
             g = p.grad
-            assert g.dtype == F32 and g.is_contiguous() and g.device == p.device
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in active) + \
+            assert getattr(p, "_mcd_deferred", False) or (g.dtype == F32 and g.is_contiguous() and g.device == p.device)
+        key = tuple((p.data_ptr(), -1 if getattr(p, "_mcd_deferred", False) else p.grad.data_ptr()) for p in active) + \
             tuple(pk.data_ptr() for p in active if p in self.conv_of for _, pk in self.conv_of[p]._packs.values())
         hit = self._tables.get(key)
         if hit is None:
@@ -267,6 +291,7 @@ class FusedSGD:
                                                ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
                   "sgd_pack_multi")
         for p in active:      # the packs were rewritten from the updated weights: keep their tags current
+            p._mcd_deferred = False
             conv = self.conv_of.get(p)
             if conv is not None:
                 tag = (p._version, p.data_ptr())
@@ -352,11 +377,29 @@ def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=N
     return dx if bn_y is None else (dx, sums)
 
 
-def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):
+def wgrad_partial_layout(g, algo=None):
+    """(ksplit, T, CoutP, CinP) of the split partial sums the tcgen05 wgrad kernel produces for geometry `g`, or
+    None when that layer has no such form (stem layers, CUDA-core path)."""
+    out = (ctypes.c_int32 * 4)()
+    ok = abi.lib().mcd_conv2d_wgrad_partials(ctypes.byref(g), _algo if algo is None else algo, out)
+    return tuple(int(v) for v in out) if ok else None
+
+
+def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False, partials=None):
     """dw (fp32 OIHW) and optionally dbias.  `out_dw` / `out_db` (e.g. param.grad or an all-reduce bucket view)
-    are written in place - overwritten, or added to when `accumulate`."""
+    are written in place - overwritten, or added to when `accumulate`.
+    partials: a persistent uint8 workspace tensor; the kernel then leaves the weight gradient there as split
+    partial sums (wgrad_partial_layout) for FusedSGD and no dw is produced (returns None, db)."""
     assert is_nhwc(x) and is_nhwc(dy)
     algo = _algo if algo is None else algo
+    if partials is not None:
+        db = None
+        if want_dbias:
+            db = out_db if out_db is not None else torch.empty(g.Cout, dtype=F32, device=x.device)
+        abi.check(abi.lib().mcd_conv2d_wgrad(_p(x), _p(dy), None, _p(db), _p(partials), partials.numel(),
+                                             ctypes.byref(g), int(accumulate), algo, _dev(x), _stream(x)),
+                  "conv2d_wgrad(partials)")
+        return None, db
     dw = out_dw if out_dw is not None else torch.empty((g.Cout, g.Cin, g.R, g.S), dtype=F32, device=x.device)
     db = None
     if want_dbias:
@@ -656,6 +699,7 @@ def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=N
     return _profiled(1, g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add, relu_src, bn_y), False, algo)
 
 
-def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False):  # noqa: F811
-    return _profiled(2, g, lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo, out_dw, out_db, accumulate), False,
-                     algo)
+def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False,  # noqa: F811
+               partials=None):
+    return _profiled(2, g, lambda: _conv_wgrad_raw(x, dy, g, want_dbias, algo, out_dw, out_db, accumulate, partials),
+                     False, algo)

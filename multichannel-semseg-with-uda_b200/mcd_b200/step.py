@@ -25,7 +25,7 @@ class MCDStep:
 
     def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
                  num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
-                 bucket_mb=25, reuse_target_forward=True, fused_sgd=True):
+                 bucket_mb=25, reuse_target_forward=True, fused_sgd=True, defer_wgrad_reduce=True):
         from models.model_util import get_optimizer
         self.mfnet = len(models) == 4
         self.gens = list(models[:-2])
@@ -49,6 +49,10 @@ class MCDStep:
         self._packer_g = None
         self._fused_g = None
         self.fused_sgd = fused_sgd     # optimizer_g.step() + weight re-pack as one kernel (plain momentum SGD only)
+        # single process + fused SGD: the split-K partial sums of the tcgen05 wgrad kernels are reduced by the
+        # optimizer kernel itself (ops.FusedSGD.deferred); with world > 1 the all-reduce needs real gradients
+        self.defer_reduce = (fused_sgd and defer_wgrad_reduce and self.sync_g.world == 1
+                             and not exact_reference_backward)
         self.world = self.sync_g.world
         if self.world > 1 and hasattr(criterion, "set_process_group"):
             criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
@@ -113,7 +117,7 @@ class MCDStep:
         from .nn import DirectGrads
         try:
             self._arena.begin()            # ONE memset for all BatchNorm-statistic / loss accumulators
-            with DirectGrads() as self._dg:
+            with DirectGrads(defer=self.defer_reduce) as self._dg:
                 self._dev = src_imgs.device
                 return self._iteration(crit, src_imgs, src_lbls, tgt_imgs)
         finally:
@@ -126,7 +130,7 @@ class MCDStep:
         if self._fused_g is None:
             convs = [m for g in self.gens for m in g.modules() if isinstance(m, Conv2d) and m._packs]
             if self.fused_sgd and ops_mod().FusedSGD.supports(self.optimizer_g):
-                self._fused_g = ops_mod().FusedSGD(self.optimizer_g, convs)
+                self._fused_g = ops_mod().FusedSGD(self.optimizer_g, convs, defer_wgrad_reduce=self.defer_reduce)
             else:
                 self._fused_g = False
         if self._fused_g:

@@ -1,0 +1,50 @@
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel -> profiles/*.csv
+
+    python scripts/ncu_launch_list.py gpurun_out/launches.csv profiles/r01b_launch_list_step_b16.csv "note"
+"""
+import collections
+import csv
+import re
+import sys
+
+src, out = sys.argv[1], sys.argv[2]
+note = sys.argv[3] if len(sys.argv) > 3 else ""
+lines = [ln for ln in open(src) if ln.startswith('"')]
+rows = list(csv.DictReader(lines))
+
+
+def short(n):
+    n = re.sub(r"^void ", "", n)
+    n = n.replace("mcd::", "")
+    m = re.match(r"(conv_umma_\w+)<(\d+)(?:, *(\(bool\))?([01]|true|false))?(?:, *(\d+))?>", n)
+    if m:
+        name = m.group(1) + "<" + m.group(2)
+        if m.group(4) in ("1", "true"):
+            name += ",pair"
+        if m.group(5) == "2":
+            name += ",occ2"
+        return name + ">"
+    return re.sub(r"\(.*$", "", n)[:70]
+
+
+agg = collections.OrderedDict()
+total = 0.0
+for r in rows:
+    if r["Metric Name"] != "gpu__time_duration.sum":
+        continue
+    us = float(r["Metric Value"].replace(",", "")) / (1e3 if r["Metric Unit"] == "ns" else 1.0)
+    k = short(r["Kernel Name"])
+    a = agg.setdefault(k, [0, 0.0])
+    a[0] += 1
+    a[1] += us
+    total += us
+n = sum(a[0] for a in agg.values())
+with open(out, "w") as f:
+    for ln in note.split("\\n"):
+        if ln:
+            f.write("# " + ln + "\n")
+    f.write("# total %.0f us over %d launches\n" % (total, n))
+    f.write("kernel,launches,total_us,share_pct,avg_us\n")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write("%s,%d,%.0f,%.2f,%.1f\n" % (k.replace(",", ";"), c, t, 100.0 * t / total, t / c))
+print("wrote", out, "total_us", round(total), "launches", n)

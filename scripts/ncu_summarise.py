@@ -31,16 +31,19 @@ def short_name(n):
     n = re.sub(r"^void ", "", n)
     n = re.sub(r"\(.*$", "", n)
     n = n.replace("mcd::", "")
-    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(true|false|\(bool\)[01])>", n)
+    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(true|false|\(bool\)[01]|[01])>", n)
     if m:
-        pair = m.group(2) in ("true", "(bool)1")
+        pair = m.group(2) in ("true", "(bool)1", "1")
         return "conv_umma_fprop_kernel<%s%s>" % (m.group(1), ",pair" if pair else "")
     return n
 
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # already exported on the GPU box: ncu -i rep --page raw --csv
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
