@@ -43,19 +43,33 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
   const int c0 = cv * 8;
   if (active) {
     const int64_t step = (int64_t)gridDim.x * rpi;
-    for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
-      const int64_t off = p * Cs + c0;
+    constexpr int U = 2;    // pixel rows per iteration, all loads first
+    for (int64_t p0 = (int64_t)blockIdx.x * rpi + pr; p0 < P; p0 += U * step) {
+      uint4 vyu[U], vdu[U], vzu[U], vru[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t pu = p0 + u * step;
+        vyu[u] = vdu[u] = vzu[u] = vru[u] = make_uint4(0, 0, 0, 0);   // a zero row adds nothing to any sum
+        if (pu < P) {
+          const int64_t off = pu * Cs + c0;
+          vyu[u] = *reinterpret_cast<const uint4*>(y + off);
+          if (MODE == 1) {
+            vdu[u] = *reinterpret_cast<const uint4*>(dz + off);
+            if (relu) vzu[u] = *reinterpret_cast<const uint4*>(z + off);
+            if (dual) vru[u] = *reinterpret_cast<const uint4*>(res + off);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
       float fy[8];
-      const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
+      const uint4 vy = vyu[u];
       if (MODE == 0) {
         unpack8(vy, fy);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a0[k] += fy[k]; a1[k] = fmaf(fy[k], fy[k], a1[k]); }
       } else {
-        const uint4 vd = *reinterpret_cast<const uint4*>(dz + off);
-        uint4 vz = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
-        if (relu) vz = *reinterpret_cast<const uint4*>(z + off);
-        if (dual) vr = *reinterpret_cast<const uint4*>(res + off);
+        const uint4 vd = vdu[u], vz = vzu[u], vr = vru[u];
         float fd[8], fz[8];
         unpack8(vy, fy); unpack8(vd, fd); unpack8(vz, fz);
         float g[8];
@@ -72,6 +86,7 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
           for (int k = 0; k < 8; ++k)
             a2[k] = fmaf(g[k], (fr[k] - co[2 * Cs + c0 + k]) * co[3 * Cs + c0 + k], a2[k]);
         }
+      }
       }
     }
 #pragma unroll
@@ -182,26 +197,45 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
   if (pr >= rpi) return;
   const int c0 = cv * 8;
   const int64_t step = (int64_t)gridDim.x * rpi;
-  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
-    const int64_t off = p * Cs + c0;
-    float f[8];
-    const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
-    uint4 vr = make_uint4(0, 0, 0, 0);
-    if (res) vr = *reinterpret_cast<const uint4*>(res + off);
-    unpack8(vy, f);
+  // channel coefficients of this thread's 8 channels live in registers; U pixel rows per iteration with all loads
+  // issued before the arithmetic (memory-level parallelism: 2-4 x 16 B in flight per thread)
+  float sc[8], sf[8], rc[8], rf[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], co[c0 + k], co[Cs + c0 + k]);
-    if (res) {
-      float r[8];
-      unpack8(vr, r);
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = co[c0 + k]; sf[k] = co[Cs + c0 + k]; rc[k] = co[2 * Cs + c0 + k]; rf[k] = co[3 * Cs + c0 + k];
+  }
+  constexpr int U = 2;
+  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += U * step) {
+    uint4 vy[U], vr[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], co[2 * Cs + c0 + k], co[3 * Cs + c0 + k]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + u * step;
+      vy[u] = make_uint4(0, 0, 0, 0); vr[u] = make_uint4(0, 0, 0, 0);
+      if (pu < P) {
+        vy[u] = __ldcs(reinterpret_cast<const uint4*>(y + pu * Cs + c0));
+        if (res) vr[u] = __ldcs(reinterpret_cast<const uint4*>(res + pu * Cs + c0));
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + u * step;
+      if (pu >= P) break;
+      float f[8];
+      unpack8(vy[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
+      if (res) {
+        float r[8];
+        unpack8(vr[u], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], rc[k], rf[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+      }
+      *reinterpret_cast<uint4*>(z + pu * Cs + c0) = pack8(f);
     }
-    *reinterpret_cast<uint4*>(z + off) = pack8(f);
   }
 }
 
@@ -262,26 +296,45 @@ bn_forward_kernel(const __nv_bfloat16* __restrict__ y, BnParams b1, const __nv_b
   if (pr >= rpi) return;
   const int c0 = cv * 8;
   const int64_t step = (int64_t)gridDim.x * rpi;
-  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
-    const int64_t off = p * Cs + c0;
-    float f[8];
-    const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
-    uint4 vr = make_uint4(0, 0, 0, 0);
-    if (res) vr = *reinterpret_cast<const uint4*>(res + off);
-    unpack8(vy, f);
+  // channel coefficients of this thread's 8 channels live in registers; U pixel rows per iteration with all loads
+  // issued before the arithmetic (memory-level parallelism: 2-4 x 16 B in flight per thread)
+  float sc[8], sf[8], rc[8], rf[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], co[c0 + k], co[Cs + c0 + k]);
-    if (res) {
-      float r[8];
-      unpack8(vr, r);
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = co[c0 + k]; sf[k] = co[Cs + c0 + k]; rc[k] = co[2 * Cs + c0 + k]; rf[k] = co[3 * Cs + c0 + k];
+  }
+  constexpr int U = 2;
+  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += U * step) {
+    uint4 vy[U], vr[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], co[2 * Cs + c0 + k], co[3 * Cs + c0 + k]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + u * step;
+      vy[u] = make_uint4(0, 0, 0, 0); vr[u] = make_uint4(0, 0, 0, 0);
+      if (pu < P) {
+        vy[u] = __ldcs(reinterpret_cast<const uint4*>(y + pu * Cs + c0));
+        if (res) vr[u] = __ldcs(reinterpret_cast<const uint4*>(res + pu * Cs + c0));
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + u * step;
+      if (pu >= P) break;
+      float f[8];
+      unpack8(vy[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
+      if (res) {
+        float r[8];
+        unpack8(vr[u], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], rc[k], rf[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
+      }
+      *reinterpret_cast<uint4*>(z + pu * Cs + c0) = pack8(f);
     }
-    *reinterpret_cast<uint4*>(z + off) = pack8(f);
   }
 }
 
@@ -346,31 +399,48 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
   if (pr >= rpi) return;
   const int c0 = cv * 8;
   const int64_t step = (int64_t)gridDim.x * rpi;
-  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += step) {
-    const int64_t off = p * Cs + c0;
-    const uint4 vd = *reinterpret_cast<const uint4*>(dz + off);
-    const uint4 vy = *reinterpret_cast<const uint4*>(y + off);
-    uint4 vz = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
-    if (relu) vz = *reinterpret_cast<const uint4*>(z + off);
-    if (has_res_bn) vr = *reinterpret_cast<const uint4*>(res + off);
-    float fd[8], fz[8], fy[8], g[8], o[8];
-    unpack8(vd, fd); unpack8(vy, fy); unpack8(vz, fz);
+  float cA[8], cB[8], cK[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
-      o[k] = fmaf(co[c0 + k], g[k], fmaf(co[Cs + c0 + k], fy[k], co[2 * Cs + c0 + k]));
+  for (int k = 0; k < 8; ++k) { cA[k] = co[c0 + k]; cB[k] = co[Cs + c0 + k]; cK[k] = co[2 * Cs + c0 + k]; }
+  constexpr int U = 2;      // pixel rows per iteration, all loads first
+  for (int64_t p = (int64_t)blockIdx.x * rpi + pr; p < P; p += U * step) {
+    uint4 vd[U], vy[U], vz[U], vr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + u * step;
+      vd[u] = vy[u] = vz[u] = vr[u] = make_uint4(0, 0, 0, 0);
+      if (pu < P) {
+        const int64_t off = pu * Cs + c0;
+        vd[u] = __ldcs(reinterpret_cast<const uint4*>(dz + off));
+        vy[u] = __ldcs(reinterpret_cast<const uint4*>(y + off));
+        if (relu) vz[u] = __ldcs(reinterpret_cast<const uint4*>(z + off));
+        if (has_res_bn) vr[u] = __ldcs(reinterpret_cast<const uint4*>(res + off));
+      }
     }
-    *reinterpret_cast<uint4*>(dy + off) = pack8(o);
-    if (dres) {
-      if (has_res_bn) {
-        float fr[8];
-        unpack8(vr, fr);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          o[k] = fmaf(co[3 * Cs + c0 + k], g[k], fmaf(co[4 * Cs + c0 + k], fr[k], co[5 * Cs + c0 + k]));
-        *reinterpret_cast<uint4*>(dres + off) = pack8(o);
-      } else {
-        *reinterpret_cast<uint4*>(dres + off) = pack8(g);
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + u * step;
+      if (pu >= P) break;
+      const int64_t off = pu * Cs + c0;
+      float fd[8], fz[8], fy[8], g[8], o[8];
+      unpack8(vd[u], fd); unpack8(vy[u], fy); unpack8(vz[u], fz);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
+        o[k] = fmaf(cA[k], g[k], fmaf(cB[k], fy[k], cK[k]));
+      }
+      *reinterpret_cast<uint4*>(dy + off) = pack8(o);
+      if (dres) {
+        if (has_res_bn) {
+          float fr[8];
+          unpack8(vr[u], fr);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            o[k] = fmaf(co[3 * Cs + c0 + k], g[k], fmaf(co[4 * Cs + c0 + k], fr[k], co[5 * Cs + c0 + k]));
+          *reinterpret_cast<uint4*>(dres + off) = pack8(o);
+        } else {
+          *reinterpret_cast<uint4*>(dres + off) = pack8(g);
+        }
       }
     }
   }

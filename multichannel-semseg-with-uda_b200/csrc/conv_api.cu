@@ -16,7 +16,7 @@ size_t umma_wgrad_workspace(const mcd_conv_geom& g);
 size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags);
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                const mcd_conv_geom& g, int accumulate, cudaStream_t st);
-int umma_problem_tile(const TapProblem& p, int planar, int* pair);
+int umma_problem_tile(const TapProblem& p, int planar, int* pair, int* halo);
 int umma_wgrad_tile(const mcd_conv_geom& g, int* rows);
 bool umma_wgrad_partial_layout(const mcd_conv_geom& g, int* out4);
 bool rowconv_fprop_ok(const mcd_conv_geom& g);
@@ -160,7 +160,7 @@ int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int alg
   }
   if (pass == 0 ? rowconv_fprop_ok(*g) : rowconv_dgrad_ok(*g)) return 3000 + 16;
   TapProblem p[4];
-  int pair = 0;
+  int pair = 0, halo = 0;
   if (pass == 0) {
     plan_fprop(*g, p[0]);
     if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p[0]);
@@ -168,8 +168,8 @@ int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int alg
     plan_dgrad(*g, p);
     if (packed_dgrad_ok(*g)) plan_dgrad_packed(*g, p[0]);
   }
-  const int bn = umma_problem_tile(p[0], pass == 0 && y_layout == MCD_OUT_PLANAR_F32, &pair);
-  return (p[0].packed ? 2000 : (pair ? 1000 : 0)) + bn;
+  const int bn = umma_problem_tile(p[0], pass == 0 && y_layout == MCD_OUT_PLANAR_F32, &pair, &halo);
+  return (p[0].packed ? 2000 : (halo ? (pair ? 7000 : 6000) : (pair ? 1000 : 0))) + bn;
 }
 
 int mcd_pack_weight_rowconv(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int Cs, int mode,

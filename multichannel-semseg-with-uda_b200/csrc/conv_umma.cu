@@ -53,6 +53,16 @@ struct FpropArgs {
   int sk_units;
   float* sk_partial;          // [gridDim.x][BN/32][128][32] fp32
   int* sk_flags;              // [gridDim.x], zero on entry
+  // halo-tile mode (HALO kernels): ONE TMA box {64 ch, halo_wb, halo_hb} per (tile, 64-channel chunk) holds every
+  // pixel any tap of the 8-wide x 16-tall output tile reads; tap t's A operand is the same buffer entered
+  // taps[t].pad0 pixel rows further down (descriptor start + pad0 * 128 B, stride between 8-pixel groups =
+  // halo_wb * 128 B).  The 128-byte swizzle is a function of absolute shared-memory address bits
+  // (profiles/r01b_exp_swizzle_shift.txt), so a descriptor may start at any row of a tile TMA wrote once.
+  int halo_bytes;             // buffer stride (box bytes rounded up to 1024)
+  int halo_tx;                // bytes one halo box delivers
+  int halo_wb;                // box width in pixels
+  int halo_oh, halo_ow;       // box origin relative to the tile origin (most negative tap offset)
+  int stages;                 // weight-tile ring depth (runtime in halo mode)
   Tap taps[kMaxTaps];
 };
 
@@ -137,7 +147,7 @@ struct FpropCfg {
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
 // registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
-template <int BN, bool PAIR, int OCC = 1>
+template <int BN, bool PAIR, int OCC = 1, bool HALO = false>
 __global__ void __launch_bounds__(kThreads, FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
   using Cfg = FpropCfg<BN, PAIR, OCC>;
@@ -145,14 +155,19 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;     // [2]
+  // HALO: [halo buffer 0][halo buffer 1][weight-tile ring]; else [A|B stage ring]
+  const int nstages = HALO ? a.stages : Cfg::STAGES;
+  const int ring_bytes = HALO ? 2 * a.halo_bytes + a.stages * Cfg::B_BYTES : Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
+  uint64_t* empty_bar = full_bar + nstages;
+  uint64_t* tmem_full_bar = empty_bar + nstages;          // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* halo_full_bar = tmem_empty_bar + 2;           // [2]
+  uint64_t* halo_empty_bar = halo_full_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_empty_bar + 2);
   // BatchNorm sum / sum of squares of all tiles of this (persistent) CTA are collected in shared memory and
   // flushed with one global atomic per channel at the end (instead of 2 per channel per warp per tile)
-  float* sstat = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  float* sstat = reinterpret_cast<float*>(smem + ring_bytes + 256);
   const bool stat_sm = a.stats != nullptr && a.rows <= Cfg::STAT_ROWS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,8 +180,11 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 8 : 4); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 8 : 4);
+      mbar_init(&halo_full_bar[s], 1); mbar_init(&halo_empty_bar[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -184,6 +202,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
+      int hb = 0; uint32_t hphase = 0;
       while (it.next()) {
         int mt = PAIR ? 2 * (it.tile / a.tiles_n) + (int)rank : it.tile / a.tiles_n;
         const int n0 = (it.tile % a.tiles_n) * BN;
@@ -191,6 +210,37 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         const int th_i = mt % a.tiles_h; mt /= a.tiles_h;
         const int n_img = mt;                      // PAIR, odd tile count: n_img == N -> TMA zero fill
         const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+        if (HALO) {
+          // per 64-channel chunk: one halo box of activations, then one weight tile per tap through the ring
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&halo_empty_bar[hb], hphase ^ 1);
+            uint8_t* sh = smem + hb * a.halo_bytes;
+            if (PAIR) {
+              const uint32_t hf = mapa_shared(smem_u32(&halo_full_bar[hb]), 0);
+              if (rank == 0) mbar_expect_tx(&halo_full_bar[hb], 2 * a.halo_tx);
+              tma_load_4d_pair(sh, &maps.a[0], hf, kc * 64, tw0 + a.halo_ow, th0 + a.halo_oh, n_img);
+            } else {
+              mbar_expect_tx(&halo_full_bar[hb], a.halo_tx);
+              tma_load_4d(sh, &maps.a[0], &halo_full_bar[hb], kc * 64, tw0 + a.halo_ow, th0 + a.halo_oh, n_img);
+            }
+            for (int t = 0; t < a.ntaps; ++t) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sb = smem + 2 * a.halo_bytes + stage * Cfg::B_BYTES;
+              const int wcol = a.taps[t].wk * a.kc_pad + kc * 64;
+              if (PAIR) {
+                const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
+                tma_load_2d_pair(sb, &maps.b, fb, wcol, n0 + (int)rank * (BN / 2));
+              } else {
+                mbar_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+                tma_load_2d(sb, &maps.b, &full_bar[stage], wcol, n0);
+              }
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+            if (++hb == 2) { hb = 0; hphase ^= 1; }
+          }
+          continue;
+        }
         int t = it.kb0 / a.kchunks, kc = it.kb0 % a.kchunks;
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           const Tap tap = a.taps[t];
@@ -228,10 +278,50 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
+    int hb = 0; uint32_t hphase = 0;
     while ((!PAIR || rank == 0) && it.next()) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+      if (HALO) {
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&halo_full_bar[hb], hphase);
+          tc_fence_after();
+          const uint32_t sh = smem_u32(smem + hb * a.halo_bytes);
+          for (int t = 0; t < a.ntaps; ++t) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+              // A: rows (pixels) of the halo buffer starting taps[t].pad0 rows in; 8-pixel groups = tile rows,
+              // halo_wb pixels apart.  B: this tap's weight tile.
+              const uint64_t adesc = smem_desc_sw128(sh + (uint32_t)a.taps[t].pad0 * 128u, 0,
+                                                     (uint32_t)a.halo_wb * 128u);
+              const uint64_t bdesc = smem_desc_sw128(smem_u32(smem + 2 * a.halo_bytes + stage * Cfg::B_BYTES), 0, 1024);
+              const bool last_t = t == a.ntaps - 1;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t accum = (kc != 0 || t != 0 || k != 0) ? 1u : 0u;
+                if (PAIR) umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+              }
+              if (PAIR) {
+                umma_commit_pair(&empty_bar[stage], 3);
+                if (last_t) umma_commit_pair(&halo_empty_bar[hb], 3);
+                if (last_t && kc == a.kchunks - 1) umma_commit_pair(&tmem_full_bar[acc], 3);
+              } else {
+                umma_commit(&empty_bar[stage]);
+                if (last_t) umma_commit(&halo_empty_bar[hb]);
+                if (last_t && kc == a.kchunks - 1) umma_commit(&tmem_full_bar[acc]);
+              }
+            }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+          if (++hb == 2) { hb = 0; hphase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -975,6 +1065,70 @@ static int launch_fprop_pair(const UmmaMaps& maps, const FpropArgs& a, int pairs
   return check_launch("conv_umma_fprop_pair");
 }
 
+// ---- halo-tile launches (HALO = true instantiations; dynamic shared memory sized per problem) -------------------
+constexpr int kHaloFixedSmem = 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 1024 * 4 /*BatchNorm staging*/;
+
+template <int BN, bool PAIR, int OCC>
+static int launch_fprop_halo(const UmmaMaps& maps, const FpropArgs& a, int grid, cudaStream_t st) {
+  using Cfg = FpropCfg<BN, PAIR, OCC>;
+  const int smem_bytes = 2 * a.halo_bytes + a.stages * Cfg::B_BYTES + kHaloFixedSmem;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, PAIR, OCC, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { set_error("fprop halo smem attr (%d B): %s", smem_bytes, cudaGetErrorString(e)); return MCD_E_CUDA; }
+    attr_bytes = smem_bytes;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = PAIR ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_fprop_kernel<BN, PAIR, OCC, true>, maps, a);
+  if (e != cudaSuccess) { set_error("conv_umma_fprop (halo): %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+  return check_launch("conv_umma_fprop_halo");
+}
+
+// MCD_HALO=0 selects the one-box-per-tap (im2col-style) staging for every layer (A/B measurements)
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCD_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+// Halo-tile plan of a stride-1, multi-tap problem with >= 64 produced channels: 8 x 16 output tiles, box =
+// tile + the extent of the tap offsets.  Returns false when the problem keeps the per-tap staging.
+static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb) {
+  if (!halo_enabled() || p.packed || p.smul != 1 || p.ntaps < 2 || BN < 64 || (BN == 256 && !pair)) return false;
+  int lo_h = 1 << 20, hi_h = -(1 << 20), lo_w = 1 << 20, hi_w = -(1 << 20);
+  for (int t = 0; t < p.ntaps; ++t) {
+    if (p.taps[t].map != 0) return false;
+    lo_h = min(lo_h, (int)p.taps[t].mdh); hi_h = max(hi_h, (int)p.taps[t].mdh);
+    lo_w = min(lo_w, (int)p.taps[t].mdw); hi_w = max(hi_w, (int)p.taps[t].mdw);
+  }
+  const int Wb = 8 + (hi_w - lo_w), hb = 16 + (hi_h - lo_h);
+  if (Wb > 256 || hb > 256) return false;
+  const int halo_bytes = round_up(Wb * hb * 128, 1024);
+  const int b_bytes = (pair ? BN / 2 : BN) * 128;
+  const int limit = (pair ? 224 : 110) * 1024;        // pair: one CTA per SM; 64 / 128 tiles: two CTAs per SM
+  const int stages = min(8, (limit - kHaloFixedSmem - 2 * halo_bytes) / b_bytes);
+  if (stages < 3) return false;
+  a->halo_bytes = halo_bytes; a->halo_tx = Wb * hb * 128; a->halo_wb = Wb; a->halo_oh = lo_h; a->halo_ow = lo_w;
+  a->stages = stages;
+  a->TH = 16; a->TW = 8;
+  a->tiles_h = (p.Ht + 15) / 16; a->tiles_w = (p.Wt + 7) / 8;
+  a->tiles_m = p.N * a->tiles_h * a->tiles_w;
+  for (int t = 0; t < p.ntaps; ++t)
+    a->taps[t].pad0 = (int16_t)((p.taps[t].mdh - lo_h) * Wb + (p.taps[t].mdw - lo_w));
+  *Hb = hb;
+  return true;
+}
+
 static bool g_pair_enabled = true;   // MCD_CTA_PAIRS=0 selects the single-CTA 128x256 tiles (A/B measurements)
 static bool pair_enabled() {
   static bool init = false;
@@ -1055,6 +1209,20 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   fprop_tiling(p, planar, &a.TH, &a.TW, &a.tiles_m, &a.tiles_n, &BN);
   const bool want_sk = ex.sk_partial && ex.sk_flags;
   const bool pair = BN == 256 && !p.packed && a.tiles_m >= 2 && !want_sk && pair_enabled();
+  int halo_hb = 0;
+  if (!want_sk && halo_plan(p, BN, pair, &a, &halo_hb)) {
+    int rc = encode_act_map(&maps.a[0], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, 1, 0, 0, a.halo_wb, halo_hb);
+    if (rc != MCD_OK) return rc;
+    rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
+    if (rc != MCD_OK) return rc;
+    if (pair) {
+      const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
+      return launch_fprop_halo<256, true, 1>(maps, a, 2 * min(pair_tiles, sm_count() / 2), st);
+    }
+    const int grid = min(a.tiles_m * a.tiles_n, 2 * sm_count());
+    return BN == 128 ? launch_fprop_halo<128, false, 2>(maps, a, grid, st)
+                     : launch_fprop_halo<64, false, 2>(maps, a, grid, st);
+  }
   int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
   if (rc != MCD_OK) return rc;
   if (pair) {
@@ -1083,11 +1251,14 @@ static int wgrad_bn(const mcd_conv_geom& g);
 static bool wgrad_rows_ok(const mcd_conv_geom& g);
 static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
                         int* ntiles, int* ksplit);
+static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb);
 // which kernel launch_umma_problem() picks for a problem: tile width BN, *pair = CTA-pair (cta_group::2) variant
-int umma_problem_tile(const TapProblem& p, int planar, int* pair) {
-  int TH, TW, tiles_m, tiles_n, BN;
+int umma_problem_tile(const TapProblem& p, int planar, int* pair, int* halo) {
+  int TH, TW, tiles_m, tiles_n, BN, hb;
   fprop_tiling(p, planar, &TH, &TW, &tiles_m, &tiles_n, &BN);
   *pair = BN == 256 && !p.packed && tiles_m >= 2 && pair_enabled();
+  FpropArgs a;
+  *halo = halo_plan(p, BN, *pair != 0, &a, &hb) ? 1 : 0;
   return BN;
 }
 

@@ -187,6 +187,9 @@ class MultiPacker:
             conv._packs[key] = ((w._version, w.data_ptr()), packed)
 
 
+_SGD_BLOCKS = int(os.environ.get("MCD_SGD_BLOCKS", "160"))   # thread blocks per parameter tensor
+
+
 class FusedSGD:
     """`optimizer.step()` of a torch.optim.SGD (one parameter group, dampening 0, no Nesterov) as ONE launch of
     mcd_sgd_pack_multi, which also refreshes the packed bf16 shadows of the convolution weights (replaces
@@ -287,7 +290,7 @@ class FusedSGD:
             if len(self._tables) > 64:
                 self._tables.clear()
             hit = self._tables[key] = (host, dev_t, len(active))
-        abi.check(abi.lib().mcd_sgd_pack_multi(_p(hit[1]), hit[2], _p(self.hyper), 64, self.dev.index,
+        abi.check(abi.lib().mcd_sgd_pack_multi(_p(hit[1]), hit[2], _p(self.hyper), _SGD_BLOCKS, self.dev.index,
                                                ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
                   "sgd_pack_multi")
         for p in active:      # the packs were rewritten from the updated weights: keep their tags current
@@ -661,6 +664,7 @@ class ConvProfiler:
 
 _KIND_NAMES = {0: "conv_umma_fprop_kernel<%d>", 1: "conv_umma_fprop_kernel<%d,pair>",
                2: "conv_umma_fprop_kernel<%d> (row-packed)", 3: "conv_umma_rowconv_kernel<%d>",
+               6: "conv_umma_fprop_kernel<%d,halo>", 7: "conv_umma_fprop_kernel<%d,pair,halo>",
                4: "conv_umma_wgrad_kernel<%d> + wgrad_reduce", 5: "conv_umma_wgrad_rows_kernel<%d> + reduce",
                9: "conv_direct_kernel"}
 

@@ -94,6 +94,36 @@ class MCDStep:
         self.graph.replay()
         return self._static_out
 
+    # -- input pipelining: the next batch travels host -> device while the current iteration computes ----------
+    def prefetch(self, src_imgs, src_lbls, tgt_imgs):
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a copy stream into staging
+        buffers; `replay_prefetched()` consumes it.  The data loader's `.cuda(non_blocking=True)` of the
+        reference (adapt_trainer.py:156-160) overlapped with the running iteration."""
+        dev = self._static[0].device
+        if getattr(self, "_stage", None) is None:
+            self._stage = tuple(torch.empty_like(t) for t in self._static)
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._copied = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(dev))
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)            # the previous staging contents have been moved into the static inputs
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage, (src_imgs, src_lbls, tgt_imgs)):
+                dst.copy_(src, non_blocking=True)
+            self._copied.record(cs)
+
+    def replay_prefetched(self):
+        """device->device move of the prefetched batch into the graph's static inputs, then one graph launch."""
+        dev = self._static[0].device
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(self._copied)
+        for dst, src in zip(self._static, self._stage):
+            dst.copy_(src, non_blocking=True)
+        self._consumed.record(main)
+        self.graph.replay()
+        return self._static_out
+
     # -- forward helpers -------------------------------------------------------------------------
     def _gen(self, x):
         if not self.mfnet:

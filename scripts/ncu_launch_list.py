@@ -13,18 +13,25 @@ lines = [ln for ln in open(src) if ln.startswith('"')]
 rows = list(csv.DictReader(lines))
 
 
-def short(n):
+def kernel_short_name(n):
+    """ncu's demangled name -> the name bench.py / DESIGN.md use."""
     n = re.sub(r"^void ", "", n)
     n = n.replace("mcd::", "")
-    m = re.match(r"(conv_umma_\w+)<(\d+)(?:, *(\(bool\))?([01]|true|false))?(?:, *(\d+))?>", n)
+    n = re.sub(r"\(bool\)", "", n)
+    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(\w+), *(\d+), *(\w+)>", n)
     if m:
-        name = m.group(1) + "<" + m.group(2)
-        if m.group(4) in ("1", "true"):
-            name += ",pair"
-        if m.group(5) == "2":
-            name += ",occ2"
-        return name + ">"
+        bn, pair, occ, halo = m.group(1), m.group(2) in ("1", "true"), m.group(3), m.group(4) in ("1", "true")
+        return "conv_umma_fprop_kernel<%s%s%s>" % (bn, ",pair" if pair else "", ",halo" if halo else "")
+    m = re.match(r"conv_umma_wgrad_kernel<(\d+), *(\d+)>", n)
+    if m:
+        return "conv_umma_wgrad_kernel<%s>" % m.group(1)
+    m = re.match(r"(conv_umma_\w+)<(\d+)>", n)
+    if m:
+        return "%s<%s>" % (m.group(1), m.group(2))
     return re.sub(r"\(.*$", "", n)[:70]
+
+
+short = kernel_short_name
 
 
 agg = collections.OrderedDict()

@@ -27,15 +27,25 @@ COLS = ["Kernel Name", "Grid Size", "Block Size", "launch__cluster_dim_x", "gpu_
         "smsp__cycles_active.avg"]
 
 
-def short_name(n):
+def kernel_short_name(n):
+    """ncu's demangled name -> the name bench.py / DESIGN.md use."""
     n = re.sub(r"^void ", "", n)
-    n = re.sub(r"\(.*$", "", n)
     n = n.replace("mcd::", "")
-    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(true|false|\(bool\)[01]|[01])>", n)
+    n = re.sub(r"\(bool\)", "", n)
+    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(\w+), *(\d+), *(\w+)>", n)
     if m:
-        pair = m.group(2) in ("true", "(bool)1", "1")
-        return "conv_umma_fprop_kernel<%s%s>" % (m.group(1), ",pair" if pair else "")
-    return n
+        bn, pair, occ, halo = m.group(1), m.group(2) in ("1", "true"), m.group(3), m.group(4) in ("1", "true")
+        return "conv_umma_fprop_kernel<%s%s%s>" % (bn, ",pair" if pair else "", ",halo" if halo else "")
+    m = re.match(r"conv_umma_wgrad_kernel<(\d+), *(\d+)>", n)
+    if m:
+        return "conv_umma_wgrad_kernel<%s>" % m.group(1)
+    m = re.match(r"(conv_umma_\w+)<(\d+)>", n)
+    if m:
+        return "%s<%s>" % (m.group(1), m.group(2))
+    return re.sub(r"\(.*$", "", n)[:70]
+
+
+short_name = kernel_short_name
 
 
 def main():
@@ -56,14 +66,15 @@ def main():
         f.write(",".join("%s [%s]" % (c, units[idx[c]]) for c in cols) + "\n")
         for r in data:
             vals = [r[idx[c]].replace(",", ";") for c in cols]
-            vals[0] = short_name(r[idx["Kernel Name"]])[:60]
+            kname = short_name(r[idx["Kernel Name"]])[:60]
+            vals[0] = kname.replace(",", ";")
             f.write(",".join(vals) + "\n")
             try:
                 def tobytes(c):
                     v, u = float(r[idx[c]].replace(",", "")), units[idx[c]].lower()
                     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                 t = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
-                ent = traffic.setdefault(vals[0], {"dram_bytes_per_launch": [], "grid": []})
+                ent = traffic.setdefault(kname, {"dram_bytes_per_launch": [], "grid": []})
                 ent["dram_bytes_per_launch"].append(t)
                 ent["grid"].append(r[idx["Grid Size"]])
             except (KeyError, ValueError):

@@ -47,6 +47,13 @@ CONV_SHAPES = [
     (2, 7, 200, 16, 16, 3, 1, 1, 1),
     (1, 8, 130, 8, 32, 3, 1, 1, 1),
     (1, 6, 129, 12, 24, 5, 1, 1, 2),
+    # halo-tile staging (8 x 16 tiles, one activation box per tile and chunk): ragged tiles, several chunks,
+    # CTA pairs with an odd tile count, two channel tiles
+    (3, 60, 80, 256, 256, 3, 1, 2, 2),
+    (2, 37, 53, 128, 128, 3, 1, 1, 1),
+    (2, 29, 43, 64, 64, 3, 1, 1, 1),
+    (1, 23, 31, 512, 256, 3, 1, 4, 4),
+    (1, 17, 9, 256, 512, 3, 1, 4, 4),
 ]
 
 STREAMK_SHAPES = [
