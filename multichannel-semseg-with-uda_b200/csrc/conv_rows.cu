@@ -11,6 +11,7 @@
 // 16-channel tensors) one 2176-byte TMA box {8 ch, 136 px} is staged, and SP/2 MMAs (K=16 = two taps) consume it.
 // Persistent CTAs, double-buffered TMEM accumulator, same epilogue contract as conv_umma_fprop_kernel
 // (bias, bf16 NHWC store, fused BatchNorm sum / sum of squares, optional fused addend).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_plan.h"
 #include "umma_ptx.cuh"
@@ -244,6 +245,139 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
   if (warp == 1) tmem_dealloc(tmem_base, 2 * NB);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same stem layers ("Toeplitz" wgrad, r01b).  dW[co][c][r][s] = sum_p dY[p][co] * x[p + (r,s)][c].
+// Per 128-pixel row tile and filter row r the staged image-row segment IS the MN-major A operand:
+//     A[m = (s, c8)][k = p] = seg[(p + s) * 16 B + c8 * 2 B]     (no-swizzle MN-major, 8-element groups 16 B apart = ONE
+//     pixel, 8-pixel K groups 128 B apart), i.e. overlapping core matrices, zero window expansion - the im2col-style
+// kernel (conv_umma_wgrad_rows_kernel) moves 7-8x the bytes through L2 and is L2 -> SM bound.  dY is staged as
+// 8-channel planes {8 ch, 128 px} (B operand, N = produced channels).  D_(r,half)[64 = 8 taps x 8 ch][NB] accumulates
+// in TMEM over ALL tiles of the persistent CTA; one epilogue per CTA parks it in the workspace
+// ws[cta][r * HC + half][64][NB], summed over CTAs by wgrad_toeplitz_reduce_kernel.
+struct ToepArgs {
+  int N, H, W, tiles_w, total_tiles;
+  int R, HC, nacc;          // filter rows, 8-channel halves of x, accumulators = R * HC
+  int roff, woff;           // x row / pixel offset of tap (0, 0) relative to the output pixel (-pad)
+  int NB, DC;               // GEMM N = dY channel stride (16 / 32), dY planes = NB / 8
+  int stages, stage_bytes, tmem_cols;
+  float* ws;
+};
+
+__global__ void __launch_bounds__(RC_THREADS, 2)
+conv_umma_wgrad_toeplitz_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dymap,
+                                const __grid_constant__ ToepArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.stages * a.stage_bytes);
+  uint64_t* empty_bar = full_bar + a.stages;
+  uint64_t* tmem_full_bar = empty_bar + a.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&xmap);
+    prefetch_tmap(&dymap);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int dy_off = a.nacc * RC_PLANE;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int wt = tile % a.tiles_w;
+        const int h = (tile / a.tiles_w) % a.H;
+        const int n = tile / (a.tiles_w * a.H);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * a.stage_bytes;
+        mbar_expect_tx(&full_bar[stage], a.stage_bytes);
+        for (int r = 0; r < a.R; ++r)
+          for (int hf = 0; hf < a.HC; ++hf)
+            tma_load_4d(st + (r * a.HC + hf) * RC_PLANE, &xmap, &full_bar[stage], hf * 8, wt * 128 + a.woff,
+                        h + r + a.roff, n);
+        for (int d = 0; d < a.DC; ++d)
+          tma_load_4d(st + dy_off + d * 2048, &dymap, &full_bar[stage], d * 8, wt * 128, h, n);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = instr_desc_bf16(64, (uint32_t)a.NB, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    uint32_t first = 1;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + stage * a.stage_bytes);
+        for (int acc = 0; acc < a.nacc; ++acc) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {       // 128 pixels = 8 x UMMA_K(16); 16 pixels = 256 B in both operands
+            const uint64_t adesc = smem_desc_nosw(st + acc * RC_PLANE + j * 256, 128, 16);
+            const uint64_t bdesc = smem_desc_nosw(st + dy_off + j * 256, 128, 2048);
+            umma_bf16(tmem_base + (uint32_t)(acc * a.NB), adesc, bdesc, idesc, (first && j == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (tile + (int)gridDim.x >= a.total_tiles) umma_commit(tmem_full_bar);
+      }
+      first = 0;
+      __syncwarp();
+      if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // M = 64 accumulators live in lanes 0..15 of each 32-lane TMEM sub-partition: row m = 16 * q + lane
+    const int q = warp & 3;
+    const int m = q * 16 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    for (int acc = 0; acc < a.nacc; ++acc) {
+      float* o = a.ws + (((int64_t)blockIdx.x * a.nacc + acc) * 64 + m) * a.NB;
+      for (int c0 = 0; c0 < a.NB; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * a.NB + c0), v);
+        tmem_ld_wait();
+        if (lane < 16) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(o + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// dw[co][c][r][s] = sum_cta ws[cta][r * HC + c / 8][s * 8 + c % 8][co]; 8 lanes share one output element
+__global__ void wgrad_toeplitz_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ncta, int nacc,
+                                             int HC, int NB, int R, int S, int Cout, int Cin, int accumulate) {
+  const int64_t total = (int64_t)Cout * Cin * R * S;
+  const int sub = threadIdx.x & 7;
+  for (int64_t i0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; i0 < ((total + 31) & ~int64_t(31));
+       i0 += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int64_t i = i0 < total ? i0 : total - 1;
+    const int sx = (int)(i % S);
+    const int r = (int)((i / S) % R);
+    const int c = (int)((i / ((int64_t)S * R)) % Cin);
+    const int co = (int)(i / ((int64_t)S * R * Cin));
+    const int64_t off = ((int64_t)(r * HC + c / 8) * 64 + sx * 8 + c % 8) * NB + co;
+    const int64_t cstride = (int64_t)nacc * 64 * NB;
+    float acc = 0.f;
+    for (int k = sub; k < ncta; k += 8) acc += ws[k * cstride + off];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0 && i0 < total) dw[i] = accumulate ? dw[i] + acc : acc;
+  }
+}
+
 __global__ void pack_weight_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout,
                                            int Cin, int R, int S, int HC, int SP, int NB, int mode) {
   const int64_t total = (int64_t)R * HC * SP * NB * 8;
@@ -345,6 +479,95 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   int grid = min(a.total_tiles, sms * (a.NB == 16 ? 4 : 2));
   kern<<<grid, RC_THREADS, smem_bytes, st>>>(xmap, a);
   return check_launch("conv_umma_rowconv");
+}
+
+// ---- Toeplitz wgrad host side ------------------------------------------------------------------------------------
+static int toeplitz_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+bool wgrad_toeplitz_ok(const mcd_conv_geom& g) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("MCD_TOEPLITZ_WGRAD"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return false;
+  const int HC = g.Cin_s / 8;
+  return g.stride == 1 && g.dil == 1 && (g.Cin_s == 8 || g.Cin_s == 16) && (g.Cout_s == 16 || g.Cout_s == 32) &&
+         g.S <= 8 && g.R <= 7 && g.pad <= 7 && g.Ho == g.H && g.Wo == g.W && g.R * HC * g.Cout_s <= 512;
+}
+
+static int toeplitz_grid(const mcd_conv_geom& g) {
+  const int total_tiles = g.N * g.H * ((g.W + 127) / 128);
+  return min(total_tiles, 2 * toeplitz_sms());
+}
+
+size_t wgrad_toeplitz_workspace(const mcd_conv_geom& g) {
+  return sizeof(float) * (size_t)toeplitz_grid(g) * g.R * (g.Cin_s / 8) * 64 * g.Cout_s;
+}
+
+int wgrad_toeplitz_launch(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, const mcd_conv_geom& g,
+                          int accumulate, cudaStream_t st) {
+  EncodeTiledFnR enc = get_encode_r();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
+  if (!ws || ws_bytes < wgrad_toeplitz_workspace(g)) {
+    set_error("toeplitz wgrad: workspace %zu < %zu", ws_bytes, wgrad_toeplitz_workspace(g));
+    return MCD_E_WORKSPACE;
+  }
+  ToepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = g.N; a.H = g.H; a.W = g.W;
+  a.tiles_w = (g.W + 127) / 128;
+  a.total_tiles = g.N * g.H * a.tiles_w;
+  a.R = g.R; a.HC = g.Cin_s / 8; a.nacc = a.R * a.HC;
+  a.roff = -g.pad; a.woff = -g.pad;
+  a.NB = g.Cout_s; a.DC = g.Cout_s / 8;
+  a.stage_bytes = a.nacc * RC_PLANE + a.DC * 2048;
+  a.stages = max(2, min(6, (100 * 1024) / a.stage_bytes));
+  const int cols = a.nacc * a.NB;
+  a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+  a.ws = reinterpret_cast<float*>(ws);
+  CUtensorMap xmap, dymap;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cin_s, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cin_s * 2, (cuuint64_t)g.W * g.Cin_s * 2, (cuuint64_t)g.H * g.W * g.Cin_s * 2};
+    cuuint32_t box[4] = {8, RC_SEG, 1, 1};
+    CUresult r = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(toeplitz x) failed: %d", (int)r); return MCD_E_CUDA; }
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cout_s, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cout_s * 2, (cuuint64_t)g.W * g.Cout_s * 2, (cuuint64_t)g.H * g.W * g.Cout_s * 2};
+    cuuint32_t box[4] = {8, 128, 1, 1};
+    CUresult r = enc(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(toeplitz dy) failed: %d", (int)r); return MCD_E_CUDA; }
+  }
+  const int smem_bytes = a.stages * a.stage_bytes + 1024 + 256;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) { set_error("toeplitz wgrad smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    attr_bytes = smem_bytes;
+  }
+  const int grid = toeplitz_grid(g);
+  conv_umma_wgrad_toeplitz_kernel<<<grid, RC_THREADS, smem_bytes, st>>>(xmap, dymap, a);
+  int rc = check_launch("conv_umma_wgrad_toeplitz");
+  if (rc != MCD_OK) return rc;
+  const int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
+  const int rgrid = (int)min64((total * 8 + 255) / 256, 148 * 8);
+  wgrad_toeplitz_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, grid, a.nacc, a.HC, a.NB, g.R, g.S, g.Cout, g.Cin,
+                                                      accumulate);
+  return check_launch("wgrad_toeplitz_reduce");
 }
 
 }  // namespace mcd

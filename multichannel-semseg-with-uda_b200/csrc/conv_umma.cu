@@ -1247,6 +1247,10 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   return launch_fprop_bn<16>(maps, a, grid, st);
 }
 
+bool wgrad_toeplitz_ok(const mcd_conv_geom& g);
+size_t wgrad_toeplitz_workspace(const mcd_conv_geom& g);
+int wgrad_toeplitz_launch(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, const mcd_conv_geom& g,
+                          int accumulate, cudaStream_t st);
 static int wgrad_bn(const mcd_conv_geom& g);
 static bool wgrad_rows_ok(const mcd_conv_geom& g);
 static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
@@ -1264,6 +1268,7 @@ int umma_problem_tile(const TapProblem& p, int planar, int* pair, int* halo) {
 
 // which kernel umma_wgrad() picks: tile width BN, *rows = all-filter-rows thin-channel kernel
 int umma_wgrad_tile(const mcd_conv_geom& g, int* rows) {
+  if (wgrad_toeplitz_ok(g)) { *rows = 2; return g.Cout_s; }
   *rows = wgrad_rows_ok(g);
   if (*rows) return 64;
   return packed_fprop_ok(g) ? 64 : wgrad_bn(g);
@@ -1272,7 +1277,7 @@ int umma_wgrad_tile(const mcd_conv_geom& g, int* rows) {
 // layout of the split partial sums the generic wgrad kernel leaves in its workspace: fp32 [ksplit][T][CoutP][CinP];
 // false for the layers that use other kernels (stem)
 bool umma_wgrad_partial_layout(const mcd_conv_geom& g, int* out4) {
-  if ((g.stride != 1 && g.stride != 2) || g.R * g.S > kMaxTaps || wgrad_rows_ok(g) || packed_fprop_ok(g)) return false;
+  if (wgrad_toeplitz_ok(g) || (g.stride != 1 && g.stride != 2) || g.R * g.S > kMaxTaps || wgrad_rows_ok(g) || packed_fprop_ok(g)) return false;
   int BN, CoutP, CinP, TH, TW, ntiles, ksplit;
   wgrad_shape(g, &BN, &CoutP, &CinP, &TH, &TW, &ntiles, &ksplit);
   out4[0] = ksplit; out4[1] = g.R * g.S; out4[2] = CoutP; out4[3] = CinP;
@@ -1367,6 +1372,7 @@ static int umma_wgrad_rows(const void* x, const void* dy, float* dw, void* ws, s
 }
 
 size_t umma_wgrad_workspace(const mcd_conv_geom& g) {
+  if (wgrad_toeplitz_ok(g)) return wgrad_toeplitz_workspace(g);
   if (wgrad_rows_ok(g)) {
     int TH, TW, ntiles, nsplit;
     wgrad_rows_shape(g, &TH, &TW, &ntiles, &nsplit);
@@ -1395,6 +1401,10 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
                const mcd_conv_geom& g, int accumulate, cudaStream_t st) {
   if (g.stride != 1 && g.stride != 2) { set_error("umma wgrad: stride %d unsupported", g.stride); return MCD_E_INVALID; }
   if (g.R * g.S > kMaxTaps) { set_error("umma wgrad: too many taps"); return MCD_E_INVALID; }
+  if (wgrad_toeplitz_ok(g)) {
+    if (!dw) { set_error("umma wgrad: partial-sum output is not available for the stem layers"); return MCD_E_INVALID; }
+    return wgrad_toeplitz_launch(x, dy, dw, ws, ws_bytes, g, accumulate, st);
+  }
   if (wgrad_rows_ok(g)) {
     if (!dw) { set_error("umma wgrad: partial-sum output is not available for the stem layers"); return MCD_E_INVALID; }
     return umma_wgrad_rows(x, dy, dw, ws, ws_bytes, g, accumulate, st);
