@@ -122,7 +122,8 @@ int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
  * 1 = conv_umma_fprop_kernel<256, pair> (cta_group::2, 256 x 256 tile), 2 = row-packed thin-channel mode of kind 0,
  * 3 = conv_umma_rowconv_kernel, 4 = conv_umma_wgrad_kernel<BN>, 5 = conv_umma_wgrad_rows_kernel,
  * 6 = kind 0 with halo-tile staging (one activation box per tile and 64-channel chunk serves all taps), 7 = kind 1
- * with halo-tile staging, 8 = conv_umma_wgrad_toeplitz_kernel (stem layers), 9 = CUDA-core direct kernels; -1 = invalid geometry.  Used by bench.py to attribute measured time to kernels. */
+ * with halo-tile staging, 8 = conv_umma_wgrad_toeplitz_kernel (stem layers), 9 = CUDA-core direct kernels,
+ * 10 = conv_umma_wgrad_pair_kernel (cta_group::2, 256 co x 256 ci tile); -1 = invalid geometry.  Used by bench.py to attribute measured time to kernels. */
 int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int algo);
 
 /* ---- convolution (nn.Conv2d: models/drn.py:21-23,126-131,171-205; dilated_fcn.py:226-232,632-658,821-823) */

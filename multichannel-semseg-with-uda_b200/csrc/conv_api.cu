@@ -156,7 +156,7 @@ int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int alg
   if (pass == 2) {
     int rows = 0;
     const int bn = umma_wgrad_tile(*g, &rows);
-    return (rows == 2 ? 8000 : (rows ? 5000 : 4000)) + bn;
+    return (rows == 3 ? 10000 : (rows == 2 ? 8000 : (rows ? 5000 : 4000))) + bn;
   }
   if (pass == 0 ? rowconv_fprop_ok(*g) : rowconv_dgrad_ok(*g)) return 3000 + 16;
   TapProblem p[4];

@@ -728,6 +728,165 @@ conv_umma_wgrad_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair wgrad for the wide layers (Cin > 128, Cout >= 256): one cta_group::2 MMA tile = 256 co x 256 ci.
+// Each CTA stages ITS 128 co of dY (A) and ITS 128 ci of X (B half): 32 KB of TMA writes and operand reads per
+// k-step and SM instead of 48 KB for the single-CTA 128 x 256 tile, which is shared-memory-bandwidth bound.
+struct WgradPairCfg {
+  static constexpr int KPIX = 64;
+  static constexpr int A_BYTES = 2 * KPIX * 128;
+  static constexpr int B_BYTES = 2 * KPIX * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;      // two 256-column accumulators
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_wgrad_pair_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ WgradArgs a) {
+  using Cfg = WgradPairCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_co = a.CoutP / 256, n_ci = a.CinP / 256;
+  const int per_split = a.T * n_co * n_ci;
+  const int total_items = per_split * a.ksplit;
+  const int per = (a.ntiles + a.ksplit - 1) / a.ksplit;
+  const int first_item = blockIdx.x / 2, item_stride = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+#define MCD_WGRADP_DECODE(item)                                             \
+  const int split = (item) / per_split;                                     \
+  int rem_ = (item) % per_split;                                            \
+  const int ci0 = (rem_ % n_ci) * 256; rem_ /= n_ci;                        \
+  const int co0 = (rem_ % n_co) * 256; rem_ /= n_co;                        \
+  const int t = rem_;                                                       \
+  const int tile_beg = split * per;                                         \
+  const int ksteps = max(min(tile_beg + per, a.ntiles) - tile_beg, 0);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = first_item; item < total_items; item += item_stride) {
+        MCD_WGRADP_DECODE(item)
+        (void)split;
+        const Tap tap = a.taps[t];
+        const CUtensorMap* xmap = &maps.a[tap.map];
+        for (int ks = 0; ks < ksteps; ++ks) {
+          int tile = tile_beg + ks;
+          const int tw_i = tile % a.tiles_w; tile /= a.tiles_w;
+          const int th_i = tile % a.tiles_h; tile /= a.tiles_h;
+          const int n_img = tile;
+          const int th0 = th_i * a.TH, tw0 = tw_i * a.TW;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            tma_load_4d_pair(sa + i * Cfg::KPIX * 128, &maps.b, fb, co0 + (int)rank * 128 + i * 64, tw0, th0, n_img);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            tma_load_4d_pair(sb + i * Cfg::KPIX * 128, xmap, fb, ci0 + (int)rank * 128 + i * 64, tw0 + tap.mdw,
+                             th0 + tap.mdh, n_img);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = instr_desc_bf16(256, 256, 1, 1);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = first_item; rank == 0 && item < total_items; item += item_stride) {
+      MCD_WGRADP_DECODE(item)
+      (void)ci0; (void)co0; (void)t; (void)split;
+      if (ksteps == 0) continue;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sa, Cfg::KPIX * 128, 1024);
+          const uint64_t bdesc = smem_desc_sw128(sb, Cfg::KPIX * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < Cfg::KPIX / 16; ++k)
+            umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (ks | k) != 0);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (ks == ksteps - 1) umma_commit_pair(&tmem_full_bar[acc], 3);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = first_item; item < total_items; item += item_stride) {
+      MCD_WGRADP_DECODE(item)
+      const int co = co0 + (int)rank * 128 + q * 32 + lane;
+      float* o = a.ws + (((int64_t)split * a.T + t) * a.CoutP + co) * a.CinP + ci0;
+      if (ksteps > 0) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+      }
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        float v[32];
+        if (ksteps > 0) {
+          tmem_ld32(tmem_d + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(o + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (ksteps > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+          else mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+#undef MCD_WGRADP_DECODE
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad of the row-packed thin-channel layers (layer0/1/2: Cout <= 64, R <= 7 filter rows).
 // One CTA owns a range of 64-pixel tiles and ALL filter rows: per tile it loads the dY tile once (A, one
 // 64-channel atom, MN-major) and the R shifted K-windows of X (B_r), and issues R accumulating MMAs
@@ -1255,6 +1414,7 @@ static int wgrad_bn(const mcd_conv_geom& g);
 static bool wgrad_rows_ok(const mcd_conv_geom& g);
 static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
                         int* ntiles, int* ksplit);
+static bool wgrad_pair(const mcd_conv_geom& g);
 static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb);
 // which kernel launch_umma_problem() picks for a problem: tile width BN, *pair = CTA-pair (cta_group::2) variant
 int umma_problem_tile(const TapProblem& p, int planar, int* pair, int* halo) {
@@ -1269,6 +1429,7 @@ int umma_problem_tile(const TapProblem& p, int planar, int* pair, int* halo) {
 // which kernel umma_wgrad() picks: tile width BN, *rows = all-filter-rows thin-channel kernel
 int umma_wgrad_tile(const mcd_conv_geom& g, int* rows) {
   if (wgrad_toeplitz_ok(g)) { *rows = 2; return g.Cout_s; }
+  if (!wgrad_rows_ok(g) && wgrad_pair(g)) { *rows = 3; return 256; }
   *rows = wgrad_rows_ok(g);
   if (*rows) return 64;
   return packed_fprop_ok(g) ? 64 : wgrad_bn(g);
@@ -1297,10 +1458,28 @@ size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags) {
 
 static int wgrad_bn(const mcd_conv_geom& g) { return g.Cin > 128 ? 256 : (g.Cin > 64 ? 128 : 64); }
 
+static bool pair_enabled();
+// CTA-pair tiles (256 co x 256 ci) for the wide layers; MCD_WGRAD_PAIRS=0 keeps the single-CTA 128 x 256 tiles
+static bool wgrad_pair(const mcd_conv_geom& g) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCD_WGRAD_PAIRS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && pair_enabled() && !packed_fprop_ok(g) && g.Cin > 128 && g.Cout >= 256;
+}
+
 static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
                         int* ntiles, int* ksplit) {
   const bool packed = packed_fprop_ok(g);
   *BN = packed ? 64 : wgrad_bn(g);
+  if (wgrad_pair(g)) {
+    *CoutP = round_up(g.Cout, 256);
+    *CinP = round_up(g.Cin, 256);
+    pick_tile(g.Ho, g.Wo, 64, TH, TW);
+    *ntiles = g.N * ((g.Ho + *TH - 1) / *TH) * ((g.Wo + *TW - 1) / *TW);
+    const int base = (*CoutP / 256) * (*CinP / 256) * g.R * g.S;
+    int ks = (sm_count() / 2) / base;
+    *ksplit = max(1, min(min(ks, *ntiles), 64));
+    return;
+  }
   *CoutP = round_up(g.Cout, 128);
   *CinP = packed ? 64 : round_up(g.Cin, *BN);
   if (packed) pick_tile_packed(g.Ho, g.Wo, 64, TH, TW);
@@ -1451,6 +1630,35 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
   int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, packed ? 1 : TW, TH);
   if (rc != MCD_OK) return rc;
 
+  if (wgrad_pair(g)) {
+    const int pair_items = (CoutP / 256) * (CinP / 256) * a.T * ksplit;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           WgradPairCfg::SMEM_BYTES);
+      if (e != cudaSuccess) { set_error("wgrad pair smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * min(pair_items, sm_count() / 2)));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = WgradPairCfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_wgrad_pair_kernel, maps, a);
+    if (e != cudaSuccess) { set_error("conv_umma_wgrad (CTA pairs): %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
+    rc = check_launch("conv_umma_wgrad_pair");
+    if (rc != MCD_OK) return rc;
+    if (!dw) return MCD_OK;
+    dim3 rg((unsigned)g.Cout, (unsigned)((g.Cin + 63) / 64));
+    wgrad_reduce_kernel<<<rg, 256, sizeof(float) * 64 * a.T, st>>>(a.ws, dw, ksplit, a.T, CoutP, CinP, g.Cout, g.Cin,
+                                                                   accumulate);
+    return check_launch("wgrad_reduce");
+  }
   const int total_items = (CoutP / 128) * (CinP / BN) * a.T * ksplit;
   const bool occ2 = BN <= 128 && thin_occ2();
   dim3 grid((unsigned)min(total_items, sm_count() * (occ2 ? 2 : 1)));

@@ -666,7 +666,8 @@ _KIND_NAMES = {0: "conv_umma_fprop_kernel<%d>", 1: "conv_umma_fprop_kernel<%d,pa
                2: "conv_umma_fprop_kernel<%d> (row-packed)", 3: "conv_umma_rowconv_kernel<%d>",
                6: "conv_umma_fprop_kernel<%d,halo>", 7: "conv_umma_fprop_kernel<%d,pair,halo>",
                4: "conv_umma_wgrad_kernel<%d> + wgrad_reduce", 5: "conv_umma_wgrad_rows_kernel<%d> + reduce",
-               8: "conv_umma_wgrad_toeplitz_kernel<%d> + reduce", 9: "conv_direct_kernel"}
+               8: "conv_umma_wgrad_toeplitz_kernel<%d> + reduce", 9: "conv_direct_kernel",
+               10: "conv_umma_wgrad_pair_kernel<%d> + wgrad_reduce"}
 
 
 def conv_kernel_name(g, pass_, planar=False, algo=None):
