@@ -23,6 +23,12 @@ namespace mcd {
 using namespace ptx;
 
 constexpr int kThreads = 192;
+// epilogue warpgroups of the CTA-pair kernels.  2 (one per TMEM accumulator buffer) was measured SLOWER on B200
+// (r01b: forward 25.2 -> 29.1 ms, dgrad 24.1 -> 29.4 ms per iteration): 320 threads cap the epilogue at 168
+// registers (270 B of spills) and the extra warps compete with the MMA / TMA warps for issue slots.
+#ifndef MCD_PAIR_EPI_WG
+#define MCD_PAIR_EPI_WG 1
+#endif
 
 struct UmmaMaps {
   CUtensorMap a[4];  // activation maps (parity sub-grids for strided problems)
@@ -142,13 +148,18 @@ struct FpropCfg {
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;              // double-buffered (power of two, <= 512)
   static constexpr int MIN_CTAS = (BN <= 32 || OCC == 2) ? 2 : 1;   // thin tiles: two CTAs per SM
+  // CTA pairs: TWO epilogue warpgroups, one per TMEM accumulator buffer (even / odd tiles), so that the epilogue of
+  // tile i+1 starts while tile i's is still running (the fused dgrad epilogue of the 256-channel layers is longer
+  // than their main loop)
+  static constexpr int EPI_WG = (PAIR && MCD_PAIR_EPI_WG == 2) ? 2 : 1;
+  static constexpr int THREADS = 64 + 128 * EPI_WG;
 };
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
 // registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
 template <int BN, bool PAIR, int OCC = 1, bool HALO = false>
-__global__ void __launch_bounds__(kThreads, FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
+__global__ void __launch_bounds__(FpropCfg<BN, PAIR, OCC>::THREADS, FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
   using Cfg = FpropCfg<BN, PAIR, OCC>;
   static_assert(!PAIR || BN == 256, "CTA pairs run the 256-channel tile only");
@@ -175,7 +186,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   // PAIR: "tiles" are pairs of pixel tiles; CTA `rank` owns pixel tile 2 * (tile / tiles_n) + rank
   const int total_tiles = PAIR ? ((a.tiles_m + 1) / 2) * a.tiles_n : a.tiles_m * a.tiles_n;
   if (stat_sm)
-    for (int i = threadIdx.x; i < 2 * a.rows; i += kThreads) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * a.rows; i += Cfg::THREADS) sstat[i] = 0.f;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.a[0]);
@@ -356,9 +367,12 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int ncover = a.planar ? a.rows : a.Cd_s;
-    int acc = 0; uint32_t acc_phase = 0;
+    const int wg = (warp - 2) >> 2;                // epilogue warpgroup (0 unless EPI_WG == 2)
+    int acc = Cfg::EPI_WG == 2 ? wg : 0; uint32_t acc_phase = 0;
+    int tile_no = 0;
     SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
     while (it.next()) {
+      if (Cfg::EPI_WG == 2 && ((tile_no++ & 1) != wg)) continue;   // the other warpgroup's accumulator
       const bool sk_dump = it.kb0 > 0;             // stream-K: tail k-blocks of a tile another CTA owns
       const bool sk_merge = it.kb1 < kblocks;      // stream-K: this CTA owns the tile, CTA+1 did the tail
       int mt = PAIR ? 2 * (it.tile / a.tiles_n) + (int)rank : it.tile / a.tiles_n;
@@ -534,7 +548,8 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         if (PAIR && rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (Cfg::EPI_WG == 2) acc_phase ^= 1;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -545,7 +560,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
   if (stat_sm && blockIdx.x < (PAIR ? 2 * total_tiles : total_tiles))
-    for (int i = threadIdx.x; i < 2 * a.rows; i += kThreads) atomicAdd(a.stats + i, sstat[i]);
+    for (int i = threadIdx.x; i < 2 * a.rows; i += Cfg::THREADS) atomicAdd(a.stats + i, sstat[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1212,7 +1227,7 @@ static int launch_fprop_pair(const UmmaMaps& maps, const FpropArgs& a, int pairs
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(2 * pairs));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr;
@@ -1241,7 +1256,7 @@ static int launch_fprop_halo(const UmmaMaps& maps, const FpropArgs& a, int grid,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr;

@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libmcd_sm100.so")
+# MCD_LIB_PATH: an alternative build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("MCD_LIB_PATH") or os.path.join(PKG_DIR, "libmcd_sm100.so")
 ABI_VERSION = 13
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
