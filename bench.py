@@ -306,6 +306,44 @@ def run_ours(args):
                        "(a CUDA-graph replay cannot be bracketed per kernel); algorithmic FLOPs = 2*N*Ho*Wo*Cout*Cin*R*S",
                 "kernels": {k: {"ms": round(v["ms"], 3), "tflops": round(v["flop"] / (v["ms"] * 1e-3) / 1e12, 1),
                                 "n": v["n"]} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+    # ---- extras (per-phase and inference throughput); never allowed to break the main line ----------
+    extras = {}
+    try:
+        step.phase_events = []
+        step(src_d, lbl_d, tgt_d)           # one eager iteration, wgrad overlapped as in the graph
+        torch.cuda.synchronize()
+        ev, step.phase_events = step.phase_events, None
+        ph = {}
+        for (n0_, e0_), (n1_, e1_) in zip(ev[:-1], ev[1:]):
+            ph[n1_] = e0_.elapsed_time(e1_)
+        c_ms = [v for k, v in ph.items() if k.startswith("C")]
+        extras["phases_eager_ms"] = {k: round(v, 3) for k, v in ph.items()}
+        extras["phases_pairs_per_s"] = {"A": B / (ph["A"] * 1e-3), "B": B / (ph["B"] * 1e-3),
+                                        "C": B / (sum(c_ms) / len(c_ms) * 1e-3)}
+        extras["phases_note"] = ("device time between CUDA events at the phase boundaries of ONE eager iteration on "
+                                 "this rank; B includes the target forward that phase C[0] re-uses, so C0 is backward only")
+        # inference (adapt_tester.py:104-124): eval-mode forward of G + both heads, argmax over the 40 valid classes
+        import util as mcd_util
+        for m in models:
+            m.eval()
+        mg, mf1, mf2 = models
+
+        def infer():
+            with torch.no_grad():
+                feat = mg(tgt_d)
+                out = mf1(feat) + mf2(feat)
+                return mcd_util.predict_labels(out, N_CLASS - 1), mcd_util.calc_entropy(out)
+        for _ in range(2):
+            infer()
+        ms_inf = timed(infer, 3)
+        for m in models:
+            m.train()
+        extras["inference"] = {"images_per_s": B * world / (ms_inf * 1e-3), "ms_per_batch": ms_inf, "batch_per_gpu": B,
+                               "what": "eval-mode DRN-D-38 6ch forward + 2 heads + argmax(40 classes) + entropy, eager "
+                                       "launches, inputs resident", "algorithmic_gflop_per_image": G_FWD_GF,
+                               "tensor_util": G_FWD_GF * 1e-3 * B / (ms_inf * 1e-3) / pk["sustained"]}
+    except Exception as exc:      # noqa: BLE001
+        extras["error"] = repr(exc)[:300]
     if rank != 0:
         return
     pairs = B * world
@@ -325,6 +363,7 @@ def run_ours(args):
         "roofline": roof,
         "tensor_util_of_step": ITER_TFLOP_PER_PAIR * B / (ms * 1e-3) / pk["sustained"],
         "algorithmic_tflop_per_pair": ITER_TFLOP_PER_PAIR,
+        "extras": extras,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample()

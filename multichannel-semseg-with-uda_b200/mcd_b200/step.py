@@ -46,6 +46,7 @@ class MCDStep:
         self.sync_g = parallel.GradSync(g_params, process_group, bucket_mb)
         self.sync_f = parallel.GradSync(f_params, process_group, bucket_mb)
         self._arena = None
+        self.phase_events = None       # a list: (phase name, CUDA event) appended at every phase boundary (bench.py)
         self._packer_g = None
         self._fused_g = None
         self.fused_sgd = fused_sgd     # optimizer_g.step() + weight re-pack as one kernel (plain momentum SGD only)
@@ -177,8 +178,15 @@ class MCDStep:
         loss.backward()
         self._dg.join(self._dev)
 
+    def _mark(self, name):
+        if self.phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.phase_events.append((name, e))
+
     def _iteration(self, crit, src_imgs, src_lbls, tgt_imgs):
         # ---- A: source supervised; updates G, F1, F2
+        self._mark("start")
         self.sync_g.zero_and_arm(), self.sync_f.zero_and_arm()
         o1, o2 = self._heads(self._gen(src_imgs))
         loss = crit(o1, src_lbls) + crit(o2, src_lbls)
@@ -186,6 +194,7 @@ class MCDStep:
         c_loss = loss.detach()
         self.sync_g.wait(), self.sync_f.wait()
         self._step_g(), self.optimizer_f.step()
+        self._mark("A")
         # ---- B: classifiers maximise the discrepancy on target; only optimizer_f steps
         self.sync_f.zero_and_arm()
         if self.exact:
@@ -211,6 +220,7 @@ class MCDStep:
         self._backward(loss)
         self.sync_f.wait()
         self.optimizer_f.step()
+        self._mark("B")
         # ---- C x num_k: generator minimises the discrepancy; only optimizer_g steps
         #      (classifier gradients of this phase are zeroed before use at adapt_trainer.py:163-164, so unless
         #       exact_reference_backward is set they are not computed at all)
@@ -227,6 +237,7 @@ class MCDStep:
             self._backward(loss)
             self.sync_g.wait()
             self._step_g()
+            self._mark("C%d" % k)
         if not self.exact:
             for p in self.sync_f.params:
                 p.requires_grad_(True)

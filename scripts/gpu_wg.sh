@@ -9,10 +9,10 @@ run() {
 import json,sys
 d=json.load(open('gpurun_out/bench_$2.json'))
 k=d['roofline']['kernels']
-print('$2', round(d['value'],2), round(d['ms_per_step'],2), round(d['e2e']['value'],2), d['clocks']['sm_mhz'], {n[10:42]:(v['ms'],v['tflops']) for n,v in k.items() if 'pair' in n})
+print('$2', round(d['value'],2), round(d['ms_per_step'],2), round(d['e2e']['value'],2), d['clocks']['sm_mhz'], {n[10:42]:(v['ms'],v['tflops']) for n,v in k.items() if 'fprop' in n})
 "
 }
-run MCD_LIB_PATH=$PWD/multichannel-semseg-with-uda_b200/libmcd_sm100_wg1.so wg1
-run MCD_X=1 wg2
-run MCD_LIB_PATH=$PWD/multichannel-semseg-with-uda_b200/libmcd_sm100_wg1.so wg1b
-run MCD_X=1 wg2b
+run MCD_LIB_PATH=$PWD/multichannel-semseg-with-uda_b200/libmcd_sm100_prev.so prev
+run MCD_X=1 new
+run MCD_LIB_PATH=$PWD/multichannel-semseg-with-uda_b200/libmcd_sm100_prev.so prevb
+run MCD_X=1 newb
