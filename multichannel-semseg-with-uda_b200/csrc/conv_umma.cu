@@ -26,6 +26,9 @@ constexpr int kThreads = 192;
 // epilogue warpgroups of the CTA-pair kernels.  2 (one per TMEM accumulator buffer) was measured SLOWER on B200
 // (r01b: forward 25.2 -> 29.1 ms, dgrad 24.1 -> 29.4 ms per iteration): 320 threads cap the epilogue at 168
 // registers (270 B of spills) and the extra warps compete with the MMA / TMA warps for issue slots.
+#ifndef MCD_ACCSTAT
+#define MCD_ACCSTAT 32     /* widest tile that keeps per-thread statistics (0 = off) */
+#endif
 #ifndef MCD_PAIR_EPI_WG
 #define MCD_PAIR_EPI_WG 1
 #endif
@@ -148,12 +151,36 @@ struct FpropCfg {
   static constexpr int ACC_COLS = BN < 32 ? 32 : BN;          // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;              // double-buffered (power of two, <= 512)
   static constexpr int MIN_CTAS = (BN <= 32 || OCC == 2) ? 2 : 1;   // thin tiles: two CTAs per SM
+  // ACCSTAT: tiles of <= 64 channels have ONE channel tile (tiles_n == 1), so every tile of a persistent CTA covers
+  // the same channels: each epilogue thread keeps its BatchNorm partial sums in registers across ALL its tiles and
+  // the warp transpose-reduce runs once per kernel instead of once per tile and 32-channel chunk (these layers have
+  // 9 - 36 k-blocks of MMA work per tile, the per-tile butterfly made their epilogue the bottleneck)
+  static constexpr bool ACCSTAT = !PAIR && BN <= MCD_ACCSTAT;
+  static constexpr int ACC_N = BN < 32 ? 32 : BN;
   // CTA pairs: TWO epilogue warpgroups, one per TMEM accumulator buffer (even / odd tiles), so that the epilogue of
   // tile i+1 starts while tile i's is still running (the fused dgrad epilogue of the 256-channel layers is longer
   // than their main loop)
   static constexpr int EPI_WG = (PAIR && MCD_PAIR_EPI_WG == 2) ? 2 : 1;
   static constexpr int THREADS = 64 + 128 * EPI_WG;
 };
+
+// column sums over the 32 lanes (pixels) of a warp for 32 columns: butterfly transpose-reduce, lane j ends up with
+// the totals of column j in s1[0] / s2[0]
+__device__ __forceinline__ void warp_colsum32(float* s1, float* s2, int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      float send1 = up ? s1[i] : s1[i + step];
+      float keep1 = up ? s1[i + step] : s1[i];
+      s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
+      float send2 = up ? s2[i] : s2[i + step];
+      float keep2 = up ? s2[i + step] : s2[i];
+      s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+    }
+  }
+}
 
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
@@ -370,6 +397,9 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     const int wg = (warp - 2) >> 2;                // epilogue warpgroup (0 unless EPI_WG == 2)
     int acc = Cfg::EPI_WG == 2 ? wg : 0; uint32_t acc_phase = 0;
     int tile_no = 0;
+    float as1[Cfg::ACCSTAT ? Cfg::ACC_N : 1], as2[Cfg::ACCSTAT ? Cfg::ACC_N : 1];
+#pragma unroll
+    for (int j = 0; j < (Cfg::ACCSTAT ? Cfg::ACC_N : 1); ++j) { as1[j] = 0.f; as2[j] = 0.f; }
     SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
     while (it.next()) {
       if (Cfg::EPI_WG == 2 && ((tile_no++ & 1) != wg)) continue;   // the other warpgroup's accumulator
@@ -442,7 +472,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         asm volatile("bar.sync 1, 128;" ::: "memory");
         part = a.sk_partial + ((int64_t)(blockIdx.x + 1) * (BN / 32) * 128 + m) * 32;
       }
-#pragma unroll 1
+#pragma unroll(Cfg::ACCSTAT ? 2 : 1)
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= ncover) break;   // warp-uniform
         if (extras && c0 > 0) prefetch(c0);
@@ -509,7 +539,18 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
             }
           }
         }
-        if (a.stats) {
+        if (Cfg::ACCSTAT) { if (a.stats) {
+          // per-thread partial sums, reduced once after the last tile (n0 == 0: one channel tile)
+          if (pvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < Cfg::ACC_N) {
+                as1[c0 + j] += v[j];
+                as2[c0 + j] = a.bn_y ? as2[c0 + j] + vy[j] : fmaf(v[j], v[j], as2[c0 + j]);
+              }
+            }
+          }
+        } } else if (a.stats) {
           // column sums over the 32 pixels of this warp: butterfly transpose-reduce, lane j ends up
           // holding column j.
           float s1[32], s2[32];
@@ -519,19 +560,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
             s1[j] = x;
             s2[j] = a.bn_y ? (pvalid ? vy[j] : 0.f) : x * x;
           }
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1) {
-            const bool up = (lane & step) != 0;
-#pragma unroll
-            for (int i = 0; i < step; ++i) {
-              float send1 = up ? s1[i] : s1[i + step];
-              float keep1 = up ? s1[i + step] : s1[i];
-              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
-              float send2 = up ? s2[i] : s2[i + step];
-              float keep2 = up ? s2[i + step] : s2[i];
-              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
-            }
-          }
+          warp_colsum32(s1, s2, lane);
           int c = n0 + c0 + lane;
           if (c < a.rows) {
             float* dst = stat_sm ? sstat : a.stats;
@@ -550,6 +579,18 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       }
       if (Cfg::EPI_WG == 2) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (Cfg::ACCSTAT && a.stats) {
+#pragma unroll
+      for (int cb = 0; cb < Cfg::ACC_N; cb += 32) {
+        warp_colsum32(as1 + cb, as2 + cb, lane);
+        const int c = cb + lane;
+        if (c < a.rows) {
+          float* dst = stat_sm ? sstat : a.stats;
+          atomicAdd(dst + c, as1[cb]);
+          atomicAdd(dst + a.rows + c, as2[cb]);
+        }
+      }
     }
   }
 
@@ -1406,7 +1447,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   const bool occ2 = (BN == 64 || BN == 128) && thin_occ2() && !want_sk;
   const int slots = sm_count() * ((BN <= 32 || occ2) ? 2 : 1);    // persistent CTAs per SM (FpropCfg::MIN_CTAS)
   G = min(a.tiles_m * a.tiles_n, slots);
-  if (ex.sk_partial && ex.sk_flags) {
+  if (ex.sk_partial && ex.sk_flags && BN > MCD_ACCSTAT) {   // per-thread statistics need whole tiles per CTA
     int units = 0, g2 = 0;
     if (streamk_plan(a.tiles_m * a.tiles_n, a.ntaps * a.kchunks, BN, p.packed, &g2, &units)) {
       G = g2; a.sk_units = units;
