@@ -27,7 +27,7 @@ constexpr int kThreads = 192;
 // (r01b: forward 25.2 -> 29.1 ms, dgrad 24.1 -> 29.4 ms per iteration): 320 threads cap the epilogue at 168
 // registers (270 B of spills) and the extra warps compete with the MMA / TMA warps for issue slots.
 #ifndef MCD_ACCSTAT
-#define MCD_ACCSTAT 32     /* widest tile that keeps per-thread statistics (0 = off) */
+#define MCD_ACCSTAT 0      /* widest tile that keeps per-thread statistics (0 = off, 32 / 64 under test) */
 #endif
 #ifndef MCD_PAIR_EPI_WG
 #define MCD_PAIR_EPI_WG 1
