@@ -26,12 +26,13 @@ constexpr int RC_PLANE = RC_SEG * 16;    // bytes of one {8 channels x 136 pixel
 
 struct RowconvArgs {
   int N, H, W, tiles_w, total_tiles;
-  int R, HC, SP;            // filter rows, 8-channel halves of the source, padded taps per row (4 or 8)
+  int R, HC, SP, S;         // filter rows, 8-channel halves of the source, padded taps per row (4 or 8), taps
   int roff, woff;           // source row / pixel offset of tap (r=0, s=0) relative to the output pixel
   int NB;                   // GEMM N: produced channels padded to 16
   int rows, Cd_s;           // produced channels, destination channel stride
   int stages, stage_bytes, w_bytes;
   int planar;               // 1: out is planar fp32 [N][rows][H][W]
+  int wide16;               // 16-channel source staged as ONE 32-byte-swizzled plane per filter row (see below)
   const float* bias;
   float* stats;
   const __nv_bfloat16* addend;     // epilogue extras, see conv_plan.h EpiExtra
@@ -40,6 +41,17 @@ struct RowconvArgs {
   void* out;
   const __nv_bfloat16* wpacked;   // [R][HC*SP][NB/8][8][8] bf16, smem-ready no-swizzle K-major B operand
 };
+
+// 32-byte swizzle, K-major or MN-major: rows of 32 B (16 bf16), 8-row groups `sbo_bytes` apart, atoms `lbo_bytes` apart
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;     // layout type SWIZZLE_32B
+  return d;
+}
 
 __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -93,10 +105,18 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = stage0 + stage * a.stage_bytes;
         mbar_expect_tx(&full_bar[stage], planes * RC_PLANE);
-        for (int r = 0; r < a.R; ++r)
-          for (int hf = 0; hf < a.HC; ++hf)
-            tma_load_4d(st + (r * a.HC + hf) * RC_PLANE, &xmap, &full_bar[stage], hf * 8, wt * 128 + a.woff,
-                        h + r + a.roff, n);
+        if (a.wide16) {
+          // 16-channel source: the pixel (32 B) is the swizzle-32B row; a tap shift is a ROW shift of the
+          // descriptor start, legal because the swizzle XOR comes from absolute smem address bits.  Half the TMA
+          // box rows (136 x 32 B instead of 2 x 136 x 16 B per filter row) and one MMA per tap.
+          for (int r = 0; r < a.R; ++r)
+            tma_load_4d(st + r * 2 * RC_PLANE, &xmap, &full_bar[stage], 0, wt * 128 + a.woff, h + r + a.roff, n);
+        } else {
+          for (int r = 0; r < a.R; ++r)
+            for (int hf = 0; hf < a.HC; ++hf)
+              tma_load_4d(st + (r * a.HC + hf) * RC_PLANE, &xmap, &full_bar[stage], hf * 8, wt * 128 + a.woff,
+                          h + r + a.roff, n);
+        }
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -115,7 +135,19 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
         const uint32_t st = smem_u32(stage0 + stage * a.stage_bytes);
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * NB);
         uint32_t first = 1;
-        for (int p = 0; p < planes; ++p) {
+        if (a.wide16) {
+          for (int r = 0; r < a.R; ++r) {
+            for (int tap = 0; tap < a.S; ++tap) {
+              // A: K = the 16 channels of pixel m + tap; B: k-groups (half 0, tap), (half 1, tap) are SP groups apart
+              const uint64_t adesc = smem_desc_sw32(st + r * 2 * RC_PLANE + tap * 32, 0, 256);
+              const uint64_t bdesc = smem_desc_nosw(wbase + (uint32_t)(r * 2 * a.SP + tap) * kg_bytes,
+                                                    (uint32_t)a.SP * kg_bytes, 128);
+              umma_bf16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+        }
+        for (int p = 0; p < (a.wide16 ? 0 : planes); ++p) {
           for (int kk = 0; kk < a.SP / 2; ++kk) {
             // A: k-groups = taps 2kk, 2kk+1 -> pixels m+2kk, m+2kk+1 (LBO = one pixel = 16 B, SBO = 8 pixels)
             const uint64_t adesc = smem_desc_nosw(st + p * RC_PLANE + kk * 32, 16, 128);
@@ -259,6 +291,9 @@ struct ToepArgs {
   int R, HC, nacc;          // filter rows, 8-channel halves of x, accumulators = R * HC
   int roff, woff;           // x row / pixel offset of tap (0, 0) relative to the output pixel (-pad)
   int NB, DC;               // GEMM N = dY channel stride (16 / 32), dY planes = NB / 8
+  int wide16;               // 16-channel x staged as ONE 32-byte-swizzled plane per filter row: M = 4 taps x 16 ch
+  int dy32;                 // NB == 16: dY staged as 32-byte-swizzled pixel rows (one box instead of two planes)
+  int xplane_bytes, dy_off; // bytes of one x plane, offset of the dY region inside a stage
   int stages, stage_bytes, tmem_cols;
   float* ws;
 };
@@ -285,7 +320,7 @@ conv_umma_wgrad_toeplitz_kernel(const __grid_constant__ CUtensorMap xmap, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int dy_off = a.nacc * RC_PLANE;
+  const int dy_off = a.dy_off;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -296,13 +331,22 @@ conv_umma_wgrad_toeplitz_kernel(const __grid_constant__ CUtensorMap xmap, const 
         const int n = tile / (a.tiles_w * a.H);
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * a.stage_bytes;
-        mbar_expect_tx(&full_bar[stage], a.stage_bytes);
-        for (int r = 0; r < a.R; ++r)
-          for (int hf = 0; hf < a.HC; ++hf)
-            tma_load_4d(st + (r * a.HC + hf) * RC_PLANE, &xmap, &full_bar[stage], hf * 8, wt * 128 + a.woff,
-                        h + r + a.roff, n);
-        for (int d = 0; d < a.DC; ++d)
-          tma_load_4d(st + dy_off + d * 2048, &dymap, &full_bar[stage], d * 8, wt * 128, h, n);
+        mbar_expect_tx(&full_bar[stage], a.nacc * a.xplane_bytes + a.DC * 2048);
+        if (a.wide16) {
+          for (int r = 0; r < a.R; ++r)
+            tma_load_4d(st + r * a.xplane_bytes, &xmap, &full_bar[stage], 0, wt * 128 + a.woff, h + r + a.roff, n);
+        } else {
+          for (int r = 0; r < a.R; ++r)
+            for (int hf = 0; hf < a.HC; ++hf)
+              tma_load_4d(st + (r * a.HC + hf) * RC_PLANE, &xmap, &full_bar[stage], hf * 8, wt * 128 + a.woff,
+                          h + r + a.roff, n);
+        }
+        if (a.dy32) {
+          tma_load_4d(st + dy_off, &dymap, &full_bar[stage], 0, wt * 128, h, n);
+        } else {
+          for (int d = 0; d < a.DC; ++d)
+            tma_load_4d(st + dy_off + d * 2048, &dymap, &full_bar[stage], d * 8, wt * 128, h, n);
+        }
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -317,9 +361,13 @@ conv_umma_wgrad_toeplitz_kernel(const __grid_constant__ CUtensorMap xmap, const 
         const uint32_t st = smem_u32(smem + stage * a.stage_bytes);
         for (int acc = 0; acc < a.nacc; ++acc) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {       // 128 pixels = 8 x UMMA_K(16); 16 pixels = 256 B in both operands
-            const uint64_t adesc = smem_desc_nosw(st + acc * RC_PLANE + j * 256, 128, 16);
-            const uint64_t bdesc = smem_desc_nosw(st + dy_off + j * 256, 128, 2048);
+          for (int j = 0; j < 8; ++j) {       // 128 pixels = 8 x UMMA_K(16) pixels
+            // A (x): 8-channel plane: 8-element groups ONE pixel (16 B) apart, 8-pixel K groups 128 B apart;
+            //        32-byte-swizzled 16-channel rows: 16-element atoms one pixel (32 B) apart, K groups 256 B apart
+            const uint64_t adesc = a.wide16 ? smem_desc_sw32(st + acc * a.xplane_bytes + j * 512, 32, 256)
+                                            : smem_desc_nosw(st + acc * RC_PLANE + j * 256, 128, 16);
+            const uint64_t bdesc = a.dy32 ? smem_desc_sw32(st + dy_off + j * 512, 32, 256)
+                                          : smem_desc_nosw(st + dy_off + j * 256, 128, 2048);
             umma_bf16(tmem_base + (uint32_t)(acc * a.NB), adesc, bdesc, idesc, (first && j == 0) ? 0u : 1u);
           }
         }
@@ -355,9 +403,9 @@ conv_umma_wgrad_toeplitz_kernel(const __grid_constant__ CUtensorMap xmap, const 
   if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-// dw[co][c][r][s] = sum_cta ws[cta][r * HC + c / 8][s * 8 + c % 8][co]; 8 lanes share one output element
+// dw[co][c][r][s] = sum_cta ws[cta][r * HC + c / CG][s * CG + c % CG][co]; 8 lanes share one output element
 __global__ void wgrad_toeplitz_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int ncta, int nacc,
-                                             int HC, int NB, int R, int S, int Cout, int Cin, int accumulate) {
+                                             int HC, int CG, int NB, int R, int S, int Cout, int Cin, int accumulate) {
   const int64_t total = (int64_t)Cout * Cin * R * S;
   const int sub = threadIdx.x & 7;
   for (int64_t i0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; i0 < ((total + 31) & ~int64_t(31));
@@ -367,7 +415,7 @@ __global__ void wgrad_toeplitz_reduce_kernel(const float* __restrict__ ws, float
     const int r = (int)((i / S) % R);
     const int c = (int)((i / ((int64_t)S * R)) % Cin);
     const int co = (int)(i / ((int64_t)S * R * Cin));
-    const int64_t off = ((int64_t)(r * HC + c / 8) * 64 + sx * 8 + c % 8) * NB + co;
+    const int64_t off = ((int64_t)(r * HC + c / CG) * 64 + sx * CG + c % CG) * NB + co;   // CG channels per M group
     const int64_t cstride = (int64_t)nacc * 64 * NB;
     float acc = 0.f;
     for (int k = sub; k < ncta; k += 8) acc += ws[k * cstride + off];
@@ -401,6 +449,13 @@ static EncodeTiledFnR get_encode_r() {
     fn = reinterpret_cast<EncodeTiledFnR>(p);
   }
   return fn;
+}
+
+// MCD_ROWCONV_WIDE16=0: stage 16-channel sources as two 8-channel planes (16-byte TMA rows) as in r01
+static bool rowconv_wide16_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCD_ROWCONV_WIDE16"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 bool rowconv_fprop_ok(const mcd_conv_geom& g) {
@@ -437,8 +492,9 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   a.N = g.N; a.H = g.H; a.W = g.W;
   a.tiles_w = (g.W + 127) / 128;
   a.total_tiles = g.N * g.H * a.tiles_w;
-  a.R = g.R;
+  a.R = g.R; a.S = g.S;
   rowconv_pack_dims(g, mode, &a.HC, &a.SP, &a.NB);
+  a.wide16 = (a.HC == 2 && rowconv_wide16_enabled()) ? 1 : 0;
   a.roff = mode ? -(g.R - 1 - g.pad) : -g.pad;
   a.woff = mode ? -(g.S - 1 - g.pad) : -g.pad;
   a.rows = mode ? g.Cin : g.Cout;
@@ -455,11 +511,11 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   CUtensorMap xmap;
   cuuint64_t dims[4] = {(cuuint64_t)srcC, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
   cuuint64_t strides[3] = {(cuuint64_t)srcCs * 2, (cuuint64_t)g.W * srcCs * 2, (cuuint64_t)g.H * g.W * srcCs * 2};
-  cuuint32_t box[4] = {8, RC_SEG, 1, 1};
+  cuuint32_t box[4] = {a.wide16 ? 16u : 8u, RC_SEG, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, a.wide16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rowconv) failed: %d", (int)r); return MCD_E_CUDA; }
   const int smem_bytes = a.w_bytes + a.stages * a.stage_bytes + 1024 + 256;
   auto kern = a.NB == 16 ? conv_umma_rowconv_kernel<16> : conv_umma_rowconv_kernel<32>;
@@ -523,10 +579,15 @@ int wgrad_toeplitz_launch(const void* x, const void* dy, float* dw, void* ws, si
   a.N = g.N; a.H = g.H; a.W = g.W;
   a.tiles_w = (g.W + 127) / 128;
   a.total_tiles = g.N * g.H * a.tiles_w;
-  a.R = g.R; a.HC = g.Cin_s / 8; a.nacc = a.R * a.HC;
+  a.R = g.R; a.HC = g.Cin_s / 8;
+  a.wide16 = (a.HC == 2 && g.S <= 4 && rowconv_wide16_enabled()) ? 1 : 0;
+  a.nacc = a.wide16 ? a.R : a.R * a.HC;
   a.roff = -g.pad; a.woff = -g.pad;
   a.NB = g.Cout_s; a.DC = g.Cout_s / 8;
-  a.stage_bytes = a.nacc * RC_PLANE + a.DC * 2048;
+  a.dy32 = (a.NB == 16 && rowconv_wide16_enabled()) ? 1 : 0;
+  a.xplane_bytes = a.wide16 ? 2 * RC_PLANE : RC_PLANE;
+  a.dy_off = round_up(a.nacc * a.xplane_bytes, 256);
+  a.stage_bytes = round_up(a.dy_off + a.DC * 2048, 256);
   a.stages = max(2, min(6, (100 * 1024) / a.stage_bytes));
   const int cols = a.nacc * a.NB;
   a.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
@@ -536,19 +597,19 @@ int wgrad_toeplitz_launch(const void* x, const void* dy, float* dw, void* ws, si
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin_s, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin_s * 2, (cuuint64_t)g.W * g.Cin_s * 2, (cuuint64_t)g.H * g.W * g.Cin_s * 2};
-    cuuint32_t box[4] = {8, RC_SEG, 1, 1};
+    cuuint32_t box[4] = {a.wide16 ? 16u : 8u, RC_SEG, 1, 1};
     CUresult r = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, a.wide16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(toeplitz x) failed: %d", (int)r); return MCD_E_CUDA; }
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cout_s, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cout_s * 2, (cuuint64_t)g.W * g.Cout_s * 2, (cuuint64_t)g.H * g.W * g.Cout_s * 2};
-    cuuint32_t box[4] = {8, 128, 1, 1};
+    cuuint32_t box[4] = {a.dy32 ? 16u : 8u, 128, 1, 1};
     CUresult r = enc(&dymap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, a.dy32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(toeplitz dy) failed: %d", (int)r); return MCD_E_CUDA; }
   }
   const int smem_bytes = a.stages * a.stage_bytes + 1024 + 256;
@@ -565,8 +626,8 @@ int wgrad_toeplitz_launch(const void* x, const void* dy, float* dw, void* ws, si
   if (rc != MCD_OK) return rc;
   const int64_t total = (int64_t)g.Cout * g.Cin * g.R * g.S;
   const int rgrid = (int)min64((total * 8 + 255) / 256, 148 * 8);
-  wgrad_toeplitz_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, grid, a.nacc, a.HC, a.NB, g.R, g.S, g.Cout, g.Cin,
-                                                      accumulate);
+  wgrad_toeplitz_reduce_kernel<<<rgrid, 256, 0, st>>>(a.ws, dw, grid, a.nacc, a.wide16 ? 1 : a.HC, a.wide16 ? 16 : 8,
+                                                      a.NB, g.R, g.S, g.Cout, g.Cin, accumulate);
   return check_launch("wgrad_toeplitz_reduce");
 }
 

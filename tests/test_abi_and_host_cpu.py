@@ -35,6 +35,39 @@ def test_library_exports_every_declared_symbol():
     assert lib.mcd_launch_count() == 0
 
 
+def test_kernel_dispatch_is_host_logic():
+    """mcd_conv2d_kernel_id / mcd_conv2d_wgrad_partials are pure host code: which kernel each DRN-D-38 layer gets
+    (kind * 1000 + tile width, include/mcd_sm100.h) at 22 images of 480x640."""
+    from mcd_b200 import abi, ops
+    lib = abi.lib()
+
+    def kid(g, p):
+        return lib.mcd_conv2d_kernel_id(ctypes.byref(g), p, abi.OUT_NHWC_BF16, abi.ALGO_AUTO)
+
+    g0 = ops.conv_geom((22, 8, 480, 640), 6, 16, 7, 7, 1, 1, 3)          # layer0
+    g1 = ops.conv_geom((22, 16, 480, 640), 16, 16, 3, 3, 1, 1, 1)        # layer1
+    g3 = ops.conv_geom((22, 64, 120, 160), 64, 64, 3, 3, 1, 1, 1)        # layer3
+    g4 = ops.conv_geom((22, 128, 60, 80), 128, 128, 3, 3, 1, 1, 1)       # layer4
+    g5 = ops.conv_geom((22, 256, 60, 80), 256, 256, 3, 3, 1, 2, 2)       # layer5 (dilation 2)
+    g6 = ops.conv_geom((22, 512, 60, 80), 512, 512, 3, 3, 1, 4, 4)       # layer6 (dilation 4)
+    gd = ops.conv_geom((22, 256, 60, 80), 256, 512, 1, 1, 1, 1, 0)       # 1x1 downsample: one tap, no halo
+    assert [kid(g, 0) for g in (g0, g1)] == [3016, 3016]                 # row convolution
+    assert [kid(g, 0) for g in (g3, g4)] == [6064, 6128]                 # halo-tile staging, one CTA per tile
+    assert [kid(g, 0) for g in (g5, g6)] == [7256, 7256]                 # CTA pairs + halo
+    assert [kid(g, 1) for g in (g5, g6)] == [7256, 7256]                 # dgrad is the same kernel
+    assert kid(gd, 0) == 1256                                            # CTA pairs, per-tap staging
+    assert [kid(g, 2) for g in (g0, g1)] == [8016, 8016]                 # Toeplitz stem wgrad
+    assert [kid(g, 2) for g in (g3, g4)] == [4064, 4128]
+    assert [kid(g, 2) for g in (g5, g6)] == [10256, 10256]               # CTA-pair wgrad
+    assert kid(g6, 0) != lib.mcd_conv2d_kernel_id(ctypes.byref(g6), 0, abi.OUT_NHWC_BF16, abi.ALGO_DIRECT)
+    # split partial-sum layout [ksplit][T][CoutP][CinP] consumed by mcd_sgd_pack_multi
+    assert ops.wgrad_partial_layout(g6) == (2, 9, 512, 512)
+    assert ops.wgrad_partial_layout(g5) == (8, 9, 256, 256)
+    assert ops.wgrad_partial_layout(g0) is None and ops.wgrad_partial_layout(g1) is None
+    ks, t, coutp, cinp = ops.wgrad_partial_layout(g6)
+    assert lib.mcd_conv2d_wgrad_workspace(ctypes.byref(g6), abi.ALGO_AUTO) == 4 * ks * t * coutp * cinp
+
+
 def test_conv_geom_struct_matches_header():
     from mcd_b200.abi import ConvGeom
     fields = re.search(r"typedef struct mcd_conv_geom \{(.*?)\} mcd_conv_geom;", open(HEADER).read(), re.S).group(1)

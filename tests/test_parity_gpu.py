@@ -338,7 +338,7 @@ def test_tester_argmax_entropy_vs_oracle(cuda_dev):
     assert abs(ent - ent_o) / abs(ent_o) <= 1e-2
 
 
-@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("graph", [False, True, "prefetch"])
 def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
     """mcd_b200.step.MCDStep (dead phase-B backward skipped, phase-B target forward re-used for C[0] with folded
     BatchNorm updates, optional CUDA-graph replay) produces the reference iteration's results."""
@@ -361,7 +361,14 @@ def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
         # 1 eager iteration + 1 graph replay = 2 iterations (capturing does not execute anything)
         step(src, lbl, tgt)
         step.capture(src, lbl, tgt, warmup=0)
-        c, d = step.replay(src, lbl, tgt)
+        if graph == "prefetch":
+            # the e2e path of bench.py: pinned host batch -> staging (copy stream) -> static inputs -> graph
+            host = [t.cpu().pin_memory() for t in (src, lbl, tgt)]
+            step._static[0].zero_()                       # the graph must see the prefetched data, not the captured
+            step.prefetch(*host)
+            c, d = step.replay_prefetched()
+        else:
+            c, d = step.replay(src, lbl, tgt)
     else:
         for _ in range(iters):
             c, d = step(src, lbl, tgt)
