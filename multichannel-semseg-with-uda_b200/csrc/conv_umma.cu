@@ -185,10 +185,15 @@ __device__ __forceinline__ void warp_colsum32(float* s1, float* s2, int lane) {
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i (TMEM ->
 // registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
-template <int BN, bool PAIR, int OCC = 1, bool HALO = false>
+// EXTRAS = false: the forward instantiation, without the addend / ReLU-mask / BatchNorm-backward inputs of the dgrad
+// epilogue (80 fewer live registers: the 168-register two-CTA variants stop spilling)
+template <int BN, bool PAIR, int OCC = 1, bool HALO = false, bool EXTRAS = true>
 __global__ void __launch_bounds__(FpropCfg<BN, PAIR, OCC>::THREADS, FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
   using Cfg = FpropCfg<BN, PAIR, OCC>;
+  const __nv_bfloat16* const x_addend = EXTRAS ? a.addend : nullptr;
+  const __nv_bfloat16* const x_mask = EXTRAS ? a.mask_src : nullptr;
+  const __nv_bfloat16* const x_bny = EXTRAS ? a.bn_y : nullptr;
   static_assert(!PAIR || BN == 256, "CTA pairs run the 256-channel tile only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -419,7 +424,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       // epilogue extras (addend / ReLU mask source / BatchNorm input) of one 32-channel chunk: all loads of a chunk
       // are issued together, and those of the first chunk before waiting for the MMAs, so that their latency
       // overlaps the wait instead of adding up load by load
-      const bool extras = !a.planar && pvalid && !sk_dump && (a.addend || a.mask_src || a.bn_y);
+      const bool extras = !a.planar && pvalid && !sk_dump && (x_addend || x_mask || x_bny);
       const int64_t obase = (((int64_t)n_img * a.Hd + hd) * a.Wd + wd) * a.Cd_s + n0;
       uint4 ea[4], em[4], ey[4];
       auto prefetch = [&](int c0) {
@@ -427,9 +432,9 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         for (int j8 = 0; j8 < 4; ++j8) {
           if (n0 + c0 + j8 * 8 < a.Cd_s) {
             const int64_t off = obase + c0 + j8 * 8;
-            if (a.addend) ea[j8] = __ldg(reinterpret_cast<const uint4*>(a.addend + off));
-            if (a.mask_src) em[j8] = __ldg(reinterpret_cast<const uint4*>(a.mask_src + off));
-            if (a.bn_y) ey[j8] = __ldg(reinterpret_cast<const uint4*>(a.bn_y + off));
+            if (x_addend) ea[j8] = __ldg(reinterpret_cast<const uint4*>(x_addend + off));
+            if (x_mask) em[j8] = __ldg(reinterpret_cast<const uint4*>(x_mask + off));
+            if (x_bny) ey[j8] = __ldg(reinterpret_cast<const uint4*>(x_bny + off));
           }
         }
       };
@@ -513,26 +518,26 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                 float f[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
-                if (a.addend) {
+                if (x_addend) {
                   float r[8];
                   unpack8(ea[j8], r);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) f[k] += r[k];
                 }
-                if (a.mask_src) {
+                if (x_mask) {
                   float r[8];
                   unpack8(em[j8], r);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) f[k] = r[k] > 0.f ? f[k] : 0.f;
                 }
-                if (a.bn_y) {
+                if (x_bny) {
                   float r[8];
                   unpack8(ey[j8], r);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) { v[j8 * 8 + k] = f[k]; vy[j8 * 8 + k] = f[k] * r[k]; }
                 }
                 *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
-              } else if (a.bn_y) {
+              } else if (x_bny) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { v[j8 * 8 + k] = 0.f; vy[j8 * 8 + k] = 0.f; }
               }
@@ -546,7 +551,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
             for (int j = 0; j < 32; ++j) {
               if (c0 + j < Cfg::ACC_N) {
                 as1[c0 + j] += v[j];
-                as2[c0 + j] = a.bn_y ? as2[c0 + j] + vy[j] : fmaf(v[j], v[j], as2[c0 + j]);
+                as2[c0 + j] = x_bny ? as2[c0 + j] + vy[j] : fmaf(v[j], v[j], as2[c0 + j]);
               }
             }
           }
@@ -558,7 +563,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           for (int j = 0; j < 32; ++j) {
             float x = pvalid ? v[j] : 0.f;
             s1[j] = x;
-            s2[j] = a.bn_y ? (pvalid ? vy[j] : 0.f) : x * x;
+            s2[j] = x_bny ? (pvalid ? vy[j] : 0.f) : x * x;
           }
           warp_colsum32(s1, s2, lane);
           int c = n0 + c0 + lane;
@@ -1234,18 +1239,26 @@ bool umma_problem_supported(const TapProblem& p) {
   return true;
 }
 
-template <int BN, int OCC = 1>
-static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
+static inline bool has_extras(const FpropArgs& a) { return a.addend || a.mask_src || a.bn_y; }
+
+template <int BN, int OCC, bool EXTRAS>
+static int launch_fprop_bn_x(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
   using Cfg = FpropCfg<BN, false, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, false, OCC>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("fprop smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
     attr_set = true;
   }
-  conv_umma_fprop_kernel<BN, false, OCC><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_fprop");
+}
+
+template <int BN, int OCC = 1>
+static int launch_fprop_bn(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
+  return has_extras(a) ? launch_fprop_bn_x<BN, OCC, true>(maps, a, grid, st)
+                       : launch_fprop_bn_x<BN, OCC, false>(maps, a, grid, st);
 }
 
 // MCD_THIN_OCC2=0 keeps one persistent CTA per SM for the 64- / 128-channel tiles (A/B measurements)
@@ -1256,11 +1269,12 @@ static bool thin_occ2() {
 }
 
 // CTA-pair variant (clusters of 2): grid = 2 * number of persistent pairs
-static int launch_fprop_pair(const UmmaMaps& maps, const FpropArgs& a, int pairs, cudaStream_t st) {
+template <bool EXTRAS>
+static int launch_fprop_pair_x(const UmmaMaps& maps, const FpropArgs& a, int pairs, cudaStream_t st) {
   using Cfg = FpropCfg<256, true>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<256, true>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<256, true, 1, false, EXTRAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("fprop pair smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
     attr_set = true;
@@ -1275,21 +1289,25 @@ static int launch_fprop_pair(const UmmaMaps& maps, const FpropArgs& a, int pairs
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_fprop_kernel<256, true>, maps, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_fprop_kernel<256, true, 1, false, EXTRAS>, maps, a);
   if (e != cudaSuccess) { set_error("conv_umma_fprop (CTA pairs): %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
   return check_launch("conv_umma_fprop_pair");
+}
+
+static int launch_fprop_pair(const UmmaMaps& maps, const FpropArgs& a, int pairs, cudaStream_t st) {
+  return has_extras(a) ? launch_fprop_pair_x<true>(maps, a, pairs, st) : launch_fprop_pair_x<false>(maps, a, pairs, st);
 }
 
 // ---- halo-tile launches (HALO = true instantiations; dynamic shared memory sized per problem) -------------------
 constexpr int kHaloFixedSmem = 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 1024 * 4 /*BatchNorm staging*/;
 
-template <int BN, bool PAIR, int OCC>
-static int launch_fprop_halo(const UmmaMaps& maps, const FpropArgs& a, int grid, cudaStream_t st) {
+template <int BN, bool PAIR, int OCC, bool EXTRAS>
+static int launch_fprop_halo_x(const UmmaMaps& maps, const FpropArgs& a, int grid, cudaStream_t st) {
   using Cfg = FpropCfg<BN, PAIR, OCC>;
   const int smem_bytes = 2 * a.halo_bytes + a.stages * Cfg::B_BYTES + kHaloFixedSmem;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, PAIR, OCC, true>,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, PAIR, OCC, true, EXTRAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("fprop halo smem attr (%d B): %s", smem_bytes, cudaGetErrorString(e)); return MCD_E_CUDA; }
     attr_bytes = smem_bytes;
@@ -1304,9 +1322,15 @@ static int launch_fprop_halo(const UmmaMaps& maps, const FpropArgs& a, int grid,
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = PAIR ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_fprop_kernel<BN, PAIR, OCC, true>, maps, a);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_fprop_kernel<BN, PAIR, OCC, true, EXTRAS>, maps, a);
   if (e != cudaSuccess) { set_error("conv_umma_fprop (halo): %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
   return check_launch("conv_umma_fprop_halo");
+}
+
+template <int BN, bool PAIR, int OCC>
+static int launch_fprop_halo(const UmmaMaps& maps, const FpropArgs& a, int grid, cudaStream_t st) {
+  return has_extras(a) ? launch_fprop_halo_x<BN, PAIR, OCC, true>(maps, a, grid, st)
+                       : launch_fprop_halo_x<BN, PAIR, OCC, false>(maps, a, grid, st);
 }
 
 // MCD_HALO=0 selects the one-box-per-tap (im2col-style) staging for every layer (A/B measurements)
