@@ -1342,7 +1342,15 @@ static bool halo_enabled() {
 
 // Halo-tile plan of a stride-1, multi-tap problem with >= 64 produced channels: 8 x 16 output tiles, box =
 // tile + the extent of the tap offsets.  Returns false when the problem keeps the per-tap staging.
-static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb) {
+// MCD_THIN_OCC2_DGRAD=1: two CTAs per SM also for the dgrad instantiations (fused-epilogue inputs) of the 64 / 128
+// channel tiles.  Default 0: they need ~250 registers, at 168 they spill ~400 B per thread in the epilogue loop.
+static bool thin_occ2_dgrad() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MCD_THIN_OCC2_DGRAD"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb, bool occ2 = true) {
   if (!halo_enabled() || p.packed || p.smul != 1 || p.ntaps < 2 || BN < 64 || (BN == 256 && !pair)) return false;
   int lo_h = 1 << 20, hi_h = -(1 << 20), lo_w = 1 << 20, hi_w = -(1 << 20);
   for (int t = 0; t < p.ntaps; ++t) {
@@ -1354,7 +1362,7 @@ static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int*
   if (Wb > 256 || hb > 256) return false;
   const int halo_bytes = round_up(Wb * hb * 128, 1024);
   const int b_bytes = (pair ? BN / 2 : BN) * 128;
-  const int limit = (pair ? 224 : 110) * 1024;        // pair: one CTA per SM; 64 / 128 tiles: two CTAs per SM
+  const int limit = ((pair || !occ2) ? 224 : 110) * 1024;   // one CTA per SM, or two (64 / 128 tiles, occ2)
   const int stages = min(8, (limit - kHaloFixedSmem - 2 * halo_bytes) / b_bytes);
   if (stages < 3) return false;
   a->halo_bytes = halo_bytes; a->halo_tx = Wb * hb * 128; a->halo_wb = Wb; a->halo_oh = lo_h; a->halo_ow = lo_w;
@@ -1449,7 +1457,9 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   const bool want_sk = ex.sk_partial && ex.sk_flags;
   const bool pair = BN == 256 && !p.packed && a.tiles_m >= 2 && !want_sk && pair_enabled();
   int halo_hb = 0;
-  if (!want_sk && halo_plan(p, BN, pair, &a, &halo_hb)) {
+  // dgrad instantiations (fused-epilogue inputs) of the 64 / 128 tiles keep one CTA per SM: register budget
+  const bool occ2_ok = thin_occ2() && (!has_extras(a) || thin_occ2_dgrad());
+  if (!want_sk && halo_plan(p, BN, pair, &a, &halo_hb, occ2_ok)) {
     int rc = encode_act_map(&maps.a[0], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, 1, 0, 0, a.halo_wb, halo_hb);
     if (rc != MCD_OK) return rc;
     rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
@@ -1458,9 +1468,12 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
       const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
       return launch_fprop_halo<256, true, 1>(maps, a, 2 * min(pair_tiles, sm_count() / 2), st);
     }
-    const int grid = min(a.tiles_m * a.tiles_n, 2 * sm_count());
-    return BN == 128 ? launch_fprop_halo<128, false, 2>(maps, a, grid, st)
-                     : launch_fprop_halo<64, false, 2>(maps, a, grid, st);
+    const int grid = min(a.tiles_m * a.tiles_n, (occ2_ok ? 2 : 1) * sm_count());
+    if (occ2_ok)
+      return BN == 128 ? launch_fprop_halo<128, false, 2>(maps, a, grid, st)
+                       : launch_fprop_halo<64, false, 2>(maps, a, grid, st);
+    return BN == 128 ? launch_fprop_halo<128, false, 1>(maps, a, grid, st)
+                     : launch_fprop_halo<64, false, 1>(maps, a, grid, st);
   }
   int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
   if (rc != MCD_OK) return rc;
@@ -1468,7 +1481,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
     const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
     return launch_fprop_pair(maps, a, min(pair_tiles, sm_count() / 2), st);
   }
-  const bool occ2 = (BN == 64 || BN == 128) && thin_occ2() && !want_sk;
+  const bool occ2 = (BN == 64 || BN == 128) && occ2_ok && !want_sk;
   const int slots = sm_count() * ((BN <= 32 || occ2) ? 2 : 1);    // persistent CTAs per SM (FpropCfg::MIN_CTAS)
   G = min(a.tiles_m * a.tiles_n, slots);
   if (ex.sk_partial && ex.sk_flags && BN > MCD_ACCSTAT) {   // per-thread statistics need whole tiles per CTA
@@ -1495,14 +1508,14 @@ static bool wgrad_rows_ok(const mcd_conv_geom& g);
 static void wgrad_shape(const mcd_conv_geom& g, int* BN, int* CoutP, int* CinP, int* TH, int* TW,
                         int* ntiles, int* ksplit);
 static bool wgrad_pair(const mcd_conv_geom& g);
-static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb);
+static bool halo_plan(const TapProblem& p, int BN, bool pair, FpropArgs* a, int* Hb, bool occ2);
 // which kernel launch_umma_problem() picks for a problem: tile width BN, *pair = CTA-pair (cta_group::2) variant
 int umma_problem_tile(const TapProblem& p, int planar, int* pair, int* halo) {
   int TH, TW, tiles_m, tiles_n, BN, hb;
   fprop_tiling(p, planar, &TH, &TW, &tiles_m, &tiles_n, &BN);
   *pair = BN == 256 && !p.packed && tiles_m >= 2 && pair_enabled();
   FpropArgs a;
-  *halo = halo_plan(p, BN, *pair != 0, &a, &hb) ? 1 : 0;
+  *halo = halo_plan(p, BN, *pair != 0, &a, &hb, true) ? 1 : 0;
   return BN;
 }
 
