@@ -187,8 +187,14 @@ __device__ __forceinline__ void warp_colsum32(float* s1, float* s2, int lane) {
 // registers -> bf16 / fp32 stores + BatchNorm statistics) overlaps the MMAs of tile i+1.
 // EXTRAS = false: the forward instantiation, without the addend / ReLU-mask / BatchNorm-backward inputs of the dgrad
 // epilogue (80 fewer live registers: the 168-register two-CTA variants stop spilling)
+// the dgrad instantiations of the 16 / 32 channel tiles (layer2 / layer3.0 dgrad with the fused BatchNorm-backward
+// epilogue) spill 300 B at the 168 registers two CTAs per SM leave them: MCD_THIN32_DGRAD_OCC1 gives them one CTA
+#ifndef MCD_THIN32_DGRAD_OCC1
+#define MCD_THIN32_DGRAD_OCC1 0   /* measured: layer2 dgrad 3.9 -> 4.85 ms with one CTA per SM */
+#endif
 template <int BN, bool PAIR, int OCC = 1, bool HALO = false, bool EXTRAS = true>
-__global__ void __launch_bounds__(FpropCfg<BN, PAIR, OCC>::THREADS, FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
+__global__ void __launch_bounds__(FpropCfg<BN, PAIR, OCC>::THREADS,
+                                  (EXTRAS && BN <= 32 && MCD_THIN32_DGRAD_OCC1) ? 1 : FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
   using Cfg = FpropCfg<BN, PAIR, OCC>;
   const __nv_bfloat16* const x_addend = EXTRAS ? a.addend : nullptr;
@@ -1482,7 +1488,8 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
     return launch_fprop_pair(maps, a, min(pair_tiles, sm_count() / 2), st);
   }
   const bool occ2 = (BN == 64 || BN == 128) && occ2_ok && !want_sk;
-  const int slots = sm_count() * ((BN <= 32 || occ2) ? 2 : 1);    // persistent CTAs per SM (FpropCfg::MIN_CTAS)
+  const bool thin32_two = BN <= 32 && !(has_extras(a) && MCD_THIN32_DGRAD_OCC1);
+  const int slots = sm_count() * ((thin32_two || occ2) ? 2 : 1);  // persistent CTAs per SM (see __launch_bounds__)
   G = min(a.tiles_m * a.tiles_n, slots);
   if (ex.sk_partial && ex.sk_flags && BN > MCD_ACCSTAT) {   // per-thread statistics need whole tiles per CTA
     int units = 0, g2 = 0;

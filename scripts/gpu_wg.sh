@@ -9,7 +9,7 @@ run() {
 import json,sys
 d=json.load(open('gpurun_out/bench_$2.json'))
 k=d['roofline']['kernels']
-print('$2', round(d['value'],2), round(d['ms_per_step'],2), round(d['e2e']['value'],2), d['clocks']['sm_mhz'], {n[10:42]:(v['ms'],v['tflops']) for n,v in k.items() if 'fprop' in n and 'dgrad' not in n})
+print('$2', round(d['value'],2), round(d['ms_per_step'],2), round(d['e2e']['value'],2), d['clocks']['sm_mhz'], {n[10:42]:(v['ms'],v['tflops']) for n,v in k.items() if '<16>' in n or '<32>' in n})
 "
 }
 run MCD_LIB_PATH=$PWD/multichannel-semseg-with-uda_b200/libmcd_sm100_prev.so prev
