@@ -32,10 +32,11 @@ def kernel_short_name(n):
     n = re.sub(r"^void ", "", n)
     n = n.replace("mcd::", "")
     n = re.sub(r"\(bool\)", "", n)
-    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(\w+), *(\d+), *(\w+)>", n)
+    m = re.match(r"conv_umma_fprop_kernel<(\d+), *(\w+), *(\d+), *(\w+)(?:, *(\w+))?>", n)
     if m:
         bn, pair, occ, halo = m.group(1), m.group(2) in ("1", "true"), m.group(3), m.group(4) in ("1", "true")
-        return "conv_umma_fprop_kernel<%s%s%s>" % (bn, ",pair" if pair else "", ",halo" if halo else "")
+        inst = "" if m.group(5) is None else (" [dgrad-epilogue inst.]" if m.group(5) in ("1", "true") else " [forward inst.]")
+        return "conv_umma_fprop_kernel<%s%s%s>%s" % (bn, ",pair" if pair else "", ",halo" if halo else "", inst)
     m = re.match(r"conv_umma_wgrad_kernel<(\d+), *(\d+)>", n)
     if m:
         return "conv_umma_wgrad_kernel<%s>" % m.group(1)
@@ -74,7 +75,7 @@ def main():
                     v, u = float(r[idx[c]].replace(",", "")), units[idx[c]].lower()
                     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                 t = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
-                ent = traffic.setdefault(kname, {"dram_bytes_per_launch": [], "grid": []})
+                ent = traffic.setdefault(kname.split(" [")[0], {"dram_bytes_per_launch": [], "grid": []})
                 ent["dram_bytes_per_launch"].append(t)
                 ent["grid"].append(r[idx["Grid Size"]])
             except (KeyError, ValueError):
