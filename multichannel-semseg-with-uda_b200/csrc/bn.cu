@@ -14,8 +14,10 @@ namespace mcd {
 // ---- per-channel reductions ------------------------------------------------------------------
 // MODE 0: stats      : acc0 = sum y, acc1 = sum y^2
 // MODE 1: bwd reduce : g = dz * (z > 0 | !relu); acc0 = sum g, acc1 = sum g*xhat(y), acc2 = sum g*xhat(res)
+// register budgets: the two-rows-in-flight loops need ~90 (apply) / ~110 (backward reduce) registers; tighter launch
+// bounds made them spill inside the streaming loop
 template <int MODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, MODE == 1 ? 2 : 3)
 bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dz,
                  const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ res,
                  const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -180,7 +182,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, double invP,
   save_rstd[c] = rstd;
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
@@ -271,7 +273,7 @@ __device__ __forceinline__ void bn_coeffs(const BnParams& b, int c, int C, doubl
   if (writer) { b.save[c] = mean; b.save[C + c] = rstd; }
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 bn_forward_kernel(const __nv_bfloat16* __restrict__ y, BnParams b1, const __nv_bfloat16* __restrict__ res,
                   BnParams b2, int has_res_bn, int relu, __nv_bfloat16* __restrict__ z, int64_t P, int C, int Cs,
                   double invP, double unbias) {
@@ -366,7 +368,7 @@ __device__ __forceinline__ void bwd_coeffs(const BwdBranch& b, const float* sums
   }
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                     const __nv_bfloat16* __restrict__ y, BwdBranch b1, const float* __restrict__ sums,
                     int relu, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma,
@@ -518,7 +520,7 @@ int mcd_bn_forward(const void* y_nhwc, const float* stats, const float* gamma, c
               res_save_mean_rstd, res_momentum, res_eps, res_training};
   double invP = 1.0 / (double)P;
   double unbias = P > 1 ? (double)P / (double)(P - 1) : 1.0;
-  int grid = rows_grid(P, Cs, 4, 148 * 8);
+  int grid = rows_grid(P, Cs, 4, 148 * 6);
   bn_forward_kernel<<<grid, 256, 4 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, b1, (const __nv_bfloat16*)res_nhwc, b2, has_res_bn, relu,
       (__nv_bfloat16*)z_nhwc, P, C, Cs, invP, unbias);
@@ -533,7 +535,7 @@ int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, con
   MCD_REQUIRE(Cs == C && C % 8 == 0, "bn_apply: needs dense channels, C %% 8 == 0 (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!rscale || (res_nhwc && rshift), "bn_apply: residual affine without residual");
   MCD_REQUIRE(Cs <= 2048, "bn_apply: channel stride %d unsupported", Cs);
-  int grid = rows_grid(P, Cs, 4, 148 * 8);
+  int grid = rows_grid(P, Cs, 4, 148 * 6);
   bn_apply_kernel<<<grid, 256, 4 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, scale, shift, (const __nv_bfloat16*)res_nhwc, rscale, rshift, relu,
       (__nv_bfloat16*)z_nhwc, P, Cs);
@@ -549,7 +551,7 @@ int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhw
   MCD_REQUIRE(!relu || z_nhwc, "bn_bwd_reduce: relu needs z");
   MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_bwd_reduce: needs dense channels (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!res_mean || (res_nhwc && res_rstd), "bn_bwd_reduce: residual stats without residual");
-  int grid = rows_grid(P, Cs, 8, 148 * 3);
+  int grid = rows_grid(P, Cs, 8, 148 * 2);     // two resident blocks per SM (launch bounds): one full wave
   bn_reduce_kernel<1><<<grid, 256, 7 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc,
       (const __nv_bfloat16*)res_nhwc, mean, rstd, res_mean, res_rstd, relu, sums, P, C, Cs);
@@ -574,7 +576,7 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
   BwdBranch b1{gamma, mean, rstd, training};
   BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
   MCD_REQUIRE(Cs <= 2048, "bn_bwd_apply: channel stride %d unsupported", Cs);
-  int grid = rows_grid(P, Cs, 4, 148 * 8);
+  int grid = rows_grid(P, Cs, 4, 148 * 6);
   bn_bwd_apply_kernel<<<grid, 256, 6 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc, (const __nv_bfloat16*)y_nhwc, b1, sums,
       relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, (const __nv_bfloat16*)res_nhwc, b2,

@@ -62,9 +62,14 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-template <int NB>
+// EXTRAS = false: forward instantiation without the dgrad-epilogue inputs (no spills at the 80 registers that four
+// CTAs per SM leave)
+template <int NB, bool EXTRAS = true>
 __global__ void __launch_bounds__(RC_THREADS, NB == 16 ? 4 : 2)
 conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ RowconvArgs a) {
+  const __nv_bfloat16* const x_addend = EXTRAS ? a.addend : nullptr;
+  const __nv_bfloat16* const x_mask = EXTRAS ? a.mask_src : nullptr;
+  const __nv_bfloat16* const x_bny = EXTRAS ? a.bn_y : nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;                                   // packed weights
@@ -182,9 +187,9 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
 #pragma unroll
       for (int j8 = 0; j8 < NB / 8; ++j8) {
         if (pvalid && j8 * 8 < a.Cd_s) {
-          if (a.addend) addv[j8] = __ldg(reinterpret_cast<const uint4*>(a.addend + ooff + j8 * 8));
-          if (a.mask_src) mskv[j8] = __ldg(reinterpret_cast<const uint4*>(a.mask_src + ooff + j8 * 8));
-          if (a.bn_y) yv[j8] = __ldg(reinterpret_cast<const uint4*>(a.bn_y + ooff + j8 * 8));
+          if (x_addend) addv[j8] = __ldg(reinterpret_cast<const uint4*>(x_addend + ooff + j8 * 8));
+          if (x_mask) mskv[j8] = __ldg(reinterpret_cast<const uint4*>(x_mask + ooff + j8 * 8));
+          if (x_bny) yv[j8] = __ldg(reinterpret_cast<const uint4*>(x_bny + ooff + j8 * 8));
         }
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -200,7 +205,7 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
 #pragma unroll
         for (int j = 0; j < NB; ++j) v[j] += (j < a.rows) ? __ldg(a.bias + j) : 0.f;
       }
-      if (want_stats && pvalid && !a.bn_y) {
+      if (want_stats && pvalid && !x_bny) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
       }
@@ -220,19 +225,19 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
             float f[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[c + k] : 0.f;
-            if (a.addend) {
+            if (x_addend) {
               float r8[8];
               unpack8(addv[j8], r8);
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[k] += r8[k];
             }
-            if (a.mask_src) {
+            if (x_mask) {
               float r8[8];
               unpack8(mskv[j8], r8);
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[k] = r8[k] > 0.f ? f[k] : 0.f;
             }
-            if (a.bn_y) {                                    // fused BatchNorm-backward sums: g, g * y
+            if (x_bny) {                                     // fused BatchNorm-backward sums: g, g * y
               float r8[8];
               unpack8(yv[j8], r8);
 #pragma unroll
@@ -518,9 +523,11 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rowconv) failed: %d", (int)r); return MCD_E_CUDA; }
   const int smem_bytes = a.w_bytes + a.stages * a.stage_bytes + 1024 + 256;
-  auto kern = a.NB == 16 ? conv_umma_rowconv_kernel<16> : conv_umma_rowconv_kernel<32>;
-  static int attr_bytes[2] = {0, 0};
-  int& ab = attr_bytes[a.NB == 16 ? 0 : 1];
+  const bool extras = a.addend || a.mask_src || a.bn_y;
+  auto kern = a.NB == 16 ? (extras ? conv_umma_rowconv_kernel<16, true> : conv_umma_rowconv_kernel<16, false>)
+                         : (extras ? conv_umma_rowconv_kernel<32, true> : conv_umma_rowconv_kernel<32, false>);
+  static int attr_bytes[4] = {0, 0, 0, 0};
+  int& ab = attr_bytes[(a.NB == 16 ? 0 : 1) + (extras ? 2 : 0)];
   if (smem_bytes > ab) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("rowconv smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
