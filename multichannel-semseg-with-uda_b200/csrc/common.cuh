@@ -37,6 +37,27 @@ inline int check_launch(const char* what) {
   return MCD_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember the largest size set
+// for (kernel, current device), so that a process that drives several devices (the reference's nn.DataParallel
+// pattern, SURVEY 8b "Threading") configures each of them.  A benign race (two threads setting the same value) is
+// the worst concurrent outcome.
+template <auto Kernel>
+inline int ensure_dyn_smem(int bytes, const char* what) {
+  constexpr int kMaxDev = 64;
+  static int set_bytes[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  const bool tracked = dev < kMaxDev;
+  if (tracked && bytes <= set_bytes[dev]) return MCD_OK;
+  cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(max dynamic smem = %d B): %s", what, bytes, cudaGetErrorString(e));
+    return MCD_E_CUDA;
+  }
+  if (tracked) set_bytes[dev] = bytes;
+  return MCD_OK;
+}
+
 #define MCD_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

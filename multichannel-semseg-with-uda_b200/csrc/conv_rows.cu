@@ -526,13 +526,11 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   const bool extras = a.addend || a.mask_src || a.bn_y;
   auto kern = a.NB == 16 ? (extras ? conv_umma_rowconv_kernel<16, true> : conv_umma_rowconv_kernel<16, false>)
                          : (extras ? conv_umma_rowconv_kernel<32, true> : conv_umma_rowconv_kernel<32, false>);
-  static int attr_bytes[4] = {0, 0, 0, 0};
-  int& ab = attr_bytes[(a.NB == 16 ? 0 : 1) + (extras ? 2 : 0)];
-  if (smem_bytes > ab) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) { set_error("rowconv smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    ab = smem_bytes;
-  }
+  int arc = a.NB == 16 ? (extras ? ensure_dyn_smem<conv_umma_rowconv_kernel<16, true>>(smem_bytes, "conv_umma_rowconv")
+                                 : ensure_dyn_smem<conv_umma_rowconv_kernel<16, false>>(smem_bytes, "conv_umma_rowconv"))
+                       : (extras ? ensure_dyn_smem<conv_umma_rowconv_kernel<32, true>>(smem_bytes, "conv_umma_rowconv")
+                                 : ensure_dyn_smem<conv_umma_rowconv_kernel<32, false>>(smem_bytes, "conv_umma_rowconv"));
+  if (arc != MCD_OK) return arc;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -620,13 +618,8 @@ int wgrad_toeplitz_launch(const void* x, const void* dy, float* dw, void* ws, si
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(toeplitz dy) failed: %d", (int)r); return MCD_E_CUDA; }
   }
   const int smem_bytes = a.stages * a.stage_bytes + 1024 + 256;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes);
-    if (e != cudaSuccess) { set_error("toeplitz wgrad smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    attr_bytes = smem_bytes;
-  }
+  int arc = ensure_dyn_smem<conv_umma_wgrad_toeplitz_kernel>(smem_bytes, "conv_umma_wgrad_toeplitz");
+  if (arc != MCD_OK) return arc;
   const int grid = toeplitz_grid(g);
   conv_umma_wgrad_toeplitz_kernel<<<grid, RC_THREADS, smem_bytes, st>>>(xmap, dymap, a);
   int rc = check_launch("conv_umma_wgrad_toeplitz");

@@ -1250,13 +1250,8 @@ static inline bool has_extras(const FpropArgs& a) { return a.addend || a.mask_sr
 template <int BN, int OCC, bool EXTRAS>
 static int launch_fprop_bn_x(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
   using Cfg = FpropCfg<BN, false, OCC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("fprop smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    attr_set = true;
-  }
+  int arc = ensure_dyn_smem<conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS>>(Cfg::SMEM_BYTES, "conv_umma_fprop");
+  if (arc != MCD_OK) return arc;
   conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_fprop");
 }
@@ -1278,13 +1273,8 @@ static bool thin_occ2() {
 template <bool EXTRAS>
 static int launch_fprop_pair_x(const UmmaMaps& maps, const FpropArgs& a, int pairs, cudaStream_t st) {
   using Cfg = FpropCfg<256, true>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<256, true, 1, false, EXTRAS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("fprop pair smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    attr_set = true;
-  }
+  int arc = ensure_dyn_smem<conv_umma_fprop_kernel<256, true, 1, false, EXTRAS>>(Cfg::SMEM_BYTES, "conv_umma_fprop_pair");
+  if (arc != MCD_OK) return arc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(2 * pairs));
@@ -1311,13 +1301,8 @@ template <int BN, bool PAIR, int OCC, bool EXTRAS>
 static int launch_fprop_halo_x(const UmmaMaps& maps, const FpropArgs& a, int grid, cudaStream_t st) {
   using Cfg = FpropCfg<BN, PAIR, OCC>;
   const int smem_bytes = 2 * a.halo_bytes + a.stages * Cfg::B_BYTES + kHaloFixedSmem;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_fprop_kernel<BN, PAIR, OCC, true, EXTRAS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) { set_error("fprop halo smem attr (%d B): %s", smem_bytes, cudaGetErrorString(e)); return MCD_E_CUDA; }
-    attr_bytes = smem_bytes;
-  }
+  int arc = ensure_dyn_smem<conv_umma_fprop_kernel<BN, PAIR, OCC, true, EXTRAS>>(smem_bytes, "conv_umma_fprop_halo");
+  if (arc != MCD_OK) return arc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -1633,13 +1618,8 @@ static int umma_wgrad_rows(const void* x, const void* dy, float* dw, void* ws, s
   int rc = encode_act_map(&maps.b, dy, g.N, g.Ho, g.Wo, g.Cout, g.Cout_s, 1, 0, 0, 1, TH);
   if (rc != MCD_OK) return rc;
   const int smem_bytes = a.stages * stage_bytes + 1024 + 256;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_rows_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) { set_error("wgrad rows smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    attr_bytes = smem_bytes;
-  }
+  int arc = ensure_dyn_smem<conv_umma_wgrad_rows_kernel>(smem_bytes, "conv_umma_wgrad_rows");
+  if (arc != MCD_OK) return arc;
   conv_umma_wgrad_rows_kernel<<<nsplit, kThreads, smem_bytes, st>>>(maps, a);
   rc = check_launch("conv_umma_wgrad_rows");
   if (rc != MCD_OK) return rc;
@@ -1665,13 +1645,8 @@ size_t umma_wgrad_workspace(const mcd_conv_geom& g) {
 template <int BN, int OCC = 1>
 static int launch_wgrad_bn(const UmmaMaps& maps, const WgradArgs& a, dim3 grid, cudaStream_t st) {
   using Cfg = WgradCfg<BN, OCC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_kernel<BN, OCC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_error("wgrad smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-    attr_set = true;
-  }
+  int arc = ensure_dyn_smem<conv_umma_wgrad_kernel<BN, OCC>>(Cfg::SMEM_BYTES, "conv_umma_wgrad");
+  if (arc != MCD_OK) return arc;
   conv_umma_wgrad_kernel<BN, OCC><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_wgrad");
 }
@@ -1732,13 +1707,8 @@ int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_byt
 
   if (wgrad_pair(g)) {
     const int pair_items = (CoutP / 256) * (CinP / 256) * a.T * ksplit;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(conv_umma_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           WgradPairCfg::SMEM_BYTES);
-      if (e != cudaSuccess) { set_error("wgrad pair smem attr: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
-      attr_set = true;
-    }
+    rc = ensure_dyn_smem<conv_umma_wgrad_pair_kernel>(WgradPairCfg::SMEM_BYTES, "conv_umma_wgrad_pair");
+    if (rc != MCD_OK) return rc;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * min(pair_items, sm_count() / 2)));

@@ -7,6 +7,7 @@
 // One thread owns two horizontally adjacent pixels (4-byte bf16x2 loads, 128 B per warp and channel
 // plane); channel loops re-read the logits from L1/L2, so DRAM sees each logit once per kernel.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mcd {
@@ -180,7 +181,7 @@ diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
 // ---- register-resident variants (C <= kRegC): a thread loads all channels of its pixel pair ONCE (C independent
 // 4-byte loads in flight per tensor), then max / sum-exp / loss / gradients come from registers: one pass over the
 // logits with no dependent re-reads.  Used for the MCD heads (C = 41); wider heads take the multi-pass kernels.
-constexpr int kRegC = 48;
+constexpr int kRegC = 42;   // >= the 41 classes of the MCD heads; wider heads take the multi-pass kernels
 constexpr uint32_t kNegInfPair = 0xFF80FF80u;   // two bf16 -inf: padding channels vanish in max and sum-exp
 
 __device__ __forceinline__ float lo_f(uint32_t u) { return __uint_as_float(u << 16); }
@@ -284,6 +285,48 @@ diff2d_fwd_reg_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* 
   }
   float r = block_sum(lsum, red);
   if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+// register-resident backward of Diff2d (C <= kRegC): both heads' logits of a pixel pair are loaded ONCE, the
+// probabilities exp(v - max) are computed ONCE (kept as half2 like the forward kernel) and both passes - the dot
+// products sum_c sign_c p_c and the gradients - run from registers.  The multi-pass kernel above reads every logit
+// twice and evaluates 4 exp per logit.  Opt-in (MCD_DIFF2D_BWD_REG=1): measured slower than the multi-pass kernel.
+__global__ void __launch_bounds__(128, 2)
+diff2d_bwd_reg_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                      const float* __restrict__ gscale, __nv_bfloat16* __restrict__ da,
+                      __nv_bfloat16* __restrict__ db, float inv_numel, int C, int64_t HW, int64_t npairs) {
+  const float coef = gscale[0] * inv_numel;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW;
+    const int64_t off = n * C * HW + hw;
+    uint32_t ra[kRegC], rb[kRegC];
+    load_pair(a + off, C, HW, ra);
+    load_pair(b + off, C, HW, rb);
+    const float2 ma = reg_max(ra), mb = reg_max(rb);
+    const float2 sa = reg_exp_inplace(ra, ma), sb = reg_exp_inplace(rb, mb);
+    const float ia0 = 1.f / sa.x, ia1 = 1.f / sa.y, ib0 = 1.f / sb.x, ib1 = 1.f / sb.y;
+    float da0 = 0.f, da1 = 0.f, db0 = 0.f, db1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRegC; ++c) {     // padding channels hold exp(-inf) = 0: sign(0 - 0) = 0, no contribution
+      const float2 ea = h2f(ra[c]), eb = h2f(rb[c]);
+      const float pa0 = ea.x * ia0, pb0 = eb.x * ib0, pa1 = ea.y * ia1, pb1 = eb.y * ib1;
+      const float s0 = sgn(pa0 - pb0), s1 = sgn(pa1 - pb1);
+      da0 = fmaf(s0, pa0, da0); db0 = fmaf(s0, pb0, db0);
+      da1 = fmaf(s1, pa1, da1); db1 = fmaf(s1, pb1, db1);
+    }
+#pragma unroll
+    for (int c = 0; c < kRegC; ++c) {
+      if (c < C) {
+        const float2 ea = h2f(ra[c]), eb = h2f(rb[c]);
+        const float pa0 = ea.x * ia0, pb0 = eb.x * ib0, pa1 = ea.y * ia1, pb1 = eb.y * ib1;
+        const float s0 = sgn(pa0 - pb0), s1 = sgn(pa1 - pb1);
+        st2(da + off + c * HW, coef * pa0 * (s0 - da0), coef * pa1 * (s1 - da1));
+        st2(db + off + c * HW, coef * pb0 * (db0 - s0), coef * pb1 * (db1 - s1));
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -485,6 +528,16 @@ int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, const floa
   MCD_CHECK_PLANAR("diff2d_bwd");
   int64_t npairs = (int64_t)N * H * W / 2;
   float inv = (float)(1.0 / ((double)N * C * H * W));
+  static int use_reg = -1;
+  // measured (r01b, 22 pairs): register-resident 836 us vs multi-pass 760 us per launch - 84 live packed logits
+  // + the two passes spill at 255 registers; opt-in only
+  if (use_reg < 0) { const char* e = getenv("MCD_DIFF2D_BWD_REG"); use_reg = (e && e[0] == '1') ? 1 : 0; }
+  if (use_reg && C <= kRegC) {
+    diff2d_bwd_reg_kernel<<<grid_reg(npairs), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (__nv_bfloat16*)da, (__nv_bfloat16*)db, inv, C,
+        (int64_t)H * W, npairs);
+    return check_launch("diff2d_bwd");
+  }
   diff2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (const float4*)stats, (__nv_bfloat16*)da,
         (__nv_bfloat16*)db, inv, C, (int64_t)H * W, npairs);
