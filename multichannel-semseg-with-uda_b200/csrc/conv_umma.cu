@@ -26,6 +26,9 @@ constexpr int kThreads = 192;
 // epilogue warpgroups of the CTA-pair kernels.  2 (one per TMEM accumulator buffer) was measured SLOWER on B200
 // (r01b: forward 25.2 -> 29.1 ms, dgrad 24.1 -> 29.4 ms per iteration): 320 threads cap the epilogue at 168
 // registers (270 B of spills) and the extra warps compete with the MMA / TMA warps for issue slots.
+#ifndef MCD_SPLIT_STATS
+#define MCD_SPLIT_STATS 1
+#endif
 #ifndef MCD_ACCSTAT
 #define MCD_ACCSTAT 0      /* widest tile that keeps per-thread statistics (0 = off, 32 / 64 under test) */
 #endif
@@ -178,6 +181,21 @@ __device__ __forceinline__ void warp_colsum32(float* s1, float* s2, int lane) {
       float send2 = up ? s2[i] : s2[i + step];
       float keep2 = up ? s2[i + step] : s2[i];
       s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, step);
+    }
+  }
+}
+
+// one statistic at a time (32 instead of 64 live sum registers): used by the dgrad-epilogue instantiations, whose
+// register budget is the tightest
+__device__ __forceinline__ void warp_colsum32_single(float* s1, int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      float send1 = up ? s1[i] : s1[i + step];
+      float keep1 = up ? s1[i + step] : s1[i];
+      s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, step);
     }
   }
 }
@@ -561,7 +579,20 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
               }
             }
           }
-        } } else if (a.stats) {
+        } } else if (a.stats && EXTRAS && MCD_SPLIT_STATS) {
+          // dgrad-epilogue instantiations: the two sums one after the other
+          const int c = n0 + c0 + lane;
+          float* dst = stat_sm ? sstat : a.stats;
+          float sA[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sA[j] = pvalid ? v[j] : 0.f;
+          warp_colsum32_single(sA, lane);
+          if (c < a.rows) atomicAdd(dst + c, sA[0]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sA[j] = pvalid ? (x_bny ? vy[j] : v[j] * v[j]) : 0.f;
+          warp_colsum32_single(sA, lane);
+          if (c < a.rows) atomicAdd(dst + a.rows + c, sA[0]);
+        } else if (a.stats) {
           // column sums over the 32 pixels of this warp: butterfly transpose-reduce, lane j ends up
           // holding column j.
           float s1[32], s2[32];
