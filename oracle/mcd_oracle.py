@@ -86,12 +86,18 @@ _STORAGE = None
 
 
 class storage:
-    def __init__(self, dtype):
-        self.dtype = dtype
+    """storage(dtype): every storage point rounds to `dtype`.  Keyword overrides per role (None = no rounding at
+    that point, "same" = `dtype`): y = pre-BatchNorm convolution outputs, w = packed weights, grad = every gradient
+    tensor on the way back, act = unit inputs / outputs and full-resolution logits."""
+
+    def __init__(self, dtype, y="same", w="same", grad="same", act="same"):
+        pick = lambda v: dtype if isinstance(v, str) else v
+        self.cfg = None if dtype is None and all(isinstance(v, str) or v is None for v in (y, w, grad, act)) else \
+            {"act": pick(act), "y": pick(y), "w": pick(w), "grad": pick(grad)}
 
     def __enter__(self):
         global _STORAGE
-        self.prev, _STORAGE = _STORAGE, self.dtype
+        self.prev, _STORAGE = _STORAGE, self.cfg
 
     def __exit__(self, *a):
         global _STORAGE
@@ -100,25 +106,25 @@ class storage:
 
 class _Round(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, dtype, fwd, bwd):
-        ctx.dtype, ctx.bwd = dtype, bwd
-        return x.to(dtype).to(x.dtype) if fwd else x.clone()
+    def forward(ctx, x, fdt, bdt):
+        ctx.bdt = bdt
+        return x.to(fdt).to(x.dtype) if fdt is not None else x.clone()
 
     @staticmethod
     def backward(ctx, g):
-        return (g.to(ctx.dtype).to(g.dtype) if ctx.bwd else g), None, None, None
+        return (g.to(ctx.bdt).to(g.dtype) if ctx.bdt is not None else g), None, None
 
 
-def _q(x):      # stored activation: value and its gradient are rounded
-    return x if _STORAGE is None else _Round.apply(x, _STORAGE, True, True)
+def _q(x, role="act"):      # stored activation: value and its gradient are rounded
+    return x if _STORAGE is None else _Round.apply(x, _STORAGE[role], _STORAGE["grad"])
 
 
 def _qw(w):     # packed weight shadow: rounded copy, fp32 gradient
-    return w if _STORAGE is None else _Round.apply(w, _STORAGE, True, False)
+    return w if _STORAGE is None else _Round.apply(w, _STORAGE["w"], None)
 
 
 def _qg(x):     # fp32 score map whose incoming gradient is stored rounded
-    return x if _STORAGE is None else _Round.apply(x, _STORAGE, False, True)
+    return x if _STORAGE is None else _Round.apply(x, None, _STORAGE["grad"])
 
 
 def _bn(sd, key, x, train):
@@ -136,20 +142,20 @@ def unit_forward(sd, unit, x, bn_train=True, taps=None):
     """one DRN unit of trunk_spec(): conv+BN+ReLU (models/drn.py:195-205) or BasicBlock (models/drn.py:43-59)."""
     if unit[0] == "cbr":
         _, kc, kb, stride, dil, pad = unit
-        y = _q(F.conv2d(x, _qw(sd[kc + ".weight"]), None, stride, pad, dil))
+        y = _q(F.conv2d(x, _qw(sd[kc + ".weight"]), None, stride, pad, dil), "y")
         out = _q(F.relu(_bn(sd, kb, y, bn_train)))
         if taps is not None:
             taps[kc + ":conv"] = y
             taps[kc + ":out"] = out
         return out
     _, p, stride, d1, d2, ds = unit
-    y1 = _q(F.conv2d(x, _qw(sd[p + ".conv1.weight"]), None, stride, d1, d1))
+    y1 = _q(F.conv2d(x, _qw(sd[p + ".conv1.weight"]), None, stride, d1, d1), "y")
     o = _q(F.relu(_bn(sd, p + ".bn1", y1, bn_train)))
-    y2 = _q(F.conv2d(o, _qw(sd[p + ".conv2.weight"]), None, 1, d2, d2))
+    y2 = _q(F.conv2d(o, _qw(sd[p + ".conv2.weight"]), None, 1, d2, d2), "y")
     o = _bn(sd, p + ".bn2", y2, bn_train)
     res = x
     if ds:
-        yd = _q(F.conv2d(x, _qw(sd[p + ".downsample.0.weight"]), None, stride, 0, 1))
+        yd = _q(F.conv2d(x, _qw(sd[p + ".downsample.0.weight"]), None, stride, 0, 1), "y")
         res = _bn(sd, p + ".downsample.1", yd, bn_train)
     out = _q(F.relu(o + res))
     if taps is not None:
@@ -203,9 +209,9 @@ def bilinear_up(x, s):
 def three_layer_decoder(sd, p, x, train=True, fix_bn=False):
     """ThreeLayerDecoder: CBR 3x3 -> CBR 1x1 -> conv 1x1, all with bias (models/dilated_fcn.py:632-658)."""
     bn_train = _bn_train_flag(train, fix_bn)
-    y = _q(F.conv2d(x, _qw(sd[p + ".cbr1.conv.weight"]), sd[p + ".cbr1.conv.bias"], padding=1))
+    y = _q(F.conv2d(x, _qw(sd[p + ".cbr1.conv.weight"]), sd[p + ".cbr1.conv.bias"], padding=1), "y")
     x = _q(F.relu(_bn(sd, p + ".cbr1.bn", y, bn_train)))
-    y = _q(F.conv2d(x, _qw(sd[p + ".cbr2.conv.weight"]), sd[p + ".cbr2.conv.bias"]))
+    y = _q(F.conv2d(x, _qw(sd[p + ".cbr2.conv.weight"]), sd[p + ".cbr2.conv.bias"]), "y")
     x = _q(F.relu(_bn(sd, p + ".cbr2.bn", y, bn_train)))
     return _qg(F.conv2d(x, _qw(sd[p + ".conv3.weight"]), sd[p + ".conv3.bias"]))
 
