@@ -15,12 +15,18 @@
  *     persistent device memory: outputs and workspaces are supplied by the caller.
  *   - `stream` is a cudaStream_t passed as void*; `device` is the CUDA ordinal the pointers live on
  *     (the call is re-entrant and may come from PyTorch's autograd worker thread).
- *   - "nhwc" tensors are bf16, channel count C must be a multiple of 8 (16-byte TMA stride rule);
+ *   - "nhwc" tensors are 16-bit, channel count C must be a multiple of 8 (16-byte TMA stride rule);
  *     "planar" tensors are NCHW-contiguous.  Image geometry is (N, H, W).
- *   - conv weights are consumed in a packed bf16 form produced by mcd_pack_weight():
+ *   - 16-bit formats: FORWARD tensors (x, y, z, residuals: "f16" below) are IEEE half - its 11 significant bits
+ *     keep per-layer activations 8x closer to an fp32 run than bf16 and the ReLU-mask flip rate 8x lower;
+ *     GRADIENT tensors (dy, dx, dz, "bf16" below) are bfloat16 - fp32 range, no loss scaling.  tcgen05.mma needs
+ *     both GEMM operands in ONE format, so every activation that feeds a weight gradient also exists as a bf16
+ *     TWIN (written by the kernel that produces it: mcd_bn_forward / mcd_nchw_f32_to_nhwc); the twin is what
+ *     mcd_conv2d_wgrad reads, and ReLU masks are taken from it (only the sign matters).
+ *   - conv weights are consumed in a packed 16-bit form produced by mcd_pack_weight():
  *         [rows][taps][kc_pad]   kc_pad = round_up(reduce-channels, 64)
- *     fprop : rows = Cout, taps in (r,s) order, reduce-channels = Cin
- *     dgrad : rows = Cin,  taps flipped,        reduce-channels = Cout
+ *     fprop (IEEE half) : rows = Cout, taps in (r,s) order, reduce-channels = Cin
+ *     dgrad (bfloat16)  : rows = Cin,  taps flipped,        reduce-channels = Cout
  */
 #ifndef MCD_SM100_H
 #define MCD_SM100_H
@@ -32,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 13
+#define MCD_ABI_VERSION 14
 
 enum {
   MCD_OK = 0,
@@ -49,9 +55,15 @@ enum {
   MCD_ALGO_UMMA = 2    /* tcgen05/TMEM/TMA implicit GEMM; MCD_E_INVALID if shape unsupported */
 };
 
+/* 16-bit element formats (= the tcgen05 instruction-descriptor codes) */
+enum {
+  MCD_FMT_F16 = 0, /* IEEE half: forward tensors */
+  MCD_FMT_BF16 = 1 /* bfloat16: gradients, wgrad twins */
+};
+
 /* output layout of mcd_conv2d_fprop */
 enum {
-  MCD_OUT_NHWC_BF16 = 0, /* [N,Ho,Wo,Cout] bf16, Cout % 8 == 0 */
+  MCD_OUT_NHWC_BF16 = 0, /* [N,Ho,Wo,Cout] 16-bit nhwc (f16 from fprop), Cout % 8 == 0; name kept from ABI 13 */
   MCD_OUT_PLANAR_F32 = 1 /* [N,Cout,Ho,Wo] fp32 (score maps: seg / decoder heads, any Cout) */
 };
 
@@ -74,14 +86,17 @@ int64_t mcd_launch_count(void);
 int mcd_check_device(int device);
 
 /* ---- layout ----------------------------------------------------------------------------- */
-/* NCHW fp32 -> NHWC bf16 with channel stride Cs (zero fill of channels >= C).  Replaces the
- * implicit layout of `Variable(...).cuda()` inputs (adapt_trainer.py:156-160). */
-int mcd_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cs,
-                              int device, void* stream);
-/* NHWC bf16 (channel stride Cs) -> NCHW fp32 (first C channels). */
-int mcd_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cs,
-                              int device, void* stream);
-/* fp32 OIHW nn.Conv2d weight -> packed bf16.  mode 0 = fprop, 1 = dgrad (see header comment).
+/* NCHW fp32 -> NHWC 16-bit with channel stride Cs (zero fill of channels >= C), as IEEE half (dst_f16) and / or
+ * bfloat16 (dst_bf16): either may be NULL.  Replaces the implicit layout of `Variable(...).cuda()` inputs
+ * (adapt_trainer.py:156-160); gradients entering from fp32 score maps use the bf16 output only. */
+int mcd_nchw_f32_to_nhwc(const float* src, void* dst_f16, void* dst_bf16, int N, int C, int H, int W, int Cs,
+                         int device, void* stream);
+/* NHWC 16-bit (format src_fmt, channel stride Cs) -> NCHW fp32 (first C channels). */
+int mcd_nhwc_to_nchw_f32(const void* src, int src_fmt, float* dst, int N, int C, int H, int W, int Cs,
+                         int device, void* stream);
+/* Re-encode a dense 16-bit tensor in the OTHER format (numel % 8 == 0): creates a missing twin. */
+int mcd_convert16(const void* src, int src_fmt, void* dst, int64_t numel, int device, void* stream);
+/* fp32 OIHW nn.Conv2d weight -> packed 16-bit.  mode 0 = fprop (IEEE half), 1 = dgrad (bfloat16), see header comment.
  * dst holds rows*R*S*kc_pad bf16 where rows = (mode ? Cin : Cout), kc_pad = round_up(mode ? Cout : Cin, 64). */
 int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int mode,
                     int device, void* stream);
@@ -127,7 +142,7 @@ int mcd_conv2d_pack_kind(const mcd_conv_geom* g, int pass, int algo);
 int mcd_conv2d_kernel_id(const mcd_conv_geom* g, int pass, int y_layout, int algo);
 
 /* ---- convolution (nn.Conv2d: models/drn.py:21-23,126-131,171-205; dilated_fcn.py:226-232,632-658,821-823) */
-/* y = conv(x, w) (+ bias).  If `stats` != NULL (fp32 [2*Cout], caller-zeroed) the kernel also
+/* y = conv(x, w) (+ bias); x and the nhwc y are f16, w_packed the mode-0 pack.  If `stats` != NULL (fp32 [2*Cout], caller-zeroed) the kernel also
  * accumulates per-channel sum and sum of squares of y for train-mode BatchNorm. */
 int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias, void* y,
                      int y_layout, float* stats, void* sk_partial, int* sk_flags, const mcd_conv_geom* g,
@@ -140,7 +155,8 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
  * pointer selects the plain tile-per-CTA schedule.  Results do not depend on the schedule beyond fp32 summation
  * order. */
 size_t mcd_conv2d_streamk_workspace(const mcd_conv_geom* g, int pass, int y_layout, int algo, int* n_flags);
-/* dx = conv_transpose(dy, w) (+ add_nhwc): gradient wrt the nhwc input.  w_packed is the mode-1 pack.
+/* dx = conv_transpose(dy, w) (+ add_nhwc): gradient wrt the nhwc input; dy, dx, add are bf16, w_packed is the
+ * mode-1 (bf16) pack, relu_src the bf16 twin of the input, bn_y the f16 pre-BatchNorm tensor.
  * add_nhwc (may be NULL): tensor of dx's geometry added in the epilogue - the gradient that reaches the same
  * activation through the identity shortcut of a BasicBlock (models/drn.py:53-58), saving a separate add pass.
  * The backward of the BatchNorm+ReLU unit that PRODUCED the convolution's input (models/drn.py:47-49,126-131)
@@ -151,7 +167,8 @@ size_t mcd_conv2d_streamk_workspace(const mcd_conv_geom* g, int pass, int y_layo
 int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc, const void* add_nhwc,
                      const void* relu_src_nhwc, const void* bn_y_nhwc, float* bn_sums, void* sk_partial,
                      int* sk_flags, const mcd_conv_geom* g, int algo, int device, void* stream);
-/* dw (fp32 OIHW) = sum_pixels dy (x) x ; dbias (fp32 [Cout], may be NULL).  accumulate = 0 overwrites,
+/* dw (fp32 OIHW) = sum_pixels dy (x) x ; x_nhwc is the bf16 TWIN of the convolution's input, dy bf16;
+ * dbias (fp32 [Cout], may be NULL).  accumulate = 0 overwrites,
  * 1 adds to the existing contents (gradient accumulation straight into param.grad / all-reduce buckets).
  * workspace: mcd_conv2d_wgrad_workspace() bytes.
  * dw_oihw == NULL ("partials only"): the tcgen05 kernel leaves its split partial sums in `workspace` as fp32
@@ -166,7 +183,7 @@ int mcd_conv2d_wgrad(const void* x_nhwc, const void* dy_nhwc, float* dw_oihw, fl
 
 /* ---- BatchNorm2d (+ReLU, +residual)  (nn.BatchNorm2d defaults eps 1e-5 momentum 0.1:
  *      models/drn.py:34-59,129-131,167-169,199-204; --fix_bn: models/model_util.py:305-310) -------- */
-/* per-channel sum / sum-of-squares of an nhwc tensor into caller-zeroed stats[2*C]. */
+/* per-channel sum / sum-of-squares of an f16 nhwc tensor into caller-zeroed stats[2*C]. */
 int mcd_bn_stats(const void* y_nhwc, float* stats, int64_t P, int C, int Cs, int device, void* stream);
 /* training: mean/var from stats (count = P), writes scale/shift (fp32 [C] each), save_mean,
  * save_rstd, and updates running_mean / running_var (unbiased) with `momentum`.
@@ -179,20 +196,22 @@ int mcd_bn_finalize(const float* stats, int64_t P, const float* gamma, const flo
                     int64_t* num_batches_tracked, int C, int device, void* stream);
 /* Fused forward: mcd_bn_finalize (for the main and, when res_save_mean_rstd != NULL, the residual/downsample
  * BatchNorm) + mcd_bn_apply in ONE launch.  save_mean_rstd: fp32 [2*C] out (mean, rstd) for the backward.
- * res_nhwc with res_save_mean_rstd == NULL is an identity residual. */
+ * res_nhwc with res_save_mean_rstd == NULL is an identity residual.  y / res are f16; the result is written as f16
+ * (z_nhwc) and / or as its bf16 twin (zb_nhwc) - either may be NULL. */
 int mcd_bn_forward(const void* y_nhwc, const float* stats, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                    float eps, int training, float* save_mean_rstd, const void* res_nhwc,
                    const float* res_stats, const float* res_gamma, const float* res_beta,
                    float* res_running_mean, float* res_running_var, int64_t* res_num_batches_tracked,
                    float res_momentum, float res_eps, int res_training, float* res_save_mean_rstd, int relu,
-                   void* z_nhwc, int64_t P, int C, int Cs, int device, void* stream);
+                   void* z_nhwc, void* zb_nhwc, int64_t P, int C, int Cs, int device, void* stream);
 /* z = act(scale*y + shift + residual'), residual' = res (identity) or rscale*res + rshift
  * (downsample branch, models/drn.py:53-56); res / rscale may be NULL; relu = 0/1. */
 int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, const void* res_nhwc,
-                 const float* rscale, const float* rshift, int relu, void* z_nhwc, int64_t P, int C,
-                 int Cs, int device, void* stream);
-/* backward reductions: g = dz * (relu ? z > 0 : 1);
+                 const float* rscale, const float* rshift, int relu, void* z_nhwc, void* zb_nhwc, int64_t P,
+                 int C, int Cs, int device, void* stream);
+/* backward (dz, dy, dres bf16; z = the bf16 twin, used as the ReLU mask; y, res f16).
+ * reductions: g = dz * (relu ? z > 0 : 1);
  *   sums[0:C]  = sum g, sums[C:2C] = sum g * xhat(y)   [, sums[2C:3C] = sum g * xhat(res) if res_mean]
  * sums is caller-zeroed fp32 [3*C]. */
 int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc,
@@ -214,13 +233,15 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
 /* ---- classifier heads --------------------------------------------------------------------- */
 /* Depthwise ConvTranspose2d(C,C,16,stride 8,pad 4,groups C,bias=False)
  * (dilated_fcn.py:357-366,465-470,479-491).  x,x2: planar fp32 [N,C,h,w]; w,w2: fp32 [C,1,16,16];
- * out: planar bf16 [N,C,8h,8w].  out = up_w(x) (+ up_w2(x2) when x2 != NULL; if w2 == NULL the
- * same weight is used, i.e. AddFusion up(x1+x2)). */
-int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const float* w2, void* out,
+ * out: planar [N,C,8h,8w], bf16 (out_f32 == 0) or fp32.  out = up_w(x) (+ up_w2(x2) when x2 != NULL; if
+ * w2 == NULL the same weight is used, i.e. AddFusion up(x1+x2)).
+ * Full-resolution tensors ("logits") and their gradients share ONE dtype (autograd's rule): bf16 - half the bytes,
+ * what MCDStep uses - or fp32, the drop-in default (`outputs.data.cpu().numpy()` of adapt_tester.py:114-118). */
+int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const float* w2, void* out, int out_f32,
                        int N, int C, int h, int w_, int device, void* stream);
-/* dx (planar fp32 [N,C,h,w], overwritten) and dw (fp32 [C,256], overwritten) from dout (planar bf16). */
-int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* dx, float* dw, int N,
-                       int C, int h, int w_, int device, void* stream);
+/* dx (planar fp32 [N,C,h,w], overwritten) and dw (fp32 [C,256], overwritten) from dout (planar bf16 / fp32). */
+int mcd_deconv16s8_bwd(const void* dout, int dout_f32, const float* x, const float* w, float* dx, float* dw,
+                       int N, int C, int h, int w_, int device, void* stream);
 /* nn.Upsample(scale_factor=s, mode='bilinear'), align_corners=False (dilated_fcn.py:676,817-819).
  * x planar fp32 [N,C,h,w] -> out planar bf16 (out_f32 == 0) or fp32 [N,C,s*h,s*w]. */
 int mcd_bilinear_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s,
@@ -230,41 +251,48 @@ int mcd_bilinear_up_bwd(const void* dout, int dout_f32, float* dx, int N, int C,
 
 /* ---- per-pixel losses (loss.py:7-13,93-100,131-138; dilated_fcn.py:712,958; util.py:44-48) - */
 /* CrossEntropyLoss2d: log_softmax(dim=1) + NLLLoss2d(weight, mean, ignore_index).
- * logits planar bf16 [N,C,H,W]; target int64 [N,H,W]; weight fp32 [C] or NULL.
+ * logits planar [N,C,H,W] bf16 (f32 == 0) or fp32; target int64 [N,H,W]; weight fp32 [C] or NULL.
  * acc (fp32 [4], caller-zeroed): acc[0] += sum w*nll, acc[1] += sum w, acc[2] += #bad labels. */
-int mcd_ce2d_fwd(const void* logits, const int64_t* target, const float* weight,
+int mcd_ce2d_fwd(const void* logits, int f32, const int64_t* target, const float* weight,
                  int64_t ignore_index, float* acc, int N, int C, int H, int W, int device,
                  void* stream);
-/* dlogits (planar bf16) = gscale[0] * w[y]*(softmax - onehot) / acc[1]; gscale is a device fp32 scalar
+/* dlogits (planar, dtype of logits) = gscale[0] * w[y]*(softmax - onehot) / acc[1]; gscale is a device fp32 scalar
  * (the upstream gradient). */
-int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
+int mcd_ce2d_bwd(const void* logits, int f32, const int64_t* target, const float* weight,
                  int64_t ignore_index, const float* acc, const float* gscale, void* dlogits, int N,
                  int C, int H, int W, int device, void* stream);
 /* Diff2d: mean |softmax(a) - softmax(b)| over N*C*H*W.  acc[0] += sum |.|
  * stats (fp32 [N*H*W*4], may be NULL): per-pixel (max_a, 1/sumexp_a, max_b, 1/sumexp_b) written by the forward
  * and consumed by the backward, which then skips its two statistic passes. */
-int mcd_diff2d_fwd(const void* a, const void* b, float* acc, float* stats, int N, int C, int H, int W,
+int mcd_diff2d_fwd(const void* a, const void* b, int f32, float* acc, float* stats, int N, int C, int H, int W,
                    int device, void* stream);
-int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, const float* stats, void* da, void* db,
-                   int N, int C, int H, int W, int device, void* stream);
-/* F.mse_loss(pred, target) with pred planar bf16, target planar fp32: acc[0] += sum (p-t)^2 */
-int mcd_mse_fwd(const void* pred, const float* target, float* acc, int64_t numel, int device,
+int mcd_diff2d_bwd(const void* a, const void* b, int f32, const float* gscale, const float* stats, void* da,
+                   void* db, int N, int C, int H, int W, int device, void* stream);
+/* F.mse_loss(pred, target) with pred planar bf16 / fp32, target planar fp32: acc[0] += sum (p-t)^2 */
+int mcd_mse_fwd(const void* pred, int f32, const float* target, float* acc, int64_t numel, int device,
                 void* stream);
-int mcd_mse_bwd(const void* pred, const float* target, const float* gscale, void* dpred,
+int mcd_mse_bwd(const void* pred, int f32, const float* target, const float* gscale, void* dpred,
                 int64_t numel, int device, void* stream);
 /* boundary head: p = (sigmoid(h1)+sigmoid(h2)+sigmoid(h3))/3 (dilated_fcn.py:913-923) followed by
- * bce2d (loss.py:131-138).  h* planar bf16 [numel]; target fp32 in {0,1}.
- * tsum (fp32[1], caller-zeroed) receives sum(target) from mcd_bce_target_sum first. */
+ * bce2d (loss.py:131-138).  h* planar bf16 / fp32 [numel]; target fp32 in {0,1}.
+ * tsum (fp32[1]) = sum(target) from mcd_sum_f32, all-reduced by the caller under data parallelism: beta =
+ * 1 - tsum / numel_global is the batch-GLOBAL class balance of loss.py:133 (numel_global <= 0: numel). */
 int mcd_sum_f32(const float* x, float* acc, int64_t numel, int device, void* stream);
-int mcd_sigmoid3_bce_fwd(const void* h1, const void* h2, const void* h3, const float* target,
-                         const float* tsum, float* acc, void* p_out, int64_t numel, int device,
-                         void* stream);
-int mcd_sigmoid3_bce_bwd(const void* h1, const void* h2, const void* h3, const float* target,
+int mcd_sigmoid3_bce_fwd(const void* h1, const void* h2, const void* h3, int f32, const float* target,
+                         const float* tsum, float* acc, void* p_out, int64_t numel, int64_t numel_global,
+                         int device, void* stream);
+int mcd_sigmoid3_bce_bwd(const void* h1, const void* h2, const void* h3, int f32, const float* target,
                          const float* tsum, const float* gscale, void* dh1, void* dh2, void* dh3,
-                         int64_t numel, int device, void* stream);
+                         int64_t numel, int64_t numel_global, int device, void* stream);
+/* bce2d(input, target) on a probability map (loss.py:130-138): p, target fp32 [numel]; acc[0] += sum w * bce with
+ * w = 1 - beta + (2 beta - 1) t and torch's log clamp at -100; dp = gscale / numel * w (p - t) / max(p (1-p), 1e-12). */
+int mcd_bce2d_fwd(const float* p, const float* target, const float* tsum, float* acc, int64_t numel,
+                  int64_t numel_global, int device, void* stream);
+int mcd_bce2d_bwd(const float* p, const float* target, const float* tsum, const float* gscale, float* dp,
+                  int64_t numel, int64_t numel_global, int device, void* stream);
 /* Testers: argmax over channels [0, C_arg) (first max wins, like torch.max) + entropy partial
  * acc[0] += sum_c p*log(p+1e-6) over all C channels (adapt_tester.py:104-124, util.py:44-48). */
-int mcd_argmax_entropy(const void* logits, int64_t* labels, float* acc, int N, int C, int C_arg,
+int mcd_argmax_entropy(const void* logits, int f32, int64_t* labels, float* acc, int N, int C, int C_arg,
                        int H, int W, int device, void* stream);
 
 /* ---- optimiser (models/model_util.py:289-302: SGD momentum / weight decay, torch semantics) - */

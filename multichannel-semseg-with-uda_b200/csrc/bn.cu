@@ -1,4 +1,7 @@
-// bn.cu — BatchNorm2d (+ReLU, +residual) forward / backward on NHWC bf16 activations.
+// bn.cu — BatchNorm2d (+ReLU, +residual) forward / backward on NHWC 16-bit activations.
+// Formats (common.cuh): forward tensors y / res / z are IEEE half (z additionally gets a bf16 twin `zb` for the
+// weight-gradient GEMM of its consumer and as the autograd-visible handle); gradients dz / dy / dres are bf16; the
+// ReLU mask is read from the bf16 twin (only its sign matters).
 // Reference semantics: nn.BatchNorm2d(eps=1e-5, momentum=0.1, affine, track_running_stats) as used by
 // models/drn.py:34-59 (BasicBlock), :129-131, :199-204 and dilated_fcn.py:632-644 (CBR); eval / --fix_bn
 // (models/model_util.py:305-310) uses the running statistics.
@@ -67,13 +70,13 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
       float fy[8];
       const uint4 vy = vyu[u];
       if (MODE == 0) {
-        unpack8(vy, fy);
+        unpack8h(vy, fy);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a0[k] += fy[k]; a1[k] = fmaf(fy[k], fy[k], a1[k]); }
       } else {
         const uint4 vd = vdu[u], vz = vzu[u], vr = vru[u];
         float fd[8], fz[8];
-        unpack8(vy, fy); unpack8(vd, fd); unpack8(vz, fz);
+        unpack8h(vy, fy); unpack8(vd, fd); unpack8(vz, fz);
         float g[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -83,7 +86,7 @@ bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __res
         }
         if (dual) {
           float fr[8];
-          unpack8(vr, fr);
+          unpack8h(vr, fr);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             a2[k] = fmaf(g[k], (fr[k] - co[2 * Cs + c0 + k]) * co[3 * Cs + c0 + k], a2[k]);
@@ -136,7 +139,7 @@ bn_mask_sums_kernel(__nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restr
       }
       if (sums) {
         float fy[8];
-        unpack8(*reinterpret_cast<const uint4*>(bn_y + off), fy);
+        unpack8h(*reinterpret_cast<const uint4*>(bn_y + off), fy);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], fy[k], a1[k]); }
       }
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
-                __nv_bfloat16* __restrict__ z, int64_t P, int Cs) {
+                __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ zb, int64_t P, int Cs) {
   extern __shared__ float co[];  // scale, shift, rscale, rshift : 4 * Cs
   for (int c = threadIdx.x; c < Cs; c += 256) {
     co[c] = scale[c]; co[Cs + c] = shift[c];
@@ -223,12 +226,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
       const int64_t pu = p + u * step;
       if (pu >= P) break;
       float f[8];
-      unpack8(vy[u], f);
+      unpack8h(vy[u], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
       if (res) {
         float r[8];
-        unpack8(vr[u], r);
+        unpack8h(vr[u], r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], rc[k], rf[k]);
       }
@@ -236,7 +239,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
       }
-      *reinterpret_cast<uint4*>(z + pu * Cs + c0) = pack8(f);
+      if (z) *reinterpret_cast<uint4*>(z + pu * Cs + c0) = pack8h(f);          // IEEE half: the next fprop's operand
+      if (zb) *reinterpret_cast<uint4*>(zb + pu * Cs + c0) = pack8(f);         // bf16 twin: wgrad operand / mask
     }
   }
 }
@@ -276,8 +280,8 @@ __device__ __forceinline__ void bn_coeffs(const BnParams& b, int c, int C, doubl
 // (256, 4): measured - three blocks per SM (no spill) was 21 % slower than four with a 12-byte spill
 __global__ void __launch_bounds__(256, 4)
 bn_forward_kernel(const __nv_bfloat16* __restrict__ y, BnParams b1, const __nv_bfloat16* __restrict__ res,
-                  BnParams b2, int has_res_bn, int relu, __nv_bfloat16* __restrict__ z, int64_t P, int C, int Cs,
-                  double invP, double unbias) {
+                  BnParams b2, int has_res_bn, int relu, __nv_bfloat16* __restrict__ z,
+                  __nv_bfloat16* __restrict__ zb, int64_t P, int C, int Cs, double invP, double unbias) {
   extern __shared__ float co[];  // scale, shift, rscale, rshift : 4 * Cs
   const bool writer = blockIdx.x == 0;   // exactly one block updates running stats / saves mean, rstd
   for (int c = threadIdx.x; c < Cs; c += 256) {
@@ -323,12 +327,12 @@ bn_forward_kernel(const __nv_bfloat16* __restrict__ y, BnParams b1, const __nv_b
       const int64_t pu = p + u * step;
       if (pu >= P) break;
       float f[8];
-      unpack8(vy[u], f);
+      unpack8h(vy[u], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sc[k], sf[k]);
       if (res) {
         float r[8];
-        unpack8(vr[u], r);
+        unpack8h(vr[u], r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] += fmaf(r[k], rc[k], rf[k]);
       }
@@ -336,7 +340,8 @@ bn_forward_kernel(const __nv_bfloat16* __restrict__ y, BnParams b1, const __nv_b
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
       }
-      *reinterpret_cast<uint4*>(z + pu * Cs + c0) = pack8(f);
+      if (z) *reinterpret_cast<uint4*>(z + pu * Cs + c0) = pack8h(f);          // IEEE half: the next fprop's operand
+      if (zb) *reinterpret_cast<uint4*>(zb + pu * Cs + c0) = pack8(f);         // bf16 twin: wgrad operand / mask
     }
   }
 }
@@ -426,7 +431,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       if (pu >= P) break;
       const int64_t off = pu * Cs + c0;
       float fd[8], fz[8], fy[8], g[8], o[8];
-      unpack8(vd[u], fd); unpack8(vy[u], fy); unpack8(vz[u], fz);
+      unpack8(vd[u], fd); unpack8h(vy[u], fy); unpack8(vz[u], fz);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         g[k] = (!relu || fz[k] > 0.f) ? fd[k] : 0.f;
@@ -436,7 +441,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
       if (dres) {
         if (has_res_bn) {
           float fr[8];
-          unpack8(vr[u], fr);
+          unpack8h(vr[u], fr);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             o[k] = fmaf(co[3 * Cs + c0 + k], g[k], fmaf(co[4 * Cs + c0 + k], fr[k], co[5 * Cs + c0 + k]));
@@ -508,9 +513,9 @@ int mcd_bn_forward(const void* y_nhwc, const float* stats, const float* gamma, c
                    const float* res_stats, const float* res_gamma, const float* res_beta,
                    float* res_running_mean, float* res_running_var, int64_t* res_num_batches_tracked,
                    float res_momentum, float res_eps, int res_training, float* res_save_mean_rstd, int relu,
-                   void* z_nhwc, int64_t P, int C, int Cs, int device, void* stream) {
+                   void* z_nhwc, void* zb_nhwc, int64_t P, int C, int Cs, int device, void* stream) {
   MCD_ENTER(device);
-  MCD_REQUIRE(y_nhwc && z_nhwc && save_mean_rstd && P > 0 && C > 0, "bn_forward: bad arguments");
+  MCD_REQUIRE(y_nhwc && (z_nhwc || zb_nhwc) && save_mean_rstd && P > 0 && C > 0, "bn_forward: bad arguments");
   MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_forward: needs dense channels, C %% 8 == 0 (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(training ? stats != nullptr : (running_mean && running_var), "bn_forward: missing statistics");
   const int has_res_bn = res_save_mean_rstd != nullptr;
@@ -524,22 +529,22 @@ int mcd_bn_forward(const void* y_nhwc, const float* stats, const float* gamma, c
   int grid = rows_grid(P, Cs, 4, 148 * 8);
   bn_forward_kernel<<<grid, 256, 4 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, b1, (const __nv_bfloat16*)res_nhwc, b2, has_res_bn, relu,
-      (__nv_bfloat16*)z_nhwc, P, C, Cs, invP, unbias);
+      (__nv_bfloat16*)z_nhwc, (__nv_bfloat16*)zb_nhwc, P, C, Cs, invP, unbias);
   return check_launch("bn_forward");
 }
 
 int mcd_bn_apply(const void* y_nhwc, const float* scale, const float* shift, const void* res_nhwc,
-                 const float* rscale, const float* rshift, int relu, void* z_nhwc, int64_t P, int C,
-                 int Cs, int device, void* stream) {
+                 const float* rscale, const float* rshift, int relu, void* z_nhwc, void* zb_nhwc, int64_t P,
+                 int C, int Cs, int device, void* stream) {
   MCD_ENTER(device);
-  MCD_REQUIRE(y_nhwc && scale && shift && z_nhwc && P > 0, "bn_apply: bad arguments");
+  MCD_REQUIRE(y_nhwc && scale && shift && (z_nhwc || zb_nhwc) && P > 0, "bn_apply: bad arguments");
   MCD_REQUIRE(Cs == C && C % 8 == 0, "bn_apply: needs dense channels, C %% 8 == 0 (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!rscale || (res_nhwc && rshift), "bn_apply: residual affine without residual");
   MCD_REQUIRE(Cs <= 2048, "bn_apply: channel stride %d unsupported", Cs);
   int grid = rows_grid(P, Cs, 4, 148 * 8);
   bn_apply_kernel<<<grid, 256, 4 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, scale, shift, (const __nv_bfloat16*)res_nhwc, rscale, rshift, relu,
-      (__nv_bfloat16*)z_nhwc, P, Cs);
+      (__nv_bfloat16*)z_nhwc, (__nv_bfloat16*)zb_nhwc, P, Cs);
   return check_launch("bn_apply");
 }
 

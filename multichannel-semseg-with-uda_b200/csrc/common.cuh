@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -96,6 +97,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---- 16-bit storage formats --------------------------------------------------------------------------------
+// FORWARD tensors (activations, packed fprop weights) are IEEE half: 11 significant bits keep the ReLU-mask flip
+// rate against an fp32 run 8x below bf16 (tests/tools/precision_study.py).  GRADIENT tensors (dy, dx, dlogits, packed
+// dgrad weights) and the bf16 TWIN of every activation that feeds a weight-gradient GEMM are bfloat16: fp32 range, no
+// loss scaling.  tcgen05.mma kind::f16 requires A and B in the SAME format (profiles/r02_exp_mixed_format.txt:
+// mixing is an illegal instruction), hence the twin.  The codes equal the UMMA instruction-descriptor formats.
+constexpr int kF16 = 0, kBF16 = 1;
+
 // unpack 8 bf16 (one 16-byte vector) to floats
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -112,6 +121,44 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return v;
+}
+// the same for IEEE half; the pack saturates to +-65504 instead of producing inf
+__device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
+  const __half2* p = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint32_t f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8h(const float* f) {
+  return make_uint4(f2h2_sat(f[0], f[1]), f2h2_sat(f[2], f[3]), f2h2_sat(f[4], f[5]), f2h2_sat(f[6], f[7]));
+}
+template <int FMT> __device__ __forceinline__ void unpack8f(const uint4& v, float* f) {
+  if (FMT == kF16) unpack8h(v, f); else unpack8(v, f);
+}
+template <int FMT> __device__ __forceinline__ uint4 pack8f(const float* f) {
+  return FMT == kF16 ? pack8h(f) : pack8(f);
+}
+__device__ __forceinline__ void unpack8r(const uint4& v, float* f, int fmt) {
+  if (fmt == kF16) unpack8h(v, f); else unpack8(v, f);
+}
+__device__ __forceinline__ uint4 pack8r(const float* f, int fmt) { return fmt == kF16 ? pack8h(f) : pack8(f); }
+// one element -> 16 storage bits
+__device__ __forceinline__ uint16_t f2bits16(float v, int fmt) {
+  if (fmt == kF16) return (uint16_t)(f2h2_sat(v, 0.f) & 0xffffu);
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ float bits16_2f(uint16_t u, int fmt) {
+  if (fmt == kF16) { __half h = *reinterpret_cast<__half*>(&u); return __half2float(h); }
+  return __uint_as_float((uint32_t)u << 16);
 }
 
 // block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0.

@@ -5,13 +5,13 @@
 
 namespace mcd {
 int launch_direct_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                          const void* addend, const TapProblem& p, cudaStream_t st);
+                          const void* addend, const TapProblem& p, int fmt, cudaStream_t st);
 int wgrad_direct(const void* x, const void* dy, float* dw, const mcd_conv_geom& g, int accumulate,
                  cudaStream_t st);
 int colsum(const void* t, float* out, int64_t P, int C, int Cs, int accumulate, cudaStream_t st);
 bool umma_problem_supported(const TapProblem& p);
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                        float* stats, const EpiExtra& ex, const TapProblem& p, cudaStream_t st);
+                        float* stats, const EpiExtra& ex, const TapProblem& p, int fmt, cudaStream_t st);
 size_t umma_wgrad_workspace(const mcd_conv_geom& g);
 size_t umma_streamk_workspace(const TapProblem& p, int planar, int* n_flags);
 int umma_wgrad(const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
@@ -78,9 +78,9 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
     if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p);   // w_packed is then the mcd_pack_weight_rows layout
     EpiExtra ex;
     ex.sk_partial = sk_partial; ex.sk_flags = sk_flags;
-    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, ex, p, st);
+    return launch_umma_problem(x_nhwc, w_packed, bias, y, planar, stats, ex, p, kF16, st);
   }
-  rc = launch_direct_problem(x_nhwc, w_packed, bias, y, planar, nullptr, p, st);
+  rc = launch_direct_problem(x_nhwc, w_packed, bias, y, planar, nullptr, p, kF16, st);
   if (rc != MCD_OK) return rc;
   if (stats) {
     MCD_REQUIRE(!planar, "conv fprop: fused BN statistics need the nhwc output layout");
@@ -109,7 +109,7 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
   int np = plan_dgrad(*g, p);
   if (algo != MCD_ALGO_DIRECT && packed_dgrad_ok(*g) && umma_problem_supported(p[0])) {
     plan_dgrad_packed(*g, p[0]);                          // w_packed_dgrad: mcd_pack_weight_rows mode 1
-    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, bn_sums, ex, p[0], st);
+    return launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, bn_sums, ex, p[0], kBF16, st);
   }
   // the ReLU mask / BatchNorm sums are fused into the epilogue when every pixel of dx is produced by a tcgen05
   // problem; otherwise one extra pass over dx applies them
@@ -133,8 +133,8 @@ int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_n
     bool umma = use_umma(algo, umma_problem_supported(p[i]), &rc);
     if (rc != MCD_OK) return rc;
     rc = umma ? launch_umma_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, fused ? bn_sums : nullptr, ex,
-                                    p[i], st)
-              : launch_direct_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, add_nhwc, p[i], st);
+                                    p[i], kBF16, st)
+              : launch_direct_problem(dy_nhwc, w_packed_dgrad, nullptr, dx_nhwc, 0, add_nhwc, p[i], kBF16, st);
     if (rc != MCD_OK) return rc;
   }
   if (post_wanted && !fused)

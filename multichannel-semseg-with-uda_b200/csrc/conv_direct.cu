@@ -12,7 +12,7 @@ template <bool PLANAR>
 __global__ void __launch_bounds__(256)
 conv_direct_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ w,
                    const float* __restrict__ bias, void* __restrict__ out,
-                   const __nv_bfloat16* __restrict__ addend, const TapProblem p) {
+                   const __nv_bfloat16* __restrict__ addend, const TapProblem p, const int fmt) {
   __shared__ float As[16][DT + 4];
   __shared__ float Bs[16][DT + 4];
   const int tid = threadIdx.x;
@@ -63,7 +63,7 @@ conv_direct_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* _
       } else {
         if (bptr && kc < p.kc_pad) v = *reinterpret_cast<const uint4*>(bptr + kc);
       }
-      unpack8(v, f);
+      unpack8r(v, f, fmt);     // src, w and the nhwc output share the format (kF16 forward / kBF16 dgrad)
       if (loadA && kc + 8 > p.Kc) {  // partial vector: channels past Kc must not contribute
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -113,7 +113,7 @@ conv_direct_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* _
           float v = row < p.rows ? acc[i][j] + (bias ? bias[row] : 0.f) : 0.f;
           const int64_t oidx = (((int64_t)n * p.Hd + hd) * p.Wd + wd) * p.Cd_s + row;
           if (addend) v += bf2f(addend[oidx]);
-          reinterpret_cast<__nv_bfloat16*>(out)[oidx] = f2bf(v);
+          reinterpret_cast<uint16_t*>(out)[oidx] = f2bits16(v, fmt);
         }
       }
     }
@@ -223,17 +223,17 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ t, float* __rest
 }
 
 int launch_direct_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                          const void* addend, const TapProblem& p, cudaStream_t st) {
+                          const void* addend, const TapProblem& p, int fmt, cudaStream_t st) {
   if (p.ntaps == 0) return MCD_OK;
   int64_t npix = (int64_t)p.N * p.Ht * p.Wt;
   int rows_cover = planar ? p.rows : p.Cd_s;
   dim3 grid((unsigned)((npix + DT - 1) / DT), (unsigned)((rows_cover + DT - 1) / DT));
   if (planar)
     conv_direct_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src,
-                                                   (const __nv_bfloat16*)w, bias, out, nullptr, p);
+                                                   (const __nv_bfloat16*)w, bias, out, nullptr, p, fmt);
   else
     conv_direct_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (const __nv_bfloat16*)w, bias, out,
-                                                    (const __nv_bfloat16*)addend, p);
+                                                    (const __nv_bfloat16*)addend, p, fmt);
   return check_launch("conv_direct");
 }
 

@@ -33,11 +33,12 @@ struct RowconvArgs {
   int stages, stage_bytes, w_bytes;
   int planar;               // 1: out is planar fp32 [N][rows][H][W]
   int wide16;               // 16-channel source staged as ONE 32-byte-swizzled plane per filter row (see below)
+  int fmt;                  // element format of src / weights / nhwc output: kF16 (forward) or kBF16 (dgrad)
   const float* bias;
   float* stats;
   const __nv_bfloat16* addend;     // epilogue extras, see conv_plan.h EpiExtra
-  const __nv_bfloat16* mask_src;
-  const __nv_bfloat16* bn_y;
+  const __nv_bfloat16* mask_src;   // bf16 twin (sign only)
+  const __half* bn_y;              // forward tensor: IEEE half
   void* out;
   const __nv_bfloat16* wpacked;   // [R][HC*SP][NB/8][8][8] bf16, smem-ready no-swizzle K-major B operand
 };
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(RC_THREADS, NB == 16 ? 4 : 2)
 conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ RowconvArgs a) {
   const __nv_bfloat16* const x_addend = EXTRAS ? a.addend : nullptr;
   const __nv_bfloat16* const x_mask = EXTRAS ? a.mask_src : nullptr;
-  const __nv_bfloat16* const x_bny = EXTRAS ? a.bn_y : nullptr;
+  const __half* const x_bny = EXTRAS ? a.bn_y : nullptr;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;                                   // packed weights
@@ -126,7 +127,7 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = instr_desc_bf16(128, NB, 0, 0);
+    const uint32_t idesc = instr_desc_16(128, NB, 0, 0, (uint32_t)a.fmt);
     constexpr uint32_t kg_bytes = (NB / 8) * 128;          // one 8-wide k-group of the weights: NB rows x 16 B
     const uint32_t wbase = smem_u32(wsm);
     int stage = 0; uint32_t phase = 0;
@@ -239,11 +240,11 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
             }
             if (x_bny) {                                     // fused BatchNorm-backward sums: g, g * y
               float r8[8];
-              unpack8(yv[j8], r8);
+              unpack8h(yv[j8], r8);
 #pragma unroll
               for (int k = 0; k < 8; ++k) { s1[c + k] += f[k]; s2[c + k] = fmaf(f[k], r8[k], s2[c + k]); }
             }
-            *reinterpret_cast<uint4*>(out + ooff + c) = pack8(f);
+            *reinterpret_cast<uint4*>(out + ooff + c) = pack8r(f, a.fmt);
           }
         }
       }
@@ -431,11 +432,12 @@ __global__ void wgrad_toeplitz_reduce_kernel(const float* __restrict__ ws, float
   }
 }
 
-__global__ void pack_weight_rowconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout,
+// mode 0 (fprop operand): IEEE half; mode 1 (dgrad operand): bfloat16 - the format of the tensor it multiplies
+__global__ void pack_weight_rowconv_kernel(const float* __restrict__ w, uint16_t* __restrict__ dst, int Cout,
                                            int Cin, int R, int S, int HC, int SP, int NB, int mode) {
   const int64_t total = (int64_t)R * HC * SP * NB * 8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    dst[i] = f2bf(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, mode));
+    dst[i] = f2bits16(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, mode), mode ? kBF16 : kF16);
 }
 
 // ---- host -----------------------------------------------------------------------------------------------
@@ -483,7 +485,7 @@ int rowconv_pack(const float* w, void* dst, int Cout, int Cin, int R, int S, int
   const int HC = Cs / 8, SP = S <= 4 ? 4 : 8, NB = round_up(mode ? Cin : Cout, 16);
   int64_t total = (int64_t)R * HC * SP * NB * 8;
   int grid = (int)min64((total + 255) / 256, 148 * 4);
-  pack_weight_rowconv_kernel<<<grid, 256, 0, st>>>(w, (__nv_bfloat16*)dst, Cout, Cin, R, S, HC, SP, NB, mode);
+  pack_weight_rowconv_kernel<<<grid, 256, 0, st>>>(w, (uint16_t*)dst, Cout, Cin, R, S, HC, SP, NB, mode);
   return check_launch("pack_weight_rowconv");
 }
 
@@ -507,10 +509,10 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   a.stage_bytes = a.R * a.HC * RC_PLANE;
   a.w_bytes = round_up(a.R * a.HC * a.SP * (a.NB / 8) * 128, 1024);
   a.stages = max(2, min(4, (54 * 1024 - a.w_bytes) / a.stage_bytes));
-  a.bias = bias; a.stats = stats;
+  a.bias = bias; a.stats = stats; a.fmt = mode ? kBF16 : kF16;
   a.addend = planar ? nullptr : (const __nv_bfloat16*)ex.addend;
   a.mask_src = planar ? nullptr : (const __nv_bfloat16*)ex.mask_src;
-  a.bn_y = planar ? nullptr : (const __nv_bfloat16*)ex.bn_y;
+  a.bn_y = planar ? nullptr : (const __half*)ex.bn_y;
   a.out = out; a.planar = planar; a.wpacked = (const __nv_bfloat16*)wpacked;
   const int srcC = mode ? g.Cout : g.Cin, srcCs = mode ? g.Cout_s : g.Cin_s;
   CUtensorMap xmap;
@@ -518,7 +520,8 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   cuuint64_t strides[3] = {(cuuint64_t)srcCs * 2, (cuuint64_t)g.W * srcCs * 2, (cuuint64_t)g.H * g.W * srcCs * 2};
   cuuint32_t box[4] = {a.wide16 ? 16u : 8u, RC_SEG, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), dims, strides, box, estr,
+  CUresult r = enc(&xmap, mode ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                   const_cast<void*>(src), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, a.wide16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rowconv) failed: %d", (int)r); return MCD_E_CUDA; }

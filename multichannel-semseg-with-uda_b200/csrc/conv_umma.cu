@@ -48,6 +48,7 @@ struct FpropArgs {
   int rows;               // produced channels
   int omul, oh0, ow0, Hd, Wd, Cd_s;
   int planar;
+  int fmt;                // element format of src / weights / nhwc output: kF16 (forward) or kBF16 (dgrad)
   int packed;             // row-packed thin-channel mode: A = TWp window loads of THp rows each
   int cs_src, smul;       // packed: source channel stride, W stride of the convolution
   const float* bias;
@@ -56,8 +57,8 @@ struct FpropArgs {
   const __nv_bfloat16* addend;   // optional nhwc tensor (output geometry) added in the epilogue: residual gradient
   // dgrad fused with the backward of the BatchNorm+ReLU unit that produced the convolution's input (all nhwc,
   // output geometry): out = mask_src > 0 ? out : 0 and, with bn_y, stats += {sum out, sum out * bn_y}
-  const __nv_bfloat16* mask_src;
-  const __nv_bfloat16* bn_y;
+  const __nv_bfloat16* mask_src;  // bf16 twin of the activation (only its sign is used)
+  const __half* bn_y;             // forward tensor: IEEE half
   // stream-K schedule (sk_units > 0): CTA i owns the (tile, k-block) units [i * sk_units, (i+1) * sk_units) of the
   // linearised tile x k-block space, so every CTA does the same amount of MMA work whatever the tile count.  A
   // tile cut by a CTA boundary is finished by the CTA that started it (its LAST segment): the next CTA computes
@@ -217,7 +218,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   using Cfg = FpropCfg<BN, PAIR, OCC>;
   const __nv_bfloat16* const x_addend = EXTRAS ? a.addend : nullptr;
   const __nv_bfloat16* const x_mask = EXTRAS ? a.mask_src : nullptr;
-  const __nv_bfloat16* const x_bny = EXTRAS ? a.bn_y : nullptr;
+  const __half* const x_bny = EXTRAS ? a.bn_y : nullptr;
   static_assert(!PAIR || BN == 256, "CTA pairs run the 256-channel tile only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -341,7 +342,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = instr_desc_bf16(PAIR ? 256 : 128, BN, 0, 0);
+    const uint32_t idesc = instr_desc_16(PAIR ? 256 : 128, BN, 0, 0, (uint32_t)a.fmt);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     SegIter it = PAIR ? make_pair_iter(total_tiles, kblocks) : make_seg_iter(a, total_tiles, kblocks);
@@ -556,11 +557,11 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                 }
                 if (x_bny) {
                   float r[8];
-                  unpack8(ey[j8], r);
+                  unpack8h(ey[j8], r);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) { v[j8 * 8 + k] = f[k]; vy[j8 * 8 + k] = f[k] * r[k]; }
                 }
-                *reinterpret_cast<uint4*>(o + j8 * 8) = pack8(f);
+                *reinterpret_cast<uint4*>(o + j8 * 8) = pack8r(f, a.fmt);
               } else if (x_bny) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { v[j8 * 8 + k] = 0.f; vy[j8 * 8 + k] = 0.f; }
@@ -1168,8 +1169,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // 4-D map over an NHWC bf16 tensor viewed through a (ph,pw) parity sub-grid with step `st`.
+static inline CUtensorMapDataType tmap_dtype(int fmt) {
+  return fmt == kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
 static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int Cs,
-                          int st, int ph, int pw, int box_w, int box_h) {
+                          int st, int ph, int pw, int box_w, int box_h, int fmt = kBF16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
   int Wsub = (W - pw + st - 1) / st, Hsub = (H - ph + st - 1) / st;
@@ -1180,7 +1185,7 @@ static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W,
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const char* p = reinterpret_cast<const char*>(base) + ((int64_t)ph * W + pw) * Cs * 2;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(p), dims, strides, box,
+  CUresult r = enc(m, tmap_dtype(fmt), 4, const_cast<char*>(p), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1193,7 +1198,7 @@ static int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W,
 
 // 3-D map {W*Cs elements, rows of parity ph (step st), N} for the row-packed window loads
 static int encode_rows_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cs, int st, int ph,
-                           int box_h) {
+                           int box_h, int fmt = kBF16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
   int Hsub = (H - ph + st - 1) / st;
@@ -1203,7 +1208,7 @@ static int encode_rows_map(CUtensorMap* m, const void* base, int N, int H, int W
   cuuint32_t box[3] = {64, (cuuint32_t)box_h, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   const char* p = reinterpret_cast<const char*>(base) + (int64_t)ph * W * Cs * 2;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<char*>(p), dims, strides, box, estr,
+  CUresult r = enc(m, tmap_dtype(fmt), 3, const_cast<char*>(p), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1231,14 +1236,14 @@ static void pick_tile_packed(int Ht, int Wt, int npix, int* TH, int* TW) {
   }
 }
 
-static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t kdim, int box_rows) {
+static int encode_weight_map(CUtensorMap* m, const void* base, int rows, int64_t kdim, int box_rows, int fmt = kBF16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MCD_E_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  CUresult r = enc(m, tmap_dtype(fmt), 2, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1434,7 +1439,7 @@ static bool streamk_plan(int total_tiles, int kblocks, int BN, int packed, int* 
 
 // src: activations for this problem; for strided fprop the parity maps are built over (Hs, Ws).
 int launch_umma_problem(const void* src, const void* w, const float* bias, void* out, int planar,
-                        float* stats, const EpiExtra& ex, const TapProblem& p, cudaStream_t st) {
+                        float* stats, const EpiExtra& ex, const TapProblem& p, int fmt, cudaStream_t st) {
   if (p.ntaps == 0) return MCD_OK;
   if (!umma_problem_supported(p)) { set_error("umma fprop: unsupported problem"); return MCD_E_INVALID; }
   FpropArgs a;
@@ -1446,10 +1451,10 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   a.tiles_h = (p.Ht + a.TH - 1) / a.TH; a.tiles_w = (p.Wt + a.TW - 1) / a.TW;
   a.kchunks = (p.Kc + 63) / 64; a.ntaps = p.ntaps; a.kc_pad = p.kc_pad;
   a.rows = p.rows; a.omul = p.omul; a.oh0 = p.oh0; a.ow0 = p.ow0; a.Hd = p.Hd; a.Wd = p.Wd;
-  a.Cd_s = p.Cd_s; a.planar = planar; a.bias = bias; a.stats = stats; a.out = out;
+  a.Cd_s = p.Cd_s; a.planar = planar; a.fmt = fmt; a.bias = bias; a.stats = stats; a.out = out;
   a.addend = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.addend);
   a.mask_src = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.mask_src);
-  a.bn_y = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.bn_y);
+  a.bn_y = planar ? nullptr : reinterpret_cast<const __half*>(ex.bn_y);
   for (int t = 0; t < p.ntaps; ++t) a.taps[t] = p.taps[t];
 
   UmmaMaps maps;
@@ -1460,7 +1465,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   if (p.packed) {
     for (int ph = 0; ph < stp; ++ph) {
       if (!used[ph]) continue;
-      int rc = encode_rows_map(&maps.a[ph], src, p.N, p.Hs, p.Ws, p.Cs_src, stp, ph, a.TH);
+      int rc = encode_rows_map(&maps.a[ph], src, p.N, p.Hs, p.Ws, p.Cs_src, stp, ph, a.TH, fmt);
       if (rc != MCD_OK) return rc;
     }
   } else {
@@ -1468,7 +1473,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
       for (int pw = 0; pw < stp; ++pw) {
         int id = ph * stp + pw;
         if (!used[id]) continue;
-        int rc = encode_act_map(&maps.a[id], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, stp, ph, pw, a.TW, a.TH);
+        int rc = encode_act_map(&maps.a[id], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, stp, ph, pw, a.TW, a.TH, fmt);
         if (rc != MCD_OK) return rc;
       }
   }
@@ -1482,9 +1487,9 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   // dgrad instantiations (fused-epilogue inputs) of the 64 / 128 tiles keep one CTA per SM: register budget
   const bool occ2_ok = thin_occ2() && (!has_extras(a) || thin_occ2_dgrad());
   if (!want_sk && halo_plan(p, BN, pair, &a, &halo_hb, occ2_ok)) {
-    int rc = encode_act_map(&maps.a[0], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, 1, 0, 0, a.halo_wb, halo_hb);
+    int rc = encode_act_map(&maps.a[0], src, p.N, p.Hs, p.Ws, p.Kc, p.Cs_src, 1, 0, 0, a.halo_wb, halo_hb, fmt);
     if (rc != MCD_OK) return rc;
-    rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
+    rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN, fmt);
     if (rc != MCD_OK) return rc;
     if (pair) {
       const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;
@@ -1497,7 +1502,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
     return BN == 128 ? launch_fprop_halo<128, false, 1>(maps, a, grid, st)
                      : launch_fprop_halo<64, false, 1>(maps, a, grid, st);
   }
-  int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN);
+  int rc = encode_weight_map(&maps.b, w, p.rows, (int64_t)p.T_total * p.kc_pad, pair ? BN / 2 : BN, fmt);
   if (rc != MCD_OK) return rc;
   if (pair) {
     const int pair_tiles = ((a.tiles_m + 1) / 2) * a.tiles_n;

@@ -14,10 +14,32 @@ namespace mcd {
 // (filter rows kh0+8).  One thread owns a cell (i, j): it loads the 6 neighbouring inputs once and emits 8 rows
 // of 8 consecutive output columns (one 16-byte store per row) with broadcast LDS.128 weight reads.
 // grid: (N*C, ceil((h+1)/cells_per_block)); block 256.
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack8(f); }
+__device__ __forceinline__ void store8(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float* f) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const float2 p0 = __bfloat1622float2(pv[0]), p1 = __bfloat1622float2(pv[1]);
+  f[0] = p0.x; f[1] = p0.y; f[2] = p1.x; f[3] = p1.y;
+}
+__device__ __forceinline__ void load4(const float* p, float* f) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+}
+__device__ __forceinline__ void load8(const float* p, float* f) { load4(p, f); load4(p + 4, f + 4); }
+
+// T = type of the full-resolution tensor: bf16 (MCDStep) or fp32 (drop-in default)
+template <typename T>
 __global__ void __launch_bounds__(256)
 deconv16s8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ x2, const float* __restrict__ w2,
-                      __nv_bfloat16* __restrict__ out, int C, int h, int wd, int cells_per_block) {
+                      T* __restrict__ out, int C, int h, int wd, int cells_per_block) {
   __shared__ __align__(16) float sw[2][256];
   const int nc = blockIdx.x, c = nc % C;
   const int H = h * 8, W = wd * 8;
@@ -25,7 +47,7 @@ deconv16s8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
   sw[1][threadIdx.x] = x2 ? (w2 ? w2 : w)[c * 256 + threadIdx.x] : 0.f;
   __syncthreads();
   const int ninputs = x2 ? 2 : 1;
-  __nv_bfloat16* op = out + (int64_t)nc * H * W;
+  T* op = out + (int64_t)nc * H * W;
   const int items = cells_per_block * wd;
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
     const int i = blockIdx.y * cells_per_block + it / wd, j = it % wd;
@@ -71,22 +93,23 @@ deconv16s8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
           f[k] = fmaf(xb[q][1], wb[k + 4], f[k]);
         }
       }
-      *reinterpret_cast<uint4*>(op + (int64_t)oh * W + j * 8) = pack8(f);
+      store8(op + (int64_t)oh * W + j * 8, f);
     }
   }
 }
 
 // dx[ih][iw] = sum_{kh,kw} dout[8ih-4+kh][8iw-4+kw] * w[kh][kw]
 // grid: (N*C, h); block 128: thread t handles iw = t, t+128, ...
+template <typename T>
 __global__ void __launch_bounds__(128)
-deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ w,
+deconv16s8_bwd_dx_kernel(const T* __restrict__ dout, const float* __restrict__ w,
                          float* __restrict__ dx, int C, int h, int wd) {
   __shared__ float sw[256];
   const int nc = blockIdx.x, c = nc % C, ih = blockIdx.y;
   const int H = h * 8, W = wd * 8;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sw[i] = w[c * 256 + i];
   __syncthreads();
-  const __nv_bfloat16* dp = dout + (int64_t)nc * H * W;
+  const T* dp = dout + (int64_t)nc * H * W;
   for (int iw = threadIdx.x; iw < wd; iw += blockDim.x) {
     float acc = 0.f;
     for (int kh = 0; kh < 16; ++kh) {
@@ -97,12 +120,11 @@ deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
       for (int k4 = 0; k4 < 4; ++k4) {
         const int ow = ow0 + 4 * k4;
         if (ow < 0 || ow + 3 >= W) continue;  // W % 8 == 0 and ow % 4 == 0: group fully in or out
-        const uint2 v = *reinterpret_cast<const uint2*>(dp + (int64_t)oh * W + ow);
-        const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
-        const float2 p0 = __bfloat1622float2(pv[0]), p1 = __bfloat1622float2(pv[1]);
+        float d4[4];
+        load4(dp + (int64_t)oh * W + ow, d4);
         const float* ww = &sw[kh * 16 + 4 * k4];
-        acc = fmaf(p0.x, ww[0], acc); acc = fmaf(p0.y, ww[1], acc);
-        acc = fmaf(p1.x, ww[2], acc); acc = fmaf(p1.y, ww[3], acc);
+        acc = fmaf(d4[0], ww[0], acc); acc = fmaf(d4[1], ww[1], acc);
+        acc = fmaf(d4[2], ww[2], acc); acc = fmaf(d4[3], ww[3], acc);
       }
     }
     dx[(int64_t)nc * h * wd + ih * wd + iw] = acc;
@@ -114,8 +136,9 @@ deconv16s8_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
 // kw0 = (ow+4)&7 these are (ih0|ih0-1, kh0|kh0+8) x (iw0|iw0-1, kw0|kw0+8).  A block owns one (c, kh0): all rows
 // with that residue, i.e. both kh bins, so dout is read exactly ONCE, as 16-byte chunks (8 ow = one iw step).
 // grid: (C*8 [c,kh0], nsplit chunks of (n,ih0) rows); block 256 = 8 warps, one row per warp-iteration; dw pre-zeroed.
+template <typename T>
 __global__ void __launch_bounds__(256)
-deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __restrict__ x,
+deconv16s8_bwd_dw_kernel(const T* __restrict__ dout, const float* __restrict__ x,
                          float* __restrict__ dw, int N, int C, int h, int wd) {
   __shared__ float red[8][32];
   const int c = blockIdx.x >> 3, kh0 = blockIdx.x & 7;
@@ -131,23 +154,22 @@ deconv16s8_bwd_dw_kernel(const __nv_bfloat16* __restrict__ dout, const float* __
     const int n = rr / (h + 1), ih0 = rr % (h + 1);
     const int oh = 8 * ih0 + kh0 - 4;
     if (oh < 0 || oh >= H) continue;
-    const __nv_bfloat16* dp = dout + (((int64_t)n * C + c) * H + oh) * W;
+    const T* dp = dout + (((int64_t)n * C + c) * H + oh) * W;
     const float* xa = x + (((int64_t)n * C + c) * h + ih0) * wd;     // valid if ih0 < h
     const float* xb = xa - wd;                                       // valid if ih0 >= 1
     const bool va = ih0 < h, vb = ih0 >= 1;
     for (int j0 = lane; j0 < wd; j0 += 96) {
-      uint4 raw[3];
+      float raw[3][8];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {          // three independent 16-byte loads per lane in flight
+      for (int q = 0; q < 3; ++q) {          // three independent vector loads per lane in flight
         const int j = j0 + 32 * q;
-        raw[q] = (j < wd) ? __ldg(reinterpret_cast<const uint4*>(dp + j * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        if (j < wd) load8(dp + j * 8, raw[q]);
       }
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const int j = j0 + 32 * q;
         if (j >= wd) continue;
-        float d[8];
-        unpack8(raw[q], d);
+        const float* d = raw[q];
         const float a0 = va ? xa[j] : 0.f, am = (va && j >= 1) ? xa[j - 1] : 0.f, ap = (va && j + 1 < wd) ? xa[j + 1] : 0.f;
         const float b0 = vb ? xb[j] : 0.f, bm = (vb && j >= 1) ? xb[j - 1] : 0.f, bp = (vb && j + 1 < wd) ? xb[j + 1] : 0.f;
 #pragma unroll
@@ -274,26 +296,32 @@ using namespace mcd;
 
 extern "C" {
 
-int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const float* w2, void* out,
+int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const float* w2, void* out, int out_f32,
                        int N, int C, int h, int w_, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(x && w && out && N > 0 && C > 0 && h > 0 && w_ > 0, "deconv16s8_fwd: bad arguments");
   int cells = w_ >= 256 ? 1 : 256 / w_;
   dim3 grid((unsigned)(N * C), (unsigned)((h + 1 + cells - 1) / cells));
-  deconv16s8_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, x2, w2, (__nv_bfloat16*)out, C,
-                                                                 h, w_, cells);
+  if (out_f32)
+    deconv16s8_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, x2, w2, (float*)out, C, h, w_, cells);
+  else
+    deconv16s8_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, x2, w2, (__nv_bfloat16*)out,
+                                                                                 C, h, w_, cells);
   return check_launch("deconv16s8_fwd");
 }
 
-int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* dx, float* dw, int N,
-                       int C, int h, int w_, int device, void* stream) {
+int mcd_deconv16s8_bwd(const void* dout, int dout_f32, const float* x, const float* w, float* dx, float* dw,
+                       int N, int C, int h, int w_, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(dout && w && N > 0 && C > 0 && h > 0 && w_ > 0, "deconv16s8_bwd: bad arguments");
   MCD_REQUIRE(!dw || x, "deconv16s8_bwd: dw needs x");
   if (dx) {
     dim3 grid((unsigned)(N * C), (unsigned)h);
-    deconv16s8_bwd_dx_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, w, dx,
-                                                                      C, h, w_);
+    if (dout_f32)
+      deconv16s8_bwd_dx_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>((const float*)dout, w, dx, C, h, w_);
+    else
+      deconv16s8_bwd_dx_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, w,
+                                                                                      dx, C, h, w_);
     int rc = check_launch("deconv16s8_bwd_dx");
     if (rc != MCD_OK) return rc;
   }
@@ -302,8 +330,11 @@ int mcd_deconv16s8_bwd(const void* dout, const float* x, const float* w, float* 
     if (e != cudaSuccess) { set_error("deconv dw memset: %s", cudaGetErrorString(e)); return MCD_E_CUDA; }
     int nsplit = min(N * (h + 1), 32);
     dim3 grid((unsigned)(C * 8), (unsigned)nsplit);
-    deconv16s8_bwd_dw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, x, dw,
-                                                                      N, C, h, w_);
+    if (dout_f32)
+      deconv16s8_bwd_dw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)dout, x, dw, N, C, h, w_);
+    else
+      deconv16s8_bwd_dw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, x,
+                                                                                      dw, N, C, h, w_);
     return check_launch("deconv16s8_bwd_dw");
   }
   return MCD_OK;

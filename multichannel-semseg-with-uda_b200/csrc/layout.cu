@@ -5,9 +5,8 @@
 namespace mcd {
 
 // one thread = one pixel x 8-channel group; lanes walk pixels so plane reads are coalesced.
-__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src,
-                                             __nv_bfloat16* __restrict__ dst, int N, int C, int HW,
-                                             int Cs) {
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst_h,
+                                        __nv_bfloat16* __restrict__ dst_b, int N, int C, int HW, int Cs) {
   int groups = Cs >> 3;
   int64_t total = (int64_t)N * HW * groups;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -22,12 +21,13 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src,
       int c = g * 8 + k;
       f[k] = c < C ? src[((int64_t)n * C + c) * HW + hw] : 0.f;
     }
-    *reinterpret_cast<uint4*>(dst + pix * Cs + g * 8) = pack8(f);
+    if (dst_h) *reinterpret_cast<uint4*>(dst_h + pix * Cs + g * 8) = pack8h(f);
+    if (dst_b) *reinterpret_cast<uint4*>(dst_b + pix * Cs + g * 8) = pack8(f);
   }
 }
 
-__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src,
-                                             float* __restrict__ dst, int N, int C, int HW, int Cs) {
+__global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int fmt,
+                                        float* __restrict__ dst, int N, int C, int HW, int Cs) {
   int groups = (C + 7) >> 3;
   int64_t total = (int64_t)N * HW * groups;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -38,7 +38,7 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
     int hw = (int)(pix % HW);
     uint4 v = *reinterpret_cast<const uint4*>(src + pix * Cs + g * 8);
     float f[8];
-    unpack8(v, f);
+    unpack8r(v, f, fmt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       int c = g * 8 + k;
@@ -47,9 +47,20 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
   }
 }
 
+// 16-bit -> 16-bit re-encoding of a dense tensor (bf16 <-> IEEE half): creates the missing twin of an activation that
+// entered the library in one format only (e.g. a bf16 tensor produced by stock torch code)
+__global__ void convert16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int src_fmt, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8r(src[i], f, src_fmt);
+    dst[i] = pack8r(f, src_fmt == kF16 ? kBF16 : kF16);
+  }
+}
+
 // mode 0: dst[co][r*S+s][kc]            = w[co][kc][r][s]                 (kc < Cin, else 0)
 // mode 1: dst[ci][(R-1-r)*S+(S-1-s)][kc] = w[kc][ci][r][s]                 (kc < Cout, else 0)
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+// packs are stored in the format of the tensor they multiply: mode 0 (fprop) IEEE half, mode 1 (dgrad) bfloat16
+__global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ dst,
                                    int Cout, int Cin, int R, int S, int mode, int rows, int kc_pad) {
   int T = R * S;
   int64_t total = (int64_t)rows * T * kc_pad;
@@ -67,14 +78,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
         v = w[(((int64_t)kc * Cin + row) * R + r) * S + s];
       }
     }
-    dst[i] = f2bf(v);
+    dst[i] = f2bits16(v, mode ? kBF16 : kF16);
   }
 }
 
 // row-packed variants (conv_plan.h): dst[row][r][k], k = s*Cs + c, 64 elements per filter row
 // mode 0: row = co, value w[co][c][r][s]            (c < Cin)
 // mode 1: row = ci, value w[c][ci][R-1-r][S-1-s]    (c < Cout)   - flipped filter for dgrad
-__global__ void pack_weight_rows_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+__global__ void pack_weight_rows_kernel(const float* __restrict__ w, uint16_t* __restrict__ dst,
                                         int Cout, int Cin, int R, int S, int Cs, int mode, int rows) {
   int64_t total = (int64_t)rows * R * 64;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -91,7 +102,7 @@ __global__ void pack_weight_rows_kernel(const float* __restrict__ w, __nv_bfloat
         if (c < Cout) v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
       }
     }
-    dst[i] = f2bf(v);
+    dst[i] = f2bits16(v, mode ? kBF16 : kF16);
   }
 }
 
@@ -108,8 +119,8 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
   __shared__ float tile[32][32 * PK_T_MAX + 1];
   const int64_t* it = items + (int64_t)blockIdx.x * 12;
   const float* w = reinterpret_cast<const float*>(it[0]);
-  __nv_bfloat16* dst_f = reinterpret_cast<__nv_bfloat16*>(it[1]);
-  __nv_bfloat16* dst_d = reinterpret_cast<__nv_bfloat16*>(it[2]);
+  uint16_t* dst_f = reinterpret_cast<uint16_t*>(it[1]);     // fprop pack: IEEE half
+  uint16_t* dst_d = reinterpret_cast<uint16_t*>(it[2]);     // dgrad pack: bfloat16
   const int Cout = (int)it[3], Cin = (int)it[4], R = (int)it[5], S = (int)it[6];
   const int kind_f = (int)it[7], kind_d = (int)it[8], cs_f = (int)it[9], cs_d = (int)it[10];
   const int T = R * S;
@@ -130,7 +141,7 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
         for (int idx = threadIdx.x; idx < nco * T * 32; idx += 256) {    // ci_l fastest
           const int ci_l = idx & 31, t = (idx >> 5) % T, co_l = idx / (32 * T);
           if (ci_l < nci)
-            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bf(tile[co_l][ci_l * T + t]);
+            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bits16(tile[co_l][ci_l * T + t], kF16);
         }
       }
       if (std_d) {
@@ -138,7 +149,7 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
           const int co_l = idx & 31, t = (idx >> 5) % T, ci_l = idx / (32 * T);
           if (co_l < nco) {
             const int tf = (R - 1 - t / S) * S + (S - 1 - t % S);
-            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bf(tile[co_l][ci_l * T + t]);
+            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bits16(tile[co_l][ci_l * T + t], kBF16);
           }
         }
       }
@@ -146,7 +157,8 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
   }
   // element-wise paths: row-packed layouts, or filters larger than the smem tile allows
   for (int pass = 0; pass < 2; ++pass) {
-    __nv_bfloat16* dst = pass ? dst_d : dst_f;
+    uint16_t* dst = pass ? dst_d : dst_f;
+    const int fmt = pass ? kBF16 : kF16;
     const int kind = pass ? kind_d : kind_f, Cs = pass ? cs_d : cs_f;
     if (!dst) continue;
     if (kind == 0 && T <= PK_T_MAX) continue;
@@ -159,13 +171,13 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
         float v = 0.f;
         if (!pass) { if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S]; }
         else if (kc < Cout) v = w[(((int64_t)kc * Cin + row) * R + (R - 1 - t / S)) * S + (S - 1 - t % S)];
-        dst[i] = f2bf(v);
+        dst[i] = f2bits16(v, fmt);
       }
     } else if (kind == 2) {
       const int HC = Cs / 8, SP = S <= 4 ? 4 : 8, NB = (rows + 15) / 16 * 16;
       const int64_t total = (int64_t)R * HC * SP * NB * 8;
       for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x)
-        dst[i] = f2bf(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, pass));
+        dst[i] = f2bits16(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, pass), fmt);
     } else {
       const int64_t total = (int64_t)rows * R * 64;
       for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.y * blockDim.x) {
@@ -176,7 +188,7 @@ pack_weights_multi_kernel(const int64_t* __restrict__ items) {
           if (!pass) { if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s]; }
           else if (c < Cout) v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
         }
-        dst[i] = f2bf(v);
+        dst[i] = f2bits16(v, fmt);
       }
     }
   }
@@ -216,8 +228,8 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
   float* w = reinterpret_cast<float*>(it[0]);
   const float* g = reinterpret_cast<const float*>(it[1]);
   float* buf = reinterpret_cast<float*>(it[2]);
-  __nv_bfloat16* dst_f = reinterpret_cast<__nv_bfloat16*>(it[3]);
-  __nv_bfloat16* dst_d = reinterpret_cast<__nv_bfloat16*>(it[4]);
+  uint16_t* dst_f = reinterpret_cast<uint16_t*>(it[3]);     // fprop pack: IEEE half
+  uint16_t* dst_d = reinterpret_cast<uint16_t*>(it[4]);     // dgrad pack: bfloat16
   const int Cout = (int)it[5], Cin = (int)it[6], R = (int)it[7], S = (int)it[8];
   const int kind_f = (int)it[9], kind_d = (int)it[10], cs_f = (int)it[11], cs_d = (int)it[12];
   const int64_t numel = it[13];
@@ -270,7 +282,7 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
         for (int idx = threadIdx.x; idx < nco * T * 32; idx += 256) {
           const int ci_l = idx & 31, t = (idx >> 5) % T, co_l = idx / (32 * T);
           if (ci_l < nci)
-            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bf(tile[co_l][ci_l * T + t]);
+            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bits16(tile[co_l][ci_l * T + t], kF16);
         }
       }
       if (dst_d) {
@@ -278,7 +290,7 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
           const int co_l = idx & 31, t = (idx >> 5) % T, ci_l = idx / (32 * T);
           if (co_l < nco) {
             const int tf = (R - 1 - t / S) * S + (S - 1 - t % S);
-            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bf(tile[co_l][ci_l * T + t]);
+            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bits16(tile[co_l][ci_l * T + t], kBF16);
           }
         }
       }
@@ -290,7 +302,8 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
   for (int64_t i = threadIdx.x; i < numel; i += blockDim.x) sgd_update(w, g, buf, i, lr, mom, wd);
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
-    __nv_bfloat16* dst = pass ? dst_d : dst_f;
+    uint16_t* dst = pass ? dst_d : dst_f;
+    const int fmt = pass ? kBF16 : kF16;
     const int kind = pass ? kind_d : kind_f, Cs = pass ? cs_d : cs_f;
     if (!dst) continue;
     const int rows = pass ? Cin : Cout;
@@ -302,13 +315,13 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
         float v = 0.f;
         if (!pass) { if (kc < Cin) v = w[(((int64_t)row * Cin + kc) * R + t / S) * S + t % S]; }
         else if (kc < Cout) v = w[(((int64_t)kc * Cin + row) * R + (R - 1 - t / S)) * S + (S - 1 - t % S)];
-        dst[i] = f2bf(v);
+        dst[i] = f2bits16(v, fmt);
       }
     } else if (kind == 2) {
       const int HC = Cs / 8, SP = S <= 4 ? 4 : 8, NB = (rows + 15) / 16 * 16;
       const int64_t total = (int64_t)R * HC * SP * NB * 8;
       for (int64_t i = threadIdx.x; i < total; i += blockDim.x)
-        dst[i] = f2bf(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, pass));
+        dst[i] = f2bits16(rowconv_pack_value(w, i, Cout, Cin, R, S, HC, SP, NB, pass), fmt);
     } else {
       const int64_t total = (int64_t)rows * R * 64;
       for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
@@ -319,7 +332,7 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
           if (!pass) { if (c < Cin) v = w[(((int64_t)row * Cin + c) * R + r) * S + s]; }
           else if (c < Cout) v = w[(((int64_t)c * Cin + row) * R + (R - 1 - r)) * S + (S - 1 - s)];
         }
-        dst[i] = f2bf(v);
+        dst[i] = f2bits16(v, fmt);
       }
     }
   }
@@ -331,30 +344,41 @@ using namespace mcd;
 
 extern "C" {
 
-int mcd_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cs,
-                              int device, void* stream) {
+int mcd_nchw_f32_to_nhwc(const float* src, void* dst_f16, void* dst_bf16, int N, int C, int H, int W, int Cs,
+                         int device, void* stream) {
   MCD_ENTER(device);
-  MCD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nchw->nhwc: bad arguments");
+  MCD_REQUIRE(src && (dst_f16 || dst_bf16) && N > 0 && C > 0 && H > 0 && W > 0, "nchw->nhwc: bad arguments");
   MCD_REQUIRE(Cs >= C && Cs % 8 == 0, "nchw->nhwc: channel stride %d must be >= C=%d and %% 8 == 0",
               Cs, C);
   int64_t total = (int64_t)N * H * W * (Cs / 8);
   int grid = (int)min64((total + 255) / 256, 148 * 16);
-  nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      src, (__nv_bfloat16*)dst, N, C, H * W, Cs);
-  return check_launch("nchw_f32_to_nhwc_bf16");
+  nchw_f32_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      src, (__nv_bfloat16*)dst_f16, (__nv_bfloat16*)dst_bf16, N, C, H * W, Cs);
+  return check_launch("nchw_f32_to_nhwc");
 }
 
-int mcd_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cs,
-                              int device, void* stream) {
+int mcd_nhwc_to_nchw_f32(const void* src, int src_fmt, float* dst, int N, int C, int H, int W, int Cs,
+                         int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "nhwc->nchw: bad arguments");
+  MCD_REQUIRE(src_fmt == MCD_FMT_F16 || src_fmt == MCD_FMT_BF16, "nhwc->nchw: bad source format %d", src_fmt);
   MCD_REQUIRE(Cs >= C && Cs % 8 == 0, "nhwc->nchw: channel stride %d must be >= C=%d and %% 8 == 0",
               Cs, C);
   int64_t total = (int64_t)N * H * W * ((C + 7) / 8);
   int grid = (int)min64((total + 255) / 256, 148 * 16);
-  nhwc_bf16_to_nchw_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)src, dst, N, C, H * W, Cs);
-  return check_launch("nhwc_bf16_to_nchw_f32");
+  nhwc_to_nchw_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, src_fmt, dst, N, C, H * W, Cs);
+  return check_launch("nhwc_to_nchw_f32");
+}
+
+int mcd_convert16(const void* src, int src_fmt, void* dst, int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(src && dst && numel > 0 && numel % 8 == 0, "convert16: bad arguments");
+  MCD_REQUIRE(src_fmt == MCD_FMT_F16 || src_fmt == MCD_FMT_BF16, "convert16: bad source format %d", src_fmt);
+  const int64_t n8 = numel / 8;
+  int grid = (int)min64((n8 + 255) / 256, 148 * 16);
+  convert16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, src_fmt, n8);
+  return check_launch("convert16");
 }
 
 int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, int S, int mode,
@@ -366,7 +390,7 @@ int mcd_pack_weight(const float* w_oihw, void* dst, int Cout, int Cin, int R, in
   int kc_pad = round_up(mode ? Cout : Cin, 64);
   int64_t total = (int64_t)rows * R * S * kc_pad;
   int grid = (int)min64((total + 255) / 256, 148 * 16);
-  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
+  pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (uint16_t*)dst, Cout, Cin,
                                                               R, S, mode, rows, kc_pad);
   return check_launch("pack_weight");
 }
@@ -381,7 +405,7 @@ int mcd_pack_weight_rows(const float* w_oihw, void* dst, int Cout, int Cin, int 
   int rows = mode ? Cin : Cout;
   int64_t total = (int64_t)rows * R * 64;
   int grid = (int)min64((total + 255) / 256, 148 * 16);
-  pack_weight_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)dst, Cout, Cin,
+  pack_weight_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, (uint16_t*)dst, Cout, Cin,
                                                                    R, S, Cs, mode, rows);
   return check_launch("pack_weight_rows");
 }

@@ -1,4 +1,7 @@
-// loss.cu — fused per-pixel losses on planar (NCHW) bf16 logits.
+// loss.cu — fused per-pixel losses on planar (NCHW) full-resolution logits.  Logits (and their gradients, which
+// autograd requires to have the same dtype) are either bf16 - MCDStep's choice, half the bytes - or fp32, the
+// drop-in default that keeps `outputs.data.cpu().numpy()` of the reference testers working (f32 flag of every entry
+// point; the register-resident fast paths exist for bf16 only).
 //   CrossEntropyLoss2d = log_softmax(dim=1) + NLLLoss2d(weight, mean)        loss.py:7-13
 //   Diff2d             = mean |softmax(a) - softmax(b)|                      loss.py:93-100
 //   F.mse_loss (HHA regression)                              models/dilated_fcn.py:712,958
@@ -18,9 +21,16 @@ __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
 __device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return bf2f(*p); }
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = f2bf(v); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 
 // max and sum-exp over channels for a pixel pair
-__device__ __forceinline__ void softmax_stats(const __nv_bfloat16* base, int C, int64_t HW, float2* mx,
+template <typename T>
+__device__ __forceinline__ void softmax_stats(const T* base, int C, int64_t HW, float2* mx,
                                               float2* se) {
   float2 m = make_float2(-INFINITY, -INFINITY);
   for (int c = 0; c < C; ++c) {
@@ -49,8 +59,9 @@ __device__ __forceinline__ LabelInfo read_label(const int64_t* target, int64_t i
 }
 
 // grid-stride over pixel pairs; npairs = N*H*W/2 (W even)
+template <typename T>
 __global__ void __launch_bounds__(256)
-ce2d_fwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+ce2d_fwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target,
                 const float* __restrict__ weight, int64_t ignore_index, float* __restrict__ acc, int C,
                 int64_t HW, int64_t npairs) {
   __shared__ float red[32];
@@ -59,13 +70,13 @@ ce2d_fwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restr
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i * 2;
     const int64_t n = pix / HW, hw = pix % HW;
-    const __nv_bfloat16* base = logits + n * C * HW + hw;
+    const T* base = logits + n * C * HW + hw;
     float2 m, s;
     softmax_stats(base, C, HW, &m, &s);
     LabelInfo l0 = read_label(target, pix, weight, ignore_index, C);
     LabelInfo l1 = read_label(target, pix + 1, weight, ignore_index, C);
-    if (l0.y >= 0) { float xy = bf2f(base[l0.y * HW]); lsum += l0.w * (m.x + __logf(s.x) - xy); wsum += l0.w; }
-    if (l1.y >= 0) { float xy = bf2f(base[l1.y * HW + 1]); lsum += l1.w * (m.y + __logf(s.y) - xy); wsum += l1.w; }
+    if (l0.y >= 0) { float xy = ld1(base + l0.y * HW); lsum += l0.w * (m.x + __logf(s.x) - xy); wsum += l0.w; }
+    if (l1.y >= 0) { float xy = ld1(base + l1.y * HW + 1); lsum += l1.w * (m.y + __logf(s.y) - xy); wsum += l1.w; }
     bad += (l0.bad ? 1.f : 0.f) + (l1.bad ? 1.f : 0.f);
   }
   float r0 = block_sum(lsum, red), r1 = block_sum(wsum, red), r2 = block_sum(bad, red);
@@ -75,10 +86,11 @@ ce2d_fwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restr
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-ce2d_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ target,
+ce2d_bwd_kernel(const T* __restrict__ logits, const int64_t* __restrict__ target,
                 const float* __restrict__ weight, int64_t ignore_index, const float* __restrict__ acc,
-                const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dlogits, int C,
+                const float* __restrict__ gscale, T* __restrict__ dlogits, int C,
                 int64_t HW, int64_t npairs) {
   const float wtot = acc[1];
   const float coef = wtot > 0.f ? gscale[0] / wtot : 0.f;
@@ -86,8 +98,8 @@ ce2d_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restr
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i * 2;
     const int64_t n = pix / HW, hw = pix % HW;
-    const __nv_bfloat16* base = logits + n * C * HW + hw;
-    __nv_bfloat16* dbase = dlogits + n * C * HW + hw;
+    const T* base = logits + n * C * HW + hw;
+    T* dbase = dlogits + n * C * HW + hw;
     float2 m, s;
     softmax_stats(base, C, HW, &m, &s);
     LabelInfo l0 = read_label(target, pix, weight, ignore_index, C);
@@ -102,8 +114,9 @@ ce2d_bwd_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restr
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-diff2d_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+diff2d_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                   float* __restrict__ acc, float4* __restrict__ stats, int C, int64_t HW, int64_t npairs) {
   __shared__ float red[32];
   float lsum = 0.f;
@@ -111,8 +124,8 @@ diff2d_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i * 2;
     const int64_t n = pix / HW, hw = pix % HW;
-    const __nv_bfloat16* pa = a + n * C * HW + hw;
-    const __nv_bfloat16* pb = b + n * C * HW + hw;
+    const T* pa = a + n * C * HW + hw;
+    const T* pb = b + n * C * HW + hw;
     float2 ma, sa, mb, sb;
     softmax_stats(pa, C, HW, &ma, &sa);
     softmax_stats(pb, C, HW, &mb, &sb);
@@ -133,10 +146,11 @@ diff2d_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+diff2d_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
                   const float* __restrict__ gscale, const float4* __restrict__ stats,
-                  __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ db, float inv_numel, int C,
+                  T* __restrict__ da, T* __restrict__ db, float inv_numel, int C,
                   int64_t HW, int64_t npairs) {
   const float coef = gscale[0] * inv_numel;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs;
@@ -144,8 +158,8 @@ diff2d_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
     const int64_t pix = i * 2;
     const int64_t n = pix / HW, hw = pix % HW;
     const int64_t off = n * C * HW + hw;
-    const __nv_bfloat16* pa = a + off;
-    const __nv_bfloat16* pb = b + off;
+    const T* pa = a + off;
+    const T* pb = b + off;
     float2 ma, mb;
     float ia0, ia1, ib0, ib1;
     if (stats) {
@@ -329,28 +343,30 @@ diff2d_bwd_reg_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* 
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-mse_fwd_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target,
+mse_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ target,
                float* __restrict__ acc, int64_t numel) {
   __shared__ float red[32];
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float d = bf2f(pred[i]) - target[i];
+    float d = ld1(pred + i) - target[i];
     s = fmaf(d, d, s);
   }
   float r = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(acc, r);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-mse_bwd_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target,
-               const float* __restrict__ gscale, __nv_bfloat16* __restrict__ dpred, float inv_numel,
+mse_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ target,
+               const float* __restrict__ gscale, T* __restrict__ dpred, float inv_numel,
                int64_t numel) {
   const float coef = 2.f * gscale[0] * inv_numel;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
        i += (int64_t)gridDim.x * blockDim.x)
-    dpred[i] = f2bf(coef * (bf2f(pred[i]) - target[i]));
+    st1(dpred + i, coef * (ld1(pred + i) - target[i]));
 }
 
 __global__ void __launch_bounds__(256)
@@ -366,18 +382,20 @@ sum_f32_kernel(const float* __restrict__ x, float* __restrict__ acc, int64_t num
 
 __device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + __expf(-v)); }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-sigmoid3_bce_fwd_kernel(const __nv_bfloat16* __restrict__ h1, const __nv_bfloat16* __restrict__ h2,
-                        const __nv_bfloat16* __restrict__ h3, const float* __restrict__ target,
+sigmoid3_bce_fwd_kernel(const T* __restrict__ h1, const T* __restrict__ h2,
+                        const T* __restrict__ h3, const float* __restrict__ target,
                         const float* __restrict__ tsum, float* __restrict__ acc,
-                        __nv_bfloat16* __restrict__ p_out, int64_t numel) {
+                        T* __restrict__ p_out, float inv_global, int64_t numel) {
   __shared__ float red[32];
-  const float beta = tsum ? 1.f - tsum[0] / (float)numel : 0.f;
+  // beta = 1 - mean(target) over the GLOBAL batch (loss.py:133; tsum is all-reduced under data parallelism)
+  const float beta = tsum ? 1.f - tsum[0] * inv_global : 0.f;
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float p = (sigmoidf(bf2f(h1[i])) + sigmoidf(bf2f(h2[i])) + sigmoidf(bf2f(h3[i]))) * (1.f / 3.f);
-    if (p_out) p_out[i] = f2bf(p);
+    float p = (sigmoidf(ld1(h1 + i)) + sigmoidf(ld1(h2 + i)) + sigmoidf(ld1(h3 + i))) * (1.f / 3.f);
+    if (p_out) st1(p_out + i, p);
     if (target) {
       float t = target[i];
       float w = 1.f - beta + (2.f * beta - 1.f) * t;
@@ -391,30 +409,63 @@ sigmoid3_bce_fwd_kernel(const __nv_bfloat16* __restrict__ h1, const __nv_bfloat1
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-sigmoid3_bce_bwd_kernel(const __nv_bfloat16* __restrict__ h1, const __nv_bfloat16* __restrict__ h2,
-                        const __nv_bfloat16* __restrict__ h3, const float* __restrict__ target,
+sigmoid3_bce_bwd_kernel(const T* __restrict__ h1, const T* __restrict__ h2,
+                        const T* __restrict__ h3, const float* __restrict__ target,
                         const float* __restrict__ tsum, const float* __restrict__ gscale,
-                        __nv_bfloat16* __restrict__ dh1, __nv_bfloat16* __restrict__ dh2,
-                        __nv_bfloat16* __restrict__ dh3, int64_t numel) {
-  const float beta = 1.f - tsum[0] / (float)numel;
+                        T* __restrict__ dh1, T* __restrict__ dh2,
+                        T* __restrict__ dh3, float inv_global, int64_t numel) {
+  const float beta = 1.f - tsum[0] * inv_global;
   const float coef = gscale[0] / (float)numel;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float s1 = sigmoidf(bf2f(h1[i])), s2 = sigmoidf(bf2f(h2[i])), s3 = sigmoidf(bf2f(h3[i]));
+    float s1 = sigmoidf(ld1(h1 + i)), s2 = sigmoidf(ld1(h2 + i)), s3 = sigmoidf(ld1(h3 + i));
     float p = (s1 + s2 + s3) * (1.f / 3.f);
     float t = target[i];
     float w = 1.f - beta + (2.f * beta - 1.f) * t;
     // F.binary_cross_entropy backward: w * (p - t) / max(p*(1-p), 1e-12)
     float dp = coef * w * (p - t) / fmaxf(p * (1.f - p), 1e-12f) * (1.f / 3.f);
-    dh1[i] = f2bf(dp * s1 * (1.f - s1));
-    dh2[i] = f2bf(dp * s2 * (1.f - s2));
-    dh3[i] = f2bf(dp * s3 * (1.f - s3));
+    st1(dh1 + i, dp * s1 * (1.f - s1));
+    st1(dh2 + i, dp * s2 * (1.f - s2));
+    st1(dh3 + i, dp * s3 * (1.f - s3));
   }
 }
 
+// bce2d on a probability map (loss.py:130-138): beta = 1 - mean(t); w = 1 - beta + (2 beta - 1) t;
+// F.binary_cross_entropy(p, t, w) with torch's log clamp at -100.  acc[0] += sum w * bce
 __global__ void __launch_bounds__(256)
-argmax_entropy_kernel(const __nv_bfloat16* __restrict__ logits, int64_t* __restrict__ labels,
+bce2d_fwd_kernel(const float* __restrict__ p, const float* __restrict__ target, const float* __restrict__ tsum,
+                 float* __restrict__ acc, float inv_global, int64_t numel) {
+  __shared__ float red[32];
+  const float beta = 1.f - tsum[0] * inv_global;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = p[i], t = target[i];
+    const float w = 1.f - beta + (2.f * beta - 1.f) * t;
+    const float lp = fmaxf(logf(pi), -100.f), lq = fmaxf(logf(1.f - pi), -100.f);
+    s -= w * (t * lp + (1.f - t) * lq);
+  }
+  float r = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, r);
+}
+
+// dp = gscale / numel * w * (p - t) / max(p (1 - p), 1e-12)   (F.binary_cross_entropy backward)
+__global__ void __launch_bounds__(256)
+bce2d_bwd_kernel(const float* __restrict__ p, const float* __restrict__ target, const float* __restrict__ tsum,
+                 const float* __restrict__ gscale, float* __restrict__ dp, float inv_global, int64_t numel) {
+  const float beta = 1.f - tsum[0] * inv_global;
+  const float coef = gscale[0] / (float)numel;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = p[i], t = target[i];
+    const float w = 1.f - beta + (2.f * beta - 1.f) * t;
+    dp[i] = coef * w * (pi - t) / fmaxf(pi * (1.f - pi), 1e-12f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_entropy_kernel(const T* __restrict__ logits, int64_t* __restrict__ labels,
                       float* __restrict__ acc, int C, int C_arg, int64_t HW, int64_t npairs) {
   __shared__ float red[32];
   float esum = 0.f;
@@ -422,7 +473,7 @@ argmax_entropy_kernel(const __nv_bfloat16* __restrict__ logits, int64_t* __restr
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i * 2;
     const int64_t n = pix / HW, hw = pix % HW;
-    const __nv_bfloat16* base = logits + n * C * HW + hw;
+    const T* base = logits + n * C * HW + hw;
     float2 m, s;
     softmax_stats(base, C, HW, &m, &s);
     float b0 = -INFINITY, b1 = -INFINITY;
@@ -475,91 +526,116 @@ using namespace mcd;
   MCD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, name ": bad sizes");                             \
   MCD_REQUIRE(W % 2 == 0, name ": W must be even (pixel-pair vectorisation), got %d", W)
 
+typedef __nv_bfloat16 bf16_t;
+
 extern "C" {
 
-int mcd_ce2d_fwd(const void* logits, const int64_t* target, const float* weight,
+int mcd_ce2d_fwd(const void* logits, int f32, const int64_t* target, const float* weight,
                  int64_t ignore_index, float* acc, int N, int C, int H, int W, int device,
                  void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(logits && target && acc, "ce2d_fwd: null pointer");
   MCD_CHECK_PLANAR("ce2d_fwd");
   int64_t npairs = (int64_t)N * H * W / 2;
-  if (C <= kRegC)
-    ce2d_fwd_reg_kernel<<<grid_reg(npairs), 128, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, C, (int64_t)H * W, npairs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32)
+    ce2d_fwd_kernel<float><<<grid_for(npairs), 256, 0, st>>>((const float*)logits, target, weight, ignore_index, acc,
+                                                             C, (int64_t)H * W, npairs);
+  else if (C <= kRegC)
+    ce2d_fwd_reg_kernel<<<grid_reg(npairs), 128, 0, st>>>((const bf16_t*)logits, target, weight, ignore_index, acc, C,
+                                                          (int64_t)H * W, npairs);
   else
-    ce2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, C, (int64_t)H * W, npairs);
+    ce2d_fwd_kernel<bf16_t><<<grid_for(npairs), 256, 0, st>>>((const bf16_t*)logits, target, weight, ignore_index,
+                                                              acc, C, (int64_t)H * W, npairs);
   return check_launch("ce2d_fwd");
 }
 
-int mcd_ce2d_bwd(const void* logits, const int64_t* target, const float* weight,
+int mcd_ce2d_bwd(const void* logits, int f32, const int64_t* target, const float* weight,
                  int64_t ignore_index, const float* acc, const float* gscale, void* dlogits, int N,
                  int C, int H, int W, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(logits && target && acc && gscale && dlogits, "ce2d_bwd: null pointer");
   MCD_CHECK_PLANAR("ce2d_bwd");
   int64_t npairs = (int64_t)N * H * W / 2;
-  ce2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)logits, target, weight, ignore_index, acc, gscale, (__nv_bfloat16*)dlogits,
-        C, (int64_t)H * W, npairs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32)
+    ce2d_bwd_kernel<float><<<grid_for(npairs), 256, 0, st>>>((const float*)logits, target, weight, ignore_index, acc,
+                                                             gscale, (float*)dlogits, C, (int64_t)H * W, npairs);
+  else
+    ce2d_bwd_kernel<bf16_t><<<grid_for(npairs), 256, 0, st>>>((const bf16_t*)logits, target, weight, ignore_index,
+                                                              acc, gscale, (bf16_t*)dlogits, C, (int64_t)H * W,
+                                                              npairs);
   return check_launch("ce2d_bwd");
 }
 
-int mcd_diff2d_fwd(const void* a, const void* b, float* acc, float* stats, int N, int C, int H, int W,
+int mcd_diff2d_fwd(const void* a, const void* b, int f32, float* acc, float* stats, int N, int C, int H, int W,
                    int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(a && b && acc, "diff2d_fwd: null pointer");
   MCD_CHECK_PLANAR("diff2d_fwd");
   int64_t npairs = (int64_t)N * H * W / 2;
-  if (C <= kRegC)
-    diff2d_fwd_reg_kernel<<<grid_reg(npairs), 128, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, (float4*)stats, C, (int64_t)H * W, npairs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32)
+    diff2d_fwd_kernel<float><<<grid_for(npairs), 256, 0, st>>>((const float*)a, (const float*)b, acc, (float4*)stats,
+                                                               C, (int64_t)H * W, npairs);
+  else if (C <= kRegC)
+    diff2d_fwd_reg_kernel<<<grid_reg(npairs), 128, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, acc, (float4*)stats,
+                                                            C, (int64_t)H * W, npairs);
   else
-    diff2d_fwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, acc, (float4*)stats, C, (int64_t)H * W, npairs);
+    diff2d_fwd_kernel<bf16_t><<<grid_for(npairs), 256, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, acc,
+                                                                (float4*)stats, C, (int64_t)H * W, npairs);
   return check_launch("diff2d_fwd");
 }
 
-int mcd_diff2d_bwd(const void* a, const void* b, const float* gscale, const float* stats, void* da, void* db,
-                   int N, int C, int H, int W, int device, void* stream) {
+int mcd_diff2d_bwd(const void* a, const void* b, int f32, const float* gscale, const float* stats, void* da,
+                   void* db, int N, int C, int H, int W, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(a && b && gscale && da && db, "diff2d_bwd: null pointer");
   MCD_CHECK_PLANAR("diff2d_bwd");
   int64_t npairs = (int64_t)N * H * W / 2;
   float inv = (float)(1.0 / ((double)N * C * H * W));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32) {
+    diff2d_bwd_kernel<float><<<grid_for(npairs), 256, 0, st>>>((const float*)a, (const float*)b, gscale,
+                                                               (const float4*)stats, (float*)da, (float*)db, inv, C,
+                                                               (int64_t)H * W, npairs);
+    return check_launch("diff2d_bwd");
+  }
   static int use_reg = -1;
   // measured (r01b, 22 pairs): register-resident 836 us vs multi-pass 760 us per launch - 84 live packed logits
   // + the two passes spill at 255 registers; opt-in only
   if (use_reg < 0) { const char* e = getenv("MCD_DIFF2D_BWD_REG"); use_reg = (e && e[0] == '1') ? 1 : 0; }
   if (use_reg && C <= kRegC) {
-    diff2d_bwd_reg_kernel<<<grid_reg(npairs), 128, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (__nv_bfloat16*)da, (__nv_bfloat16*)db, inv, C,
-        (int64_t)H * W, npairs);
+    diff2d_bwd_reg_kernel<<<grid_reg(npairs), 128, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, gscale, (bf16_t*)da,
+                                                            (bf16_t*)db, inv, C, (int64_t)H * W, npairs);
     return check_launch("diff2d_bwd");
   }
-  diff2d_bwd_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gscale, (const float4*)stats, (__nv_bfloat16*)da,
-        (__nv_bfloat16*)db, inv, C, (int64_t)H * W, npairs);
+  diff2d_bwd_kernel<bf16_t><<<grid_for(npairs), 256, 0, st>>>((const bf16_t*)a, (const bf16_t*)b, gscale,
+                                                              (const float4*)stats, (bf16_t*)da, (bf16_t*)db, inv, C,
+                                                              (int64_t)H * W, npairs);
   return check_launch("diff2d_bwd");
 }
 
-int mcd_mse_fwd(const void* pred, const float* target, float* acc, int64_t numel, int device,
+int mcd_mse_fwd(const void* pred, int f32, const float* target, float* acc, int64_t numel, int device,
                 void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(pred && target && acc && numel > 0, "mse_fwd: bad arguments");
-  mse_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)pred, target,
-                                                                     acc, numel);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32) mse_fwd_kernel<float><<<grid_for(numel), 256, 0, st>>>((const float*)pred, target, acc, numel);
+  else mse_fwd_kernel<bf16_t><<<grid_for(numel), 256, 0, st>>>((const bf16_t*)pred, target, acc, numel);
   return check_launch("mse_fwd");
 }
 
-int mcd_mse_bwd(const void* pred, const float* target, const float* gscale, void* dpred,
+int mcd_mse_bwd(const void* pred, int f32, const float* target, const float* gscale, void* dpred,
                 int64_t numel, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(pred && target && gscale && dpred && numel > 0, "mse_bwd: bad arguments");
-  mse_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)pred, target, gscale, (__nv_bfloat16*)dpred, (float)(1.0 / (double)numel),
-      numel);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv = (float)(1.0 / (double)numel);
+  if (f32) mse_bwd_kernel<float><<<grid_for(numel), 256, 0, st>>>((const float*)pred, target, gscale, (float*)dpred,
+                                                                  inv, numel);
+  else mse_bwd_kernel<bf16_t><<<grid_for(numel), 256, 0, st>>>((const bf16_t*)pred, target, gscale, (bf16_t*)dpred,
+                                                               inv, numel);
   return check_launch("mse_bwd");
 }
 
@@ -570,40 +646,77 @@ int mcd_sum_f32(const float* x, float* acc, int64_t numel, int device, void* str
   return check_launch("sum_f32");
 }
 
-int mcd_sigmoid3_bce_fwd(const void* h1, const void* h2, const void* h3, const float* target,
-                         const float* tsum, float* acc, void* p_out, int64_t numel, int device,
-                         void* stream) {
+int mcd_sigmoid3_bce_fwd(const void* h1, const void* h2, const void* h3, int f32, const float* target,
+                         const float* tsum, float* acc, void* p_out, int64_t numel, int64_t numel_global,
+                         int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(h1 && h2 && h3 && numel > 0, "sigmoid3_bce_fwd: bad arguments");
   MCD_REQUIRE(!target || (tsum && acc), "sigmoid3_bce_fwd: target needs tsum and acc");
   MCD_REQUIRE(target || p_out, "sigmoid3_bce_fwd: nothing to compute");
-  sigmoid3_bce_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)h1, (const __nv_bfloat16*)h2, (const __nv_bfloat16*)h3, target, tsum,
-      target ? acc : nullptr, (__nv_bfloat16*)p_out, numel);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_global = (float)(1.0 / (double)(numel_global > 0 ? numel_global : numel));
+  if (f32)
+    sigmoid3_bce_fwd_kernel<float><<<grid_for(numel), 256, 0, st>>>(
+        (const float*)h1, (const float*)h2, (const float*)h3, target, tsum, target ? acc : nullptr, (float*)p_out,
+        inv_global, numel);
+  else
+    sigmoid3_bce_fwd_kernel<bf16_t><<<grid_for(numel), 256, 0, st>>>(
+        (const bf16_t*)h1, (const bf16_t*)h2, (const bf16_t*)h3, target, tsum, target ? acc : nullptr,
+        (bf16_t*)p_out, inv_global, numel);
   return check_launch("sigmoid3_bce_fwd");
 }
 
-int mcd_sigmoid3_bce_bwd(const void* h1, const void* h2, const void* h3, const float* target,
+int mcd_sigmoid3_bce_bwd(const void* h1, const void* h2, const void* h3, int f32, const float* target,
                          const float* tsum, const float* gscale, void* dh1, void* dh2, void* dh3,
-                         int64_t numel, int device, void* stream) {
+                         int64_t numel, int64_t numel_global, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(h1 && h2 && h3 && target && tsum && gscale && dh1 && dh2 && dh3 && numel > 0,
               "sigmoid3_bce_bwd: bad arguments");
-  sigmoid3_bce_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)h1, (const __nv_bfloat16*)h2, (const __nv_bfloat16*)h3, target, tsum, gscale,
-      (__nv_bfloat16*)dh1, (__nv_bfloat16*)dh2, (__nv_bfloat16*)dh3, numel);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_global = (float)(1.0 / (double)(numel_global > 0 ? numel_global : numel));
+  if (f32)
+    sigmoid3_bce_bwd_kernel<float><<<grid_for(numel), 256, 0, st>>>(
+        (const float*)h1, (const float*)h2, (const float*)h3, target, tsum, gscale, (float*)dh1, (float*)dh2,
+        (float*)dh3, inv_global, numel);
+  else
+    sigmoid3_bce_bwd_kernel<bf16_t><<<grid_for(numel), 256, 0, st>>>(
+        (const bf16_t*)h1, (const bf16_t*)h2, (const bf16_t*)h3, target, tsum, gscale, (bf16_t*)dh1, (bf16_t*)dh2,
+        (bf16_t*)dh3, inv_global, numel);
   return check_launch("sigmoid3_bce_bwd");
 }
 
-int mcd_argmax_entropy(const void* logits, int64_t* labels, float* acc, int N, int C, int C_arg,
+int mcd_bce2d_fwd(const float* p, const float* target, const float* tsum, float* acc, int64_t numel,
+                  int64_t numel_global, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(p && target && tsum && acc && numel > 0, "bce2d_fwd: bad arguments");
+  const float inv_global = (float)(1.0 / (double)(numel_global > 0 ? numel_global : numel));
+  bce2d_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(p, target, tsum, acc, inv_global, numel);
+  return check_launch("bce2d_fwd");
+}
+
+int mcd_bce2d_bwd(const float* p, const float* target, const float* tsum, const float* gscale, float* dp,
+                  int64_t numel, int64_t numel_global, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(p && target && tsum && gscale && dp && numel > 0, "bce2d_bwd: bad arguments");
+  const float inv_global = (float)(1.0 / (double)(numel_global > 0 ? numel_global : numel));
+  bce2d_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(p, target, tsum, gscale, dp, inv_global, numel);
+  return check_launch("bce2d_bwd");
+}
+
+int mcd_argmax_entropy(const void* logits, int f32, int64_t* labels, float* acc, int N, int C, int C_arg,
                        int H, int W, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(logits && (labels || acc), "argmax_entropy: null pointer");
   MCD_CHECK_PLANAR("argmax_entropy");
   MCD_REQUIRE(C_arg >= 1 && C_arg <= C, "argmax_entropy: C_arg=%d out of range", C_arg);
   int64_t npairs = (int64_t)N * H * W / 2;
-  argmax_entropy_kernel<<<grid_for(npairs), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)logits, labels, acc, C, C_arg, (int64_t)H * W, npairs);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32)
+    argmax_entropy_kernel<float><<<grid_for(npairs), 256, 0, st>>>((const float*)logits, labels, acc, C, C_arg,
+                                                                   (int64_t)H * W, npairs);
+  else
+    argmax_entropy_kernel<bf16_t><<<grid_for(npairs), 256, 0, st>>>((const bf16_t*)logits, labels, acc, C, C_arg,
+                                                                    (int64_t)H * W, npairs);
   return check_launch("argmax_entropy");
 }
 

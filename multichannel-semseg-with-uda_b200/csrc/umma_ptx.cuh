@@ -95,7 +95,7 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA.
+// D[tmem] (+)= A[smem] * B[smem], 16-bit inputs (format in idesc), fp32 accumulate, single CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -219,11 +219,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
   return d;
 }
-// instruction descriptor: kind::f16, bf16 x bf16 -> fp32, dense.  major: 0 = K-major, 1 = MN-major
+// instruction descriptor: kind::f16, fp32 accumulate, dense.  major: 0 = K-major, 1 = MN-major.  fmt: element format
+// of BOTH operands (0 = IEEE half, 1 = bfloat16): the hardware rejects a_format != b_format (illegal instruction,
+// profiles/r02_exp_mixed_format.txt).
+__host__ __device__ constexpr uint32_t instr_desc_16(uint32_t M, uint32_t N, uint32_t a_mn_major,
+                                                     uint32_t b_mn_major, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t instr_desc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
                                                        uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
-         ((N >> 3) << 17) | ((M >> 4) << 24);
+  return instr_desc_16(M, N, a_mn_major, b_mn_major, 1u);
 }
 
 }  // namespace ptx

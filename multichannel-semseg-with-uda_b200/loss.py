@@ -22,9 +22,10 @@ _CHECK_LABELS = os.environ.get("MCD_CHECK_LABELS", "0") == "1"
 
 
 def _logits(x):
-    """full-resolution predictions are bf16 NCHW-contiguous; convert anything else (differentiably)."""
-    if x.dtype != BF16:
-        x = x.to(BF16)
+    """full-resolution predictions are bf16 or fp32 NCHW-contiguous tensors (mcd_b200.nn.logits_dtype); anything
+    else is converted to fp32 (differentiably)."""
+    if x.dtype not in (BF16, F32):
+        x = x.float()
     return x.contiguous()
 
 
@@ -135,19 +136,60 @@ def mse_loss(pred, target):
     return _MSEFn.apply(_logits(pred), target.to(F32).contiguous())
 
 
+# data-parallel runs (one process per GPU): batch-GLOBAL statistics inside a criterion are all-reduced over this
+# group - the class-balance beta of bce2d (loss.py:133 `1 - mean(target)`; what nn.DataParallel computes on the
+# gathered outputs).  The loss VALUES stay local means; the step runner divides by the world size so that
+# SUM-all-reduced gradients equal the global-batch gradients (mcd_b200/parallel.py).
+_dp_group = False
+
+
+def set_process_group(group=None):
+    """None = the default group (when torch.distributed is initialised with world > 1), False = single process."""
+    global _dp_group
+    import torch.distributed as dist
+    ok = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    _dp_group = group if ok else False
+
+
+def _target_sum(target):
+    """(sum(target) over the global batch, global element count)"""
+    tsum = ops.sum_f32(target)
+    if _dp_group is False:
+        return tsum, target.numel()
+    import torch.distributed as dist
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM, group=_dp_group)
+    return tsum, target.numel() * dist.get_world_size(_dp_group)
+
+
 class _Sigmoid3BCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h1, h2, h3, target):
-        tsum = ops.sum_f32(target)
-        acc, _ = ops.sigmoid3_bce_fwd(h1, h2, h3, target, tsum)
+        tsum, nglobal = _target_sum(target)
+        acc, _ = ops.sigmoid3_bce_fwd(h1, h2, h3, target, tsum, numel_global=nglobal)
         ctx.save_for_backward(h1, h2, h3, target, tsum)
+        ctx.nglobal = nglobal
         return acc[0] / float(h1.numel())
 
     @staticmethod
     def backward(ctx, go):
         h1, h2, h3, target, tsum = ctx.saved_tensors
-        d1, d2, d3 = ops.sigmoid3_bce_bwd(h1, h2, h3, target, tsum, _gscale(go))
+        d1, d2, d3 = ops.sigmoid3_bce_bwd(h1, h2, h3, target, tsum, _gscale(go), numel_global=ctx.nglobal)
         return d1, d2, d3, None
+
+
+class _BCE2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, target):
+        tsum, nglobal = _target_sum(target)
+        acc = ops.bce2d_fwd(p, target, tsum, numel_global=nglobal)
+        ctx.save_for_backward(p, target, tsum)
+        ctx.nglobal = nglobal
+        return acc[0] / float(p.numel())
+
+    @staticmethod
+    def backward(ctx, go):
+        p, target, tsum = ctx.saved_tensors
+        return ops.bce2d_bwd(p, target, tsum, _gscale(go), numel_global=ctx.nglobal), None
 
 
 def sigmoid3_bce2d(h1, h2, h3, target):
@@ -165,10 +207,13 @@ def sigmoid3_mean(h1, h2, h3):
 
 
 def bce2d(input, target):
-    """Class-balanced BCE on a probability map (reference loss.py:131-138).  The MCD decoders call the fused
-    `sigmoid3_bce2d` instead; a bare probability input has no kernel on the hot path."""
-    raise NotImplementedError("use loss.sigmoid3_bce2d(h1, h2, h3, target): the boundary head fuses the "
-                              "sigmoid average with bce2d")
+    """Class-balanced binary cross entropy on a probability map (reference loss.py:130-138):
+    beta = 1 - mean(target); weights = 1 - beta + (2 beta - 1) target; F.binary_cross_entropy(input, target, weights)
+    (mean, torch's log clamp at -100).  One forward and one backward kernel over fp32 maps; the MCD decoders call the
+    fused `sigmoid3_bce2d`, which never materialises the probability map."""
+    assert not target.requires_grad, "nn criterions don't compute the gradient w.r.t. targets"
+    assert input.shape == target.shape, "bce2d: input %s vs target %s" % (tuple(input.shape), tuple(target.shape))
+    return _BCE2dFn.apply(input.to(F32).contiguous(), target.to(F32).contiguous())
 
 
 def get_prob_distance_criterion(criterion_name, n_class=None):

@@ -11,10 +11,11 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # MCD_LIB_PATH: an alternative build of the same library (A/B measurements of compile-time variants)
 LIB_PATH = os.environ.get("MCD_LIB_PATH") or os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
+FMT_F16, FMT_BF16 = 0, 1      # 16-bit element formats: forward tensors IEEE half, gradients / wgrad twins bfloat16
 
 
 class McdError(RuntimeError):
@@ -37,8 +38,9 @@ _SIGNATURES = {
     "mcd_version": (c_int, []),
     "mcd_launch_count": (c_int64, []),
     "mcd_check_device": (c_int, [c_int]),
-    "mcd_nchw_f32_to_nhwc_bf16": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_nhwc_bf16_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_nchw_f32_to_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_nhwc_to_nchw_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_convert16": (c_int, [P, c_int, P, c_int64, c_int, P]),
     "mcd_pack_weight": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_pack_weight_rows": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_pack_weight_rowconv": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
@@ -56,25 +58,27 @@ _SIGNATURES = {
     "mcd_bn_finalize": (c_int, [P, c_int64, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, c_int,
                                 c_int, P]),
     "mcd_bn_forward": (c_int, [P, P, P, P, P, P, P, c_float, c_float, c_int, P, P, P, P, P, P, P, P, c_float,
-                               c_float, c_int, P, c_int, P, c_int64, c_int, c_int, c_int, P]),
-    "mcd_bn_apply": (c_int, [P, P, P, P, P, P, c_int, P, c_int64, c_int, c_int, c_int, P]),
+                               c_float, c_int, P, c_int, P, P, c_int64, c_int, c_int, c_int, P]),
+    "mcd_bn_apply": (c_int, [P, P, P, P, P, P, c_int, P, P, c_int64, c_int, c_int, c_int, P]),
     "mcd_bn_bwd_reduce": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int64, c_int, c_int, c_int, P]),
     "mcd_bn_bwd_apply": (c_int, [P, P, P, P, P, P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P,
                                  P, c_int, c_int64, c_int, c_int, c_int, P]),
-    "mcd_deconv16s8_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_deconv16s8_bwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_deconv16s8_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_deconv16s8_bwd": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_bilinear_up_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_bilinear_up_bwd": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_ce2d_fwd": (c_int, [P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_ce2d_bwd": (c_int, [P, P, P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_diff2d_fwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_diff2d_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    "mcd_mse_fwd": (c_int, [P, P, P, c_int64, c_int, P]),
-    "mcd_mse_bwd": (c_int, [P, P, P, P, c_int64, c_int, P]),
+    "mcd_ce2d_fwd": (c_int, [P, c_int, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_ce2d_bwd": (c_int, [P, c_int, P, P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_diff2d_fwd": (c_int, [P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_diff2d_bwd": (c_int, [P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_mse_fwd": (c_int, [P, c_int, P, P, c_int64, c_int, P]),
+    "mcd_mse_bwd": (c_int, [P, c_int, P, P, P, c_int64, c_int, P]),
     "mcd_sum_f32": (c_int, [P, P, c_int64, c_int, P]),
-    "mcd_sigmoid3_bce_fwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, P]),
-    "mcd_sigmoid3_bce_bwd": (c_int, [P, P, P, P, P, P, P, P, P, c_int64, c_int, P]),
-    "mcd_argmax_entropy": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_sigmoid3_bce_fwd": (c_int, [P, P, P, c_int, P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mcd_sigmoid3_bce_bwd": (c_int, [P, P, P, c_int, P, P, P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mcd_bce2d_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mcd_bce2d_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mcd_argmax_entropy": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_int, c_int, P]),
 }
 EXPORTS = tuple(_SIGNATURES)

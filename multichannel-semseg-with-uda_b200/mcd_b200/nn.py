@@ -4,6 +4,11 @@ The modules subclass the stock torch containers (`nn.Conv2d`, `nn.BatchNorm2d`, 
 only so that parameters, buffers, initialisation and state_dict keys are byte-compatible with the
 reference's checkpoints (adapt_trainer.py:232-245, adapt_tester.py:79-83); their `forward` never calls
 a stock torch kernel - it launches the library's kernels through `ops`.
+
+Numerics (mcd_b200/ops.py): forward activations are IEEE half, gradients bfloat16.  The unit of execution is
+conv -> BatchNorm (+ residual) -> ReLU as ONE autograd Function (`_UnitFn`): the IEEE-half pre-BatchNorm tensor never
+crosses an autograd edge, what does is the unit's output as a bfloat16 twin (autograd requires gradients in the dtype
+of the tensor they belong to, and gradients are bfloat16) that carries the IEEE-half original as `_mcd_h16`.
 """
 import os
 
@@ -12,7 +17,7 @@ import torch.nn as nn
 
 from . import ops
 
-BF16, F32 = torch.bfloat16, torch.float32
+BF16, F16, F32 = torch.bfloat16, torch.float16, torch.float32
 
 # number of identical forward passes one BatchNorm forward stands for (MCDStep re-uses the phase-B target
 # forward for the first phase-C step): the running statistics then take that many momentum updates at once.
@@ -32,6 +37,39 @@ class bn_update_repeat:
         _bn_repeat = self.prev
 
 
+# dtype of the full-resolution predictions the heads / decoders return: fp32 is the drop-in default (the reference
+# testers call `.data.cpu().numpy()` on them, adapt_tester.py:114-118); MCDStep switches to bfloat16, which halves
+# the traffic of the head and loss kernels - the largest tensors of the step.
+_logits_dtype = F32
+
+
+class logits_dtype:
+    """`with logits_dtype(torch.bfloat16):` or `logits_dtype.set(...)`."""
+
+    def __init__(self, dtype):
+        assert dtype in (BF16, F32)
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _logits_dtype
+        self.prev, _logits_dtype = _logits_dtype, self.dtype
+
+    def __exit__(self, *a):
+        global _logits_dtype
+        _logits_dtype = self.prev
+
+    @staticmethod
+    def set(dtype):
+        global _logits_dtype
+        assert dtype in (BF16, F32)
+        prev, _logits_dtype = _logits_dtype, dtype
+        return prev
+
+    @staticmethod
+    def get():
+        return _logits_dtype
+
+
 _overlap_wgrad = True
 _side_streams = {}
 
@@ -45,7 +83,7 @@ def _side_stream(device):
 
 class DirectGrads:
     """Context of MCDStep's backward passes: convolution weight gradients are written by the wgrad kernels
-    directly into param.grad on the side stream (see _ConvFn.backward) instead of travelling through autograd.
+    directly into param.grad on the side stream (see _conv_backward) instead of travelling through autograd.
     `join()` makes the main stream wait for them and releases the operands that were kept alive."""
 
     def __init__(self, defer=False):
@@ -92,114 +130,129 @@ def set_overlap_wgrad(flag):
 
 
 def _as_nhwc_grad(dy):
-    """Gradients arriving from autograd for an nhwc activation: make them nhwc bf16 again."""
-    if ops.is_nhwc(dy):
+    """Gradients arriving from autograd for an nhwc activation: make them nhwc bfloat16 again."""
+    if ops.is_nhwc(dy) and dy.dtype == BF16:
         return dy
-    if dy.dtype == BF16 and dy.shape[1] % 8 == 0:
-        return dy.contiguous(memory_format=torch.channels_last)
-    return ops.to_nhwc(dy)
+    if dy.dtype in (BF16, F16) and dy.shape[1] % 8 == 0:
+        return ops.to_nhwc(dy.contiguous(memory_format=torch.channels_last), grad=True)
+    return ops.to_nhwc(dy, grad=True)
 
 
 # ---------------------------------------------------------------------------------------------
+def _weight_tag(w):
+    return (w._version, w.data_ptr(), getattr(w, "_mcd_step", 0))
+
+
+def _conv_backward(mod, g, x, dy, need_dx, need_dw, want_db, bn_y, w_tag=None):
+    """dgrad + wgrad of one convolution.  x: the input handle (its bf16 twin feeds wgrad and the ReLU mask of the fused
+    dgrad epilogue), dy: bf16 nhwc gradient of the output, bn_y: see _UnitFn.  Returns (dx, dw, db); in
+    direct-gradient mode dw / db are written in place and None is returned for them."""
+    dx = dw = db = None
+    only_db = want_db and not need_dw         # frozen weight, trainable bias: dbias comes with the wgrad call
+    need_dw = need_dw or want_db
+    if w_tag is not None and need_dx and w_tag != _weight_tag(mod.weight):
+        # dgrad re-reads the packed weights at backward time: they must still be the ones the forward used
+        raise RuntimeError("mcd_b200: the weights of a convolution were modified between its forward and its "
+                           "backward (optimizer step inside a forward/backward pair?)")
+    if _direct is not None and need_dw:
+        # direct-gradient mode (MCDStep): wgrad is enqueued on the side stream and writes straight into
+        # param.grad (or its all-reduce bucket view); nothing is returned to autograd for the weights, so no
+        # accumulation kernel runs and the main stream goes on with dgrad / BatchNorm backward while the
+        # tensor-bound wgrad kernels trail behind.  MCDStep joins the side stream before optimizer.step().
+        main = torch.cuda.current_stream(dy.device)
+        # set_overlap_wgrad(False): everything on the main stream (per-kernel timing in bench.py)
+        side = _side_stream(dy.device) if _overlap_wgrad else main
+        ready = torch.cuda.Event()
+        ready.record(main)                    # dy (and everything before it) is complete here
+        w, b = mod.weight, mod.bias
+        acc = getattr(w, "_mcd_written", False) and w.grad is not None
+        defer = getattr(mod, "_mcd_defer", None) if (_direct.defer and not only_db) else None
+        if defer is not None and defer[0] != g.key():
+            defer = None
+        if defer is not None and getattr(w, "_mcd_deferred", False):
+            raise RuntimeError("mcd_b200: a deferred weight gradient was produced twice before optimizer_g.step()")
+        if defer is None and w.grad is None and not only_db:
+            w.grad = torch.empty_like(w)
+        if want_db and b.grad is None:
+            b.grad = torch.empty_like(b)
+    # dgrad is enqueued FIRST: it heads the critical path (dgrad -> BatchNorm backward -> next dgrad) and
+    # cannot share an SM with the persistent wgrad CTAs (both want ~190 KB of shared memory); the wgrad
+    # that follows on the side stream then overlaps the memory-bound BatchNorm kernels of the next unit.
+    add = _direct.stash.pop(x.data_ptr(), None) if _direct is not None else None   # identity-shortcut gradient
+    if need_dx and bn_y is not None and _fuse_bn_bwd and _direct is not None:
+        dx, sums = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add, relu_src=x, bn_y=bn_y)
+        _direct.bnsums[dx.data_ptr()] = (sums, bn_y.data_ptr(), dx)
+    elif need_dx:
+        dx = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add)
+    elif add is not None:
+        dx = add
+    if not need_dw:
+        return dx, None, None
+    if _direct is not None:
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            if only_db:
+                ops.conv_wgrad(x, dy, g, want_dbias=True, out_db=b.grad, accumulate=False)
+            elif defer is not None:
+                # split partial sums stay in the convolution's persistent workspace; FusedSGD reduces them
+                ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_db=b.grad if want_db else None, accumulate=acc,
+                               partials=defer[1])
+                w._mcd_deferred = True
+            else:
+                ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
+                               accumulate=acc)
+        if not only_db:
+            w._mcd_written = True
+        _direct.keep.append((x, dy))          # keep the operands alive until the side stream is joined
+        for p in ((w, b) if want_db else (w,)):
+            sync = getattr(p, "_mcd_sync", None)
+            if sync is not None and not (p is w and only_db):
+                sync.mark_ready(p, side)
+        return dx, None, None
+    if need_dx and _overlap_wgrad:
+        # dgrad and wgrad both consume dy and are independent: wgrad runs on a side stream so that its CTAs
+        # fill the SMs the other kernel's last (partial) wave of tiles leaves idle.  Every use of the side
+        # stream is preceded by side.wait_stream(main), which also makes the caching allocator's per-stream
+        # reuse of the workspace / gradient blocks safe.
+        main = torch.cuda.current_stream(dy.device)
+        side = _side_stream(dy.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
+        main.wait_stream(side)
+        return dx, (None if only_db else dw), db
+    dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
+    return dx, (None if only_db else dw), db
+
+
 class _ConvFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, mod, planar, want_stats, bn_y):
-        g = mod.geom(x.shape)
-        y, stats = ops.conv_fprop(x, mod.packed(0, g), bias, g, planar=planar, want_stats=want_stats)
-        ctx.mod, ctx.g, ctx.planar = mod, g, planar
-        ctx.has_bias = bias is not None
-        # bn_y: x = relu(bn(bn_y)) and this convolution is x's only consumer (apart from an identity shortcut):
-        # in direct-gradient mode the dgrad epilogue then applies the ReLU mask and accumulates the BatchNorm
-        # backward sums, which removes that unit's reduction pass
-        ctx.bn_y = bn_y
-        ctx.save_for_backward(x)
-        if stats is None:
-            stats = torch.empty(0, dtype=F32, device=x.device)
-        ctx.mark_non_differentiable(stats)
-        return y, stats
+    """a convolution on its own: the planar fp32 score-map heads (`seg`, decoder outputs) and generic use."""
 
     @staticmethod
-    def backward(ctx, dy, _dstats):
+    def forward(ctx, x, weight, bias, mod, planar):
+        g = mod.geom(x.shape)
+        y, _ = ops.conv_fprop(x, mod.packed(0, g), bias, g, planar=planar)
+        ctx.mod, ctx.g, ctx.planar = mod, g, planar
+        ctx.has_bias = bias is not None
+        ctx.w_tag = _weight_tag(weight)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        g, mod = ctx.g, ctx.mod
-        dy = ops.to_nhwc(dy) if ctx.planar else _as_nhwc_grad(dy)
-        dx = dw = db = None
-        need_dx = ctx.needs_input_grad[0]
-        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        dy = ops.to_nhwc(dy, grad=True) if ctx.planar else _as_nhwc_grad(dy)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
-        if need_dw and _direct is not None:
-            # direct-gradient mode (MCDStep): wgrad is enqueued on the side stream and writes straight into
-            # param.grad (or its all-reduce bucket view); nothing is returned to autograd for the weights, so no
-            # accumulation kernel runs and the main stream goes on with dgrad / BatchNorm backward while the
-            # tensor-bound wgrad kernels trail behind.  MCDStep joins the side stream before optimizer.step().
-            main = torch.cuda.current_stream(dy.device)
-            # set_overlap_wgrad(False): everything on the main stream (per-kernel timing in bench.py)
-            side = _side_stream(dy.device) if _overlap_wgrad else main
-            ready = torch.cuda.Event()
-            ready.record(main)                    # dy (and everything before it) is complete here
-            w, b = mod.weight, mod.bias
-            acc = getattr(w, "_mcd_written", False) and w.grad is not None
-            defer = getattr(mod, "_mcd_defer", None) if _direct.defer else None
-            if defer is not None and defer[0] != g.key():
-                defer = None
-            if defer is not None and getattr(w, "_mcd_deferred", False):
-                raise RuntimeError("mcd_b200: a deferred weight gradient was produced twice before optimizer_g.step()")
-            if defer is None and w.grad is None:
-                w.grad = torch.empty_like(w)
-            if want_db and b.grad is None:
-                b.grad = torch.empty_like(b)
-            # dgrad is enqueued FIRST: it heads the critical path (dgrad -> BatchNorm backward -> next dgrad) and
-            # cannot share an SM with the persistent wgrad CTAs (both want ~190 KB of shared memory); the wgrad
-            # that follows on the side stream then overlaps the memory-bound BatchNorm kernels of the next unit.
-            add = _direct.stash.pop(x.data_ptr(), None)      # identity-shortcut gradient of a BasicBlock
-            if need_dx and ctx.bn_y is not None and _fuse_bn_bwd:
-                dx, sums = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add, relu_src=x, bn_y=ctx.bn_y)
-                _direct.bnsums[dx.data_ptr()] = (sums, ctx.bn_y.data_ptr(), dx)
-            elif need_dx:
-                dx = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add)
-            elif add is not None:
-                dx = add
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                if defer is not None:
-                    # split partial sums stay in the convolution's persistent workspace; FusedSGD reduces them
-                    ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_db=b.grad if want_db else None, accumulate=acc,
-                                   partials=defer[1])
-                    w._mcd_deferred = True
-                else:
-                    ops.conv_wgrad(x, dy, g, want_dbias=want_db, out_dw=w.grad, out_db=b.grad if want_db else None,
-                                   accumulate=acc)
-            w._mcd_written = True
-            _direct.keep.append((x, dy))          # keep the operands alive until the side stream is joined
-            for p in ((w, b) if want_db else (w,)):
-                sync = getattr(p, "_mcd_sync", None)
-                if sync is not None:
-                    sync.mark_ready(p, side)
-            return dx, None, None, None, None, None, None
-        if need_dx and need_dw and _overlap_wgrad:
-            # dgrad and wgrad both consume dy and are independent: wgrad runs on a side stream so that its CTAs
-            # fill the SMs the other kernel's last (partial) wave of tiles leaves idle.  Every use of the side
-            # stream is preceded by side.wait_stream(main), which also makes the caching allocator's per-stream
-            # reuse of the workspace / gradient blocks safe.
-            main = torch.cuda.current_stream(dy.device)
-            side = _side_stream(dy.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
-            dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
-            main.wait_stream(side)
-            return dx, dw, db, None, None, None, None
-        if need_dx:
-            dx = ops.conv_dgrad(dy, mod.packed(1, g), g)
-        if need_dw:
-            dw, db = ops.conv_wgrad(x, dy, g, want_dbias=want_db)
-        return dx, dw, db, None, None, None, None
+        dx, dw, db = _conv_backward(ctx.mod, ctx.g, x, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1], want_db,
+                                    None, ctx.w_tag)
+        return dx, dw, db, None, None
 
 
 class Conv2d(nn.Conv2d):
     """nn.Conv2d parameter container whose forward is the library's implicit-GEMM convolution.
 
-    Input / output are bf16 channels_last activations (`planar_out=True`: fp32 NCHW score map).
+    Input: an nhwc activation (IEEE half or its bf16 twin) or a planar fp32 tensor; output: IEEE-half nhwc, or with
+    `planar_out=True` an fp32 NCHW score map.
     """
 
     def __init__(self, *args, planar_out=False, **kwargs):
@@ -221,8 +274,9 @@ class Conv2d(nn.Conv2d):
         return g
 
     def packed(self, mode, g):
-        """bf16 packed shadow of the fp32 master weight (layout chosen by the library for geometry `g`),
-        refreshed when the parameter changes (optimizer step, load_state_dict, .to())."""
+        """16-bit packed shadow of the fp32 master weight (layout chosen by the library for geometry `g`; IEEE half
+        for the forward operand, bfloat16 for the dgrad operand), refreshed when the parameter changes (optimizer
+        step, load_state_dict, .to())."""
         w = self.weight
         tag = (w._version, w.data_ptr())
         key = ops.pack_key(g, mode)
@@ -232,55 +286,74 @@ class Conv2d(nn.Conv2d):
             self._packs[key] = hit
         return hit[1]
 
-    def conv_raw(self, x, want_stats=False, sole=False):
-        """sole=True: the caller guarantees that this convolution is the only consumer of `x` (an identity
-        shortcut of the same block aside), see _ConvFn.forward."""
-        bn_y = getattr(x, "_mcd_bn_y", None) if sole else None
+    def prepare(self, x):
         x = ops.to_nhwc(x)
         if x.shape[1] < self.in_channels:
             raise ValueError("Conv2d expected >= %d input channels, got %d" % (self.in_channels, x.shape[1]))
-        if bn_y is not None and (tuple(bn_y.shape) != tuple(x.shape) or x.shape[1] != self.in_channels):
-            bn_y = None
-        y, stats = _ConvFn.apply(x, self.weight, self.bias, self, self.planar_out, want_stats, bn_y)
-        return y, (stats if want_stats else None)
+        return x
 
     def forward(self, x):
-        return self.conv_raw(x)[0]
+        return _ConvFn.apply(self.prepare(x), self.weight, self.bias, self, self.planar_out)
 
 
 # ---------------------------------------------------------------------------------------------
+def _bn_backward(ctx_relu, training, res_training, has_res_bn, want_dres, res_ptr, dz, z, y, gamma, aff, res, res_gamma,
+                 res_aff):
+    """BatchNorm (+ residual) + ReLU backward of one unit; returns dy, dgamma, dbeta, dres, dres_gamma, dres_beta."""
+    fused = _direct.bnsums.pop(dz.data_ptr(), None) if _direct is not None else None
+    if fused is not None and (fused[1] != y.data_ptr() or has_res_bn or not ctx_relu or not training):
+        raise RuntimeError("mcd_b200: fused BatchNorm-backward sums reached the wrong unit")
+    dy, dgamma, dbeta, dres, dres_gamma, dres_beta = ops.bn_bwd(
+        dz, z, y, gamma, aff, training, ctx_relu, res=res, res_gamma=res_gamma, res_aff=res_aff,
+        res_training=res_training, want_dres=want_dres or has_res_bn, raw_sums=fused[0] if fused is not None else None)
+    if not (want_dres or has_res_bn):
+        dres = None
+    elif _direct is not None and not has_res_bn and res_ptr is not None:
+        # direct-gradient mode: the identity-shortcut gradient is not returned to autograd (which would add
+        # it to conv1's dgrad in a separate pass) but handed to conv1's dgrad kernel, whose epilogue adds it
+        _direct.stash[res_ptr] = dres
+        dres = None
+    return dy, dgamma, dbeta, dres, dres_gamma, dres_beta
+
+
 class _BNActFn(torch.autograd.Function):
+    """BatchNorm (+ residual) (+ ReLU) on its own (BatchNorm2d.forward / .fused); units use _UnitFn."""
+
     @staticmethod
-    def forward(ctx, y, stats, gamma, beta, res, res_stats, res_gamma, res_beta, bn, res_bn, relu):
+    def forward(ctx, y, stats, gamma, beta, res, res_stats, res_gamma, res_beta, bn, res_bn, relu, twin):
         training = bn.training
         z, aff, res_aff = ops.bn_forward(y, stats, bn, relu, res=res, res_stats=res_stats, res_bn=res_bn,
-                                         repeat=_bn_repeat)
+                                         repeat=_bn_repeat, twin=twin)
         ctx.relu, ctx.training = relu, training
         ctx.res_training = res_bn.training if res_bn is not None else False
         ctx.has_res, ctx.has_res_bn = res is not None, res_bn is not None
         ctx.res_ptr = res.data_ptr() if (res is not None and res_bn is None and getattr(res, "_mcd_shortcut", False)) else None
         ctx.save_for_backward(y, z, gamma, aff, res if res_bn is not None else None, res_gamma, res_aff)
-        return z
+        z16 = getattr(z, "_mcd_h16", None)
+        if z16 is None:
+            return z, torch.empty(0, dtype=F16, device=z.device)
+        ctx.mark_non_differentiable(z16)
+        return z, z16
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, _):
         y, z, gamma, aff, res, res_gamma, res_aff = ctx.saved_tensors
         dz = _as_nhwc_grad(dz)
         want_dres = ctx.has_res and ctx.needs_input_grad[4]
-        fused = _direct.bnsums.pop(dz.data_ptr(), None) if _direct is not None else None
-        if fused is not None and (fused[1] != y.data_ptr() or ctx.has_res_bn or not ctx.relu or not ctx.training):
-            raise RuntimeError("mcd_b200: fused BatchNorm-backward sums reached the wrong unit")
-        dy, dgamma, dbeta, dres, dres_gamma, dres_beta = ops.bn_bwd(
-            dz, z, y, gamma, aff, ctx.training, ctx.relu, res=res, res_gamma=res_gamma, res_aff=res_aff,
-            res_training=ctx.res_training, want_dres=want_dres, raw_sums=fused[0] if fused is not None else None)
+        dy, dgamma, dbeta, dres, dres_gamma, dres_beta = _bn_backward(
+            ctx.relu, ctx.training, ctx.res_training, ctx.has_res_bn, want_dres, ctx.res_ptr, dz, z, y, gamma, aff, res,
+            res_gamma, res_aff)
         if not want_dres:
             dres = None
-        elif _direct is not None and not ctx.has_res_bn and ctx.res_ptr is not None:
-            # direct-gradient mode: the identity-shortcut gradient is not returned to autograd (which would add
-            # it to conv1's dgrad in a separate pass) but handed to conv1's dgrad kernel, whose epilogue adds it
-            _direct.stash[ctx.res_ptr] = dres
-            dres = None
-        return dy, None, dgamma, dbeta, dres, None, dres_gamma, dres_beta, None, None, None
+        return dy, None, dgamma, dbeta, dres, None, dres_gamma, dres_beta, None, None, None, None
+
+
+def _with_twin(out):
+    """(handle, IEEE-half original or empty) as returned by the Functions -> the handle with `_mcd_h16` attached."""
+    z, z16 = out
+    if z16.numel():
+        z._mcd_h16 = z16
+    return z
 
 
 class BatchNorm2d(nn.BatchNorm2d):
@@ -294,12 +367,10 @@ class BatchNorm2d(nn.BatchNorm2d):
     def fused(self, y, stats, relu=True, res=None, res_stats=None, res_bn=None):
         assert self.affine and self.track_running_stats
         if res_bn is not None:
-            return _BNActFn.apply(y, stats, self.weight, self.bias, res, res_stats, res_bn.weight,
-                                  res_bn.bias, self, res_bn, relu)
-        z = _BNActFn.apply(y, stats, self.weight, self.bias, res, None, None, None, self, None, relu)
-        if relu and self.training and y.shape[1] == self.num_features:
-            z._mcd_bn_y = y      # lets a sole-consumer convolution start this unit's backward in its dgrad epilogue
-        return z
+            return _with_twin(_BNActFn.apply(y, stats, self.weight, self.bias, res, res_stats, res_bn.weight,
+                                             res_bn.bias, self, res_bn, relu, ops.want_twin()))
+        return _with_twin(_BNActFn.apply(y, stats, self.weight, self.bias, res, None, None, None, self, None, relu,
+                                         ops.want_twin()))
 
     def forward(self, x):
         x = ops.to_nhwc(x)
@@ -307,14 +378,82 @@ class BatchNorm2d(nn.BatchNorm2d):
         return self.fused(x, stats, relu=False)
 
 
+# ---------------------------------------------------------------------------------------------
+class _UnitFn(torch.autograd.Function):
+    """z = act(bn(conv(x)) + residual), residual = res (identity) | res_bn(res_conv(res)) - the BasicBlock half /
+    conv-BN-ReLU unit of models/drn.py:43-59,126-131,195-205 and CBR of models/dilated_fcn.py:632-644.
+
+    x_bn_y: x = relu(bn(x_bn_y)) was produced by the previous unit and this convolution is x's only consumer (an
+    identity shortcut of the same block aside): in direct-gradient mode the dgrad epilogue then applies the ReLU mask
+    and accumulates the BatchNorm-backward sums of that unit, which removes its reduction pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, res, res_weight, res_gamma, res_beta, conv, bn, res_conv, res_bn,
+                relu, x_bn_y, twin):
+        g = conv.geom(x.shape)
+        training = bn.training
+        y, stats = ops.conv_fprop(x, conv.packed(0, g), bias, g, want_stats=training)
+        ry = rstats = rg = None
+        if res_conv is not None:
+            rg = res_conv.geom(res.shape)
+            ry, rstats = ops.conv_fprop(res, res_conv.packed(0, rg), None, rg, want_stats=res_bn.training)
+        # twin: autograd is recording (decided by the caller - grad mode is always off inside forward)
+        z, aff, res_aff = ops.bn_forward(y, stats, bn, relu, res=ry if res_conv is not None else res,
+                                         res_stats=rstats, res_bn=res_bn, repeat=_bn_repeat, twin=twin)
+        ctx.conv, ctx.g, ctx.res_conv, ctx.rg = conv, g, res_conv, rg
+        ctx.relu, ctx.training = relu, training
+        ctx.res_training = res_bn.training if res_bn is not None else False
+        ctx.has_res, ctx.has_res_bn, ctx.has_bias = res is not None, res_bn is not None, bias is not None
+        ctx.res_ptr = res.data_ptr() if (res is not None and res_bn is None and getattr(res, "_mcd_shortcut", False)) else None
+        ctx.x_bn_y = x_bn_y
+        ctx.w_tag = _weight_tag(weight)
+        ctx.rw_tag = _weight_tag(res_weight) if res_conv is not None else None
+        # backward needs: x (wgrad operand / mask: its bf16 twin), y (BatchNorm input), z (ReLU mask: the bf16 twin)
+        ctx.save_for_backward(x, y, z, gamma, aff, ry, res if res_conv is not None else None, res_gamma, res_aff)
+        z16 = getattr(z, "_mcd_h16", None)
+        if z16 is None:
+            return z, torch.empty(0, dtype=F16, device=z.device), y
+        ctx.mark_non_differentiable(z16, y)
+        return z, z16, y
+
+    @staticmethod
+    def backward(ctx, dz, _z16, _y):
+        x, y, z, gamma, aff, ry, res, res_gamma, res_aff = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dz = _as_nhwc_grad(dz)
+        want_dres = ctx.has_res and need[5]
+        dy, dgamma, dbeta, dres, dres_gamma, dres_beta = _bn_backward(
+            ctx.relu, ctx.training, ctx.res_training, ctx.has_res_bn, want_dres, ctx.res_ptr, dz, z, y, gamma, aff, ry,
+            res_gamma, res_aff)
+        drw = None
+        if ctx.has_res_bn:
+            # downsample branch: dres is the gradient of the 1x1 convolution's output
+            dres, drw, _ = _conv_backward(ctx.res_conv, ctx.rg, res, dres, need[5], need[6], False, None, ctx.rw_tag)
+        elif not want_dres:
+            dres = None
+        dx, dw, db = _conv_backward(ctx.conv, ctx.g, x, dy, need[0], need[1] , ctx.has_bias and need[2], ctx.x_bn_y,
+                                    ctx.w_tag)
+        return (dx, dw, db, dgamma, dbeta, dres, drw, dres_gamma, dres_beta, None, None, None, None, None, None, None)
+
+
 def conv_bn_act(conv, bn, x, relu=True, res=None, res_conv=None, res_bn=None, sole=False):
-    """z = act(bn(conv(x)) + residual); residual = res (identity) or res_bn(res_conv(x_res)).
-    sole: `conv` is the only consumer of x (Conv2d.conv_raw)."""
-    y, stats = conv.conv_raw(x, want_stats=bn.training, sole=sole)
-    if res_conv is not None:
-        ry, rstats = res_conv.conv_raw(res, want_stats=res_bn.training)
-        return bn.fused(y, stats, relu=relu, res=ry, res_stats=rstats, res_bn=res_bn)
-    return bn.fused(y, stats, relu=relu, res=res)
+    """z = act(bn(conv(x)) + residual); residual = res (identity) or res_bn(res_conv(res)).
+    sole: `conv` is the only consumer of x (an identity shortcut of the same block aside), see _UnitFn."""
+    bn_y = getattr(x, "_mcd_bn_y", None) if sole else None
+    x = conv.prepare(x)
+    if bn_y is not None and (tuple(bn_y.shape) != tuple(x.shape) or x.shape[1] != conv.in_channels):
+        bn_y = None
+    if res is not None:
+        res = res_conv.prepare(res) if res_conv is not None else ops.to_nhwc(res)
+    assert bn.affine and bn.track_running_stats
+    out = _UnitFn.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, res,
+                        res_conv.weight if res_conv is not None else None,
+                        res_bn.weight if res_bn is not None else None, res_bn.bias if res_bn is not None else None,
+                        conv, bn, res_conv, res_bn, relu, bn_y, ops.want_twin())
+    z = _with_twin(out[:2])
+    if relu and bn.training and res_bn is None and out[2].shape[1] == bn.num_features:
+        z._mcd_bn_y = out[2]     # lets a sole-consumer convolution start this unit's backward in its dgrad epilogue
+    return z
 
 
 class ConvBNReLU(nn.Sequential):
@@ -335,7 +474,7 @@ class ConvBNReLU(nn.Sequential):
 class SoleChain(nn.Sequential):
     """nn.Sequential whose intermediate activations are read by the next child only (the DRN trunk stages,
     reference models/dilated_fcn.py `self.base = nn.Sequential(*list(model.children())[:-2])`).  It flags them so
-    that the next stage's first convolution may fuse the producing unit's BatchNorm backward (Conv2d.conv_raw)."""
+    that the next stage's first convolution may fuse the producing unit's BatchNorm backward (_UnitFn)."""
 
     def forward(self, x):
         mods = list(self.children())
@@ -349,22 +488,21 @@ class SoleChain(nn.Sequential):
 # ---------------------------------------------------------------------------------------------
 class _Deconv16s8Fn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, x2, w2):
-        out = ops.deconv16s8_fwd(x, w, x2, w2)
+    def forward(ctx, x, w, x2, w2, out_dtype):
+        out = ops.deconv16s8_fwd(x, w, x2, w2, out_dtype)
         ctx.save_for_backward(x, w, x2, w2)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, w, x2, w2 = ctx.saved_tensors
-        dout = dout.contiguous()
         need = ctx.needs_input_grad
         dx = dw = dx2 = dw2 = None
         if need[0] or need[1]:
             dx, dw = ops.deconv16s8_bwd(dout, x, w, want_dx=need[0], want_dw=need[1])
         if x2 is not None and (need[2] or need[3]):
             dx2, dw2 = ops.deconv16s8_bwd(dout, x2, w2, want_dx=need[2], want_dw=need[3])
-        return dx, dw, dx2, dw2
+        return dx, dw, dx2, dw2, None
 
 
 def _planar_f32(x):
@@ -375,7 +513,7 @@ def _planar_f32(x):
 
 class DepthwiseDeconv16s8(nn.ConvTranspose2d):
     """ConvTranspose2d(C, C, 16, stride=8, padding=4, groups=C, bias=False): the *learned* upsampling of
-    the MCD heads (models/dilated_fcn.py:357-360).  fp32 planar score map in, bf16 planar logits out."""
+    the MCD heads (models/dilated_fcn.py:357-360).  fp32 planar score map in, planar logits out (`logits_dtype`)."""
 
     def __init__(self, n_class):
         super().__init__(n_class, n_class, 16, stride=8, padding=4, output_padding=0, groups=n_class,
@@ -384,8 +522,8 @@ class DepthwiseDeconv16s8(nn.ConvTranspose2d):
     def forward(self, x, x2=None, other=None):
         x = _planar_f32(x)
         if x2 is None:
-            return _Deconv16s8Fn.apply(x, self.weight, None, None)
-        return _Deconv16s8Fn.apply(x, self.weight, _planar_f32(x2), other.weight)
+            return _Deconv16s8Fn.apply(x, self.weight, None, None, _logits_dtype)
+        return _Deconv16s8Fn.apply(x, self.weight, _planar_f32(x2), other.weight, _logits_dtype)
 
 
 class _BilinearFn(torch.autograd.Function):
@@ -400,11 +538,12 @@ class _BilinearFn(torch.autograd.Function):
 
 
 class BilinearUpsample(nn.Module):
-    """nn.Upsample(scale_factor=s, mode='bilinear') (align_corners=False), models/dilated_fcn.py:676,817-819."""
+    """nn.Upsample(scale_factor=s, mode='bilinear') (align_corners=False), models/dilated_fcn.py:676,817-819.
+    Output dtype: `logits_dtype` (out_f32=True forces fp32)."""
 
     def __init__(self, scale_factor, out_f32=False):
         super().__init__()
         self.scale_factor, self.out_f32 = int(scale_factor), out_f32
 
     def forward(self, x):
-        return _BilinearFn.apply(_planar_f32(x), self.scale_factor, self.out_f32)
+        return _BilinearFn.apply(_planar_f32(x), self.scale_factor, self.out_f32 or _logits_dtype == F32)

@@ -1,8 +1,16 @@
 """Tensor-level wrappers over the C-ABI: validate, allocate outputs with torch, pass raw pointers.
 
 PyTorch is plumbing here (device memory, streams); every computation is a libmcd_sm100 kernel.
-Activations are bf16 NHWC buffers exposed as logical-NCHW `channels_last` tensors; score maps and
+Activations are 16-bit NHWC buffers exposed as logical-NCHW `channels_last` tensors; score maps and
 full-resolution logits are ordinary contiguous NCHW ("planar") tensors.
+
+16-bit formats (include/mcd_sm100.h): FORWARD values are IEEE half (torch.float16) - what the tcgen05 forward GEMMs
+read and write; GRADIENTS are torch.bfloat16.  The tensor that travels between modules (and through autograd, whose
+gradients must have the dtype of the tensor they belong to) is the bfloat16 TWIN of an activation: an honest, slightly
+less precise copy that also is the operand of the weight-gradient GEMM (tcgen05 needs both operands in one format) and
+the ReLU mask of the backward pass.  It carries its IEEE-half original as the attribute `_mcd_h16`; `h16()` / `b16()`
+return either form of any activation (re-encoding with one kernel when a tensor arrives without its twin).  With
+autograd disabled nothing needs the twin and the IEEE-half tensor itself is what travels.
 """
 import ctypes
 import os
@@ -13,6 +21,7 @@ from . import abi
 from .abi import ConvGeom
 
 BF16 = torch.bfloat16
+F16 = torch.float16
 F32 = torch.float32
 
 _algo = abi.ALGO_AUTO
@@ -86,48 +95,100 @@ def zeros_f32(n, device):
 
 # ---- layout ------------------------------------------------------------------------------------
 def is_nhwc(t):
-    return (t.dim() == 4 and t.dtype == BF16 and t.shape[1] % 8 == 0
+    return (t.dim() == 4 and t.dtype in (BF16, F16) and t.shape[1] % 8 == 0
             and t.permute(0, 2, 3, 1).is_contiguous())
 
 
-def nhwc_empty(n, c, h, w, device):
-    """bf16 [n,h,w,c] buffer viewed as logical NCHW (channels_last strides)."""
-    return torch.empty((n, h, w, c), dtype=BF16, device=device).permute(0, 3, 1, 2)
+def _fmt(t):
+    return abi.FMT_F16 if t.dtype == F16 else abi.FMT_BF16
 
 
-def to_nhwc(x):
-    """NCHW fp32 (any C) -> channels_last bf16 with C padded to a multiple of 8 (zero fill)."""
+def nhwc_empty(n, c, h, w, device, dtype=BF16):
+    """16-bit [n,h,w,c] buffer viewed as logical NCHW (channels_last strides)."""
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def convert16(x):
+    """re-encode a 16-bit nhwc tensor in the other format (bf16 <-> IEEE half), one kernel."""
+    assert is_nhwc(x)
+    n, c, h, w = x.shape
+    out = nhwc_empty(n, c, h, w, x.device, BF16 if x.dtype == F16 else F16)
+    abi.check(abi.lib().mcd_convert16(_p(x), _fmt(x), _p(out), x.numel(), _dev(x), _stream(x)), "convert16")
+    return out
+
+
+def h16(x):
+    """IEEE-half form of an activation (the operand of the forward GEMMs)."""
+    if x.dtype == F16:
+        return x
+    tw = getattr(x, "_mcd_h16", None)
+    if tw is None:                     # a bf16 tensor that did not come from this library: exact re-encoding
+        tw = convert16(x)
+        x._mcd_h16 = tw
+    return tw
+
+
+def b16(x):
+    """bfloat16 twin of an activation (operand of the weight-gradient GEMM, ReLU mask of the backward pass)."""
+    if x.dtype == BF16:
+        return x
+    tw = getattr(x, "_mcd_b16", None)
+    if tw is None:
+        tw = convert16(x)
+        x._mcd_b16 = tw
+    return tw
+
+
+def want_twin():
+    """autograd is recording: activations get their bf16 twin, which then is the tensor that travels.
+    NB: evaluate this OUTSIDE torch.autograd.Function.forward (grad mode is always off in there) and pass it in."""
+    return torch.is_grad_enabled()
+
+
+def to_nhwc(x, grad=False, twin=None):
+    """NCHW fp32 (any C) -> channels_last 16-bit with C padded to a multiple of 8 (zero fill).
+    Activations (grad=False): IEEE half, plus the bf16 twin while autograd records - the twin is returned and
+    carries the IEEE-half tensor as `_mcd_h16`.  grad=True: a gradient tensor, bfloat16 only."""
     if is_nhwc(x):
+        if grad and x.dtype != BF16:
+            return convert16(x)
         return x
     if x.dtype != F32:
         x = x.float()
     x = x.contiguous()
     n, c, h, w = x.shape
     cs = round_up(c, 8)
-    out = nhwc_empty(n, cs, h, w, x.device)
-    abi.check(abi.lib().mcd_nchw_f32_to_nhwc_bf16(_p(x), _p(out), n, c, h, w, cs, _dev(x), _stream(x)),
-              "nchw_f32_to_nhwc_bf16")
-    return out
+    twin = grad or (want_twin() if twin is None else twin)
+    o16 = None if grad else nhwc_empty(n, cs, h, w, x.device, F16)
+    ob = nhwc_empty(n, cs, h, w, x.device, BF16) if twin else None
+    abi.check(abi.lib().mcd_nchw_f32_to_nhwc(_p(x), _p(o16), _p(ob), n, c, h, w, cs, _dev(x), _stream(x)),
+              "nchw_f32_to_nhwc")
+    if ob is None:
+        return o16
+    if o16 is not None:
+        ob._mcd_h16 = o16
+    return ob
 
 
 def to_nchw_f32(x, c=None):
-    """channels_last bf16 -> contiguous NCHW fp32 (first c channels)."""
+    """channels_last 16-bit -> contiguous NCHW fp32 (first c channels); reads the IEEE-half form when there is one."""
     assert is_nhwc(x)
+    x = getattr(x, "_mcd_h16", x)
     n, cs, h, w = x.shape
     c = cs if c is None else c
     out = torch.empty((n, c, h, w), dtype=F32, device=x.device)
-    abi.check(abi.lib().mcd_nhwc_bf16_to_nchw_f32(_p(x), _p(out), n, c, h, w, cs, _dev(x), _stream(x)),
-              "nhwc_bf16_to_nchw_f32")
+    abi.check(abi.lib().mcd_nhwc_to_nchw_f32(_p(x), _fmt(x), _p(out), n, c, h, w, cs, _dev(x), _stream(x)),
+              "nhwc_to_nchw_f32")
     return out
 
 
 def pack_weight(w, mode):
-    """fp32 OIHW -> packed bf16 [rows][R*S][kc_pad] (mode 0 fprop / 1 dgrad)."""
+    """fp32 OIHW -> packed [rows][R*S][kc_pad]: mode 0 fprop operand (IEEE half) / 1 dgrad operand (bfloat16)."""
     w = w.detach()
     assert w.dtype == F32 and w.is_contiguous()
     co, ci, r, s = w.shape
     rows, kc = (ci, co) if mode else (co, ci)
-    out = torch.empty((rows, r * s, round_up(kc, 64)), dtype=BF16, device=w.device)
+    out = torch.empty((rows, r * s, round_up(kc, 64)), dtype=BF16 if mode else F16, device=w.device)
     abi.check(abi.lib().mcd_pack_weight(_p(w), _p(out), co, ci, r, s, mode, _dev(w), _stream(w)),
               "pack_weight")
     return out
@@ -145,12 +206,12 @@ def pack_weight_for(w, g, mode, algo=None):
     co, ci, r, s = w.shape
     rows, cs = (ci, g.Cout_s) if mode else (co, g.Cin_s)
     if kind == 2:      # "row convolution" operand for the stride-1 stem layers (csrc/conv_rows.cu)
-        out = torch.empty((r, (cs // 8) * (4 if s <= 4 else 8), round_up(rows, 16) // 8, 8, 8), dtype=BF16,
-                          device=w.device)
+        out = torch.empty((r, (cs // 8) * (4 if s <= 4 else 8), round_up(rows, 16) // 8, 8, 8),
+                          dtype=BF16 if mode else F16, device=w.device)
         abi.check(abi.lib().mcd_pack_weight_rowconv(_p(w), _p(out), co, ci, r, s, cs, mode, _dev(w), _stream(w)),
                   "pack_weight_rowconv")
         return out
-    out = torch.empty((rows, r, 64), dtype=BF16, device=w.device)
+    out = torch.empty((rows, r, 64), dtype=BF16 if mode else F16, device=w.device)
     abi.check(abi.lib().mcd_pack_weight_rows(_p(w), _p(out), co, ci, r, s, cs, mode, _dev(w), _stream(w)),
               "pack_weight_rows")
     return out
@@ -295,6 +356,7 @@ class FusedSGD:
                   "sgd_pack_multi")
         for p in active:      # the packs were rewritten from the updated weights: keep their tags current
             p._mcd_deferred = False
+            p._mcd_step = getattr(p, "_mcd_step", 0) + 1     # in-place update the autograd version counter cannot see
             conv = self.conv_of.get(p)
             if conv is not None:
                 tag = (p._version, p.data_ptr())
@@ -347,13 +409,14 @@ def _streamk_ws(g, mode, planar, algo, device):
 
 
 def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
-    """returns (y, stats) - y nhwc bf16 [N,Cout_s,Ho,Wo] or planar fp32 [N,Cout,Ho,Wo]."""
+    """returns (y, stats) - y nhwc IEEE half [N,Cout_s,Ho,Wo] or planar fp32 [N,Cout,Ho,Wo]."""
+    x = h16(x)
     assert is_nhwc(x) and x.shape[1] == g.Cin_s
     algo = _algo if algo is None else algo
     if planar:
         y = torch.empty((g.N, g.Cout, g.Ho, g.Wo), dtype=F32, device=x.device)
     else:
-        y = nhwc_empty(g.N, g.Cout_s, g.Ho, g.Wo, x.device)
+        y = nhwc_empty(g.N, g.Cout_s, g.Ho, g.Wo, x.device, F16)
     stats = zeros_f32(2 * g.Cout, x.device) if want_stats else None
     skp, skf = _streamk_ws(g, 0, planar, algo, x.device)
     abi.check(abi.lib().mcd_conv2d_fprop(
@@ -366,9 +429,14 @@ def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=N
     """dx = dgrad (+ add: an nhwc tensor of dx's shape, e.g. the identity-shortcut gradient).
     relu_src (the convolution's input, a ReLU output): dx is masked by relu_src > 0 in the epilogue;
     bn_y (input of the BatchNorm that produced relu_src): also returns the fp32 [2,C] raw sums
-    {sum dx, sum dx*bn_y} for bn_bwd(..., raw_sums=...).  Returns dx or (dx, sums)."""
+    {sum dx, sum dx*bn_y} for bn_bwd(..., raw_sums=...).  Returns dx or (dx, sums).
+    Formats: dy, dx, add bfloat16; relu_src the bf16 twin of the input; bn_y IEEE half."""
+    dy = to_nhwc(dy, grad=True)
     assert is_nhwc(dy) and dy.shape[1] == g.Cout_s
     dx = nhwc_empty(g.N, g.Cin_s, g.H, g.W, dy.device)
+    add = None if add is None else to_nhwc(add, grad=True)
+    relu_src = None if relu_src is None else b16(relu_src)
+    bn_y = None if bn_y is None else h16(bn_y)
     for t in (add, relu_src, bn_y):
         assert t is None or (is_nhwc(t) and tuple(t.shape) == tuple(dx.shape))
     sums = zeros_f32(2 * g.Cin, dy.device) if bn_y is not None else None
@@ -392,7 +460,9 @@ def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, 
     """dw (fp32 OIHW) and optionally dbias.  `out_dw` / `out_db` (e.g. param.grad or an all-reduce bucket view)
     are written in place - overwritten, or added to when `accumulate`.
     partials: a persistent uint8 workspace tensor; the kernel then leaves the weight gradient there as split
-    partial sums (wgrad_partial_layout) for FusedSGD and no dw is produced (returns None, db)."""
+    partial sums (wgrad_partial_layout) for FusedSGD and no dw is produced (returns None, db).
+    Both operands bfloat16: x is the twin of the convolution's input."""
+    x, dy = b16(x), to_nhwc(dy, grad=True)
     assert is_nhwc(x) and is_nhwc(dy)
     algo = _algo if algo is None else algo
     if partials is not None:
@@ -417,6 +487,7 @@ def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, 
 
 # ---- batch norm --------------------------------------------------------------------------------
 def bn_stats(y, c):
+    y = h16(y)
     n, cs, h, w = y.shape
     stats = torch.zeros(2 * c, dtype=F32, device=y.device)
     abi.check(abi.lib().mcd_bn_stats(_p(y), _p(stats), n * h * w, c, cs, _dev(y), _stream(y)), "bn_stats")
@@ -435,16 +506,20 @@ def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, 
     return out
 
 
-def bn_forward(y, stats, bn, relu, res=None, res_stats=None, res_bn=None, repeat=1):
+def bn_forward(y, stats, bn, relu, res=None, res_stats=None, res_bn=None, repeat=1, twin=None):
     """fused finalize + normalise (+residual / downsample BatchNorm) (+ReLU).  `bn` / `res_bn` are nn.BatchNorm2d
     modules (parameters, running buffers, momentum, eps, .training).  Returns z, save[2,C], res_save[2,C]|None;
-    save rows are (mean, rstd) for the backward."""
+    save rows are (mean, rstd) for the backward.  y / res IEEE half; z = the bf16 twin carrying `_mcd_h16` while
+    autograd records, else the IEEE-half tensor."""
+    y = h16(y)
+    res = None if res is None else h16(res)
     n, c, h, w = y.shape
 
     def mom(m):
         return m.momentum if repeat == 1 else 1.0 - (1.0 - m.momentum) ** repeat
 
-    z = nhwc_empty(n, c, h, w, y.device)
+    z16 = nhwc_empty(n, c, h, w, y.device, F16)
+    zb = nhwc_empty(n, c, h, w, y.device, BF16) if (want_twin() if twin is None else twin) else None
     save = torch.empty((2, c), dtype=F32, device=y.device)
     rsave = torch.empty((2, c), dtype=F32, device=y.device) if res_bn is not None else None
     tr = repeat if bn.training else 0
@@ -458,18 +533,27 @@ def bn_forward(y, stats, bn, relu, res=None, res_stats=None, res_bn=None, repeat
         _p(res_bn.running_var) if res_bn is not None else None,
         (_p(res_bn.num_batches_tracked) if rtr else None) if res_bn is not None else None,
         float(mom(res_bn)) if res_bn is not None else 0.0, float(res_bn.eps) if res_bn is not None else 0.0,
-        rtr, _p(rsave), int(relu), _p(z), n * h * w, c, c, _dev(y), _stream(y)), "bn_forward")
-    return z, save, rsave
+        rtr, _p(rsave), int(relu), _p(z16), _p(zb), n * h * w, c, c, _dev(y), _stream(y)), "bn_forward")
+    if zb is None:
+        return z16, save, rsave
+    zb._mcd_h16 = z16
+    return zb, save, rsave
 
 
-def bn_apply(y, aff, res, res_aff, relu):
+def bn_apply(y, aff, res, res_aff, relu, twin=None):
+    y = h16(y)
+    res = None if res is None else h16(res)
     n, c, h, w = y.shape
-    z = nhwc_empty(n, c, h, w, y.device)
+    z16 = nhwc_empty(n, c, h, w, y.device, F16)
+    zb = nhwc_empty(n, c, h, w, y.device, BF16) if (want_twin() if twin is None else twin) else None
     abi.check(abi.lib().mcd_bn_apply(
         _p(y), _p(aff[0]), _p(aff[1]), _p(res), _p(res_aff[0]) if res_aff is not None else None,
-        _p(res_aff[1]) if res_aff is not None else None, int(relu), _p(z), n * h * w, c, c, _dev(y),
+        _p(res_aff[1]) if res_aff is not None else None, int(relu), _p(z16), _p(zb), n * h * w, c, c, _dev(y),
         _stream(y)), "bn_apply")
-    return z
+    if zb is None:
+        return z16
+    zb._mcd_h16 = z16
+    return zb
 
 
 def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_aff=None,
@@ -477,7 +561,12 @@ def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_a
     """returns dy, dgamma, dbeta, dres, dres_gamma, dres_beta.  `aff` / `res_aff`: either the [4,C] tensor of
     bn_finalize (scale, shift, mean, rstd) or the [2,C] (mean, rstd) tensor of bn_forward.
     raw_sums: the [2*C] sums of conv_dgrad(..., relu_src=z, bn_y=y) - dz is then already ReLU-masked, the reduction
-    pass is skipped and the identity-residual gradient is dz itself."""
+    pass is skipped and the identity-residual gradient is dz itself.
+    Formats: dz / dy / dres bfloat16, z the bf16 twin (ReLU mask), y / res IEEE half."""
+    dz = to_nhwc(dz, grad=True)
+    z = None if z is None else b16(z)
+    y = h16(y)
+    res = None if res is None else h16(res)
     if aff.shape[0] == 2:
         aff = (None, None, aff[0], aff[1])
     if res_aff is not None and res_aff.shape[0] == 2:
@@ -514,19 +603,27 @@ def bn_bwd(dz, z, y, gamma, aff, training, relu, res=None, res_gamma=None, res_a
 
 
 # ---- heads -------------------------------------------------------------------------------------
-def deconv16s8_fwd(x, w, x2=None, w2=None):
+def _full(t):
+    """full-resolution planar tensor: bf16 or fp32, contiguous; returns (tensor, f32 flag)."""
+    if t.dtype not in (BF16, F32):
+        t = t.float()
+    return t.contiguous(), int(t.dtype == F32)
+
+
+def deconv16s8_fwd(x, w, x2=None, w2=None, out_dtype=BF16):
     n, c, h, wd = x.shape
-    out = torch.empty((n, c, 8 * h, 8 * wd), dtype=BF16, device=x.device)
-    abi.check(abi.lib().mcd_deconv16s8_fwd(_p(x), _p(w), _p(x2), _p(w2), _p(out), n, c, h, wd, _dev(x),
-                                           _stream(x)), "deconv16s8_fwd")
+    out = torch.empty((n, c, 8 * h, 8 * wd), dtype=out_dtype, device=x.device)
+    abi.check(abi.lib().mcd_deconv16s8_fwd(_p(x), _p(w), _p(x2), _p(w2), _p(out), int(out_dtype == F32), n, c, h, wd,
+                                           _dev(x), _stream(x)), "deconv16s8_fwd")
     return out
 
 
 def deconv16s8_bwd(dout, x, w, want_dx=True, want_dw=True):
     n, c, h, wd = x.shape
+    dout, f32 = _full(dout)
     dx = torch.empty_like(x) if want_dx else None
     dw = torch.empty_like(w) if want_dw else None
-    abi.check(abi.lib().mcd_deconv16s8_bwd(_p(dout), _p(x), _p(w), _p(dx), _p(dw), n, c, h, wd, _dev(x),
+    abi.check(abi.lib().mcd_deconv16s8_bwd(_p(dout), f32, _p(x), _p(w), _p(dx), _p(dw), n, c, h, wd, _dev(x),
                                            _stream(x)), "deconv16s8_bwd")
     return dx, dw
 
@@ -548,18 +645,25 @@ def bilinear_up_bwd(dout, s):
 
 
 # ---- losses ------------------------------------------------------------------------------------
+# full-resolution logits are planar bf16 or fp32 tensors (`_f32(t)` is the flag the kernels take); gradients have the
+# dtype of the logits, as autograd requires
+def _f32(t):
+    assert t.dtype in (BF16, F32) and t.is_contiguous()
+    return int(t.dtype == F32)
+
+
 def ce2d_fwd(logits, target, weight, ignore_index):
     n, c, h, w = logits.shape
     acc = zeros_f32(4, logits.device)
-    abi.check(abi.lib().mcd_ce2d_fwd(_p(logits), _p(target), _p(weight), int(ignore_index), _p(acc), n, c,
-                                     h, w, _dev(logits), _stream(logits)), "ce2d_fwd")
+    abi.check(abi.lib().mcd_ce2d_fwd(_p(logits), _f32(logits), _p(target), _p(weight), int(ignore_index), _p(acc), n,
+                                     c, h, w, _dev(logits), _stream(logits)), "ce2d_fwd")
     return acc
 
 
 def ce2d_bwd(logits, target, weight, ignore_index, acc, gscale):
     n, c, h, w = logits.shape
     d = torch.empty_like(logits)
-    abi.check(abi.lib().mcd_ce2d_bwd(_p(logits), _p(target), _p(weight), int(ignore_index), _p(acc),
+    abi.check(abi.lib().mcd_ce2d_bwd(_p(logits), _f32(logits), _p(target), _p(weight), int(ignore_index), _p(acc),
                                      _p(gscale), _p(d), n, c, h, w, _dev(logits), _stream(logits)),
               "ce2d_bwd")
     return d
@@ -567,9 +671,10 @@ def ce2d_bwd(logits, target, weight, ignore_index, acc, gscale):
 
 def diff2d_fwd(a, b, want_stats=False):
     n, c, h, w = a.shape
+    assert a.dtype == b.dtype
     acc = zeros_f32(1, a.device)
     stats = torch.empty((n, h, w, 4), dtype=F32, device=a.device) if want_stats else None
-    abi.check(abi.lib().mcd_diff2d_fwd(_p(a), _p(b), _p(acc), _p(stats), n, c, h, w, _dev(a), _stream(a)),
+    abi.check(abi.lib().mcd_diff2d_fwd(_p(a), _p(b), _f32(a), _p(acc), _p(stats), n, c, h, w, _dev(a), _stream(a)),
               "diff2d_fwd")
     return (acc, stats) if want_stats else acc
 
@@ -577,21 +682,21 @@ def diff2d_fwd(a, b, want_stats=False):
 def diff2d_bwd(a, b, gscale, stats=None):
     n, c, h, w = a.shape
     da, db = torch.empty_like(a), torch.empty_like(b)
-    abi.check(abi.lib().mcd_diff2d_bwd(_p(a), _p(b), _p(gscale), _p(stats), _p(da), _p(db), n, c, h, w, _dev(a),
-                                       _stream(a)), "diff2d_bwd")
+    abi.check(abi.lib().mcd_diff2d_bwd(_p(a), _p(b), _f32(a), _p(gscale), _p(stats), _p(da), _p(db), n, c, h, w,
+                                       _dev(a), _stream(a)), "diff2d_bwd")
     return da, db
 
 
 def mse_fwd(pred, target):
     acc = torch.zeros(1, dtype=F32, device=pred.device)
-    abi.check(abi.lib().mcd_mse_fwd(_p(pred), _p(target), _p(acc), pred.numel(), _dev(pred), _stream(pred)),
-              "mse_fwd")
+    abi.check(abi.lib().mcd_mse_fwd(_p(pred), _f32(pred), _p(target), _p(acc), pred.numel(), _dev(pred),
+                                    _stream(pred)), "mse_fwd")
     return acc
 
 
 def mse_bwd(pred, target, gscale):
     d = torch.empty_like(pred)
-    abi.check(abi.lib().mcd_mse_bwd(_p(pred), _p(target), _p(gscale), _p(d), pred.numel(), _dev(pred),
+    abi.check(abi.lib().mcd_mse_bwd(_p(pred), _f32(pred), _p(target), _p(gscale), _p(d), pred.numel(), _dev(pred),
                                     _stream(pred)), "mse_bwd")
     return d
 
@@ -602,20 +707,35 @@ def sum_f32(x):
     return acc
 
 
-def sigmoid3_bce_fwd(h1, h2, h3, target=None, tsum=None, want_p=False):
+def sigmoid3_bce_fwd(h1, h2, h3, target=None, tsum=None, want_p=False, numel_global=0):
     acc = torch.zeros(1, dtype=F32, device=h1.device) if target is not None else None
     p = torch.empty_like(h1) if want_p else None
-    abi.check(abi.lib().mcd_sigmoid3_bce_fwd(_p(h1), _p(h2), _p(h3), _p(target), _p(tsum), _p(acc), _p(p),
-                                             h1.numel(), _dev(h1), _stream(h1)), "sigmoid3_bce_fwd")
+    abi.check(abi.lib().mcd_sigmoid3_bce_fwd(_p(h1), _p(h2), _p(h3), _f32(h1), _p(target), _p(tsum), _p(acc), _p(p),
+                                             h1.numel(), int(numel_global), _dev(h1), _stream(h1)),
+              "sigmoid3_bce_fwd")
     return acc, p
 
 
-def sigmoid3_bce_bwd(h1, h2, h3, target, tsum, gscale):
+def sigmoid3_bce_bwd(h1, h2, h3, target, tsum, gscale, numel_global=0):
     d1, d2, d3 = torch.empty_like(h1), torch.empty_like(h2), torch.empty_like(h3)
-    abi.check(abi.lib().mcd_sigmoid3_bce_bwd(_p(h1), _p(h2), _p(h3), _p(target), _p(tsum), _p(gscale),
-                                             _p(d1), _p(d2), _p(d3), h1.numel(), _dev(h1), _stream(h1)),
-              "sigmoid3_bce_bwd")
+    abi.check(abi.lib().mcd_sigmoid3_bce_bwd(_p(h1), _p(h2), _p(h3), _f32(h1), _p(target), _p(tsum), _p(gscale),
+                                             _p(d1), _p(d2), _p(d3), h1.numel(), int(numel_global), _dev(h1),
+                                             _stream(h1)), "sigmoid3_bce_bwd")
     return d1, d2, d3
+
+
+def bce2d_fwd(p, target, tsum, numel_global=0):
+    acc = torch.zeros(1, dtype=F32, device=p.device)
+    abi.check(abi.lib().mcd_bce2d_fwd(_p(p), _p(target), _p(tsum), _p(acc), p.numel(), int(numel_global), _dev(p),
+                                      _stream(p)), "bce2d_fwd")
+    return acc
+
+
+def bce2d_bwd(p, target, tsum, gscale, numel_global=0):
+    d = torch.empty_like(p)
+    abi.check(abi.lib().mcd_bce2d_bwd(_p(p), _p(target), _p(tsum), _p(gscale), _p(d), p.numel(), int(numel_global),
+                                      _dev(p), _stream(p)), "bce2d_bwd")
+    return d
 
 
 def argmax_entropy(logits, c_arg=None, want_labels=True, want_entropy=True):
@@ -624,8 +744,8 @@ def argmax_entropy(logits, c_arg=None, want_labels=True, want_entropy=True):
     c_arg = c if c_arg is None else c_arg
     labels = torch.empty((n, h, w), dtype=torch.int64, device=logits.device) if want_labels else None
     acc = torch.zeros(1, dtype=F32, device=logits.device) if want_entropy else None
-    abi.check(abi.lib().mcd_argmax_entropy(_p(logits), _p(labels), _p(acc), n, c, c_arg, h, w, _dev(logits),
-                                           _stream(logits)), "argmax_entropy")
+    abi.check(abi.lib().mcd_argmax_entropy(_p(logits), _f32(logits), _p(labels), _p(acc), n, c, c_arg, h, w,
+                                           _dev(logits), _stream(logits)), "argmax_entropy")
     ent = (-acc[0] / float(n * c * h * w)) if want_entropy else None
     return labels, ent
 

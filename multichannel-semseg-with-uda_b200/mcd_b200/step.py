@@ -25,7 +25,8 @@ class MCDStep:
 
     def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
                  num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
-                 bucket_mb=25, reuse_target_forward=True, fused_sgd=True, defer_wgrad_reduce=True):
+                 bucket_mb=25, reuse_target_forward=True, fused_sgd=True, defer_wgrad_reduce=True,
+                 logits_dtype=torch.bfloat16):
         from models.model_util import get_optimizer
         self.mfnet = len(models) == 4
         self.gens = list(models[:-2])
@@ -33,6 +34,9 @@ class MCDStep:
         self.criterion, self.criterion_d = criterion, criterion_d
         self.num_k, self.mult = num_k, num_multiply_d_loss
         self.exact = exact_reference_backward
+        # full-resolution predictions only travel from the heads to the criteria inside the step: bfloat16 halves the
+        # traffic of the largest tensors (the modules' drop-in default is fp32, mcd_b200.nn.logits_dtype)
+        self.logits_dtype = logits_dtype
         # G is not updated between the phase-B target forward and the first phase-C forward (only optimizer_f
         # steps in between, adapt_trainer.py:195-207), so both forwards are the same computation: run it once,
         # keep its autograd graph for the C[0] backward and let BatchNorm take both momentum updates at once.
@@ -145,10 +149,10 @@ class MCDStep:
         if self._arena is None or self._arena.buf.device != src_imgs.device:
             self._arena = ops.ZeroArena(src_imgs.device)
         prev_arena = ops.set_arena(self._arena)
-        from .nn import DirectGrads
+        from .nn import DirectGrads, logits_dtype
         try:
             self._arena.begin()            # ONE memset for all BatchNorm-statistic / loss accumulators
-            with DirectGrads(defer=self.defer_reduce) as self._dg:
+            with DirectGrads(defer=self.defer_reduce) as self._dg, logits_dtype(self.logits_dtype):
                 self._dev = src_imgs.device
                 return self._iteration(crit, src_imgs, src_lbls, tgt_imgs)
         finally:

@@ -22,7 +22,7 @@ def get_class_weight_from_file(n_class, weight_filename=None, add_bg_loss=False)
 
 def calc_entropy(output):
     """-mean(p * log(p + 1e-6)), p = softmax(output, dim=1): one fused kernel over the logits."""
-    logits = output if output.dtype == torch.bfloat16 else output.to(torch.bfloat16)
+    logits = output if output.dtype in (torch.bfloat16, torch.float32) else output.float()
     _, ent = ops.argmax_entropy(logits.contiguous(), want_labels=False, want_entropy=True)
     return ent
 
@@ -30,7 +30,7 @@ def calc_entropy(output):
 def predict_labels(output, n_valid_class=None):
     """argmax over the first n_valid_class channels (testers drop the background channel:
     adapt_tester.py:121-124, adapt_triple_multitask_tester.py:139-142) -> int64 [B,H,W]."""
-    logits = output if output.dtype == torch.bfloat16 else output.to(torch.bfloat16)
+    logits = output if output.dtype in (torch.bfloat16, torch.float32) else output.float()
     labels, _ = ops.argmax_entropy(logits.contiguous(), c_arg=n_valid_class, want_labels=True,
                                    want_entropy=False)
     return labels

@@ -118,7 +118,7 @@ def test_conv_dgrad_wgrad(cuda_dev, shape, algo_name):
     gen = torch.Generator(device="cpu").manual_seed(7)
     dy = bf16_round(torch.randn(ref.shape, generator=gen)).to(cuda_dev)
     dx_ref, dw_ref = torch.autograd.grad(ref, (x, wt), dy)
-    xn, dyn = ops.to_nhwc(x.detach()), ops.to_nhwc(dy)
+    xn, dyn = ops.to_nhwc(x.detach()), ops.to_nhwc(dy, grad=True)
     g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
     dx = ops.conv_dgrad(dyn, ops.pack_weight_for(wt.detach(), g, 1, algo), g, algo=algo)
     dw, db = ops.conv_wgrad(xn, dyn, g, want_dbias=True, algo=algo)
@@ -160,7 +160,7 @@ def test_conv_dgrad_relu_bn_epilogue(cuda_dev, shape, algo_name):
     add = bf16_round(torch.randn(x.shape, generator=gen)).to(cuda_dev)
     (dx_ref,) = torch.autograd.grad(ref, xr, dy)
     g_ref = (dx_ref + add) * (x > 0)
-    xn, dyn, addn, yn = ops.to_nhwc(x), ops.to_nhwc(dy), ops.to_nhwc(add), ops.to_nhwc(bn_y)
+    xn, dyn, addn, yn = ops.to_nhwc(x), ops.to_nhwc(dy, grad=True), ops.to_nhwc(add, grad=True), ops.to_nhwc(bn_y)
     g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
     dx, sums = ops.conv_dgrad(dyn, ops.pack_weight_for(wt, g, 1, algo), g, algo=algo, add=addn, relu_src=xn,
                               bn_y=yn)
@@ -189,7 +189,7 @@ def test_conv_streamk_schedule(cuda_dev, shape):
     gen = torch.Generator(device="cpu").manual_seed(11)
     xn = ops.to_nhwc(x)
     g = ops.conv_geom(xn.shape, cin, cout, k, k, stride, dil, pad)
-    dyn = ops.to_nhwc(bf16_round(torch.randn(n, cout, g.Ho, g.Wo, generator=gen)).to(cuda_dev))
+    dyn = ops.to_nhwc(bf16_round(torch.randn(n, cout, g.Ho, g.Wo, generator=gen)).to(cuda_dev), grad=True)
     yn = ops.to_nhwc(bf16_round(torch.randn(n, cin, h, w, generator=gen)).to(cuda_dev))
     wf, wd = ops.pack_weight_for(wt, g, 0, abi.ALGO_UMMA), ops.pack_weight_for(wt, g, 1, abi.ALGO_UMMA)
     nf = ctypes.c_int(0)
@@ -264,7 +264,7 @@ def test_bn_act_fwd_bwd(cuda_dev, mode, training):
     else:
         rst = ops.bn_stats(rn.detach(), c) if training else None
         z = bn.fused(yn, st, relu=True, res=rn, res_stats=rst, res_bn=bn2)
-    z.backward(ops.to_nhwc(dz))
+    z.backward(ops.to_nhwc(dz, grad=True))
     torch.cuda.synchronize()
     assert rel_err(ops.to_nchw_f32(z.detach()), out) < 1e-2
     assert rel_err(ops.to_nchw_f32(yn.grad), yr.grad) < 1.5e-2

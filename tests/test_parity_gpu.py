@@ -1,23 +1,25 @@
-"""Parity of the CUDA path (reference-named modules over libmcd_sm100; bf16 storage, fp32 accumulate)
-against the fp32 oracle on identical weights and synthetic inputs.  Protocol and the
-tolerances asserted here:
+"""Parity of the CUDA path (reference-named modules over libmcd_sm100: IEEE-half forward storage, bfloat16 gradient
+storage, fp32 accumulate) against the fp32 oracle on identical weights and synthetic inputs.  Protocol (SURVEY.md
+section 8c) and what is asserted here; "max-norm" = max|a-b| / max|b|, "rel-L2" = |a-b|_2 / |b|_2:
 
-  per-layer activations                  max|a-b| / max|b| <= 2e-2 against fp32; every DRN unit of the real
-                                         network is fed the ORACLE's input / upstream gradient, so the number
-                                         measures that layer's kernels only
-  per-layer gradients                    relative L2 <= 4e-2 against the oracle with bf16-storage emulation,
-                                         <= 1.2e-1 against fp32 (ReLU-mask flips, see the comment at the asserts)
-  losses (CE, Diff2d, phases A/B/C)      relative <= 1e-3 (C-phase discrepancy <= 5e-3) against fp32
-  updated weights after one iteration    max|a-b| / max|b| <= 1e-3
-  argmax label maps (tester)             agreement >= 99 % against fp32 on random weights (the fp32 oracle vs its
-                                         own bf16-storage emulation reaches 99.2 %)
+  per-layer activations                  max-norm <= 2e-3 against fp32 (north_star bound 2e-2; measured 8.6e-4); every
+                                         DRN unit of the real network is fed the ORACLE's input / upstream gradient, so
+                                         the number measures that layer's kernels only
+  per-layer gradients                    rel-L2 <= 2e-2 against the oracle run with the SAME storage formats (kernel
+                                         correctness: measured <= 1.4e-2), and against fp32: dx <= 3e-2, parameter
+                                         gradients <= 6e-2, with >= 99 % of all gradient elements within 2e-2 of max|ref|
+  losses (CE, Diff2d, phases A/B/C, MFNet, multitask)   relative <= 1e-3 against fp32
+  updated weights after one iteration    max-norm <= 1e-3
+  argmax label maps (testers)            agreement >= 99.5 % against fp32 (measured 99.9 %)
   integer label / ignore_index / argmax handling: bit-exact (tests/test_kernels_gpu.py)
 
-End-to-end element-wise drift is REPORTED, not bounded at 2e-2: DRN-D-38 with train-mode BatchNorm at random
-weights amplifies any perturbation ~1.2x per layer (BatchNorm removes the perfectly-correlated channel mean
-after every ReLU), so two correct implementations that differ only in storage rounding end ~20 % apart after
-41 layers.  The test shows that our drift equals the drift of the fp32 oracle run with bf16 STORAGE emulation
-(oracle.storage) and asserts it stays within 1.5x of it.
+Why gradients are not within 2e-2 of fp32 element for element: the backward pass multiplies by the ReLU mask of the
+forward pass.  A pre-activation within rounding distance of zero has a different sign in any two implementations that
+round differently - a 100 % error on that element - and the rel-L2 error of a unit's gradients is 1.5 * sqrt(flip
+rate) (tests/tools/precision_study.py, tests/tools/debug_unit_real.py).  16-bit tensor-core operands bound the flip
+rate from below: 1e-4 with IEEE half (rel-L2 1.5e-2 ... 3e-2; what this library stores), 8e-4 with bfloat16
+(4e-2 ... 1e-1; round 1).  tcgen05 has no wider operand format at full rate, so the remaining distance to fp32 is the
+hardware's, not the kernels': against the oracle run with the same storage formats every unit agrees to <= 1.4e-2.
 """
 import os
 import warnings
@@ -118,9 +120,14 @@ def test_per_layer_forward_backward_vs_oracle(cuda_dev, size, n):
         return float((a - b).norm() / (b.norm() + 1e-30))
 
     spec_units = [u for stage in O.trunk_spec("drn_d_38", "base.") for u in stage]
-    lines = ["# unit | act max-err vs fp32 | dx, worst param-grad relative-L2 vs bf16-STORAGE oracle unit | "
-             "dx, worst param-grad relative-L2 vs fp32 oracle"]
+    lines = ["# unit | act max-norm vs fp32 | dx, worst param-grad rel-L2 vs the SAME-STORAGE oracle unit | "
+             "dx, worst param-grad rel-L2 vs fp32 oracle | fraction of gradient elements off by > 2e-2 of max|ref|"]
     worst = [0.0, 0.0, 0.0, 0.0, 0.0]
+    n_far, n_all = 0, 0
+
+    def far(a, b):
+        a, b = a.detach().float(), b.detach().float()
+        return int(((a - b).abs() > 2e-2 * b.abs().max()).sum()), a.numel()
     x_in, dx_ref_key = src, None
     for (key, mod, prefix), unit in zip(_units(mg), spec_units):
         assert O.unit_key(unit) == key
@@ -128,7 +135,7 @@ def test_per_layer_forward_backward_vs_oracle(cuda_dev, size, n):
         # bf16-storage emulation of this unit on the same input / upstream gradient
         sd_u = {k: v.detach().clone().requires_grad_(k in gG) for k, v in Go.items() if k.startswith(prefix)}
         xe = x_in.detach().clone().requires_grad_(not first)
-        with O.storage(torch.bfloat16):
+        with O.storage(torch.float16, grad=torch.bfloat16):
             oe = O.unit_forward(sd_u, unit, O._q(xe), True)
         pk = [k for k in sd_u if sd_u[k].requires_grad]
         ge = torch.autograd.grad(oe, ([] if first else [xe]) + [sd_u[k] for k in pk], d_out[key])
@@ -138,13 +145,18 @@ def test_per_layer_forward_backward_vs_oracle(cuda_dev, size, n):
         xin = ops.to_nhwc(x_in.detach()).requires_grad_(not first)
         mod.zero_grad()
         out = mod(xin)
-        out.backward(ops.to_nhwc(d_out[key]))
+        out.backward(ops.to_nhwc(d_out[key], grad=True))
         e_act = nerr(ops.to_nchw_f32(out), taps[key])
         e_dx = 0.0 if first else l2err(ops.to_nchw_f32(xin.grad), ge_x)
         l_dx = 0.0 if first else l2err(ops.to_nchw_f32(xin.grad), d_out[dx_ref_key])
         e_p = max(l2err(p.grad, ge_p[prefix + name]) for name, p in mod.named_parameters())
         l_p = max(l2err(p.grad, gG[prefix + name]) for name, p in mod.named_parameters())
-        lines.append("%-16s %.3e | %.3e %.3e | %.3e %.3e" % (key, e_act, e_dx, e_p, l_dx, l_p))
+        fa = [far(p.grad, gG[prefix + name]) for name, p in mod.named_parameters()]
+        if not first:
+            fa.append(far(ops.to_nchw_f32(xin.grad), d_out[dx_ref_key]))
+        n_far, n_all = n_far + sum(f[0] for f in fa), n_all + sum(f[1] for f in fa)
+        lines.append("%-16s %.3e | %.3e %.3e | %.3e %.3e | %.2e" % (key, e_act, e_dx, e_p, l_dx, l_p,
+                                                                   sum(f[0] for f in fa) / sum(f[1] for f in fa)))
         worst = [max(a, b) for a, b in zip(worst, (e_act, e_dx, e_p, l_dx, l_p))]
         x_in, dx_ref_key = taps[key], key
     # seg conv, head and loss, each on the oracle's input
@@ -161,18 +173,16 @@ def test_per_layer_forward_backward_vs_oracle(cuda_dev, size, n):
     (CrossEntropyLoss2d(w)(p1, lbl) + 0).backward()
     e_head = (nerr(p1, o1), nerr(mf1.up.weight.grad, g_up))
     lines += ["seg              %.3e %.3e %.3e" % e_seg, "head+ce          %.3e %.3e" % e_head]
-    lines.append("worst            %.3e | %.3e %.3e | %.3e %.3e" % tuple(worst))
+    lines.append("worst            %.3e | %.3e %.3e | %.3e %.3e | %.2e" % (tuple(worst) + (n_far / n_all,)))
     _log("parity_per_layer_%dx%d.txt" % size, lines)
-    assert worst[0] <= 2e-2, "activation %.3e" % worst[0]
-    # Gradients are compared norm-wise (relative L2).  A ReLU whose pre-activation lies within bf16 rounding of
-    # zero (0.14 % of elements vs fp32, 0.01 % vs the bf16-storage oracle) flips its mask, which is a 100 %
-    # error on that single element and, through the identity shortcut of a BasicBlock, lands un-diluted in dx:
-    # element-wise max errors are then O(0.3) for ANY two implementations (measured identically between the
-    # fp32 oracle and its own bf16-storage emulation, and between our tcgen05 and CUDA-core kernels).
-    assert worst[1] <= 4e-2, "input gradient vs bf16-storage oracle %.3e" % worst[1]
-    assert worst[2] <= 4e-2, "parameter gradient vs bf16-storage oracle %.3e" % worst[2]
-    assert worst[3] <= 0.12 and worst[4] <= 0.12, "fp32 relative-L2 %.3e %.3e" % (worst[3], worst[4])
-    assert max(e_seg) <= 2e-2 and max(e_head) <= 2e-2
+    assert worst[0] <= 2e-3, "activation %.3e" % worst[0]
+    # gradients: see the module docstring (ReLU-mask flips bound the distance to fp32 for 16-bit operands)
+    assert worst[1] <= 2e-2, "input gradient vs same-storage oracle %.3e" % worst[1]
+    assert worst[2] <= 2e-2, "parameter gradient vs same-storage oracle %.3e" % worst[2]
+    assert worst[3] <= 3e-2, "input gradient vs fp32: rel-L2 %.3e" % worst[3]
+    assert worst[4] <= 6e-2, "parameter gradient vs fp32: rel-L2 %.3e" % worst[4]
+    assert n_far / n_all <= 1e-2, "gradient elements off by more than 2e-2 of max|ref|: %.3e" % (n_far / n_all)
+    assert max(e_seg) <= 5e-3 and max(e_head) <= 2e-3
 
 
 def test_end_to_end_losses_and_drift_vs_oracle(cuda_dev):
@@ -197,7 +207,7 @@ def test_end_to_end_losses_and_drift_vs_oracle(cuda_dev):
         return g_, taps_, feat_, float(ce_), float(d_)
 
     g32, taps32, feat32, ce32, d32 = run_oracle(None)
-    _, taps16, feat16, ce16, d16 = run_oracle(torch.bfloat16)
+    _, taps16, feat16, ce16, d16 = run_oracle(torch.float16)
     outs = {}
     handles = [mod.register_forward_hook(lambda m, i, o, key=key: outs.__setitem__(key, o.detach()))
                for key, mod, _ in _units(mg)]
@@ -211,7 +221,7 @@ def test_end_to_end_losses_and_drift_vs_oracle(cuda_dev):
         ft = mg(tgt)
         d = float(Diff2d()(mf1(ft), mf2(ft)))
     from mcd_b200 import ops
-    lines = ["# unit   cuda-vs-fp32   bf16-storage-oracle-vs-fp32   cuda-vs-bf16-storage-oracle"]
+    lines = ["# unit   cuda-vs-fp32   same-storage-oracle-vs-fp32   cuda-vs-same-storage-oracle   (max-norm)"]
     ratio_ok = True
     for key in outs:
         a = ops.to_nchw_f32(outs[key])
@@ -219,12 +229,13 @@ def test_end_to_end_losses_and_drift_vs_oracle(cuda_dev):
         lines.append("%-16s %.3e %.3e %.3e" % (key, e_c, e_e, nerr(a, taps16[key])))
         ratio_ok &= e_c <= 1.5 * e_e + 5e-3
     lines += ["feat %.3e %.3e" % (nerr(feat, feat32), nerr(feat16, feat32)),
-              "ce   cuda %.6f  fp32 %.6f  bf16-storage %.6f" % (ce, ce32, ce16),
-              "diff cuda %.6e  fp32 %.6e  bf16-storage %.6e" % (d, d32, d16)]
+              "ce   cuda %.6f  fp32 %.6f  same-storage %.6f" % (ce, ce32, ce16),
+              "diff cuda %.6e  fp32 %.6e  same-storage %.6e" % (d, d32, d16)]
     _log("parity_end_to_end_drift.txt", lines)
     assert abs(ce - ce32) / abs(ce32) <= 1e-3
-    assert abs(d - d32) / abs(d32) <= 5e-3
-    assert ratio_ok, "drift exceeds 1.5x the bf16-storage emulation of the oracle"
+    assert abs(d - d32) / abs(d32) <= 1e-3
+    assert ratio_ok, "drift exceeds 1.5x the same-storage emulation of the oracle"
+    assert nerr(feat, feat32) <= 6e-2          # 41 layers end to end (bf16 storage: 0.26)
     # running statistics took the same two momentum updates (src, tgt)
     assert nerr(mg.base[8][1].running_var, g32["base.8.1.running_var"]) < 2e-2
     assert nerr(mg.base[0][1].running_mean, g32["base.0.1.running_mean"]) < 2e-2
@@ -288,7 +299,7 @@ def test_mcd_iteration_vs_oracle(cuda_dev):
     assert abs(c_loss - c_o) / abs(c_o) <= 1e-3
     assert abs(b_loss - float(rec["B_loss"])) / abs(float(rec["B_loss"])) <= 1e-3
     for a, b in zip(c_losses, rec["C_losses"]):
-        assert abs(a - b) / abs(b) <= 5e-3
+        assert abs(a - b) / abs(b) <= 1e-3
     assert max(werr.values()) <= 1e-3          # weights after 5 G-steps at lr 1e-3
     assert nerr(model_f1.up.weight, F1["up.weight"]) <= 1e-3
     assert nerr(model_g.base[4][0].bn1.running_var, G["base.4.0.bn1.running_var"]) <= 2e-2
@@ -316,7 +327,7 @@ def test_tester_argmax_entropy_vs_oracle(cuda_dev):
     with torch.no_grad():
         out = mf1(mg(tgt))
         ref = O.head_forward(F1, O.seg_base_forward(G, tgt, train=False))
-        with O.storage(torch.bfloat16):
+        with O.storage(torch.float16, act=None):     # trunk storage as ours; the predictions stay fp32
             ref16 = O.head_forward(F1, O.seg_base_forward(G, tgt, train=False))
     pred = util.predict_labels(out, N_CLASS - 1)
     ref_pred = O.predict_labels(ref, N_CLASS - 1)
@@ -325,17 +336,17 @@ def test_tester_argmax_entropy_vs_oracle(cuda_dev):
     agree_oo = float((O.predict_labels(ref16, N_CLASS - 1) == ref_pred).float().mean())
     ent, ent_o = float(util.calc_entropy(out)), float(O.calc_entropy(ref))
     _log("parity_tester.txt", ["argmax agreement cuda vs fp32 oracle %.5f" % agree,
-                               "argmax agreement cuda vs bf16-storage oracle %.5f" % agree16,
-                               "argmax agreement bf16-storage oracle vs fp32 oracle %.5f" % agree_oo,
+                               "argmax agreement cuda vs same-storage oracle %.5f" % agree16,
+                               "argmax agreement same-storage oracle vs fp32 oracle %.5f" % agree_oo,
                                "entropy %.6e vs %.6e" % (ent, ent_o),
-                               "logit err vs fp32 %.3e vs bf16-storage %.3e" % (nerr(out, ref), nerr(out, ref16)),
+                               "logit err vs fp32 %.3e vs same-storage %.3e" % (nerr(out, ref), nerr(out, ref16)),
                                "distinct labels %d" % int(ref_pred.unique().numel())])
     assert pred.dtype == torch.int64 and pred.shape == (1, 480, 640)
-    # synthetic random weights give 40-way near-ties on most pixels: bf16 storage alone (the fp32 oracle against
-    # its own bf16-storage emulation) moves 0.8 % of them, and so does the CUDA path.
-    assert agree >= 0.99 and agree16 >= 0.99, (agree, agree16)
-    assert agree >= agree_oo - 0.003
-    assert abs(ent - ent_o) / abs(ent_o) <= 1e-2
+    assert out.dtype == torch.float32          # the drop-in default: `.cpu().numpy()` of adapt_tester.py:114-118 works
+    assert out[0].data.cpu().numpy().shape == (N_CLASS, 480, 640)
+    # north_star: >= 99.5 % of the pixels (synthetic random weights give 40-way near-ties: bf16 storage moved 0.8 %)
+    assert agree >= 0.995 and agree16 >= 0.995, (agree, agree16)
+    assert abs(ent - ent_o) / abs(ent_o) <= 1e-3
 
 
 @pytest.mark.parametrize("graph", [False, True, "prefetch"])
@@ -374,7 +385,7 @@ def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
             c, d = step(src, lbl, tgt)
     torch.cuda.synchronize()
     assert abs(float(c) - c_o) / abs(c_o) <= 1e-3
-    assert abs(float(d) - d_o) / abs(d_o) <= 5e-3
+    assert abs(float(d) - d_o) / abs(d_o) <= 1e-3
     werr = max(nerr(p, G[k]) for k, p in models[0].named_parameters())
     assert werr <= 2e-3, werr
     assert nerr(models[1].up.weight, F1["up.weight"]) <= 2e-3
@@ -418,11 +429,11 @@ def test_mfnet_step_vs_oracle(cuda_dev, method, kind):
     torch.cuda.synchronize()
     assert outputs1.shape == (n, N_CLASS, *size)
     assert abs(float(ce) - float(ce_o)) / abs(float(ce_o)) <= 1e-3
-    assert abs(float(d) - float(d_o)) / abs(float(d_o)) <= 1e-2
-    # head parameters: dW = sum x (x) dout inherits the ~20 % end-to-end drift of the 41-layer features x
+    assert abs(float(d) - float(d_o)) / abs(float(d_o)) <= 1e-3
+    # head parameters: dW = sum x (x) dout inherits the end-to-end drift of the 41-layer features x (3 % at layer 8)
     for k, p in f1.named_parameters():
         e = float((p.grad - gF1[k]).norm() / gF1[k].norm())
-        assert e <= 0.25, (k, e)
+        assert e <= 0.05, (k, e)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for m in (g3, g1) for p in m.parameters())
     # the fused ScoreAdd head equals up1(x1) + up2(x2) on identical inputs
     with torch.no_grad():
@@ -473,8 +484,8 @@ def test_triple_multitask_vs_oracle(cuda_dev):
     torch.cuda.synchronize()
     for name, a, b in (("semseg", semseg, semseg_o), ("depth", dep, dep_o), ("boundary", bd, bd_o),
                        ("tgt_depth", tdep, tdep_o)):
-        assert abs(float(a) - float(b)) / abs(float(b)) <= 5e-3, (name, float(a), float(b))
-    assert abs(float(disc) - float(disc_o)) / abs(float(disc_o)) <= 2e-2
+        assert abs(float(a) - float(b)) / abs(float(b)) <= 1e-3, (name, float(a), float(b))
+    assert abs(float(disc) - float(disc_o)) / abs(float(disc_o)) <= 1e-3
     # decoder-side gradients (short path): uncertainty scalars, boundary convs, last decoder layers
     for k in ("s_semsegcls", "s_deprgr", "s_boundary", "conv3.bias", "conv1.weight", "deprgr_dec.conv3.weight",
               "semsegcls_dec1.conv3.bias"):
@@ -493,7 +504,7 @@ def test_triple_multitask_vs_oracle(cuda_dev):
         depth_o, bd_map_o = O.triple_depth(D, f, train=False), O.triple_boundary(D, f)
     assert semseg1.shape == (1, N_CLASS, *size) and depth.shape == (1, 3, *size) and boundary.shape == (1, 1, *size)
     agree = float((util.predict_labels(semseg1, N_CLASS - 1) == O.predict_labels(s1_o, N_CLASS - 1)).float().mean())
-    assert agree >= 0.98, agree
+    assert agree >= 0.995, agree
     # eval mode on un-calibrated random running statistics is ill-conditioned for the deep h8 branch: compare the
     # probability maps on average, the shallow-branch-dominated structure must agree
     assert float((boundary.float() - bd_map_o).abs().mean()) <= 2e-2
