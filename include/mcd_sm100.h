@@ -290,6 +290,9 @@ int mcd_bce2d_fwd(const float* p, const float* target, const float* tsum, float*
                   int64_t numel_global, int device, void* stream);
 int mcd_bce2d_bwd(const float* p, const float* target, const float* tsum, const float* gscale, float* dp,
                   int64_t numel, int64_t numel_global, int device, void* stream);
+/* get_boundary of models/dilated_fcn.py:769-773: out (fp32 [N,H,W]) = 1 where the 3x3 max of x differs from the
+ * 3x3 min (max_pool2d(x) != -max_pool2d(-x), stride 1, padding 1), else 0.  x: int64 labels (is_int64) or fp32. */
+int mcd_label_boundary(const void* x, int is_int64, float* out, int N, int H, int W, int device, void* stream);
 /* Testers: argmax over channels [0, C_arg) (first max wins, like torch.max) + entropy partial
  * acc[0] += sum_c p*log(p+1e-6) over all C channels (adapt_tester.py:104-124, util.py:44-48). */
 int mcd_argmax_entropy(const void* logits, int f32, int64_t* labels, float* acc, int N, int C, int C_arg,

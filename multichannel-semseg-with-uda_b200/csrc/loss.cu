@@ -463,6 +463,33 @@ bce2d_bwd_kernel(const float* __restrict__ p, const float* __restrict__ target, 
   }
 }
 
+// morphological boundary of a label / value map (models/dilated_fcn.py:769-773 get_boundary): out = 1 where the 3x3
+// maximum differs from the 3x3 minimum (max_pool2d of x and of -x, padding excluded), else 0.  T = int64 labels or
+// fp32 values; comparisons are exact in either type.
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_boundary_kernel(const T* __restrict__ x, float* __restrict__ out, int H, int W, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), h = (int)((i / W) % H);
+    const T* base = x + (i - (int64_t)h * W - w);
+    T mx = base[(int64_t)h * W + w], mn = mx;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int hh = h + dh;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int ww = w + dw;
+        if (ww < 0 || ww >= W) continue;
+        const T v = base[(int64_t)hh * W + ww];
+        mx = v > mx ? v : mx;
+        mn = v < mn ? v : mn;
+      }
+    }
+    out[i] = mx != mn ? 1.f : 0.f;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 argmax_entropy_kernel(const T* __restrict__ logits, int64_t* __restrict__ labels,
@@ -701,6 +728,17 @@ int mcd_bce2d_bwd(const float* p, const float* target, const float* tsum, const 
   const float inv_global = (float)(1.0 / (double)(numel_global > 0 ? numel_global : numel));
   bce2d_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(p, target, tsum, gscale, dp, inv_global, numel);
   return check_launch("bce2d_bwd");
+}
+
+int mcd_label_boundary(const void* x, int is_int64, float* out, int N, int H, int W, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && out && N > 0 && H > 0 && W > 0, "label_boundary: bad arguments");
+  const int64_t total = (int64_t)N * H * W;
+  if (is_int64)
+    label_boundary_kernel<int64_t><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const int64_t*)x, out, H, W, total);
+  else
+    label_boundary_kernel<float><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const float*)x, out, H, W, total);
+  return check_launch("label_boundary");
 }
 
 int mcd_argmax_entropy(const void* logits, int f32, int64_t* labels, float* acc, int N, int C, int C_arg,

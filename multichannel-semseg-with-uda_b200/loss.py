@@ -33,10 +33,54 @@ def _gscale(go):
     return go.reshape(1).to(F32).contiguous()
 
 
+# data-parallel runs (one process per GPU, mcd_b200/parallel.py): with a process group set, every criterion returns
+# its rank's SHARE of the loss nn.DataParallel computes on the gathered outputs, so that the shares sum to the
+# global-batch loss and SUM-all-reduced gradients equal the global-batch gradients:
+#   CrossEntropyLoss2d   local sum w*nll / GLOBAL sum w (the normaliser is all-reduced)
+#   Diff2d, mse, bce2d   local mean / world; the class balance beta of bce2d (loss.py:133 `1 - mean(target)`) is
+#                        computed from the all-reduced target sum.
+_dp_group = False
+
+
+def set_process_group(group=None):
+    """None = the default group (when torch.distributed is initialised with world > 1), False = single process."""
+    global _dp_group
+    import torch.distributed as dist
+    ok = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    _dp_group = group if ok else False
+
+
+def _target_sum(target):
+    """(sum(target) over the global batch, global element count)"""
+    tsum = ops.sum_f32(target)
+    if _dp_group is False:
+        return tsum, target.numel()
+    import torch.distributed as dist
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM, group=_dp_group)
+    return tsum, target.numel() * dist.get_world_size(_dp_group)
+
+
+def dp_world():
+    """number of ranks the criteria share the global batch with (1 = single process)."""
+    if _dp_group is False:
+        return 1
+    import torch.distributed as dist
+    return dist.get_world_size(_dp_group)
+
+
+def _share(go):
+    """mean-type criteria return local_mean / world: their rank's share of the global-batch mean"""
+    g = _gscale(go)
+    w = dp_world()
+    return g / w if w > 1 else g
+
+
 class _CE2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, weight, ignore_index, size_average, dist_group=False):
         acc = ops.ce2d_fwd(logits, target, weight, ignore_index)
+        if dist_group is False:
+            dist_group = _dp_group
         if dist_group is not False and size_average:
             # data parallel: the normaliser sum_i w[y_i] is global (what nn.DataParallel computes on the
             # gathered outputs); the numerator stays local so that SUM-all-reduced gradients are exact.
@@ -100,12 +144,12 @@ class _Diff2dFn(torch.autograd.Function):
         else:
             acc, stats = ops.diff2d_fwd(a, b), None
         ctx.save_for_backward(a, b, stats)
-        return acc[0] / float(a.numel())
+        return acc[0] / float(a.numel() * dp_world())
 
     @staticmethod
     def backward(ctx, go):
         a, b, stats = ctx.saved_tensors
-        da, db = ops.diff2d_bwd(a, b, _gscale(go), stats)
+        da, db = ops.diff2d_bwd(a, b, _share(go), stats)
         return da, db
 
 
@@ -123,42 +167,17 @@ class _MSEFn(torch.autograd.Function):
     def forward(ctx, pred, target):
         acc = ops.mse_fwd(pred, target)
         ctx.save_for_backward(pred, target)
-        return acc[0] / float(pred.numel())
+        return acc[0] / float(pred.numel() * dp_world())
 
     @staticmethod
     def backward(ctx, go):
         pred, target = ctx.saved_tensors
-        return ops.mse_bwd(pred, target, _gscale(go)), None
+        return ops.mse_bwd(pred, target, _share(go)), None
 
 
 def mse_loss(pred, target):
     """F.mse_loss(pred, target) for the HHA regression head (reference models/dilated_fcn.py:712,958)."""
     return _MSEFn.apply(_logits(pred), target.to(F32).contiguous())
-
-
-# data-parallel runs (one process per GPU): batch-GLOBAL statistics inside a criterion are all-reduced over this
-# group - the class-balance beta of bce2d (loss.py:133 `1 - mean(target)`; what nn.DataParallel computes on the
-# gathered outputs).  The loss VALUES stay local means; the step runner divides by the world size so that
-# SUM-all-reduced gradients equal the global-batch gradients (mcd_b200/parallel.py).
-_dp_group = False
-
-
-def set_process_group(group=None):
-    """None = the default group (when torch.distributed is initialised with world > 1), False = single process."""
-    global _dp_group
-    import torch.distributed as dist
-    ok = group is not False and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    _dp_group = group if ok else False
-
-
-def _target_sum(target):
-    """(sum(target) over the global batch, global element count)"""
-    tsum = ops.sum_f32(target)
-    if _dp_group is False:
-        return tsum, target.numel()
-    import torch.distributed as dist
-    dist.all_reduce(tsum, op=dist.ReduceOp.SUM, group=_dp_group)
-    return tsum, target.numel() * dist.get_world_size(_dp_group)
 
 
 class _Sigmoid3BCEFn(torch.autograd.Function):
@@ -168,12 +187,12 @@ class _Sigmoid3BCEFn(torch.autograd.Function):
         acc, _ = ops.sigmoid3_bce_fwd(h1, h2, h3, target, tsum, numel_global=nglobal)
         ctx.save_for_backward(h1, h2, h3, target, tsum)
         ctx.nglobal = nglobal
-        return acc[0] / float(h1.numel())
+        return acc[0] / float(nglobal)
 
     @staticmethod
     def backward(ctx, go):
         h1, h2, h3, target, tsum = ctx.saved_tensors
-        d1, d2, d3 = ops.sigmoid3_bce_bwd(h1, h2, h3, target, tsum, _gscale(go), numel_global=ctx.nglobal)
+        d1, d2, d3 = ops.sigmoid3_bce_bwd(h1, h2, h3, target, tsum, _share(go), numel_global=ctx.nglobal)
         return d1, d2, d3, None
 
 
@@ -184,12 +203,12 @@ class _BCE2dFn(torch.autograd.Function):
         acc = ops.bce2d_fwd(p, target, tsum, numel_global=nglobal)
         ctx.save_for_backward(p, target, tsum)
         ctx.nglobal = nglobal
-        return acc[0] / float(p.numel())
+        return acc[0] / float(nglobal)
 
     @staticmethod
     def backward(ctx, go):
         p, target, tsum = ctx.saved_tensors
-        return ops.bce2d_bwd(p, target, tsum, _gscale(go), numel_global=ctx.nglobal), None
+        return ops.bce2d_bwd(p, target, tsum, _share(go), numel_global=ctx.nglobal), None
 
 
 def sigmoid3_bce2d(h1, h2, h3, target):

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "mcd_sigmoid3_bce_bwd": (c_int, [P, P, P, c_int, P, P, P, P, P, P, c_int64, c_int64, c_int, P]),
     "mcd_bce2d_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, P]),
     "mcd_bce2d_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, P]),
+    "mcd_label_boundary": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "mcd_argmax_entropy": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_int, c_int, P]),
 }

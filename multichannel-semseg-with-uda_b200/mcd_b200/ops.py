@@ -738,6 +738,18 @@ def bce2d_bwd(p, target, tsum, gscale, numel_global=0):
     return d
 
 
+def label_boundary(x):
+    """3x3 morphological boundary map (fp32 0/1, shape of x) of int64 labels or fp32 values [..., H, W]."""
+    x = x.contiguous()
+    if x.dtype not in (torch.int64, F32):
+        x = x.float()
+    h, w = x.shape[-2], x.shape[-1]
+    out = torch.empty(x.shape, dtype=F32, device=x.device)
+    abi.check(abi.lib().mcd_label_boundary(_p(x), int(x.dtype == torch.int64), _p(out), x.numel() // (h * w), h, w,
+                                           _dev(x), _stream(x)), "label_boundary")
+    return out
+
+
 def argmax_entropy(logits, c_arg=None, want_labels=True, want_entropy=True):
     """labels int64 [N,H,W] = argmax over channels [0,c_arg); entropy = -mean(p*log(p+1e-6))."""
     n, c, h, w = logits.shape

@@ -37,6 +37,7 @@ class GradSync:
         if dist.is_available() and dist.is_initialized():
             self.world = dist.get_world_size(process_group)
         self.armed = False
+        self._got = set()
         self.buckets = []
         self._by_param = {}
         self.flat = self.world > 1
@@ -90,6 +91,7 @@ class GradSync:
                     p.grad = b.flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
             b.pending, b.work, b.event = len(b.params), None, None
+        self._got = set()
         self.armed = armed and self.world > 1
 
     def disarm(self):
@@ -99,6 +101,7 @@ class GradSync:
         if not self.armed:
             return
         b = self._by_param[p]
+        self._got.add(p)
         b.pending -= 1
         if b.pending == 0:
             self._launch(b)
@@ -137,6 +140,11 @@ class GradSync:
                 b.work = None
         if self.comm_stream is not None:
             torch.cuda.current_stream(self.buckets[0].flat.device).wait_stream(self.comm_stream)
+        # parameters no rank produced a gradient for (unused decoders: identical on every rank) keep `grad is None`
+        # semantics: the optimizer skips them instead of applying momentum / weight decay to a zero gradient
+        for p in self.params:
+            if p not in self._got:
+                p.grad = None
         self.armed = False
 
 

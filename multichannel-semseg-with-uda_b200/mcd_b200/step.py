@@ -1,13 +1,24 @@
-"""The MCD iteration (phase A, B, num_k x C) as one callable, mirroring the reference's inline loop bodies
-(adapt_trainer.py:162-212, adapt_mfnet_trainer.py:181-235) over the drop-in modules.
+"""The MCD iteration (phase A, B, num_k x C) as one callable, mirroring the reference's inline loop bodies over the
+drop-in modules:
 
-Differences from the reference loop that do NOT change any result (SURVEY.md section 8a16 "legal savings"):
-  * phase B back-propagates only into the classifiers: the reference also back-propagates through G and then
-    throws those gradients away (`optimizer_g.zero_grad()` at adapt_trainer.py:205 before any use), which is
-    ~1 TFLOP of dead work per image pair.  `exact_reference_backward=True` restores the dead work.
+    early fusion   adapt_trainer.py:162-212                      MCDStep((model_g, model_f1, model_f2), ...)
+    MFNet          adapt_mfnet_trainer.py:181-235                MCDStep((model_g_3ch, model_g_1ch, model_f1, model_f2), ...)
+    seg + HHA      adapt_multitask_trainer.py:194-262            MCDStep.multitask(model_enc, model_dec, triple=False, ...)
+    seg+HHA+bd     adapt_triple_multitask_trainer.py:202-287     MCDStep.multitask(model_enc, model_dec, triple=True, ...)
+
+Differences from the reference loops that do NOT change any result (SURVEY.md section 8a16 "legal savings"):
+  * phase B back-propagates only into the classifiers / decoders: the reference also back-propagates through the
+    generator / encoder and then throws those gradients away (`optimizer_g.zero_grad()` at adapt_trainer.py:205
+    before any use), which is ~1 TFLOP of dead work per image pair.  `exact_reference_backward=True` restores it.
+  * the triple trainer computes the depth and boundary losses of phase B and does not use them
+    (adapt_triple_multitask_trainer.py:256-276): only the weighted segmentation term is back-propagated; the depth
+    decoder still runs forward (no graph) because its train-mode BatchNorm statistics take an update there.
   * gradients live in flat per-optimizer buffers (one memset instead of ~250 zero_grad kernels); with
     world_size > 1 the buffers are all-reduced with NCCL in buckets overlapped with wgrad (parallel.GradSync).
   * losses stay on the device; `.item()` is the caller's choice (the reference syncs every phase).
+Parameters that receive no gradient in a phase (unused decoders, adapt_triple_multitask_trainer.py:276; `nmlrgr_dec`
+always) are skipped by the optimizer, as torch.optim does for `grad is None` (torch >= 2.0 `zero_grad()`, which is what
+the oracle is pinned against; torch 0.4.1 would still apply momentum / weight decay to them).
 """
 import torch
 
@@ -19,20 +30,95 @@ def ops_mod():
     return ops
 
 
+def _detach(t):
+    """detach a feature structure (tensor / tuple / dict) keeping the IEEE-half originals attached (mcd_b200.ops)."""
+    if isinstance(t, dict):
+        return {k: _detach(v) for k, v in t.items()}
+    if isinstance(t, (tuple, list)):
+        return tuple(_detach(v) for v in t)
+    d = t.detach()
+    tw = getattr(t, "_mcd_h16", None)
+    if tw is not None:
+        d._mcd_h16 = tw
+    return d
+
+
+# ---- the four trainers as "tasks": what differs between them is how features and the three objectives are formed --
+class _EarlyFusionTask:
+    """adapt_trainer.py:162-212 (one generator) / adapt_mfnet_trainer.py:181-235 (RGB + HHA generators)."""
+    a_uses_target = False
+
+    def __init__(self, models, criterion, criterion_d, mult):
+        self.gens, (self.f1, self.f2) = list(models[:-2]), models[-2:]
+        self.clfs = [self.f1] if self.f2 is self.f1 else [self.f1, self.f2]
+        self.mfnet = len(self.gens) == 2
+        self.criterion, self.criterion_d = criterion, criterion_d
+        # adapt_mfnet_trainer.py:233 does NOT multiply the phase-C loss by num_multiply_d_loss (adapt_trainer.py:210 does)
+        self.mult = 1.0 if self.mfnet else mult
+
+    def features(self, x):
+        if not self.mfnet:
+            return (self.gens[0](x),)
+        return self.gens[0](x[:, :3]), self.gens[1](x[:, 3:])       # adapt_mfnet_trainer.py:186-187
+
+    def _ce(self, feats, lbls):
+        return self.criterion(self.f1(*feats), lbls) + self.criterion(self.f2(*feats), lbls)
+
+    def loss_a(self, fs, ft, src, lbls, tgt):
+        return self._ce(fs, lbls)
+
+    def loss_b(self, fs, ft, src, lbls, tgt):
+        return self._ce(fs, lbls) - self.disc(ft)
+
+    def disc(self, ft):
+        return self.criterion_d(self.f1(*ft), self.f2(*ft))
+
+
+class _MultiTaskTask:
+    """adapt_multitask_trainer.py:194-262 (triple=False) / adapt_triple_multitask_trainer.py:202-287 (triple=True)."""
+    a_uses_target = True
+
+    def __init__(self, model_enc, model_dec, triple, mult):
+        self.gens, self.clfs = [model_enc], [model_dec]
+        self.enc, self.dec, self.triple, self.mult = model_enc, model_dec, triple, mult
+
+    def features(self, x):
+        return self.enc(x[:, :3])
+
+    def loss_a(self, fs, ft, src, lbls, tgt):
+        if self.triple:
+            terms = self.dec.get_loss(fs, lbls, src[:, 3:-1], src[:, -1:], separately_returning=True)
+        else:
+            terms = self.dec.get_loss(fs, lbls, src[:, 3:], separately_returning=True)
+        return sum(terms) + self.dec.get_depth_loss(ft, tgt[:, 3:])
+
+    def loss_b(self, fs, ft, src, lbls, tgt):
+        if self.triple:      # :274-276 loss = src_semseg_loss - tgt_discrepancy (depth / boundary terms are dead)
+            with torch.no_grad():           # ... but get_loss() ran the depth decoder in train mode: its BatchNorm
+                self.dec.depth_forward(fs)  # running statistics take that update (forward only, 25 GF / image)
+            return self.dec.get_weighted_semseg_loss(fs, lbls) - self.disc(ft)
+        semseg, depth = self.dec.get_loss(fs, lbls, src[:, 3:], separately_returning=True)
+        return semseg + depth + self.dec.get_depth_loss(ft, tgt[:, 3:]) - self.disc(ft)    # adapt_multitask_trainer.py:220
+
+    def disc(self, ft):
+        return self.dec.get_cls_descrepancy(ft)
+
+
 class MCDStep:
     """method 'MCD' (early fusion): models = (model_g, model_f1, model_f2);
-    method 'MFNet': models = (model_g_3ch, model_g_1ch, model_f1, model_f2)."""
+    method 'MFNet': models = (model_g_3ch, model_g_1ch, model_f1, model_f2);
+    multitask trainers: MCDStep.multitask(model_enc, model_dec, triple=...).
+    Call it with (src_imgs, src_lbls, tgt_imgs) exactly as the trainers' loops receive them."""
 
     def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
                  num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
                  bucket_mb=25, reuse_target_forward=True, fused_sgd=True, defer_wgrad_reduce=True,
-                 logits_dtype=torch.bfloat16):
+                 logits_dtype=torch.bfloat16, task=None):
         from models.model_util import get_optimizer
-        self.mfnet = len(models) == 4
-        self.gens = list(models[:-2])
-        self.f1, self.f2 = models[-2], models[-1]
-        self.criterion, self.criterion_d = criterion, criterion_d
-        self.num_k, self.mult = num_k, num_multiply_d_loss
+        self.task = task if task is not None else _EarlyFusionTask(models, criterion, criterion_d, num_multiply_d_loss)
+        self.gens, self.clfs = self.task.gens, self.task.clfs
+        self.mfnet = getattr(self.task, "mfnet", False)
+        self.num_k, self.mult = num_k, self.task.mult
         self.exact = exact_reference_backward
         # full-resolution predictions only travel from the heads to the criteria inside the step: bfloat16 halves the
         # traffic of the largest tensors (the modules' drop-in default is fp32, mcd_b200.nn.logits_dtype)
@@ -42,37 +128,46 @@ class MCDStep:
         # keep its autograd graph for the C[0] backward and let BatchNorm take both momentum updates at once.
         self.reuse_t = reuse_target_forward and not exact_reference_backward
         g_params = [p for m in self.gens for p in m.parameters() if p.requires_grad]
-        f_params = [p for p in self.f1.parameters() if p.requires_grad]
-        if self.f2 is not self.f1:
-            f_params += [p for p in self.f2.parameters() if p.requires_grad]
+        f_params = [p for m in self.clfs for p in m.parameters() if p.requires_grad]
         self.optimizer_g = get_optimizer(g_params, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.optimizer_f = get_optimizer(f_params, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay)
         self.sync_g = parallel.GradSync(g_params, process_group, bucket_mb)
         self.sync_f = parallel.GradSync(f_params, process_group, bucket_mb)
         self._arena = None
         self.phase_events = None       # a list: (phase name, CUDA event) appended at every phase boundary (bench.py)
-        self._packer_g = None
-        self._fused_g = None
-        self.fused_sgd = fused_sgd     # optimizer_g.step() + weight re-pack as one kernel (plain momentum SGD only)
+        self._packers, self._fused = {}, {}
+        self.fused_sgd = fused_sgd     # optimizer.step() + weight re-pack as one kernel (plain momentum SGD only)
         # single process + fused SGD: the split-K partial sums of the tcgen05 wgrad kernels are reduced by the
         # optimizer kernel itself (ops.FusedSGD.deferred); with world > 1 the all-reduce needs real gradients
         self.defer_reduce = (fused_sgd and defer_wgrad_reduce and self.sync_g.world == 1
                              and not exact_reference_backward)
         self.world = self.sync_g.world
-        if self.world > 1 and hasattr(criterion, "set_process_group"):
-            criterion.set_process_group(process_group)   # global sum-of-weights normaliser (DataParallel parity)
+        self.group = process_group
+        if self.world > 1:
+            # every criterion returns this rank's SHARE of the global-batch loss (loss.set_process_group): the
+            # SUM-all-reduced gradients then equal the gradients nn.DataParallel computes on the gathered outputs
+            import loss as _loss
+            _loss.set_process_group(process_group)
+        self.graph = None
+        self._captured_lr = None
+
+    @classmethod
+    def multitask(cls, model_enc, model_dec, triple=True, num_multiply_d_loss=1.0, **kw):
+        """adapt_multitask_trainer.py (triple=False) / adapt_triple_multitask_trainer.py (triple=True): the criteria
+        live inside model_dec (semseg_criterion / discrepancy_criterion given to get_*multitask_models)."""
+        return cls(None, None, None, task=_MultiTaskTask(model_enc, model_dec, triple, num_multiply_d_loss), **kw)
 
     # -- CUDA-graph execution ---------------------------------------------------------------------
     def capture(self, src_imgs, src_lbls, tgt_imgs, warmup=2):
         """Capture the whole iteration (forward, backward, optimizer steps, weight re-packing) in ONE CUDA
-        graph: the ~3500 kernel launches of an iteration are then replayed without any host work.  Inputs are
+        graph: the kernel launches of an iteration are then replayed without any host work.  Inputs are
         copied into static buffers by `replay`."""
         from . import abi
-        # world > 1: the NCCL bucket all-reduces (side stream, forked / joined with stream waits) and the 4-float
-        # normaliser all-reduce are captured as graph nodes too; every rank replays the same sequence.
+        # world > 1: the NCCL bucket all-reduces (side stream, forked / joined with stream waits) and the scalar
+        # all-reduces of the criteria are captured as graph nodes too; every rank replays the same sequence.
         dev = src_imgs.device
-        if self._packer_g is None and not self._fused_g:
-            warmup = max(warmup, 1)        # lazily built host tables (weight re-pack list) need one eager iteration
+        if not self._fused:
+            warmup = max(warmup, 1)        # lazily built host tables (optimizer / re-pack lists) need one eager iteration
         self._static = (src_imgs.clone(), src_lbls.clone(), tgt_imgs.clone())
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -89,13 +184,34 @@ class MCDStep:
         with torch.cuda.graph(self.graph, stream=cap_stream):
             self._static_out = self(*self._static)
         self.launches_per_replay = abi.launch_count() - n0
+        self._captured_lr = self._hyper_snapshot()
         return self
+
+    def _hyper_snapshot(self):
+        return tuple((g["lr"], g.get("momentum", 0), g.get("weight_decay", 0))
+                     for o in (self.optimizer_g, self.optimizer_f) for g in o.param_groups)
+
+    def _before_replay(self):
+        """learning-rate schedules (util.adjust_learning_rate on optimizer_g / optimizer_f every epoch) must reach the
+        captured kernels: the fused optimizers read lr / momentum / weight decay from a device tensor that is refreshed
+        here; an optimizer torch.optim executes inside the graph has its hyper-parameters baked in at capture."""
+        for f in self._fused.values():
+            if f:
+                f.refresh_hyper()
+        if self._hyper_snapshot() != self._captured_lr:
+            baked = [name for name in ("g", "f") if not self._fused.get(name)]
+            if baked:
+                raise RuntimeError("MCDStep: hyper-parameters of optimizer_%s changed after capture() and that optimizer "
+                                   "is not the fused SGD (its values are baked into the CUDA graph): call capture() "
+                                   "again" % "/".join(baked))
+            self._captured_lr = self._hyper_snapshot()
 
     def replay(self, src_imgs, src_lbls, tgt_imgs):
         s, l, t = self._static
         s.copy_(src_imgs, non_blocking=True)
         l.copy_(src_lbls, non_blocking=True)
         t.copy_(tgt_imgs, non_blocking=True)
+        self._before_replay()
         self.graph.replay()
         return self._static_out
 
@@ -126,25 +242,12 @@ class MCDStep:
         for dst, src in zip(self._static, self._stage):
             dst.copy_(src, non_blocking=True)
         self._consumed.record(main)
+        self._before_replay()
         self.graph.replay()
         return self._static_out
 
-    # -- forward helpers -------------------------------------------------------------------------
-    def _gen(self, x):
-        if not self.mfnet:
-            return (self.gens[0](x),)
-        # adapt_mfnet_trainer.py:186-187: RGB stream and HHA stream
-        return self.gens[0](x[:, :3]), self.gens[1](x[:, 3:])
-
-    def _heads(self, feats):
-        return self.f1(*feats), self.f2(*feats)
-
-    def _disc(self, o1, o2):
-        d = self.criterion_d(o1, o2)
-        return d / self.world if self.world > 1 else d   # SUM all-reduce of gradients => global mean
-
+    # -- one iteration ------------------------------------------------------------------------------
     def __call__(self, src_imgs, src_lbls, tgt_imgs):
-        crit = self.criterion
         from . import ops
         if self._arena is None or self._arena.buf.device != src_imgs.device:
             self._arena = ops.ZeroArena(src_imgs.device)
@@ -154,28 +257,31 @@ class MCDStep:
             self._arena.begin()            # ONE memset for all BatchNorm-statistic / loss accumulators
             with DirectGrads(defer=self.defer_reduce) as self._dg, logits_dtype(self.logits_dtype):
                 self._dev = src_imgs.device
-                return self._iteration(crit, src_imgs, src_lbls, tgt_imgs)
+                return self._iteration(src_imgs, src_lbls, tgt_imgs)
         finally:
             ops.set_arena(prev_arena)
 
-    def _step_g(self):
-        """optimizer_g.step() and the refresh of all packed bf16 weight shadows of G: ONE fused kernel when the
-        optimizer is plain momentum SGD (ops.FusedSGD), else optimizer.step() + one multi-tensor re-pack."""
+    def _step(self, which):
+        """optimizer.step() and the refresh of the packed 16-bit weight shadows of the stepped modules: ONE fused
+        kernel when the optimizer is plain momentum SGD (ops.FusedSGD), else optimizer.step() + one multi-tensor
+        re-pack."""
         from .nn import Conv2d
-        if self._fused_g is None:
-            convs = [m for g in self.gens for m in g.modules() if isinstance(m, Conv2d) and m._packs]
-            if self.fused_sgd and ops_mod().FusedSGD.supports(self.optimizer_g):
-                self._fused_g = ops_mod().FusedSGD(self.optimizer_g, convs, defer_wgrad_reduce=self.defer_reduce)
+        opt, mods = (self.optimizer_g, self.gens) if which == "g" else (self.optimizer_f, self.clfs)
+        if which not in self._fused:
+            convs = [m for g in mods for m in g.modules() if isinstance(m, Conv2d) and m._packs]
+            if self.fused_sgd and ops_mod().FusedSGD.supports(opt):
+                self._fused[which] = ops_mod().FusedSGD(opt, convs,
+                                                        defer_wgrad_reduce=self.defer_reduce and which == "g")
             else:
-                self._fused_g = False
-        if self._fused_g:
-            self._fused_g.step()
+                self._fused[which] = False
+        if self._fused[which]:
+            self._fused[which].step()
             return
-        self.optimizer_g.step()
-        if self._packer_g is None:
-            convs = [m for g in self.gens for m in g.modules() if isinstance(m, Conv2d) and m._packs]
-            self._packer_g = ops_mod().MultiPacker(convs)
-        self._packer_g.repack()
+        opt.step()
+        if which not in self._packers:
+            convs = [m for g in mods for m in g.modules() if isinstance(m, Conv2d) and m._packs]
+            self._packers[which] = ops_mod().MultiPacker(convs)
+        self._packers[which].repack()
 
     def _backward(self, loss):
         """loss.backward() + join of the side stream that carries the convolution weight gradients."""
@@ -188,42 +294,48 @@ class MCDStep:
             e.record()
             self.phase_events.append((name, e))
 
-    def _iteration(self, crit, src_imgs, src_lbls, tgt_imgs):
-        # ---- A: source supervised; updates G, F1, F2
+    def _global(self, loss):
+        """the logged scalar: with world > 1 every criterion returned this rank's share, the sum is the global loss"""
+        v = loss.detach().clone()
+        if self.world > 1:
+            torch.distributed.all_reduce(v, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        return v
+
+    def _iteration(self, src_imgs, src_lbls, tgt_imgs):
+        task = self.task
+        from .nn import bn_update_repeat
+        # ---- A: source supervised; updates G (encoder) and F1, F2 (decoder)
         self._mark("start")
         self.sync_g.zero_and_arm(), self.sync_f.zero_and_arm()
-        o1, o2 = self._heads(self._gen(src_imgs))
-        loss = crit(o1, src_lbls) + crit(o2, src_lbls)
+        fs = task.features(src_imgs)
+        ft = task.features(tgt_imgs) if task.a_uses_target else None
+        loss = task.loss_a(fs, ft, src_imgs, src_lbls, tgt_imgs)
         self._backward(loss)
-        c_loss = loss.detach()
+        c_loss = self._global(loss)
         self.sync_g.wait(), self.sync_f.wait()
-        self._step_g(), self.optimizer_f.step()
+        self._step("g"), self._step("f")
         self._mark("A")
         # ---- B: classifiers maximise the discrepancy on target; only optimizer_f steps
         self.sync_f.zero_and_arm()
         if self.exact:
             self.sync_g.zero_and_arm(armed=False)
-            feats_s, feats_t = self._gen(src_imgs), self._gen(tgt_imgs)
-            feats_t_graph = None
+            fs, ft = task.features(src_imgs), task.features(tgt_imgs)
+            ft_graph = None
         else:
             with torch.no_grad():
-                feats_s = self._gen(src_imgs)
+                fs = task.features(src_imgs)
             if self.reuse_t:
-                from .nn import bn_update_repeat
                 with bn_update_repeat(2):
-                    feats_t_graph = self._gen(tgt_imgs)
-                feats_t = tuple(f.detach() for f in feats_t_graph)
+                    ft_graph = task.features(tgt_imgs)
+                ft = _detach(ft_graph)
             else:
-                feats_t_graph = None
+                ft_graph = None
                 with torch.no_grad():
-                    feats_t = self._gen(tgt_imgs)
-        o1, o2 = self._heads(feats_s)
-        loss = crit(o1, src_lbls) + crit(o2, src_lbls)
-        t1, t2 = self._heads(feats_t)
-        loss = loss - self._disc(t1, t2)
+                    ft = task.features(tgt_imgs)
+        loss = task.loss_b(fs, ft, src_imgs, src_lbls, tgt_imgs)
         self._backward(loss)
         self.sync_f.wait()
-        self.optimizer_f.step()
+        self._step("f")
         self._mark("B")
         # ---- C x num_k: generator minimises the discrepancy; only optimizer_g steps
         #      (classifier gradients of this phase are zeroed before use at adapt_trainer.py:163-164, so unless
@@ -232,18 +344,19 @@ class MCDStep:
         if not self.exact:
             for p in self.sync_f.params:
                 p.requires_grad_(False)
-        for k in range(self.num_k):
-            self.sync_g.zero_and_arm()
-            feats = feats_t_graph if (k == 0 and feats_t_graph is not None) else self._gen(tgt_imgs)
-            feats_t_graph = None
-            t1, t2 = self._heads(feats)
-            loss = self._disc(t1, t2) * self.mult
-            self._backward(loss)
-            self.sync_g.wait()
-            self._step_g()
-            self._mark("C%d" % k)
-        if not self.exact:
-            for p in self.sync_f.params:
-                p.requires_grad_(True)
-        d_loss = loss.detach() * (self.world / self.num_k)
+        try:
+            for k in range(self.num_k):
+                self.sync_g.zero_and_arm()
+                feats = ft_graph if (k == 0 and ft_graph is not None) else task.features(tgt_imgs)
+                ft_graph = None
+                loss = task.disc(feats) * self.mult
+                self._backward(loss)
+                self.sync_g.wait()
+                self._step("g")
+                self._mark("C%d" % k)
+        finally:
+            if not self.exact:
+                for p in self.sync_f.params:
+                    p.requires_grad_(True)
+        d_loss = self._global(loss) / self.num_k
         return c_loss, d_loss

@@ -13,6 +13,8 @@ module names (=> state_dict keys) and call signatures:
 
 Score maps (n_class / depth / boundary channels at 1/8, 1/4, 1/2 resolution) are fp32 NCHW tensors, the
 full-resolution predictions bf16 NCHW tensors; trunk activations are bf16 channels_last.
+  get_boundary_loss (:743-787)                morphological label-map boundary + bce2d
+
 Everything else in the reference file (DRNSeg, ver2 heads, FuseDRNSegBase, domain classifiers, the
 vendored fyu/drn CLI, shortcut / seg2bd options) is outside SURVEY.md section 8 and raises NotImplementedError.
 """
@@ -26,6 +28,13 @@ from mcd_b200 import ops
 from mcd_b200.nn import (BatchNorm2d, BilinearUpsample, Conv2d, DepthwiseDeconv16s8, SoleChain, conv_bn_act)
 from models import drn
 from models.fusion import AddFusion, get_fusion_model
+
+
+def util_predict(logits):
+    """pred.max(1)[1]: argmax over ALL channels (reference :994-995), int64 [N,H,W], one kernel."""
+    lg = logits if logits.dtype in (torch.bfloat16, torch.float32) else logits.float()
+    labels, _ = ops.argmax_entropy(lg.contiguous(), want_labels=True, want_entropy=False)
+    return labels
 
 
 def _he_init(conv):
@@ -162,8 +171,20 @@ def _scalar_param():
 
 
 def _weighted(s, value):
-    """learned log-variance task weighting exp(-s) * L + s (reference :1008-1014)."""
-    return torch.exp(-s) * value + s
+    """learned log-variance task weighting exp(-s) * L + s (reference :1008-1014).  Data parallel: `value` is this
+    rank's share of the global loss (loss.set_process_group), so the regulariser s is shared out as well."""
+    return torch.exp(-s) * value + s / _loss.dp_world()
+
+
+def get_boundary_loss(pred, gt, pred_type="semseg", gt_type="semseg"):
+    """reference models/dilated_fcn.py:743-787: the morphological boundary (3x3 max-pool of x and of -x differ) of an
+    integer label map - for the prediction and / or the ground truth - compared with bce2d.  The boundary maps are
+    hard 0/1 (no gradient flows into a "semseg"-type prediction, exactly as in the reference)."""
+    assert pred_type in ["semseg", "boundary"]
+    assert gt_type in ["semseg", "boundary"]
+    gt_boundary = ops.label_boundary(gt.detach()) if gt_type == "semseg" else gt.detach().clone()
+    pred_boundary = ops.label_boundary(pred.detach()) if pred_type == "semseg" else pred
+    return _loss.bce2d(pred_boundary.float(), gt_boundary.float().reshape(pred_boundary.shape))
 
 
 class MCDMultiTaskDecoder(nn.Module):
@@ -222,9 +243,9 @@ class MCDTripleMultiTaskDecoder(nn.Module):
                  semseg_shortcut=False, depth_shortcut=False, add_pred_seg_boundary_loss=False,
                  use_seg2bd_conv=False):
         super().__init__()
-        if semseg_shortcut or depth_shortcut or add_pred_seg_boundary_loss or use_seg2bd_conv:
-            raise NotImplementedError("shortcut / pred-seg-boundary / seg2bd options are default-off in the "
-                                      "reference trainer and outside the libmcd_sm100 hot-path scope")
+        if semseg_shortcut or depth_shortcut or use_seg2bd_conv:
+            raise NotImplementedError("shortcut / seg2bd options are default-off in the reference trainer and "
+                                      "outside the libmcd_sm100 hot-path scope (SURVEY.md section 8f4)")
         self.s_semsegcls = _scalar_param()
         self.s_deprgr = _scalar_param()
         self.s_boundary = _scalar_param()
@@ -279,6 +300,23 @@ class MCDTripleMultiTaskDecoder(nn.Module):
     def get_boundary_loss(self, x_dic, gt_boundary):
         # sigmoid-average + bce2d fused: the averaged probability map is never materialised
         return _loss.sigmoid3_bce2d(*self._boundary_maps(x_dic), gt_boundary)
+
+    def get_psuedo_boundary_loss(self, x_dic, separately_returning=False):
+        """--add_pred_seg_boundary_loss (reference :990-1000): boundary of each classifier's argmax label map against
+        the (detached) boundary head.  The reference passes a keyword `pred_semseg=` that get_boundary_loss does not
+        have (TypeError); this is the evident intent: pred_type "semseg", gt_type "boundary"."""
+        assert self.add_pred_seg_boundary_loss
+        psuedo_boundary = self.boundary_forward(x_dic).detach().float()
+        pred_semseg1, pred_semseg2 = self.semseg_forward(x_dic)
+        loss1 = get_boundary_loss(util_predict(pred_semseg1), psuedo_boundary[:, 0], gt_type="boundary")
+        loss2 = get_boundary_loss(util_predict(pred_semseg2), psuedo_boundary[:, 0], gt_type="boundary")
+        return (loss1, loss2) if separately_returning else loss1 + loss2
+
+    def get_weighted_semseg_loss(self, x, gt_semseg):
+        """the `semseg_loss` term of get_loss() alone (phase B of adapt_triple_multitask_trainer.py:256-276 uses
+        nothing else of get_loss's three results)."""
+        l1, l2 = self.get_semseg_loss(x, gt_semseg, separately_returning=True)
+        return (_weighted(self.s_semsegcls, l1) + _weighted(self.s_semsegcls, l2)) / 2
 
     def get_loss(self, x, gt_semseg, gt_dep, gt_boundary, separately_returning=False):
         l1, l2 = self.get_semseg_loss(x, gt_semseg, separately_returning=True)

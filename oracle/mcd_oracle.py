@@ -455,12 +455,34 @@ def _req(sds, flag=True):
             sd[k].requires_grad_(flag)
 
 
+def _dp_seg_base_forward(G, x, name, world):
+    """nn.DataParallel(model_g) (--is_data_parallel, models/model_util.py:283-284): the batch is scattered over
+    `world` replicas that share the parameters; every replica normalises with ITS OWN batch statistics and only
+    replica 0's running-statistics buffers survive; the outputs are gathered (criteria see the global batch)."""
+    if world == 1:
+        return seg_base_forward(G, x, name)
+    outs = []
+    for r, xs in enumerate(x.chunk(world)):
+        sd = G if r == 0 else {k: (v.clone() if (k.endswith("running_mean") or k.endswith("running_var") or
+                                                  k.endswith("num_batches_tracked")) else v) for k, v in G.items()}
+        outs.append(seg_base_forward(sd, xs, name))
+    return torch.cat(outs)
+
+
+def mcd_step_early_dp(G, F1, F2, src, lbl, tgt, weight, opt_g, opt_f, world, **kw):
+    """mcd_step_early with nn.DataParallel semantics over `world` replicas (global batch in, see above)."""
+    return mcd_step_early(G, F1, F2, src, lbl, tgt, weight, opt_g, opt_f, world=world, **kw)
+
+
 def mcd_step_early(G, F1, F2, src, lbl, tgt, weight, opt_g, opt_f, num_k=4, num_multiply_d_loss=1.0,
-                   name="drn_d_38", record=None):
+                   name="drn_d_38", record=None, world=1):
     """One iteration of adapt_trainer.py:162-212 (phase A, B, num_k x C).  G/F1/F2 are state dicts and are
     updated in place; returns (c_loss, d_loss) like the trainer's running numbers.  `record` (dict) receives
     intermediate tensors for parity tests."""
     _req([G, F1, F2])
+
+    def seg_base_forward(sd, x, nm):      # noqa: F811  (world > 1: nn.DataParallel semantics)
+        return _dp_seg_base_forward(sd, x, nm, world)
     # ---- A: source supervised, updates G, F1, F2 (adapt_trainer.py:163-185)
     feat = seg_base_forward(G, src, name)
     o1, o2 = head_forward(F1, feat), head_forward(F2, feat)
@@ -501,3 +523,126 @@ def mcd_step_early(G, F1, F2, src, lbl, tgt, weight, opt_g, opt_f, num_k=4, num_
     _req([G, F1, F2], False)
     d_loss = float(loss) / num_k
     return c_loss, d_loss
+
+
+# ------------------------------------------------------------------------------------------------
+# MFNet iteration (adapt_mfnet_trainer.py:181-235): two generators (RGB stream, HHA stream) stepped by ONE optimizer_g,
+# heads take both score maps.  Quirks kept: phase C is NOT multiplied by num_multiply_d_loss (:233); the
+# `optimizer_f.zero_grad()` after phase B (:222) has no effect on any result (the next use re-zeroes anyway).
+def mcd_step_mfnet(G3, G1, F1, F2, src, lbl, tgt, weight, opt_g, opt_f, kind="add", num_k=4, name="drn_d_38",
+                   record=None):
+    sds = [G3, G1, F1, F2]
+    _req(sds)
+
+    def fwd(x):
+        f = (seg_base_forward(G3, x[:, :3], name), seg_base_forward(G1, x[:, 3:], name))
+        return head_forward(F1, f, kind), head_forward(F2, f, kind)
+
+    o1, o2 = fwd(src)
+    loss = ce2d(o1, lbl, weight) + ce2d(o2, lbl, weight)
+    g3, g1, gf1, gf2 = _grads(loss, sds)
+    c_loss = float(loss)
+    if record is not None:
+        record.update(A_loss=c_loss)
+    opt_g.step(G3, g3), opt_g.step(G1, g1)
+    opt_f.step(F1, gf1), opt_f.step(F2, gf2)
+    o1, o2 = fwd(src)
+    loss = ce2d(o1, lbl, weight) + ce2d(o2, lbl, weight)
+    t1, t2 = fwd(tgt)
+    loss = loss - diff2d(t1, t2)
+    _, _, gf1, gf2 = _grads(loss, sds)
+    if record is not None:
+        record.update(B_loss=float(loss))
+    opt_f.step(F1, gf1), opt_f.step(F2, gf2)
+    for i in range(num_k):
+        t1, t2 = fwd(tgt)
+        loss = diff2d(t1, t2)
+        g3, g1, _, _ = _grads(loss, sds)
+        if record is not None:
+            record.setdefault("C_losses", []).append(float(loss))
+        opt_g.step(G3, g3), opt_g.step(G1, g1)
+    _req(sds, False)
+    return c_loss, float(loss) / num_k
+
+
+# ------------------------------------------------------------------------------------------------
+# seg + HHA decoder (models/dilated_fcn.py:661-739) and the two multitask iterations
+def init_multitask_decoder(n_class=41, depth_ch=3, gen=None):
+    gen = gen or torch.Generator().manual_seed(2)
+    sd = {"s_semsegcls": torch.ones(1), "s_deprgr": torch.ones(1)}
+    init_three_layer_decoder(sd, "semsegcls_dec1", n_class, gen)
+    init_three_layer_decoder(sd, "semsegcls_dec2", n_class, gen)
+    init_three_layer_decoder(sd, "deprgr_dec", depth_ch, gen)
+    return sd
+
+
+def _feat(E, x, triple, name):
+    hs = trunk_forward(E, x[:, :3], name, "main_layer" if triple else "base.")
+    return {"h%d" % i: h for i, h in enumerate(hs)} if triple else {"h8": hs[-1]}
+
+
+def _weighted_semseg(D, hd, lbl, weight):
+    s1, s2 = triple_semseg(D, hd)
+    return (_uw(D["s_semsegcls"], ce2d(s1, lbl, weight)) + _uw(D["s_semsegcls"], ce2d(s2, lbl, weight))) / 2
+
+
+def mcd_step_multitask(E, D, src, lbl, tgt, weight, opt_e, opt_d, triple=True, num_k=4, num_multiply_d_loss=1.0,
+                       name="drn_d_38", record=None):
+    """adapt_triple_multitask_trainer.py:202-287 (triple: src [N,7,H,W] = RGB + HHA + boundary) or
+    adapt_multitask_trainer.py:194-262 (src [N,6,H,W]); tgt [N,6,H,W].  Parameters without a gradient are skipped by
+    the optimizer (torch >= 2.0 zero_grad semantics, see mcd_b200/step.py)."""
+    sds = [E, D]
+    _req(sds)
+    gt_dep = src[:, 3:-1] if triple else src[:, 3:]
+    # ---- A
+    fs, ft = _feat(E, src, triple, name), _feat(E, tgt, triple, name)
+    semseg = _weighted_semseg(D, fs, lbl, weight)
+    dep = _uw(D["s_deprgr"], F.mse_loss(triple_depth(D, fs), gt_dep))
+    tdep = F.mse_loss(triple_depth(D, ft), tgt[:, 3:])
+    loss = semseg + dep + tdep
+    if triple:
+        loss = loss + _uw(D["s_boundary"], bce2d(triple_boundary(D, fs), src[:, -1:]))
+    ge, gd = _grads(loss, sds)
+    c_loss = float(loss)
+    if record is not None:
+        record.update(A_loss=c_loss, A_grad_d=gd)
+    opt_e.step(E, ge), opt_d.step(D, gd)
+    # ---- B (only optimizer_dec steps)
+    fs = _feat(E, src, triple, name)
+    loss = _weighted_semseg(D, fs, lbl, weight)
+    dep_b = _uw(D["s_deprgr"], F.mse_loss(triple_depth(D, fs), gt_dep))
+    if not triple:
+        loss = loss + dep_b
+    # triple (:256-276): get_loss() evaluates depth and boundary too and the objective drops them - but the depth
+    # decoder's train-mode BatchNorm layers have taken their running-statistics update by then
+    ft = _feat(E, tgt, triple, name)
+    if not triple:
+        loss = loss + F.mse_loss(triple_depth(D, ft), tgt[:, 3:])
+    loss = loss - diff2d(*triple_semseg(D, ft))
+    _, gd = _grads(loss, sds)
+    if record is not None:
+        record.update(B_loss=float(loss))
+    opt_d.step(D, gd)
+    # ---- C x num_k (only optimizer_enc steps)
+    for i in range(num_k):
+        ft = _feat(E, tgt, triple, name)
+        loss = diff2d(*triple_semseg(D, ft)) * num_multiply_d_loss
+        ge, _ = _grads(loss, sds)
+        if record is not None:
+            record.setdefault("C_losses", []).append(float(loss))
+        opt_e.step(E, ge)
+    _req(sds, False)
+    return c_loss, float(loss) / num_k
+
+
+def label_boundary(x):
+    """get_boundary of models/dilated_fcn.py:769-773"""
+    v = x.float()
+    return F.max_pool2d(v, kernel_size=3, stride=1, padding=1) != -F.max_pool2d(-v, kernel_size=3, stride=1, padding=1)
+
+
+def get_boundary_loss(pred, gt, pred_type="semseg", gt_type="semseg"):
+    """models/dilated_fcn.py:743-787"""
+    gt_b = label_boundary(gt) if gt_type == "semseg" else gt.detach().clone()
+    pred_b = label_boundary(pred) if pred_type == "semseg" else pred
+    return bce2d(pred_b.float(), gt_b.float())

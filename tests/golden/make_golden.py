@@ -251,6 +251,141 @@ def golden_losses():
     print("losses: ce %.6f diff %.6f bce %.6f" % (float(ce), float(df), float(bc)))
 
 
+def golden_iterations():
+    """Full A / B / num_k x C iterations of the MFNet and the two multitask trainers replayed verbatim (python-3
+    spellings) with torch.optim.SGD: adapt_mfnet_trainer.py:181-235, adapt_triple_multitask_trainer.py:202-287,
+    adapt_multitask_trainer.py:194-262; plus get_boundary_loss (models/dilated_fcn.py:743-787)."""
+    from loss import CrossEntropyLoss2d, Diff2d, get_prob_distance_criterion
+    from models.dilated_fcn import get_boundary_loss
+    from models.model_util import get_models, get_multitask_models, get_optimizer, get_triple_multitask_models
+    from util import get_class_weight_from_file
+    out, size, num_k = {}, (48, 64), 2
+    weight = get_class_weight_from_file(n_class=N_CLASS)
+    kw = dict(lr=1e-3, momentum=0.9, opt="sgd", weight_decay=2e-5)
+
+    # ---- MFNet ScoreAddFusion
+    g3, g1, f1, f2 = get_models(net_name="drn_d_38", res="50", input_ch=6, n_class=N_CLASS,
+                                method="MCD-MFNet-ScoreAddFusion")
+    filled(g3, 41), filled(g1, 42), filled(f1, 43), filled(f2, 44)
+    optimizer_g = get_optimizer(list(g3.parameters()) + list(g1.parameters()), **kw)
+    optimizer_f = get_optimizer(list(f1.parameters()) + list(f2.parameters()), **kw)
+    criterion, criterion_d = CrossEntropyLoss2d(weight), get_prob_distance_criterion("diff")
+    for m in (g3, g1, f1, f2):
+        m.train()
+    src_imgs, tgt_imgs, src_lbls = inputs(505, size=size)
+    optimizer_g.zero_grad(), optimizer_f.zero_grad()
+    a, b = g3(src_imgs[:, :3, :, :]), g1(src_imgs[:, 3:, :, :])
+    loss = criterion(f1(a, b), src_lbls) + criterion(f2(a, b), src_lbls)
+    loss.backward()
+    out["mf_A"] = float(loss)
+    optimizer_g.step(), optimizer_f.step()
+    optimizer_g.zero_grad(), optimizer_f.zero_grad()
+    a, b = g3(src_imgs[:, :3, :, :]), g1(src_imgs[:, 3:, :, :])
+    loss = criterion(f1(a, b), src_lbls) + criterion(f2(a, b), src_lbls)
+    a, b = g3(tgt_imgs[:, :3, :, :]), g1(tgt_imgs[:, 3:, :, :])
+    loss = loss - criterion_d(f1(a, b), f2(a, b))
+    loss.backward()
+    out["mf_B"] = float(loss)
+    optimizer_f.step()
+    optimizer_f.zero_grad()
+    cl = []
+    for i in range(num_k):
+        optimizer_g.zero_grad()
+        a, b = g3(tgt_imgs[:, :3, :, :]), g1(tgt_imgs[:, 3:, :, :])
+        loss = criterion_d(f1(a, b), f2(a, b))
+        loss.backward()
+        optimizer_g.step()
+        cl.append(float(loss))
+    out["mf_C"] = np.array(cl)
+    sk, sv = summarize(g1.state_dict())
+    out["mf_g1_keys"], out["mf_g1_sums"] = np.array(sk), sv
+    out["mf_up1"] = f1.up1.weight.detach().numpy().copy()
+    print("mfnet iteration: A %.6f B %.6f C %s" % (out["mf_A"], out["mf_B"], cl))
+
+    # ---- multitask trainers
+    for tag, triple in (("tri", True), ("mt", False)):
+        crit = CrossEntropyLoss2d(weight)
+        if triple:
+            enc, dec = get_triple_multitask_models(net_name="drn_d_38", input_ch=6, n_class=N_CLASS,
+                                                   semseg_criterion=crit, discrepancy_criterion=Diff2d())
+        else:
+            enc, dec = get_multitask_models(net_name="drn_d_38", input_ch=6, n_class=N_CLASS,
+                                            semseg_criterion=crit, discrepancy_criterion=Diff2d())
+        filled(enc, 51), filled(dec, 52)
+        enc.train(), dec.train()
+        optimizer_enc = get_optimizer(enc.parameters(), **kw)
+        optimizer_dec = get_optimizer(dec.parameters(), **kw)
+        g = torch.Generator().manual_seed(606)
+        src_imgs = torch.randn(2, 7 if triple else 6, *size, generator=g)
+        if triple:
+            src_imgs[:, 6] = (torch.rand(2, *size, generator=g) < 0.1).float()
+        tgt_imgs = torch.randn(2, 6, *size, generator=g)
+        src_gt_semseg = torch.randint(0, N_CLASS, (2, *size), generator=g)
+        src_rgbs = src_imgs[:, :3, :, :]
+        src_depths = src_imgs[:, 3:-1, :, :] if triple else src_imgs[:, 3:, :, :]
+        src_boundary = src_imgs[:, -1:, :, :]
+        tgt_rgbs, tgt_depths = tgt_imgs[:, :3, :, :], tgt_imgs[:, 3:, :, :]
+        # A
+        optimizer_enc.zero_grad(), optimizer_dec.zero_grad()
+        src_fet, tgt_fet = enc(src_rgbs), enc(tgt_rgbs)
+        if triple:
+            terms = dec.get_loss(src_fet, src_gt_semseg, src_depths, src_boundary, separately_returning=True)
+        else:
+            terms = dec.get_loss(src_fet, src_gt_semseg, src_depths, separately_returning=True)
+        tgt_depth_loss = dec.get_depth_loss(tgt_fet, tgt_depths)
+        loss = sum(terms) + tgt_depth_loss
+        loss.backward()
+        out[tag + "_A"] = float(loss)
+        out[tag + "_A_terms"] = np.array([float(t) for t in terms] + [float(tgt_depth_loss)])
+        optimizer_enc.step(), optimizer_dec.step()
+        # B
+        optimizer_enc.zero_grad(), optimizer_dec.zero_grad()
+        src_fet = enc(src_rgbs)
+        if triple:
+            src_semseg_loss, _, _ = dec.get_loss(src_fet, src_gt_semseg, src_depths, src_boundary, separately_returning=True)
+            tgt_fet = enc(tgt_rgbs)
+            loss = src_semseg_loss - dec.get_cls_descrepancy(tgt_fet)
+        else:
+            src_semseg_loss, src_depth_loss = dec.get_loss(src_fet, src_gt_semseg, src_depths, separately_returning=True)
+            tgt_fet = enc(tgt_rgbs)
+            tgt_depth_loss = dec.get_depth_loss(tgt_fet, tgt_depths)
+            loss = src_semseg_loss + src_depth_loss + tgt_depth_loss - dec.get_cls_descrepancy(tgt_fet)
+        loss.backward()
+        out[tag + "_B"] = float(loss)
+        optimizer_dec.step()
+        # C
+        cl = []
+        for i in range(num_k):
+            optimizer_enc.zero_grad()
+            tgt_fet = enc(tgt_rgbs)
+            loss = dec.get_cls_descrepancy(tgt_fet) * 1.0
+            loss.backward()
+            optimizer_enc.step()
+            cl.append(float(loss))
+        out[tag + "_C"] = np.array(cl)
+        sk, sv = summarize(enc.state_dict())
+        out[tag + "_enc_keys"], out[tag + "_enc_sums"] = np.array(sk), sv
+        sk, sv = summarize({k: v for k, v in dec.state_dict().items() if "criterion" not in k})
+        out[tag + "_dec_keys"], out[tag + "_dec_sums"] = np.array(sk), sv
+        print("%s iteration: A %.6f B %.6f C %s" % (tag, out[tag + "_A"], out[tag + "_B"], cl))
+
+    # ---- get_boundary_loss
+    g = torch.Generator().manual_seed(707)
+    lab_p = torch.randint(0, 5, (2, 20, 24), generator=g)
+    lab_g = torch.randint(0, 5, (2, 20, 24), generator=g)
+    lab_p[:, 5:15, 6:18] = 2          # uniform regions: boundary only at their rims
+    lab_g[:, 2:12, 3:20] = 1
+    lab_g[:, 14:, :] = 3
+    bmap = (torch.rand(2, 20, 24, generator=g) < 0.3).float()
+    out["bd_lab_p"], out["bd_lab_g"], out["bd_map"] = lab_p.numpy(), lab_g.numpy(), bmap.numpy()
+    out["bd_ss"] = float(get_boundary_loss(lab_p, lab_g))
+    out["bd_sb"] = float(get_boundary_loss(lab_p, bmap, gt_type="boundary"))
+    v = lab_p.float()
+    out["bd_boundary_of_p"] = (torch.nn.functional.max_pool2d(v, 3, 1, 1) != -torch.nn.functional.max_pool2d(-v, 3, 1, 1)).numpy()
+    print("boundary losses:", out["bd_ss"], out["bd_sb"])
+    np.savez_compressed(os.path.join(HERE, "iterations.npz"), **out)
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
     torch.set_num_threads(8)
@@ -259,3 +394,4 @@ if __name__ == "__main__":
     golden_early_fusion()
     golden_mfnet()
     golden_triple()
+    golden_iterations()

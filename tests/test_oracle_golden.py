@@ -144,3 +144,61 @@ def test_triple_multitask_matches_reference():
     close(float(O.calc_entropy(s1)), z["test_entropy"], rtol=1e-3)
     close(depth[:, :, ::8, ::8].numpy(), z["test_depth_sub"])
     close(boundary[:, :, ::8, ::8].numpy(), z["test_boundary_sub"])
+
+
+# ---- full iterations of the other three trainers + get_boundary_loss (tests/golden/iterations.npz) ---------------
+def _check_sums(keys, sums, sd):
+    for k, (s_ref, n_ref) in zip(keys, sums):
+        t = sd[str(k)].double()
+        assert abs(float(t.norm()) - n_ref) <= 1e-6 + 2e-5 * abs(n_ref), (k, float(t.norm()), n_ref)
+        assert abs(float(t.sum()) - s_ref) <= 1e-4 + 2e-4 * abs(n_ref), (k, float(t.sum()), s_ref)
+
+
+@pytest.mark.timeout(900)
+def test_mfnet_iteration_matches_reference():
+    """adapt_mfnet_trainer.py:181-235 (ScoreAddFusion), A + B + 2 x C with torch.optim.SGD."""
+    z = np.load(os.path.join(GOLD, "iterations.npz"))
+    G3 = O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 41)
+    G1 = O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 42)
+    F1 = O.fill_state_dict_(O.init_head(N_CLASS, "scoreadd"), 43)
+    F2 = O.fill_state_dict_(O.init_head(N_CLASS, "scoreadd"), 44)
+    src, tgt, lbl = _inputs(505, size=(48, 64))
+    rec = {}
+    og, of = O.SGD(), O.SGD()
+    c, d = O.mcd_step_mfnet(G3, G1, F1, F2, src, lbl, tgt, O.class_weight(N_CLASS), og, of, kind="scoreadd", num_k=2,
+                            record=rec)
+    close(rec["A_loss"], z["mf_A"]), close(rec["B_loss"], z["mf_B"]), close(rec["C_losses"], z["mf_C"])
+    _check_sums(z["mf_g1_keys"], z["mf_g1_sums"], G1)
+    close(F1["up1.weight"].numpy(), z["mf_up1"])
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("tag,triple", [("tri", True), ("mt", False)])
+def test_multitask_iteration_matches_reference(tag, triple):
+    """adapt_triple_multitask_trainer.py:202-287 / adapt_multitask_trainer.py:194-262, A + B + 2 x C."""
+    z = np.load(os.path.join(GOLD, "iterations.npz"))
+    E = O.fill_state_dict_(O.init_trunk("drn_d_38", 3, "main_layer" if triple else "base."), 51)
+    D = O.fill_state_dict_(O.init_triple_decoder(N_CLASS, 3) if triple else O.init_multitask_decoder(N_CLASS, 3), 52)
+    g = torch.Generator().manual_seed(606)
+    size = (48, 64)
+    src = torch.randn(2, 7 if triple else 6, *size, generator=g)
+    if triple:
+        src[:, 6] = (torch.rand(2, *size, generator=g) < 0.1).float()
+    tgt = torch.randn(2, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (2, *size), generator=g)
+    rec = {}
+    c, d = O.mcd_step_multitask(E, D, src, lbl, tgt, O.class_weight(N_CLASS), O.SGD(), O.SGD(), triple=triple, num_k=2,
+                                record=rec)
+    close(rec["A_loss"], z[tag + "_A"]), close(rec["B_loss"], z[tag + "_B"]), close(rec["C_losses"], z[tag + "_C"])
+    _check_sums(z[tag + "_enc_keys"], z[tag + "_enc_sums"], E)
+    _check_sums(z[tag + "_dec_keys"], z[tag + "_dec_sums"], D)
+    if triple:        # never used, never updated (reference :813)
+        assert rec["A_grad_d"]["nmlrgr_dec.conv3.weight"] is None
+
+
+def test_boundary_loss_matches_reference():
+    z = np.load(os.path.join(GOLD, "iterations.npz"))
+    lab_p, lab_g, bmap = torch.tensor(z["bd_lab_p"]), torch.tensor(z["bd_lab_g"]), torch.tensor(z["bd_map"])
+    assert np.array_equal(O.label_boundary(lab_p).numpy(), z["bd_boundary_of_p"])     # integer part: bit-exact
+    close(float(O.get_boundary_loss(lab_p, lab_g)), z["bd_ss"])
+    close(float(O.get_boundary_loss(lab_p, bmap, gt_type="boundary")), z["bd_sb"])

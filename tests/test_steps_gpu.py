@@ -1,0 +1,354 @@
+"""The other trainers / testers of the reference through the drop-in modules and mcd_b200.step.MCDStep, against the
+oracle's restatement of the same loops (pinned to the real reference by tests/golden/iterations.npz):
+
+  adapt_mfnet_trainer.py:181-235             MFNet Add / ScoreAdd iteration (quirks :222, :233)
+  adapt_triple_multitask_trainer.py:202-287  seg + HHA + boundary iteration
+  adapt_multitask_trainer.py:194-262         seg + HHA iteration
+  adapt_tester.py:104-124, adapt_triple_multitask_tester.py:117-179   tester loop bodies incl. `.data.cpu().numpy()`
+  loss.py:130-138 bce2d, models/dilated_fcn.py:743-787 get_boundary_loss
+  util.adjust_learning_rate after MCDStep.capture()
+  2 ranks x B/2 == nn.DataParallel semantics of the global batch (needs 2 GPUs: `gpurun --gpus 2`)
+
+Tolerances: losses 1e-3 relative (north_star), updated weights 2e-3 max-norm, BatchNorm buffers 2e-2, integer maps
+bit-exact."""
+import os
+import socket
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mcd_oracle as O
+
+pytestmark = pytest.mark.gpu
+N_CLASS = 41
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def nerr(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+def rel(a, b):
+    return abs(float(a) - float(b)) / abs(float(b))
+
+
+def _load(module, sd, strict=True):
+    module.load_state_dict({k: v.detach().clone() for k, v in sd.items()}, strict=strict)
+
+
+def _inputs(seed, n, size, dev, src_ch=6):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(n, src_ch, *size, generator=g)
+    if src_ch == 7:
+        src[:, 6] = (torch.rand(n, *size, generator=g) < 0.1).float()
+    tgt = torch.randn(n, 6, *size, generator=g)
+    lbl = torch.randint(0, N_CLASS, (n, *size), generator=g)
+    return src.to(dev), tgt.to(dev), lbl.to(dev)
+
+
+def _log(name, lines):
+    if os.path.isdir(OUT):
+        with open(os.path.join(OUT, name), "a") as f:
+            f.write("\n".join(lines) + "\n")
+
+
+# ---- config 3: MFNet iteration through MCDStep -----------------------------------------------------------------
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("method,kind", [("MCD-MFNet-AddFusion", "add"), ("MCD-MFNet-ScoreAddFusion", "scoreadd")])
+def test_mfnet_mcdstep_vs_oracle(cuda_dev, method, kind, graph):
+    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+    from mcd_b200.step import MCDStep
+    from models.model_util import get_models
+    dev, size, n = cuda_dev, (240, 320), 2
+    G3 = O.to_device(O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 21), dev)
+    G1 = O.to_device(O.fill_state_dict_(O.init_seg_base("drn_d_38", 3, N_CLASS), 22), dev)
+    F1 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS, kind), 23), dev)
+    F2 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS, kind), 24), dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS, method=method)]
+    for m, sd in zip(models, (G3, G1, F1, F2)):
+        _load(m, sd)
+    src, tgt, lbl = _inputs(31, n, size, dev)
+    w = O.class_weight(N_CLASS).to(dev)
+    # num_multiply_d_loss = 3 must be IGNORED by the MFNet loop (adapt_mfnet_trainer.py:233)
+    step = MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=2, num_multiply_d_loss=3.0)
+    assert step.mfnet and step.mult == 1.0
+    iters = 2 if graph else 1
+    rec = {}
+    og, of = O.SGD(), O.SGD()
+    for _ in range(iters):
+        c_o, d_o = O.mcd_step_mfnet(G3, G1, F1, F2, src, lbl, tgt, w, og, of, kind=kind, num_k=2, record=rec)
+    if graph:
+        step(src, lbl, tgt)
+        step.capture(src, lbl, tgt, warmup=0)
+        c, d = step.replay(src, lbl, tgt)
+    else:
+        c, d = step(src, lbl, tgt)
+    torch.cuda.synchronize()
+    _log("parity_steps.txt", ["mfnet %s graph=%s: c %.6f vs %.6f  d %.6e vs %.6e" % (kind, graph, float(c), c_o, float(d), d_o)])
+    assert rel(c, c_o) <= 1e-3 and rel(d, d_o) <= 1e-3
+    for m, sd in zip(models, (G3, G1, F1, F2)):
+        werr = max(nerr(p, sd[k]) for k, p in m.named_parameters())
+        assert werr <= 2e-3, werr
+    bn = models[1].base[5][2].bn2
+    assert int(bn.num_batches_tracked) == 5 * iters == int(G1["base.5.2.bn2.num_batches_tracked"])   # A, B-src, B-tgt==C0, C1
+    assert nerr(bn.running_var, G1["base.5.2.bn2.running_var"]) <= 2e-2
+
+
+# ---- config 4 (+ adapt_multitask_trainer.py): multitask iterations through MCDStep ------------------------------
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("triple", [True, False])
+def test_multitask_mcdstep_vs_oracle(cuda_dev, triple, graph):
+    from loss import CrossEntropyLoss2d, Diff2d
+    from mcd_b200.step import MCDStep
+    from models.model_util import get_multitask_models, get_triple_multitask_models
+    dev, size, n = cuda_dev, (240, 320), 2
+    E = O.to_device(O.fill_state_dict_(O.init_trunk("drn_d_38", 3, "main_layer" if triple else "base."), 51), dev)
+    D = O.to_device(O.fill_state_dict_(O.init_triple_decoder(N_CLASS, 3) if triple
+                                       else O.init_multitask_decoder(N_CLASS, 3), 52), dev)
+    w = O.class_weight(N_CLASS).to(dev)
+    factory = get_triple_multitask_models if triple else get_multitask_models
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        enc, dec = factory("drn_d_38", 6, N_CLASS, semseg_criterion=CrossEntropyLoss2d(w),
+                           discrepancy_criterion=Diff2d())
+    enc, dec = enc.to(dev).train(), dec.to(dev).train()
+    _load(enc, E)
+    _load(dec, D, strict=False)                   # the criterion's class-weight buffer stays as configured
+    src, tgt, lbl = _inputs(61, n, size, dev, src_ch=7 if triple else 6)
+    step = MCDStep.multitask(enc, dec, triple=triple, num_k=2)
+    iters = 2 if graph else 1
+    rec = {}
+    oe, od = O.SGD(), O.SGD()
+    for _ in range(iters):
+        c_o, d_o = O.mcd_step_multitask(E, D, src, lbl, tgt, w, oe, od, triple=triple, num_k=2, record=rec)
+    if graph:
+        step(src, lbl, tgt)
+        step.capture(src, lbl, tgt, warmup=0)
+        c, d = step.replay(src, lbl, tgt)
+    else:
+        c, d = step(src, lbl, tgt)
+    torch.cuda.synchronize()
+    _log("parity_steps.txt", ["multitask triple=%s graph=%s: c %.6f vs %.6f  d %.6e vs %.6e" % (triple, graph, float(c), c_o, float(d), d_o)])
+    assert rel(c, c_o) <= 1e-3 and rel(d, d_o) <= 1e-3
+    assert max(nerr(p, E[k]) for k, p in enc.named_parameters()) <= 2e-3
+    dpar = dict(dec.named_parameters())
+    werr = {k: nerr(p, D[k]) for k, p in dpar.items()}
+    assert max(werr.values()) <= 2e-3, sorted(werr.items(), key=lambda kv: -kv[1])[:3]
+    if triple:       # constructed, never used, never updated (reference :813)
+        assert torch.equal(dpar["nmlrgr_dec.conv3.weight"], D["nmlrgr_dec.conv3.weight"])
+    # BatchNorm buffers, incl. the depth decoder whose phase-B forward is "dead" in the triple trainer but still counts
+    for key, mod in (("deprgr_dec.cbr1.bn", dec.deprgr_dec.cbr1.bn), ("semsegcls_dec1.cbr2.bn", dec.semsegcls_dec1.cbr2.bn)):
+        assert int(mod.num_batches_tracked) == int(D[key + ".num_batches_tracked"]), key
+        assert nerr(mod.running_mean, D[key + ".running_mean"]) <= 2e-2, key
+        assert nerr(mod.running_var, D[key + ".running_var"]) <= 2e-2, key
+
+
+# ---- bce2d, get_boundary_loss ----------------------------------------------------------------------------------
+def test_bce2d_and_boundary_loss(cuda_dev):
+    import loss as L
+    from mcd_b200 import ops
+    from models.dilated_fcn import get_boundary_loss
+    z = np.load(os.path.join(ROOT, "tests", "golden", "losses.npz"))
+    p = torch.tensor(z["p"], device=cuda_dev, requires_grad=True)
+    tb = torch.tensor(z["tb"], device=cuda_dev)
+    bc = L.bce2d(p, tb)
+    (bc * 1.0).backward()
+    assert rel(bc, z["bce"]) <= 1e-5                      # golden value produced by the reference's own bce2d
+    assert nerr(p.grad, torch.tensor(z["dp"], device=cuda_dev)) <= 1e-5
+    # saturated probabilities: torch's log clamp at -100
+    ps = torch.tensor([[0.0, 1.0, 0.5, 1.0]], device=cuda_dev).view(1, 1, 2, 2)
+    ts = torch.tensor([[1.0, 0.0, 1.0, 1.0]], device=cuda_dev).view(1, 1, 2, 2)
+    assert rel(L.bce2d(ps, ts), O.bce2d(ps, ts)) <= 1e-6
+    g = np.load(os.path.join(ROOT, "tests", "golden", "iterations.npz"))
+    lab_p = torch.tensor(g["bd_lab_p"], device=cuda_dev)
+    lab_g = torch.tensor(g["bd_lab_g"], device=cuda_dev)
+    bmap = torch.tensor(g["bd_map"], device=cuda_dev)
+    assert np.array_equal(ops.label_boundary(lab_p).cpu().numpy() != 0, g["bd_boundary_of_p"])     # integer part: bit-exact
+    assert np.array_equal(ops.label_boundary(lab_p.float()).cpu().numpy() != 0, g["bd_boundary_of_p"])
+    assert rel(get_boundary_loss(lab_p, lab_g), g["bd_ss"]) <= 1e-5
+    assert rel(get_boundary_loss(lab_p, bmap, gt_type="boundary"), g["bd_sb"]) <= 1e-5
+    # full-size map against the oracle
+    big = torch.randint(0, 41, (2, 480, 640), device=cuda_dev)
+    big[:, 100:300, 200:500] = 7
+    assert torch.equal(ops.label_boundary(big) != 0, O.label_boundary(big))
+
+
+# ---- tester loop bodies, verbatim modulo python-3 spellings ------------------------------------------------------
+def test_tester_loops_verbatim(cuda_dev):
+    import util
+    from loss import CrossEntropyLoss2d, Diff2d
+    from models.model_util import get_models, get_triple_multitask_models
+    from util import calc_entropy
+    dev, n_class = cuda_dev, N_CLASS
+    g = torch.Generator().manual_seed(77)
+    imgs = torch.randn(1, 7, 240, 320, generator=g).to(dev)
+    # --- adapt_tester.py:99-124 with --use_f2 and --saves_prob
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        G, F1, F2 = [m.to(dev) for m in get_models("drn_d_38", 6, n_class)]
+    Gs = O.to_device(O.fill_state_dict_(O.init_seg_base("drn_d_38", 6, n_class), 7), dev)
+    F1s = O.to_device(O.fill_state_dict_(O.init_head(n_class), 8), dev)
+    F2s = O.to_device(O.fill_state_dict_(O.init_head(n_class), 9), dev)
+    _load(G, Gs), _load(F1, F1s), _load(F2, F2s)
+    G.eval(), F1.eval(), F2.eval()
+    feature = G(imgs[:, :6])
+    outputs = F1(feature)
+    outputs += F2(feature)
+    outputs /= 2
+    total_ent = float(calc_entropy(outputs).data.cpu().numpy())
+    prob = outputs[0].data.cpu().numpy()                        # np.save(prob_outfn, ...)
+    pred = outputs[0, :n_class - 1].data.max(0)[1].cpu()
+    img = np.uint8(pred.numpy())                                # Image.fromarray(...)
+    with torch.no_grad():
+        fo = O.seg_base_forward(Gs, imgs[:, :6], train=False)
+        ref = (O.head_forward(F1s, fo) + O.head_forward(F2s, fo)) / 2
+    assert prob.dtype == np.float32 and prob.shape == (n_class, 240, 320) and img.shape == (240, 320)
+    assert rel(total_ent, O.calc_entropy(ref)) <= 1e-3
+    assert torch.equal(pred.to(dev), util.predict_labels(outputs, n_class - 1)[0])     # library argmax == torch's
+    # --- adapt_triple_multitask_tester.py:117-179
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model_enc, model_dec = get_triple_multitask_models("drn_d_38", 6, n_class, semseg_criterion=CrossEntropyLoss2d(),
+                                                           discrepancy_criterion=Diff2d())
+    model_enc, model_dec = model_enc.to(dev).eval(), model_dec.to(dev).eval()
+    rgbs = imgs[:, :3, :, :]
+    feature = model_enc(rgbs)
+    pred_semseg1, pred_semseg2, pred_depth, pred_boundary = model_dec(feature)
+    total_ent += float(calc_entropy(pred_semseg1).data.cpu().numpy())
+    prob = pred_semseg1[0].data.cpu().numpy()
+    pred = pred_semseg1[0, :n_class - 1].data.max(0)[1].cpu()
+    depth_im = pred_depth.data.cpu().numpy()[0].transpose([1, 2, 0])
+    boundary_im = np.uint8(pred_boundary.data.cpu().numpy()[0].transpose([1, 2, 0])[:, :, 0] * 255)
+    assert sorted(feature) == ["h%d" % i for i in range(9)]
+    assert prob.shape == (n_class, 240, 320) and depth_im.shape == (240, 320, 3) and boundary_im.shape == (240, 320)
+    assert np.isfinite(depth_im).all() and pred.dtype == torch.int64 and np.isfinite(total_ent)
+
+
+# ---- learning-rate schedules must reach a captured graph -----------------------------------------------
+def test_lr_change_after_capture(cuda_dev):
+    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+    from mcd_b200.step import MCDStep
+    from models.model_util import get_models
+    from util import adjust_learning_rate
+    dev, size, n = cuda_dev, (64, 96), 2
+    src, tgt, lbl = _inputs(5, n, size, dev)
+    w = O.class_weight(N_CLASS).to(dev)
+
+    def make():
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS)]
+        return models, MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=1)
+
+    (ma, sa), (mb, sb) = make(), make()
+    for m1, m2 in zip(ma, mb):
+        m2.load_state_dict(m1.state_dict())
+    sa(src, lbl, tgt), sb(src, lbl, tgt)                      # iteration 1, lr 1e-3 (eager)
+    sb.capture(src, lbl, tgt, warmup=0)
+    for step in (sa, sb):                                     # epoch boundary: lr * decay (adapt_trainer.py:228-230)
+        adjust_learning_rate(step.optimizer_g, 1e-3, 0.1, epoch=8, num_epochs=10)
+        adjust_learning_rate(step.optimizer_f, 1e-3, 0.1, epoch=8, num_epochs=10)
+    assert sa.optimizer_g.param_groups[0]["lr"] == pytest.approx(1e-5)
+    sa(src, lbl, tgt)                                         # iteration 2 eager with the new lr ...
+    sb.replay(src, lbl, tgt)                                  # ... and as a graph replay captured with the OLD lr
+    torch.cuda.synchronize()
+    for m1, m2 in zip(ma, mb):
+        for (k, p), q in zip(m1.named_parameters(), m2.parameters()):
+            assert nerr(q, p) <= 1e-5, k
+    # the update really used the small lr: one more step at lr 1e-3 would move seg.bias ~100x further
+    moved = float((ma[0].seg.bias - mb[0].seg.bias).abs().max())
+    assert moved <= 1e-7
+
+
+# ---- 2 GPUs: 2 ranks x B/2 reproduce nn.DataParallel's global-batch iteration -------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, graph, q):
+    try:
+        pkg = os.path.join(ROOT, "multichannel-semseg-with-uda_b200")
+        for p in (pkg, ROOT):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                          LOCAL_RANK=str(rank))
+        from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+        from mcd_b200 import parallel
+        from mcd_b200.step import MCDStep
+        from models.model_util import get_models
+        parallel.init_from_env()
+        dev = torch.device("cuda", rank)
+        G = O.to_device(O.fill_state_dict_(O.init_seg_base("drn_d_38", 6, N_CLASS), 1), dev)
+        F1 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS), 2), dev)
+        F2 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS), 3), dev)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS)]
+        for m, sd in zip(models, (G, F1, F2)):
+            _load(m, sd)
+        src, tgt, lbl = _inputs(9, 2 * world, (240, 320), dev)              # the GLOBAL batch, known to every rank
+        # make the per-shard sum of class weights differ (class 40 has weight 0): the normaliser must be global
+        lbl[:2] = torch.where(torch.rand(lbl[:2].shape, device=dev) < 0.5, torch.full_like(lbl[:2], 40), lbl[:2])
+        sl = slice(2 * rank, 2 * rank + 2)
+        w = O.class_weight(N_CLASS).to(dev)
+        step = MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=2)
+        assert step.world == world
+        iters = 2 if graph else 1
+        if graph:
+            step(src[sl], lbl[sl], tgt[sl])
+            step.capture(src[sl], lbl[sl], tgt[sl], warmup=0)
+            c, d = step.replay(src[sl], lbl[sl], tgt[sl])
+        else:
+            c, d = step(src[sl], lbl[sl], tgt[sl])
+        torch.cuda.synchronize()
+        res = None
+        if rank == 0:
+            # oracle with nn.DataParallel semantics: per-replica BatchNorm statistics (replica 0's buffers survive),
+            # criteria on the gathered outputs, one optimizer
+            og, of = O.SGD(), O.SGD()
+            for _ in range(iters):
+                c_o, d_o = O.mcd_step_early_dp(G, F1, F2, src, lbl, tgt, w, og, of, world, num_k=2)
+            werr = max(nerr(p, G[k]) for k, p in models[0].named_parameters())
+            res = dict(c=float(c), c_o=c_o, d=float(d), d_o=d_o, werr=werr,
+                       up=nerr(models[1].up.weight, F1["up.weight"]),
+                       rv=nerr(models[0].base[5][2].bn2.running_var, G["base.5.2.bn2.running_var"]))
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+        q.put((rank, "ok", res))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc()), None))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_gpu_matches_dataparallel_semantics(graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, graph, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(120)
+    assert all(r[1] == "ok" for r in res), res
+    r0 = [r[2] for r in res if r[0] == 0][0]
+    _log("parity_two_gpu.txt", ["graph=%s %s" % (graph, r0)])
+    assert rel(r0["c"], r0["c_o"]) <= 1e-3 and rel(r0["d"], r0["d_o"]) <= 1e-3, r0
+    assert r0["werr"] <= 2e-3 and r0["up"] <= 2e-3 and r0["rv"] <= 2e-2, r0
