@@ -139,8 +139,10 @@ class MCDStep:
         self.fused_sgd = fused_sgd     # optimizer.step() + weight re-pack as one kernel (plain momentum SGD only)
         # single process + fused SGD: the split-K partial sums of the tcgen05 wgrad kernels are reduced by the
         # optimizer kernel itself (ops.FusedSGD.deferred); with world > 1 the all-reduce needs real gradients
+        # (and a weight gradient may be left in split form only once per step: the multitask trainers run the encoder
+        # twice in phase A, source and target, so their gradients accumulate in param.grad instead)
         self.defer_reduce = (fused_sgd and defer_wgrad_reduce and self.sync_g.world == 1
-                             and not exact_reference_backward)
+                             and not exact_reference_backward and not self.task.a_uses_target)
         self.world = self.sync_g.world
         self.group = process_group
         if self.world > 1:
