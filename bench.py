@@ -1,16 +1,24 @@
 #!/usr/bin/env python
 """bench.py - MCD-step throughput of the B200-native path (and of the reference's CPU path).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm; N>1 under torchrun, one rank per GPU
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+    python bench.py --gpus N --steps K --warmup W                  # our arm; N>1 under torchrun, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W          # the reference's own modules on the host cores
+    python bench.py --workload {early,mfnet-add,mfnet-scoreadd,multitask,triple,infer} --batch B   # BASELINE configs 2-5
 
 Metric (BASELINE.json): "MCD-step images/s" = source/target image PAIRS per second through one full MCD
-iteration (phase A + B + num_k=4 x C, adapt_trainer.py:162-212) of DRN-D-38, input_ch=6, n_class=41,
-480x640, SGD(lr 1e-3, momentum .9, wd 2e-5), random-init weights, synthetic N(0,1) images and uniform labels.
-A "step" is one MCD iteration over a batch of `--batch` pairs per GPU (weak scaling).
+iteration (phase A + B + num_k=4 x C) at 480x640, SGD(lr 1e-3, momentum .9, wd 2e-5), random-init weights, synthetic
+N(0,1) images and uniform labels.  A "step" is one MCD iteration over a batch of `--batch` pairs per GPU (weak scaling).
+Workloads (the loops they time, and the reference file that owns each):
+    early           adapt_trainer.py:162-212                     DRN-D-38 input_ch=6, 2 heads        [default, headline]
+    mfnet-add       adapt_mfnet_trainer.py:181-235               2 x DRN-D-38 (RGB, HHA), AddFusion heads
+    mfnet-scoreadd  adapt_mfnet_trainer.py:181-235               2 x DRN-D-38, ScoreAddFusion heads
+    multitask       adapt_multitask_trainer.py:194-262           RGB encoder + seg / HHA decoders
+    triple          adapt_triple_multitask_trainer.py:202-287    RGB encoder + seg / HHA / boundary decoders
+    infer           adapt_triple_multitask_tester.py:117-142     eval forward + argmax(40) + entropy; images/s; `--sweep`
+                                                                 runs batch 1..64
 
 One JSON line is printed by rank 0; see README/DESIGN.md for the keys (value, e2e, roofline, cpu_baseline,
-clocks, gpu_launches).
+clocks, gpu_launches, flops).
 """
 import argparse
 import json
@@ -23,19 +31,40 @@ import warnings
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "multichannel-semseg-with-uda_b200")
-for p in (PKG, ROOT):
-    if p not in sys.path:
-        sys.path.insert(0, p)
 
 import torch  # noqa: E402
 
 N_CLASS = 41
-METRIC = "MCD-step images/s, DRN-D-38 6ch 480x640"
 UNIT = "image pairs/s"
 FULL = (480, 640)
-# algorithmic conv FLOPs per image pair and MCD iteration: 7 fwd + 5 bwd of G
-G_FWD_GF = 260.33
-ITER_TFLOP_PER_PAIR = (7 * G_FWD_GF + 5 * (2 * G_FWD_GF - 2.89)) / 1e3
+# algorithmic conv FLOPs, GF per 480x640 image
+G6_FWD, G3_FWD, ENC_FWD = 260.33, 258.89, 258.69
+DEC_SEG, DEC_DEP, DEC_BD = 25.37, 25.18, 0.012
+
+WORKLOADS = {
+    "early": dict(metric="MCD-step images/s, DRN-D-38 6ch 480x640", src_ch=6, gen_fwd=G6_FWD,
+                  text="early-fusion MCD iteration (A+B+4xC), DRN-D-38 input_ch=6 n_class=41 480x640 "
+                       "(adapt_trainer.py:162-212)"),
+    "mfnet-add": dict(metric="MCD-step images/s, MFNet-AddFusion 2 x DRN-D-38 480x640", src_ch=6, gen_fwd=2 * G3_FWD,
+                      text="MFNet AddFusion MCD iteration, RGB + HHA DRN-D-38 streams (adapt_mfnet_trainer.py:181-235)"),
+    "mfnet-scoreadd": dict(metric="MCD-step images/s, MFNet-ScoreAddFusion 2 x DRN-D-38 480x640", src_ch=6,
+                           gen_fwd=2 * G3_FWD,
+                           text="MFNet ScoreAddFusion MCD iteration, RGB + HHA DRN-D-38 streams "
+                                "(adapt_mfnet_trainer.py:181-235)"),
+    "multitask": dict(metric="MCD-step images/s, seg+HHA multitask DRN-D-38 480x640", src_ch=6, gen_fwd=ENC_FWD,
+                      text="seg + HHA-regression MCD iteration (adapt_multitask_trainer.py:194-262)"),
+    "triple": dict(metric="MCD-step images/s, seg+HHA+boundary triple-task DRN-D-38 480x640", src_ch=7, gen_fwd=ENC_FWD,
+                   text="seg + HHA-regression + boundary MCD iteration (adapt_triple_multitask_trainer.py:202-287)"),
+    "infer": dict(metric="inference images/s, triple-task DRN-D-38 480x640", src_ch=6, gen_fwd=ENC_FWD,
+                  text="eval-mode encoder + decoders + argmax(40 classes) + entropy "
+                       "(adapt_triple_multitask_tester.py:117-142)"),
+}
+
+
+def use_ours():
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
 
 
 def peaks():
@@ -94,47 +123,173 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
-    capture (profiles/ncu_traffic.json, written by scripts/ncu_summarise.py); None when no capture covers it."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by scripts/ncu_summarise.py): the largest launch recorded for it (the
+    512 -> 512 layer for the dominant convolution kernel), with the algorithmic bytes of that same launch next to it."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
-        return None
+        return None, None
     ent = json.load(open(path)).get(kernel.split(" [")[0])
     if not ent or not ent.get("dram_bytes_per_launch"):
-        return None
-    v = ent["dram_bytes_per_launch"]
-    return sum(v) / len(v)
+        return None, None
+    return max(ent["dram_bytes_per_launch"]), ent.get("source")
 
 
 # --------------------------------------------------------------------------------------------------
-def synth(batch, size, seed):
+def synth(batch, size, seed, src_ch=6):
     g = torch.Generator().manual_seed(seed)
-    src = torch.randn(batch, 6, *size, generator=g)
+    src = torch.randn(batch, src_ch, *size, generator=g)
+    if src_ch == 7:                    # SUNCG source: RGB + HHA + boundary map in {0,1} (datasets.py:680-695)
+        src[:, 6] = (torch.rand(batch, *size, generator=g) < 0.1).float()
     tgt = torch.randn(batch, 6, *size, generator=g)
     lbl = torch.randint(0, N_CLASS, (batch, *size), generator=g)
     return src, lbl, tgt
 
 
-def run_reference(args):
-    """The reference's algorithm on the host cores: the oracle port (fp32, stock torch CPU ops), all threads.
-    Each step = one MCD iteration on a bounded sample of the workload (see `sample`)."""
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own nn.Modules / criteria / loop bodies on the host cores
+def reference_iteration_fn(workload):
+    """returns (fn(src, lbl, tgt) running ONE iteration of the reference's trainer loop body on CPU, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import stage_reference
+    ref = stage_reference.import_reference()
+    if ref is None:
+        return port_iteration_fn(workload), "port"
+    L, MU, U = ref["loss"], ref["model_util"], ref["util"]
+    weight = U.get_class_weight_from_file(n_class=N_CLASS, weight_filename=None, add_bg_loss=False)
+    kw = dict(lr=1e-3, momentum=0.9, opt="sgd", weight_decay=2e-5)
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if workload in ("early", "mfnet-add", "mfnet-scoreadd"):
+            method = {"early": "MCD", "mfnet-add": "MCD-MFNet-AddFusion", "mfnet-scoreadd": "MCD-MFNet-ScoreAddFusion"}[workload]
+            models = MU.get_models(net_name="drn_d_38", res="50", input_ch=6, n_class=N_CLASS, method=method)
+            gens, (f1, f2) = models[:-2], models[-2:]
+            opt_g = MU.get_optimizer([p for g in gens for p in g.parameters()], **kw)
+            opt_f = MU.get_optimizer(list(f1.parameters()) + list(f2.parameters()), **kw)
+            crit, crit_d = L.CrossEntropyLoss2d(weight), L.get_prob_distance_criterion("diff")
+            for m in models:
+                m.train()
+
+            def fwd(x):
+                feats = [gens[0](x)] if len(gens) == 1 else [gens[0](x[:, :3, :, :]), gens[1](x[:, 3:, :, :])]
+                return f1(*feats), f2(*feats)
+
+            def it(src, lbl, tgt):           # adapt_trainer.py:162-212 / adapt_mfnet_trainer.py:181-235
+                opt_g.zero_grad(), opt_f.zero_grad()
+                o1, o2 = fwd(src)
+                loss = crit(o1, lbl) + crit(o2, lbl)
+                loss.backward()
+                opt_g.step(), opt_f.step()
+                opt_g.zero_grad(), opt_f.zero_grad()
+                o1, o2 = fwd(src)
+                loss = crit(o1, lbl) + crit(o2, lbl)
+                o1, o2 = fwd(tgt)
+                loss = loss - crit_d(o1, o2)
+                loss.backward()
+                opt_f.step()
+                for _ in range(4):
+                    opt_g.zero_grad()
+                    o1, o2 = fwd(tgt)
+                    loss = crit_d(o1, o2) * 1.0
+                    loss.backward()
+                    opt_g.step()
+                return float(loss)
+            return it, "reference"
+        triple = workload in ("triple", "infer")
+        factory = MU.get_triple_multitask_models if triple else MU.get_multitask_models
+        enc, dec = factory(net_name="drn_d_38", input_ch=6, n_class=N_CLASS, semseg_criterion=L.CrossEntropyLoss2d(weight),
+                           discrepancy_criterion=L.Diff2d())
+    if workload == "infer":
+        enc.eval(), dec.eval()
+
+        def infer(src, lbl, tgt):            # adapt_triple_multitask_tester.py:117-142
+            feature = enc(tgt[:, :3, :, :])
+            s1, s2, depth, boundary = dec(feature)
+            ent = U.calc_entropy(s1)
+            pred = s1[0, :N_CLASS - 1].data.max(0)[1]
+            return float(ent) + float(pred[0, 0])
+        return infer, "reference"
+    opt_e, opt_d = MU.get_optimizer(enc.parameters(), **kw), MU.get_optimizer(dec.parameters(), **kw)
+    enc.train(), dec.train()
+
+    def it(src, lbl, tgt):                   # adapt_triple_multitask_trainer.py:202-287 / adapt_multitask_trainer.py:194-262
+        rgb, trgb, tdep = src[:, :3, :, :], tgt[:, :3, :, :], tgt[:, 3:, :, :]
+        args = (lbl, src[:, 3:-1, :, :], src[:, -1:, :, :]) if triple else (lbl, src[:, 3:, :, :])
+        opt_e.zero_grad(), opt_d.zero_grad()
+        fs, ft = enc(rgb), enc(trgb)
+        loss = sum(dec.get_loss(fs, *args, separately_returning=True)) + dec.get_depth_loss(ft, tdep)
+        loss.backward()
+        opt_e.step(), opt_d.step()
+        opt_e.zero_grad(), opt_d.zero_grad()
+        fs = enc(rgb)
+        terms = dec.get_loss(fs, *args, separately_returning=True)
+        ft = enc(trgb)
+        if triple:
+            loss = terms[0] - dec.get_cls_descrepancy(ft)
+        else:
+            loss = terms[0] + terms[1] + dec.get_depth_loss(ft, tdep) - dec.get_cls_descrepancy(ft)
+        loss.backward()
+        opt_d.step()
+        for _ in range(4):
+            opt_e.zero_grad()
+            loss = dec.get_cls_descrepancy(enc(trgb)) * 1.0
+            loss.backward()
+            opt_e.step()
+        return float(loss)
+    return it, "reference"
+
+
+def port_iteration_fn(workload):
+    """fallback when baseline/_ref was never staged: the oracle port (same torch CPU operators)."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     from oracle import mcd_oracle as O
+    w = O.class_weight(N_CLASS)
+    if workload in ("early", "mfnet-add", "mfnet-scoreadd"):
+        if workload == "early":
+            G = O.init_seg_base("drn_d_38", 6, N_CLASS, torch.Generator().manual_seed(0))
+            F1, F2 = O.init_head(N_CLASS), O.init_head(N_CLASS, gen=torch.Generator().manual_seed(2))
+            og, of = O.SGD(), O.SGD()
+            return lambda s, l, t: O.mcd_step_early(G, F1, F2, s, l, t, w, og, of, num_k=4)[1]
+        kind = "add" if workload == "mfnet-add" else "scoreadd"
+        G3, G1 = O.init_seg_base("drn_d_38", 3, N_CLASS), O.init_seg_base("drn_d_38", 3, N_CLASS, torch.Generator().manual_seed(5))
+        F1, F2 = O.init_head(N_CLASS, kind), O.init_head(N_CLASS, kind, torch.Generator().manual_seed(2))
+        og, of = O.SGD(), O.SGD()
+        return lambda s, l, t: O.mcd_step_mfnet(G3, G1, F1, F2, s, l, t, w, og, of, kind=kind, num_k=4)[1]
+    triple = workload in ("triple", "infer")
+    E = O.init_trunk("drn_d_38", 3, "main_layer" if triple else "base.")
+    D = O.init_triple_decoder(N_CLASS, 3) if triple else O.init_multitask_decoder(N_CLASS, 3)
+    if workload == "infer":
+        def infer(s, l, t):
+            with torch.no_grad():
+                f = O.encoder_dict(E, t[:, :3], train=False)
+                s1, _ = O.triple_semseg(D, f, train=False)
+                O.triple_depth(D, f, train=False), O.triple_boundary(D, f)
+                return float(O.calc_entropy(s1)) + float(O.predict_labels(s1, N_CLASS - 1)[0, 0, 0])
+        return infer
+    oe, od = O.SGD(), O.SGD()
+    return lambda s, l, t: O.mcd_step_multitask(E, D, s, l, t, w, oe, od, triple=triple, num_k=4)[1]
+
+
+def run_reference(args):
+    """The reference's own implementation of the workload on the host cores (baseline/_ref: the unmodified reference
+    modules + loop body; the oracle port if that was never staged), all threads.  Each step = one iteration on a
+    bounded sample of the workload (see `sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # choose the largest sample whose projected run time stays within ~4 minutes
-    budget_s, steps = 240.0, args.steps + args.warmup
-    G = O.init_seg_base("drn_d_38", 6, N_CLASS, torch.Generator().manual_seed(0))
-    F1, F2 = O.init_head(N_CLASS, gen=torch.Generator().manual_seed(1)), O.init_head(N_CLASS, gen=torch.Generator().manual_seed(2))
-    w = O.class_weight(N_CLASS)
-    og, of = O.SGD(), O.SGD()
+    fn, kind = reference_iteration_fn(args.workload)
+    infer = args.workload == "infer"
+    budget_s, steps = (25.0 if args.sample_only else 240.0), args.steps + args.warmup
 
     def one(size):
-        src, lbl, tgt = synth(1, size, 3)
+        src, lbl, tgt = synth(1, size, 3, wl["src_ch"])
         t0 = time.perf_counter()
-        O.mcd_step_early(G, F1, F2, src, lbl, tgt, w, og, of, num_k=4)
+        fn(src, lbl, tgt)
         return time.perf_counter() - t0
 
     t_small = min(one((120, 160)), one((120, 160)))
@@ -150,68 +305,74 @@ def run_reference(args):
         one(size)
     dt = (time.perf_counter() - t0) / args.steps
     frac = (size[0] * size[1]) / float(FULL[0] * FULL[1])
-    value = frac / dt   # 480x640-equivalent pairs per second
-    sample = ("1 pair per step at %dx%d (%.4f of a 480x640 pair by pixel count; value is in 480x640-pair "
-              "equivalents), fp32, %d torch threads" % (size[0], size[1], frac, cores))
+    value = frac / dt   # 480x640-equivalent pairs (images for `infer`) per second
+    what = "image" if infer else "pair"
+    sample = ("1 %s per step at %dx%d (%.4f of a 480x640 %s by pixel count; value is in 480x640-%s equivalents), fp32, "
+              "%d torch threads, %.2f s per step" % (what, size[0], size[1], frac, what, what, cores, dt))
+    unit = "images/s" if infer else UNIT
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "early-fusion MCD iteration (A+B+4xC), DRN-D-38 6ch, n_class 41", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": wl["text"], "sample": sample,
+                   "implementation": "baseline/_ref: the reference's own modules and loop body" if kind == "reference"
+                   else "oracle/mcd_oracle.py port (baseline/_ref not staged)"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline_sample():
-    """bounded CPU sample for the N=1 line: one MCD iteration of the oracle port on the host cores."""
-    from oracle import mcd_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    G = O.init_seg_base("drn_d_38", 6, N_CLASS, torch.Generator().manual_seed(0))
-    F1, F2 = O.init_head(N_CLASS, gen=torch.Generator().manual_seed(1)), O.init_head(N_CLASS, gen=torch.Generator().manual_seed(2))
-    w, og, of = O.class_weight(N_CLASS), O.SGD(), O.SGD()
-    size = (240, 320)
-    src, lbl, tgt = synth(1, size, 3)
-    O.mcd_step_early(G, F1, F2, src, lbl, tgt, w, og, of, num_k=4)   # warm-up
-    t0 = time.perf_counter()
-    n = 2
-    for _ in range(n):
-        O.mcd_step_early(G, F1, F2, src, lbl, tgt, w, og, of, num_k=4)
-    dt = (time.perf_counter() - t0) / n
-    frac = (size[0] * size[1]) / float(FULL[0] * FULL[1])
-    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d MCD iterations of 1 pair at %dx%d (%.2f of a 480x640 pair; value in 480x640-pair "
-                      "equivalents), fp32 oracle port, %d torch threads, %.2f s/iteration"
-                      % (n, size[0], size[1], frac, cores, dt)}
+def cpu_baseline_sample(workload):
+    """bounded CPU sample for the N=1 line: run the reference arm in a SUBPROCESS (its `models` / `loss` / `util`
+    packages have the same names as ours) for ~10-30 s and take its cpu_baseline object."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                            "--steps", "2", "--warmup", "1", "--sample-only"], capture_output=True, text=True, timeout=600)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as exc:      # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(exc)[:200]}
 
 
 # --------------------------------------------------------------------------------------------------
-def run_ours(args):
-    from mcd_b200 import abi, ops, parallel
+def build_step(workload, dev):
+    """the MCDStep of a workload over freshly initialised drop-in modules."""
     from mcd_b200.step import MCDStep
-    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
-    from models.model_util import get_models
+    from loss import CrossEntropyLoss2d, Diff2d, get_prob_distance_criterion
+    from models.model_util import get_models, get_multitask_models, get_triple_multitask_models
     from util import get_class_weight_from_file
+    w = get_class_weight_from_file(N_CLASS).to(dev)
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if workload in ("early", "mfnet-add", "mfnet-scoreadd"):
+            method = {"early": "MCD", "mfnet-add": "MCD-MFNet-AddFusion", "mfnet-scoreadd": "MCD-MFNet-ScoreAddFusion"}[workload]
+            models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS, method=method)]
+            return MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=4), models
+        triple = workload == "triple"
+        factory = get_triple_multitask_models if triple else get_multitask_models
+        enc, dec = factory("drn_d_38", 6, N_CLASS, semseg_criterion=CrossEntropyLoss2d(w), discrepancy_criterion=Diff2d())
+        enc, dec = enc.to(dev).train(), dec.to(dev).train()
+        return MCDStep.multitask(enc, dec, triple=triple, num_k=4), [enc, dec]
 
+
+def run_ours(args):
+    use_ours()
+    from mcd_b200 import abi, ops, parallel
     rank, local, world = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     abi.check(abi.lib().mcd_check_device(local), "mcd_check_device")
+    if args.workload == "infer":
+        return run_infer(args, rank, local, world, dev)
     pk = peaks()
+    wl = WORKLOADS[args.workload]
     B, size = args.batch, FULL
+    step, models = build_step(args.workload, dev)
 
-    torch.manual_seed(0)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS, method="MCD")]
-    criterion = CrossEntropyLoss2d(get_class_weight_from_file(N_CLASS).to(dev))
-    criterion_d = get_prob_distance_criterion("diff")
-    step = MCDStep(models, criterion, criterion_d, num_k=4)
-
-    src_h, lbl_h, tgt_h = [t.pin_memory() for t in synth(B, size, 100 + rank)]
+    src_h, lbl_h, tgt_h = [t.pin_memory() for t in synth(B, size, 100 + rank, wl["src_ch"])]
     src_d, lbl_d, tgt_d = src_h.to(dev), lbl_h.to(dev), tgt_h.to(dev)
     h2d = sum(t.numel() * t.element_size() for t in (src_h, lbl_h, tgt_h))
 
@@ -251,6 +412,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     mcd_nn.set_overlap_wgrad(prev_overlap)
     fam = prof.summary()
+    executed_tflop = sum(v["flop"] for v in fam.values()) / 1e12 / B      # every convolution launch of the iteration
     if use_graph:
         step.capture(src_d, lbl_d, tgt_d, warmup=1)
 
@@ -274,6 +436,7 @@ def run_ours(args):
 
     for _ in range(3):
         resident_step()
+
     def measure():
         sampler = ClockSampler(local)
         if rank == 0:
@@ -311,21 +474,22 @@ def run_ours(args):
     if dom:
         ach = fam[dom]["flop"] / (fam[dom]["ms"] * 1e-3) / 1e12
         serial_ms = sum(v["ms"] for v in fam.values())
+        traffic, tsrc = ncu_traffic(dom)
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["sustained"], "traffic": ncu_traffic(dom),
-                "traffic_note": "mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the launches of this "
-                                "kernel in profiles/r01b_ncu_full_conv_bn.csv (512->512 and 256->256 3x3 layers, 22 "
-                                "images, forward and dgrad); algorithmic bytes of the 512-channel forward: 221 MB",
+                "frac": ach / pk["sustained"], "traffic": traffic,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of this kernel in "
+                                "profiles/%s (the 512 -> 512 3x3 layer at 22 images: 221 MB algorithmic = activations in "
+                                "+ out + weights once)" % tsrc,
                 "peak_source": pk["src"] + ", sustained",
                 "launches": fam[dom]["n"], "avg_launch_ms": fam[dom]["ms"] / fam[dom]["n"],
                 "flop_per_launch": fam[dom]["flop"] / fam[dom]["n"],
                 "share_of_conv_time": fam[dom]["ms"] / serial_ms,
                 "how": "CUDA-event pair on the launching stream around every convolution launch of one eager, "
-                       "fully serialised MCD iteration run inside this process right before the timed region "
+                       "fully serialised iteration run inside this process right before the timed region "
                        "(a CUDA-graph replay cannot be bracketed per kernel); algorithmic FLOPs = 2*N*Ho*Wo*Cout*Cin*R*S",
                 "kernels": {k: {"ms": round(v["ms"], 3), "tflops": round(v["flop"] / (v["ms"] * 1e-3) / 1e12, 1),
                                 "n": v["n"]} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
-    # ---- extras (per-phase and inference throughput); never allowed to break the main line ----------
+    # ---- extras (per-phase throughput); never allowed to break the main line ----------
     extras = {}
     try:
         step(src_d, lbl_d, tgt_d)           # untimed: re-populates the eager allocator pool after the graph capture
@@ -343,51 +507,142 @@ def run_ours(args):
                                         "C": B / (sum(c_ms) / len(c_ms) * 1e-3)}
         extras["phases_note"] = ("device time between CUDA events at the phase boundaries of ONE eager iteration on "
                                  "this rank; B includes the target forward that phase C[0] re-uses, so C0 is backward only")
-        # inference (adapt_tester.py:104-124): eval-mode forward of G + both heads, argmax over the 40 valid classes
-        import util as mcd_util
-        for m in models:
-            m.eval()
-        mg, mf1, mf2 = models
-
-        def infer():
-            with torch.no_grad():
-                feat = mg(tgt_d)
-                out = mf1(feat) + mf2(feat)
-                return mcd_util.predict_labels(out, N_CLASS - 1), mcd_util.calc_entropy(out)
-        for _ in range(2):
-            infer()
-        ms_inf = timed(infer, 3)
-        for m in models:
-            m.train()
-        extras["inference"] = {"images_per_s": B * world / (ms_inf * 1e-3), "ms_per_batch": ms_inf, "batch_per_gpu": B,
-                               "what": "eval-mode DRN-D-38 6ch forward + 2 heads + argmax(40 classes) + entropy, eager "
-                                       "launches, inputs resident", "algorithmic_gflop_per_image": G_FWD_GF,
-                               "tensor_util": G_FWD_GF * 1e-3 * B / (ms_inf * 1e-3) / pk["sustained"]}
     except Exception as exc:      # noqa: BLE001
         extras["error"] = repr(exc)[:300]
     if rank != 0:
         return
     pairs = B * world
     value = pairs / (ms * 1e-3)
+    credited = executed_tflop + wl["gen_fwd"] / 1e3       # the re-used phase-B target forward, counted once more
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "early-fusion MCD iteration (A+B+4xC), DRN-D-38 input_ch=6 n_class=41 480x640, "
-                               "SGD momentum .9 wd 2e-5, random init", "pairs_per_gpu": B, "global_pairs": pairs,
-                   "parallelism": "dp%d" % world, "l2": "per-step working set (activations > 1 GB) exceeds the 126 MB L2",
+        "vs_baseline": None, "dtype": "f16 forward / bf16 gradients, fp32 accumulate", "data": "synthetic",
+        "config": {"workload": wl["text"] + ", SGD momentum .9 wd 2e-5, random init", "pairs_per_gpu": B,
+                   "global_pairs": pairs, "parallelism": "dp%d" % world,
+                   "l2": "per-step working set (activations > 1 GB) exceeds the 126 MB L2",
                    "dead_phaseB_backward_skipped": True, "cuda_graph": bool(use_graph)},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
-        "tensor_util_of_step": ITER_TFLOP_PER_PAIR * B / (ms * 1e-3) / pk["sustained"],
-        "algorithmic_tflop_per_pair": ITER_TFLOP_PER_PAIR,
+        "flops": {"executed_tflop_per_pair": executed_tflop, "credited_tflop_per_pair": credited,
+                  "tensor_util_executed": executed_tflop * B / (ms * 1e-3) / pk["sustained"],
+                  "tensor_util_credited": credited * B / (ms * 1e-3) / pk["sustained"],
+                  "note": "executed = algorithmic FLOPs (2*N*Ho*Wo*Cout*Cin*R*S) of every convolution launch of one "
+                          "iteration, counted by the instrumented run; credited adds the one generator forward that the "
+                          "phase-B / phase-C[0] re-use saves (the NECESSARY work of the reference loop, SURVEY 8d: 4.411 "
+                          "TFLOP per pair for early fusion); both against the sustained bf16 peak"},
         "extras": extras,
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_sample()
+        out["cpu_baseline"] = cpu_baseline_sample(args.workload)
+    print(json.dumps(out))
+
+
+def run_infer(args, rank, local, world, dev):
+    """config 5: adapt_triple_multitask_tester.py:117-142 - eval-mode encoder + decoders, argmax over the 40 valid
+    classes and prediction entropy, per batch size; N GPUs = N independent replicas (no collective)."""
+    from mcd_b200 import abi
+    from loss import CrossEntropyLoss2d, Diff2d
+    from models.model_util import get_triple_multitask_models
+    import util as mcd_util
+    pk = peaks()
+    wl = WORKLOADS["infer"]
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        enc, dec = get_triple_multitask_models("drn_d_38", 6, N_CLASS, semseg_criterion=CrossEntropyLoss2d(),
+                                               discrepancy_criterion=Diff2d())
+    enc, dec = enc.to(dev).eval(), dec.to(dev).eval()
+    gf_img = ENC_FWD + 2 * DEC_SEG + DEC_DEP + DEC_BD
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def bench_batch(B, steps):
+        x_h = torch.randn(B, 6, *FULL, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
+        x_d = x_h.to(dev)
+        static = x_d.clone()
+
+        def forward():
+            with torch.no_grad():
+                s1, s2, depth, boundary = dec(enc(static[:, :3]))
+                return mcd_util.predict_labels(s1, N_CLASS - 1), mcd_util.calc_entropy(s1), depth, boundary
+        for _ in range(max(args.warmup, 3)):
+            forward()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = abi.launch_count()
+        with torch.cuda.graph(graph):
+            out = forward()
+        launches = abi.launch_count() - n0
+
+        def timed(fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1) / steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+                ms = float(t)
+            return ms
+
+        def e2e():
+            static.copy_(x_h, non_blocking=True)
+            graph.replay()
+            return out[0].cpu(), float(out[1])       # label maps and the entropy scalar back on the host
+        for _ in range(2):
+            graph.replay()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms = timed(graph.replay)
+        clocks = sampler.stop() if rank == 0 else None
+        e2e()
+        ms_e2e = timed(e2e)
+        res = dict(batch_per_gpu=B, ms_per_batch=ms, images_per_s=B * world / (ms * 1e-3),
+                   e2e_images_per_s=B * world / (ms_e2e * 1e-3), gpu_launches_per_batch=launches,
+                   tensor_util=gf_img * 1e-3 * B / (ms * 1e-3) / pk["sustained"],
+                   h2d_bytes=x_h.numel() * 4, d2h_bytes=B * FULL[0] * FULL[1] * 8 + 4)
+        del graph
+        return res, clocks
+
+    batches = [1, 2, 4, 8, 16, 32, 64] if args.sweep else [args.batch]
+    sweep, clocks = [], None
+    for B in batches:
+        r, c = bench_batch(B, args.steps)
+        sweep.append(r)
+        clocks = c or clocks
+    if rank != 0:
+        return
+    best = max(sweep, key=lambda r: r["images_per_s"])
+    out = {
+        "metric": wl["metric"], "value": best["images_per_s"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": best["ms_per_batch"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 storage, fp32 accumulate", "data": "synthetic",
+        "config": {"workload": wl["text"], "batch_per_gpu": best["batch_per_gpu"], "parallelism": "%d replicas" % world,
+                   "cuda_graph": True, "algorithmic_gflop_per_image": gf_img,
+                   "l2": "inputs and activations of a batch exceed the 126 MB L2 from batch 2 on"},
+        "e2e": {"value": best["e2e_images_per_s"], "unit": "images/s", "h2d_bytes_per_step": best["h2d_bytes"],
+                "d2h_bytes_per_step": best["d2h_bytes"]},
+        "gpu_launches": int(best["gpu_launches_per_batch"] * args.steps),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": gf_img * 1e-3 * best["images_per_s"] / world, "peak": pk["sustained"],
+                     "unit": "TFLOP/s", "frac": best["tensor_util"], "traffic": None, "kernel": "whole forward",
+                     "peak_source": pk["src"] + ", sustained"},
+        "extras": {"sweep": sweep},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_sample("infer")
     print(json.dumps(out))
 
 
@@ -397,10 +652,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="early", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=22,
                     help="image pairs per GPU and step (22 x 40 = 880 pixel tiles of 128 = 5.95 / 11.9 full waves of "
-                         "the 74 CTA pairs for the 256- / 512-channel layers)")
+                         "the 74 CTA pairs for the 256- / 512-channel layers); the reference's default is 1")
+    ap.add_argument("--sweep", action="store_true", help="infer: batch 1, 2, 4, ..., 64 (BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-only", action="store_true", help="reference arm: ~25 s budget (the cpu_baseline leg)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of one CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
