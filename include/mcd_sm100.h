@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 14
+#define MCD_ABI_VERSION 15
 
 enum {
   MCD_OK = 0,
@@ -242,6 +242,25 @@ int mcd_deconv16s8_fwd(const float* x, const float* w, const float* x2, const fl
 /* dx (planar fp32 [N,C,h,w], overwritten) and dw (fp32 [C,256], overwritten) from dout (planar bf16 / fp32). */
 int mcd_deconv16s8_bwd(const void* dout, int dout_f32, const float* x, const float* w, float* dx, float* dw,
                        int N, int C, int h, int w_, int device, void* stream);
+/* ---- classifier head FUSED with its loss: the full-resolution logits are never materialised -----------------
+ * One kernel = x8 upsampling head (learned 16x16/s8 depthwise deconv, models/dilated_fcn.py:357-366,465-491, or
+ * nn.Upsample(x8, bilinear) of the multitask decoders :676,817-819 when the filter pointers are NULL) + softmax +
+ * loss + the gradients of the loss w.r.t. the head's inputs and filters, for an upstream gradient of 1.
+ *   mode 0: CrossEntropyLoss2d (loss.py:7-13) of ONE head;  mode 1: Diff2d (loss.py:93-100) between TWO heads.
+ * x / w / dx / dw: host arrays of nheads * nin DEVICE pointers, index head * nin + input; a head's logits are the sum
+ * over its `nin` (input, filter) pairs (ScoreAddFusion: up1(x1) + up2(x2); AddFusion: pass x1 + x2 as one input).
+ * dx[i] (fp32 [N,C,h,w]) and dw[i] (fp32 [C,256]) are ACCUMULATED INTO (caller-zeroed; two heads may share one dx
+ * buffer when they read the same score map); NULL = gradient not wanted.
+ * target / cls_weight / ignore_index / wsum: cross entropy only; wsum = device scalar, the (global, all-reduced)
+ * normaliser sum_i w[y_i] from mcd_label_weight_sum (NULL: 1).  inv_numel: Diff2d only, 1 / (N*C*H*W*world).
+ * acc (fp32[4], caller-zeroed): acc[0] += loss numerator (sum w*nll, or sum |pa - pb|), acc[2] += bad labels. */
+int mcd_head_loss(int mode, int nheads, int nin, const float* const* x, const float* const* w, float* const* dx,
+                  float* const* dw, const int64_t* target, const float* cls_weight, int64_t ignore_index,
+                  const float* wsum, float inv_numel, float* acc, int N, int C, int h, int w_, int device,
+                  void* stream);
+/* acc2[0] += sum_i w[y_i] over a label map (ignore_index skipped), acc2[1] += labels outside [0, C). */
+int mcd_label_weight_sum(const int64_t* target, const float* weight, int64_t ignore_index, int C, float* acc2,
+                         int64_t numel, int device, void* stream);
 /* nn.Upsample(scale_factor=s, mode='bilinear'), align_corners=False (dilated_fcn.py:676,817-819).
  * x planar fp32 [N,C,h,w] -> out planar bf16 (out_f32 == 0) or fp32 [N,C,s*h,s*w]. */
 int mcd_bilinear_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s,

@@ -61,8 +61,33 @@ class _EarlyFusionTask:
             return (self.gens[0](x),)
         return self.gens[0](x[:, :3]), self.gens[1](x[:, 3:])       # adapt_mfnet_trainer.py:186-187
 
+    # The classifier heads only feed the criteria: head + softmax + loss + gradients run as ONE kernel that never
+    # materialises the full-resolution logits (mcd_b200/headloss.py) whenever the modules are the reference's plain
+    # learned-deconvolution heads and the criteria CrossEntropyLoss2d / Diff2d; anything else takes the module path.
+    def _fused_inputs(self, head, feats, n_heads):
+        import loss as _loss
+        from . import headloss
+        if not headloss.enabled():
+            return None
+        crit_ok = type(self.criterion) is _loss.CrossEntropyLoss2d if n_heads == 1 else type(self.criterion_d) is _loss.Diff2d
+        hi = headloss.classifier_inputs(head, feats) if crit_ok else None
+        if hi is None:
+            return None
+        want_dw = any(w.requires_grad for w in hi[1]) and torch.is_grad_enabled()
+        if not headloss.fits(n_heads, len(hi[0]), hi[0][0].shape[1], want_dw, False):
+            return None
+        return hi
+
+    def _ce_head(self, head, feats, lbls):
+        from . import headloss
+        hi = self._fused_inputs(head, feats, 1)
+        if hi is None:
+            return self.criterion(head(*feats), lbls)
+        c = self.criterion
+        return headloss.head_ce2d(hi[0], hi[1], lbls, c.nll_loss.weight, c.ignore_index, c.size_average)
+
     def _ce(self, feats, lbls):
-        return self.criterion(self.f1(*feats), lbls) + self.criterion(self.f2(*feats), lbls)
+        return self._ce_head(self.f1, feats, lbls) + self._ce_head(self.f2, feats, lbls)
 
     def loss_a(self, fs, ft, src, lbls, tgt):
         return self._ce(fs, lbls)
@@ -71,7 +96,11 @@ class _EarlyFusionTask:
         return self._ce(fs, lbls) - self.disc(ft)
 
     def disc(self, ft):
-        return self.criterion_d(self.f1(*ft), self.f2(*ft))
+        from . import headloss
+        ha, hb = self._fused_inputs(self.f1, ft, 2), self._fused_inputs(self.f2, ft, 2)
+        if ha is None or hb is None:
+            return self.criterion_d(self.f1(*ft), self.f2(*ft))
+        return headloss.head_diff2d(ha[0], ha[1], hb[0], hb[1])
 
 
 class _MultiTaskTask:

@@ -170,6 +170,26 @@ def _scalar_param():
     return p
 
 
+def _fused_semseg_ce(dec, scores, gt_semseg):
+    """CrossEntropyLoss2d(upsample8(score), gt) for each of the two classifiers' 1/8-resolution score maps as ONE kernel
+    per classifier (mcd_b200/headloss.py: the full-resolution logits are never written), or None when the criterion is
+    not the library's CrossEntropyLoss2d."""
+    from mcd_b200 import headloss
+    c = dec.semseg_criterion
+    if not headloss.enabled() or type(c) is not _loss.CrossEntropyLoss2d or not headloss.fits(1, 1, scores[0].shape[1], False, True):
+        return None
+    return tuple(headloss.head_ce2d([sc], None, gt_semseg, c.nll_loss.weight, c.ignore_index, c.size_average)
+                 for sc in scores)
+
+
+def _fused_discrepancy(dec, scores):
+    from mcd_b200 import headloss
+    if (not headloss.enabled() or type(dec.discrepancy_criterion) is not _loss.Diff2d
+            or not headloss.fits(2, 1, scores[0].shape[1], False, True)):
+        return None
+    return headloss.head_diff2d([scores[0]], None, [scores[1]], None)
+
+
 def _weighted(s, value):
     """learned log-variance task weighting exp(-s) * L + s (reference :1008-1014).  Data parallel: `value` is this
     rank's share of the global loss (loss.set_process_group), so the regulariser s is shared out as well."""
@@ -199,8 +219,12 @@ class MCDMultiTaskDecoder(nn.Module):
         self.discrepancy_criterion = discrepancy_criterion
         self.upsample = BilinearUpsample(8)
 
+    def _semseg_scores(self, x):
+        return self.semsegcls_dec1(x), self.semsegcls_dec2(x)
+
     def semseg_forward(self, x):
-        return self.upsample(self.semsegcls_dec1(x)), self.upsample(self.semsegcls_dec2(x))
+        s1, s2 = self._semseg_scores(x)
+        return self.upsample(s1), self.upsample(s2)
 
     def depth_forward(self, x):
         return self.upsample(self.deprgr_dec(x))
@@ -210,13 +234,20 @@ class MCDMultiTaskDecoder(nn.Module):
         return pred_semseg1, pred_semseg2, self.depth_forward(x)
 
     def get_cls_descrepancy(self, x):
-        pred_semseg1, pred_semseg2 = self.semseg_forward(x)
-        return self.discrepancy_criterion(pred_semseg1, pred_semseg2)
+        scores = self._semseg_scores(x)
+        d = _fused_discrepancy(self, scores)
+        if d is not None:
+            return d
+        return self.discrepancy_criterion(self.upsample(scores[0]), self.upsample(scores[1]))
 
     def get_semseg_loss(self, x, gt_semseg, separately_returning=False):
-        pred_semseg1, pred_semseg2 = self.semseg_forward(x)
-        loss1 = self.semseg_criterion(pred_semseg1, gt_semseg)
-        loss2 = self.semseg_criterion(pred_semseg2, gt_semseg)
+        scores = self._semseg_scores(x)
+        fused = _fused_semseg_ce(self, scores, gt_semseg)
+        if fused is not None:
+            loss1, loss2 = fused
+        else:
+            loss1 = self.semseg_criterion(self.upsample(scores[0]), gt_semseg)
+            loss2 = self.semseg_criterion(self.upsample(scores[1]), gt_semseg)
         return (loss1, loss2) if separately_returning else loss1 + loss2
 
     def get_depth_loss(self, x, gt_dep):
@@ -266,9 +297,13 @@ class MCDTripleMultiTaskDecoder(nn.Module):
         self.add_pred_seg_boundary_loss = add_pred_seg_boundary_loss
         self.use_seg2bd_conv = use_seg2bd_conv
 
-    def semseg_forward(self, x_dic):
+    def _semseg_scores(self, x_dic):
         h8 = x_dic["h8"]
-        return self.upsample3(self.semsegcls_dec1(h8)), self.upsample3(self.semsegcls_dec2(h8))
+        return self.semsegcls_dec1(h8), self.semsegcls_dec2(h8)
+
+    def semseg_forward(self, x_dic):
+        s1, s2 = self._semseg_scores(x_dic)
+        return self.upsample3(s1), self.upsample3(s2)
 
     def depth_forward(self, x_dic):
         return self.upsample3(self.deprgr_dec(x_dic["h8"]))
@@ -285,13 +320,20 @@ class MCDTripleMultiTaskDecoder(nn.Module):
         return pred_semseg1, pred_semseg2, self.depth_forward(x_dic), self.boundary_forward(x_dic)
 
     def get_cls_descrepancy(self, x_dic):
-        pred_semseg1, pred_semseg2 = self.semseg_forward(x_dic)
-        return self.discrepancy_criterion(pred_semseg1, pred_semseg2)
+        scores = self._semseg_scores(x_dic)
+        d = _fused_discrepancy(self, scores)
+        if d is not None:
+            return d
+        return self.discrepancy_criterion(self.upsample3(scores[0]), self.upsample3(scores[1]))
 
     def get_semseg_loss(self, x_dic, gt_semseg, separately_returning=False):
-        pred_semseg1, pred_semseg2 = self.semseg_forward(x_dic)
-        loss1 = self.semseg_criterion(pred_semseg1, gt_semseg)
-        loss2 = self.semseg_criterion(pred_semseg2, gt_semseg)
+        scores = self._semseg_scores(x_dic)
+        fused = _fused_semseg_ce(self, scores, gt_semseg)
+        if fused is not None:
+            loss1, loss2 = fused
+        else:
+            loss1 = self.semseg_criterion(self.upsample3(scores[0]), gt_semseg)
+            loss2 = self.semseg_criterion(self.upsample3(scores[1]), gt_semseg)
         return (loss1, loss2) if separately_returning else loss1 + loss2
 
     def get_depth_loss(self, x_dic, gt_dep):

@@ -412,3 +412,77 @@ def test_sgd_step(cuda_dev):
         opt.step()
         ops.sgd_step(p, g, buf, 1e-3, 0.9, 2e-5, it == 0)
     assert rel_err(p, pr.detach()) < 1e-6
+
+
+# ---- classifier head fused with its loss (csrc/headloss.cu): no full-resolution tensor -------------------------------
+def _head_ref(xs, ws, bilinear):
+    out = 0
+    for x, w in zip(xs, ws):
+        out = out + (F.interpolate(x, scale_factor=8, mode="bilinear", align_corners=False) if bilinear
+                     else F.conv_transpose2d(x, w, None, stride=8, padding=4, groups=x.shape[1]))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["deconv", "scoreadd", "bilinear"])
+@pytest.mark.parametrize("shape", [(2, 41, 6, 10), (1, 41, 7, 5), (3, 5, 4, 9)])
+def test_head_ce2d_fused(cuda_dev, kind, shape):
+    from mcd_b200 import headloss
+    torch.manual_seed(11)
+    n, c, h, w = shape
+    n_in = 2 if kind == "scoreadd" else 1
+    xs = [(torch.randn(n, c, h, w, device=cuda_dev) * 2).requires_grad_(True) for _ in range(n_in)]
+    ws = [(torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1).requires_grad_(True) for _ in range(n_in)]
+    target = torch.randint(0, c, (n, 8 * h, 8 * w), device=cuda_dev)
+    target[0, 0, :5] = -100
+    weight = torch.ones(c, device=cuda_dev)
+    weight[c - 1] = 0
+    weight[1] = 2.5
+    ref = F.cross_entropy(_head_ref(xs, ws, kind == "bilinear"), target, weight, ignore_index=-100)
+    g_ref = torch.autograd.grad(ref * 1.7, xs + (ws if kind != "bilinear" else []))
+    xo = [x.detach().clone().requires_grad_(True) for x in xs]
+    wo = [wt.detach().clone().requires_grad_(True) for wt in ws]
+    got = headloss.head_ce2d(xo, None if kind == "bilinear" else wo, target, weight)
+    (got * 1.7).backward()
+    assert abs(float(got) - float(ref)) / abs(float(ref)) < 2e-5
+    for a_, b_ in zip(xo + (wo if kind != "bilinear" else []), g_ref):
+        assert rel_err(a_.grad, b_) < 6e-3, kind
+    # un-normalised (size_average=False) and gradient-free calls
+    with torch.no_grad():
+        s = headloss.head_ce2d(xo, None if kind == "bilinear" else wo, target, weight, size_average=False)
+    ref_s = F.cross_entropy(_head_ref(xs, ws, kind == "bilinear"), target, weight, ignore_index=-100, reduction="sum")
+    assert abs(float(s) - float(ref_s)) / abs(float(ref_s)) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["deconv", "scoreadd", "bilinear", "deconv_frozen"])
+@pytest.mark.parametrize("shape", [(2, 41, 6, 10), (1, 41, 7, 5)])
+def test_head_diff2d_fused(cuda_dev, kind, shape):
+    from mcd_b200 import headloss
+    torch.manual_seed(12)
+    n, c, h, w = shape
+    bil = kind == "bilinear"
+    n_in = 2 if kind == "scoreadd" else 1
+    # learned heads: both classifiers read the SAME score maps; bilinear (multitask decoders): one score map each
+    xs = [(torch.randn(n, c, h, w, device=cuda_dev) * 2).requires_grad_(True) for _ in range(n_in)]
+    xs_b = [(torch.randn(n, c, h, w, device=cuda_dev) * 2).requires_grad_(True) for _ in range(n_in)] if bil else xs
+    # filter gradients of 2 heads x 2 inputs do not fit the shared memory (headloss.fits): ScoreAdd trains its filters
+    # through the un-fused head in phase B and uses the fused kernel with frozen filters in phase C
+    train_w = kind == "deconv"
+    assert headloss.fits(2, n_in, c, train_w, bil) and not headloss.fits(2, 2, 41, True, False)
+    wa = [(torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1).requires_grad_(train_w) for _ in range(n_in)]
+    wb = [(torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1).requires_grad_(train_w) for _ in range(n_in)]
+    pa, pb = F.softmax(_head_ref(xs, wa, bil), 1), F.softmax(_head_ref(xs_b, wb, bil), 1)
+    ref = torch.mean(torch.abs(pa - pb))
+    leaves = xs + (xs_b if bil else []) + ((wa + wb) if train_w else [])
+    g_ref = torch.autograd.grad(-ref, leaves)
+    xo = [x.detach().clone().requires_grad_(True) for x in xs]
+    xo_b = [x.detach().clone().requires_grad_(True) for x in xs_b] if bil else xo
+    wao = [t.detach().clone().requires_grad_(t.requires_grad) for t in wa]
+    wbo = [t.detach().clone().requires_grad_(t.requires_grad) for t in wb]
+    got = headloss.head_diff2d(xo, None if bil else wao, xo_b, None if bil else wbo)
+    (-got).backward()
+    assert abs(float(got) - float(ref)) / float(ref) < 2e-5
+    ours = xo + (xo_b if bil else []) + ((wao + wbo) if train_w else [])
+    for a_, b_ in zip(ours, g_ref):
+        assert rel_err(a_.grad, b_) < 6e-3, kind
+    if kind == "deconv_frozen":
+        assert wao[0].grad is None
