@@ -335,7 +335,7 @@ def cpu_baseline_sample(workload):
 
 
 # --------------------------------------------------------------------------------------------------
-def build_step(workload, dev):
+def build_step(workload, dev, pipeline=None):
     """the MCDStep of a workload over freshly initialised drop-in modules."""
     from mcd_b200.step import MCDStep
     from loss import CrossEntropyLoss2d, Diff2d, get_prob_distance_criterion
@@ -348,12 +348,13 @@ def build_step(workload, dev):
         if workload in ("early", "mfnet-add", "mfnet-scoreadd"):
             method = {"early": "MCD", "mfnet-add": "MCD-MFNet-AddFusion", "mfnet-scoreadd": "MCD-MFNet-ScoreAddFusion"}[workload]
             models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS, method=method)]
-            return MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=4), models
+            return MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=4,
+                           input_pipeline=pipeline), models
         triple = workload == "triple"
         factory = get_triple_multitask_models if triple else get_multitask_models
         enc, dec = factory("drn_d_38", 6, N_CLASS, semseg_criterion=CrossEntropyLoss2d(w), discrepancy_criterion=Diff2d())
         enc, dec = enc.to(dev).train(), dec.to(dev).train()
-        return MCDStep.multitask(enc, dec, triple=triple, num_k=4), [enc, dec]
+        return MCDStep.multitask(enc, dec, triple=triple, num_k=4, input_pipeline=pipeline), [enc, dec]
 
 
 def run_ours(args):
@@ -370,11 +371,35 @@ def run_ours(args):
     pk = peaks()
     wl = WORKLOADS[args.workload]
     B, size = args.batch, FULL
-    step, models = build_step(args.workload, dev)
+    pipe = None
+    if args.input == "u8":
+        # the loader's DECODED uint8 planes cross PCIe; ToTensor / Normalize / concat / ReLabel (transform.py:302-325)
+        # run on the GPU as the first kernels of the captured iteration (mcd_b200/pipeline.py)
+        from mcd_b200.pipeline import InputPipeline
+        mode = "early" if args.workload == "early" else ("mfnet" if args.workload.startswith("mfnet") else "multitask")
+        pipe = InputPipeline(mode, N_CLASS)
+    step, models = build_step(args.workload, dev, pipe)
 
-    src_h, lbl_h, tgt_h = [t.pin_memory() for t in synth(B, size, 100 + rank, wl["src_ch"])]
-    src_d, lbl_d, tgt_d = src_h.to(dev), lbl_h.to(dev), tgt_h.to(dev)
-    h2d = sum(t.numel() * t.element_size() for t in (src_h, lbl_h, tgt_h))
+    def tree(fn, t):
+        return tuple(tree(fn, v) for v in t) if isinstance(t, tuple) else fn(t)
+
+    def leaves(t):
+        return [x for v in t for x in leaves(v)] if isinstance(t, tuple) else [t]
+
+    if pipe is None:
+        src_h, lbl_h, tgt_h = [t.pin_memory() for t in synth(B, size, 100 + rank, wl["src_ch"])]
+    else:
+        g = torch.Generator().manual_seed(100 + rank)
+
+        def u8(*shape):
+            return torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).pin_memory()
+        src_h = (u8(B, *size, 3), u8(B, *size, 3))
+        if wl["src_ch"] == 7:
+            src_h += ((torch.rand(B, *size, generator=g) < 0.1).to(torch.uint8).mul_(255).pin_memory(),)
+        tgt_h = (u8(B, *size, 3), u8(B, *size, 3))
+        lbl_h = torch.randint(0, N_CLASS, (B, *size), generator=g, dtype=torch.uint8).pin_memory()
+    src_d, lbl_d, tgt_d = tree(lambda t: t.to(dev), (src_h, lbl_h, tgt_h))
+    h2d = sum(t.numel() * t.element_size() for t in leaves((src_h, lbl_h, tgt_h)))
 
     def barrier():
         if world > 1:
@@ -430,8 +455,7 @@ def run_ours(args):
             c, d = step.replay_prefetched()
             step.prefetch(src_h, lbl_h, tgt_h)
         else:
-            c, d = step(src_h.to(dev, non_blocking=True), lbl_h.to(dev, non_blocking=True),
-                        tgt_h.to(dev, non_blocking=True))
+            c, d = step(*tree(lambda t: t.to(dev, non_blocking=True), (src_h, lbl_h, tgt_h)))
         return float(c), float(d)      # device -> host read of the step's result
 
     for _ in range(3):
@@ -521,7 +545,9 @@ def run_ours(args):
         "config": {"workload": wl["text"] + ", SGD momentum .9 wd 2e-5, random init", "pairs_per_gpu": B,
                    "global_pairs": pairs, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (activations > 1 GB) exceeds the 126 MB L2",
-                   "dead_phaseB_backward_skipped": True, "cuda_graph": bool(use_graph)},
+                   "dead_phaseB_backward_skipped": True, "cuda_graph": bool(use_graph),
+                   "input": "fp32 NCHW tensors as the reference's loader yields them" if pipe is None else
+                            "decoded uint8 HWC planes, transform.py:302-325 on the GPU inside the iteration"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
@@ -596,10 +622,31 @@ def run_infer(args, rank, local, world, dev):
                 ms = float(t)
             return ms
 
+        # e2e: the next batch travels pinned host -> staging on a copy stream while the current one computes; label maps
+        # and the entropy scalar come back into pinned host buffers; the step ends when they are on the host.
+        stage, lab_h, ent_h = torch.empty_like(static), torch.empty(out[0].shape, dtype=out[0].dtype).pin_memory(), \
+            torch.empty((), dtype=out[1].dtype).pin_memory()
+        cs, copied, consumed = torch.cuda.Stream(dev), torch.cuda.Event(), torch.cuda.Event()
+
+        def prefetch():
+            cs.wait_event(consumed)
+            with torch.cuda.stream(cs):
+                stage.copy_(x_h, non_blocking=True)
+                copied.record(cs)
+
         def e2e():
-            static.copy_(x_h, non_blocking=True)
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(copied)
+            static.copy_(stage, non_blocking=True)
+            consumed.record(main)
+            prefetch()
             graph.replay()
-            return out[0].cpu(), float(out[1])       # label maps and the entropy scalar back on the host
+            lab_h.copy_(out[0], non_blocking=True)
+            ent_h.copy_(out[1], non_blocking=True)
+            main.synchronize()
+            return lab_h, float(ent_h)
+        consumed.record(torch.cuda.current_stream(dev))
+        prefetch()
         for _ in range(2):
             graph.replay()
         sampler = ClockSampler(local)
@@ -653,6 +700,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="early", choices=sorted(WORKLOADS))
+    ap.add_argument("--input", default="f32", choices=["f32", "u8"],
+                    help="training workloads: what crosses PCIe every step (u8 = GPU input pipeline)")
     ap.add_argument("--batch", type=int, default=22,
                     help="image pairs per GPU and step (22 x 40 = 880 pixel tiles of 128 = 5.95 / 11.9 full waves of "
                          "the 74 CTA pairs for the 256- / 512-channel layers); the reference's default is 1")

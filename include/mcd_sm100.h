@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 15
+#define MCD_ABI_VERSION 16
 
 enum {
   MCD_OK = 0,
@@ -316,6 +316,33 @@ int mcd_label_boundary(const void* x, int is_int64, float* out, int N, int H, in
  * acc[0] += sum_c p*log(p+1e-6) over all C channels (adapt_tester.py:104-124, util.py:44-48). */
 int mcd_argmax_entropy(const void* logits, int f32, int64_t* labels, float* acc, int N, int C, int C_arg,
                        int H, int W, int device, void* stream);
+
+/* ---- input pipeline and evaluation counts ----------------------------- */
+/* transform.py:302-314 get_img_transform (ToTensor: uint8 / 255; Normalize: (x - mean) / std) and the channel
+ * concatenation of datasets.py:667-695, over a batch, in one pass.  Plane s is [N*H*W][src_stride[s]] uint8 (HWC
+ * bytes as PIL decodes them); channels [src_first[s], src_first[s] + src_count[s]) are taken.  src_raw[s] != 0 marks a
+ * label plane (the boundary map of the 7-channel input): value relabel_from becomes relabel_to (ReLabel(255, 1)),
+ * converted with .float(), neither scaled nor normalised.  mean / stdv: HOST arrays with one entry per OUTPUT
+ * channel (NULL = 0 / 1).  Outputs (any subset): NCHW fp32 [N,C,H,W] - bit-identical to torchvision's fp32
+ * arithmetic; NHWC IEEE half and its bfloat16 twin [N,H,W,CP=8] (zero padded) - the stem convolution's operand. */
+int mcd_input_transform(const void* const* src, const int* src_stride, const int* src_first, const int* src_count,
+                        const int* src_raw, int n_src, const float* mean, const float* stdv, int relabel_from,
+                        int relabel_to, float* out_nchw, void* out_nhwc_f16, void* out_nhwc_bf16, int CP, int N, int H,
+                        int W, int device, void* stream);
+/* transform.py:21-48,317-324 ToLabel + ReLabel(background_id, n_class - 1): uint8 label map -> int64. */
+int mcd_relabel_u8(const void* src, int64_t* dst, int from, int to, int64_t numel, int device, void* stream);
+/* adapt_tester.py:124-126 Image.resize(test_img_shape, NEAREST) of uint8 label maps [N,H,W] -> [N,OH,OW];
+ * ytab / xtab: DEVICE int32 source indices per output row / column (mcd_b200.pipeline.pil_nearest_table). */
+int mcd_resize_nearest_u8(const void* src, void* dst, const int* ytab_dev, const int* xtab_dev, int N, int H, int W,
+                          int OH, int OW, int device, void* stream);
+/* eval.py:21-23 fast_hist(a = ground truth, b = prediction, n): hist[n*a + b] += 1 for 0 <= a < n (int64 counts,
+ * accumulated into hist[0 .. n*n)); hist[n*n] counts predictions outside [0, n), for which numpy's bincount would
+ * leave the n x n table.  Labels: uint8 or int64.  n <= 104. */
+int mcd_fast_hist(const void* gt, int gt_is_int64, const void* pred, int pred_is_int64, int n, int64_t numel,
+                  int64_t* hist, int device, void* stream);
+/* transform.py:285-294 unnormalize: uint8((x * std + mean) * 255) in float64, x fp32 [N,3,H,W] -> uint8 [N,H,W,3]. */
+int mcd_unnormalize_u8(const float* x, void* dst, const double* mean3, const double* std3, int N, int H, int W,
+                       int device, void* stream);
 
 /* ---- optimiser (models/model_util.py:289-302: SGD momentum / weight decay, torch semantics) - */
 int mcd_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t numel, float lr,

@@ -349,8 +349,12 @@ class FusedSGD:
             dev_t = torch.empty(host.shape, dtype=torch.int64, device=self.dev)
             dev_t.copy_(host, non_blocking=True)
             if len(self._tables) > 64:
-                self._tables.clear()
-            hit = self._tables[key] = (host, dev_t, len(active))
+                # evict only tables no captured CUDA graph reads (a replay dereferences the device table it recorded)
+                for k_ in [k_ for k_, v_ in self._tables.items() if not v_[3][0]]:
+                    del self._tables[k_]
+            hit = self._tables[key] = (host, dev_t, len(active), [False])
+        if torch.cuda.is_current_stream_capturing():
+            hit[3][0] = True
         abi.check(abi.lib().mcd_sgd_pack_multi(_p(hit[1]), hit[2], _p(self.hyper), _SGD_BLOCKS, self.dev.index,
                                                ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)),
                   "sgd_pack_multi")

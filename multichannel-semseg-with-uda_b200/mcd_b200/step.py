@@ -43,6 +43,30 @@ def _detach(t):
     return d
 
 
+def _tree(fn, t):
+    """apply fn to every tensor of a (nested) tuple of tensors - the uint8 planes of an InputPipeline batch"""
+    if isinstance(t, (tuple, list)):
+        return tuple(_tree(fn, v) for v in t)
+    return fn(t)
+
+
+def _tree_copy(dst, src):
+    if isinstance(dst, (tuple, list)):
+        for d, s_ in zip(dst, src):
+            _tree_copy(d, s_)
+    else:
+        dst.copy_(src, non_blocking=True)
+
+
+def _first(t):
+    return _first(t[0]) if isinstance(t, (tuple, list)) else t
+
+
+def _streams(x):
+    """generator inputs of a batch: a pre-transformed pipeline.Batch carries them, a loader tensor is sliced"""
+    return x.streams if hasattr(x, "streams") else None
+
+
 # ---- the four trainers as "tasks": what differs between them is how features and the three objectives are formed --
 class _EarlyFusionTask:
     """adapt_trainer.py:162-212 (one generator) / adapt_mfnet_trainer.py:181-235 (RGB + HHA generators)."""
@@ -57,8 +81,11 @@ class _EarlyFusionTask:
         self.mult = 1.0 if self.mfnet else mult
 
     def features(self, x):
+        st = _streams(x)
         if not self.mfnet:
-            return (self.gens[0](x),)
+            return (self.gens[0](x if st is None else st[0]),)
+        if st is not None:
+            return self.gens[0](st[0]), self.gens[1](st[1])
         return self.gens[0](x[:, :3]), self.gens[1](x[:, 3:])       # adapt_mfnet_trainer.py:186-187
 
     # The classifier heads only feed the criteria: head + softmax + loss + gradients run as ONE kernel that never
@@ -112,22 +139,29 @@ class _MultiTaskTask:
         self.enc, self.dec, self.triple, self.mult = model_enc, model_dec, triple, mult
 
     def features(self, x):
-        return self.enc(x[:, :3])
+        st = _streams(x)
+        return self.enc(x[:, :3] if st is None else st[0])
+
+    @staticmethod
+    def _rest(x):
+        """channels 3.. of the loader tensor (HHA regression target [, boundary map])"""
+        return x[:, 3:] if _streams(x) is None else x.aux
 
     def loss_a(self, fs, ft, src, lbls, tgt):
+        rest = self._rest(src)
         if self.triple:
-            terms = self.dec.get_loss(fs, lbls, src[:, 3:-1], src[:, -1:], separately_returning=True)
+            terms = self.dec.get_loss(fs, lbls, rest[:, :-1], rest[:, -1:], separately_returning=True)
         else:
-            terms = self.dec.get_loss(fs, lbls, src[:, 3:], separately_returning=True)
-        return sum(terms) + self.dec.get_depth_loss(ft, tgt[:, 3:])
+            terms = self.dec.get_loss(fs, lbls, rest, separately_returning=True)
+        return sum(terms) + self.dec.get_depth_loss(ft, self._rest(tgt))
 
     def loss_b(self, fs, ft, src, lbls, tgt):
         if self.triple:      # :274-276 loss = src_semseg_loss - tgt_discrepancy (depth / boundary terms are dead)
             with torch.no_grad():           # ... but get_loss() ran the depth decoder in train mode: its BatchNorm
                 self.dec.depth_forward(fs)  # running statistics take that update (forward only, 25 GF / image)
             return self.dec.get_weighted_semseg_loss(fs, lbls) - self.disc(ft)
-        semseg, depth = self.dec.get_loss(fs, lbls, src[:, 3:], separately_returning=True)
-        return semseg + depth + self.dec.get_depth_loss(ft, tgt[:, 3:]) - self.disc(ft)    # adapt_multitask_trainer.py:220
+        semseg, depth = self.dec.get_loss(fs, lbls, self._rest(src), separately_returning=True)
+        return semseg + depth + self.dec.get_depth_loss(ft, self._rest(tgt)) - self.disc(ft)    # adapt_multitask_trainer.py:220
 
     def disc(self, ft):
         return self.dec.get_cls_descrepancy(ft)
@@ -137,12 +171,15 @@ class MCDStep:
     """method 'MCD' (early fusion): models = (model_g, model_f1, model_f2);
     method 'MFNet': models = (model_g_3ch, model_g_1ch, model_f1, model_f2);
     multitask trainers: MCDStep.multitask(model_enc, model_dec, triple=...).
-    Call it with (src_imgs, src_lbls, tgt_imgs) exactly as the trainers' loops receive them."""
+    Call it with (src_imgs, src_lbls, tgt_imgs) exactly as the trainers' loops receive them - or, with
+    input_pipeline = mcd_b200.pipeline.InputPipeline(mode), with the loader's DECODED uint8 arrays: src_imgs / tgt_imgs =
+    (rgb [N,H,W,3], hha [N,H,W,3][, boundary [N,H,W]]) and src_lbls uint8 [N,H,W]; ToTensor / Normalize / concat /
+    ReLabel (transform.py:302-325) then run on the GPU as the first kernels of the (captured) iteration."""
 
     def __init__(self, models, criterion, criterion_d, lr=1e-3, momentum=0.9, weight_decay=2e-5, num_k=4,
                  num_multiply_d_loss=1.0, opt="sgd", exact_reference_backward=False, process_group=None,
                  bucket_mb=25, reuse_target_forward=True, fused_sgd=True, defer_wgrad_reduce=True,
-                 logits_dtype=torch.bfloat16, task=None):
+                 logits_dtype=torch.bfloat16, task=None, input_pipeline=None):
         from models.model_util import get_optimizer
         self.task = task if task is not None else _EarlyFusionTask(models, criterion, criterion_d, num_multiply_d_loss)
         self.gens, self.clfs = self.task.gens, self.task.clfs
@@ -181,6 +218,7 @@ class MCDStep:
             _loss.set_process_group(process_group)
         self.graph = None
         self._captured_lr = None
+        self.pipeline = input_pipeline
 
     @classmethod
     def multitask(cls, model_enc, model_dec, triple=True, num_multiply_d_loss=1.0, **kw):
@@ -196,10 +234,10 @@ class MCDStep:
         from . import abi
         # world > 1: the NCCL bucket all-reduces (side stream, forked / joined with stream waits) and the scalar
         # all-reduces of the criteria are captured as graph nodes too; every rank replays the same sequence.
-        dev = src_imgs.device
+        dev = _first(src_imgs).device
         if not self._fused:
             warmup = max(warmup, 1)        # lazily built host tables (optimizer / re-pack lists) need one eager iteration
-        self._static = (src_imgs.clone(), src_lbls.clone(), tgt_imgs.clone())
+        self._static = _tree(torch.clone, (src_imgs, src_lbls, tgt_imgs))
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -238,10 +276,7 @@ class MCDStep:
             self._captured_lr = self._hyper_snapshot()
 
     def replay(self, src_imgs, src_lbls, tgt_imgs):
-        s, l, t = self._static
-        s.copy_(src_imgs, non_blocking=True)
-        l.copy_(src_lbls, non_blocking=True)
-        t.copy_(tgt_imgs, non_blocking=True)
+        _tree_copy(self._static, (src_imgs, src_lbls, tgt_imgs))
         self._before_replay()
         self.graph.replay()
         return self._static_out
@@ -251,9 +286,9 @@ class MCDStep:
         """Start the host->device copy of the NEXT batch (pinned host tensors) on a copy stream into staging
         buffers; `replay_prefetched()` consumes it.  The data loader's `.cuda(non_blocking=True)` of the
         reference (adapt_trainer.py:156-160) overlapped with the running iteration."""
-        dev = self._static[0].device
+        dev = _first(self._static).device
         if getattr(self, "_stage", None) is None:
-            self._stage = tuple(torch.empty_like(t) for t in self._static)
+            self._stage = _tree(torch.empty_like, self._static)
             self._copy_stream = torch.cuda.Stream(dev)
             self._copied = torch.cuda.Event()
             self._consumed = torch.cuda.Event()
@@ -261,17 +296,15 @@ class MCDStep:
         cs = self._copy_stream
         cs.wait_event(self._consumed)            # the previous staging contents have been moved into the static inputs
         with torch.cuda.stream(cs):
-            for dst, src in zip(self._stage, (src_imgs, src_lbls, tgt_imgs)):
-                dst.copy_(src, non_blocking=True)
+            _tree_copy(self._stage, (src_imgs, src_lbls, tgt_imgs))
             self._copied.record(cs)
 
     def replay_prefetched(self):
         """device->device move of the prefetched batch into the graph's static inputs, then one graph launch."""
-        dev = self._static[0].device
+        dev = _first(self._static).device
         main = torch.cuda.current_stream(dev)
         main.wait_event(self._copied)
-        for dst, src in zip(self._static, self._stage):
-            dst.copy_(src, non_blocking=True)
+        _tree_copy(self._static, self._stage)
         self._consumed.record(main)
         self._before_replay()
         self.graph.replay()
@@ -280,14 +313,20 @@ class MCDStep:
     # -- one iteration ------------------------------------------------------------------------------
     def __call__(self, src_imgs, src_lbls, tgt_imgs):
         from . import ops
-        if self._arena is None or self._arena.buf.device != src_imgs.device:
-            self._arena = ops.ZeroArena(src_imgs.device)
+        dev = _first(src_imgs).device
+        if self._arena is None or self._arena.buf.device != dev:
+            self._arena = ops.ZeroArena(dev)
         prev_arena = ops.set_arena(self._arena)
         from .nn import DirectGrads, logits_dtype
         try:
             self._arena.begin()            # ONE memset for all BatchNorm-statistic / loss accumulators
             with DirectGrads(defer=self.defer_reduce) as self._dg, logits_dtype(self.logits_dtype):
-                self._dev = src_imgs.device
+                self._dev = dev
+                if self.pipeline is not None:
+                    pl = self.pipeline
+                    bd = src_imgs[2] if len(src_imgs) > 2 else None
+                    src_imgs, tgt_imgs = pl.images(src_imgs[:2], bd), pl.images(tgt_imgs[:2])
+                    src_lbls = pl.labels(src_lbls)
                 return self._iteration(src_imgs, src_lbls, tgt_imgs)
         finally:
             ops.set_arena(prev_arena)

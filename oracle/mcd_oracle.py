@@ -27,6 +27,7 @@ tests (test/test_loss.py) do not touch this path, so those golden vectors are th
 import math
 import zlib
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -646,3 +647,73 @@ def get_boundary_loss(pred, gt, pred_type="semseg", gt_type="semseg"):
     gt_b = label_boundary(gt) if gt_type == "semseg" else gt.detach().clone()
     pred_b = label_boundary(pred) if pred_type == "semseg" else pred
     return bce2d(pred_b.float(), gt_b.float())
+
+
+# ---- byte-side neighbours of the step: numpy / torch restatements --------------------------
+IMAGENET_MEAN = (.485, .456, .406, .485, .485, .485)
+IMAGENET_STD = (.229, .224, .225, .229, .229, .229)
+CITY_MEAN = (0.290101, 0.328081, 0.286964)
+CITY_STD = (0.182954, 0.186566, 0.184475)
+
+
+def img_transform(img_u8_hwc, normalize_way="imagenet"):
+    """transform.py:302-314 on one decoded image: ToTensor (uint8 HWC -> float CHW / 255) and Normalize as the
+    torchvision 0.2 loop `for t, m, s in zip(tensor, mean, std): t.sub_(m).div_(s)` (the first c entries are used)."""
+    x = torch.from_numpy(np.ascontiguousarray(img_u8_hwc)).permute(2, 0, 1).contiguous().float().div(255)
+    c = x.shape[0]
+    if normalize_way == "imagenet":
+        mean, std = IMAGENET_MEAN[:c], IMAGENET_STD[:c]
+    elif normalize_way == "city":
+        mean, std = CITY_MEAN[:c], CITY_STD[:c]
+    else:
+        return x
+    m = torch.tensor(mean, dtype=torch.float32)[:, None, None]
+    s = torch.tensor(std, dtype=torch.float32)[:, None, None]
+    return (x - m) / s
+
+
+def lbl_transform(lbl_u8, n_class, background_id=255):
+    """transform.py:21-48,317-324: ToLabel (long) + ReLabel(background_id, n_class - 1)"""
+    t = torch.from_numpy(np.ascontiguousarray(lbl_u8)).long()
+    t[t == background_id] = n_class - 1
+    return t
+
+
+def assemble_input(rgb, hha, boundary=None, normalize_way="imagenet"):
+    """datasets.py:667-695: cat([img_transform(rgb), img_transform(hha)[, ReLabel(255, 1)(boundary).float()]])"""
+    parts = [img_transform(rgb, normalize_way), img_transform(hha, normalize_way)]
+    if boundary is not None:
+        parts.append(lbl_transform(boundary, 2).unsqueeze(0).float())
+    return torch.cat(parts)
+
+
+def unnormalize(x_hwc):
+    """transform.py:285-294 (float64 arithmetic of numpy, uint8 cast)"""
+    std, mean = np.array([.229, .224, .225]), np.array([.485, .456, .406])
+    return np.uint8((np.asarray(x_hwc) * std + mean) * 255)
+
+
+def fast_hist(a, b, n):
+    """eval.py:21-23"""
+    k = (a >= 0) & (a < n)
+    return np.bincount(n * a[k].astype(int) + b[k], minlength=n ** 2).reshape(n, n)
+
+
+def per_class_iu(hist):
+    """eval.py:26-27"""
+    return np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
+
+
+def resize_nearest(lbl_u8, size):
+    """adapt_tester.py:124-126: PIL's NEAREST resize, restated: the source index of output coordinate x is
+    int(0.5 * s + x * s) with s = n_in / n_out accumulated step by step in double precision (PIL Geometry.c affine
+    scale path); size = (width, height)."""
+    def table(n_in, n_out):
+        s, xin, tab = float(n_in) / float(n_out), 0.0, []
+        xin = 0.5 * s
+        for _ in range(n_out):
+            tab.append(min(max(int(xin), 0), n_in - 1))
+            xin += s
+        return np.array(tab)
+    h, w = lbl_u8.shape
+    return lbl_u8[table(h, size[1])][:, table(w, size[0])]

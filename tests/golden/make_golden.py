@@ -386,6 +386,70 @@ def golden_iterations():
     np.savez_compressed(os.path.join(HERE, "iterations.npz"), **out)
 
 
+def golden_pipeline():
+    """The byte-side neighbours of the step, from the reference's own code: transform.py ToLabel / ReLabel /
+    get_img_transform / get_lbl_transform / unnormalize (imported from the staged copy; `Scale` is spelled `Resize` in
+    today's torchvision, and Normalize is the torchvision-0.2 loop `for t, m, s in zip(tensor, mean, std)` the reference
+    was written against - with 6 means on a 3-channel image it uses the first three), eval.py fast_hist and scores
+    (function sources executed from the file: the module itself imports matplotlib), PIL's NEAREST resize."""
+    import ast
+    import torchvision.transforms as T
+    from PIL import Image
+    T.Scale = T.Resize
+
+    class ZipNormalize:                                  # torchvision 0.2.x transforms.Normalize.__call__
+        def __init__(self, mean, std):
+            self.mean, self.std = mean, std
+
+        def __call__(self, tensor):
+            for t, m, s in zip(tensor, self.mean, self.std):
+                t.sub_(m).div_(s)
+            return tensor
+
+    T.Normalize = ZipNormalize
+    import transform as RT
+    rng = np.random.RandomState(7)
+    H, W = 10, 14
+    rgb = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    hha = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    lbl = rng.randint(0, 41, (H, W)).astype(np.uint8)
+    lbl[rng.rand(H, W) < 0.2] = 255
+    bd = np.where(rng.rand(H, W) < 0.3, 255, 0).astype(np.uint8)
+    out = {"rgb": rgb, "hha": hha, "lbl": lbl, "bd": bd}
+    img_t = RT.get_img_transform((W, H), "imagenet", use_crop=True)
+    lbl_t = RT.get_lbl_transform((W, H), N_CLASS, use_crop=True)
+    x_rgb, x_hha = img_t(Image.fromarray(rgb)), img_t(Image.fromarray(hha))
+    out["img6"] = torch.cat([x_rgb, x_hha]).numpy()                                  # datasets.py:667-680
+    out["lbl_out"] = lbl_t(Image.fromarray(lbl)).numpy()
+    to_bd = T.Compose(lbl_t.transforms[:-1] + [RT.ReLabel(255, 1)])                   # datasets.py:688-690
+    out["img7"] = torch.cat([x_rgb, x_hha, to_bd(Image.fromarray(bd)).unsqueeze(0).float()]).numpy()
+    city = RT.get_img_transform((W, H), "city", use_crop=True)
+    out["img3_city"] = city(Image.fromarray(rgb)).numpy()
+    un = RT.unnormalize(np.transpose(x_rgb.numpy(), (1, 2, 0)))
+    out["unnorm"] = np.array(un)
+    # eval.py functions
+    src = open(os.path.join(REF, "eval.py")).read()
+    tree = ast.parse(src)
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("fast_hist", "per_class_iu", "calc_fw_iu",
+                                                                 "calc_pixel_accuracy", "calc_mean_accuracy"):
+            exec(compile(ast.Module([node], []), "eval.py", "exec"), ns)
+    gt = rng.randint(0, 41, 4000).astype(np.int64)
+    gt[rng.rand(4000) < 0.1] = 255
+    pred = np.where(rng.rand(4000) < 0.6, np.minimum(gt, 39), rng.randint(0, 40, 4000)).astype(np.int64)
+    hist = ns["fast_hist"](gt, pred, 40)
+    out.update(h_gt=gt, h_pred=pred, hist=hist, iu=ns["per_class_iu"](hist), fw_iu=ns["calc_fw_iu"](hist),
+               pix_acc=ns["calc_pixel_accuracy"](hist), mean_acc=ns["calc_mean_accuracy"](hist))
+    # PIL NEAREST resize of a label map: (in, out) size pairs incl. non-integer ratios
+    for i, ((ih, iw), (oh, ow)) in enumerate([((10, 14), (20, 28)), ((10, 14), (7, 9)), ((48, 64), (53, 71)),
+                                              ((30, 40), (1, 3)), ((9, 7), (64, 50))]):
+        m = rng.randint(0, 41, (ih, iw)).astype(np.uint8)
+        out["rs%d_in" % i] = m
+        out["rs%d_out" % i] = np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST))
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
     torch.set_num_threads(8)
@@ -395,3 +459,4 @@ if __name__ == "__main__":
     golden_mfnet()
     golden_triple()
     golden_iterations()
+    golden_pipeline()

@@ -202,3 +202,39 @@ def test_boundary_loss_matches_reference():
     assert np.array_equal(O.label_boundary(lab_p).numpy(), z["bd_boundary_of_p"])     # integer part: bit-exact
     close(float(O.get_boundary_loss(lab_p, lab_g)), z["bd_ss"])
     close(float(O.get_boundary_loss(lab_p, bmap, gt_type="boundary")), z["bd_sb"])
+
+
+# ---- byte-side neighbours of the step: input transform, label transform, evaluation counts ----
+def _pipe():
+    return np.load(os.path.join(GOLD, "pipeline.npz"))
+
+
+def test_oracle_input_transform_matches_reference_bitwise():
+    d = _pipe()
+    img6 = O.assemble_input(d["rgb"], d["hha"]).numpy()
+    assert np.array_equal(img6, d["img6"])
+    img7 = O.assemble_input(d["rgb"], d["hha"], d["bd"]).numpy()
+    assert np.array_equal(img7, d["img7"])
+    assert np.array_equal(O.img_transform(d["rgb"], "city").numpy(), d["img3_city"])
+    assert np.array_equal(O.lbl_transform(d["lbl"], 41).numpy(), d["lbl_out"])
+    assert np.array_equal(O.unnormalize(np.transpose(img6[:3], (1, 2, 0))), d["unnorm"])
+
+
+def test_oracle_eval_counts_match_reference():
+    d = _pipe()
+    hist = O.fast_hist(d["h_gt"], d["h_pred"], 40)
+    assert np.array_equal(hist, d["hist"])
+    assert np.array_equal(O.per_class_iu(hist), d["iu"])
+
+
+def test_oracle_nearest_resize_matches_pil():
+    from PIL import Image
+    d = _pipe()
+    for i in range(5):
+        m, ref = d["rs%d_in" % i], d["rs%d_out" % i]
+        assert np.array_equal(O.resize_nearest(m, (ref.shape[1], ref.shape[0])), ref), i
+    rng = np.random.RandomState(0)          # and against PIL itself (same image here and on the GPU box)
+    for (ih, iw), (oh, ow) in [((480, 640), (530, 730)), ((480, 640), (425, 560)), ((60, 80), (480, 640)), ((33, 47), (100, 31))]:
+        m = rng.randint(0, 41, (ih, iw)).astype(np.uint8)
+        ref = np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST))
+        assert np.array_equal(O.resize_nearest(m, (ow, oh)), ref), ((ih, iw), (oh, ow))
