@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 16
+#define MCD_ABI_VERSION 17
 
 enum {
   MCD_OK = 0,
@@ -155,6 +155,16 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
  * pointer selects the plain tile-per-CTA schedule.  Results do not depend on the schedule beyond fp32 summation
  * order. */
 size_t mcd_conv2d_streamk_workspace(const mcd_conv_geom* g, int pass, int y_layout, int algo, int* n_flags);
+/* Inference form of the unit conv -> BatchNorm (eval: running statistics) -> (+ residual) -> ReLU of
+ * models/drn.py:43-59,126-131,195-205 with the BatchNorm folded into the operands by the caller (w_packed =
+ * pack(gamma / sqrt(var + eps) * W), bias = beta - mean * gamma / sqrt(var + eps) [+ scaled conv bias]):
+ *   y_nhwc (IEEE half) = [relu]( conv(x, w_packed) + bias + res_nhwc )      res_nhwc: IEEE half, y's geometry, or NULL
+ * one kernel, no pre-BatchNorm tensor.  tcgen05 paths only: mcd_conv2d_fprop_act_supported(g) says whether geometry
+ * g has one (else run mcd_conv2d_fprop + mcd_bn_apply). */
+int mcd_conv2d_fprop_act_supported(const mcd_conv_geom* g);
+int mcd_conv2d_fprop_act(const void* x_nhwc, const void* w_packed, const float* bias, const void* res_nhwc, int relu,
+                         void* y_nhwc, void* sk_partial, int* sk_flags, const mcd_conv_geom* g, int algo, int device,
+                         void* stream);
 /* dx = conv_transpose(dy, w) (+ add_nhwc): gradient wrt the nhwc input; dy, dx, add are bf16, w_packed is the
  * mode-1 (bf16) pack, relu_src the bf16 twin of the input, bn_y the f16 pre-BatchNorm tensor.
  * add_nhwc (may be NULL): tensor of dx's geometry added in the epilogue - the gradient that reaches the same

@@ -89,6 +89,33 @@ int mcd_conv2d_fprop(const void* x_nhwc, const void* w_packed, const float* bias
   return MCD_OK;
 }
 
+int mcd_conv2d_fprop_act_supported(const mcd_conv_geom* g) {
+  if (!g || validate(g) != MCD_OK) return 0;
+  TapProblem p;
+  plan_fprop(*g, p);
+  return umma_problem_supported(p) ? 1 : 0;
+}
+
+int mcd_conv2d_fprop_act(const void* x_nhwc, const void* w_packed, const float* bias, const void* res_nhwc, int relu,
+                         void* y_nhwc, void* sk_partial, int* sk_flags, const mcd_conv_geom* g, int algo, int device,
+                         void* stream) {
+  MCD_ENTER(device);
+  int rc = validate(g);
+  if (rc != MCD_OK) return rc;
+  MCD_REQUIRE(x_nhwc && w_packed && y_nhwc, "conv fprop_act: null pointer");
+  MCD_REQUIRE(algo != MCD_ALGO_DIRECT, "conv fprop_act: tcgen05 paths only");
+  cudaStream_t st = (cudaStream_t)stream;
+  TapProblem p;
+  plan_fprop(*g, p);
+  MCD_REQUIRE(umma_problem_supported(p), "conv fprop_act: shape not supported by the tcgen05 path");
+  EpiExtra ex;
+  ex.addend = res_nhwc; ex.relu = relu != 0;
+  if (rowconv_fprop_ok(*g)) return rowconv_launch(x_nhwc, w_packed, bias, y_nhwc, 0, nullptr, ex, *g, 0, st);
+  if (packed_fprop_ok(*g)) plan_fprop_packed(*g, p);
+  ex.sk_partial = sk_partial; ex.sk_flags = sk_flags;
+  return launch_umma_problem(x_nhwc, w_packed, bias, y_nhwc, 0, nullptr, ex, p, kF16, st);
+}
+
 int mcd_conv2d_dgrad(const void* dy_nhwc, const void* w_packed_dgrad, void* dx_nhwc, const void* add_nhwc,
                      const void* relu_src_nhwc, const void* bn_y_nhwc, float* bn_sums, void* sk_partial,
                      int* sk_flags, const mcd_conv_geom* g, int algo, int device, void* stream) {

@@ -21,6 +21,7 @@ struct EpiExtra {
   const void* addend = nullptr;    // out += addend                       (identity-shortcut gradient)
   const void* mask_src = nullptr;  // out  = mask_src > 0 ? out : 0       (ReLU backward of the producing unit)
   const void* bn_y = nullptr;      // stats += {sum out, sum out * bn_y}  (BatchNorm backward sums)
+  int relu = 0;                    // out  = max(out, 0)                  (forward of an eval-mode conv-BN-ReLU unit)
   void* sk_partial = nullptr;      // stream-K workspace (tcgen05 path): fp32 partial tiles ...
   int* sk_flags = nullptr;         // ... and ready flags (zeroed by the caller); see mcd_conv2d_streamk_workspace
 };

@@ -36,6 +36,7 @@ struct RowconvArgs {
   int fmt;                  // element format of src / weights / nhwc output: kF16 (forward) or kBF16 (dgrad)
   const float* bias;
   float* stats;
+  int relu;                        // max(., 0) on the nhwc output (eval-mode unit)
   const __nv_bfloat16* addend;     // epilogue extras, see conv_plan.h EpiExtra
   const __nv_bfloat16* mask_src;   // bf16 twin (sign only)
   const __half* bn_y;              // forward tensor: IEEE half
@@ -228,9 +229,13 @@ conv_umma_rowconv_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_
             for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[c + k] : 0.f;
             if (x_addend) {
               float r8[8];
-              unpack8(addv[j8], r8);
+              unpack8r(addv[j8], r8, a.fmt);
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[k] += r8[k];
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
             }
             if (x_mask) {
               float r8[8];
@@ -510,6 +515,7 @@ int rowconv_launch(const void* src, const void* wpacked, const float* bias, void
   a.w_bytes = round_up(a.R * a.HC * a.SP * (a.NB / 8) * 128, 1024);
   a.stages = max(2, min(4, (54 * 1024 - a.w_bytes) / a.stage_bytes));
   a.bias = bias; a.stats = stats; a.fmt = mode ? kBF16 : kF16;
+  a.relu = planar ? 0 : ex.relu;
   a.addend = planar ? nullptr : (const __nv_bfloat16*)ex.addend;
   a.mask_src = planar ? nullptr : (const __nv_bfloat16*)ex.mask_src;
   a.bn_y = planar ? nullptr : (const __half*)ex.bn_y;

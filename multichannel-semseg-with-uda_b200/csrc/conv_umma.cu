@@ -52,9 +52,11 @@ struct FpropArgs {
   int packed;             // row-packed thin-channel mode: A = TWp window loads of THp rows each
   int cs_src, smul;       // packed: source channel stride, W stride of the convolution
   const float* bias;
+  int relu;               // nhwc output: max(., 0) after bias and addend - the eval-mode unit conv -> folded BatchNorm -> ReLU
   float* stats;
   void* out;
-  const __nv_bfloat16* addend;   // optional nhwc tensor (output geometry) added in the epilogue: residual gradient
+  const __nv_bfloat16* addend;   // optional nhwc tensor (output geometry, element format `fmt`) added in the epilogue:
+                                 // the residual gradient (dgrad) or the residual branch of an eval-mode block (forward)
   // dgrad fused with the backward of the BatchNorm+ReLU unit that produced the convolution's input (all nhwc,
   // output geometry): out = mask_src > 0 ? out : 0 and, with bn_y, stats += {sum out, sum out * bn_y}
   const __nv_bfloat16* mask_src;  // bf16 twin of the activation (only its sign is used)
@@ -545,9 +547,13 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
                 for (int k = 0; k < 8; ++k) f[k] = (c + k < a.rows) ? v[j8 * 8 + k] : 0.f;
                 if (x_addend) {
                   float r[8];
-                  unpack8(ea[j8], r);
+                  unpack8r(ea[j8], r, a.fmt);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) f[k] += r[k];
+                }
+                if (a.relu) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f);
                 }
                 if (x_mask) {
                   float r[8];
@@ -1452,6 +1458,7 @@ int launch_umma_problem(const void* src, const void* w, const float* bias, void*
   a.kchunks = (p.Kc + 63) / 64; a.ntaps = p.ntaps; a.kc_pad = p.kc_pad;
   a.rows = p.rows; a.omul = p.omul; a.oh0 = p.oh0; a.ow0 = p.ow0; a.Hd = p.Hd; a.Wd = p.Wd;
   a.Cd_s = p.Cd_s; a.planar = planar; a.fmt = fmt; a.bias = bias; a.stats = stats; a.out = out;
+  a.relu = planar ? 0 : ex.relu;
   a.addend = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.addend);
   a.mask_src = planar ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ex.mask_src);
   a.bn_y = planar ? nullptr : reinterpret_cast<const __half*>(ex.bn_y);

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # MCD_LIB_PATH: an alternative build of the same library (A/B measurements of compile-time variants)
 LIB_PATH = os.environ.get("MCD_LIB_PATH") or os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
@@ -51,6 +51,8 @@ _SIGNATURES = {
     "mcd_conv2d_fprop": (c_int, [P, P, P, P, c_int, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
     "mcd_conv2d_streamk_workspace": (c_size_t, [POINTER(ConvGeom), c_int, c_int, c_int, POINTER(c_int)]),
     "mcd_conv2d_dgrad": (c_int, [P, P, P, P, P, P, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
+    "mcd_conv2d_fprop_act_supported": (c_int, [POINTER(ConvGeom)]),
+    "mcd_conv2d_fprop_act": (c_int, [P, P, P, P, c_int, P, P, P, POINTER(ConvGeom), c_int, c_int, P]),
     "mcd_conv2d_wgrad_workspace": (c_size_t, [POINTER(ConvGeom), c_int]),
     "mcd_conv2d_wgrad_partials": (c_int, [POINTER(ConvGeom), c_int, POINTER(c_int32)]),
     "mcd_conv2d_wgrad": (c_int, [P, P, P, P, P, c_size_t, POINTER(ConvGeom), c_int, c_int, c_int, P]),

@@ -263,6 +263,7 @@ class Conv2d(nn.Conv2d):
         self.planar_out = planar_out
         self._packs = {}
         self._geoms = {}
+        self._folds = {}
 
     def geom(self, x_shape):
         key = tuple(x_shape)
@@ -285,6 +286,26 @@ class Conv2d(nn.Conv2d):
             hit = (tag, ops.pack_weight_for(w, g, mode))
             self._packs[key] = hit
         return hit[1]
+
+    def folded(self, bn, g):
+        """eval-mode BatchNorm folded into this convolution: (packed IEEE-half weights scale[o] * W[o], fp32 bias
+        beta - mean * scale (+ scale * conv bias)), scale = gamma / sqrt(running_var + eps); rebuilt when any of the
+        tensors involved changes (optimizer step, load_state_dict, a training-mode forward of `bn`)."""
+        ts = (self.weight, self.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        tag = tuple((t._version, t.data_ptr(), getattr(t, "_mcd_step", 0)) for t in ts if t is not None) + \
+            (getattr(bn, "_mcd_stat_step", 0), float(bn.eps))
+        key = ("fold", id(bn)) + tuple(ops.pack_key(g, 0))
+        hit = self._folds.get(key)
+        if hit is None or hit[0] != tag:
+            with torch.no_grad():
+                scale = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+                shift = bn.bias.float() - bn.running_mean.float() * scale
+                if self.bias is not None:
+                    shift = shift + self.bias.float() * scale
+                w = (self.weight.float() * scale[:, None, None, None]).contiguous()
+                hit = (tag, ops.pack_weight_for(w, g, 0), shift.contiguous())
+            self._folds[key] = hit
+        return hit[1], hit[2]
 
     def prepare(self, x):
         x = ops.to_nhwc(x)
@@ -444,11 +465,37 @@ class _UnitFn(torch.autograd.Function):
         return (dx, dw, db, dgamma, dbeta, dres, drw, dres_gamma, dres_beta, None, None, None, None, None, None, None)
 
 
+_fold_eval = True
+
+
+def set_fold_eval(flag):
+    """A/B switch of the inference path: False = convolution, then BatchNorm as a separate pass (the training layout)."""
+    global _fold_eval
+    prev, _fold_eval = _fold_eval, bool(flag)
+    return prev
+
+
+def folded_unit(conv, bn, x, relu, res=None):
+    """inference (no autograd, BatchNorm in eval mode): z = act(conv'(x) + bias' + res) in one kernel, the BatchNorm
+    folded into conv' / bias' (Conv2d.folded) - no pre-BatchNorm tensor, no normalisation pass."""
+    g = conv.geom(x.shape)
+    w, b = conv.folded(bn, g)
+    return ops.conv_fprop_act(x, w, b, g, res=res, relu=relu)
+
+
 def conv_bn_act(conv, bn, x, relu=True, res=None, res_conv=None, res_bn=None, sole=False):
     """z = act(bn(conv(x)) + residual); residual = res (identity) or res_bn(res_conv(res)).
     sole: `conv` is the only consumer of x (an identity shortcut of the same block aside), see _UnitFn."""
     bn_y = getattr(x, "_mcd_bn_y", None) if sole else None
     x = conv.prepare(x)
+    if (_fold_eval and not torch.is_grad_enabled() and not bn.training and (res_bn is None or not res_bn.training)
+            and bn.affine and bn.track_running_stats):
+        r = res
+        if res is not None:
+            r = folded_unit(res_conv, res_bn, res_conv.prepare(res), False) if res_conv is not None else ops.to_nhwc(res)
+        z = folded_unit(conv, bn, x, relu, r) if (res is None or r is not None) else None
+        if z is not None:
+            return z
     if bn_y is not None and (tuple(bn_y.shape) != tuple(x.shape) or x.shape[1] != conv.in_channels):
         bn_y = None
     if res is not None:

@@ -429,6 +429,27 @@ def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
     return y, stats
 
 
+def conv_fprop_act(x, w_packed, bias, g, res=None, relu=True, algo=None):
+    """z = act(conv(x) + bias + res) in ONE kernel, IEEE-half nhwc (the eval-mode conv -> BatchNorm -> (+ residual) ->
+    ReLU unit with the BatchNorm folded into weights and bias, nn.folded_unit).  Returns None when this geometry has
+    no tcgen05 path (the caller then takes the un-fused route)."""
+    x = h16(x)
+    assert is_nhwc(x) and x.shape[1] == g.Cin_s
+    algo = _algo if algo is None else algo
+    if algo == abi.ALGO_DIRECT or not int(abi.lib().mcd_conv2d_fprop_act_supported(ctypes.byref(g))):
+        return None
+    res = None if res is None else h16(res)
+    z = nhwc_empty(g.N, g.Cout_s, g.Ho, g.Wo, x.device, F16)
+    assert res is None or (is_nhwc(res) and tuple(res.shape) == tuple(z.shape))
+    skp, skf = _streamk_ws(g, 0, False, algo, x.device)
+
+    def run():
+        abi.check(abi.lib().mcd_conv2d_fprop_act(_p(x), _p(w_packed), _p(bias), _p(res), int(relu), _p(z), _p(skp), _p(skf),
+                                                 ctypes.byref(g), algo, _dev(x), _stream(x)), "conv2d_fprop_act")
+        return z
+    return _profiled(0, g, run, False, algo)
+
+
 def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=None):
     """dx = dgrad (+ add: an nhwc tensor of dx's shape, e.g. the identity-shortcut gradient).
     relu_src (the convolution's input, a ReLU output): dx is masked by relu_src > 0 in the epilogue;
@@ -528,6 +549,10 @@ def bn_forward(y, stats, bn, relu, res=None, res_stats=None, res_bn=None, repeat
     rsave = torch.empty((2, c), dtype=F32, device=y.device) if res_bn is not None else None
     tr = repeat if bn.training else 0
     rtr = (repeat if res_bn.training else 0) if res_bn is not None else 0
+    if tr:            # the kernel writes the running statistics through raw pointers: the tensors' autograd version
+        bn._mcd_stat_step = getattr(bn, "_mcd_stat_step", 0) + 1       # counters do not see it (nn.folded_unit tag)
+    if rtr:
+        res_bn._mcd_stat_step = getattr(res_bn, "_mcd_stat_step", 0) + 1
     abi.check(abi.lib().mcd_bn_forward(
         _p(y), _p(stats) if tr else None, _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
         _p(bn.num_batches_tracked) if tr else None, float(mom(bn)), float(bn.eps), tr, _p(save), _p(res),

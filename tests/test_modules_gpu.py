@@ -130,3 +130,70 @@ def test_fused_sgd_matches_torch_sgd_and_refreshes_packs():
 def ops_conv():
     from mcd_b200.nn import Conv2d
     return Conv2d
+
+
+def test_eval_units_fold_batchnorm_into_the_convolution(cuda_dev):
+    """inference (adapt_tester.py:104-124): eval-mode conv -> BatchNorm -> (+ residual) -> ReLU units run as ONE kernel
+    with the BatchNorm folded into weights and bias (nn.folded_unit).  Same predictions as the two-pass layout, fewer
+    launches, and the folded operands follow every way the underlying tensors can change: a training-mode forward
+    (running statistics written by our kernel), an optimizer step of the fused SGD, load_state_dict."""
+    from mcd_b200 import abi, nn as mcd_nn
+    from models.model_util import get_models
+    torch.manual_seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g, f1, _ = [m.to(cuda_dev) for m in get_models("drn_d_38", 6, 41)]
+    x = torch.randn(2, 6, 128, 160, device=cuda_dev)
+    g.train()
+    with torch.no_grad():
+        for _ in range(3):
+            g(x)                      # move the running statistics away from (0, 1)
+
+    def run(fold):
+        prev = mcd_nn.set_fold_eval(fold)
+        try:
+            n0 = abi.launch_count()
+            with torch.no_grad():
+                out = g(x).float()
+            torch.cuda.synchronize()
+            return out, abi.launch_count() - n0
+        finally:
+            mcd_nn.set_fold_eval(prev)
+
+    g.eval()
+    two_pass, n_two = run(False)
+    folded, n_fold = run(True)
+    # two different placements of the IEEE-half roundings (folded: weights * scale rounded once, no pre-BatchNorm
+    # tensor; two-pass: y rounded, then normalised): at random weights DRN-D-38 amplifies such a perturbation ~1.2x per
+    # layer (DESIGN.md section 6), 6.6e-3 measured after 41 layers; the predictions against the fp32 oracle are checked
+    # by test_parity_gpu.py::test_tester_argmax_entropy_vs_oracle (folded: 1.3e-3 / 99.92 %)
+    tol = 2e-2
+    err = float((folded - two_pass).abs().max() / two_pass.abs().max())
+    assert err <= tol, err
+    assert n_fold <= n_two - 35, (n_fold, n_two)          # 41 BatchNorm passes gone
+    # (1) running statistics change under a training-mode forward
+    g.train()
+    with torch.no_grad():
+        g(3.0 * x + 1.0)
+    g.eval()
+    a, _ = run(True)
+    b, _ = run(False)
+    assert float((a - folded).abs().max()) > 1e-3 * float(folded.abs().max())       # the statistics did move
+    assert float((a - b).abs().max() / b.abs().max()) <= tol
+    # (2) load_state_dict
+    sd = {k: (v * 1.05 if v.is_floating_point() and k.endswith("weight") else v) for k, v in g.state_dict().items()}
+    g.load_state_dict(sd)
+    a, _ = run(True)
+    b, _ = run(False)
+    assert float((a - b).abs().max() / b.abs().max()) <= tol
+    # (3) a fused-SGD step (writes the parameters through raw pointers)
+    from mcd_b200 import ops
+    from mcd_b200.nn import Conv2d
+    g.train()
+    g(x).square().mean().backward()
+    opt = torch.optim.SGD([p for p in g.parameters() if p.grad is not None], lr=0.05, momentum=0.9)
+    ops.FusedSGD(opt, [m for m in g.modules() if isinstance(m, Conv2d) and m._packs]).step()
+    g.eval()
+    a, _ = run(True)
+    b, _ = run(False)
+    assert float((a - b).abs().max() / b.abs().max()) <= tol

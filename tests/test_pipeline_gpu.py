@@ -219,7 +219,8 @@ def test_mcdstep_from_uint8_equals_fp32_inputs(cuda_dev, graph):
         torch.cuda.synchronize()
         res.append((float(c), float(dl), [p.detach().clone() for m in models for p in m.parameters()]))
     (c0, d0, p0), (c1, d1, p1) = res
-    assert abs(c0 - c1) <= 2e-5 * abs(c0) and abs(d0 - d1) <= 2e-4 * abs(d0), (c0, c1, d0, d1)
+    # (the graph variant compares the SECOND iteration: weights already differ by the order of the fp32 atomics)
+    assert abs(c0 - c1) <= 1e-4 * abs(c0) and abs(d0 - d1) <= 1e-3 * abs(d0), (c0, c1, d0, d1)
     for a, b in zip(p0, p1):            # identical operands; the order of the fp32 atomics differs between two runs
         assert float((a - b).abs().max()) <= 1e-3 * float(a.abs().max()) + 1e-7
 
