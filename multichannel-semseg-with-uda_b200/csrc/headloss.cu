@@ -14,9 +14,11 @@
 // of 256 threads works on 4 horizontally adjacent cells at a time (thread = one output pixel):
 //   phase 1  logits of all channels in registers (filters and inputs staged in shared memory as float4 per (channel,
 //            position) / (channel, cell)), softmax, loss term, d(loss)/d(logit) -> shared memory (bf16)
-//   phase 2  the transposed products that turn the logit gradients into score-map gradients (dot products of 64 over
-//            the cell) and filter gradients (owner-computes accumulation in shared memory over all cells of the block),
-//            then one atomicAdd per score-map element / filter element.
+//   phase 2  the transposed products that turn the logit gradients into score-map gradients (work unit = channel x
+//            quarter of the 64 positions, 4 cells x 4 taps partial sums -> a 2 x 5 tile per channel in shared memory ->
+//            one global atomicAdd per score-map element of the item) and filter gradients (thread t owns bin (position
+//            t / 4, tap t % 4) of every channel in REGISTERS over all items of the persistent block; one atomicAdd per
+//            filter element and block at the end).
 // Gradients are produced for an upstream gradient of 1; the autograd Function scales them (mcd_b200/headloss.py).
 #include "common.cuh"
 

@@ -11,9 +11,11 @@ module names (=> state_dict keys) and call signatures:
   CBR (:632-644), ThreeLayerDecoder (:647-658)
   MCDMultiTaskDecoder (:661-739), MCDTripleMultiTaskDecoder (:790-1024)
 
-Score maps (n_class / depth / boundary channels at 1/8, 1/4, 1/2 resolution) are fp32 NCHW tensors, the
-full-resolution predictions bf16 NCHW tensors; trunk activations are bf16 channels_last.
   get_boundary_loss (:743-787)                morphological label-map boundary + bce2d
+
+Score maps (n_class / depth / boundary channels at 1/8, 1/4, 1/2 resolution) are fp32 NCHW tensors; the full-resolution
+predictions are fp32 NCHW by default (what the reference's testers call `.cpu().numpy()` on; bfloat16 inside MCDStep,
+mcd_b200.nn.logits_dtype); trunk activations are IEEE-half channels_last with a bfloat16 twin while autograd records.
 
 Everything else in the reference file (DRNSeg, ver2 heads, FuseDRNSegBase, domain classifiers, the
 vendored fyu/drn CLI, shortcut / seg2bd options) is outside SURVEY.md section 8 and raises NotImplementedError.
