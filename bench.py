@@ -129,7 +129,8 @@ def ncu_traffic(kernel):
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None, None
-    ent = json.load(open(path)).get(kernel.split(" [")[0])
+    table = json.load(open(path))
+    ent = table.get(kernel) or table.get(kernel.split(" [")[0])
     if not ent or not ent.get("dram_bytes_per_launch"):
         return None, None
     return max(ent["dram_bytes_per_launch"]), ent.get("source")

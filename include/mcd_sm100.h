@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 17
+#define MCD_ABI_VERSION 18
 
 enum {
   MCD_OK = 0,
@@ -297,6 +297,14 @@ int mcd_diff2d_fwd(const void* a, const void* b, int f32, float* acc, float* sta
                    int device, void* stream);
 int mcd_diff2d_bwd(const void* a, const void* b, int f32, const float* gscale, const float* stats, void* da,
                    void* db, int N, int C, int H, int W, int device, void* stream);
+/* The other discrepancy criteria of loss.py:68-171 (get_prob_distance_criterion: every name but 'diff'), forward and
+ * backward in one entry point.  mode 1: symkl / nmlsymkl / mysymkl = mean 0.5 (pa - pb)(log pa - log pb);
+ * mode 2: jsd = mean 0.5 [pa (log pa - log pm) + pb (log pb - log pm)], pm = softmax((a + b) / 2);
+ * mode 3: mis_symkl / spatial_jsd = mean 0.5 [pb (log pb - pa) + pa (log pa - pb)] (kl_div fed with probabilities).
+ * acc (may be NULL): acc[0] += sum over all elements (divide by N*C*H*W); da / db (may be NULL, dtype of a / b,
+ * overwritten) = gscale[0] * inv_numel * d(sum)/d(a|b), exact derivatives through both arguments. */
+int mcd_pairdist(int mode, const void* a, const void* b, int f32, float* acc, const float* gscale, void* da, void* db,
+                 float inv_numel, int N, int C, int H, int W, int device, void* stream);
 /* F.mse_loss(pred, target) with pred planar bf16 / fp32, target planar fp32: acc[0] += sum (p-t)^2 */
 int mcd_mse_fwd(const void* pred, int f32, const float* target, float* acc, int64_t numel, int device,
                 void* stream);

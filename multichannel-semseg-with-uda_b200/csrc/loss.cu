@@ -192,6 +192,107 @@ diff2d_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
   }
 }
 
+// ---- the other discrepancy criteria of loss.py:68-171 (get_prob_distance_criterion names other than 'diff'): all are
+// per-pixel functions of the two softmax distributions averaged over N*C*H*W elements.  With pa = softmax(a), la = log pa:
+//   MODE 1  symkl / nmlsymkl (Symkl2d :103-117) and mysymkl (MySymkl2d :141-151):  0.5 * sum_c (pa - pb)(la - lb)
+//           (the view(-1, n_target_ch) of Symkl2d regroups elements of an element-wise mean: no effect)
+//   MODE 2  jsd (JSD :79-90):  0.5 * sum_c [ pa (la - lm) + pb (lb - lm) ],  lm = log_softmax((a + b) / 2)
+//   MODE 3  mis_symkl (MisSymKLD :68-76) and spatial_jsd (SpatialJSD2d :154-170): F.kl_div fed with PROBABILITIES where it
+//           expects log-probabilities:  0.5 * sum_c [ pb (lb - pa) + pa (la - pb) ]
+// Gradients are the exact derivatives through both arguments (torch >= 1.x differentiates F.kl_div w.r.t. its target):
+//   1: da_c = 0.5 [ pa_c (la_c - lb_c) + pa_c - pb_c - pa_c KL(a||b) ]                    (db: a <-> b)
+//   2: da_c = 0.5 pa_c [ (la_c - lm_c) - KL(a||m) ] - 0.25 (pa_c + pb_c - 2 pm_c)        (db: a <-> b)
+//   3: da_c = 0.5 pa_c [ (la_c + 1 - 2 pb_c) - (sum_k pa_k la_k + 1 - 2 <pa, pb>) ]       (db: a <-> b)
+// Multi-pass over the channel planes of a pixel pair (the re-reads hit L1 / L2); these criteria are options of the
+// trainers (--d_loss), not the default path.
+struct PixSoft { float m, ls; };        // max and log(sum exp): log p_c = v_c - m - ls
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+pairdist_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ acc, const float* __restrict__ gscale,
+                T* __restrict__ da, T* __restrict__ db, float inv_numel, int C, int64_t HW, int64_t npairs) {
+  __shared__ float red[32];
+  const bool bwd = da != nullptr;
+  const float coef = bwd ? gscale[0] * inv_numel : 0.f;
+  float lsum = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i * 2;
+    const int64_t n = pix / HW, hw = pix % HW, off = n * C * HW + hw;
+    const T* pa = a + off;
+    const T* pb = b + off;
+    // pass 1: softmax statistics of a, b (and of m = (a + b) / 2 for the Jensen-Shannon form)
+    float ma[2] = {-INFINITY, -INFINITY}, mb[2] = {-INFINITY, -INFINITY}, mm[2] = {-INFINITY, -INFINITY};
+    for (int c = 0; c < C; ++c) {
+      const float2 va = ld2(pa + c * HW), vb = ld2(pb + c * HW);
+      ma[0] = fmaxf(ma[0], va.x); ma[1] = fmaxf(ma[1], va.y);
+      mb[0] = fmaxf(mb[0], vb.x); mb[1] = fmaxf(mb[1], vb.y);
+      if (MODE == 2) { mm[0] = fmaxf(mm[0], 0.5f * (va.x + vb.x)); mm[1] = fmaxf(mm[1], 0.5f * (va.y + vb.y)); }
+    }
+    float sa[2] = {0.f, 0.f}, sb[2] = {0.f, 0.f}, sm[2] = {0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float2 va = ld2(pa + c * HW), vb = ld2(pb + c * HW);
+      sa[0] += __expf(va.x - ma[0]); sa[1] += __expf(va.y - ma[1]);
+      sb[0] += __expf(vb.x - mb[0]); sb[1] += __expf(vb.y - mb[1]);
+      if (MODE == 2) { sm[0] += __expf(0.5f * (va.x + vb.x) - mm[0]); sm[1] += __expf(0.5f * (va.y + vb.y) - mm[1]); }
+    }
+    float lsa[2], lsb[2], lsm[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { lsa[h] = __logf(sa[h]); lsb[h] = __logf(sb[h]); lsm[h] = MODE == 2 ? __logf(sm[h]) : 0.f; }
+    // pass 2: the per-pixel scalars (loss term and the inner products the gradients need)
+    float t0[2] = {0.f, 0.f}, t1[2] = {0.f, 0.f}, t2[2] = {0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float2 va2 = ld2(pa + c * HW), vb2 = ld2(pb + c * HW);
+      const float va[2] = {va2.x, va2.y}, vb[2] = {vb2.x, vb2.y};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float la = va[h] - ma[h] - lsa[h], lb = vb[h] - mb[h] - lsb[h];
+        const float qa = __expf(la), qb = __expf(lb);
+        if (MODE == 1) { t0[h] += qa * (la - lb); t1[h] += qb * (lb - la); }            // KL(a||b), KL(b||a)
+        if (MODE == 2) {
+          const float lm = 0.5f * (va[h] + vb[h]) - mm[h] - lsm[h];
+          t0[h] += qa * (la - lm); t1[h] += qb * (lb - lm);                              // KL(a||m), KL(b||m)
+        }
+        if (MODE == 3) { t0[h] += qa * la; t1[h] += qb * lb; t2[h] += qa * qb; }         // -H(a), -H(b), <pa, pb>
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (MODE == 1 || MODE == 2) lsum += 0.5f * (t0[h] + t1[h]);
+      if (MODE == 3) lsum += 0.5f * (t0[h] + t1[h] - 2.f * t2[h]);
+    }
+    if (!bwd) continue;
+    // pass 3: gradients
+    for (int c = 0; c < C; ++c) {
+      const float2 va2 = ld2(pa + c * HW), vb2 = ld2(pb + c * HW);
+      const float va[2] = {va2.x, va2.y}, vb[2] = {vb2.x, vb2.y};
+      float ga[2], gb[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float la = va[h] - ma[h] - lsa[h], lb = vb[h] - mb[h] - lsb[h];
+        const float qa = __expf(la), qb = __expf(lb);
+        if (MODE == 1) {
+          ga[h] = 0.5f * (qa * (la - lb) + qa - qb - qa * t0[h]);
+          gb[h] = 0.5f * (qb * (lb - la) + qb - qa - qb * t1[h]);
+        } else if (MODE == 2) {
+          const float lm = 0.5f * (va[h] + vb[h]) - mm[h] - lsm[h];
+          const float mix = 0.25f * (qa + qb - 2.f * __expf(lm));
+          ga[h] = 0.5f * qa * ((la - lm) - t0[h]) - mix;
+          gb[h] = 0.5f * qb * ((lb - lm) - t1[h]) - mix;
+        } else {
+          ga[h] = 0.5f * qa * ((la + 1.f - 2.f * qb) - (t0[h] + 1.f - 2.f * t2[h]));
+          gb[h] = 0.5f * qb * ((lb + 1.f - 2.f * qa) - (t1[h] + 1.f - 2.f * t2[h]));
+        }
+      }
+      st2(da + off + c * HW, coef * ga[0], coef * ga[1]);
+      st2(db + off + c * HW, coef * gb[0], coef * gb[1]);
+    }
+  }
+  if (acc) {
+    const float r = block_sum(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(acc, r);
+  }
+}
+
 // ---- register-resident variants (C <= kRegC): a thread loads all channels of its pixel pair ONCE (C independent
 // 4-byte loads in flight per tensor), then max / sum-exp / loss / gradients come from registers: one pass over the
 // logits with no dependent re-reads.  Used for the MCD heads (C = 41); wider heads take the multi-pass kernels.
@@ -555,6 +656,17 @@ using namespace mcd;
 
 typedef __nv_bfloat16 bf16_t;
 
+template <typename T>
+static int launch_pairdist(int mode, const T* a, const T* b, float* acc, const float* gscale, T* da, T* db, float inv_numel,
+                           int C, int64_t HW, int64_t npairs, cudaStream_t st) {
+  const int grid = grid_for(npairs);
+  if (mode == 1) pairdist_kernel<T, 1><<<grid, 256, 0, st>>>(a, b, acc, gscale, da, db, inv_numel, C, HW, npairs);
+  else if (mode == 2) pairdist_kernel<T, 2><<<grid, 256, 0, st>>>(a, b, acc, gscale, da, db, inv_numel, C, HW, npairs);
+  else pairdist_kernel<T, 3><<<grid, 256, 0, st>>>(a, b, acc, gscale, da, db, inv_numel, C, HW, npairs);
+  return check_launch("pairdist");
+}
+
+
 extern "C" {
 
 int mcd_ce2d_fwd(const void* logits, int f32, const int64_t* target, const float* weight,
@@ -641,6 +753,22 @@ int mcd_diff2d_bwd(const void* a, const void* b, int f32, const float* gscale, c
                                                               (const float4*)stats, (bf16_t*)da, (bf16_t*)db, inv, C,
                                                               (int64_t)H * W, npairs);
   return check_launch("diff2d_bwd");
+}
+
+int mcd_pairdist(int mode, const void* a, const void* b, int f32, float* acc, const float* gscale, void* da, void* db,
+                 float inv_numel, int N, int C, int H, int W, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(a && b && (acc || da), "pairdist: null pointer");
+  MCD_REQUIRE(mode >= 1 && mode <= 3, "pairdist: mode %d (1 symmetric KL, 2 Jensen-Shannon, 3 kl_div on probabilities)", mode);
+  MCD_REQUIRE((da != nullptr) == (db != nullptr) && (!da || gscale), "pairdist: da, db and gscale go together");
+  MCD_CHECK_PLANAR("pairdist");
+  const int64_t HW = (int64_t)H * W, npairs = (int64_t)N * HW / 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f32)
+    return launch_pairdist<float>(mode, (const float*)a, (const float*)b, acc, gscale, (float*)da, (float*)db, inv_numel, C,
+                                  HW, npairs, st);
+  return launch_pairdist<bf16_t>(mode, (const bf16_t*)a, (const bf16_t*)b, acc, gscale, (bf16_t*)da, (bf16_t*)db, inv_numel,
+                                 C, HW, npairs, st);
 }
 
 int mcd_mse_fwd(const void* pred, int f32, const float* target, float* acc, int64_t numel, int device,

@@ -162,6 +162,80 @@ class Diff2d(nn.Module):
         return _Diff2dFn.apply(_logits(inputs1), _logits(inputs2))
 
 
+class _PairDistFn(torch.autograd.Function):
+    """mode 1 symmetric KL, 2 Jensen-Shannon, 3 kl_div on probabilities (ops.pairdist); mean or sum over elements"""
+
+    @staticmethod
+    def forward(ctx, a, b, mode, mean):
+        acc, _, _ = ops.pairdist(mode, a, b)
+        ctx.save_for_backward(a, b)
+        ctx.mode, ctx.inv = mode, (1.0 / float(a.numel()) if mean else 1.0)
+        return acc[0] * (ctx.inv / dp_world())
+
+    @staticmethod
+    def backward(ctx, go):
+        a, b = ctx.saved_tensors
+        _, da, db = ops.pairdist(ctx.mode, a, b, gscale=_share(go), inv_numel=ctx.inv, want_loss=False)
+        return da, db, None, None
+
+
+def _pairdist(mode, inputs1, inputs2, mean=True):
+    a, b = _logits(inputs1), _logits(inputs2)
+    if a.dtype != b.dtype:
+        a, b = a.float(), b.float()
+    return _PairDistFn.apply(a.contiguous(), b.contiguous(), mode, mean)
+
+
+class JSD(nn.Module):
+    """loss.py:79-90: 0.5 (kl_div(log_softmax(m), softmax(a)) + kl_div(log_softmax(m), softmax(b))), m = (a + b) / 2"""
+
+    def __init__(self, weight=None, size_average=True):
+        super().__init__()
+        self.weight, self.size_average = weight, size_average
+
+    def forward(self, inputs1, inputs2):
+        return _pairdist(2, inputs1, inputs2, self.size_average)
+
+
+class Symkl2d(nn.Module):
+    """loss.py:103-117: 0.5 (kl_div(log p1, p2) + kl_div(log p2, p1)); the view(-1, n_target_ch) of the reference only
+    regroups the elements of an element-wise mean / sum"""
+
+    def __init__(self, weight=None, n_target_ch=None, size_average=True):
+        super().__init__()
+        self.weight, self.size_average, self.n_target_ch = weight, size_average, n_target_ch
+
+    def forward(self, inputs1, inputs2):
+        return _pairdist(1, inputs1, inputs2, self.size_average)
+
+
+class MySymkl2d(nn.Module):
+    """loss.py:141-151: mean 0.5 (p1 log(p1 / p2) + p2 log(p2 / p1))"""
+
+    def __init__(self, weight=None, size_average=True):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, inputs1, inputs2):
+        return _pairdist(1, inputs1, inputs2)
+
+
+class MisSymKLD(nn.Module):
+    """loss.py:68-76 ("strange but somehow works well"): F.kl_div fed with probabilities where it expects
+    log-probabilities: mean 0.5 (p2 (log p2 - p1) + p1 (log p1 - p2))"""
+
+    def __init__(self, weight=None, size_average=True):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, inputs1, inputs2):
+        return _pairdist(3, inputs1, inputs2)
+
+
+class SpatialJSD2d(MisSymKLD):
+    """loss.py:154-170: the spatial views it builds are unused; what it returns is MisSymKLD's expression"""
+
+
 class _MSEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target):
@@ -236,9 +310,18 @@ def bce2d(input, target):
 
 
 def get_prob_distance_criterion(criterion_name, n_class=None):
+    if criterion_name == "jsd":
+        return JSD()
     if criterion_name == 'diff':
         return Diff2d()
-    if criterion_name in ("jsd", "symkl", "nmlsymkl", "mysymkl", "spatial_jsd", "mis_symkl"):
-        raise NotImplementedError("d_loss=%s is outside the libmcd_sm100 hot-path scope (default is 'diff')"
-                                  % criterion_name)
+    if criterion_name == "symkl":
+        return Symkl2d(n_target_ch=n_class)
+    if criterion_name == "nmlsymkl":
+        return Symkl2d(n_target_ch=n_class, size_average=True)
+    if criterion_name == "mysymkl":
+        return MySymkl2d()
+    if criterion_name == "spatial_jsd":
+        return SpatialJSD2d()
+    if criterion_name == 'mis_symkl':
+        return MisSymKLD()
     raise NotImplementedError()

@@ -447,7 +447,7 @@ def conv_fprop_act(x, w_packed, bias, g, res=None, relu=True, algo=None):
         abi.check(abi.lib().mcd_conv2d_fprop_act(_p(x), _p(w_packed), _p(bias), _p(res), int(relu), _p(z), _p(skp), _p(skf),
                                                  ctypes.byref(g), algo, _dev(x), _stream(x)), "conv2d_fprop_act")
         return z
-    return _profiled(0, g, run, False, algo)
+    return _profiled(0, g, run, False, algo, extras=res is not None)
 
 
 def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=None):
@@ -716,6 +716,20 @@ def diff2d_bwd(a, b, gscale, stats=None):
     return da, db
 
 
+def pairdist(mode, a, b, gscale=None, inv_numel=1.0, want_loss=True):
+    """the discrepancy criteria other than Diff2d (csrc/loss.cu pairdist_kernel): returns (acc | None, da | None,
+    db | None); gradients when `gscale` (device fp32 scalar) is given."""
+    n, c, h, w = a.shape
+    assert a.dtype == b.dtype and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    acc = zeros_f32(1, a.device) if want_loss else None
+    da = db = None
+    if gscale is not None:
+        da, db = torch.empty_like(a), torch.empty_like(b)
+    abi.check(abi.lib().mcd_pairdist(int(mode), _p(a), _p(b), _f32(a), _p(acc), _p(gscale), _p(da), _p(db),
+                                     float(inv_numel), n, c, h, w, _dev(a), _stream(a)), "pairdist")
+    return acc, da, db
+
+
 def mse_fwd(pred, target):
     acc = torch.zeros(1, dtype=F32, device=pred.device)
     abi.check(abi.lib().mcd_mse_fwd(_p(pred), _f32(pred), _p(target), _p(acc), pred.numel(), _dev(pred),
@@ -840,11 +854,16 @@ def conv_kernel_name(g, pass_, planar=False, algo=None):
     return name % bn if "%d" in name else name
 
 
-def _profiled(pass_, g, fn, planar=False, algo=None):
+def _profiled(pass_, g, fn, planar=False, algo=None, extras=False):
+    """extras: the call uses the epilogue inputs (addend / ReLU mask / BatchNorm-backward sums).  Records are keyed by
+    the kernel INSTANTIATION that runs - what an ncu launch list shows - not by the pass: a dgrad without epilogue
+    inputs runs the forward instantiation, the folded inference unit with a residual the dgrad-epilogue one."""
     prof = ConvProfiler.active
     if prof is None:
         return fn()
-    name = conv_kernel_name(g, pass_, planar, algo) + (" [fprop]", " [dgrad]", "")[pass_]
+    name = conv_kernel_name(g, pass_, planar, algo)
+    if pass_ < 2:
+        name += " [dgrad-epilogue inst.]" if extras else " [forward inst.]"
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     out = fn()
@@ -862,7 +881,8 @@ def conv_fprop(x, w_packed, bias, g, planar=False, want_stats=False, algo=None):
 
 
 def conv_dgrad(dy, w_packed_dgrad, g, algo=None, add=None, relu_src=None, bn_y=None):  # noqa: F811
-    return _profiled(1, g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add, relu_src, bn_y), False, algo)
+    return _profiled(1, g, lambda: _conv_dgrad_raw(dy, w_packed_dgrad, g, algo, add, relu_src, bn_y), False, algo,
+                     extras=add is not None or relu_src is not None or bn_y is not None)
 
 
 def conv_wgrad(x, dy, g, want_dbias=False, algo=None, out_dw=None, out_db=None, accumulate=False,  # noqa: F811

@@ -49,7 +49,7 @@ def _he_init(conv):
 def _trunk(model_name, pretrained, input_ch):
     factory = drn.__dict__.get(model_name)
     if factory is None:
-        raise NotImplementedError("%s: only drn_d_22 / drn_d_38 are built on libmcd_sm100" % model_name)
+        raise NotImplementedError("%s: only drn_d_22 / _38 / _54 / _105 are built on libmcd_sm100" % model_name)
     return factory(pretrained=pretrained, num_classes=1000, input_ch=input_ch)
 
 

@@ -1,12 +1,13 @@
-"""Dilated Residual Network, arch 'D' with BasicBlock (DRN-D-22 / DRN-D-38) on libmcd_sm100.
+"""Dilated Residual Network, arch 'D' (BasicBlock: DRN-D-22 / -38; Bottleneck: DRN-D-54 / -105) on libmcd_sm100.
 
 Drop-in for the reference's models/drn.py on the MCD hot path: same factory names, constructor
 arguments, module tree and therefore the same state_dict keys (reference models/drn.py:103-253 DRN,
 :26-59 BasicBlock, :256-299 replace_first_conv, :323-334 drn_d_22 / drn_d_38).  Convolutions,
-BatchNorm, ReLU and the residual add run as fused library kernels on bf16 NHWC activations.
+BatchNorm, ReLU and the residual add run as fused library kernels on 16-bit NHWC activations.  Bottleneck
+(:62-100) and drn_d_54 / drn_d_105 (:337-348) are the SURVEY 8(f) rank-4 widening: same units, 1x1 / 3x3 / 1x1.
 
-Out of scope here: arch 'C', Bottleneck variants (drn_c_*, drn_d_54/105) and the
-model-zoo download (`pretrained=True`), which raise NotImplementedError.
+Out of scope here: arch 'C' (drn_c_*, no reference trainer uses it) and the
+model-zoo download (`pretrained=True`, no network: see _load_pretrained).
 """
 import math
 
@@ -14,7 +15,7 @@ import torch.nn as nn
 
 from mcd_b200.nn import BatchNorm2d, Conv2d, ConvBNReLU, conv_bn_act
 
-__all__ = ['DRN', 'BasicBlock', 'drn_d_22', 'drn_d_38', 'replace_first_conv']
+__all__ = ['DRN', 'BasicBlock', 'Bottleneck', 'drn_d_22', 'drn_d_38', 'drn_d_54', 'drn_d_105', 'replace_first_conv']
 
 # stage -> (channels, dilation) of DRN-D; stages 3..6 are residual, 0..2 and 7..8 plain conv stacks
 _CHANNELS = (16, 32, 64, 128, 256, 512, 512, 512)
@@ -58,12 +59,42 @@ class BasicBlock(nn.Module):
         return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x, sole=True)
 
 
+class Bottleneck(nn.Module):
+    """1x1 conv-bn-relu, 3x3 (dilated) conv-bn-relu, 1x1 conv-bn (+identity | +bn(1x1 conv)) -relu, output width
+    4 x planes (reference models/drn.py:62-100; DRN-D-54 / -105).  `residual` is accepted and ignored like there."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=(1, 1), residual=True):
+        super().__init__()
+        self.conv1 = Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = BatchNorm2d(planes)
+        self.conv2 = Conv2d(planes, planes, kernel_size=3, stride=stride, padding=dilation[1], bias=False,
+                            dilation=dilation[1])
+        self.bn2 = BatchNorm2d(planes)
+        self.conv3 = Conv2d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)  # parameter-free; kept for module-tree parity
+        self.downsample = downsample
+        self.stride = stride
+        self.inner_input = False
+
+    def forward(self, x):
+        sole = (self.inner_input or getattr(x, "_mcd_sole", False)) and self.downsample is None
+        out = conv_bn_act(self.conv1, self.bn1, x, relu=True, sole=sole)
+        out = conv_bn_act(self.conv2, self.bn2, out, relu=True, sole=True)
+        if self.downsample is not None:
+            ds_conv, ds_bn = self.downsample[0], self.downsample[1]
+            return conv_bn_act(self.conv3, self.bn3, out, relu=True, res=x, res_conv=ds_conv, res_bn=ds_bn, sole=True)
+        x._mcd_shortcut = True
+        return conv_bn_act(self.conv3, self.bn3, out, relu=True, res=x, sole=True)
+
+
 class DRN(nn.Module):
     def __init__(self, block, layers, num_classes=1000, channels=_CHANNELS, out_map=False,
                  out_middle=False, pool_size=28, arch='D'):
         super().__init__()
-        if arch != 'D' or block is not BasicBlock:
-            raise NotImplementedError("libmcd_sm100 build covers DRN arch 'D' with BasicBlock only")
+        if arch != 'D' or block not in (BasicBlock, Bottleneck):
+            raise NotImplementedError("libmcd_sm100 build covers DRN arch 'D' (BasicBlock / Bottleneck) only")
         self.inplanes = channels[0]
         self.out_map = out_map
         self.out_dim = channels[-1]
@@ -179,8 +210,8 @@ def _load_pretrained(model, name):
                       "random He-normal initialisation" % name)
 
 
-def _build(name, layers, pretrained, input_ch, **kwargs):
-    model = DRN(BasicBlock, layers, arch='D', **kwargs)
+def _build(name, layers, pretrained, input_ch, block=BasicBlock, **kwargs):
+    model = DRN(block, layers, arch='D', **kwargs)
     if pretrained:
         _load_pretrained(model, name)
     return replace_first_conv(model, input_ch=input_ch, arch="D")
@@ -192,3 +223,11 @@ def drn_d_22(pretrained=False, input_ch=3, **kwargs):
 
 def drn_d_38(pretrained=False, input_ch=3, **kwargs):
     return _build("drn_d_38", [1, 1, 3, 4, 6, 3, 1, 1], pretrained, input_ch, **kwargs)
+
+
+def drn_d_54(pretrained=False, input_ch=3, **kwargs):
+    return _build("drn_d_54", [1, 1, 3, 4, 6, 3, 1, 1], pretrained, input_ch, block=Bottleneck, **kwargs)
+
+
+def drn_d_105(pretrained=False, input_ch=3, **kwargs):
+    return _build("drn_d_105", [1, 1, 3, 4, 23, 3, 1, 1], pretrained, input_ch, block=Bottleneck, **kwargs)

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 from torch.nn.modules.batchnorm import _BatchNorm
 
-_DRN_NAMES = ("drn_d_22", "drn_d_38")
+_DRN_NAMES = ("drn_d_22", "drn_d_38", "drn_d_54", "drn_d_105")
 
 
 def _check_drn(net_name):

@@ -31,7 +31,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-LAYERS = {"drn_d_22": [1, 1, 2, 2, 2, 2, 1, 1], "drn_d_38": [1, 1, 3, 4, 6, 3, 1, 1]}
+LAYERS = {"drn_d_22": [1, 1, 2, 2, 2, 2, 1, 1], "drn_d_38": [1, 1, 3, 4, 6, 3, 1, 1],
+          "drn_d_54": [1, 1, 3, 4, 6, 3, 1, 1], "drn_d_105": [1, 1, 3, 4, 23, 3, 1, 1]}
+BOTTLENECK = ("drn_d_54", "drn_d_105")            # models/drn.py:337-348: Bottleneck blocks, expansion 4
 CHANNELS = (16, 32, 64, 128, 256, 512, 512, 512)
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
@@ -40,8 +42,10 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 # architecture description (models/drn.py:103-205): a list of stages; each stage is a list of units
 #   ("cbr", key_conv, key_bn, stride, dil)                               conv3x3/7x7 + BN + ReLU
 #   ("block", prefix, stride, dil1, dil2, has_downsample)                 BasicBlock
+#   ("bneck", prefix, stride, dil1, dil2, has_downsample)                 Bottleneck (1x1, 3x3 dilation dil2, 1x1 x4)
 def trunk_spec(name="drn_d_38", prefix="base."):
     layers = LAYERS[name]
+    kind, exp = ("bneck", 4) if name in BOTTLENECK else ("block", 1)
     spec = [[("cbr", "%s0.0" % prefix, "%s0.1" % prefix, 1, 1, 3)]]          # 7x7 pad 3
     inplanes = CHANNELS[0]
 
@@ -57,12 +61,12 @@ def trunk_spec(name="drn_d_38", prefix="base."):
     def block_stack(idx, planes, blocks, stride=1, dilation=1, new_level=True):
         nonlocal inplanes
         units = []
-        ds = stride != 1 or inplanes != planes
+        ds = stride != 1 or inplanes != planes * exp
         d0 = (1, 1) if dilation == 1 else ((dilation // 2 if new_level else dilation), dilation)
-        units.append(("block", "%s%d.0" % (prefix, idx), stride, d0[0], d0[1], ds))
-        inplanes = planes
+        units.append((kind, "%s%d.0" % (prefix, idx), stride, d0[0], d0[1], ds))
+        inplanes = planes * exp
         for b in range(1, blocks):
-            units.append(("block", "%s%d.%d" % (prefix, idx, b), 1, dilation, dilation, False))
+            units.append((kind, "%s%d.%d" % (prefix, idx, b), 1, dilation, dilation, False))
         return units
 
     spec.append(conv_stack(1, CHANNELS[0], layers[0], stride=1))
@@ -150,6 +154,22 @@ def unit_forward(sd, unit, x, bn_train=True, taps=None):
             taps[kc + ":out"] = out
         return out
     _, p, stride, d1, d2, ds = unit
+    if unit[0] == "bneck":          # Bottleneck.forward, models/drn.py:80-100
+        y1 = _q(F.conv2d(x, _qw(sd[p + ".conv1.weight"])), "y")
+        o = _q(F.relu(_bn(sd, p + ".bn1", y1, bn_train)))
+        y2 = _q(F.conv2d(o, _qw(sd[p + ".conv2.weight"]), None, stride, d2, d2), "y")
+        o = _q(F.relu(_bn(sd, p + ".bn2", y2, bn_train)))
+        y3 = _q(F.conv2d(o, _qw(sd[p + ".conv3.weight"])), "y")
+        o = _bn(sd, p + ".bn3", y3, bn_train)
+        res = x
+        if ds:
+            yd = _q(F.conv2d(x, _qw(sd[p + ".downsample.0.weight"]), None, stride, 0, 1), "y")
+            res = _bn(sd, p + ".downsample.1", yd, bn_train)
+        out = _q(F.relu(o + res))
+        if taps is not None:
+            taps[p + ".conv1:conv"], taps[p + ".conv2:conv"], taps[p + ".conv3:conv"] = y1, y2, y3
+            taps[p + ":out"] = out
+        return out
     y1 = _q(F.conv2d(x, _qw(sd[p + ".conv1.weight"]), None, stride, d1, d1), "y")
     o = _q(F.relu(_bn(sd, p + ".bn1", y1, bn_train)))
     y2 = _q(F.conv2d(o, _qw(sd[p + ".conv2.weight"]), None, 1, d2, d2), "y")
@@ -321,6 +341,18 @@ def init_trunk(name="drn_d_38", input_ch=3, prefix="base.", gen=None):
                 _, p, stride, d1, d2, ds = unit
                 idx = int(p[len(prefix):].split(".")[0])
                 planes = CHANNELS[idx - 1]
+                if unit[0] == "bneck":
+                    sd[p + ".conv1.weight"] = _he_normal((planes, cin, 1, 1), gen)
+                    _bn_state(sd, p + ".bn1", planes)
+                    sd[p + ".conv2.weight"] = _he_normal((planes, planes, 3, 3), gen)
+                    _bn_state(sd, p + ".bn2", planes)
+                    sd[p + ".conv3.weight"] = _he_normal((4 * planes, planes, 1, 1), gen)
+                    _bn_state(sd, p + ".bn3", 4 * planes)
+                    if ds:
+                        sd[p + ".downsample.0.weight"] = _he_normal((4 * planes, cin, 1, 1), gen)
+                        _bn_state(sd, p + ".downsample.1", 4 * planes)
+                    cin = 4 * planes
+                    continue
                 sd[p + ".conv1.weight"] = _he_normal((planes, cin, 3, 3), gen)
                 _bn_state(sd, p + ".bn1", planes)
                 sd[p + ".conv2.weight"] = _he_normal((planes, planes, 3, 3), gen)
@@ -717,3 +749,27 @@ def resize_nearest(lbl_u8, size):
         return np.array(tab)
     h, w = lbl_u8.shape
     return lbl_u8[table(h, size[1])][:, table(w, size[0])]
+
+
+# ---- the other discrepancy criteria (loss.py:68-171; get_prob_distance_criterion names) ---------------------------
+def _kl_div(inp, target, mean=True):
+    """F.kl_div(input, target) of torch: target * (log(target) - input), 0 where target == 0; element mean or sum"""
+    out = torch.xlogy(target, target) - target * inp
+    return out.mean() if mean else out.sum()
+
+
+def pair_distance(name, a, b, size_average=True):
+    pa, pb = F.softmax(a, dim=1), F.softmax(b, dim=1)
+    la, lb = F.log_softmax(a, dim=1), F.log_softmax(b, dim=1)
+    if name == "diff":
+        return diff2d(a, b)
+    if name in ("symkl", "nmlsymkl"):                    # loss.py:103-117
+        return 0.5 * (_kl_div(la, pb, size_average) + _kl_div(lb, pa, size_average))
+    if name == "mysymkl":                                # loss.py:141-151
+        return torch.mean(0.5 * (pa * torch.log(pa / pb) + pb * torch.log(pb / pa)))
+    if name == "jsd":                                    # loss.py:79-90
+        lm = F.log_softmax(0.5 * (a + b), dim=1)
+        return 0.5 * (_kl_div(lm, pa, size_average) + _kl_div(lm, pb, size_average))
+    if name in ("mis_symkl", "spatial_jsd"):             # loss.py:68-76,154-170: kl_div fed with probabilities
+        return 0.5 * (_kl_div(pa, pb) + _kl_div(pb, pa))
+    raise NotImplementedError(name)

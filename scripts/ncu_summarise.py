@@ -75,7 +75,7 @@ def main():
                     v, u = float(r[idx[c]].replace(",", "")), units[idx[c]].lower()
                     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
                 t = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
-                ent = traffic.setdefault(kname.split(" [")[0], {"dram_bytes_per_launch": [], "grid": []})
+                ent = traffic.setdefault(kname, {"dram_bytes_per_launch": [], "grid": []})   # per instantiation
                 ent["dram_bytes_per_launch"].append(t)
                 ent["grid"].append(r[idx["Grid Size"]])
             except (KeyError, ValueError):

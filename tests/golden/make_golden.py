@@ -450,6 +450,44 @@ def golden_pipeline():
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
 
 
+def golden_discrepancies():
+    """every name get_prob_distance_criterion (loss.py:192-210) knows, from the reference's own classes: value and the
+    gradients w.r.t. both logit tensors (torch 2.x differentiates F.kl_div through its target as well)."""
+    from loss import get_prob_distance_criterion
+    g = torch.Generator().manual_seed(505)
+    a0 = torch.randn(2, N_CLASS, 6, 8, generator=g) * 2.5
+    b0 = a0 + torch.randn(2, N_CLASS, 6, 8, generator=g) * 1.5
+    out = {"a": a0.numpy(), "b": b0.numpy()}
+    for name in ("diff", "jsd", "symkl", "nmlsymkl", "mysymkl", "spatial_jsd", "mis_symkl"):
+        a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        v = get_prob_distance_criterion(name, N_CLASS)(a, b)
+        v.backward()
+        out[name] = float(v)
+        out[name + "_da"], out[name + "_db"] = a.grad.numpy(), b.grad.numpy()
+        print("discrepancy %-12s %.8e" % (name, float(v)))
+    np.savez_compressed(os.path.join(HERE, "discrepancies.npz"), **out)
+
+
+def golden_bottleneck():
+    """DRN-D-54 (Bottleneck blocks, models/drn.py:62-100,337-341) through the reference's DRNSegBase: train-mode forward
+    and the gradient norms of a quadratic objective, plus the BatchNorm bookkeeping of one forward."""
+    from models.dilated_fcn import DRNSegBase
+    torch.manual_seed(0)
+    ref = DRNSegBase("drn_d_54", N_CLASS, pretrained=False, input_ch=6)
+    G = O.fill_state_dict_(O.init_seg_base("drn_d_54", 6, N_CLASS), 54)
+    assert set(G) == set(ref.state_dict())
+    ref.load_state_dict({k: v.clone() for k, v in G.items()})
+    ref.train()
+    x = torch.randn(2, 6, 64, 96, generator=torch.Generator().manual_seed(540))
+    feat = ref(x)
+    feat.square().mean().backward()
+    gk, gn = norms({k: p.grad for k, p in ref.named_parameters()})
+    sk, sv = summarize(ref.state_dict())
+    np.savez_compressed(os.path.join(HERE, "drn_d_54.npz"), feat=feat.detach().numpy(), grad_keys=np.array(gk),
+                        grad_norms=gn, state_keys=np.array(sk), state_sums=sv)
+    print("drn_d_54: %d state entries, feat norm %.6f" % (len(G), float(feat.norm())))
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
     torch.set_num_threads(8)
@@ -460,3 +498,5 @@ if __name__ == "__main__":
     golden_triple()
     golden_iterations()
     golden_pipeline()
+    golden_discrepancies()
+    golden_bottleneck()

@@ -355,6 +355,40 @@ def test_diff2d(cuda_dev):
     assert rel_err(ao.grad, ar.grad) < 1e-2 and rel_err(bo.grad, br.grad) < 1e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, BF16])
+@pytest.mark.parametrize("name", ["jsd", "symkl", "nmlsymkl", "mysymkl", "spatial_jsd", "mis_symkl"])
+def test_discrepancy_criteria(cuda_dev, name, dtype):
+    """every get_prob_distance_criterion name besides 'diff' (loss.py:68-171, csrc/loss.cu pairdist_kernel) against the
+    oracle restatement (pinned to the reference's classes by tests/golden/discrepancies.npz): the committed golden
+    inputs in fp32, and a ragged full-width case with bf16 logits (gradients rounded to bf16: 1e-2 of max)."""
+    import os
+    import numpy as np
+    from oracle import mcd_oracle as O
+    from loss import get_prob_distance_criterion
+    crit = get_prob_distance_criterion(name, 41)
+    if dtype == torch.float32:
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "discrepancies.npz"))
+        a = torch.from_numpy(d["a"]).to(cuda_dev).requires_grad_(True)
+        b = torch.from_numpy(d["b"]).to(cuda_dev).requires_grad_(True)
+        v = crit(a, b)
+        (3.0 * v).backward()
+        assert abs(float(v) - float(d[name])) <= 2e-5 * abs(float(d[name])), (float(v), float(d[name]))
+        ga, gb = torch.from_numpy(d[name + "_da"]).to(cuda_dev), torch.from_numpy(d[name + "_db"]).to(cuda_dev)
+        assert rel_err(a.grad / 3.0, ga) < 1e-4 and rel_err(b.grad / 3.0, gb) < 1e-4
+        return
+    torch.manual_seed(9)
+    a = bf16_round(torch.randn(3, 41, 10, 36) * 2).to(cuda_dev)
+    b = bf16_round(a.cpu() + torch.randn(3, 41, 10, 36)).to(cuda_dev)
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = O.pair_distance(name, ar, br)
+    ref.backward()
+    ao, bo = a.to(BF16).requires_grad_(True), b.to(BF16).requires_grad_(True)
+    got = crit(ao, bo)
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 1e-4 * abs(float(ref))
+    assert ao.grad.dtype == BF16 and rel_err(ao.grad, ar.grad) < 1e-2 and rel_err(bo.grad, br.grad) < 1e-2
+
+
 def test_mse_and_boundary_bce(cuda_dev):
     import loss as L
     torch.manual_seed(5)

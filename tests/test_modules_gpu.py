@@ -4,6 +4,7 @@ and the tcgen05 path agrees with the CUDA-core cross-check kernels end to end.
 Element-wise agreement after 41 chaotic layers is not expected between ANY two bf16 implementations (see
 tests/test_parity_gpu.py); the losses, which average over all pixels, agree tightly and the gradients agree
 norm-wise."""
+import os
 import warnings
 
 import pytest
@@ -162,6 +163,7 @@ def test_eval_units_fold_batchnorm_into_the_convolution(cuda_dev):
 
     g.eval()
     two_pass, n_two = run(False)
+    run(True)                         # first folded run also builds the folded weight packs (41 pack launches)
     folded, n_fold = run(True)
     # two different placements of the IEEE-half roundings (folded: weights * scale rounded once, no pre-BatchNorm
     # tensor; two-pass: y rounded, then normalised): at random weights DRN-D-38 amplifies such a perturbation ~1.2x per
@@ -197,3 +199,56 @@ def test_eval_units_fold_batchnorm_into_the_convolution(cuda_dev):
     a, _ = run(True)
     b, _ = run(False)
     assert float((a - b).abs().max() / b.abs().max()) <= tol
+
+
+@pytest.mark.parametrize("name,n_state", [("drn_d_54", 344), ("drn_d_22", 152)])
+def test_other_drn_depths_vs_oracle(cuda_dev, name, n_state):
+    """get_models(net_name=...) for the other DRN-D depths (models/drn.py:323-348): DRN-D-54's Bottleneck blocks
+    (1x1 -> 3x3 dilated -> 1x1 x4, widths up to 2048) and DRN-D-22, against the oracle restatement (Bottleneck pinned to
+    the reference by tests/golden/drn_d_54.npz): train-mode forward, parameter gradients of a quadratic objective,
+    BatchNorm running statistics, and the folded inference forward."""
+    from oracle import mcd_oracle as O
+    from models.model_util import get_models
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g = get_models(name, 6, 41)[0].to(cuda_dev).train()
+    G = O.to_device(O.fill_state_dict_(O.init_seg_base(name, 6, 41), 54), cuda_dev)
+    assert len(G) == n_state and set(G) == set(g.state_dict())
+    g.load_state_dict({k: v.clone() for k, v in G.items()})
+    x = torch.randn(2, 6, 128, 160, generator=torch.Generator().manual_seed(540)).to(cuda_dev)
+    feat = g(x)
+    feat.float().square().mean().backward()
+    O._req([G], True)
+    ref = O.seg_base_forward(G, x, name=name)
+    gr = O._grads(ref.square().mean(), [G])[0]
+    with O.storage(torch.float16, grad=torch.bfloat16):
+        G2 = O.to_device(O.fill_state_dict_(O.init_seg_base(name, 6, 41), 54), cuda_dev)
+        O._req([G2], True)
+        ref16 = O.seg_base_forward(G2, x, name=name)
+        gr16 = O._grads(ref16.square().mean(), [G2])[0]
+    err = float((feat.float() - ref).abs().max() / ref.abs().max())
+    err16 = float((feat.float() - ref16).abs().max() / ref16.abs().max())
+    e32, e16 = [], []
+    for k, p in g.named_parameters():
+        e32.append(float((p.grad - gr[k]).norm()) / (float(gr[k].norm()) + 1e-20))
+        e16.append(float((p.grad - gr16[k]).norm()) / (float(gr16[k].norm()) + 1e-20))
+    e32, e16 = torch.tensor(e32), torch.tensor(e16)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_other_depths.txt"), "a") as f:
+            f.write("%s: feat vs fp32 %.3e vs same-storage %.3e | param-grad rel-L2 vs fp32 median %.3e max %.3e | vs "
+                    "same-storage median %.3e max %.3e\n" % (name, err, err16, float(e32.median()), float(e32.max()),
+                                                            float(e16.median()), float(e16.max())))
+    # end-to-end drift of a random-weight network (every unit is tested in isolation at 2e-2 by test_parity_gpu.py):
+    # the whole-trunk budget of DESIGN.md section 6; a wrong kernel gives O(1) here
+    assert err <= 6e-2 and err16 <= 6e-2, (err, err16)
+    assert float(e16.median()) <= 6e-2 and float(e32.median()) <= 6e-2 and float(e32.max()) <= 0.5, (e32.max(), e16.max())
+    bn = g.base[6][0].bn2
+    key = "base.6.0.bn2"
+    assert int(bn.num_batches_tracked) == 1
+    assert float((bn.running_var - G[key + ".running_var"]).abs().max() / G[key + ".running_var"].abs().max()) <= 2e-2
+    g.eval()
+    with torch.no_grad():
+        out = g(x).float()
+        ref_e = O.seg_base_forward(G, x, name=name, train=False)
+    assert float((out - ref_e).abs().max() / ref_e.abs().max()) <= 6e-2

@@ -238,3 +238,37 @@ def test_oracle_nearest_resize_matches_pil():
         m = rng.randint(0, 41, (ih, iw)).astype(np.uint8)
         ref = np.array(Image.fromarray(m).resize((ow, oh), Image.NEAREST))
         assert np.array_equal(O.resize_nearest(m, (ow, oh)), ref), ((ih, iw), (oh, ow))
+
+
+DISCREPANCIES = ("diff", "jsd", "symkl", "nmlsymkl", "mysymkl", "spatial_jsd", "mis_symkl")
+
+
+@pytest.mark.parametrize("name", DISCREPANCIES)
+def test_oracle_discrepancy_criteria_match_reference(name):
+    """loss.py:68-171 through get_prob_distance_criterion of the real reference (tests/golden/discrepancies.npz)"""
+    d = np.load(os.path.join(GOLD, "discrepancies.npz"))
+    a = torch.from_numpy(d["a"]).requires_grad_(True)
+    b = torch.from_numpy(d["b"]).requires_grad_(True)
+    v = O.pair_distance(name, a, b)
+    v.backward()
+    assert abs(float(v) - float(d[name])) <= 1e-6 * abs(float(d[name]))
+    close(a.grad.numpy(), d[name + "_da"], rtol=1e-5, atol=1e-12)
+    close(b.grad.numpy(), d[name + "_db"], rtol=1e-5, atol=1e-12)
+
+
+def test_oracle_bottleneck_trunk_matches_reference():
+    """DRN-D-54 (Bottleneck, models/drn.py:62-100) restated in the oracle vs the reference's DRNSegBase("drn_d_54")"""
+    d = np.load(os.path.join(GOLD, "drn_d_54.npz"))
+    G = O.fill_state_dict_(O.init_seg_base("drn_d_54", 6, N_CLASS), 54)
+    assert len(G) == 344
+    O._req([G], True)
+    x = torch.randn(2, 6, 64, 96, generator=torch.Generator().manual_seed(540))
+    feat = O.seg_base_forward(G, x, name="drn_d_54")
+    close(feat.detach().numpy(), d["feat"], rtol=1e-5)
+    grads = O._grads(feat.square().mean(), [G])[0]
+    keys = [str(k) for k in d["grad_keys"]]
+    got = np.array([float(grads[k].norm()) for k in keys])
+    close(got, d["grad_norms"], rtol=2e-4)
+    sk = [str(k) for k in d["state_keys"]]
+    got_s = np.array([[float(G[k].detach().double().sum()), float(G[k].detach().double().norm())] for k in sk])
+    close(got_s, d["state_sums"], rtol=1e-5)          # incl. the running statistics after one train-mode forward
