@@ -463,6 +463,8 @@ static inline int rows_grid(int64_t P, int Cs, int rows_per_thread, int max_bloc
 
 int bn_stats_launch(const void* y, float* stats, int64_t P, int C, int Cs, cudaStream_t st) {
   int grid = rows_grid(P, Cs, 8, 148 * 3);
+  // (Bottleneck trunks reach 2048 channels: 7 * 2048 floats = 56 KB of dynamic shared memory, above the 48 KB default)
+  if (ensure_dyn_smem<bn_reduce_kernel<0>>(7 * Cs * (int)sizeof(float), "bn_stats") != MCD_OK) return MCD_E_CUDA;
   bn_reduce_kernel<0><<<grid, 256, 7 * Cs * sizeof(float), st>>>(
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stats, P,
       C, Cs);
@@ -558,6 +560,7 @@ int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhw
   MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_bwd_reduce: needs dense channels (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!res_mean || (res_nhwc && res_rstd), "bn_bwd_reduce: residual stats without residual");
   int grid = rows_grid(P, Cs, 8, 148 * 2);     // two resident blocks per SM (launch bounds): one full wave
+  if (ensure_dyn_smem<bn_reduce_kernel<1>>(7 * Cs * (int)sizeof(float), "bn_bwd_reduce") != MCD_OK) return MCD_E_CUDA;
   bn_reduce_kernel<1><<<grid, 256, 7 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y_nhwc, (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc,
       (const __nv_bfloat16*)res_nhwc, mean, rstd, res_mean, res_rstd, relu, sums, P, C, Cs);
@@ -583,6 +586,7 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
   BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
   MCD_REQUIRE(Cs <= 2048, "bn_bwd_apply: channel stride %d unsupported", Cs);
   int grid = rows_grid(P, Cs, 4, 148 * 6);
+  if (ensure_dyn_smem<bn_bwd_apply_kernel>(6 * Cs * (int)sizeof(float), "bn_bwd_apply") != MCD_OK) return MCD_E_CUDA;
   bn_bwd_apply_kernel<<<grid, 256, 6 * Cs * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dz_nhwc, (const __nv_bfloat16*)z_nhwc, (const __nv_bfloat16*)y_nhwc, b1, sums,
       relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, (const __nv_bfloat16*)res_nhwc, b2,
