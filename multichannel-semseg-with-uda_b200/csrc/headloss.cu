@@ -165,6 +165,12 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
       v0[c] = s0;
       if (MODE == 1) v1[c] = s1;
     }
+#if defined(HL_EXP) && HL_EXP == 1
+    { float t = 0.f;
+#pragma unroll
+      for (int c = 0; c < HL_MAXC; ++c) t += (c < C ? v0[c] : 0.f) + (MODE == 1 && c < C ? v1[c] : 0.f);
+      loss_acc += t; continue; }
+#endif
     // cross entropy: the label and its raw logit (before the logits are overwritten by their exponentials)
     float wy = 0.f, xy = 0.f;
     int y = -1;
@@ -217,6 +223,12 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
         v1[c] = kk * pb * (db - s);
       }
     }
+#if defined(HL_EXP) && HL_EXP == 2
+    { float t = 0.f;
+#pragma unroll
+      for (int c = 0; c < HL_MAXC; ++c) t += v0[c] + (MODE == 1 ? v1[c] : 0.f);
+      loss_acc += t * 1e-30f; continue; }
+#endif
     if (!a.want_grad) continue;
     // logit gradients -> shared memory (bf16, [head][c][pos][cell]); invalid pixels contribute zeros
 #pragma unroll
@@ -227,6 +239,9 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
       }
     }
     __syncthreads();
+#if defined(HL_EXP) && HL_EXP == 3
+    continue;
+#endif
     // ---- phase 2a: score-map gradients.  Work unit (channel c, quarter of the 64 positions): the 4 cells x 4 taps
     //      partial sums over its 16 positions (one 8-byte load = the logit gradient of a position in all 4 cells, one
     //      16-byte load = its 4 filter taps), added to the item's 2 x 5 score-map gradient tile: tap (a, b) of cell
