@@ -60,7 +60,11 @@ struct HeadLossArgs {
 __device__ __forceinline__ void sm_add(float* p, float v) { atomicAdd(p, v); }
 
 // DWN: number of (head, input) pairs whose filter gradient is accumulated in registers (0 = none wanted)
-template <int MODE, bool BILINEAR, int DWN>
+// CT / NIT: class count and inputs per head as COMPILE-TIME constants (0 = take them from the arguments).  The kernel is
+// issue-bound and, with run-time C and nin, two thirds of the instructions of its inner loops were integer address
+// arithmetic and bounds predicates (scripts/gpu_hl_exp.sh: 41 x 2 x (2 loads + 4 FMAs) cost 1400 instructions per thread);
+// with CT = 41, NIT = 1 (every MCD head of the reference) the shared-memory offsets become immediates.
+template <int MODE, bool BILINEAR, int DWN, int CT, int NIT>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
   constexpr bool DW = DWN > 0;
@@ -71,9 +75,10 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
   __nv_bfloat16* dls = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<float*>(hl_smem) + a.off_dl);   // [head][C][pos][cell]
   float* dxs = reinterpret_cast<float*>(hl_smem) + a.off_dx;    // [head][in][C][2 rows][5 cols] score-map gradients of this item
   __shared__ float red[32];
-  const int C = a.C, h = a.h, w = a.w, H = 8 * a.h, W = 8 * a.w;
+  const int C = CT > 0 ? CT : a.C, h = a.h, w = a.w, H = 8 * a.h, W = 8 * a.w;
   const int tid = threadIdx.x, q = tid >> 6, pos = tid & 63, kh0 = pos >> 3, kw0 = pos & 7;
-  const int NH = a.nheads, NI = a.nin;
+  constexpr int NH = MODE == 1 ? 2 : 1;
+  const int NI = NIT > 0 ? NIT : a.nin;
 
   // ---- filters -> shared memory [c][pos][tap], tap = 2a + b <-> (kh0 + 8a, kw0 + 8b)
   if (!BILINEAR) {
@@ -234,8 +239,9 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
 #pragma unroll
     for (int c = 0; c < HL_MAXC; ++c) {
       if (c < C) {
-        dls[(0 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(pvalid ? v0[c] : 0.f);
-        if (MODE == 1) dls[(1 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(pvalid ? v1[c] : 0.f);
+        // (pixels outside the image already hold zeros: no label / k = 0 above)
+        dls[(0 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(v0[c]);
+        if (MODE == 1) dls[(1 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(v1[c]);
       }
     }
     __syncthreads();
@@ -382,13 +388,22 @@ static int sm_count_hl() {
   return n;
 }
 
-template <int MODE, bool BIL, int DWN>
-static int launch_head_loss(HeadLossArgs& a, cudaStream_t st) {
-  int rc = ensure_dyn_smem<head_loss_kernel<MODE, BIL, DWN>>(a.smem_bytes, "head_loss");
+template <int MODE, bool BIL, int DWN, int CT, int NIT>
+static int launch_head_loss_x(HeadLossArgs& a, cudaStream_t st) {
+  int rc = ensure_dyn_smem<head_loss_kernel<MODE, BIL, DWN, CT, NIT>>(a.smem_bytes, "head_loss");
   if (rc != MCD_OK) return rc;
   const int grid = min(a.total_items, sm_count_hl());
-  head_loss_kernel<MODE, BIL, DWN><<<grid, HL_THREADS, a.smem_bytes, st>>>(a);
+  head_loss_kernel<MODE, BIL, DWN, CT, NIT><<<grid, HL_THREADS, a.smem_bytes, st>>>(a);
   return check_launch("head_loss");
+}
+
+template <int MODE, bool BIL, int DWN>
+static int launch_head_loss(HeadLossArgs& a, cudaStream_t st) {
+  // the 41-class, one-input heads of the reference's trainers get the constant-folded instantiation
+  if constexpr (!(MODE == 0 && DWN == 2)) {       // (one head, two filter gradients) implies two inputs
+    if (a.C == 41 && a.nin == 1) return launch_head_loss_x<MODE, BIL, DWN, 41, 1>(a, st);
+  }
+  return launch_head_loss_x<MODE, BIL, DWN, 0, 0>(a, st);
 }
 
 }  // namespace mcd
