@@ -238,6 +238,7 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
   const int ksplit = (int)(it[15] & 0xFFFF), CoutP = (int)((it[15] >> 16) & 0xFFFF), CinP = (int)((it[15] >> 32) & 0xFFFF);
   const float lr = hyper[0], mom = hyper[1], wd = hyper[2];
   const int T = R * S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool any_pack = dst_f || dst_d;
   if (!any_pack) {                       // BatchNorm affine parameters, biases, ...: element-wise by all blocks
     for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.y * blockDim.x)
@@ -256,42 +257,47 @@ sgd_pack_multi_kernel(const int64_t* __restrict__ items, const float* __restrict
       if (gws) {
         // reduce the split partial sums of this tile (coalesced along ci) into shared memory, OIHW order
         const int64_t kstride = (int64_t)T * CoutP * CinP;
+#pragma unroll 4
         for (int idx = threadIdx.x; idx < T * 32 * 32; idx += 256) {
           const int ci_l = idx & 31, co_l = (idx >> 5) & 31, t = idx >> 10;
           if (ci_l < nci && co_l < nco) {
             const float* q = gws + ((int64_t)t * CoutP + co0 + co_l) * CinP + ci0 + ci_l;
             float acc = 0.f;
+#pragma unroll 4
             for (int k = 0; k < ksplit; ++k) acc += __ldcs(q + k * kstride);
             tile[co_l][ci_l * T + t] = acc;
           }
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {
-          const int co_l = idx / (nci * T), rem = idx % (nci * T);
-          if (co_l < nco)
-            tile[co_l][rem] = sgd_update_g(w, tile[co_l][rem], buf, ((int64_t)(co0 + co_l) * Cin + ci0) * T + rem, lr, mom, wd);
+        // (loops below: a warp walks rows, lanes the contiguous dimension - no per-element integer divisions)
+        for (int co_l = warp; co_l < nco; co_l += 8) {
+          const int64_t base = ((int64_t)(co0 + co_l) * Cin + ci0) * T;
+          for (int rem = lane; rem < nci * T; rem += 32)
+            tile[co_l][rem] = sgd_update_g(w, tile[co_l][rem], buf, base + rem, lr, mom, wd);
         }
       } else {
-        for (int idx = threadIdx.x; idx < 32 * nci * T; idx += 256) {
-          const int co_l = idx / (nci * T), rem = idx % (nci * T);
-          if (co_l < nco) tile[co_l][rem] = sgd_update(w, g, buf, ((int64_t)(co0 + co_l) * Cin + ci0) * T + rem, lr, mom, wd);
+        for (int co_l = warp; co_l < nco; co_l += 8) {
+          const int64_t base = ((int64_t)(co0 + co_l) * Cin + ci0) * T;
+          for (int rem = lane; rem < nci * T; rem += 32)
+            tile[co_l][rem] = sgd_update(w, g, buf, base + rem, lr, mom, wd);
         }
       }
       __syncthreads();
-      if (dst_f) {
-        for (int idx = threadIdx.x; idx < nco * T * 32; idx += 256) {
-          const int ci_l = idx & 31, t = (idx >> 5) % T, co_l = idx / (32 * T);
-          if (ci_l < nci)
-            dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + ci_l] = f2bits16(tile[co_l][ci_l * T + t], kF16);
+      if (dst_f && lane < nci) {          // rows (co_l, t); lane = ci_l
+        int co_l = warp / T, t = warp % T;
+        for (int row = warp; row < nco * T; row += 8) {
+          dst_f[((int64_t)(co0 + co_l) * T + t) * kpf + ci0 + lane] = f2bits16(tile[co_l][lane * T + t], kF16);
+          t += 8;
+          while (t >= T) { t -= T; ++co_l; }
         }
       }
-      if (dst_d) {
-        for (int idx = threadIdx.x; idx < nci * T * 32; idx += 256) {
-          const int co_l = idx & 31, t = (idx >> 5) % T, ci_l = idx / (32 * T);
-          if (co_l < nco) {
-            const int tf = (R - 1 - t / S) * S + (S - 1 - t % S);
-            dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + co_l] = f2bits16(tile[co_l][ci_l * T + t], kBF16);
-          }
+      if (dst_d && lane < nco) {          // rows (ci_l, t); lane = co_l
+        int ci_l = warp / T, t = warp % T;
+        for (int row = warp; row < nci * T; row += 8) {
+          const int tf = (R - 1 - t / S) * S + (S - 1 - t % S);
+          dst_d[((int64_t)(ci0 + ci_l) * T + tf) * kpd + co0 + lane] = f2bits16(tile[lane][ci_l * T + t], kBF16);
+          t += 8;
+          while (t >= T) { t -= T; ++ci_l; }
         }
       }
     }
