@@ -144,7 +144,19 @@ __device__ __forceinline__ SegIter make_pair_iter(int total_pair_tiles, int kblo
 // (96 KB per 512 MMA cycles at 128 B/clk ~ 68 % of the tensor peak, which is what ncu shows).
 // OCC = 2: half the pipeline stages so that two persistent CTAs share an SM (thin layers, BN 64 / 128): their
 // per-tile chains (TMA -> MMA -> commit -> epilogue) are latency-bound, a second CTA fills the bubbles.
-template <int BN, bool PAIR = false, int OCC = 1>
+// EPI2 (r02): TWO epilogue warpgroups in ONE CTA, one per TMEM accumulator buffer (even / odd tiles).  Used by the
+// dgrad-epilogue instantiations of the 64- / 128-channel tiles: their epilogue (three extra 16-byte loads per 8 channels,
+// ReLU mask, two BatchNorm sums) is bound by the issue latency of ONE warp per scheduler (IPC 0.87 per SM at 246 registers,
+// one CTA per SM: profiles/r02_ncu_full_kernels.csv), a second CTA does not fit the register file, eight epilogue warps at
+// <= 204 registers do.
+#ifndef MCD_THIN_EPI2
+#define MCD_THIN_EPI2 1
+#endif
+constexpr bool fprop_epi2(int BN, bool PAIR, int OCC, bool EXTRAS) {
+  return MCD_THIN_EPI2 && EXTRAS && !PAIR && OCC == 1 && (BN == 64 || BN == 128);
+}
+
+template <int BN, bool PAIR = false, int OCC = 1, bool EPI2 = false>
 struct FpropCfg {
   static constexpr int A_BYTES = 128 * 128;          // 128 pixels x 64 ch bf16
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;   // rows x 64 ch bf16
@@ -166,7 +178,7 @@ struct FpropCfg {
   // CTA pairs: TWO epilogue warpgroups, one per TMEM accumulator buffer (even / odd tiles), so that the epilogue of
   // tile i+1 starts while tile i's is still running (the fused dgrad epilogue of the 256-channel layers is longer
   // than their main loop)
-  static constexpr int EPI_WG = (PAIR && MCD_PAIR_EPI_WG == 2) ? 2 : 1;
+  static constexpr int EPI_WG = ((PAIR && MCD_PAIR_EPI_WG == 2) || EPI2) ? 2 : 1;
   static constexpr int THREADS = 64 + 128 * EPI_WG;
 };
 
@@ -214,10 +226,10 @@ __device__ __forceinline__ void warp_colsum32_single(float* s1, int lane) {
 #define MCD_THIN32_DGRAD_OCC1 0   /* measured: layer2 dgrad 3.9 -> 4.85 ms with one CTA per SM */
 #endif
 template <int BN, bool PAIR, int OCC = 1, bool HALO = false, bool EXTRAS = true>
-__global__ void __launch_bounds__(FpropCfg<BN, PAIR, OCC>::THREADS,
+__global__ void __launch_bounds__(FpropCfg<BN, PAIR, OCC, fprop_epi2(BN, PAIR, OCC, EXTRAS)>::THREADS,
                                   (EXTRAS && BN <= 32 && MCD_THIN32_DGRAD_OCC1) ? 1 : FpropCfg<BN, PAIR, OCC>::MIN_CTAS)
 conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ FpropArgs a) {
-  using Cfg = FpropCfg<BN, PAIR, OCC>;
+  using Cfg = FpropCfg<BN, PAIR, OCC, fprop_epi2(BN, PAIR, OCC, EXTRAS)>;
   const __nv_bfloat16* const x_addend = EXTRAS ? a.addend : nullptr;
   const __nv_bfloat16* const x_mask = EXTRAS ? a.mask_src : nullptr;
   const __half* const x_bny = EXTRAS ? a.bn_y : nullptr;
@@ -486,9 +498,10 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");      // one named barrier per epilogue warpgroup
         if (m == 0) asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(a.sk_flags + blockIdx.x), "r"(1) : "memory");
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (Cfg::EPI_WG == 2) acc_phase ^= 1;
+        else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       const float* part = nullptr;
@@ -501,7 +514,7 @@ conv_umma_fprop_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           } while (!ready);
         }
         __syncwarp();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         part = a.sk_partial + ((int64_t)(blockIdx.x + 1) * (BN / 32) * 128 + m) * 32;
       }
 #pragma unroll(Cfg::ACCSTAT ? 2 : 1)
@@ -1291,10 +1304,10 @@ static inline bool has_extras(const FpropArgs& a) { return a.addend || a.mask_sr
 
 template <int BN, int OCC, bool EXTRAS>
 static int launch_fprop_bn_x(const UmmaMaps& maps, const FpropArgs& a, dim3 grid, cudaStream_t st) {
-  using Cfg = FpropCfg<BN, false, OCC>;
+  using Cfg = FpropCfg<BN, false, OCC, fprop_epi2(BN, false, OCC, EXTRAS)>;
   int arc = ensure_dyn_smem<conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS>>(Cfg::SMEM_BYTES, "conv_umma_fprop");
   if (arc != MCD_OK) return arc;
-  conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(maps, a);
+  conv_umma_fprop_kernel<BN, false, OCC, false, EXTRAS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(maps, a);
   return check_launch("conv_umma_fprop");
 }
 
@@ -1341,7 +1354,7 @@ constexpr int kHaloFixedSmem = 1024 /*align slack*/ + 256 /*barriers*/ + 2 * 102
 
 template <int BN, bool PAIR, int OCC, bool EXTRAS>
 static int launch_fprop_halo_x(const UmmaMaps& maps, const FpropArgs& a, int grid, cudaStream_t st) {
-  using Cfg = FpropCfg<BN, PAIR, OCC>;
+  using Cfg = FpropCfg<BN, PAIR, OCC, fprop_epi2(BN, PAIR, OCC, EXTRAS)>;
   const int smem_bytes = 2 * a.halo_bytes + a.stages * Cfg::B_BYTES + kHaloFixedSmem;
   int arc = ensure_dyn_smem<conv_umma_fprop_kernel<BN, PAIR, OCC, true, EXTRAS>>(smem_bytes, "conv_umma_fprop_halo");
   if (arc != MCD_OK) return arc;
