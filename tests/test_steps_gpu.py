@@ -334,6 +334,42 @@ def _free_port():
     return port
 
 
+def test_full_size_iteration_is_batch_order_invariant(cuda_dev):
+    """size-independent property at the BASELINE frame size (480 x 640, 8 pairs): an MCD iteration does not depend on
+    the ORDER of the pairs in the batch - BatchNorm statistics, the weighted CE mean, Diff2d and every weight gradient
+    are sums over the batch.  Catches any kernel whose result depends on where in the batch / tile grid an image
+    sits (tile-edge handling, persistent-CTA item order, split-K partitioning); only the order of fp32 atomics
+    differs between the two runs."""
+    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+    from mcd_b200.step import MCDStep
+    from models.model_util import get_models
+    dev, size, n = cuda_dev, (480, 640), 8
+    src, tgt, lbl = _inputs(77, n, size, dev)
+    w = O.class_weight(N_CLASS).to(dev)
+    perm = torch.tensor([5, 2, 7, 0, 3, 6, 1, 4], device=dev)
+    states = (O.fill_state_dict_(O.init_seg_base("drn_d_38", 6, N_CLASS), 1), O.fill_state_dict_(O.init_head(N_CLASS), 2),
+              O.fill_state_dict_(O.init_head(N_CLASS), 3))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ma = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS)]
+        mb = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS)]
+    for m1, m2, sd in zip(ma, mb, states):      # the oracle's deterministic non-trivial state (no zero-initialised tensors)
+        _load(m1, sd), _load(m2, sd)
+    sa = MCDStep(ma, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=2)
+    sb = MCDStep(mb, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=2)
+    ca, da = sa(src, lbl, tgt)
+    cb, db = sb(src[perm].contiguous(), lbl[perm].contiguous(), tgt[perm].contiguous())
+    torch.cuda.synchronize()
+    assert rel(ca, cb) <= 2e-5 and rel(da, db) <= 2e-4, (float(ca), float(cb), float(da), float(db))
+    worst = max(nerr(p, q) for m1, m2 in zip(ma, mb) for p, q in zip(m1.parameters(), m2.parameters()))
+    assert worst <= 1e-3, worst
+    bn_a, bn_b = ma[0].base[6][1].bn1, mb[0].base[6][1].bn1
+    assert nerr(bn_a.running_var, bn_b.running_var) <= 1e-2 and int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked)
+    _log("parity_steps.txt", ["batch-order invariance 8 x 480x640: c %.6f / %.6f  d %.6e / %.6e  weights %.2e" %
+                              (float(ca), float(cb), float(da), float(db), worst)])
+
+
+
 def _dp_worker(rank, world, port, graph, q):
     try:
         import faulthandler
