@@ -429,6 +429,9 @@ class _UnitFn(torch.autograd.Function):
         ctx.res_training = res_bn.training if res_bn is not None else False
         ctx.has_res, ctx.has_res_bn, ctx.has_bias = res is not None, res_bn is not None, bias is not None
         ctx.res_ptr = res.data_ptr() if (res is not None and res_bn is None and getattr(res, "_mcd_shortcut", False)) else None
+        # downsample shortcut: x feeds conv1 (an earlier unit) and this unit's 1x1 convolution; the gradient that
+        # reaches x through the 1x1 convolution is handed to conv1's dgrad epilogue instead of an autograd add
+        ctx.ds_ptr = res.data_ptr() if (res_conv is not None and getattr(res, "_mcd_shortcut", False)) else None
         ctx.x_bn_y = x_bn_y
         ctx.w_tag = _weight_tag(weight)
         ctx.rw_tag = _weight_tag(res_weight) if res_conv is not None else None
@@ -458,6 +461,9 @@ class _UnitFn(torch.autograd.Function):
         if ctx.has_res_bn:
             # downsample branch: dres is the gradient of the 1x1 convolution's output
             dres, drw, _ = _conv_backward(ctx.res_conv, ctx.rg, res, dres, need[5], need[6], False, None, ctx.rw_tag)
+            if _direct is not None and ctx.ds_ptr is not None and dres is not None:
+                _direct.stash[ctx.ds_ptr] = dres
+                dres = None
         elif not want_dres:
             dres = None
         dx, dw, db = _conv_backward(ctx.conv, ctx.g, x, dy, need[0], need[1] , ctx.has_bias and need[2], ctx.x_bn_y,

@@ -51,6 +51,7 @@ class BasicBlock(nn.Module):
             return conv_bn_act(self.conv2, self.bn2, out, relu=True, sole=True)
         if self.downsample is not None:
             ds_conv, ds_bn = self.downsample[0], self.downsample[1]
+            x._mcd_shortcut = True     # (its gradient through the 1x1 convolution joins conv1's dgrad epilogue)
             return conv_bn_act(self.conv2, self.bn2, out, relu=True, res=x, res_conv=ds_conv, res_bn=ds_bn,
                                sole=True)
         # identity shortcut: x feeds conv1 AND the residual add; the flag lets MCDStep fuse the shortcut gradient
@@ -84,6 +85,7 @@ class Bottleneck(nn.Module):
         out = conv_bn_act(self.conv2, self.bn2, out, relu=True, sole=True)
         if self.downsample is not None:
             ds_conv, ds_bn = self.downsample[0], self.downsample[1]
+            x._mcd_shortcut = True
             return conv_bn_act(self.conv3, self.bn3, out, relu=True, res=x, res_conv=ds_conv, res_bn=ds_bn, sole=True)
         x._mcd_shortcut = True
         return conv_bn_act(self.conv3, self.bn3, out, relu=True, res=x, sole=True)
