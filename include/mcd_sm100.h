@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 18
+#define MCD_ABI_VERSION 19
 
 enum {
   MCD_OK = 0,
@@ -256,7 +256,9 @@ int mcd_deconv16s8_bwd(const void* dout, int dout_f32, const float* x, const flo
  * One kernel = x8 upsampling head (learned 16x16/s8 depthwise deconv, models/dilated_fcn.py:357-366,465-491, or
  * nn.Upsample(x8, bilinear) of the multitask decoders :676,817-819 when the filter pointers are NULL) + softmax +
  * loss + the gradients of the loss w.r.t. the head's inputs and filters, for an upstream gradient of 1.
- *   mode 0: CrossEntropyLoss2d (loss.py:7-13) of ONE head;  mode 1: Diff2d (loss.py:93-100) between TWO heads.
+ *   mode 0: CrossEntropyLoss2d (loss.py:7-13) of ONE head;  mode 1: Diff2d (loss.py:93-100) between TWO heads;
+ *   mode 2: CrossEntropyLoss2d of TWO heads against the same labels, summed (adapt_trainer.py:171-175:
+ *           criterion(outputs1, lbls) + criterion(outputs2, lbls)), labels read once.
  * x / w / dx / dw: host arrays of nheads * nin DEVICE pointers, index head * nin + input; a head's logits are the sum
  * over its `nin` (input, filter) pairs (ScoreAddFusion: up1(x1) + up2(x2); AddFusion: pass x1 + x2 as one input).
  * dx[i] (fp32 [N,C,h,w]) and dw[i] (fp32 [C,256]) are ACCUMULATED INTO (caller-zeroed; two heads may share one dx

@@ -77,7 +77,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
   __shared__ float red[32];
   const int C = CT > 0 ? CT : a.C, h = a.h, w = a.w, H = 8 * a.h, W = 8 * a.w;
   const int tid = threadIdx.x, q = tid >> 6, pos = tid & 63, kh0 = pos >> 3, kw0 = pos & 7;
-  constexpr int NH = MODE == 1 ? 2 : 1;
+  constexpr int NH = MODE >= 1 ? 2 : 1;     // MODE 1: Diff2d(a, b); MODE 2: CE(a, y) + CE(b, y), one label read
   const int NI = NIT > 0 ? NIT : a.nin;
 
   // ---- filters -> shared memory [c][pos][tap], tap = 2a + b <-> (kh0 + 8a, kw0 + 8b)
@@ -103,7 +103,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
     for (int c = 0; c < (DW ? HL_MAXC : 1); ++c) dwacc[i][c] = 0.f;
 
   float loss_acc = 0.f, bad_acc = 0.f;
-  const float wsum = (MODE == 0 && a.wsum) ? a.wsum[0] : 1.f;
+  const float wsum = (MODE != 1 && a.wsum) ? a.wsum[0] : 1.f;
   const float ce_coef = wsum > 0.f ? 1.f / wsum : 0.f;
 
   for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
@@ -139,7 +139,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
     const int cj = cj0 + q;
     const int oh = 8 * ci - 4 + kh0, ow = 8 * cj - 4 + kw0;
     const bool pvalid = oh >= 0 && oh < H && ow >= 0 && ow < W && cj <= w;
-    float v0[HL_MAXC], v1[MODE == 1 ? HL_MAXC : 1];
+    float v0[HL_MAXC], v1[MODE >= 1 ? HL_MAXC : 1];
 #pragma unroll
     for (int c = 0; c < HL_MAXC; ++c) {
       float s0 = -INFINITY, s1 = -INFINITY;
@@ -155,7 +155,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
               const float4 w0 = *reinterpret_cast<const float4*>(ws + ((0 * NI + k) * C + c) * HL_WS + pos * 4);
               s0 += x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w;
             }
-            if (MODE == 1) {
+            if (MODE >= 1) {
               const float4 x1 = *reinterpret_cast<const float4*>(xs + (((1 * NI + k) * C + c) * HL_CELLS + q) * 4);
               if (BILINEAR) {
                 s1 += x1.x * bw4[0] + x1.y * bw4[1] + x1.z * bw4[2] + x1.w * bw4[3];
@@ -168,18 +168,18 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
         }
       }
       v0[c] = s0;
-      if (MODE == 1) v1[c] = s1;
+      if (MODE >= 1) v1[c] = s1;
     }
 #if defined(HL_EXP) && HL_EXP == 1
     { float t = 0.f;
 #pragma unroll
-      for (int c = 0; c < HL_MAXC; ++c) t += (c < C ? v0[c] : 0.f) + (MODE == 1 && c < C ? v1[c] : 0.f);
+      for (int c = 0; c < HL_MAXC; ++c) t += (c < C ? v0[c] : 0.f) + (MODE >= 1 && c < C ? v1[c] : 0.f);
       loss_acc += t; continue; }
 #endif
     // cross entropy: the label and its raw logit (before the logits are overwritten by their exponentials)
-    float wy = 0.f, xy = 0.f;
+    float wy = 0.f, xy = 0.f, xy1 = 0.f;
     int y = -1;
-    if (MODE == 0) {
+    if (MODE != 1) {
       if (pvalid) {
         const int64_t yy = __ldcs(a.target + ((int64_t)n * H + oh) * W + ow);
         if (yy != a.ignore_index) {
@@ -188,24 +188,33 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
         }
       }
 #pragma unroll
-      for (int c = 0; c < HL_MAXC; ++c) xy = (c == y) ? v0[c] : xy;
+      for (int c = 0; c < HL_MAXC; ++c) {
+        xy = (c == y) ? v0[c] : xy;
+        if (MODE == 2) xy1 = (c == y) ? v1[c] : xy1;
+      }
     }
     // softmax statistics
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < HL_MAXC; ++c) { m0 = fmaxf(m0, v0[c]); if (MODE == 1) m1 = fmaxf(m1, v1[c]); }
+    for (int c = 0; c < HL_MAXC; ++c) { m0 = fmaxf(m0, v0[c]); if (MODE >= 1) m1 = fmaxf(m1, v1[c]); }
     float se0 = 0.f, se1 = 0.f;
 #pragma unroll
     for (int c = 0; c < HL_MAXC; ++c) {
       v0[c] = __expf(v0[c] - m0); se0 += v0[c];          // padding channels: exp(-inf) = 0
-      if (MODE == 1) { v1[c] = __expf(v1[c] - m1); se1 += v1[c]; }
+      if (MODE >= 1) { v1[c] = __expf(v1[c] - m1); se1 += v1[c]; }
     }
-    if (MODE == 0) {
+    if (MODE != 1) {
       // nll = max + log(sum exp) - x_y;  d logit_c = w_y / wsum * (p_c - [c == y])
       if (y >= 0) loss_acc += wy * (m0 + __logf(se0) - xy);
       const float kk = wy * ce_coef / se0;
 #pragma unroll
       for (int c = 0; c < HL_MAXC; ++c) v0[c] = (y >= 0) ? (kk * v0[c] - (c == y ? wy * ce_coef : 0.f)) : 0.f;
+      if (MODE == 2) {      // the second classifier on the same labels
+        if (y >= 0) loss_acc += wy * (m1 + __logf(se1) - xy1);
+        const float k1 = wy * ce_coef / se1;
+#pragma unroll
+        for (int c = 0; c < HL_MAXC; ++c) v1[c] = (y >= 0) ? (k1 * v1[c] - (c == y ? wy * ce_coef : 0.f)) : 0.f;
+      }
     } else {
       // Diff2d: loss += sum_c |pa - pb|; d/d logit_a = k pa (s_c - sum s pa), d/d logit_b = k pb (sum s pb - s_c)
       const float i0 = 1.f / se0, i1 = 1.f / se1;
@@ -231,7 +240,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
 #if defined(HL_EXP) && HL_EXP == 2
     { float t = 0.f;
 #pragma unroll
-      for (int c = 0; c < HL_MAXC; ++c) t += v0[c] + (MODE == 1 ? v1[c] : 0.f);
+      for (int c = 0; c < HL_MAXC; ++c) t += v0[c] + (MODE >= 1 ? v1[c] : 0.f);
       loss_acc += t * 1e-30f; continue; }
 #endif
     if (!a.want_grad) continue;
@@ -241,7 +250,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
       if (c < C) {
         // (pixels outside the image already hold zeros: no label / k = 0 above)
         dls[(0 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(v0[c]);
-        if (MODE == 1) dls[(1 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(v1[c]);
+        if (MODE >= 1) dls[(1 * C + c) * HL_DL + pos * 4 + q] = __float2bfloat16_rn(v1[c]);
       }
     }
     __syncthreads();
@@ -337,7 +346,7 @@ head_loss_kernel(const __grid_constant__ HeadLossArgs a) {
   // ---- block results
   const float r0 = block_sum(loss_acc, red);
   if (tid == 0 && r0 != 0.f) atomicAdd(a.acc + 0, r0);
-  if (MODE == 0) {
+  if (MODE != 1) {
     const float r2 = block_sum(bad_acc, red);
     if (tid == 0 && r2 != 0.f) atomicAdd(a.acc + 2, r2);
   }
@@ -425,7 +434,7 @@ int mcd_head_loss(int mode, int nheads, int nin, const float* const* x, const fl
                   float* const* dw, const int64_t* target, const float* cls_weight, int64_t ignore_index,
                   const float* wsum, float inv_numel, float* acc, int N, int C, int h, int w_, int device, void* stream) {
   MCD_ENTER(device);
-  MCD_REQUIRE(mode == 0 || mode == 1, "head_loss: mode must be 0 (cross entropy) or 1 (Diff2d)");
+  MCD_REQUIRE(mode >= 0 && mode <= 2, "head_loss: mode must be 0 (cross entropy), 1 (Diff2d) or 2 (cross entropy of two heads)");
   MCD_REQUIRE(nheads == (mode ? 2 : 1) && (nin == 1 || nin == 2), "head_loss: %d heads / %d inputs unsupported", nheads, nin);
   MCD_REQUIRE(x && w && dx && dw && acc && N > 0 && C > 0 && h > 0 && w_ > 0, "head_loss: bad arguments");
   MCD_REQUIRE(C <= HL_MAXC, "head_loss: at most %d classes (got %d)", HL_MAXC, C);
@@ -479,6 +488,10 @@ int mcd_head_loss(int mode, int nheads, int nin, const float* const* x, const fl
     if (bil) return launch_head_loss<0, true, 0>(a, st);
     if (!any_dw) return launch_head_loss<0, false, 0>(a, st);
     return nhi == 1 ? launch_head_loss<0, false, 1>(a, st) : launch_head_loss<0, false, 2>(a, st);
+  }
+  if (mode == 2) {
+    if (bil) return launch_head_loss<2, true, 0>(a, st);
+    return any_dw ? launch_head_loss<2, false, 2>(a, st) : launch_head_loss<2, false, 0>(a, st);
   }
   if (bil) return launch_head_loss<1, true, 0>(a, st);
   return any_dw ? launch_head_loss<1, false, 2>(a, st) : launch_head_loss<1, false, 0>(a, st);

@@ -3,6 +3,7 @@ ONE kernel - the full-resolution logits (41 x 480 x 640 per image and head) and 
 
     head_ce2d(inputs, filters, target, criterion)            CrossEntropyLoss2d(head(inputs), target)    loss.py:7-13
     head_diff2d(inputs_a, filters_a, inputs_b, filters_b)    Diff2d(head_a(.), head_b(.))                loss.py:93-100
+    head_ce2d_pair(inputs, filters_a, filters_b, target, ...) CE(head_a(.), t) + CE(head_b(.), t)   adapt_trainer.py:171-175
 
 `inputs` / `filters`: lists of one or two fp32 score maps [N,C,h,w] and depthwise ConvTranspose2d filters [C,1,16,16]
 (DRNSegPixelClassifier: one pair; ScoreFusionDRNSegPixelClassifier: up1(x1) + up2(x2), two pairs); filters = None is
@@ -111,6 +112,43 @@ class _HeadCEFn(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(grads)
 
 
+class _HeadCEPairFn(torch.autograd.Function):
+    """criterion(F1(feat), lbls) + criterion(F2(feat), lbls) in one launch (mode 2): both classifiers read the same score
+    maps and the same labels; the score-map gradient is their sum, accumulated into one buffer."""
+
+    @staticmethod
+    def forward(ctx, target, cls_weight, ignore_index, size_average, n_in, *xw):
+        xs, wa, wb = list(xw[:n_in]), list(xw[n_in:2 * n_in]), list(xw[2 * n_in:])
+        need = ctx.needs_input_grad[5:]
+        dxs = [torch.zeros_like(x) if need[i] else None for i, x in enumerate(xs)]
+        dwa = [torch.zeros_like(w) if need[n_in + i] else None for i, w in enumerate(wa)]
+        dwb = [torch.zeros_like(w) if need[2 * n_in + i] else None for i, w in enumerate(wb)]
+        wsum = None
+        if size_average:
+            acc2 = ops.zeros_f32(2, target.device)
+            dev = target.device.index if target.device.index is not None else torch.cuda.current_device()
+            abi.check(abi.lib().mcd_label_weight_sum(
+                ctypes.c_void_p(target.data_ptr()), ctypes.c_void_p(cls_weight.data_ptr()) if cls_weight is not None else None,
+                int(ignore_index), xs[0].shape[1], ctypes.c_void_p(acc2.data_ptr()), target.numel(), dev,
+                ctypes.c_void_p(torch.cuda.current_stream(target.device).cuda_stream)), "label_weight_sum")
+            wsum = acc2[0:1]
+            group, world = _dp()
+            if world > 1:
+                torch.distributed.all_reduce(wsum, op=torch.distributed.ReduceOp.SUM, group=group)
+        acc = ops.zeros_f32(4, xs[0].device)
+        _launch(2, 2, n_in, xs + xs, wa + wb, dxs + dxs, dwa + dwb, target, cls_weight, ignore_index, wsum, 0.0, acc)
+        out = dxs + dwa + dwb
+        ctx.present = [t is not None for t in out]
+        ctx.save_for_backward(*[t for t in out if t is not None])
+        return acc[0] / wsum[0] if size_average else acc[0].clone()
+
+    @staticmethod
+    def backward(ctx, go):
+        saved = list(ctx.saved_tensors)
+        grads = [saved.pop(0) * go if p else None for p in ctx.present]
+        return (None, None, None, None, None) + tuple(grads)
+
+
 class _HeadDiffFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n_in, *xw):
@@ -158,6 +196,18 @@ def head_ce2d(inputs, filters, target, weight=None, ignore_index=-100, size_aver
         target = target.long()
     w = None if weight is None else weight.to(device=xs[0].device, dtype=F32).contiguous()
     return _HeadCEFn.apply(target.contiguous(), w, ignore_index, size_average, n_in, *xs, *ws)
+
+
+def head_ce2d_pair(inputs, filters_a, filters_b, target, weight=None, ignore_index=-100, size_average=True):
+    """CrossEntropyLoss2d(head_a(inputs), target) + CrossEntropyLoss2d(head_b(inputs), target): the supervised term of
+    every MCD phase (adapt_trainer.py:171-175,191-194), one launch for both classifiers."""
+    n_in = len(inputs)
+    xs = [_f32c(x) for x in inputs]
+    if target.dtype != torch.int64:
+        target = target.long()
+    w = None if weight is None else weight.to(device=xs[0].device, dtype=F32).contiguous()
+    return _HeadCEPairFn.apply(target.contiguous(), w, ignore_index, size_average, n_in, *xs,
+                               *[_f32c(t) for t in filters_a], *[_f32c(t) for t in filters_b])
 
 
 def head_diff2d(inputs_a, filters_a, inputs_b, filters_b):

@@ -114,6 +114,15 @@ class _EarlyFusionTask:
         return headloss.head_ce2d(hi[0], hi[1], lbls, c.nll_loss.weight, c.ignore_index, c.size_average)
 
     def _ce(self, feats, lbls):
+        from . import headloss
+        if self.f2 is not self.f1:
+            ha, hb = self._fused_inputs(self.f1, feats, 1), self._fused_inputs(self.f2, feats, 1)
+            # both classifiers on the same score maps and labels: ONE launch (mode 2) when it fits
+            if (ha is not None and hb is not None and all(p is q for p, q in zip(ha[0], hb[0]))
+                    and headloss.fits(2, len(ha[0]), ha[0][0].shape[1],
+                                      torch.is_grad_enabled() and any(w.requires_grad for w in ha[1] + hb[1]), False)):
+                c = self.criterion
+                return headloss.head_ce2d_pair(ha[0], ha[1], hb[1], lbls, c.nll_loss.weight, c.ignore_index, c.size_average)
         return self._ce_head(self.f1, feats, lbls) + self._ce_head(self.f2, feats, lbls)
 
     def loss_a(self, fs, ft, src, lbls, tgt):

@@ -487,6 +487,37 @@ def test_head_ce2d_fused(cuda_dev, kind, shape):
     assert abs(float(s) - float(ref_s)) / abs(float(ref_s)) < 2e-5
 
 
+@pytest.mark.parametrize("mode", ["train", "frozen_features", "frozen_filters"])
+@pytest.mark.parametrize("shape", [(2, 41, 6, 10), (1, 41, 7, 5), (3, 5, 4, 9)])
+def test_head_ce2d_pair_fused(cuda_dev, shape, mode):
+    """criterion(F1(feat), lbls) + criterion(F2(feat), lbls) (adapt_trainer.py:171-175) as ONE launch (mode 2 of
+    mcd_head_loss): both classifiers on the same score map and labels; phase A trains everything, phase B only the
+    filters (features detached), and a frozen-classifier call only the features."""
+    from mcd_b200 import headloss
+    torch.manual_seed(12)
+    n, c, h, w = shape
+    x = (torch.randn(n, c, h, w, device=cuda_dev) * 2).requires_grad_(mode != "frozen_features")
+    wa = (torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1).requires_grad_(mode != "frozen_filters")
+    wb = (torch.randn(c, 1, 16, 16, device=cuda_dev) * 0.1).requires_grad_(mode != "frozen_filters")
+    target = torch.randint(0, c, (n, 8 * h, 8 * w), device=cuda_dev)
+    target[0, 1, :7] = -100
+    weight = torch.ones(c, device=cuda_dev)
+    weight[c - 1] = 0
+    weight[2] = 0.5
+    leaves = [t for t in (x, wa, wb) if t.requires_grad]
+    ref = (F.cross_entropy(_head_ref([x], [wa], False), target, weight, ignore_index=-100) +
+           F.cross_entropy(_head_ref([x], [wb], False), target, weight, ignore_index=-100))
+    g_ref = torch.autograd.grad(ref * 0.6, leaves)
+    xo, wao, wbo = [t.detach().clone().requires_grad_(t.requires_grad) for t in (x, wa, wb)]
+    got = headloss.head_ce2d_pair([xo], [wao], [wbo], target, weight)
+    (got * 0.6).backward()
+    assert abs(float(got) - float(ref)) / abs(float(ref)) < 2e-5
+    for a_, b_ in zip([t for t in (xo, wao, wbo) if t.requires_grad], g_ref):
+        assert rel_err(a_.grad, b_) < 6e-3, mode
+    two = headloss.head_ce2d([xo], [wao], target, weight) + headloss.head_ce2d([xo], [wbo], target, weight)
+    assert abs(float(got) - float(two)) <= 2e-6 * abs(float(two))
+
+
 @pytest.mark.parametrize("kind", ["deconv", "scoreadd", "bilinear", "deconv_frozen"])
 @pytest.mark.parametrize("shape", [(2, 41, 6, 10), (1, 41, 7, 5)])
 def test_head_diff2d_fused(cuda_dev, kind, shape):
