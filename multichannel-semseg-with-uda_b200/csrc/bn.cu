@@ -556,224 +556,16 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* _
   }
 }
 
-// ---- bulk-copy staged backward kernels (same ring as bn_forward_bulk_kernel; 8 KB per tensor and stage: up to four
-//      input tensors per stage) --------------------------------------------------------------------------------------
-constexpr int kBnBwdTileBytes = 8192;
-
-struct BulkSrc {
-  const uint8_t* p[4];       // dz, y, then z (ReLU mask) and / or res as present
-  int n;
-};
-
-// shared pipeline: thread 0 issues one bulk copy per source for tile `tile` into stage `stage`
-__device__ __forceinline__ void bulk_issue(const BulkSrc& src, uint8_t* ring, uint64_t* full, int tile, int stage,
-                                           int rows_per_tile, int64_t P, int64_t row_bytes, int tile_bytes) {
-  const int64_t r0 = (int64_t)tile * rows_per_tile;
-  const int64_t left = P - r0;
-  const uint32_t bytes = (uint32_t)((left < rows_per_tile ? left : (int64_t)rows_per_tile) * row_bytes);
-  ptx::mbar_expect_tx(&full[stage], bytes * src.n);
-  for (int i = 0; i < src.n; ++i)
-    bulk_load_1d(ring + (stage * src.n + i) * tile_bytes, src.p[i] + r0 * row_bytes, bytes, &full[stage]);
-}
-
-__global__ void __launch_bounds__(256, 2)
-bn_bwd_apply_bulk_kernel(BulkSrc src, BwdBranch b1, const float* __restrict__ sums, int relu,
-                         __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                         BwdBranch b2, int has_res_bn, __nv_bfloat16* __restrict__ dres, float* __restrict__ dres_gamma,
-                         float* __restrict__ dres_beta, float invP, int64_t P, int Cs, int C, int raw, int rows_per_tile,
-                         int ntiles) {
-  extern __shared__ __align__(128) uint8_t bsm[];
-  uint8_t* ring = bsm;
-  float* co = reinterpret_cast<float*>(bsm + kBnStages * src.n * kBnBwdTileBytes);    // A1, B1, K1, A2, B2, K2
-  uint64_t* full = reinterpret_cast<uint64_t*>(co + 6 * Cs);
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int s = 0; s < kBnStages; ++s) ptx::mbar_init(&full[s], 1);
-    ptx::fence_barrier_init();
-  }
-  if (blockIdx.x == 0) {
-    for (int c = tid; c < C; c += 256) {
-      if (dgamma) dgamma[c] = bwd_second(b1, sums, C, c, raw);
-      if (dbeta) dbeta[c] = sums[c];
-      if (dres_gamma) dres_gamma[c] = sums[2 * C + c];
-      if (dres_beta) dres_beta[c] = sums[c];
-    }
-  }
-  for (int c = tid; c < Cs; c += 256) {
-    float A = 0.f, B = 0.f, K = 0.f, A2 = 0.f, B2 = 0.f, K2 = 0.f;
-    if (c < C) {
-      bwd_coeffs(b1, sums, C, C, c, invP, raw, &A, &B, &K);
-      if (has_res_bn) bwd_coeffs(b2, sums, 2 * C, C, c, invP, 0, &A2, &B2, &K2);
-    }
-    co[c] = A; co[Cs + c] = B; co[2 * Cs + c] = K;
-    co[3 * Cs + c] = A2; co[4 * Cs + c] = B2; co[5 * Cs + c] = K2;
-  }
-  __syncthreads();
-  const int64_t row_bytes = (int64_t)Cs * 2;
-  if (tid == 0)
-    for (int s = 0; s < kBnStages; ++s) {
-      const int t = blockIdx.x + s * gridDim.x;
-      if (t < ntiles) bulk_issue(src, ring, full, t, s, rows_per_tile, P, row_bytes, kBnBwdTileBytes);
-    }
-  const int vpr = Cs >> 3, rpi = 256 / vpr;
-  const int cv = tid % vpr, pr = tid / vpr, c0 = cv * 8;
-  const int iz = relu ? 2 : -1, ir = has_res_bn ? (relu ? 3 : 2) : -1;
-  float cA[8], cB[8], cK[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { cA[k] = co[c0 + k]; cB[k] = co[Cs + c0 + k]; cK[k] = co[2 * Cs + c0 + k]; }
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it % kBnStages;
-    const int64_t r0 = (int64_t)tile * rows_per_tile;
-    const int nrows = (P - r0 < rows_per_tile) ? (int)(P - r0) : rows_per_tile;
-    ptx::mbar_wait(&full[stage], (uint32_t)((it / kBnStages) & 1));
-    const uint8_t* base = ring + (stage * src.n) * kBnBwdTileBytes;
-    const uint4* sd = reinterpret_cast<const uint4*>(base);
-    const uint4* sy = reinterpret_cast<const uint4*>(base + kBnBwdTileBytes);
-    const uint4* sz = reinterpret_cast<const uint4*>(base + (iz > 0 ? iz : 0) * kBnBwdTileBytes);
-    const uint4* sr = reinterpret_cast<const uint4*>(base + (ir > 0 ? ir : 0) * kBnBwdTileBytes);
-#pragma unroll 2
-    for (int r = pr; r < nrows; r += rpi) {
-      const int e = r * vpr + cv;
-      const int64_t off = (r0 + r) * Cs + c0;
-      float fd[8], fy[8], g[8], o[8];
-      unpack8(sd[e], fd); unpack8h(sy[e], fy);
-      if (relu) {
-        float fz[8];
-        unpack8(sz[e], fz);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = fz[k] > 0.f ? fd[k] : 0.f;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = fd[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = fmaf(cA[k], g[k], fmaf(cB[k], fy[k], cK[k]));
-      *reinterpret_cast<uint4*>(dy + off) = pack8(o);
-      if (dres) {
-        if (has_res_bn) {
-          float fr[8];
-          unpack8h(sr[e], fr);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            o[k] = fmaf(co[3 * Cs + c0 + k], g[k], fmaf(co[4 * Cs + c0 + k], fr[k], co[5 * Cs + c0 + k]));
-          *reinterpret_cast<uint4*>(dres + off) = pack8(o);
-        } else {
-          *reinterpret_cast<uint4*>(dres + off) = pack8(g);
-        }
-      }
-    }
-    __syncthreads();
-    const int nt = tile + kBnStages * gridDim.x;
-    if (tid == 0 && nt < ntiles) bulk_issue(src, ring, full, nt, stage, rows_per_tile, P, row_bytes, kBnBwdTileBytes);
-  }
-}
-
-// backward reduction (MODE 1 of bn_reduce_kernel) with bulk-staged inputs: sums of g, g * xhat(y) [, g * xhat(res)]
-__global__ void __launch_bounds__(256, 2)
-bn_bwd_reduce_bulk_kernel(BulkSrc src, const float* __restrict__ mean, const float* __restrict__ rstd,
-                          const float* __restrict__ res_mean, const float* __restrict__ res_rstd, int relu,
-                          float* __restrict__ out, int64_t P, int C, int Cs, int rows_per_tile, int ntiles) {
-  extern __shared__ __align__(128) uint8_t bsm[];
-  uint8_t* ring = bsm;
-  float* sh = reinterpret_cast<float*>(bsm + kBnStages * src.n * kBnBwdTileBytes);     // 3 * Cs accumulators
-  float* co = sh + 3 * Cs;                                                             // mean, rstd, res_mean, res_rstd
-  uint64_t* full = reinterpret_cast<uint64_t*>(co + 4 * Cs);
-  const int tid = threadIdx.x;
-  const bool dual = res_mean != nullptr;
-  if (tid == 0) {
-    for (int s = 0; s < kBnStages; ++s) ptx::mbar_init(&full[s], 1);
-    ptx::fence_barrier_init();
-  }
-  for (int i = tid; i < 3 * Cs; i += 256) sh[i] = 0.f;
-  for (int c = tid; c < Cs; c += 256) {
-    const int cc = min(c, C - 1);
-    co[c] = mean[cc]; co[Cs + c] = rstd[cc];
-    co[2 * Cs + c] = dual ? res_mean[cc] : 0.f; co[3 * Cs + c] = dual ? res_rstd[cc] : 0.f;
-  }
-  __syncthreads();
-  const int64_t row_bytes = (int64_t)Cs * 2;
-  if (tid == 0)
-    for (int s = 0; s < kBnStages; ++s) {
-      const int t = blockIdx.x + s * gridDim.x;
-      if (t < ntiles) bulk_issue(src, ring, full, t, s, rows_per_tile, P, row_bytes, kBnBwdTileBytes);
-    }
-  const int vpr = Cs >> 3, rpi = 256 / vpr;
-  const int cv = tid % vpr, pr = tid / vpr, c0 = cv * 8;
-  const int iz = relu ? 2 : -1, ir = dual ? (relu ? 3 : 2) : -1;
-  float a0[8], a1[8], a2[8], cm[8], cr[8], dm[8], dr[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    a0[k] = a1[k] = a2[k] = 0.f;
-    cm[k] = co[c0 + k]; cr[k] = co[Cs + c0 + k]; dm[k] = co[2 * Cs + c0 + k]; dr[k] = co[3 * Cs + c0 + k];
-  }
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it % kBnStages;
-    const int64_t r0 = (int64_t)tile * rows_per_tile;
-    const int nrows = (P - r0 < rows_per_tile) ? (int)(P - r0) : rows_per_tile;
-    ptx::mbar_wait(&full[stage], (uint32_t)((it / kBnStages) & 1));
-    const uint8_t* base = ring + (stage * src.n) * kBnBwdTileBytes;
-    const uint4* sd = reinterpret_cast<const uint4*>(base);
-    const uint4* sy = reinterpret_cast<const uint4*>(base + kBnBwdTileBytes);
-    const uint4* sz = reinterpret_cast<const uint4*>(base + (iz > 0 ? iz : 0) * kBnBwdTileBytes);
-    const uint4* sr = reinterpret_cast<const uint4*>(base + (ir > 0 ? ir : 0) * kBnBwdTileBytes);
-#pragma unroll 2
-    for (int r = pr; r < nrows; r += rpi) {
-      const int e = r * vpr + cv;
-      float fd[8], fy[8], g[8];
-      unpack8(sd[e], fd); unpack8h(sy[e], fy);
-      if (relu) {
-        float fz[8];
-        unpack8(sz[e], fz);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = fz[k] > 0.f ? fd[k] : 0.f;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = fd[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a0[k] += g[k]; a1[k] = fmaf(g[k], (fy[k] - cm[k]) * cr[k], a1[k]); }
-      if (dual) {
-        float fr[8];
-        unpack8h(sr[e], fr);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a2[k] = fmaf(g[k], (fr[k] - dm[k]) * dr[k], a2[k]);
-      }
-    }
-    __syncthreads();
-    const int nt = tile + kBnStages * gridDim.x;
-    if (tid == 0 && nt < ntiles) bulk_issue(src, ring, full, nt, stage, rows_per_tile, P, row_bytes, kBnBwdTileBytes);
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sh[c0 + k], a0[k]);
-    atomicAdd(&sh[Cs + c0 + k], a1[k]);
-    if (dual) atomicAdd(&sh[2 * Cs + c0 + k], a2[k]);
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += 256) {
-    atomicAdd(out + c, sh[c]);
-    atomicAdd(out + C + c, sh[Cs + c]);
-    if (dual) atomicAdd(out + 2 * C + c, sh[2 * Cs + c]);
-  }
-}
-
 // MCD_BN_BULK=0: the register-staged BatchNorm forward everywhere (A/B measurements).
 static bool bn_bulk_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MCD_BN_BULK"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
-// The bulk-staged BACKWARD kernels are faster alone (512 channels: 63 -> 58 us) but slower inside the iteration
-// (137.0 -> 138.2 ms): backward BatchNorm kernels run next to the wgrad kernels of the side stream, and a block that
-// needs 50 - 100 KB of shared memory cannot share an SM with a wgrad CTA (190 KB) the way the register-staged blocks do.
-// MCD_BN_BULK_BWD=1 enables them (A/B measurements, backward passes without concurrent wgrad).
-static bool bn_bulk_bwd_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MCD_BN_BULK_BWD"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
+// (bulk-staged BACKWARD kernels were tried and dropped: faster alone - 512 channels 63 -> 58 us - but slower inside the
+// iteration, 137.0 -> 138.2 ms: backward BatchNorm kernels run next to the wgrad kernels of the side stream, and a block
+// that needs 50 - 100 KB of shared memory cannot share an SM with a 190 KB wgrad CTA the way these register-staged
+// blocks do.)
 
 static inline int rows_grid(int64_t P, int Cs, int rows_per_thread, int max_blocks) {
   int rpi = 256 / (Cs / 8);
@@ -903,24 +695,6 @@ int mcd_bn_bwd_reduce(const void* dz_nhwc, const void* z_nhwc, const void* y_nhw
   MCD_REQUIRE(!relu || z_nhwc, "bn_bwd_reduce: relu needs z");
   MCD_REQUIRE(Cs == C && C % 8 == 0 && Cs <= 2048, "bn_bwd_reduce: needs dense channels (C=%d Cs=%d)", C, Cs);
   MCD_REQUIRE(!res_mean || (res_nhwc && res_rstd), "bn_bwd_reduce: residual stats without residual");
-  {
-    const int vpr = Cs / 8;
-    if (bn_bulk_bwd_enabled() && vpr >= 2 && vpr <= 256 && (256 % vpr) == 0 && P * (int64_t)Cs * 2 >= (8ll << 20)) {
-      BulkSrc src{};
-      src.p[src.n++] = (const uint8_t*)dz_nhwc; src.p[src.n++] = (const uint8_t*)y_nhwc;
-      if (relu) src.p[src.n++] = (const uint8_t*)z_nhwc;
-      if (res_mean) src.p[src.n++] = (const uint8_t*)res_nhwc;
-      const int rows_per_tile = max(1, kBnBwdTileBytes / (Cs * 2));
-      const int64_t ntiles = (P + rows_per_tile - 1) / rows_per_tile;
-      const int smem = kBnStages * src.n * kBnBwdTileBytes + 7 * Cs * (int)sizeof(float) + 64;
-      if (ntiles < (1ll << 30)) {
-        if (ensure_dyn_smem<bn_bwd_reduce_bulk_kernel>(smem, "bn_bwd_reduce") != MCD_OK) return MCD_E_CUDA;
-        bn_bwd_reduce_bulk_kernel<<<(int)min64(ntiles, 148 * 2), 256, smem, (cudaStream_t)stream>>>(
-            src, mean, rstd, res_mean, res_rstd, relu, sums, P, C, Cs, rows_per_tile, (int)ntiles);
-        return check_launch("bn_bwd_reduce");
-      }
-    }
-  }
   int grid = rows_grid(P, Cs, 8, 148 * 2);     // two resident blocks per SM (launch bounds): one full wave
   if (ensure_dyn_smem<bn_reduce_kernel<1>>(7 * Cs * (int)sizeof(float), "bn_bwd_reduce") != MCD_OK) return MCD_E_CUDA;
   bn_reduce_kernel<1><<<grid, 256, 7 * Cs * sizeof(float), (cudaStream_t)stream>>>(
@@ -947,26 +721,6 @@ int mcd_bn_bwd_apply(const void* dz_nhwc, const void* z_nhwc, const void* y_nhwc
   BwdBranch b1{gamma, mean, rstd, training};
   BwdBranch b2{res_gamma, res_mean, res_rstd, res_training};
   MCD_REQUIRE(Cs <= 2048, "bn_bwd_apply: channel stride %d unsupported", Cs);
-  {
-    const int vpr = Cs / 8;
-    const int has_res_bn = dres_nhwc && res_gamma;
-    if (bn_bulk_bwd_enabled() && vpr >= 2 && vpr <= 256 && (256 % vpr) == 0 && P * (int64_t)Cs * 2 >= (8ll << 20)) {
-      BulkSrc src{};
-      src.p[src.n++] = (const uint8_t*)dz_nhwc; src.p[src.n++] = (const uint8_t*)y_nhwc;
-      if (relu) src.p[src.n++] = (const uint8_t*)z_nhwc;
-      if (has_res_bn) src.p[src.n++] = (const uint8_t*)res_nhwc;
-      const int rows_per_tile = max(1, kBnBwdTileBytes / (Cs * 2));
-      const int64_t ntiles = (P + rows_per_tile - 1) / rows_per_tile;
-      const int smem = kBnStages * src.n * kBnBwdTileBytes + 6 * Cs * (int)sizeof(float) + 64;
-      if (ntiles < (1ll << 30)) {
-        if (ensure_dyn_smem<bn_bwd_apply_bulk_kernel>(smem, "bn_bwd_apply") != MCD_OK) return MCD_E_CUDA;
-        bn_bwd_apply_bulk_kernel<<<(int)min64(ntiles, 148 * 2), 256, smem, (cudaStream_t)stream>>>(
-            src, b1, sums, relu, (__nv_bfloat16*)dy_nhwc, dgamma, dbeta, b2, has_res_bn, (__nv_bfloat16*)dres_nhwc,
-            dres_gamma, dres_beta, (float)(1.0 / (double)P), P, Cs, C, sums_kind, rows_per_tile, (int)ntiles);
-        return check_launch("bn_bwd_apply");
-      }
-    }
-  }
   int grid = rows_grid(P, Cs, 4, 148 * 6);
   if (ensure_dyn_smem<bn_bwd_apply_kernel>(6 * Cs * (int)sizeof(float), "bn_bwd_apply") != MCD_OK) return MCD_E_CUDA;
   bn_bwd_apply_kernel<<<grid, 256, 6 * Cs * sizeof(float), (cudaStream_t)stream>>>(

@@ -230,23 +230,9 @@ def test_bn_act_fwd_bwd(cuda_dev, mode, training):
 
 @pytest.mark.parametrize("mode", ["plain", "identity", "downsample"])
 def test_bn_act_large_bulk_staged(cuda_dev, mode):
-    """a tensor large enough (9.3 MB, ragged last tile) for the bulk-copy staged kernels: forward by default, the
-    backward apply / reduce kernels when the process runs with MCD_BN_BULK_BWD=1 (test_bn_bulk_backward_kernels)"""
+    """a tensor large enough (9.3 MB, ragged last tile) for the bulk-copy staged forward kernel (csrc/bn.cu
+    bn_forward_bulk_kernel; smaller tensors take the register-staged kernel)"""
     _bn_act_case(cuda_dev, mode, True, (3, 64, 150, 161))
-
-
-def test_bn_bulk_backward_kernels(cuda_dev):
-    """the bulk-staged backward kernels are off by default (slower next to the wgrad stream, csrc/bn.cu): run the
-    large-tensor cases in a process that enables them"""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MCD_BN_BULK_BWD="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-q", "-p",
-                        "no:cacheprovider", "-k", "bn_act_large"], cwd=root, env=env, capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def _bn_act_case(cuda_dev, mode, training, shape):
