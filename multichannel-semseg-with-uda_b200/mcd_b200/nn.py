@@ -229,10 +229,10 @@ class _ConvFn(torch.autograd.Function):
     """a convolution on its own: the planar fp32 score-map heads (`seg`, decoder outputs) and generic use."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, mod, planar, x_bn_y=None):
+    def forward(ctx, x, weight, bias, mod, planar):
         g = mod.geom(x.shape)
         y, _ = ops.conv_fprop(x, mod.packed(0, g), bias, g, planar=planar)
-        ctx.mod, ctx.g, ctx.planar, ctx.x_bn_y = mod, g, planar, x_bn_y
+        ctx.mod, ctx.g, ctx.planar = mod, g, planar
         ctx.has_bias = bias is not None
         ctx.w_tag = _weight_tag(weight)
         ctx.save_for_backward(x)
@@ -244,8 +244,8 @@ class _ConvFn(torch.autograd.Function):
         dy = ops.to_nhwc(dy, grad=True) if ctx.planar else _as_nhwc_grad(dy)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         dx, dw, db = _conv_backward(ctx.mod, ctx.g, x, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1], want_db,
-                                    ctx.x_bn_y, ctx.w_tag)
-        return dx, dw, db, None, None, None
+                                    None, ctx.w_tag)
+        return dx, dw, db, None, None
 
 
 class Conv2d(nn.Conv2d):
@@ -314,13 +314,7 @@ class Conv2d(nn.Conv2d):
         return x
 
     def forward(self, x):
-        # x = relu(bn(x_bn_y)) of a unit whose only reader is this convolution: its BatchNorm backward may start in
-        # this convolution's dgrad epilogue (direct-gradient mode, see _UnitFn)
-        bn_y = getattr(x, "_mcd_bn_y", None) if getattr(x, "_mcd_sole", False) else None
-        x = self.prepare(x)
-        if bn_y is not None and (tuple(bn_y.shape) != tuple(x.shape) or x.shape[1] != self.in_channels):
-            bn_y = None
-        return _ConvFn.apply(x, self.weight, self.bias, self, self.planar_out, bn_y)
+        return _ConvFn.apply(self.prepare(x), self.weight, self.bias, self, self.planar_out)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,9 +65,7 @@ class DRNSegBase(nn.Module):
         _he_init(self.seg)
 
     def forward(self, x):
-        h = self.base(x)
-        h._mcd_sole = True      # `seg` is the only reader of the trunk output (fused BatchNorm backward, mcd_b200.nn)
-        return self.seg(h)
+        return self.seg(self.base(x))
 
     def optim_parameters(self, memo=None):
         for param in self.base.parameters():
@@ -153,9 +151,8 @@ class CBR(nn.Module):
                            dilation=dilation, groups=groups, bias=bias)
         self.bn = BatchNorm2d(out_channels)
 
-    def forward(self, x, sole=False):
-        # sole: this convolution is the only reader of x (see mcd_b200.nn._UnitFn: fused BatchNorm backward)
-        return conv_bn_act(self.conv, self.bn, x, relu=True, sole=sole)
+    def forward(self, x):
+        return conv_bn_act(self.conv, self.bn, x, relu=True)
 
 
 class ThreeLayerDecoder(nn.Module):
@@ -166,9 +163,7 @@ class ThreeLayerDecoder(nn.Module):
         self.conv3 = Conv2d(512, output_ch, kernel_size=1, planar_out=True)
 
     def forward(self, x):
-        h = self.cbr2(self.cbr1(x), sole=True)
-        h._mcd_sole = True          # conv3 is its only reader
-        return self.conv3(h)
+        return self.conv3(self.cbr2(self.cbr1(x)))
 
 
 def _scalar_param():
