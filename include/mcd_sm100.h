@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 19
+#define MCD_ABI_VERSION 20
 
 enum {
   MCD_OK = 0,
@@ -363,6 +363,42 @@ int mcd_fast_hist(const void* gt, int gt_is_int64, const void* pred, int pred_is
 /* transform.py:285-294 unnormalize: uint8((x * std + mean) * 255) in float64, x fp32 [N,3,H,W] -> uint8 [N,H,W,3]. */
 int mcd_unnormalize_u8(const float* x, void* dst, const double* mean3, const double* std3, int N, int H, int W,
                        int device, void* stream);
+
+/* ---- option surface around the hot path: fusion heads, FuseDRNSegBase, torch_up ----------- */
+/* FuseDRNSegBase.forward `x = torch.add(x, x_dK)` (models/dilated_fcn.py:308-329) and AddFusion on ver2 trunk
+ * features (models/fusion.py:24-29): z = a + b on dense IEEE-half nhwc activations, written as IEEE half and, when
+ * out_bf16 != NULL, as the bfloat16 twin.  numel % 8 == 0. */
+int mcd_add_nhwc(const void* a_f16, const void* b_f16, void* out_f16, void* out_bf16, int64_t numel, int device,
+                 void* stream);
+/* GateFusion (models/fusion.py:17-21): out = x1 * sigmoid(a) + x2 * (1 - sigmoid(a)), a = conv(cat(x1, x2));
+ * all planar fp32 of one shape.  Backward: any of dx1 / dx2 / dgate_logits may be NULL. */
+int mcd_gate_fuse_fwd(const float* x1, const float* x2, const float* gate_logits, float* out, int64_t numel,
+                      int device, void* stream);
+int mcd_gate_fuse_bwd(const float* x1, const float* x2, const float* gate_logits, const float* dout, float* dx1,
+                      float* dx2, float* dgate_logits, int64_t numel, int device, void* stream);
+/* F.softmax over dim 1 of a planar fp32 [N,C,HW] tensor (ScoreGateFusion, models/fusion.py:13-15) and its backward
+ * dx = p * (dp - sum_c dp * p). */
+int mcd_softmax_ch_fwd(const float* x, float* p, int N, int C, int64_t HW, int device, void* stream);
+int mcd_softmax_ch_bwd(const float* p, const float* dp, float* dx, int N, int C, int64_t HW, int device,
+                       void* stream);
+/* torch.cat([a, b], 1) of planar fp32 tensors [N,Ca,HW], [N,Cb,HW] (models/fusion.py:16,37,47) and its backward
+ * (either output of the split may be NULL). */
+int mcd_cat2_f32(const float* a, int Ca, const float* b, int Cb, float* out, int N, int64_t HW, int device,
+                 void* stream);
+int mcd_split2_f32(const float* src, float* a, int Ca, float* b, int Cb, int N, int64_t HW, int device,
+                   void* stream);
+/* F.sigmoid on fp32 (seg2bd boundary maps, models/dilated_fcn.py:965-966); backward from the OUTPUT y. */
+int mcd_sigmoid_fwd(const float* x, float* y, int64_t numel, int device, void* stream);
+int mcd_sigmoid_bwd(const float* y, const float* dy, float* dx, int64_t numel, int device, void* stream);
+/* out = a + b (+ c, may be NULL) on fp32: the shortcut decoders' h1 + h2 + h3 (models/dilated_fcn.py:875,884,904). */
+int mcd_add3_f32(const float* a, const float* b, const float* c, float* out, int64_t numel, int device,
+                 void* stream);
+/* nn.UpsamplingBilinear2d(scale_factor=s) = bilinear with align_corners=True (`use_torch_up`,
+ * models/dilated_fcn.py:354-355,443-444).  Same tensor conventions as mcd_bilinear_up_fwd / _bwd; any s >= 1. */
+int mcd_bilinear_ac_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s, int device,
+                           void* stream);
+int mcd_bilinear_ac_up_bwd(const void* dout, int dout_f32, float* dx, int N, int C, int h, int w_, int s, int device,
+                           void* stream);
 
 /* ---- optimiser (models/model_util.py:289-302: SGD momentum / weight decay, torch semantics) - */
 int mcd_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t numel, float lr,

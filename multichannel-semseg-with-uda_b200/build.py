@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcd_sm100.so")
 SOURCES = ["api.cu", "layout.cu", "conv_direct.cu", "conv_umma.cu", "conv_rows.cu", "conv_api.cu", "bn.cu",
-           "heads.cu", "loss.cu", "headloss.cu", "pipeline.cu"]
+           "heads.cu", "loss.cu", "headloss.cu", "pipeline.cu", "variants.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

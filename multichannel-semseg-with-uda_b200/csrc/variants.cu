@@ -1,0 +1,313 @@
+// variants.cu — the small memory-bound kernels behind the option surface around the MCD hot path (SURVEY.md
+// section 8 row f4): the Gate / Concat fusion heads (models/fusion.py:6-50), FuseDRNSegBase's per-stage adds
+// (models/dilated_fcn.py:294-331), nn.UpsamplingBilinear2d (align_corners=True; `use_torch_up`, :354-355,443-444),
+// F.softmax over channels (ScoreGateFusion, fusion.py:13-15) and F.sigmoid of the seg -> boundary convolution
+// (dilated_fcn.py:965-966).  All of them are single-pass, vectorised where the geometry allows, HBM-bound.
+#include "common.cuh"
+
+namespace mcd {
+
+// ---- z = a + b on nhwc IEEE-half activations, written as IEEE half and (optionally) the bf16 twin ----------------
+__global__ void __launch_bounds__(256)
+add_nhwc_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out16,
+                uint4* __restrict__ twin, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float fa[8], fb[8];
+    unpack8h(a[i], fa);
+    unpack8h(b[i], fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+    out16[i] = pack8h(fa);
+    if (twin) twin[i] = pack8(fa);
+  }
+}
+
+// ---- out = x1 * sigmoid(a) + x2 * (1 - sigmoid(a))   (GateFusion, models/fusion.py:17-21) ---------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+__global__ void __launch_bounds__(256)
+gate_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ a,
+                float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = sigmoidf_(a[i]);
+    out[i] = x1[i] * g + x2[i] * (1.f - g);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ a,
+                const float* __restrict__ dout, float* __restrict__ dx1, float* __restrict__ dx2,
+                float* __restrict__ da, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = sigmoidf_(a[i]), d = dout[i];
+    if (dx1) dx1[i] = d * g;
+    if (dx2) dx2[i] = d * (1.f - g);
+    if (da) da[i] = d * (x1[i] - x2[i]) * g * (1.f - g);
+  }
+}
+
+// ---- softmax over the channel axis of a planar fp32 tensor (one thread per pixel, coalesced across pixels) -------
+__global__ void __launch_bounds__(256)
+softmax_ch_fwd_kernel(const float* __restrict__ x, float* __restrict__ p, int C, int64_t HW, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, px = i % HW;
+    const float* xp = x + n * C * HW + px;
+    float* pp = p + n * C * HW + px;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, xp[c * HW]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += __expf(xp[c * HW] - m);
+    const float inv = 1.f / s;
+    for (int c = 0; c < C; ++c) pp[c * HW] = __expf(xp[c * HW] - m) * inv;
+  }
+}
+
+// dx = p * (dp - sum_c dp * p)
+__global__ void __launch_bounds__(256)
+softmax_ch_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dx, int C,
+                      int64_t HW, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, px = i % HW;
+    const int64_t base = n * C * HW + px;
+    float dot = 0.f;
+    for (int c = 0; c < C; ++c) dot = fmaf(dp[base + c * HW], p[base + c * HW], dot);
+    for (int c = 0; c < C; ++c) dx[base + c * HW] = p[base + c * HW] * (dp[base + c * HW] - dot);
+  }
+}
+
+// ---- torch.cat([a, b], 1) and its backward (split) on planar fp32 tensors ------------------------------------------
+// cat == 1: ab[n][0:Ca] = a[n], ab[n][Ca:] = b[n];  cat == 0: the reverse copy (a / b may be null)
+__global__ void __launch_bounds__(256)
+cat2_kernel(float* __restrict__ a, float* __restrict__ b, float* __restrict__ ab, int64_t ea, int64_t eb,
+            int64_t total, int cat) {
+  const int64_t e = ea + eb;   // elements per image
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / e, r = i % e;
+    float* part = r < ea ? (a ? a + n * ea + r : nullptr) : (b ? b + n * eb + (r - ea) : nullptr);
+    if (!part) continue;
+    if (cat) ab[i] = *part; else *part = ab[i];
+  }
+}
+
+// ---- sigmoid ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = sigmoidf_(x[i]);
+}
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * y[i] * (1.f - y[i]);
+}
+
+// ---- out = a + b (+ c) on fp32 tensors (the shortcut decoders' h1 + h2 + h3, dilated_fcn.py:875,884,904) -----------
+__global__ void __launch_bounds__(256)
+add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+            float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i] + (c ? c[i] : 0.f);
+}
+
+// ---- bilinear upsample, align_corners=True (nn.UpsamplingBilinear2d) -------------------------------------------------
+// ATen's area_pixel_compute_scale: scale = (in - 1) / (out - 1) for out > 1, else 0; src = scale * o, in float.
+__device__ __forceinline__ void bil_src_ac(int o, float scale, int in, int* i0, int* i1, float* lam) {
+  const float src = scale * (float)o;
+  int a = (int)src;
+  if (a > in - 1) a = in - 1;
+  *i0 = a;
+  *i1 = a + (a < in - 1 ? 1 : 0);
+  *lam = src - (float)a;
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256)
+bilinear_ac_fwd_kernel(const float* __restrict__ x, void* __restrict__ out, int h, int wd, int H, int W, float sh,
+                       float sw, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % W);
+    const int oh = (int)((i / W) % H);
+    const int64_t nc = i / ((int64_t)W * H);
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bil_src_ac(oh, sh, h, &h0, &h1, &lh);
+    bil_src_ac(ow, sw, wd, &w0, &w1, &lw);
+    const float* r0 = x + (nc * h + h0) * wd;
+    const float* r1 = x + (nc * h + h1) * wd;
+    // ATen's weighting order: h0lambda * (w0lambda * p00 + w1lambda * p01) + h1lambda * (w0lambda * p10 + w1lambda * p11)
+    const float l0h = 1.f - lh, l0w = 1.f - lw;
+    const float v = l0h * (l0w * r0[w0] + lw * r0[w1]) + lh * (l0w * r1[w0] + lw * r1[w1]);
+    if (OUT_F32) reinterpret_cast<float*>(out)[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(out)[i] = f2bf(v);
+  }
+}
+
+// block = one (n*c, ih) low-resolution row, separable gather like bilinear_bwd_kernel (heads.cu)
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+bilinear_ac_bwd_kernel(const void* __restrict__ dout, float* __restrict__ dx, int h, int wd, int H, int W, float sh,
+                       float sw) {
+  extern __shared__ float col[];  // W floats
+  const int64_t nc = blockIdx.x;
+  const int ih = blockIdx.y;
+  int oh_lo = 0, oh_hi = H - 1;
+  if (sh > 0.f) {
+    oh_lo = max(0, (int)floorf((float)(ih - 1) / sh) - 1);
+    oh_hi = min(H - 1, (int)ceilf((float)(ih + 1) / sh) + 1);
+  }
+  for (int ow = threadIdx.x; ow < W; ow += blockDim.x) {
+    float acc = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int h0, h1; float lh;
+      bil_src_ac(oh, sh, h, &h0, &h1, &lh);
+      const float wgt = (h0 == ih ? 1.f - lh : 0.f) + (h1 == ih ? lh : 0.f);
+      if (wgt == 0.f) continue;
+      const int64_t o = (nc * H + oh) * (int64_t)W + ow;
+      const float v = IN_F32 ? reinterpret_cast<const float*>(dout)[o]
+                             : bf2f(reinterpret_cast<const __nv_bfloat16*>(dout)[o]);
+      acc = fmaf(wgt, v, acc);
+    }
+    col[ow] = acc;
+  }
+  __syncthreads();
+  for (int iw = threadIdx.x; iw < wd; iw += blockDim.x) {
+    int ow_lo = 0, ow_hi = W - 1;
+    if (sw > 0.f) {
+      ow_lo = max(0, (int)floorf((float)(iw - 1) / sw) - 1);
+      ow_hi = min(W - 1, (int)ceilf((float)(iw + 1) / sw) + 1);
+    }
+    float acc = 0.f;
+    for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+      int w0, w1; float lw;
+      bil_src_ac(ow, sw, wd, &w0, &w1, &lw);
+      const float wgt = (w0 == iw ? 1.f - lw : 0.f) + (w1 == iw ? lw : 0.f);
+      acc = fmaf(wgt, col[ow], acc);
+    }
+    dx[(nc * h + ih) * wd + iw] = acc;
+  }
+}
+
+static inline int grid_for(int64_t n) { return (int)max64(1, min64((n + 255) / 256, 148 * 16)); }
+
+}  // namespace mcd
+
+using namespace mcd;
+
+extern "C" {
+
+int mcd_add_nhwc(const void* a_f16, const void* b_f16, void* out_f16, void* out_bf16, int64_t numel, int device,
+                 void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(a_f16 && b_f16 && out_f16 && numel > 0 && numel % 8 == 0, "add_nhwc: bad arguments");
+  add_nhwc_kernel<<<grid_for(numel / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)a_f16, (const uint4*)b_f16, (uint4*)out_f16, (uint4*)out_bf16, numel / 8);
+  return check_launch("add_nhwc");
+}
+
+int mcd_gate_fuse_fwd(const float* x1, const float* x2, const float* gate_logits, float* out, int64_t numel,
+                      int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x1 && x2 && gate_logits && out && numel > 0, "gate_fuse_fwd: bad arguments");
+  gate_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x1, x2, gate_logits, out, numel);
+  return check_launch("gate_fuse_fwd");
+}
+
+int mcd_gate_fuse_bwd(const float* x1, const float* x2, const float* gate_logits, const float* dout, float* dx1,
+                      float* dx2, float* dgate_logits, int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x1 && x2 && gate_logits && dout && numel > 0, "gate_fuse_bwd: bad arguments");
+  gate_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x1, x2, gate_logits, dout, dx1, dx2,
+                                                                     dgate_logits, numel);
+  return check_launch("gate_fuse_bwd");
+}
+
+int mcd_softmax_ch_fwd(const float* x, float* p, int N, int C, int64_t HW, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && p && N > 0 && C > 0 && HW > 0, "softmax_ch_fwd: bad arguments");
+  const int64_t total = (int64_t)N * HW;
+  softmax_ch_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, p, C, HW, total);
+  return check_launch("softmax_ch_fwd");
+}
+
+int mcd_softmax_ch_bwd(const float* p, const float* dp, float* dx, int N, int C, int64_t HW, int device,
+                       void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(p && dp && dx && N > 0 && C > 0 && HW > 0, "softmax_ch_bwd: bad arguments");
+  const int64_t total = (int64_t)N * HW;
+  softmax_ch_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(p, dp, dx, C, HW, total);
+  return check_launch("softmax_ch_bwd");
+}
+
+int mcd_cat2_f32(const float* a, int Ca, const float* b, int Cb, float* out, int N, int64_t HW, int device,
+                 void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(a && b && out && N > 0 && Ca > 0 && Cb > 0 && HW > 0, "cat2_f32: bad arguments");
+  const int64_t total = (int64_t)N * (Ca + Cb) * HW;
+  cat2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(a), const_cast<float*>(b), out,
+                                                                 Ca * HW, Cb * HW, total, 1);
+  return check_launch("cat2_f32");
+}
+
+int mcd_split2_f32(const float* src, float* a, int Ca, float* b, int Cb, int N, int64_t HW, int device,
+                   void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(src && (a || b) && N > 0 && Ca > 0 && Cb > 0 && HW > 0, "split2_f32: bad arguments");
+  const int64_t total = (int64_t)N * (Ca + Cb) * HW;
+  cat2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a, b, const_cast<float*>(src), Ca * HW, Cb * HW,
+                                                                 total, 0);
+  return check_launch("split2_f32");
+}
+
+int mcd_sigmoid_fwd(const float* x, float* y, int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && y && numel > 0, "sigmoid_fwd: bad arguments");
+  sigmoid_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x, y, numel);
+  return check_launch("sigmoid_fwd");
+}
+
+int mcd_sigmoid_bwd(const float* y, const float* dy, float* dx, int64_t numel, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(y && dy && dx && numel > 0, "sigmoid_bwd: bad arguments");
+  sigmoid_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, numel);
+  return check_launch("sigmoid_bwd");
+}
+
+int mcd_add3_f32(const float* a, const float* b, const float* c, float* out, int64_t numel, int device,
+                 void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(a && b && out && numel > 0, "add3_f32: bad arguments");
+  add3_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(a, b, c, out, numel);
+  return check_launch("add3_f32");
+}
+
+int mcd_bilinear_ac_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s, int device,
+                           void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(x && out && N > 0 && C > 0 && h > 0 && w_ > 0 && s >= 1, "bilinear_ac_up_fwd: bad arguments");
+  const int H = h * s, W = w_ * s;
+  const float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sw = W > 1 ? (float)(w_ - 1) / (float)(W - 1) : 0.f;
+  const int64_t total = (int64_t)N * C * H * W;
+  if (out_f32)
+    bilinear_ac_fwd_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, out, h, w_, H, W, sh, sw, total);
+  else
+    bilinear_ac_fwd_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, out, h, w_, H, W, sh, sw, total);
+  return check_launch("bilinear_ac_up_fwd");
+}
+
+int mcd_bilinear_ac_up_bwd(const void* dout, int dout_f32, float* dx, int N, int C, int h, int w_, int s, int device,
+                           void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(dout && dx && N > 0 && C > 0 && h > 0 && w_ > 0 && s >= 1, "bilinear_ac_up_bwd: bad arguments");
+  const int H = h * s, W = w_ * s;
+  MCD_REQUIRE((size_t)W * sizeof(float) <= 48 * 1024, "bilinear_ac_up_bwd: output rows wider than 12288 unsupported");
+  const float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sw = W > 1 ? (float)(w_ - 1) / (float)(W - 1) : 0.f;
+  dim3 grid((unsigned)(N * C), (unsigned)h);
+  const size_t smem = sizeof(float) * (size_t)W;
+  if (dout_f32)
+    bilinear_ac_bwd_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, dx, h, w_, H, W, sh, sw);
+  else
+    bilinear_ac_bwd_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(dout, dx, h, w_, H, W, sh, sw);
+  return check_launch("bilinear_ac_up_bwd");
+}
+
+}  // extern "C"

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # MCD_LIB_PATH: an alternative build of the same library (A/B measurements of compile-time variants)
 LIB_PATH = os.environ.get("MCD_LIB_PATH") or os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
@@ -91,6 +91,18 @@ _SIGNATURES = {
     "mcd_fast_hist": (c_int, [P, c_int, P, c_int, c_int, c_int64, P, c_int, P]),
     "mcd_unnormalize_u8": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "mcd_argmax_entropy": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_add_nhwc": (c_int, [P, P, P, P, c_int64, c_int, P]),
+    "mcd_gate_fuse_fwd": (c_int, [P, P, P, P, c_int64, c_int, P]),
+    "mcd_gate_fuse_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, P]),
+    "mcd_softmax_ch_fwd": (c_int, [P, P, c_int, c_int, c_int64, c_int, P]),
+    "mcd_softmax_ch_bwd": (c_int, [P, P, P, c_int, c_int, c_int64, c_int, P]),
+    "mcd_cat2_f32": (c_int, [P, c_int, P, c_int, P, c_int, c_int64, c_int, P]),
+    "mcd_split2_f32": (c_int, [P, P, c_int, P, c_int, c_int, c_int64, c_int, P]),
+    "mcd_sigmoid_fwd": (c_int, [P, P, c_int64, c_int, P]),
+    "mcd_sigmoid_bwd": (c_int, [P, P, P, c_int64, c_int, P]),
+    "mcd_add3_f32": (c_int, [P, P, P, P, c_int64, c_int, P]),
+    "mcd_bilinear_ac_up_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_bilinear_ac_up_bwd": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_int, c_int, P]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -308,7 +308,7 @@ class Conv2d(nn.Conv2d):
         return hit[1], hit[2]
 
     def prepare(self, x):
-        x = ops.to_nhwc(x)
+        x = to_nhwc_act(x)
         if x.shape[1] < self.in_channels:
             raise ValueError("Conv2d expected >= %d input channels, got %d" % (self.in_channels, x.shape[1]))
         return x
@@ -539,9 +539,18 @@ class SoleChain(nn.Sequential):
 
     def forward(self, x):
         mods = list(self.children())
-        for i, m in enumerate(mods):
-            x = m(x)
-            if i + 1 < len(mods):
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if (isinstance(m, Conv2d) and i + 2 < len(mods) and isinstance(mods[i + 1], BatchNorm2d)
+                    and isinstance(mods[i + 2], nn.ReLU)):
+                # DRN arch 'C' registers its stem as three separate children (models/drn.py:113-119)
+                x = conv_bn_act(m, mods[i + 1], x, relu=True, sole=getattr(x, "_mcd_sole", False))
+                i += 3
+            else:
+                x = m(x)
+                i += 1
+            if i < len(mods):
                 x._mcd_sole = True
         return x
 
@@ -608,3 +617,191 @@ class BilinearUpsample(nn.Module):
 
     def forward(self, x):
         return _BilinearFn.apply(_planar_f32(x), self.scale_factor, self.out_f32 or _logits_dtype == F32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Option surface around the hot path (csrc/variants.cu): the pieces the Gate / Concat fusion heads, FuseDRNSegBase,
+# the `ver2` / `use_torch_up` heads and the shortcut / seg2bd decoder options are composed of.
+class _AddNHWCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, twin):
+        z = ops.add_nhwc(a, b, twin=twin)
+        ctx.set_materialize_grads(False)
+        z16 = getattr(z, "_mcd_h16", None)
+        if z16 is None:
+            return z, torch.empty(0, dtype=F16, device=z.device)
+        ctx.mark_non_differentiable(z16)
+        return z, z16
+
+    @staticmethod
+    def backward(ctx, dz, _):
+        if dz is None:
+            return None, None, None
+        dz = _as_nhwc_grad(dz)
+        return dz, dz, None
+
+
+def add_nhwc(a, b):
+    """torch.add of two nhwc activations (FuseDRNSegBase, models/dilated_fcn.py:308-329; AddFusion on trunk features)."""
+    return _with_twin(_AddNHWCFn.apply(ops.to_nhwc(a), ops.to_nhwc(b), ops.want_twin()))
+
+
+class _ToPlanarFn(torch.autograd.Function):
+    """nhwc activation -> planar fp32 NCHW (first c channels); backward: the gradient as a bf16 nhwc tensor."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cs = x.shape[1]
+        return ops.to_nchw_f32(x, c)
+
+    @staticmethod
+    def backward(ctx, d):
+        if d is None:
+            return None, None
+        d = ops._pf32(d)
+        if d.shape[1] != ctx.cs:
+            raise RuntimeError("mcd_b200: to_planar with a channel subset is forward-only")
+        return ops.to_nhwc(d, grad=True), None
+
+
+class _ToNHWCFn(torch.autograd.Function):
+    """planar fp32 NCHW (produced by an autograd op) -> nhwc activation; backward: planar fp32 gradient."""
+
+    @staticmethod
+    def forward(ctx, x, twin):
+        ctx.c = x.shape[1]
+        z = ops.to_nhwc(x, twin=twin)
+        ctx.set_materialize_grads(False)
+        z16 = getattr(z, "_mcd_h16", None)
+        if z16 is None:
+            return z, torch.empty(0, dtype=F16, device=z.device)
+        ctx.mark_non_differentiable(z16)
+        return z, z16
+
+    @staticmethod
+    def backward(ctx, dz, _):
+        if dz is None:
+            return None, None
+        return ops.to_nchw_f32(_as_nhwc_grad(dz), ctx.c), None
+
+
+def to_planar(x):
+    """planar fp32 view of an activation for the fp32 element-wise fusion kernels (autograd-aware)."""
+    if ops.is_nhwc(x):
+        return _ToPlanarFn.apply(x, None)
+    return _planar_f32(x)
+
+
+def to_nhwc_act(x):
+    """nhwc activation from whatever a module hands to a convolution (autograd-aware for planar fp32 inputs)."""
+    if ops.is_nhwc(x):
+        return x
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _with_twin(_ToNHWCFn.apply(_planar_f32(x), True))
+    return ops.to_nhwc(x)
+
+
+class _GateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, a):
+        ctx.save_for_backward(x1, x2, a)
+        return ops.gate_fuse_fwd(x1, x2, a)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x1, x2, a = ctx.saved_tensors
+        return tuple(ops.gate_fuse_bwd(x1, x2, a, dout, want=ctx.needs_input_grad[:3]))
+
+
+def gate_fuse(x1, x2, gate_logits):
+    """x1 * sigmoid(a) + x2 * (1 - sigmoid(a)), planar fp32 (GateFusion, models/fusion.py:17-21)."""
+    return _GateFn.apply(_planar_f32(x1), _planar_f32(x2), _planar_f32(gate_logits))
+
+
+class _SoftmaxChFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        p = ops.softmax_ch_fwd(x)
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        return ops.softmax_ch_bwd(p, dp)
+
+
+def softmax_ch(x):
+    return _SoftmaxChFn.apply(_planar_f32(x))
+
+
+class _Cat2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[1]
+        return ops.cat2_f32(a, b)
+
+    @staticmethod
+    def backward(ctx, d):
+        return ops.split2_f32(d, ctx.ca, want=ctx.needs_input_grad[:2])
+
+
+def cat2(a, b):
+    """torch.cat([a, b], 1) on planar fp32 tensors."""
+    return _Cat2Fn.apply(_planar_f32(a), _planar_f32(b))
+
+
+class _SigmoidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = ops.sigmoid_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ops.sigmoid_bwd(y, dy)
+
+
+def sigmoid(x):
+    return _SigmoidFn.apply(_planar_f32(x))
+
+
+class _Add3Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, c):
+        return ops.add3_f32(a, b, c)
+
+    @staticmethod
+    def backward(ctx, d):
+        d = ops._pf32(d)
+        return d, d, (d if ctx.needs_input_grad[2] else None)
+
+
+def add3(a, b, c=None):
+    """a + b (+ c) on planar fp32 tensors of one shape."""
+    return _Add3Fn.apply(_planar_f32(a), _planar_f32(b), None if c is None else _planar_f32(c))
+
+
+class _BilinearACFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, out_f32):
+        ctx.s = s
+        return ops.bilinear_ac_up_fwd(x, s, out_f32)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return ops.bilinear_ac_up_bwd(dout, ctx.s), None, None
+
+
+class UpsamplingBilinear2d(nn.Module):
+    """nn.UpsamplingBilinear2d(scale_factor=s): bilinear with align_corners=True (`use_torch_up`,
+    models/dilated_fcn.py:354-355,443-444).  Output dtype: `logits_dtype`."""
+
+    def __init__(self, scale_factor, out_f32=False):
+        super().__init__()
+        self.scale_factor, self.out_f32 = int(scale_factor), out_f32
+
+    def forward(self, x):
+        return _BilinearACFn.apply(_planar_f32(x), self.scale_factor, self.out_f32 or _logits_dtype == F32)

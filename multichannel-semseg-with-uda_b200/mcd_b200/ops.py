@@ -811,6 +811,121 @@ def sgd_step(param, grad, buf, lr, momentum, weight_decay, first_step):
                                      _stream(param)), "sgd_step")
 
 
+# ---- option surface around the hot path (csrc/variants.cu) ----------------------------------------
+def _pf32(t):
+    """planar fp32, contiguous"""
+    if t.dtype != F32:
+        t = t.float()
+    return t.contiguous()
+
+
+def add_nhwc(a, b, twin=None):
+    """a + b on nhwc activations: IEEE half out, plus the bf16 twin (returned, carrying `_mcd_h16`) when recording."""
+    a16, b16_ = h16(a), h16(b)
+    assert is_nhwc(a16) and a16.shape == b16_.shape
+    n, c, h, w = a16.shape
+    twin = want_twin() if twin is None else twin
+    o16 = nhwc_empty(n, c, h, w, a16.device, F16)
+    ob = nhwc_empty(n, c, h, w, a16.device, BF16) if twin else None
+    abi.check(abi.lib().mcd_add_nhwc(_p(a16), _p(b16_), _p(o16), _p(ob), o16.numel(), _dev(o16), _stream(o16)),
+              "add_nhwc")
+    if ob is None:
+        return o16
+    ob._mcd_h16 = o16
+    return ob
+
+
+def gate_fuse_fwd(x1, x2, a):
+    out = torch.empty_like(x1)
+    abi.check(abi.lib().mcd_gate_fuse_fwd(_p(x1), _p(x2), _p(a), _p(out), out.numel(), _dev(out), _stream(out)),
+              "gate_fuse_fwd")
+    return out
+
+
+def gate_fuse_bwd(x1, x2, a, dout, want=(True, True, True)):
+    dout = _pf32(dout)
+    d = [torch.empty_like(x1) if w_ else None for w_ in want]
+    abi.check(abi.lib().mcd_gate_fuse_bwd(_p(x1), _p(x2), _p(a), _p(dout), _p(d[0]), _p(d[1]), _p(d[2]), x1.numel(),
+                                          _dev(x1), _stream(x1)), "gate_fuse_bwd")
+    return d
+
+
+def softmax_ch_fwd(x):
+    n, c = x.shape[:2]
+    p = torch.empty_like(x)
+    abi.check(abi.lib().mcd_softmax_ch_fwd(_p(x), _p(p), n, c, x.numel() // (n * c), _dev(x), _stream(x)),
+              "softmax_ch_fwd")
+    return p
+
+
+def softmax_ch_bwd(p, dp):
+    n, c = p.shape[:2]
+    dp = _pf32(dp)
+    dx = torch.empty_like(p)
+    abi.check(abi.lib().mcd_softmax_ch_bwd(_p(p), _p(dp), _p(dx), n, c, p.numel() // (n * c), _dev(p), _stream(p)),
+              "softmax_ch_bwd")
+    return dx
+
+
+def cat2_f32(a, b):
+    n, ca, cb = a.shape[0], a.shape[1], b.shape[1]
+    assert a.shape[0] == b.shape[0] and a.shape[2:] == b.shape[2:]
+    out = torch.empty((n, ca + cb) + tuple(a.shape[2:]), dtype=F32, device=a.device)
+    abi.check(abi.lib().mcd_cat2_f32(_p(a), ca, _p(b), cb, _p(out), n, a.numel() // (n * ca), _dev(a), _stream(a)),
+              "cat2_f32")
+    return out
+
+
+def split2_f32(src, ca, want=(True, True)):
+    src = _pf32(src)
+    n, c = src.shape[:2]
+    cb = c - ca
+    a = torch.empty((n, ca) + tuple(src.shape[2:]), dtype=F32, device=src.device) if want[0] else None
+    b = torch.empty((n, cb) + tuple(src.shape[2:]), dtype=F32, device=src.device) if want[1] else None
+    if a is None and b is None:
+        return None, None
+    abi.check(abi.lib().mcd_split2_f32(_p(src), _p(a), ca, _p(b), cb, n, src.numel() // (n * c), _dev(src),
+                                       _stream(src)), "split2_f32")
+    return a, b
+
+
+def sigmoid_fwd(x):
+    y = torch.empty_like(x)
+    abi.check(abi.lib().mcd_sigmoid_fwd(_p(x), _p(y), x.numel(), _dev(x), _stream(x)), "sigmoid_fwd")
+    return y
+
+
+def sigmoid_bwd(y, dy):
+    dy = _pf32(dy)
+    dx = torch.empty_like(y)
+    abi.check(abi.lib().mcd_sigmoid_bwd(_p(y), _p(dy), _p(dx), y.numel(), _dev(y), _stream(y)), "sigmoid_bwd")
+    return dx
+
+
+def add3_f32(a, b, c=None):
+    assert a.shape == b.shape and (c is None or c.shape == a.shape)
+    out = torch.empty_like(a)
+    abi.check(abi.lib().mcd_add3_f32(_p(a), _p(b), _p(c), _p(out), a.numel(), _dev(a), _stream(a)), "add3_f32")
+    return out
+
+
+def bilinear_ac_up_fwd(x, s, out_f32=False):
+    n, c, h, wd = x.shape
+    out = torch.empty((n, c, s * h, s * wd), dtype=F32 if out_f32 else BF16, device=x.device)
+    abi.check(abi.lib().mcd_bilinear_ac_up_fwd(_p(x), _p(out), int(out_f32), n, c, h, wd, s, _dev(x), _stream(x)),
+              "bilinear_ac_up_fwd")
+    return out
+
+
+def bilinear_ac_up_bwd(dout, s):
+    dout, f32 = _full(dout)
+    n, c, hh, ww = dout.shape
+    dx = torch.empty((n, c, hh // s, ww // s), dtype=F32, device=dout.device)
+    abi.check(abi.lib().mcd_bilinear_ac_up_bwd(_p(dout), f32, _p(dx), n, c, hh // s, ww // s, s,
+                                               _dev(dout), _stream(dout)), "bilinear_ac_up_bwd")
+    return dx
+
+
 # ---- measurement hook (bench.py roofline) ---------------------------------------------------------
 class ConvProfiler:
     """Records a CUDA-event pair on the launching stream around every convolution call made while active and

@@ -1,4 +1,5 @@
-"""Dilated Residual Network, arch 'D' (BasicBlock: DRN-D-22 / -38; Bottleneck: DRN-D-54 / -105) on libmcd_sm100.
+"""Dilated Residual Network, arch 'D' (BasicBlock: DRN-D-22 / -38; Bottleneck: DRN-D-54 / -105) and arch 'C'
+(DRN-C-26 / -42 / -58: BasicBlock stages 1, 2, 7, 8 instead of plain convolution stacks) on libmcd_sm100.
 
 Drop-in for the reference's models/drn.py on the MCD hot path: same factory names, constructor
 arguments, module tree and therefore the same state_dict keys (reference models/drn.py:103-253 DRN,
@@ -6,8 +7,9 @@ arguments, module tree and therefore the same state_dict keys (reference models/
 BatchNorm, ReLU and the residual add run as fused library kernels on 16-bit NHWC activations.  Bottleneck
 (:62-100) and drn_d_54 / drn_d_105 (:337-348) are the SURVEY 8(f) rank-4 widening: same units, 1x1 / 3x3 / 1x1.
 
-Out of scope here: arch 'C' (drn_c_*, no reference trainer uses it) and the
-model-zoo download (`pretrained=True`, no network: see _load_pretrained).
+Arch 'C' (:113-124,147-153,303-320) registers `conv1`, `bn1`, `relu` as separate children; DRNSegBase's
+`nn.Sequential(*children[:-2])` keeps them separate (state_dict keys base.0 / base.1), mcd_b200.nn.SoleChain runs the
+triple as one fused unit.  Out of scope: the model-zoo download (`pretrained=True`, no network: see _load_pretrained).
 """
 import math
 
@@ -15,7 +17,8 @@ import torch.nn as nn
 
 from mcd_b200.nn import BatchNorm2d, Conv2d, ConvBNReLU, conv_bn_act
 
-__all__ = ['DRN', 'BasicBlock', 'Bottleneck', 'drn_d_22', 'drn_d_38', 'drn_d_54', 'drn_d_105', 'replace_first_conv']
+__all__ = ['DRN', 'BasicBlock', 'Bottleneck', 'drn_c_26', 'drn_c_42', 'drn_c_58', 'drn_d_22', 'drn_d_38', 'drn_d_54',
+           'drn_d_105', 'replace_first_conv']
 
 # stage -> (channels, dilation) of DRN-D; stages 3..6 are residual, 0..2 and 7..8 plain conv stacks
 _CHANNELS = (16, 32, 64, 128, 256, 512, 512, 512)
@@ -95,26 +98,39 @@ class DRN(nn.Module):
     def __init__(self, block, layers, num_classes=1000, channels=_CHANNELS, out_map=False,
                  out_middle=False, pool_size=28, arch='D'):
         super().__init__()
-        if arch != 'D' or block not in (BasicBlock, Bottleneck):
-            raise NotImplementedError("libmcd_sm100 build covers DRN arch 'D' (BasicBlock / Bottleneck) only")
+        if arch not in ('C', 'D') or block not in (BasicBlock, Bottleneck):
+            raise NotImplementedError("libmcd_sm100 build covers DRN arch 'C' / 'D' (BasicBlock / Bottleneck) only")
         self.inplanes = channels[0]
         self.out_map = out_map
         self.out_dim = channels[-1]
         self.out_middle = out_middle
         self.arch = arch
 
-        self.layer0 = ConvBNReLU(
-            Conv2d(3, channels[0], kernel_size=7, stride=1, padding=3, bias=False),
-            BatchNorm2d(channels[0]), nn.ReLU(inplace=True))
-        self.layer1 = self._make_conv_layers(channels[0], layers[0], stride=1)
-        self.layer2 = self._make_conv_layers(channels[1], layers[1], stride=2)
+        if arch == 'C':
+            self.conv1 = Conv2d(3, channels[0], kernel_size=7, stride=1, padding=3, bias=False)
+            self.bn1 = BatchNorm2d(channels[0])
+            self.relu = nn.ReLU(inplace=True)
+            self.layer1 = self._make_layer(BasicBlock, channels[0], layers[0], stride=1)
+            self.layer2 = self._make_layer(BasicBlock, channels[1], layers[1], stride=2)
+        else:
+            self.layer0 = ConvBNReLU(
+                Conv2d(3, channels[0], kernel_size=7, stride=1, padding=3, bias=False),
+                BatchNorm2d(channels[0]), nn.ReLU(inplace=True))
+            self.layer1 = self._make_conv_layers(channels[0], layers[0], stride=1)
+            self.layer2 = self._make_conv_layers(channels[1], layers[1], stride=2)
         self.layer3 = self._make_layer(block, channels[2], layers[2], stride=2)
         self.layer4 = self._make_layer(block, channels[3], layers[3], stride=2)
         self.layer5 = self._make_layer(block, channels[4], layers[4], dilation=2, new_level=False)
         self.layer6 = None if layers[5] == 0 else \
             self._make_layer(block, channels[5], layers[5], dilation=4, new_level=False)
-        self.layer7 = None if layers[6] == 0 else self._make_conv_layers(channels[6], layers[6], dilation=2)
-        self.layer8 = None if layers[7] == 0 else self._make_conv_layers(channels[7], layers[7], dilation=1)
+        if arch == 'C':
+            self.layer7 = None if layers[6] == 0 else \
+                self._make_layer(BasicBlock, channels[6], layers[6], dilation=2, new_level=False, residual=False)
+            self.layer8 = None if layers[7] == 0 else \
+                self._make_layer(BasicBlock, channels[7], layers[7], dilation=1, new_level=False, residual=False)
+        else:
+            self.layer7 = None if layers[6] == 0 else self._make_conv_layers(channels[6], layers[6], dilation=2)
+            self.layer8 = None if layers[7] == 0 else self._make_conv_layers(channels[7], layers[7], dilation=1)
 
         if num_classes > 0:
             # classification head of the ImageNet model: never executed on the MCD path (DRNSegBase drops
@@ -155,6 +171,10 @@ class DRN(nn.Module):
         return ConvBNReLU(*mods)
 
     def stages(self):
+        if self.arch == 'C':
+            stem = ConvBNReLU(self.conv1, self.bn1, self.relu)     # a view: same modules, fused execution
+            return [stem] + [s for s in (self.layer1, self.layer2, self.layer3, self.layer4, self.layer5, self.layer6,
+                                         self.layer7, self.layer8) if s is not None]
         return [s for s in (self.layer0, self.layer1, self.layer2, self.layer3, self.layer4, self.layer5,
                             self.layer6, self.layer7, self.layer8) if s is not None]
 
@@ -177,9 +197,7 @@ def replace_first_conv(res_model, input_ch, arch):
     of channels 0.. of the 3-channel filter."""
     if input_ch == 3:
         return res_model
-    if arch != "D":
-        raise NotImplementedError("arch 'D' only")
-    old_conv, bn = res_model.layer0[0], res_model.layer0[1]
+    old_conv = res_model.conv1 if arch == "C" else res_model.layer0[0]
     new_conv = Conv2d(input_ch, 16, kernel_size=7, stride=1, padding=3, bias=False)
     if input_ch == 1:
         new_conv.weight.data = old_conv.weight.data[:, 0:1, :, :].clone()
@@ -189,7 +207,10 @@ def replace_first_conv(res_model, input_ch, arch):
         new_conv.weight.data[:, 3:3 + extra] = old_conv.weight.data[:, 0:extra]
     else:
         raise NotImplementedError()
-    res_model.layer0 = ConvBNReLU(new_conv, bn, nn.ReLU(inplace=True))
+    if arch == "C":
+        res_model.conv1 = new_conv
+    else:
+        res_model.layer0 = ConvBNReLU(new_conv, res_model.layer0[1], nn.ReLU(inplace=True))
     return res_model
 
 
@@ -212,11 +233,23 @@ def _load_pretrained(model, name):
                       "random He-normal initialisation" % name)
 
 
-def _build(name, layers, pretrained, input_ch, block=BasicBlock, **kwargs):
-    model = DRN(block, layers, arch='D', **kwargs)
+def _build(name, layers, pretrained, input_ch, block=BasicBlock, arch='D', **kwargs):
+    model = DRN(block, layers, arch=arch, **kwargs)
     if pretrained:
         _load_pretrained(model, name)
-    return replace_first_conv(model, input_ch=input_ch, arch="D")
+    return replace_first_conv(model, input_ch=input_ch, arch=arch)
+
+
+def drn_c_26(pretrained=False, input_ch=3, **kwargs):
+    return _build("drn_c_26", [1, 1, 2, 2, 2, 2, 1, 1], pretrained, input_ch, arch='C', **kwargs)
+
+
+def drn_c_42(pretrained=False, input_ch=3, **kwargs):
+    return _build("drn_c_42", [1, 1, 3, 4, 6, 3, 1, 1], pretrained, input_ch, arch='C', **kwargs)
+
+
+def drn_c_58(pretrained=False, input_ch=3, **kwargs):
+    return _build("drn_c_58", [1, 1, 3, 4, 6, 3, 1, 1], pretrained, input_ch, block=Bottleneck, arch='C', **kwargs)
 
 
 def drn_d_22(pretrained=False, input_ch=3, **kwargs):

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 from torch.nn.modules.batchnorm import _BatchNorm
 
-_DRN_NAMES = ("drn_d_22", "drn_d_38", "drn_d_54", "drn_d_105")
+_DRN_NAMES = ("drn_c_26", "drn_c_42", "drn_c_58", "drn_d_22", "drn_d_38", "drn_d_54", "drn_d_105")
 
 
 def _check_drn(net_name):
@@ -27,25 +27,44 @@ def _no_data_parallel(flag):
 
 
 def get_models(net_name, input_ch, n_class, res="50", method="MCD", is_data_parallel=False):
-    """(model_g, model_f1, model_f2) for method "MCD"; (model_g_3ch, model_g_1ch, model_f1, model_f2) for
-    "MCD-MFNet-AddFusion" / "MCD-MFNet-ScoreAddFusion" (reference models/model_util.py:160-286)."""
-    from models.dilated_fcn import (DRNSegBase, DRNSegPixelClassifier, FusionDRNSegPixelClassifier,
+    """(model_g, model_f1, model_f2) for method "MCD" (`drn_*`, `drn_*_ver2`, `drn_*_fusenet`);
+    (model_g_3ch, model_g_1ch, model_f1, model_f2) for "MCD-MFNet-<Fusion>" / "MCD-MFNet-Score<Fusion>" with any
+    fusion of models/fusion.py (reference models/model_util.py:160-286)."""
+    from models.dilated_fcn import (DRNSegBase, DRNSegPixelClassifier, FuseDRNSegBase, FusionDRNSegPixelClassifier,
                                     ScoreFusionDRNSegPixelClassifier)
     if method == "MCD":
-        _check_drn(net_name)
-        model_list = [DRNSegBase(model_name=net_name, n_class=n_class, input_ch=input_ch),
-                      DRNSegPixelClassifier(n_class=n_class), DRNSegPixelClassifier(n_class=n_class)]
+        if "drn" not in net_name:
+            raise NotImplementedError("Only FCN (Including Dilated FCN), SegNet, PSPNet UNet are supported!")
+        if "fusenet" in net_name:
+            drn_name = net_name.replace("_fusenet", "")
+            _check_drn(drn_name)
+            model_list = [FuseDRNSegBase(model_name=drn_name, n_class=n_class, input_ch=input_ch),
+                          DRNSegPixelClassifier(n_class=n_class), DRNSegPixelClassifier(n_class=n_class)]
+        else:
+            ver = "ver2" if "ver2" in net_name else "ver1"
+            drn_name = net_name.replace("_ver2", "")
+            _check_drn(drn_name)
+            model_list = [DRNSegBase(model_name=drn_name, n_class=n_class, input_ch=input_ch, ver=ver),
+                          DRNSegPixelClassifier(n_class=n_class, ver=ver),
+                          DRNSegPixelClassifier(n_class=n_class, ver=ver)]
     elif "MFNet" in method:
         assert input_ch in [4, 6]
         if "drn" not in net_name:
             raise NotImplementedError("Only Dilated FCN is supported!")
-        _check_drn(net_name)
+        ver = "ver2" if "ver2" in net_name else "ver1"
+        drn_name = net_name.replace("_ver2", "")
+        _check_drn(drn_name)
         fusion_type = method.split("-")[-1]
-        head = ScoreFusionDRNSegPixelClassifier if "score" in method.lower() else FusionDRNSegPixelClassifier
-        model_list = [DRNSegBase(model_name=net_name, n_class=n_class, input_ch=3),
-                      DRNSegBase(model_name=net_name, n_class=n_class, input_ch=input_ch - 3),
-                      head(fusion_type=fusion_type, n_class=n_class),
-                      head(fusion_type=fusion_type, n_class=n_class)]
+        print("fusion type: %s" % fusion_type)
+        model_list = [DRNSegBase(model_name=drn_name, n_class=n_class, input_ch=3, ver=ver),
+                      DRNSegBase(model_name=drn_name, n_class=n_class, input_ch=input_ch - 3, ver=ver)]
+        if "score" in method.lower():
+            print("Score Fusion!!!")
+            model_list += [ScoreFusionDRNSegPixelClassifier(fusion_type=fusion_type, n_class=n_class)
+                           for _ in range(2)]
+        else:
+            model_list += [FusionDRNSegPixelClassifier(fusion_type=fusion_type, n_class=n_class, ver=ver)
+                           for _ in range(2)]
     else:
         # the reference *returns* (does not raise) the exception object here (models/model_util.py:281)
         return NotImplementedError("Sorry... Only MCD is supported!")
@@ -55,14 +74,14 @@ def get_models(net_name, input_ch, n_class, res="50", method="MCD", is_data_para
 
 def get_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
                          is_data_parallel=False, is_src_only=False):
-    """(model_enc, model_dec): RGB encoder + seg/HHA MCD decoder (reference models/model_util.py:81-99)."""
-    from models.dilated_fcn import MCDMultiTaskDecoder, MultiTaskEncoder
+    """(model_enc, model_dec): RGB encoder + seg/HHA decoder - the MCD pair of classifiers, or one classifier with
+    `is_src_only` (reference models/model_util.py:81-99)."""
+    from models.dilated_fcn import MCDMultiTaskDecoder, MultiTaskDecoder, MultiTaskEncoder
     _check_drn(net_name)
-    if is_src_only:
-        raise NotImplementedError("source-only decoders are outside the libmcd_sm100 hot-path scope")
     model_enc = MultiTaskEncoder(model_name=net_name, input_ch=3)  # RGB is 3 channel
-    model_dec = MCDMultiTaskDecoder(n_class=n_class, depth_ch=input_ch - 3, semseg_criterion=semseg_criterion,
-                                    discrepancy_criterion=discrepancy_criterion)
+    dec = MultiTaskDecoder if is_src_only else MCDMultiTaskDecoder
+    model_dec = dec(n_class=n_class, depth_ch=input_ch - 3, semseg_criterion=semseg_criterion,
+                    discrepancy_criterion=discrepancy_criterion)
     _no_data_parallel(is_data_parallel)
     return model_enc, model_dec
 
@@ -70,18 +89,41 @@ def get_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, dis
 def get_triple_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
                                 is_data_parallel=False, semseg_shortcut=False, depth_shortcut=False,
                                 add_pred_seg_boundary_loss=False, is_src_only=False, use_seg2bd_conv=False):
-    """(model_enc, model_dec): RGB encoder returning h0..h8 + seg/HHA/boundary MCD decoder; `input_ch` is
+    """(model_enc, model_dec): RGB encoder returning h0..h8 + seg/HHA/boundary decoder; `input_ch` is
     ignored exactly as in the reference (models/model_util.py:102-130)."""
-    from models.dilated_fcn import MCDTripleMultiTaskDecoder, MultiTaskEncoderReturningMultipleFeaturemaps
+    from models.dilated_fcn import (MCDTripleMultiTaskDecoder, MultiTaskEncoderReturningMultipleFeaturemaps,
+                                    TripleMultiTaskDecoder)
     _check_drn(net_name)
-    if is_src_only:
-        raise NotImplementedError("source-only decoders are outside the libmcd_sm100 hot-path scope")
     model_enc = MultiTaskEncoderReturningMultipleFeaturemaps(model_name=net_name, input_ch=3)
-    model_dec = MCDTripleMultiTaskDecoder(n_class=n_class, depth_ch=3, semseg_criterion=semseg_criterion,
-                                          discrepancy_criterion=discrepancy_criterion,
-                                          semseg_shortcut=semseg_shortcut, depth_shortcut=depth_shortcut,
-                                          add_pred_seg_boundary_loss=add_pred_seg_boundary_loss,
-                                          use_seg2bd_conv=use_seg2bd_conv)
+    if is_src_only:
+        model_dec = TripleMultiTaskDecoder(n_class=n_class, depth_ch=3, semseg_criterion=semseg_criterion,
+                                           semseg_shortcut=semseg_shortcut, depth_shortcut=depth_shortcut,
+                                           add_pred_seg_boundary_loss=add_pred_seg_boundary_loss)
+    else:
+        model_dec = MCDTripleMultiTaskDecoder(n_class=n_class, depth_ch=3, semseg_criterion=semseg_criterion,
+                                              discrepancy_criterion=discrepancy_criterion,
+                                              semseg_shortcut=semseg_shortcut, depth_shortcut=depth_shortcut,
+                                              add_pred_seg_boundary_loss=add_pred_seg_boundary_loss,
+                                              use_seg2bd_conv=use_seg2bd_conv)
+    _no_data_parallel(is_data_parallel)
+    return model_enc, model_dec
+
+
+def get_segbd_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
+                               is_data_parallel=False, semseg_shortcut=False, depth_shortcut=False,
+                               add_pred_seg_boundary_loss=False, is_src_only=False, use_seg2bd_conv=False):
+    """(model_enc, model_dec): RGB encoder returning h0..h8 + seg/boundary MCD decoder (reference
+    models/model_util.py:133-157); `depth_shortcut` is accepted and not forwarded, as there."""
+    from models.dilated_fcn import MCDSegBDMultiTaskDecoder, MultiTaskEncoderReturningMultipleFeaturemaps
+    _check_drn(net_name)
+    model_enc = MultiTaskEncoderReturningMultipleFeaturemaps(model_name=net_name, input_ch=3)
+    if is_src_only:
+        raise NotImplementedError()
+    model_dec = MCDSegBDMultiTaskDecoder(n_class=n_class, depth_ch=3, semseg_criterion=semseg_criterion,
+                                         discrepancy_criterion=discrepancy_criterion,
+                                         semseg_shortcut=semseg_shortcut,
+                                         add_pred_seg_boundary_loss=add_pred_seg_boundary_loss,
+                                         use_seg2bd_conv=use_seg2bd_conv)
     _no_data_parallel(is_data_parallel)
     return model_enc, model_dec
 

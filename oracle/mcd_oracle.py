@@ -32,8 +32,11 @@ import torch
 import torch.nn.functional as F
 
 LAYERS = {"drn_d_22": [1, 1, 2, 2, 2, 2, 1, 1], "drn_d_38": [1, 1, 3, 4, 6, 3, 1, 1],
-          "drn_d_54": [1, 1, 3, 4, 6, 3, 1, 1], "drn_d_105": [1, 1, 3, 4, 23, 3, 1, 1]}
-BOTTLENECK = ("drn_d_54", "drn_d_105")            # models/drn.py:337-348: Bottleneck blocks, expansion 4
+          "drn_d_54": [1, 1, 3, 4, 6, 3, 1, 1], "drn_d_105": [1, 1, 3, 4, 23, 3, 1, 1],
+          "drn_c_26": [1, 1, 2, 2, 2, 2, 1, 1], "drn_c_42": [1, 1, 3, 4, 6, 3, 1, 1],
+          "drn_c_58": [1, 1, 3, 4, 6, 3, 1, 1]}
+BOTTLENECK = ("drn_d_54", "drn_d_105", "drn_c_58")  # models/drn.py:337-348,317-320: Bottleneck blocks, expansion 4
+ARCH_C = ("drn_c_26", "drn_c_42", "drn_c_58")     # models/drn.py:113-124,147-153: BasicBlock stages 1, 2, 7, 8
 CHANNELS = (16, 32, 64, 128, 256, 512, 512, 512)
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 
@@ -43,9 +46,12 @@ BN_EPS, BN_MOMENTUM = 1e-5, 0.1
 #   ("cbr", key_conv, key_bn, stride, dil)                               conv3x3/7x7 + BN + ReLU
 #   ("block", prefix, stride, dil1, dil2, has_downsample)                 BasicBlock
 #   ("bneck", prefix, stride, dil1, dil2, has_downsample)                 Bottleneck (1x1, 3x3 dilation dil2, 1x1 x4)
+# a 7th element False marks a BasicBlock built with residual=False (arch C stages 7, 8)
 def trunk_spec(name="drn_d_38", prefix="base."):
     layers = LAYERS[name]
     kind, exp = ("bneck", 4) if name in BOTTLENECK else ("block", 1)
+    if name in ARCH_C:
+        return _trunk_spec_c(layers, kind, exp, prefix)
     spec = [[("cbr", "%s0.0" % prefix, "%s0.1" % prefix, 1, 1, 3)]]          # 7x7 pad 3
     inplanes = CHANNELS[0]
 
@@ -77,6 +83,32 @@ def trunk_spec(name="drn_d_38", prefix="base."):
     spec.append(block_stack(6, CHANNELS[5], layers[5], dilation=4, new_level=False))
     spec.append(conv_stack(7, CHANNELS[6], layers[6], dil=2))
     spec.append(conv_stack(8, CHANNELS[7], layers[7], dil=1))
+    return spec
+
+
+def _trunk_spec_c(layers, kind, exp, prefix):
+    """arch C (models/drn.py:113-124,147-153): children conv1, bn1, relu, layer1..layer8 -> `prefix`0, 1, 2, 3..10."""
+    spec = [[("cbr", "%s0" % prefix, "%s1" % prefix, 1, 1, 3)]]
+    state = {"inplanes": CHANNELS[0]}
+
+    def stack(stage, kind_, exp_, planes, blocks, stride=1, dilation=1, new_level=True, residual=True):
+        idx = stage + 2
+        ds = stride != 1 or state["inplanes"] != planes * exp_
+        d0 = (1, 1) if dilation == 1 else ((dilation // 2 if new_level else dilation), dilation)
+        units = [(kind_, "%s%d.0" % (prefix, idx), stride, d0[0], d0[1], ds, residual)]
+        state["inplanes"] = planes * exp_
+        units += [(kind_, "%s%d.%d" % (prefix, idx, b), 1, dilation, dilation, False, residual)
+                  for b in range(1, blocks)]
+        return units
+
+    spec.append(stack(1, "block", 1, CHANNELS[0], layers[0], stride=1))
+    spec.append(stack(2, "block", 1, CHANNELS[1], layers[1], stride=2))
+    spec.append(stack(3, kind, exp, CHANNELS[2], layers[2], stride=2))
+    spec.append(stack(4, kind, exp, CHANNELS[3], layers[3], stride=2))
+    spec.append(stack(5, kind, exp, CHANNELS[4], layers[4], dilation=2, new_level=False))
+    spec.append(stack(6, kind, exp, CHANNELS[5], layers[5], dilation=4, new_level=False))
+    spec.append(stack(7, "block", 1, CHANNELS[6], layers[6], dilation=2, new_level=False, residual=False))
+    spec.append(stack(8, "block", 1, CHANNELS[7], layers[7], dilation=1, new_level=False, residual=False))
     return spec
 
 
@@ -153,7 +185,8 @@ def unit_forward(sd, unit, x, bn_train=True, taps=None):
             taps[kc + ":conv"] = y
             taps[kc + ":out"] = out
         return out
-    _, p, stride, d1, d2, ds = unit
+    _, p, stride, d1, d2, ds = unit[:6]
+    residual = unit[6] if len(unit) > 6 else True
     if unit[0] == "bneck":          # Bottleneck.forward, models/drn.py:80-100
         y1 = _q(F.conv2d(x, _qw(sd[p + ".conv1.weight"])), "y")
         o = _q(F.relu(_bn(sd, p + ".bn1", y1, bn_train)))
@@ -175,10 +208,10 @@ def unit_forward(sd, unit, x, bn_train=True, taps=None):
     y2 = _q(F.conv2d(o, _qw(sd[p + ".conv2.weight"]), None, 1, d2, d2), "y")
     o = _bn(sd, p + ".bn2", y2, bn_train)
     res = x
-    if ds:
+    if ds:                          # evaluated even with residual=False (models/drn.py:52-53): BatchNorm bookkeeping
         yd = _q(F.conv2d(x, _qw(sd[p + ".downsample.0.weight"]), None, stride, 0, 1), "y")
         res = _bn(sd, p + ".downsample.1", yd, bn_train)
-    out = _q(F.relu(o + res))
+    out = _q(F.relu(o + res if residual else o))
     if taps is not None:
         taps[p + ".conv1:conv"] = y1
         taps[p + ".conv2:conv"] = y2
@@ -338,7 +371,7 @@ def init_trunk(name="drn_d_38", input_ch=3, prefix="base.", gen=None):
                 _bn_state(sd, kb, cout)
                 cin = cout
             else:
-                _, p, stride, d1, d2, ds = unit
+                _, p, stride, d1, d2, ds = unit[:6]
                 idx = int(p[len(prefix):].split(".")[0])
                 planes = CHANNELS[idx - 1]
                 if unit[0] == "bneck":
@@ -773,3 +806,98 @@ def pair_distance(name, a, b, size_average=True):
     if name in ("mis_symkl", "spatial_jsd"):             # loss.py:68-76,154-170: kl_div fed with probabilities
         return 0.5 * (_kl_div(pa, pb) + _kl_div(pb, pa))
     raise NotImplementedError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# option surface around the hot path
+def fusion(sd, kind, x1, x2, prefix="fusion."):
+    """models/fusion.py:6-50.  kind: gate | scoregate (GateFusion with apply_softmax) | add | concat | concatconv."""
+    if kind in ("gate", "scoregate"):
+        if kind == "scoregate":
+            x1, x2 = F.softmax(x1, 1), F.softmax(x2, 1)
+        g = torch.sigmoid(F.conv2d(torch.cat([x1, x2], 1), sd[prefix + "conv.weight"], sd[prefix + "conv.bias"]))
+        return x1 * g + x2 * (1 - g)
+    if kind == "add":
+        return x1 + x2
+    if kind == "concat":
+        return torch.cat([x1, x2], 1)
+    if kind == "concatconv":
+        return F.conv2d(torch.cat([x1, x2], 1), sd[prefix + "conv.weight"], sd[prefix + "conv.bias"], padding=1)
+    raise ValueError(kind)
+
+
+def bilinear_up_ac(x, s):
+    """nn.UpsamplingBilinear2d(scale_factor=s): align_corners=True (models/dilated_fcn.py:354-355,443-444)."""
+    return F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=True)
+
+
+def fusion_head_forward(sd, kind, x1, x2, ver="ver1", torch_up=False):
+    """FusionDRNSegPixelClassifier.forward (models/dilated_fcn.py:465-470)."""
+    h = fusion(sd, kind, x1, x2)
+    if ver == "ver2":
+        h = F.conv2d(h, sd["seg.weight"], sd["seg.bias"])
+    if torch_up:
+        return bilinear_up_ac(h, 8)
+    w = sd["up.weight"]
+    groups = w.shape[0] // 2 if kind == "concat" else w.shape[0]
+    return F.conv_transpose2d(h, w, None, stride=8, padding=4, groups=groups)
+
+
+def score_fusion_head_forward(sd, kind, x1, x2):
+    """ScoreFusionDRNSegPixelClassifier.forward (models/dilated_fcn.py:487-491)."""
+    return fusion(sd, kind, up_head(sd["up1.weight"], x1), up_head(sd["up2.weight"], x2))
+
+
+def single_head_forward(sd, x, ver="ver1", torch_up=False):
+    """DRNSegPixelClassifier.forward (models/dilated_fcn.py:362-366)."""
+    if ver == "ver2":
+        x = F.conv2d(x, sd["seg.weight"], sd["seg.bias"])
+    return bilinear_up_ac(x, 8) if torch_up else up_head(sd["up.weight"], x)
+
+
+def fuse_seg_base_forward(sd, x, name="drn_d_22", train=True, fix_bn=False):
+    """FuseDRNSegBase.forward (models/dilated_fcn.py:294-331): the HHA half, then the RGB half, both through
+    `main_layerK`; the HHA activation of every stage is added to the RGB one."""
+    bn_train = _bn_train_flag(train, fix_bn)
+    spec = trunk_spec(name, "main_layer")
+    h, x_d = _q(x[:, 3:]), []
+    for stage in spec:
+        for unit in stage:
+            h = unit_forward(sd, unit, h, bn_train)
+        x_d.append(h)
+    h = _q(x[:, :3])
+    for stage, d in zip(spec, x_d):
+        for unit in stage:
+            h = unit_forward(sd, unit, h, bn_train)
+        h = _q(h + d)
+    return _qg(F.conv2d(h, _qw(sd["seg.weight"]), sd["seg.bias"]))
+
+
+# ---- decoder options (models/dilated_fcn.py:797-1019, 1027-1222, 1258-1398) ---------------------------------------
+def _shortcut_sum(sd, hd, prefix):
+    """upsample1(c1(h2)) + upsample2(c2(h3)) + upsample3(c3(h8)), 512 channels at full resolution (:866-875)"""
+    hs = [bilinear_up(F.conv2d(hd[k], _qw(sd[(prefix % i) + ".weight"]), sd[(prefix % i) + ".bias"]), s)
+          for i, k, s in ((1, "h2", 2), (2, "h3", 4), (3, "h8", 8))]
+    return hs[0] + hs[1] + hs[2]
+
+
+def opt_semseg(sd, hd, dec, conv_prefix, shortcut, train=True):
+    if shortcut:
+        return three_layer_decoder(sd, dec, _shortcut_sum(sd, hd, conv_prefix), train)
+    return bilinear_up(three_layer_decoder(sd, dec, hd["h8"], train), 8)
+
+
+def opt_semseg_losses(sd, hd, gt_semseg, weight, shortcut=False, add_pred_seg_boundary_loss=False, train=True,
+                      decs=(("semsegcls_dec1", "seg_conv%d_1"), ("semsegcls_dec2", "seg_conv%d_2"))):
+    """get_semseg_loss(separately_returning=True) (:936-954) and the predictions"""
+    preds = [opt_semseg(sd, hd, d, c, shortcut, train) for d, c in decs]
+    losses = [ce2d(p, gt_semseg, weight) for p in preds]
+    if add_pred_seg_boundary_loss:
+        losses = [l + get_boundary_loss(p.max(1)[1], gt_semseg) for l, p in zip(losses, preds)]
+    return losses, preds
+
+
+def seg2bd_losses(sd, preds, gt_bd):
+    """get_boundary_loss_by_extra_conv (:960-981) given the classifiers' predictions"""
+    return [bce2d(torch.sigmoid(F.conv2d(p, _qw(sd["seg2bd_conv.weight"]), sd["seg2bd_conv.bias"], padding=2)),
+                  gt_bd.reshape(p.shape[0], 1, *p.shape[2:])) for p in preds]

@@ -46,11 +46,14 @@ def stage_reference():
 
     patch("loss.py", [("print prob1", "print(prob1)")])
     patch("models/dilated_fcn.py", [("cuda(async=True)", "cuda(non_blocking=True)"),
-                                    ("\nimport drn\n", "\nfrom models import drn\n")])
+                                    ("\nimport drn\n", "\nfrom models import drn\n"),
+                                    # CPU-only container: the option branches call .cuda() unconditionally
+                                    ("loss1 += extra_loss1.cuda()", "loss1 += extra_loss1"),
+                                    ("loss2 += extra_loss2.cuda()", "loss2 += extra_loss2")])
     patch("models/drn.py", [("gen.next()", "next(gen)")])
     sys.path.insert(0, STAGE)
     import models.drn as drn
-    for name in ("drn_d_22", "drn_d_38"):
+    for name in ("drn_d_22", "drn_d_38", "drn_c_26"):
         orig = getattr(drn, name)
         setattr(drn, name, (lambda f: lambda pretrained=False, **kw: f(pretrained=False, **kw))(orig))
 
@@ -488,6 +491,170 @@ def golden_bottleneck():
     print("drn_d_54: %d state entries, feat norm %.6f" % (len(G), float(feat.norm())))
 
 
+def _grads_of(obj, named):
+    """obj.backward() and the gradients of the named leaves as numpy arrays"""
+    for t in named.values():
+        t.grad = None
+    obj.backward()
+    return {k: (t.grad.numpy().copy() if t.grad is not None else None) for k, t in named.items()}
+
+
+def sample(a, n=512):
+    """a strided sample of at most ~n elements of an array (the fixtures stay small)"""
+    f = np.asarray(a).reshape(-1)
+    return f[::max(1, f.size // n)].copy()
+
+
+def variant_head_inputs(i, cin, h, w):
+    """seeded inputs of head case i (regenerated, not stored, by tests/test_variants_gpu.py): two score maps
+    (41 channels) or two post-ReLU trunk features (512 channels) and the weights r of the objective mean(out * r)"""
+    g = torch.Generator().manual_seed(7100 + i)
+    scale = 2.0 if cin != 512 else 0.5
+    x1 = torch.randn(2, cin, h, w, generator=g) * scale
+    x2 = torch.randn(2, cin, h, w, generator=g) * scale
+    if cin == 512:
+        x1, x2 = x1.clamp_(min=0), x2.clamp_(min=0)
+    r = torch.randn(2, N_CLASS, 8 * h, 8 * w, generator=g)
+    return x1.requires_grad_(True), x2.requires_grad_(True), r
+
+
+def golden_variants():
+    """The option surface around the hot path from the reference's own classes:
+    fusion heads (models/fusion.py:6-65 through models/dilated_fcn.py:340-366,431-491 incl. ver2 and use_torch_up),
+    FuseDRNSegBase (:253-337), DRN arch C (models/drn.py:113-153,303-306), the triple decoder's shortcut / seg2bd /
+    add_pred_seg_boundary_loss options (:797-1019), MCDSegBDMultiTaskDecoder (:1027-1222) and the source-only decoders
+    (:1225-1398)."""
+    from loss import CrossEntropyLoss2d, Diff2d
+    from models import dilated_fcn as D
+    from util import get_class_weight_from_file
+    out = {}
+    h, w = 6, 8
+
+    # ---- heads: objective = mean(out * r), r seeded; gradients w.r.t. the inputs and every parameter
+    cases = [
+        ("gate_v1", lambda: D.FusionDRNSegPixelClassifier("GateFusion", N_CLASS), N_CLASS),
+        ("concat_v1", lambda: D.FusionDRNSegPixelClassifier("ConcatFusion", N_CLASS), N_CLASS),
+        ("concatconv_v1", lambda: D.FusionDRNSegPixelClassifier("ConcatConvFusion", N_CLASS), N_CLASS),
+        ("add_v2", lambda: D.FusionDRNSegPixelClassifier("AddFusion", N_CLASS, ver="ver2"), 512),
+        ("gate_v2", lambda: D.FusionDRNSegPixelClassifier("GateFusion", N_CLASS, ver="ver2"), 512),
+        ("add_torchup", lambda: D.FusionDRNSegPixelClassifier("AddFusion", N_CLASS, use_torch_up=True), N_CLASS),
+        ("scoregate", lambda: D.ScoreFusionDRNSegPixelClassifier("ScoreGateFusion", N_CLASS), N_CLASS),
+        ("scoregate_nosm", lambda: D.ScoreFusionDRNSegPixelClassifier("GateFusion", N_CLASS), N_CLASS),
+        ("single_v2", lambda: D.DRNSegPixelClassifier(N_CLASS, ver="ver2"), 512),
+        ("single_torchup", lambda: D.DRNSegPixelClassifier(N_CLASS, use_torch_up=True), N_CLASS),
+    ]
+    for i, (tag, make, cin) in enumerate(cases):
+        head = filled(make(), 70 + i)
+        head.train()
+        two = not tag.startswith("single")
+        x1, x2, r = variant_head_inputs(i, cin, h, w)
+        o = head(x1, x2) if two else head(x1)
+        named = {"x1": x1, **({"x2": x2} if two else {}), **{"p:" + k: p for k, p in head.named_parameters()}}
+        gr = _grads_of((o * r).mean(), named)
+        out[tag + ":out_sub"] = o.detach()[:, :, ::4, ::4].numpy()
+        out[tag + ":out_norm"] = float(o.norm())
+        for k, v in gr.items():
+            out[tag + ":gn:" + k] = float(np.linalg.norm(v))
+            out[tag + ":gs:" + k] = sample(v)
+        print("variant head %-16s out %s |out| %.5f" % (tag, tuple(o.shape), float(o.norm())))
+
+    # ---- FuseDRNSegBase (drn_d_22_fusenet) and DRN arch C (drn_c_26): eval forward, then one train-mode
+    #      forward + backward of a quadratic objective (gradient norms, BatchNorm bookkeeping)
+    for tag, make in (("fusenet", lambda: D.FuseDRNSegBase("drn_d_22", N_CLASS, pretrained=False, input_ch=6)),
+                      ("drn_c_26", lambda: D.DRNSegBase("drn_c_26", N_CLASS, pretrained=False, input_ch=6))):
+        torch.manual_seed(0)
+        net = filled(make(), 81)
+        x = torch.randn(2, 6, 64, 96, generator=torch.Generator().manual_seed(808))
+        net.eval()
+        with torch.no_grad():
+            out[tag + ":eval"] = net(x).numpy()
+        net.train()
+        feat = net(x)
+        feat.square().mean().backward()
+        gk, gn = norms({k: p.grad for k, p in net.named_parameters()})
+        sk, sv = summarize(net.state_dict())
+        out[tag + ":train"] = feat.detach().numpy()
+        out[tag + ":grad_keys"], out[tag + ":grad_norms"] = np.array(gk), gn
+        out[tag + ":state_keys"], out[tag + ":state_sums"] = np.array(sk), sv
+        out[tag + ":nbt"] = np.array([int(v) for k, v in net.state_dict().items() if k.endswith("num_batches_tracked")])
+        print("variant trunk %-10s %d state entries, eval |feat| %.5f" % (tag, len(net.state_dict()),
+                                                                           float(np.linalg.norm(out[tag + ":eval"]))))
+
+    # ---- decoders with options, on seeded feature maps (full resolution 32 x 48)
+    weight = get_class_weight_from_file(n_class=N_CLASS)
+    H, W = 32, 48
+
+    def feats(seed):
+        gg = torch.Generator().manual_seed(seed)
+        return {k: (torch.randn(2, c, H // d, W // d, generator=gg).clamp_(min=0) * 0.7).requires_grad_(True)
+                for k, c, d in (("h2", 32, 2), ("h3", 64, 4), ("h8", 512, 8))}
+
+    gg = torch.Generator().manual_seed(909)
+    gt_semseg = torch.randint(0, N_CLASS, (2, H, W), generator=gg)
+    gt_semseg[:, 5:20, 10:30] = 7                     # some structure, so that the label boundaries are not everywhere
+    gt_semseg[:, 22:, :15] = 3
+    gt_dep = torch.randn(2, 3, H, W, generator=gg)
+    gt_bd = (torch.rand(2, 1, H, W, generator=gg) < 0.15).float()
+    out.update({"dec:gt_semseg": gt_semseg.numpy(), "dec:gt_dep": gt_dep.numpy(), "dec:gt_bd": gt_bd.numpy()})
+
+    def record(tag, dec, fd, total, scalars):
+        named = {**{"x:" + k: v for k, v in fd.items()}, **{"p:" + k: p for k, p in dec.named_parameters()}}
+        gr = _grads_of(total, named)
+        for k, v in scalars.items():
+            out[tag + ":" + k] = float(v)
+        keys = sorted(k for k, v in gr.items() if v is not None)
+        out[tag + ":grad_keys"] = np.array(keys)
+        out[tag + ":grad_norms"] = np.array([float(np.linalg.norm(gr[k])) for k in keys])
+        out[tag + ":g:x:h8"], out[tag + ":g:x:h2"] = gr["x:h8"], gr["x:h2"]
+        print("variant decoder %-14s %s" % (tag, {k: round(float(v), 6) for k, v in scalars.items()}))
+
+    # (a) MCDTripleMultiTaskDecoder, every option on
+    dec = filled(D.MCDTripleMultiTaskDecoder(N_CLASS, 3, semseg_criterion=CrossEntropyLoss2d(weight),
+                                             discrepancy_criterion=Diff2d(), semseg_shortcut=True,
+                                             depth_shortcut=True, add_pred_seg_boundary_loss=True,
+                                             use_seg2bd_conv=True), 91)
+    dec.train()
+    fd = feats(1001)
+    l_seg, l_dep, l_bd = dec.get_loss(fd, gt_semseg, gt_dep, gt_bd, separately_returning=True)
+    l_x_src = dec.get_boundary_loss_by_extra_conv(fd, gt_bd)
+    l_x_tgt = dec.get_boundary_loss_by_extra_conv(fd)
+    l_disc = dec.get_cls_descrepancy(fd)
+    with torch.no_grad():
+        p1, p2, pdep, pbd = dec(fd)
+    out["tri_opt:pred1_sub"], out["tri_opt:pdep_sub"] = p1[:, :, ::4, ::4].numpy(), pdep[:, :, ::4, ::4].numpy()
+    out["tri_opt:pbd"] = pbd.numpy()
+    record("tri_opt", dec, fd, l_seg + l_dep + l_bd + l_x_src + 0.5 * l_x_tgt - l_disc,
+           dict(seg=l_seg, dep=l_dep, bd=l_bd, x_src=l_x_src, x_tgt=l_x_tgt, disc=l_disc))
+
+    # (b) MCDSegBDMultiTaskDecoder (default options).  torch >= 1.x refuses F.binary_cross_entropy on [N,1,H,W] vs
+    #     [N,H,W]; torch 0.4.1 (the reference's pin) only warned and paired the elements in flat order, which is what
+    #     squeezing the channel axis computes.
+    dec = filled(D.MCDSegBDMultiTaskDecoder(N_CLASS, 3, semseg_criterion=CrossEntropyLoss2d(weight),
+                                            discrepancy_criterion=Diff2d()), 92)
+    dec.get_boundary_loss = lambda x_dic, gt: D.get_boundary_loss(pred=dec.boundary_forward(x_dic)[:, 0], gt=gt,
+                                                                   pred_type="boundary")
+    dec.train()
+    fd = feats(1002)
+    l_seg, l_bd = dec.get_loss(fd, gt_semseg, separately_returning=True)
+    l_disc = dec.get_cls_descrepancy(fd)
+    record("segbd", dec, fd, l_seg + l_bd - l_disc, dict(seg=l_seg, bd=l_bd, disc=l_disc))
+
+    # (c) source-only TripleMultiTaskDecoder and MultiTaskDecoder
+    dec = filled(D.TripleMultiTaskDecoder(N_CLASS, 3, semseg_criterion=CrossEntropyLoss2d(weight)), 93)
+    dec.train()
+    fd = feats(1003)
+    l_seg, l_dep, l_bd = dec.get_loss(fd, gt_semseg, gt_dep, gt_bd, separately_returning=True)
+    record("tri_src", dec, fd, l_seg + l_dep + l_bd, dict(seg=l_seg, dep=l_dep, bd=l_bd))
+    dec = D.MultiTaskDecoder(N_CLASS, 3, semseg_criterion=CrossEntropyLoss2d(weight))
+    dec.s_semsegcls.data.fill_(1), dec.s_deprgr.data.fill_(1)        # uninitialised memory in the reference
+    filled(dec, 94)
+    dec.eval()
+    with torch.no_grad():
+        ps, pd = dec(feats(1004)["h8"])
+    out["mt_src:semseg"], out["mt_src:dep"] = ps.numpy(), pd.numpy()
+    np.savez_compressed(os.path.join(HERE, "variants.npz"), **{k: v for k, v in out.items() if v is not None})
+
+
 if __name__ == "__main__":
     warnings.simplefilter("ignore")
     torch.set_num_threads(8)
@@ -500,3 +667,4 @@ if __name__ == "__main__":
     golden_pipeline()
     golden_discrepancies()
     golden_bottleneck()
+    golden_variants()

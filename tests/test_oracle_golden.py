@@ -272,3 +272,210 @@ def test_oracle_bottleneck_trunk_matches_reference():
     sk = [str(k) for k in d["state_keys"]]
     got_s = np.array([[float(G[k].detach().double().sum()), float(G[k].detach().double().norm())] for k in sk])
     close(got_s, d["state_sums"], rtol=1e-5)          # incl. the running statistics after one train-mode forward
+
+
+# ---- option surface around the hot path: oracle restatements vs tests/golden/variants.npz ---------
+def _variants():
+    return np.load(os.path.join(GOLD, "variants.npz"), allow_pickle=False)
+
+
+_HEAD_CASES = [("gate_v1", "fusion", "gate", "ver1", False, 41), ("concat_v1", "fusion", "concat", "ver1", False, 41),
+               ("concatconv_v1", "fusion", "concatconv", "ver1", False, 41), ("add_v2", "fusion", "add", "ver2", False, 512),
+               ("gate_v2", "fusion", "gate", "ver2", False, 512), ("add_torchup", "fusion", "add", "ver1", True, 41),
+               ("scoregate", "score", "scoregate", "ver1", False, 41), ("scoregate_nosm", "score", "gate", "ver1", False, 41),
+               ("single_v2", "single", None, "ver2", False, 512), ("single_torchup", "single", None, "ver1", True, 41)]
+
+
+def head_state(tag, cls, kind, ver, torch_up, cin, n_class=41):
+    """state_dict of one head case with the reference's key names and shapes, filled like make_golden.filled()."""
+    sd = {}
+    if kind in ("gate", "scoregate"):
+        sd["fusion.conv.weight"], sd["fusion.conv.bias"] = torch.empty(cin, 2 * cin, 1, 1), torch.empty(cin)
+    if kind == "concatconv":
+        sd["fusion.conv.weight"], sd["fusion.conv.bias"] = torch.empty(cin, 2 * cin, 3, 3), torch.empty(cin)
+    if ver == "ver2":
+        sd["seg.weight"], sd["seg.bias"] = torch.empty(n_class, 512, 1, 1), torch.empty(n_class)
+    if cls == "score":
+        sd["up1.weight"], sd["up2.weight"] = torch.empty(n_class, 1, 16, 16), torch.empty(n_class, 1, 16, 16)
+    elif not torch_up:
+        sd["up.weight"] = torch.empty(2 * n_class if kind == "concat" else n_class, 1, 16, 16)
+    return sd
+
+
+def head_case_inputs(i, cin, h=6, w=8, n_class=41):
+    """tests/golden/make_golden.py::variant_head_inputs"""
+    g = torch.Generator().manual_seed(7100 + i)
+    scale = 2.0 if cin != 512 else 0.5
+    x1 = torch.randn(2, cin, h, w, generator=g) * scale
+    x2 = torch.randn(2, cin, h, w, generator=g) * scale
+    if cin == 512:
+        x1, x2 = x1.clamp_(min=0), x2.clamp_(min=0)
+    r = torch.randn(2, n_class, 8 * h, 8 * w, generator=g)
+    return x1.requires_grad_(True), x2.requires_grad_(True), r
+
+
+def _sample(a, n=512):
+    f = np.asarray(a).reshape(-1)
+    return f[::max(1, f.size // n)]
+
+
+@pytest.mark.parametrize("i", range(len(_HEAD_CASES)))
+def test_oracle_fusion_heads_match_reference(i):
+    tag, cls, kind, ver, torch_up, cin = _HEAD_CASES[i]
+    z = _variants()
+    sd = O.fill_state_dict_(head_state(tag, cls, kind, ver, torch_up, cin), 70 + i)
+    for v in sd.values():
+        v.requires_grad_(True)
+    x1, x2, r = head_case_inputs(i, cin)
+    if cls == "fusion":
+        out = O.fusion_head_forward(sd, kind, x1, x2, ver, torch_up)
+    elif cls == "score":
+        out = O.score_fusion_head_forward(sd, kind, x1, x2)
+    else:
+        out = O.single_head_forward(sd, x1, ver, torch_up)
+    (out * r).mean().backward()
+    assert np.allclose(out.detach()[:, :, ::4, ::4].numpy(), z[tag + ":out_sub"], rtol=1e-4, atol=1e-5)
+    named = {"x1": x1, **({"x2": x2} if cls != "single" else {}), **{"p:" + k: v for k, v in sd.items()}}
+    for k, t in named.items():
+        assert np.allclose(_sample(t.grad.numpy()), z[tag + ":gs:" + k], rtol=1e-3, atol=1e-7), (tag, k)
+
+
+@pytest.mark.parametrize("tag,name", [("fusenet", "drn_d_22"), ("drn_c_26", "drn_c_26")])
+def test_oracle_fusenet_and_arch_c_match_reference(tag, name):
+    """FuseDRNSegBase (models/dilated_fcn.py:253-337) and DRN arch C through DRNSegBase: eval and train forward,
+    BatchNorm bookkeeping (two updates per stage and forward for the fusenet generator)."""
+    z = _variants()
+    keys = [str(k) for k in z[tag + ":state_keys"]]
+    x = torch.randn(2, 6, 64, 96, generator=torch.Generator().manual_seed(808))
+    fwd = O.fuse_seg_base_forward if tag == "fusenet" else O.seg_base_forward
+
+    def state():
+        sd = {}
+        if tag == "fusenet":
+            for pre, ch in (("main_layer", 3), ("sub_layer", 3)):
+                sd.update(O.init_trunk(name, ch, pre))
+            sd["seg.weight"], sd["seg.bias"] = torch.empty(41, 512, 1, 1), torch.empty(41)
+        else:
+            sd = _arch_c_state(name)
+        assert set(k for k in sd if torch.is_floating_point(sd[k])) == set(keys)
+        return O.fill_state_dict_(sd, 81)
+
+    with torch.no_grad():
+        ev = fwd(state(), x, name=name, train=False)
+    close(ev.numpy(), z[tag + ":eval"], rtol=2e-4)
+    sd = state()
+    with torch.no_grad():
+        tr = fwd(sd, x, name=name, train=True)
+    ref = z[tag + ":train"]
+    assert float(np.abs(tr.numpy() - ref).max()) <= 2e-3 * float(np.abs(ref).max())
+    nbt = sorted(int(v) for k, v in sd.items() if k.endswith("num_batches_tracked"))
+    assert nbt == sorted(int(v) for v in z[tag + ":nbt"])
+    sums = {k: v for k, v in zip(keys, z[tag + ":state_sums"])}
+    for k in keys:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert abs(float(sd[k].double().norm()) - sums[k][1]) <= 2e-3 * sums[k][1] + 1e-6, k
+
+
+def _arch_c_state(name):
+    """state_dict shapes of DRNSegBase(drn_c_*, input_ch=6) from the oracle's architecture description"""
+    sd, cin = {}, 6
+    for stage in O.trunk_spec(name, "base."):
+        for unit in stage:
+            if unit[0] == "cbr":
+                sd[unit[1] + ".weight"] = torch.empty(16, cin, 7, 7)
+                O._bn_state(sd, unit[2], 16)
+                cin = 16
+                continue
+            p, ds = unit[1], unit[5]
+            planes = O.CHANNELS[int(p.split(".")[1]) - 3]
+            assert unit[0] == "block"
+            sd[p + ".conv1.weight"] = torch.empty(planes, cin, 3, 3)
+            O._bn_state(sd, p + ".bn1", planes)
+            sd[p + ".conv2.weight"] = torch.empty(planes, planes, 3, 3)
+            O._bn_state(sd, p + ".bn2", planes)
+            if ds:
+                sd[p + ".downsample.0.weight"] = torch.empty(planes, cin, 1, 1)
+                O._bn_state(sd, p + ".downsample.1", planes)
+            cin = planes
+    sd["seg.weight"], sd["seg.bias"] = torch.empty(41, 512, 1, 1), torch.empty(41)
+    return sd
+
+
+def decoder_option_feats(seed, H=32, W=48):
+    """tests/golden/make_golden.py::golden_variants.feats"""
+    gg = torch.Generator().manual_seed(seed)
+    return {k: (torch.randn(2, c, H // d, W // d, generator=gg).clamp_(min=0) * 0.7).requires_grad_(True)
+            for k, c, d in (("h2", 32, 2), ("h3", 64, 4), ("h8", 512, 8))}
+
+
+def decoder_option_state(kind, seed):
+    """state_dict (reference key names / shapes) of MCDTripleMultiTaskDecoder with every option on ("tri_opt"),
+    MCDSegBDMultiTaskDecoder ("segbd") or the source-only TripleMultiTaskDecoder ("tri_src")."""
+    g = torch.Generator().manual_seed(0)
+    sd = {"s_semsegcls": torch.ones(1), "s_boundary": torch.ones(1)}
+    decs = {"tri_opt": ("semsegcls_dec1", "semsegcls_dec2", "deprgr_dec", "nmlrgr_dec"),
+            "segbd": ("semsegcls_dec1", "semsegcls_dec2"), "tri_src": ("semsegcls_dec", "deprgr_dec", "nmlrgr_dec")}[kind]
+    for d in decs:
+        O.init_three_layer_decoder(sd, d, N_CLASS if d.startswith("semseg") else 3, g)
+    if kind != "segbd":
+        sd["s_deprgr"] = torch.ones(1)
+    for i, c in ((1, 32), (2, 64), (3, 512)):
+        O._default_conv(sd, "conv%d" % i, 1, c, 1, g)
+        if kind == "tri_opt":
+            for nm in ("seg_conv%d_1", "seg_conv%d_2", "dep_conv%d"):
+                O._default_conv(sd, nm % i, 512, c, 1, g)
+    if kind == "tri_opt":
+        sd["s_pred_seg_boundary"] = torch.ones(1)
+        O._default_conv(sd, "seg2bd_conv", 1, N_CLASS, 5, g)
+    return O.fill_state_dict_(sd, seed)
+
+
+def decoder_option_losses(kind, sd, hd, z):
+    """the scalars tests/golden/make_golden.py::golden_variants records for decoder case `kind`, from the oracle"""
+    import torch.nn.functional as F
+    gt_semseg, gt_dep, gt_bd = (torch.tensor(z["dec:gt_semseg"]).to(hd["h8"].device),
+                                torch.tensor(z["dec:gt_dep"]).to(hd["h8"].device),
+                                torch.tensor(z["dec:gt_bd"]).to(hd["h8"].device))
+    weight = O.class_weight(N_CLASS).to(hd["h8"].device)
+    opt = kind == "tri_opt"
+    decs = (("semsegcls_dec", "seg_conv%d_1"),) if kind == "tri_src" else \
+        (("semsegcls_dec1", "seg_conv%d_1"), ("semsegcls_dec2", "seg_conv%d_2"))
+    ls, preds = O.opt_semseg_losses(sd, hd, gt_semseg, weight, shortcut=opt,
+                                       add_pred_seg_boundary_loss=opt or kind == "segbd", decs=decs)
+    out = {"seg": sum(O._uw(sd["s_semsegcls"], l) for l in ls) / len(ls)}
+    if kind != "segbd":
+        dep_in = O._shortcut_sum(sd, hd, "dep_conv%d") if opt else hd["h8"]
+        dep = O.three_layer_decoder(sd, "deprgr_dec", dep_in)
+        out["dep"] = O._uw(sd["s_deprgr"], F.mse_loss(dep if opt else O.bilinear_up(dep, 8), gt_dep))
+        out["bd"] = O._uw(sd["s_boundary"], O.bce2d(O.triple_boundary(sd, hd), gt_bd))
+    else:
+        out["bd"] = O._uw(sd["s_boundary"], O.get_boundary_loss(O.triple_boundary(sd, hd)[:, 0], gt_semseg,
+                                                                pred_type="boundary"))
+    if opt:
+        out["x_src"] = sum(O.seg2bd_losses(sd, preds, gt_bd))
+        out["x_tgt"] = sum(O.seg2bd_losses(sd, preds, O.triple_boundary(sd, hd).detach()))
+    if kind != "tri_src":
+        out["disc"] = O.diff2d(preds[0], preds[1])
+    total = out["seg"] + out["bd"] + out.get("dep", 0) + out.get("x_src", 0) + 0.5 * out.get("x_tgt", 0) - out.get("disc", 0)
+    return out, total, preds
+
+
+@pytest.mark.parametrize("kind,seed,fseed", [("tri_opt", 91, 1001), ("segbd", 92, 1002), ("tri_src", 93, 1003)])
+def test_oracle_decoder_options_match_reference(kind, seed, fseed):
+    z = _variants()
+    sd = decoder_option_state(kind, seed)
+    for k in O.trainable(sd):
+        sd[k].requires_grad_(True)
+    hd = decoder_option_feats(fseed)
+    out, total, preds = decoder_option_losses(kind, sd, hd, z)
+    for k, v in out.items():
+        assert abs(float(v) - float(z["%s:%s" % (kind, k)])) <= 2e-4 * abs(float(z["%s:%s" % (kind, k)])) + 1e-6, k
+    total.backward()
+    named = {**{"x:" + k: v for k, v in hd.items()}, **{"p:" + k: sd[k] for k in O.trainable(sd)}}
+    keys = [str(k) for k in z[kind + ":grad_keys"]]
+    assert sorted(k for k, v in named.items() if v.grad is not None) == keys
+    got = np.array([float(named[k].grad.norm()) for k in keys])
+    close(got, z[kind + ":grad_norms"], rtol=2e-3)
+    close(hd["h8"].grad.numpy(), z[kind + ":g:x:h8"], rtol=2e-3)
+    if kind == "tri_opt":
+        close(preds[0].detach()[:, :, ::4, ::4].numpy(), z["tri_opt:pred1_sub"], rtol=1e-3)
