@@ -226,10 +226,16 @@ def classifier_inputs(head, feats):
     from models.dilated_fcn import (DRNSegPixelClassifier, FusionDRNSegPixelClassifier,
                                     ScoreFusionDRNSegPixelClassifier)
     from models.fusion import AddFusion
-    if type(head) is DRNSegPixelClassifier and len(feats) == 1:
-        return [feats[0]], [head.up.weight]
-    if type(head) is FusionDRNSegPixelClassifier and isinstance(head.fusion, AddFusion) and len(feats) == 2:
-        return [head.fusion(feats[0], feats[1])], [head.up.weight]      # up(x1 + x2): the 60x80 add stays a torch op
+    from .nn import DepthwiseDeconv16s8
+
+    def score(h):      # ver2: the 1x1 `seg` convolution sits in the head (models/dilated_fcn.py:362-365,467-468)
+        return head.seg(h) if getattr(head, "ver", "ver1") == "ver2" else h
+    if type(head) is DRNSegPixelClassifier and len(feats) == 1 and type(head.up) is DepthwiseDeconv16s8:
+        return [score(feats[0])], [head.up.weight]
+    if type(head) is FusionDRNSegPixelClassifier and len(feats) == 2 and type(head.up) is DepthwiseDeconv16s8:
+        # up([seg](fusion(x1, x2))): the fusion (Add: a 60x80 torch add; Gate / ConcatConv: library kernels) runs as a
+        # module, the upsampling + criterion as the fused kernel
+        return [score(head.fusion(feats[0], feats[1]))], [head.up.weight]
     if type(head) is ScoreFusionDRNSegPixelClassifier and isinstance(head.fusion, AddFusion) and len(feats) == 2:
         return [feats[0], feats[1]], [head.up1.weight, head.up2.weight]
     return None

@@ -105,9 +105,10 @@ class _EarlyFusionTask:
             return None
         return hi
 
-    def _ce_head(self, head, feats, lbls):
+    def _ce_head(self, head, feats, lbls, hi=False):
         from . import headloss
-        hi = self._fused_inputs(head, feats, 1)
+        if hi is False:
+            hi = self._fused_inputs(head, feats, 1)
         if hi is None:
             return self.criterion(head(*feats), lbls)
         c = self.criterion
@@ -123,6 +124,8 @@ class _EarlyFusionTask:
                                       torch.is_grad_enabled() and any(w.requires_grad for w in ha[1] + hb[1]), False)):
                 c = self.criterion
                 return headloss.head_ce2d_pair(ha[0], ha[1], hb[1], lbls, c.nll_loss.weight, c.ignore_index, c.size_average)
+            # (ver2 heads: each classifier's own `seg` convolution has already produced its score map - reuse it)
+            return self._ce_head(self.f1, feats, lbls, ha) + self._ce_head(self.f2, feats, lbls, hb)
         return self._ce_head(self.f1, feats, lbls) + self._ce_head(self.f2, feats, lbls)
 
     def loss_a(self, fs, ft, src, lbls, tgt):

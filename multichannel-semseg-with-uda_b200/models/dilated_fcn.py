@@ -412,7 +412,10 @@ class _HedBranches(nn.Module):
         preds = preds if isinstance(preds, tuple) else (preds,)
         if gt_bdry is None:
             gt_bdry = self.boundary_forward(x_dic).detach().float()
-        losses = [_loss.bce2d(mnn.sigmoid(self.seg2bd_conv(p)), gt_bdry) for p in preds]
+        losses = []
+        for p in preds:
+            pred_bdry = mnn.sigmoid(self.seg2bd_conv(p))
+            losses.append(_loss.bce2d(pred_bdry, gt_bdry.reshape(pred_bdry.shape)))
         if separately_returning:
             return tuple(losses)
         return sum(losses[1:], losses[0])

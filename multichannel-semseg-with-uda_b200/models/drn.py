@@ -13,6 +13,7 @@ triple as one fused unit.  Out of scope: the model-zoo download (`pretrained=Tru
 """
 import math
 
+import torch
 import torch.nn as nn
 
 from mcd_b200.nn import BatchNorm2d, Conv2d, ConvBNReLU, conv_bn_act
@@ -51,6 +52,11 @@ class BasicBlock(nn.Module):
         sole = (self.inner_input or getattr(x, "_mcd_sole", False)) and self.downsample is None
         out = conv_bn_act(self.conv1, self.bn1, x, relu=True, sole=sole)
         if not self.residual:
+            if self.downsample is not None and self.downsample[1].training:
+                # the reference evaluates the downsample branch even when it does not add it (models/drn.py:52-56):
+                # its BatchNorm running statistics move; forward only, the result is dropped
+                with torch.no_grad():
+                    conv_bn_act(self.downsample[0], self.downsample[1], x, relu=False)
             return conv_bn_act(self.conv2, self.bn2, out, relu=True, sole=True)
         if self.downsample is not None:
             ds_conv, ds_bn = self.downsample[0], self.downsample[1]

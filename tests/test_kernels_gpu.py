@@ -260,6 +260,10 @@ def _bn_act_case(cuda_dev, mode, training, shape):
         out = out + rr
     elif mode == "downsample":
         out = out + rbn2(rr)
+    # ReLU-mask ambiguity: BatchNorm statistics are accumulated with atomics (summation order varies run to run), so a
+    # pre-activation within rounding distance of zero can land on either side; at 4.6 M elements that happens in a
+    # noticeable fraction of the runs and moves ONE element of dy by |dz * gamma * rstd|.  Those positions are excluded.
+    keep = (out.detach().abs() > 1e-4).float()
     out = F.relu(out)
     gen = torch.Generator(device="cpu").manual_seed(5)
     dz = bf16_round(torch.randn(out.shape, generator=gen)).to(cuda_dev)
@@ -278,11 +282,12 @@ def _bn_act_case(cuda_dev, mode, training, shape):
     z.backward(ops.to_nhwc(dz, grad=True))
     torch.cuda.synchronize()
     assert rel_err(ops.to_nchw_f32(z.detach()), out) < 1e-2
-    assert rel_err(ops.to_nchw_f32(yn.grad), yr.grad) < 1.5e-2
+    assert float(keep.mean()) > 0.999
+    assert rel_err(ops.to_nchw_f32(yn.grad) * keep, yr.grad * keep) < 1.5e-2
     assert rel_err(bn.weight.grad, rbn.weight.grad) < 1e-2
     assert rel_err(bn.bias.grad, rbn.bias.grad) < 1e-2
     if mode != "plain":
-        assert rel_err(ops.to_nchw_f32(rn.grad), rr.grad) < 1.5e-2
+        assert rel_err(ops.to_nchw_f32(rn.grad) * keep, rr.grad * keep) < 1.5e-2
     if mode == "downsample":
         assert rel_err(bn2.weight.grad, rbn2.weight.grad) < 1e-2
     if training:
