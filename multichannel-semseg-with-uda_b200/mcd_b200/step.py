@@ -179,6 +179,33 @@ class _MultiTaskTask:
         return self.dec.get_cls_descrepancy(ft)
 
 
+class _SegBDTask(_MultiTaskTask):
+    """adapt_segbd_multitask_trainer.py:193-255: segmentation (two MCD classifiers) + boundary decoder whose boundary
+    ground truth is derived from the segmentation labels.  Phase A: get_loss(src) [+ scale_bd_loss * a pseudo-boundary
+    term on the target features once the trainer is past --boundary_loss_converging_epoch: `pseudo` = "pred_seg"
+    (--add_pred_seg_boundary_loss) or "seg2bd" (--use_seg2bd_conv)]; phase B: src_semseg_loss - discrepancy (the
+    boundary term get_loss() also evaluates there is dead and has no state).  The target forward of phase A always
+    runs (BatchNorm running statistics), without autograd when no pseudo term reads it."""
+    a_uses_target = True
+
+    def __init__(self, model_enc, model_dec, mult, pseudo=None, scale_bd_loss=1.0):
+        super().__init__(model_enc, model_dec, True, mult)
+        assert pseudo in (None, "pred_seg", "seg2bd")
+        self.pseudo, self.scale = pseudo, scale_bd_loss
+        self.a_target_forward_only = pseudo is None
+
+    def loss_a(self, fs, ft, src, lbls, tgt):
+        loss = sum(self.dec.get_loss(fs, lbls, separately_returning=True))
+        if self.pseudo == "pred_seg":
+            loss = loss + self.dec.get_psuedo_boundary_loss(ft, separately_returning=False) * self.scale
+        elif self.pseudo == "seg2bd":
+            loss = loss + self.dec.get_boundary_loss_by_extra_conv(ft, separately_returning=False) * self.scale
+        return loss
+
+    def loss_b(self, fs, ft, src, lbls, tgt):
+        return self.dec.get_weighted_semseg_loss(fs, lbls) - self.disc(ft)
+
+
 class MCDStep:
     """method 'MCD' (early fusion): models = (model_g, model_f1, model_f2);
     method 'MFNet': models = (model_g_3ch, model_g_1ch, model_f1, model_f2);
@@ -237,6 +264,12 @@ class MCDStep:
         """adapt_multitask_trainer.py (triple=False) / adapt_triple_multitask_trainer.py (triple=True): the criteria
         live inside model_dec (semseg_criterion / discrepancy_criterion given to get_*multitask_models)."""
         return cls(None, None, None, task=_MultiTaskTask(model_enc, model_dec, triple, num_multiply_d_loss), **kw)
+
+    @classmethod
+    def segbd(cls, model_enc, model_dec, num_multiply_d_loss=1.0, pseudo=None, scale_bd_loss=1.0, **kw):
+        """adapt_segbd_multitask_trainer.py: get_segbd_multitask_models' encoder + MCDSegBDMultiTaskDecoder."""
+        return cls(None, None, None, task=_SegBDTask(model_enc, model_dec, num_multiply_d_loss, pseudo, scale_bd_loss),
+                   **kw)
 
     # -- CUDA-graph execution ---------------------------------------------------------------------
     def capture(self, src_imgs, src_lbls, tgt_imgs, warmup=2):
@@ -390,7 +423,10 @@ class MCDStep:
         self._mark("start")
         self.sync_g.zero_and_arm(), self.sync_f.zero_and_arm()
         fs = task.features(src_imgs)
-        ft = task.features(tgt_imgs) if task.a_uses_target else None
+        ft = None
+        if task.a_uses_target:
+            with torch.set_grad_enabled(not getattr(task, "a_target_forward_only", False)):
+                ft = task.features(tgt_imgs)
         loss = task.loss_a(fs, ft, src_imgs, src_lbls, tgt_imgs)
         self._backward(loss)
         c_loss = self._global(loss)
