@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MCD_ABI_VERSION 20
+#define MCD_ABI_VERSION 21
 
 enum {
   MCD_OK = 0,
@@ -393,6 +393,15 @@ int mcd_sigmoid_bwd(const float* y, const float* dy, float* dx, int64_t numel, i
 /* out = a + b (+ c, may be NULL) on fp32: the shortcut decoders' h1 + h2 + h3 (models/dilated_fcn.py:875,884,904). */
 int mcd_add3_f32(const float* a, const float* b, const float* c, float* out, int64_t numel, int device,
                  void* stream);
+/* ProbCrossEntropyLoss2d (loss.py:16-30; the criterion adapt_mfnet_trainer.py:149 selects for the Gate fusions):
+ * NLLLoss2d(weight, mean, ignore_index)(log(p), target) on a planar fp32 probability map p [N,C,H,W].
+ * acc (fp32 [4], caller-zeroed) as in mcd_ce2d_fwd: acc[0] += sum w * -log p[y], acc[1] += sum w, acc[2] += #bad labels.
+ * Backward: dp = gscale[0] * (c == y ? -w[y] / (p[y] * acc[1]) : 0), dense over all channels. */
+int mcd_prob_ce2d_fwd(const float* p, const int64_t* target, const float* weight, int64_t ignore_index, float* acc,
+                      int N, int C, int H, int W, int device, void* stream);
+int mcd_prob_ce2d_bwd(const float* p, const int64_t* target, const float* weight, int64_t ignore_index,
+                      const float* acc, const float* gscale, float* dp, int N, int C, int H, int W, int device,
+                      void* stream);
 /* nn.UpsamplingBilinear2d(scale_factor=s) = bilinear with align_corners=True (`use_torch_up`,
  * models/dilated_fcn.py:354-355,443-444).  Same tensor conventions as mcd_bilinear_up_fwd / _bwd; any s >= 1. */
 int mcd_bilinear_ac_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s, int device,

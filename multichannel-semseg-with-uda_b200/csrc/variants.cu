@@ -187,6 +187,46 @@ bilinear_ac_bwd_kernel(const void* __restrict__ dout, float* __restrict__ dx, in
   }
 }
 
+// ---- ProbCrossEntropyLoss2d (loss.py:16-30): NLLLoss2d(weight, mean)(log(p), target) on a probability map -----------
+// acc[0] += sum w[y] * -log p[y], acc[1] += sum w[y], acc[2] += labels outside [0, C) and != ignore_index
+__global__ void __launch_bounds__(256)
+prob_ce_fwd_kernel(const float* __restrict__ p, const int64_t* __restrict__ target, const float* __restrict__ weight,
+                   int64_t ignore_index, float* __restrict__ acc, int C, int64_t HW, int64_t total) {
+  __shared__ float red[32];
+  float s_l = 0.f, s_w = 0.f, s_bad = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t y = target[i];
+    if (y == ignore_index) continue;
+    if (y < 0 || y >= C) { s_bad += 1.f; continue; }
+    const int64_t n = i / HW, px = i % HW;
+    const float w = weight ? weight[y] : 1.f;
+    s_l -= w * logf(p[(n * C + y) * HW + px]);
+    s_w += w;
+  }
+  float t = block_sum(s_l, red);
+  if (threadIdx.x == 0 && t != 0.f) atomicAdd(acc + 0, t);
+  t = block_sum(s_w, red);
+  if (threadIdx.x == 0 && t != 0.f) atomicAdd(acc + 1, t);
+  t = block_sum(s_bad, red);
+  if (threadIdx.x == 0 && t != 0.f) atomicAdd(acc + 2, t);
+}
+
+// dp[n,c,px] = c == y ? -gscale * w[y] / (p[y] * acc[1]) : 0   (acc[1] = 1 for size_average=False)
+__global__ void __launch_bounds__(256)
+prob_ce_bwd_kernel(const float* __restrict__ p, const int64_t* __restrict__ target, const float* __restrict__ weight,
+                   int64_t ignore_index, const float* __restrict__ acc, const float* __restrict__ gscale,
+                   float* __restrict__ dp, int C, int64_t HW, int64_t total) {
+  const float scale = gscale[0] / acc[1];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t y = target[i];
+    const int64_t n = i / HW, px = i % HW;
+    const bool valid = y != ignore_index && y >= 0 && y < C;
+    float gy = 0.f;
+    if (valid) gy = -scale * (weight ? weight[y] : 1.f) / p[(n * C + y) * HW + px];
+    for (int c = 0; c < C; ++c) dp[(n * C + c) * HW + px] = (valid && c == y) ? gy : 0.f;
+  }
+}
+
 static inline int grid_for(int64_t n) { return (int)max64(1, min64((n + 255) / 256, 148 * 16)); }
 
 }  // namespace mcd
@@ -278,6 +318,27 @@ int mcd_add3_f32(const float* a, const float* b, const float* c, float* out, int
   MCD_REQUIRE(a && b && out && numel > 0, "add3_f32: bad arguments");
   add3_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(a, b, c, out, numel);
   return check_launch("add3_f32");
+}
+
+int mcd_prob_ce2d_fwd(const float* p, const int64_t* target, const float* weight, int64_t ignore_index, float* acc,
+                      int N, int C, int H, int W, int device, void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(p && target && acc && N > 0 && C > 0 && H > 0 && W > 0, "prob_ce2d_fwd: bad arguments");
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  prob_ce_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(p, target, weight, ignore_index, acc, C, HW,
+                                                                        total);
+  return check_launch("prob_ce2d_fwd");
+}
+
+int mcd_prob_ce2d_bwd(const float* p, const int64_t* target, const float* weight, int64_t ignore_index,
+                      const float* acc, const float* gscale, float* dp, int N, int C, int H, int W, int device,
+                      void* stream) {
+  MCD_ENTER(device);
+  MCD_REQUIRE(p && target && acc && gscale && dp && N > 0 && C > 0 && H > 0 && W > 0, "prob_ce2d_bwd: bad arguments");
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  prob_ce_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(p, target, weight, ignore_index, acc, gscale,
+                                                                        dp, C, HW, total);
+  return check_launch("prob_ce2d_bwd");
 }
 
 int mcd_bilinear_ac_up_fwd(const float* x, void* out, int out_f32, int N, int C, int h, int w_, int s, int device,

@@ -1,13 +1,14 @@
 """Per-pixel losses of the MCD step on libmcd_sm100 (drop-in for the reference's loss.py).
 
   CrossEntropyLoss2d(weight, size_average, ignore_index)(inputs[B,C,H,W], targets[B,H,W] int64)   loss.py:7-13
+  ProbCrossEntropyLoss2d(weight, size_average)(probabilities, targets)   (Gate fusions)          loss.py:16-30
   Diff2d()(inputs1, inputs2) = mean |softmax - softmax|                                          loss.py:93-100
+  JSD, Symkl2d, MySymkl2d, MisSymKLD, SpatialJSD2d                                               loss.py:68-171
   bce2d(input, target)   class-balanced binary cross entropy                                     loss.py:131-138
-  get_prob_distance_criterion(name, n_class)                                                     loss.py:192-210
+  get_prob_distance_criterion(name, n_class)   every name the reference knows                    loss.py:192-210
 
 Each criterion is ONE fused forward kernel and ONE fused backward kernel over the full-resolution
-logits (softmax is never materialised).  Other divergences of the reference (jsd, symkl, ...) are not on
-the default `--d_loss diff` path (argmyparse.py:131) and raise NotImplementedError.
+logits (softmax is never materialised).
 Extra entry points used by the multitask decoders: mse_loss, sigmoid3_mean, sigmoid3_bce2d.
 """
 import os
@@ -133,6 +134,47 @@ class CrossEntropyLoss2d(nn.Module):
             w = w.to(logits.device)
         return _CE2dFn.apply(logits, targets.contiguous(), w, self.ignore_index, self.size_average,
                              self._dist_group)
+
+
+class _ProbCE2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, target, weight, ignore_index, size_average):
+        acc = ops.prob_ce2d_fwd(p, target, weight, ignore_index)
+        if _dp_group is not False and size_average:
+            import torch.distributed as dist        # global normaliser, local numerator (as CrossEntropyLoss2d)
+            dist.all_reduce(acc[1:2], op=dist.ReduceOp.SUM, group=_dp_group)
+        if _CHECK_LABELS and float(acc[2]) != 0:
+            raise IndexError("ProbCrossEntropyLoss2d: %d target labels outside [0, %d)" % (int(acc[2]), p.shape[1]))
+        ctx.save_for_backward(p, target, weight, acc)
+        ctx.ignore_index, ctx.size_average = ignore_index, size_average
+        return acc[0] / acc[1] if size_average else acc[0].clone()
+
+    @staticmethod
+    def backward(ctx, go):
+        p, target, weight, acc = ctx.saved_tensors
+        if not ctx.size_average:
+            acc = torch.ones_like(acc)
+        return ops.prob_ce2d_bwd(p, target, weight, ctx.ignore_index, acc, _gscale(go)), None, None, None, None
+
+
+class ProbCrossEntropyLoss2d(nn.Module):
+    """cross entropy between a probability tensor (0..1) and the labels: NLLLoss2d(weight, size_average)(log(inputs),
+    targets) - reference loss.py:16-30, the criterion adapt_mfnet_trainer.py:149 selects for the Gate fusions."""
+
+    def __init__(self, weight=None, size_average=True):
+        super().__init__()
+        self.nll_loss = _NLLState(weight)
+        self.size_average = size_average
+        self.ignore_index = -100
+
+    def forward(self, inputs, targets):
+        p = inputs if inputs.dtype == F32 else inputs.float()
+        if targets.dtype != torch.int64:
+            targets = targets.long()
+        w = self.nll_loss.weight
+        if w is not None and w.device != p.device:
+            w = w.to(p.device)
+        return _ProbCE2dFn.apply(p.contiguous(), targets.contiguous(), w, self.ignore_index, self.size_average)
 
 
 class _Diff2dFn(torch.autograd.Function):

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # MCD_LIB_PATH: an alternative build of the same library (A/B measurements of compile-time variants)
 LIB_PATH = os.environ.get("MCD_LIB_PATH") or os.path.join(PKG_DIR, "libmcd_sm100.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
 OUT_NHWC_BF16, OUT_PLANAR_F32 = 0, 1
@@ -101,6 +101,8 @@ _SIGNATURES = {
     "mcd_sigmoid_fwd": (c_int, [P, P, c_int64, c_int, P]),
     "mcd_sigmoid_bwd": (c_int, [P, P, P, c_int64, c_int, P]),
     "mcd_add3_f32": (c_int, [P, P, P, P, c_int64, c_int, P]),
+    "mcd_prob_ce2d_fwd": (c_int, [P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "mcd_prob_ce2d_bwd": (c_int, [P, P, P, c_int64, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_bilinear_ac_up_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_bilinear_ac_up_bwd": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "mcd_sgd_step": (c_int, [P, P, P, c_int64, c_float, c_float, c_float, c_int, c_int, P]),

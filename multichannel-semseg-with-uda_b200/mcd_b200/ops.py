@@ -909,6 +909,22 @@ def add3_f32(a, b, c=None):
     return out
 
 
+def prob_ce2d_fwd(p, target, weight, ignore_index):
+    n, c, h, w = p.shape
+    acc = zeros_f32(4, p.device)
+    abi.check(abi.lib().mcd_prob_ce2d_fwd(_p(p), _p(target), _p(weight), int(ignore_index), _p(acc), n, c, h, w,
+                                          _dev(p), _stream(p)), "prob_ce2d_fwd")
+    return acc
+
+
+def prob_ce2d_bwd(p, target, weight, ignore_index, acc, gscale):
+    n, c, h, w = p.shape
+    d = torch.empty_like(p)
+    abi.check(abi.lib().mcd_prob_ce2d_bwd(_p(p), _p(target), _p(weight), int(ignore_index), _p(acc), _p(gscale), _p(d),
+                                          n, c, h, w, _dev(p), _stream(p)), "prob_ce2d_bwd")
+    return d
+
+
 def bilinear_ac_up_fwd(x, s, out_f32=False):
     n, c, h, wd = x.shape
     out = torch.empty((n, c, s * h, s * wd), dtype=F32 if out_f32 else BF16, device=x.device)

@@ -283,6 +283,11 @@ def ce2d(logits, target, weight=None, ignore_index=-100):
     return F.nll_loss(F.log_softmax(logits, dim=1), target, weight, ignore_index=ignore_index)
 
 
+def prob_ce2d(p, target, weight=None, ignore_index=-100):
+    """ProbCrossEntropyLoss2d (loss.py:16-30): NLLLoss2d(weight)(log(p), target) on a probability map"""
+    return F.nll_loss(torch.log(p), target, weight, ignore_index=ignore_index)
+
+
 def diff2d(a, b):
     return torch.mean(torch.abs(F.softmax(a, dim=1) - F.softmax(b, dim=1)))
 

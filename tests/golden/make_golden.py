@@ -652,6 +652,15 @@ def golden_variants():
     with torch.no_grad():
         ps, pd = dec(feats(1004)["h8"])
     out["mt_src:semseg"], out["mt_src:dep"] = ps.numpy(), pd.numpy()
+    # ---- ProbCrossEntropyLoss2d (loss.py:16-30): the criterion of the Gate fusions (adapt_mfnet_trainer.py:149)
+    from loss import ProbCrossEntropyLoss2d
+    gg = torch.Generator().manual_seed(1111)
+    p = torch.softmax(torch.randn(2, N_CLASS, 6, 8, generator=gg) * 2, 1).requires_grad_(True)
+    t = torch.randint(0, N_CLASS, (2, 6, 8), generator=gg)
+    t[0, 0, :3] = -100                                  # NLLLoss2d's default ignore_index
+    v = ProbCrossEntropyLoss2d(weight)(p, t)
+    v.backward()
+    out.update({"pce:p": p.detach().numpy(), "pce:t": t.numpy(), "pce:loss": float(v), "pce:dp": p.grad.numpy()})
     np.savez_compressed(os.path.join(HERE, "variants.npz"), **{k: v for k, v in out.items() if v is not None})
 
 

@@ -479,3 +479,12 @@ def test_oracle_decoder_options_match_reference(kind, seed, fseed):
     close(hd["h8"].grad.numpy(), z[kind + ":g:x:h8"], rtol=2e-3)
     if kind == "tri_opt":
         close(preds[0].detach()[:, :, ::4, ::4].numpy(), z["tri_opt:pred1_sub"], rtol=1e-3)
+
+
+def test_oracle_prob_cross_entropy_matches_reference():
+    z = _variants()
+    p = torch.tensor(z["pce:p"], requires_grad=True)
+    v = O.prob_ce2d(p, torch.tensor(z["pce:t"]), O.class_weight(N_CLASS))
+    v.backward()
+    assert abs(float(v) - float(z["pce:loss"])) <= 1e-6 * abs(float(z["pce:loss"]))
+    close(p.grad.numpy(), z["pce:dp"], rtol=1e-6)
