@@ -148,6 +148,54 @@ class GradSync:
         self.armed = False
 
 
+class DataParallel(torch.nn.Module):
+    """What `is_data_parallel=True` of the reference's factories returns (models/model_util.py:75-76,96-97,283-284:
+    `torch.nn.DataParallel(model)`), for one process per GPU.
+
+    torch.nn.DataParallel replicates a module over the GPUs of ONE process every forward; here every rank of a
+    `torchrun` job holds its own replica and its own shard of the batch.  The wrapper keeps what scripts and
+    checkpoints see of nn.DataParallel - the `.module` attribute, the `module.` prefix of the state_dict keys, the
+    call signature - and makes a hand-written training loop data parallel: with torch.distributed initialised
+    (world > 1) rank 0's parameters and buffers are broadcast at construction (replica 0 is the one nn.DataParallel
+    keeps) and every parameter gradient is SUM-all-reduced when autograd delivers it.  The criteria return each rank's
+    SHARE of the global-batch loss once `loss.set_process_group()` has been called, so the summed gradients are the
+    global-batch gradients (DataParallel's semantics; BatchNorm statistics stay per replica, as there).
+    With one process it is a transparent wrapper.  `mcd_b200.step.MCDStep` unwraps it and uses its own bucketed,
+    overlapped GradSync instead of the per-parameter collectives of this slow-but-general path."""
+
+    def __init__(self, module, process_group=None):
+        super().__init__()
+        self.module = module
+        self.group = process_group
+        self.sync_in_backward = True
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t, 0, group=process_group)
+            for prm in module.parameters():
+                if prm.requires_grad:
+                    prm.register_hook(self._reduce)     # fires once per backward with the gradient of THAT pass
+
+    def _reduce(self, grad):
+        if not self.sync_in_backward:
+            return None
+        g = grad.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        return g
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)
+
+
+def unwrap(module):
+    """the module inside a DataParallel wrapper (whose own gradient exchange is switched off: the caller takes over)"""
+    if isinstance(module, DataParallel):
+        module.sync_in_backward = False
+        return module.module
+    return module
+
+
 def init_from_env(backend=None):
     """torchrun entry: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment."""
     import os

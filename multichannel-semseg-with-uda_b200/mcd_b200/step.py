@@ -73,6 +73,7 @@ class _EarlyFusionTask:
     a_uses_target = False
 
     def __init__(self, models, criterion, criterion_d, mult):
+        models = [parallel.unwrap(m) for m in models]       # is_data_parallel=True wrappers: MCDStep syncs itself
         self.gens, (self.f1, self.f2) = list(models[:-2]), models[-2:]
         self.clfs = [self.f1] if self.f2 is self.f1 else [self.f1, self.f2]
         self.mfnet = len(self.gens) == 2
@@ -147,6 +148,7 @@ class _MultiTaskTask:
     a_uses_target = True
 
     def __init__(self, model_enc, model_dec, triple, mult):
+        model_enc, model_dec = parallel.unwrap(model_enc), parallel.unwrap(model_dec)
         self.gens, self.clfs = [model_enc], [model_dec]
         self.enc, self.dec, self.triple, self.mult = model_enc, model_dec, triple, mult
 

@@ -2,9 +2,9 @@
 
 Same function names, argument meaning and error behaviour as the reference (file:line below) for the DRN
 branches that are on the hot path; every other `net_name` raises NotImplementedError like the reference does
-for unknown names.  `is_data_parallel=True` is refused: the reference's single-process nn.DataParallel
-(models/model_util.py:283-284) is replaced by one process per GPU with NCCL gradient all-reduce
-(mcd_b200/parallel.py).
+for unknown names.  `is_data_parallel=True` wraps the models in mcd_b200.parallel.DataParallel: the reference's
+single-process nn.DataParallel (models/model_util.py:283-284) becomes one process per GPU with NCCL gradient
+all-reduce, behind the same `.module` / `module.`-prefixed state_dict interface.
 """
 import torch
 from torch import nn
@@ -20,10 +20,14 @@ def _check_drn(net_name):
         raise NotImplementedError("libmcd_sm100 builds %s only (got %s)" % (", ".join(_DRN_NAMES), net_name))
 
 
-def _no_data_parallel(flag):
-    if flag:
-        raise NotImplementedError("nn.DataParallel is replaced by one process per GPU: launch with torchrun "
-                                  "and wrap the models with mcd_b200.parallel.GradSync")
+def _data_parallel(models, flag):
+    """`is_data_parallel=True` (reference models/model_util.py:75-76,96-97,283-284 wraps every model in
+    torch.nn.DataParallel): one process per GPU here, see mcd_b200.parallel.DataParallel - same `.module` attribute
+    and `module.`-prefixed checkpoints, gradient all-reduce over the ranks of a torchrun job."""
+    if not flag:
+        return models
+    from mcd_b200.parallel import DataParallel
+    return [DataParallel(m) for m in models]
 
 
 def get_models(net_name, input_ch, n_class, res="50", method="MCD", is_data_parallel=False):
@@ -68,8 +72,7 @@ def get_models(net_name, input_ch, n_class, res="50", method="MCD", is_data_para
     else:
         # the reference *returns* (does not raise) the exception object here (models/model_util.py:281)
         return NotImplementedError("Sorry... Only MCD is supported!")
-    _no_data_parallel(is_data_parallel)
-    return model_list
+    return _data_parallel(model_list, is_data_parallel)
 
 
 def get_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
@@ -82,8 +85,7 @@ def get_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, dis
     dec = MultiTaskDecoder if is_src_only else MCDMultiTaskDecoder
     model_dec = dec(n_class=n_class, depth_ch=input_ch - 3, semseg_criterion=semseg_criterion,
                     discrepancy_criterion=discrepancy_criterion)
-    _no_data_parallel(is_data_parallel)
-    return model_enc, model_dec
+    return tuple(_data_parallel([model_enc, model_dec], is_data_parallel))
 
 
 def get_triple_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
@@ -105,8 +107,7 @@ def get_triple_multitask_models(net_name, input_ch, n_class, semseg_criterion=No
                                               semseg_shortcut=semseg_shortcut, depth_shortcut=depth_shortcut,
                                               add_pred_seg_boundary_loss=add_pred_seg_boundary_loss,
                                               use_seg2bd_conv=use_seg2bd_conv)
-    _no_data_parallel(is_data_parallel)
-    return model_enc, model_dec
+    return tuple(_data_parallel([model_enc, model_dec], is_data_parallel))
 
 
 def get_segbd_multitask_models(net_name, input_ch, n_class, semseg_criterion=None, discrepancy_criterion=None,
@@ -124,8 +125,7 @@ def get_segbd_multitask_models(net_name, input_ch, n_class, semseg_criterion=Non
                                          semseg_shortcut=semseg_shortcut,
                                          add_pred_seg_boundary_loss=add_pred_seg_boundary_loss,
                                          use_seg2bd_conv=use_seg2bd_conv)
-    _no_data_parallel(is_data_parallel)
-    return model_enc, model_dec
+    return tuple(_data_parallel([model_enc, model_dec], is_data_parallel))
 
 
 def get_optimizer(model_parameters, opt, lr, momentum, weight_decay):

@@ -101,3 +101,82 @@ def test_gradsync_single_process_drops_grads():
     assert lin.weight.grad is None            # single process: gradients are dropped, not zero-filled
     lin(torch.ones(2, 4)).sum().backward()
     assert torch.equal(lin.weight.grad, g)
+
+
+def _dp_worker(rank, world, port, q):
+    try:
+        for p in (PKG, ROOT):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                          WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+        from mcd_b200 import parallel
+        parallel.init_from_env(backend="gloo")
+        torch.manual_seed(rank)                   # DIFFERENT initial replicas: rank 0's must win (nn.DataParallel)
+        inner = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(),
+                                    torch.nn.Linear(16, 4))
+        net = parallel.DataParallel(inner)
+        assert net.module is inner and net.world == world
+        assert all(k.startswith("module.") for k in net.state_dict())
+        torch.manual_seed(0)
+        ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(),
+                                  torch.nn.Linear(16, 4))
+        for a, b in zip(inner.state_dict().values(), ref.state_dict().values()):
+            assert torch.equal(a, b), "rank 0's replica was not broadcast"
+        gen = torch.Generator().manual_seed(1)
+        xs = [torch.randn(6, 8, generator=gen) for _ in range(world)]
+        inner.eval(), ref.eval()                  # per-replica BatchNorm statistics are DataParallel's too; keep it simple
+        # every rank's loss is its SHARE of the global objective, as the library's criteria return it
+        for accumulate in (False, True):          # second pass WITHOUT zero_grad: gradients accumulate correctly
+            if not accumulate:
+                net.zero_grad(), ref.zero_grad()
+            net(xs[rank]).pow(2).sum().backward()
+            sum(ref(x).pow(2).sum() for x in xs).backward()
+            for p_, q_ in zip(inner.parameters(), ref.parameters()):
+                assert torch.allclose(p_.grad, q_.grad, rtol=1e-5, atol=1e-6), (accumulate, rank)
+        # MCDStep takes the exchange over: unwrap() switches the wrapper's collectives off
+        assert parallel.unwrap(net) is inner and net.sync_in_backward is False
+        net.zero_grad()
+        net(xs[rank]).pow(2).sum().backward()
+        ref.zero_grad()
+        ref(xs[rank]).pow(2).sum().backward()
+        for p_, q_ in zip(inner.parameters(), ref.parameters()):
+            assert torch.allclose(p_.grad, q_.grad, rtol=1e-5, atol=1e-6)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc())))
+
+
+def test_data_parallel_wrapper_world2_gloo():
+    """models.model_util factories with is_data_parallel=True return mcd_b200.parallel.DataParallel wrappers
+    (reference models/model_util.py:283-284): replica broadcast, summed gradients == global-batch gradients,
+    accumulation across backward passes, `module.` state_dict keys."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_factories_wrap_with_is_data_parallel():
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import warnings
+    from mcd_b200 import parallel
+    from models.model_util import get_models, get_multitask_models
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ms = get_models("drn_d_22", 6, 41, is_data_parallel=True)
+        enc, dec = get_multitask_models("drn_d_22", 6, 41, is_data_parallel=True)
+    assert isinstance(ms, list) and all(isinstance(m, parallel.DataParallel) for m in ms + [enc, dec])
+    assert all(k.startswith("module.") for k in ms[0].state_dict()) and hasattr(ms[0].module, "seg")
+    assert not hasattr(dec, "get_loss")           # nn.DataParallel does not delegate attributes either
