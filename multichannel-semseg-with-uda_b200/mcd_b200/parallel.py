@@ -156,8 +156,9 @@ class DataParallel(torch.nn.Module):
     `torchrun` job holds its own replica and its own shard of the batch.  The wrapper keeps what scripts and
     checkpoints see of nn.DataParallel - the `.module` attribute, the `module.` prefix of the state_dict keys, the
     call signature - and makes a hand-written training loop data parallel: with torch.distributed initialised
-    (world > 1) rank 0's parameters and buffers are broadcast at construction (replica 0 is the one nn.DataParallel
-    keeps) and every parameter gradient is SUM-all-reduced when autograd delivers it.  The criteria return each rank's
+    (world > 1) rank 0's parameters and buffers are broadcast before the first forward (replica 0 is the one
+    nn.DataParallel keeps; by then the script has moved the model to its device, which NCCL needs) and every parameter
+    gradient is SUM-all-reduced when autograd delivers it.  The criteria return each rank's
     SHARE of the global-batch loss once `loss.set_process_group()` has been called, so the summed gradients are the
     global-batch gradients (DataParallel's semantics; BatchNorm statistics stay per replica, as there).
     With one process it is a transparent wrapper.  `mcd_b200.step.MCDStep` unwraps it and uses its own bucketed,
@@ -169,10 +170,8 @@ class DataParallel(torch.nn.Module):
         self.group = process_group
         self.sync_in_backward = True
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._replicated = self.world == 1
         if self.world > 1:
-            with torch.no_grad():
-                for t in list(module.parameters()) + list(module.buffers()):
-                    dist.broadcast(t, 0, group=process_group)
             for prm in module.parameters():
                 if prm.requires_grad:
                     prm.register_hook(self._reduce)     # fires once per backward with the gradient of THAT pass
@@ -184,13 +183,23 @@ class DataParallel(torch.nn.Module):
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         return g
 
+    def replicate(self):
+        """rank 0's parameters and buffers to every rank (once; idempotent)"""
+        if not self._replicated:
+            with torch.no_grad():
+                for t in list(self.module.parameters()) + list(self.module.buffers()):
+                    dist.broadcast(t, 0, group=self.group)
+            self._replicated = True
+
     def forward(self, *inputs, **kwargs):
+        self.replicate()
         return self.module(*inputs, **kwargs)
 
 
 def unwrap(module):
     """the module inside a DataParallel wrapper (whose own gradient exchange is switched off: the caller takes over)"""
     if isinstance(module, DataParallel):
+        module.replicate()
         module.sync_in_backward = False
         return module.module
     return module

@@ -121,11 +121,13 @@ def _dp_worker(rank, world, port, q):
         torch.manual_seed(0)
         ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(),
                                   torch.nn.Linear(16, 4))
-        for a, b in zip(inner.state_dict().values(), ref.state_dict().values()):
-            assert torch.equal(a, b), "rank 0's replica was not broadcast"
         gen = torch.Generator().manual_seed(1)
         xs = [torch.randn(6, 8, generator=gen) for _ in range(world)]
         inner.eval(), ref.eval()                  # per-replica BatchNorm statistics are DataParallel's too; keep it simple
+        with torch.no_grad():
+            net(xs[rank])                         # the first forward replicates rank 0's parameters and buffers
+        for a, b in zip(inner.state_dict().values(), ref.state_dict().values()):
+            assert torch.equal(a, b), "rank 0's replica was not broadcast"
         # every rank's loss is its SHARE of the global objective, as the library's criteria return it
         for accumulate in (False, True):          # second pass WITHOUT zero_grad: gradients accumulate correctly
             if not accumulate:

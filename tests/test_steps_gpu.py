@@ -374,7 +374,7 @@ def _dp_worker(rank, world, port, graph, q):
     try:
         import faulthandler
         if os.path.isdir(OUT):          # a rank that hangs leaves its Python stack behind
-            fh = open(os.path.join(OUT, "dp_worker_rank%d_graph%d.log" % (rank, int(bool(graph)))), "w")
+            fh = open(os.path.join(OUT, "dp_worker_rank%d_graph%s.log" % (rank, graph)), "w")
             faulthandler.dump_traceback_later(240, exit=True, file=fh)
         pkg = os.path.join(ROOT, "multichannel-semseg-with-uda_b200")
         for p in (pkg, ROOT):
@@ -393,18 +393,60 @@ def _dp_worker(rank, world, port, graph, q):
         F2 = O.to_device(O.fill_state_dict_(O.init_head(N_CLASS), 3), dev)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS)]
+            models = [m.to(dev).train() for m in get_models("drn_d_38", 6, N_CLASS, is_data_parallel=graph == "loop")]
         for m, sd in zip(models, (G, F1, F2)):
-            _load(m, sd)
+            _load(parallel.unwrap(m) if graph != "loop" else m.module, sd)
         src, tgt, lbl = _inputs(9, 2 * world, (240, 320), dev)              # the GLOBAL batch, known to every rank
         # make the per-shard sum of class weights differ (class 40 has weight 0): the normaliser must be global
         lbl[:2] = torch.where(torch.rand(lbl[:2].shape, device=dev) < 0.5, torch.full_like(lbl[:2], 40), lbl[:2])
         sl = slice(2 * rank, 2 * rank + 2)
         w = O.class_weight(N_CLASS).to(dev)
-        step = MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=2)
-        assert step.world == world
-        iters = 2 if graph else 1
-        if graph:
+        step = None
+        if graph == "loop":
+            # the reference's loop body (adapt_trainer.py:162-212) verbatim on is_data_parallel=True models: the
+            # wrappers exchange the gradients, the criteria return this rank's share of the global loss
+            import loss as loss_mod
+            from models.model_util import get_optimizer
+            loss_mod.set_process_group()
+            model_g, model_f1, model_f2 = models
+            assert all(isinstance(m, parallel.DataParallel) for m in models)
+            kw = dict(lr=1e-3, momentum=0.9, opt="sgd", weight_decay=2e-5)
+            optimizer_g = get_optimizer(model_g.parameters(), **kw)
+            optimizer_f = get_optimizer(list(model_f1.parameters()) + list(model_f2.parameters()), **kw)
+            criterion, criterion_d = CrossEntropyLoss2d(w), get_prob_distance_criterion("diff")
+            src_imgs, src_lbls, tgt_imgs = src[sl], lbl[sl], tgt[sl]
+            optimizer_g.zero_grad(), optimizer_f.zero_grad()
+            outputs = model_g(src_imgs)
+            loss = criterion(model_f1(outputs), src_lbls) + criterion(model_f2(outputs), src_lbls)
+            loss.backward()
+            c = loss.detach().clone()
+            torch.distributed.all_reduce(c)               # shares -> the global-batch loss
+            optimizer_g.step(), optimizer_f.step()
+            optimizer_g.zero_grad(), optimizer_f.zero_grad()
+            outputs = model_g(src_imgs)
+            loss = criterion(model_f1(outputs), src_lbls) + criterion(model_f2(outputs), src_lbls)
+            outputs = model_g(tgt_imgs)
+            loss = loss - criterion_d(model_f1(outputs), model_f2(outputs))
+            loss.backward()
+            optimizer_f.step()
+            for i in range(2):
+                optimizer_g.zero_grad()
+                outputs = model_g(tgt_imgs)
+                loss = criterion_d(model_f1(outputs), model_f2(outputs)) * 1.0
+                loss.backward()
+                optimizer_g.step()
+            d = loss.detach().clone()
+            torch.distributed.all_reduce(d)
+            d = d / 2
+            models = [m.module for m in models]
+            iters = 1
+        else:
+            step = MCDStep(models, CrossEntropyLoss2d(w), get_prob_distance_criterion("diff"), num_k=2)
+            assert step.world == world
+            iters = 2 if graph else 1
+        if graph == "loop":
+            pass
+        elif graph:
             step(src[sl], lbl[sl], tgt[sl])
             step.capture(src[sl], lbl[sl], tgt[sl], warmup=0)
             c, d = step.replay(src[sl], lbl[sl], tgt[sl])
@@ -424,7 +466,8 @@ def _dp_worker(rank, world, port, graph, q):
                        rv=nerr(models[0].base[5][2].bn2.running_var, G["base.5.2.bn2.running_var"]))
         q.put((rank, "ok", res))
         # a live CUDA graph that holds NCCL kernels blocks destroy_process_group(): release it first
-        step.graph = None
+        if step is not None:
+            step.graph = None
         del step
         import gc
         gc.collect()
@@ -436,7 +479,7 @@ def _dp_worker(rank, world, port, graph, q):
         q.put((rank, "fail: %s\n%s" % (e, traceback.format_exc()), None))
 
 
-@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("graph", [False, True, "loop"])
 def test_two_gpu_matches_dataparallel_semantics(graph):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
