@@ -25,44 +25,98 @@ add_nhwc_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4*
 // ---- out = x1 * sigmoid(a) + x2 * (1 - sigmoid(a))   (GateFusion, models/fusion.py:17-21) ---------------------------
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
+// element-wise kernels: a float4 body over the first 4 * n4 elements (n4 = 0 when a pointer is not 16-byte aligned)
+// and a scalar tail; 16 bytes per load keep enough bytes in flight for the HBM latency at 2048 threads per SM
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i) { return reinterpret_cast<const float4*>(p)[i]; }
+__device__ __forceinline__ void st4(float* p, int64_t i, float4 v) { reinterpret_cast<float4*>(p)[i] = v; }
+__device__ __forceinline__ float gate1(float x1, float x2, float a) {
+  const float g = sigmoidf_(a);
+  return x1 * g + x2 * (1.f - g);
+}
+
 __global__ void __launch_bounds__(256)
 gate_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ a,
-                float* __restrict__ out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float g = sigmoidf_(a[i]);
-    out[i] = x1[i] * g + x2[i] * (1.f - g);
+                float* __restrict__ out, int64_t n, int64_t n4) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 u = ld4(x1, i), v = ld4(x2, i), w = ld4(a, i);
+    st4(out, i, make_float4(gate1(u.x, v.x, w.x), gate1(u.y, v.y, w.y), gate1(u.z, v.z, w.z), gate1(u.w, v.w, w.w)));
   }
+  for (int64_t i = 4 * n4 + t0; i < n; i += stride) out[i] = gate1(x1[i], x2[i], a[i]);
+}
+
+__device__ __forceinline__ void gate_bwd1(float x1, float x2, float a, float d, float* g1, float* g2, float* ga) {
+  const float g = sigmoidf_(a);
+  *g1 = d * g;
+  *g2 = d * (1.f - g);
+  *ga = d * (x1 - x2) * g * (1.f - g);
 }
 
 __global__ void __launch_bounds__(256)
 gate_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ a,
                 const float* __restrict__ dout, float* __restrict__ dx1, float* __restrict__ dx2,
-                float* __restrict__ da, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float g = sigmoidf_(a[i]), d = dout[i];
-    if (dx1) dx1[i] = d * g;
-    if (dx2) dx2[i] = d * (1.f - g);
-    if (da) da[i] = d * (x1[i] - x2[i]) * g * (1.f - g);
+                float* __restrict__ da, int64_t n, int64_t n4) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 u = ld4(x1, i), v = ld4(x2, i), w = ld4(a, i), d = ld4(dout, i);
+    float4 r1, r2, ra;
+    gate_bwd1(u.x, v.x, w.x, d.x, &r1.x, &r2.x, &ra.x);
+    gate_bwd1(u.y, v.y, w.y, d.y, &r1.y, &r2.y, &ra.y);
+    gate_bwd1(u.z, v.z, w.z, d.z, &r1.z, &r2.z, &ra.z);
+    gate_bwd1(u.w, v.w, w.w, d.w, &r1.w, &r2.w, &ra.w);
+    if (dx1) st4(dx1, i, r1);
+    if (dx2) st4(dx2, i, r2);
+    if (da) st4(da, i, ra);
+  }
+  for (int64_t i = 4 * n4 + t0; i < n; i += stride) {
+    float r1, r2, ra;
+    gate_bwd1(x1[i], x2[i], a[i], dout[i], &r1, &r2, &ra);
+    if (dx1) dx1[i] = r1;
+    if (dx2) dx2[i] = r2;
+    if (da) da[i] = ra;
   }
 }
 
 // ---- softmax over the channel axis of a planar fp32 tensor (one thread per pixel, coalesced across pixels) -------
+// C <= SM_CMAX (= 44): the channel vector of the pixel lives in registers - ONE pass over the input, all C loads of a thread
+// independent and in flight together; larger C: three passes (the re-reads hit L2).
+constexpr int SM_CMAX = 44;          // 41 classes padded to a multiple of 4
+
+template <bool REG>
 __global__ void __launch_bounds__(256)
 softmax_ch_fwd_kernel(const float* __restrict__ x, float* __restrict__ p, int C, int64_t HW, int64_t total) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / HW, px = i % HW;
     const float* xp = x + n * C * HW + px;
     float* pp = p + n * C * HW + px;
-    float m = -INFINITY;
-    for (int c = 0; c < C; ++c) m = fmaxf(m, xp[c * HW]);
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s += __expf(xp[c * HW] - m);
-    const float inv = 1.f / s;
-    for (int c = 0; c < C; ++c) pp[c * HW] = __expf(xp[c * HW] - m) * inv;
+    if (REG) {
+      float v[SM_CMAX];
+#pragma unroll
+      for (int c = 0; c < SM_CMAX; ++c) v[c] = c < C ? xp[c * HW] : -INFINITY;
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < SM_CMAX; ++c) m = fmaxf(m, v[c]);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < SM_CMAX; ++c) { v[c] = __expf(v[c] - m); s += v[c]; }      // exp(-inf) = 0 for the padding
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int c = 0; c < SM_CMAX; ++c)
+        if (c < C) pp[c * HW] = v[c] * inv;
+    } else {
+      float m = -INFINITY;
+      for (int c = 0; c < C; ++c) m = fmaxf(m, xp[c * HW]);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += __expf(xp[c * HW] - m);
+      const float inv = 1.f / s;
+      for (int c = 0; c < C; ++c) pp[c * HW] = __expf(xp[c * HW] - m) * inv;
+    }
   }
 }
 
-// dx = p * (dp - sum_c dp * p)
+// dx = p * (dp - sum_c dp * p).  Two passes over p and dp (the second hits L1 / L2): measured 4.3 TB/s of algorithmic
+// traffic; register-resident variants were slower (both vectors: 138 registers, one block per SM, 3.7 TB/s; p only with
+// dp re-read: 2.6 TB/s) - scripts/bench_variants.py
 __global__ void __launch_bounds__(256)
 softmax_ch_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ dx, int C,
                       int64_t HW, int64_t total) {
@@ -76,14 +130,16 @@ softmax_ch_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
 }
 
 // ---- torch.cat([a, b], 1) and its backward (split) on planar fp32 tensors ------------------------------------------
-// cat == 1: ab[n][0:Ca] = a[n], ab[n][Ca:] = b[n];  cat == 0: the reverse copy (a / b may be null)
+// cat == 1: ab[n][0:Ca] = a[n], ab[n][Ca:] = b[n];  cat == 0: the reverse copy (a / b may be null).
+// T = float4 when the per-image element counts are multiples of 4 and the pointers 16-byte aligned (ea / eb / total
+// are then counted in float4 units), else float.
+template <typename T>
 __global__ void __launch_bounds__(256)
-cat2_kernel(float* __restrict__ a, float* __restrict__ b, float* __restrict__ ab, int64_t ea, int64_t eb,
-            int64_t total, int cat) {
+cat2_kernel(T* __restrict__ a, T* __restrict__ b, T* __restrict__ ab, int64_t ea, int64_t eb, int64_t total, int cat) {
   const int64_t e = ea + eb;   // elements per image
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / e, r = i % e;
-    float* part = r < ea ? (a ? a + n * ea + r : nullptr) : (b ? b + n * eb + (r - ea) : nullptr);
+    T* part = r < ea ? (a ? a + n * ea + r : nullptr) : (b ? b + n * eb + (r - ea) : nullptr);
     if (!part) continue;
     if (cat) ab[i] = *part; else *part = ab[i];
   }
@@ -91,14 +147,24 @@ cat2_kernel(float* __restrict__ a, float* __restrict__ b, float* __restrict__ ab
 
 // ---- sigmoid ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = sigmoidf_(x[i]);
+sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int64_t n4) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 v = ld4(x, i);
+    st4(y, i, make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w)));
+  }
+  for (int64_t i = 4 * n4 + t0; i < n; i += stride) y[i] = sigmoidf_(x[i]);
 }
 __global__ void __launch_bounds__(256)
-sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dx[i] = dy[i] * y[i] * (1.f - y[i]);
+sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, int64_t n,
+                   int64_t n4) {
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < n4; i += stride) {
+    const float4 v = ld4(y, i), d = ld4(dy, i);
+    st4(dx, i, make_float4(d.x * v.x * (1.f - v.x), d.y * v.y * (1.f - v.y), d.z * v.z * (1.f - v.z),
+                           d.w * v.w * (1.f - v.w)));
+  }
+  for (int64_t i = 4 * n4 + t0; i < n; i += stride) dx[i] = dy[i] * y[i] * (1.f - y[i]);
 }
 
 // ---- out = a + b (+ c) on fp32 tensors (the shortcut decoders' h1 + h2 + h3, dilated_fcn.py:875,884,904) -----------
@@ -120,25 +186,46 @@ __device__ __forceinline__ void bil_src_ac(int o, float scale, int in, int* i0, 
   *lam = src - (float)a;
 }
 
-template <bool OUT_F32>
+// V = 8: a thread produces 8 adjacent output pixels of a row (W % 8 == 0) and stores them as 2 x float4 / one 16-byte
+// bf16 vector; V = 1: any width.  The gathers hit L1 / L2 (the source is s^2 times smaller than the output).
+template <bool OUT_F32, int V>
 __global__ void __launch_bounds__(256)
 bilinear_ac_fwd_kernel(const float* __restrict__ x, void* __restrict__ out, int h, int wd, int H, int W, float sh,
                        float sw, int64_t total) {
+  const int wv = W / V;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ow = (int)(i % W);
-    const int oh = (int)((i / W) % H);
-    const int64_t nc = i / ((int64_t)W * H);
-    int h0, h1, w0, w1;
-    float lh, lw;
+    const int j = (int)(i % wv);
+    const int oh = (int)((i / wv) % H);
+    const int64_t nc = i / ((int64_t)wv * H);
+    int h0, h1;
+    float lh;
     bil_src_ac(oh, sh, h, &h0, &h1, &lh);
-    bil_src_ac(ow, sw, wd, &w0, &w1, &lw);
     const float* r0 = x + (nc * h + h0) * wd;
     const float* r1 = x + (nc * h + h1) * wd;
-    // ATen's weighting order: h0lambda * (w0lambda * p00 + w1lambda * p01) + h1lambda * (w0lambda * p10 + w1lambda * p11)
-    const float l0h = 1.f - lh, l0w = 1.f - lw;
-    const float v = l0h * (l0w * r0[w0] + lw * r0[w1]) + lh * (l0w * r1[w0] + lw * r1[w1]);
-    if (OUT_F32) reinterpret_cast<float*>(out)[i] = v;
-    else reinterpret_cast<__nv_bfloat16*>(out)[i] = f2bf(v);
+    const float l0h = 1.f - lh;
+    float f[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      int w0, w1;
+      float lw;
+      bil_src_ac(j * V + k, sw, wd, &w0, &w1, &lw);
+      // ATen's weighting order: h0lambda * (w0lambda * p00 + w1lambda * p01) + h1lambda * (w0lambda * p10 + w1lambda * p11)
+      const float l0w = 1.f - lw;
+      f[k] = l0h * (l0w * r0[w0] + lw * r0[w1]) + lh * (l0w * r1[w0] + lw * r1[w1]);
+    }
+    const int64_t o = (nc * H + oh) * (int64_t)W + (int64_t)j * V;
+    if (V == 8) {
+      if (OUT_F32) {
+        float* op = reinterpret_cast<float*>(out) + o;
+        *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(f[4 % V], f[5 % V], f[6 % V], f[7 % V]);
+      } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) = pack8(f);
+      }
+    } else {
+      if (OUT_F32) reinterpret_cast<float*>(out)[o] = f[0];
+      else reinterpret_cast<__nv_bfloat16*>(out)[o] = f2bf(f[0]);
+    }
   }
 }
 
@@ -212,22 +299,40 @@ prob_ce_fwd_kernel(const float* __restrict__ p, const int64_t* __restrict__ targ
 }
 
 // dp[n,c,px] = c == y ? -gscale * w[y] / (p[y] * acc[1]) : 0   (acc[1] = 1 for size_average=False)
+// VEC = 4: a thread owns 4 adjacent pixels (HW % 4 == 0, 16-byte aligned dp) and writes one float4 per channel
+template <int VEC>
 __global__ void __launch_bounds__(256)
 prob_ce_bwd_kernel(const float* __restrict__ p, const int64_t* __restrict__ target, const float* __restrict__ weight,
                    int64_t ignore_index, const float* __restrict__ acc, const float* __restrict__ gscale,
                    float* __restrict__ dp, int C, int64_t HW, int64_t total) {
   const float scale = gscale[0] / acc[1];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t y = target[i];
+  const int64_t groups = total / VEC;
+  for (int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < groups; gi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = gi * VEC;
     const int64_t n = i / HW, px = i % HW;
-    const bool valid = y != ignore_index && y >= 0 && y < C;
-    float gy = 0.f;
-    if (valid) gy = -scale * (weight ? weight[y] : 1.f) / p[(n * C + y) * HW + px];
-    for (int c = 0; c < C; ++c) dp[(n * C + c) * HW + px] = (valid && c == y) ? gy : 0.f;
+    int yy[VEC];
+    float gy[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int64_t y = target[i + k];
+      const bool valid = y != ignore_index && y >= 0 && y < C;
+      yy[k] = valid ? (int)y : -1;
+      gy[k] = valid ? -scale * (weight ? weight[y] : 1.f) / p[(n * C + y) * HW + px + k] : 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      float* o = dp + (n * C + c) * HW + px;
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(yy[0] == c ? gy[0] : 0.f, yy[1] == c ? gy[1] : 0.f,
+                                                    yy[2] == c ? gy[2] : 0.f, yy[3] == c ? gy[3] : 0.f);
+      } else {
+        o[0] = yy[0] == c ? gy[0] : 0.f;
+      }
+    }
   }
 }
 
 static inline int grid_for(int64_t n) { return (int)max64(1, min64((n + 255) / 256, 148 * 16)); }
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace mcd
 
@@ -248,7 +353,8 @@ int mcd_gate_fuse_fwd(const float* x1, const float* x2, const float* gate_logits
                       int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(x1 && x2 && gate_logits && out && numel > 0, "gate_fuse_fwd: bad arguments");
-  gate_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x1, x2, gate_logits, out, numel);
+  const int64_t n4 = (al16(x1) && al16(x2) && al16(gate_logits) && al16(out)) ? numel / 4 : 0;
+  gate_fwd_kernel<<<grid_for(n4 ? n4 : numel), 256, 0, (cudaStream_t)stream>>>(x1, x2, gate_logits, out, numel, n4);
   return check_launch("gate_fuse_fwd");
 }
 
@@ -256,8 +362,10 @@ int mcd_gate_fuse_bwd(const float* x1, const float* x2, const float* gate_logits
                       float* dx2, float* dgate_logits, int64_t numel, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(x1 && x2 && gate_logits && dout && numel > 0, "gate_fuse_bwd: bad arguments");
-  gate_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x1, x2, gate_logits, dout, dx1, dx2,
-                                                                     dgate_logits, numel);
+  const int64_t n4 = (al16(x1) && al16(x2) && al16(gate_logits) && al16(dout) && al16(dx1) && al16(dx2) &&
+                      al16(dgate_logits)) ? numel / 4 : 0;
+  gate_bwd_kernel<<<grid_for(n4 ? n4 : numel), 256, 0, (cudaStream_t)stream>>>(x1, x2, gate_logits, dout, dx1, dx2,
+                                                                               dgate_logits, numel, n4);
   return check_launch("gate_fuse_bwd");
 }
 
@@ -265,7 +373,10 @@ int mcd_softmax_ch_fwd(const float* x, float* p, int N, int C, int64_t HW, int d
   MCD_ENTER(device);
   MCD_REQUIRE(x && p && N > 0 && C > 0 && HW > 0, "softmax_ch_fwd: bad arguments");
   const int64_t total = (int64_t)N * HW;
-  softmax_ch_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, p, C, HW, total);
+  if (C <= SM_CMAX)
+    softmax_ch_fwd_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, p, C, HW, total);
+  else
+    softmax_ch_fwd_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, p, C, HW, total);
   return check_launch("softmax_ch_fwd");
 }
 
@@ -282,9 +393,14 @@ int mcd_cat2_f32(const float* a, int Ca, const float* b, int Cb, float* out, int
                  void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(a && b && out && N > 0 && Ca > 0 && Cb > 0 && HW > 0, "cat2_f32: bad arguments");
-  const int64_t total = (int64_t)N * (Ca + Cb) * HW;
-  cat2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(a), const_cast<float*>(b), out,
-                                                                 Ca * HW, Cb * HW, total, 1);
+  const int64_t total = (int64_t)N * (Ca + Cb) * HW, ea = Ca * HW, eb = Cb * HW;
+  float *pa = const_cast<float*>(a), *pb = const_cast<float*>(b);
+  if (ea % 4 == 0 && eb % 4 == 0 && al16(a) && al16(b) && al16(out))
+    cat2_kernel<float4><<<grid_for(total / 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(pa), reinterpret_cast<float4*>(pb), reinterpret_cast<float4*>(out), ea / 4, eb / 4,
+        total / 4, 1);
+  else
+    cat2_kernel<float><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(pa, pb, out, ea, eb, total, 1);
   return check_launch("cat2_f32");
 }
 
@@ -292,23 +408,30 @@ int mcd_split2_f32(const float* src, float* a, int Ca, float* b, int Cb, int N, 
                    void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(src && (a || b) && N > 0 && Ca > 0 && Cb > 0 && HW > 0, "split2_f32: bad arguments");
-  const int64_t total = (int64_t)N * (Ca + Cb) * HW;
-  cat2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a, b, const_cast<float*>(src), Ca * HW, Cb * HW,
-                                                                 total, 0);
+  const int64_t total = (int64_t)N * (Ca + Cb) * HW, ea = Ca * HW, eb = Cb * HW;
+  float* ps = const_cast<float*>(src);
+  if (ea % 4 == 0 && eb % 4 == 0 && al16(a) && al16(b) && al16(src))
+    cat2_kernel<float4><<<grid_for(total / 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), reinterpret_cast<float4*>(ps), ea / 4, eb / 4,
+        total / 4, 0);
+  else
+    cat2_kernel<float><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a, b, ps, ea, eb, total, 0);
   return check_launch("split2_f32");
 }
 
 int mcd_sigmoid_fwd(const float* x, float* y, int64_t numel, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(x && y && numel > 0, "sigmoid_fwd: bad arguments");
-  sigmoid_fwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(x, y, numel);
+  const int64_t n4 = (al16(x) && al16(y)) ? numel / 4 : 0;
+  sigmoid_fwd_kernel<<<grid_for(n4 ? n4 : numel), 256, 0, (cudaStream_t)stream>>>(x, y, numel, n4);
   return check_launch("sigmoid_fwd");
 }
 
 int mcd_sigmoid_bwd(const float* y, const float* dy, float* dx, int64_t numel, int device, void* stream) {
   MCD_ENTER(device);
   MCD_REQUIRE(y && dy && dx && numel > 0, "sigmoid_bwd: bad arguments");
-  sigmoid_bwd_kernel<<<grid_for(numel), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, numel);
+  const int64_t n4 = (al16(y) && al16(dy) && al16(dx)) ? numel / 4 : 0;
+  sigmoid_bwd_kernel<<<grid_for(n4 ? n4 : numel), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, numel, n4);
   return check_launch("sigmoid_bwd");
 }
 
@@ -336,8 +459,12 @@ int mcd_prob_ce2d_bwd(const float* p, const int64_t* target, const float* weight
   MCD_ENTER(device);
   MCD_REQUIRE(p && target && acc && gscale && dp && N > 0 && C > 0 && H > 0 && W > 0, "prob_ce2d_bwd: bad arguments");
   const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
-  prob_ce_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(p, target, weight, ignore_index, acc, gscale,
-                                                                        dp, C, HW, total);
+  if (HW % 4 == 0 && al16(dp))
+    prob_ce_bwd_kernel<4><<<grid_for(total / 4), 256, 0, (cudaStream_t)stream>>>(p, target, weight, ignore_index, acc,
+                                                                                 gscale, dp, C, HW, total);
+  else
+    prob_ce_bwd_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(p, target, weight, ignore_index, acc,
+                                                                             gscale, dp, C, HW, total);
   return check_launch("prob_ce2d_bwd");
 }
 
@@ -348,10 +475,14 @@ int mcd_bilinear_ac_up_fwd(const float* x, void* out, int out_f32, int N, int C,
   const int H = h * s, W = w_ * s;
   const float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sw = W > 1 ? (float)(w_ - 1) / (float)(W - 1) : 0.f;
   const int64_t total = (int64_t)N * C * H * W;
-  if (out_f32)
-    bilinear_ac_fwd_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, out, h, w_, H, W, sh, sw, total);
-  else
-    bilinear_ac_fwd_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, out, h, w_, H, W, sh, sw, total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (W % 8 == 0 && al16(out)) {
+    if (out_f32) bilinear_ac_fwd_kernel<true, 8><<<grid_for(total / 8), 256, 0, st>>>(x, out, h, w_, H, W, sh, sw, total / 8);
+    else bilinear_ac_fwd_kernel<false, 8><<<grid_for(total / 8), 256, 0, st>>>(x, out, h, w_, H, W, sh, sw, total / 8);
+  } else {
+    if (out_f32) bilinear_ac_fwd_kernel<true, 1><<<grid_for(total), 256, 0, st>>>(x, out, h, w_, H, W, sh, sw, total);
+    else bilinear_ac_fwd_kernel<false, 1><<<grid_for(total), 256, 0, st>>>(x, out, h, w_, H, W, sh, sw, total);
+  }
   return check_launch("bilinear_ac_up_fwd");
 }
 
