@@ -113,14 +113,21 @@ class DirectGrads:
 
 
 _direct = None
-_fuse_bn_bwd = os.environ.get("MCD_FUSE_BN_BWD", "1") != "0"
+# Opt-in (A/B switch, OFF by default): fuse the ReLU mask and the BatchNorm-backward sums {sum g, sum g * y} of the
+# producing unit into the dgrad epilogue of its sole-consumer convolution (direct-gradient mode only), which removes that
+# unit's reduction pass.  With the round-2 kernels the epilogue costs more than the pass it replaces: +47...+95 us per
+# launch (scripts/bench_thin_dgrad.py) against a memory-bound reduction that overlaps the tensor-bound wgrad stream;
+# whole iteration at 22 pairs: 137.4 ms fused everywhere, 135.4 ms for >= 128 / 256 channels only, 133.7 ms for >= 512
+# only, 133.5 ms never (profiles/r02e_ab_fuse_bn_bwd.txt).  MCD_FUSE_BN_BWD=1 [MCD_FUSE_BN_BWD_MIN_C=c] switches it on
+# (for convolutions whose input has >= c channels).
+_fuse_bn_bwd = os.environ.get("MCD_FUSE_BN_BWD", "0") == "1"
+_fuse_bn_bwd_min_c = int(os.environ.get("MCD_FUSE_BN_BWD_MIN_C", "0"))
 
 
-def set_fuse_bn_bwd(flag):
-    """fuse ReLU mask + BatchNorm-backward sums into the dgrad epilogue of sole-consumer convolutions
-    (direct-gradient mode only); off = separate reduction pass (for A/B measurements and tests)."""
-    global _fuse_bn_bwd
-    _fuse_bn_bwd = bool(flag)
+def set_fuse_bn_bwd(flag, min_channels=0):
+    """see above; off = separate reduction pass (the default)."""
+    global _fuse_bn_bwd, _fuse_bn_bwd_min_c
+    _fuse_bn_bwd, _fuse_bn_bwd_min_c = bool(flag), int(min_channels)
 
 
 def set_overlap_wgrad(flag):
@@ -179,7 +186,7 @@ def _conv_backward(mod, g, x, dy, need_dx, need_dw, want_db, bn_y, w_tag=None):
     # cannot share an SM with the persistent wgrad CTAs (both want ~190 KB of shared memory); the wgrad
     # that follows on the side stream then overlaps the memory-bound BatchNorm kernels of the next unit.
     add = _direct.stash.pop(x.data_ptr(), None) if _direct is not None else None   # identity-shortcut gradient
-    if need_dx and bn_y is not None and _fuse_bn_bwd and _direct is not None:
+    if need_dx and bn_y is not None and _fuse_bn_bwd and _direct is not None and x.shape[1] >= _fuse_bn_bwd_min_c:
         dx, sums = ops.conv_dgrad(dy, mod.packed(1, g), g, add=add, relu_src=x, bn_y=bn_y)
         _direct.bnsums[dx.data_ptr()] = (sums, bn_y.data_ptr(), dx)
     elif need_dx:

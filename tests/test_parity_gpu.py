@@ -349,10 +349,27 @@ def test_tester_argmax_entropy_vs_oracle(cuda_dev):
     assert abs(ent - ent_o) / abs(ent_o) <= 1e-3
 
 
-@pytest.mark.parametrize("graph", [False, True, "prefetch"])
+@pytest.mark.parametrize("graph", [False, True, "prefetch", "fused-bn-bwd", "fused-bn-bwd-512"])
 def test_mcdstep_runner_vs_oracle(cuda_dev, graph):
     """mcd_b200.step.MCDStep (dead phase-B backward skipped, phase-B target forward re-used for C[0] with folded
-    BatchNorm updates, optional CUDA-graph replay) produces the reference iteration's results."""
+    BatchNorm updates, optional CUDA-graph replay) produces the reference iteration's results.
+    "fused-bn-bwd[-512]": the same with the opt-in dgrad epilogue that applies the ReLU mask and accumulates the
+    BatchNorm-backward sums of the producing unit (everywhere / for >= 512-channel inputs only) - measured slower than
+    the separate reduction pass and off by default, kept and tested as an A/B switch."""
+    from loss import CrossEntropyLoss2d, get_prob_distance_criterion
+    from mcd_b200 import nn as mnn
+    from mcd_b200.step import MCDStep
+    if isinstance(graph, str) and graph.startswith("fused-bn-bwd"):
+        prev = (mnn._fuse_bn_bwd, mnn._fuse_bn_bwd_min_c)
+        mnn.set_fuse_bn_bwd(True, 512 if graph.endswith("512") else 0)
+        try:
+            return _mcdstep_runner_case(cuda_dev, False)
+        finally:
+            mnn.set_fuse_bn_bwd(*prev)
+    return _mcdstep_runner_case(cuda_dev, graph)
+
+
+def _mcdstep_runner_case(cuda_dev, graph):
     from loss import CrossEntropyLoss2d, get_prob_distance_criterion
     from mcd_b200.step import MCDStep
     dev, size, n = cuda_dev, (240, 320), 2
