@@ -58,16 +58,18 @@ class ConcatConvFusion(nn.Module):
         return self.conv(mnn.cat2(mnn.to_planar(x1), mnn.to_planar(x2)))
 
 
+# first substring match wins, in the reference's order (models/fusion.py:53-65)
+_BY_SUBSTRING = (
+    ("ScoreGateFusion", lambda n_ch: GateFusion(n_ch, apply_softmax=True)),
+    ("GateFusion", lambda n_ch: GateFusion(n_ch)),
+    ("AddFusion", lambda n_ch: AddFusion()),
+    ("ConcatFusion", lambda n_ch: ConcatFusion()),
+    ("ConcatConvFusion", lambda n_ch: ConcatConvFusion(n_ch)),
+)
+
+
 def get_fusion_model(fusion_type, n_ch):
-    if "ScoreGateFusion" in fusion_type:
-        return GateFusion(n_ch, apply_softmax=True)
-    if "GateFusion" in fusion_type:
-        return GateFusion(n_ch)
-    elif "AddFusion" in fusion_type:
-        return AddFusion()
-    elif "ConcatFusion" in fusion_type:
-        return ConcatFusion()
-    elif "ConcatConvFusion" in fusion_type:
-        return ConcatConvFusion(n_ch)
-    else:
-        raise NotImplementedError()
+    for key, make in _BY_SUBSTRING:
+        if key in fusion_type:
+            return make(n_ch)
+    raise NotImplementedError()
