@@ -248,7 +248,13 @@ class MCDStep:
         # optimizer kernel itself (ops.FusedSGD.deferred); with world > 1 the all-reduce needs real gradients
         # (and a weight gradient may be left in split form only once per step: the multitask trainers run the encoder
         # twice in phase A, source and target, so their gradients accumulate in param.grad instead)
-        self.defer_reduce = (fused_sgd and defer_wgrad_reduce and self.sync_g.world == 1
+        # a generator that runs its convolutions more than once per forward (FuseDRNSegBase: RGB and HHA through the same
+        # trunk) accumulates its weight gradients in param.grad as well, and its BatchNorm layers see two different
+        # batches per forward - folding the momentum updates of the shared B / C[0] target forward would reorder them
+        shared = any(getattr(m, "_mcd_shared_weights", False) for m in self.gens)
+        if shared:
+            self.reuse_t = False
+        self.defer_reduce = (fused_sgd and defer_wgrad_reduce and self.sync_g.world == 1 and not shared
                              and not exact_reference_backward and not self.task.a_uses_target)
         self.world = self.sync_g.world
         self.group = process_group

@@ -90,6 +90,7 @@ class FuseDRNSegBase(nn.Module):
     `main_layerK` (the `sub_layerK` trunk is constructed and never used - kept: it is part of the state_dict), the HHA
     activations are added after every stage.  Each stage therefore runs twice per forward on shared weights: BatchNorm
     running statistics take two updates, weight gradients accumulate over both passes."""
+    _mcd_shared_weights = True      # tells mcd_b200.step.MCDStep: no deferred split-K gradients, no folded BatchNorm updates
 
     def __init__(self, model_name, n_class, pretrained=True, input_ch=3, ver="ver1"):
         super().__init__()
