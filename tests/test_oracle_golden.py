@@ -488,3 +488,42 @@ def test_oracle_prob_cross_entropy_matches_reference():
     v.backward()
     assert abs(float(v) - float(z["pce:loss"])) <= 1e-6 * abs(float(z["pce:loss"]))
     close(p.grad.numpy(), z["pce:dp"], rtol=1e-6)
+
+
+def test_variant_modules_keep_the_reference_state_dict_layout():
+    """drop-in contract of the option surface, checkable without a GPU: the modules of multichannel-semseg-with-uda_b200
+    have exactly the state_dict keys and shapes of the reference's classes (recorded in variants.npz / restated by
+    head_state), so the reference's checkpoints load."""
+    import warnings
+    from models import dilated_fcn as D
+    from models.model_util import get_models
+    z = _variants()
+    fusion_type = {"gate": "GateFusion", "scoregate": "ScoreGateFusion", "add": "AddFusion", "concat": "ConcatFusion",
+                   "concatconv": "ConcatConvFusion", None: None}
+    for tag, cls, kind, ver, torch_up, cin in _HEAD_CASES:
+        if cls == "fusion":
+            m = D.FusionDRNSegPixelClassifier(fusion_type[kind], N_CLASS, use_torch_up=torch_up, ver=ver)
+        elif cls == "score":
+            m = D.ScoreFusionDRNSegPixelClassifier(fusion_type[kind], N_CLASS)
+        else:
+            m = D.DRNSegPixelClassifier(N_CLASS, use_torch_up=torch_up, ver=ver)
+        want = head_state(tag, cls, kind, ver, torch_up, cin)
+        got = m.state_dict()
+        assert set(got) == set(want), (tag, set(got) ^ set(want))
+        assert all(tuple(got[k].shape) == tuple(want[k].shape) for k in want), tag
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nets = {"fusenet": get_models("drn_d_22_fusenet", 6, N_CLASS)[0], "drn_c_26": get_models("drn_c_26", 6, N_CLASS)[0]}
+    for tag, net in nets.items():
+        keys = sorted(k for k, v in net.state_dict().items() if torch.is_floating_point(v))
+        assert keys == [str(k) for k in z[tag + ":state_keys"]], tag
+    decs = {"tri_opt": D.MCDTripleMultiTaskDecoder(N_CLASS, 3, semseg_shortcut=True, depth_shortcut=True,
+                                                   add_pred_seg_boundary_loss=True, use_seg2bd_conv=True),
+            "segbd": D.MCDSegBDMultiTaskDecoder(N_CLASS, 3), "tri_src": D.TripleMultiTaskDecoder(N_CLASS, 3)}
+    for tag, dec in decs.items():
+        want = decoder_option_state(tag, 0)
+        got = {k: v for k, v in dec.state_dict().items() if "criterion" not in k}
+        assert set(got) == set(want), (tag, set(got) ^ set(want))
+        assert all(tuple(got[k].shape) == tuple(want[k].shape) for k in want), tag
+        trained = set(k[2:] for k in (str(s_) for s_ in z[tag + ":grad_keys"]) if k.startswith("p:"))
+        assert trained <= set(k for k, _ in dec.named_parameters())
