@@ -1,8 +1,9 @@
 // variants.cu — the small memory-bound kernels behind the option surface around the MCD hot path (SURVEY.md
 // section 8 row f4): the Gate / Concat fusion heads (models/fusion.py:6-50), FuseDRNSegBase's per-stage adds
 // (models/dilated_fcn.py:294-331), nn.UpsamplingBilinear2d (align_corners=True; `use_torch_up`, :354-355,443-444),
-// F.softmax over channels (ScoreGateFusion, fusion.py:13-15) and F.sigmoid of the seg -> boundary convolution
-// (dilated_fcn.py:965-966).  All of them are single-pass, vectorised where the geometry allows, HBM-bound.
+// F.softmax over channels (ScoreGateFusion, fusion.py:13-15), F.sigmoid of the seg -> boundary convolution
+// (dilated_fcn.py:965-966) and ProbCrossEntropyLoss2d (loss.py:16-30, the Gate fusions' criterion).  Element-wise kernels
+// have 16-byte vector bodies with scalar tails; measured bandwidths: profiles/r02f_bench_variants.txt.
 #include "common.cuh"
 
 namespace mcd {
