@@ -76,6 +76,15 @@ def _share(go):
     return g / w if w > 1 else g
 
 
+def _check_target(logits, targets, who):
+    """nll_loss's own check (torch raises for a target whose batch / spatial sizes differ from the input's): the kernels
+    index the label map with the logits' geometry, so a smaller map would be read out of bounds"""
+    want = (logits.shape[0],) + tuple(logits.shape[2:])
+    if logits.dim() != 4 or tuple(targets.shape) != want:
+        raise ValueError("%s: input and target batch or spatial sizes don't match: target %s, input %s"
+                         % (who, list(targets.shape), list(logits.shape)))
+
+
 class _CE2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, weight, ignore_index, size_average, dist_group=False):
@@ -127,6 +136,7 @@ class CrossEntropyLoss2d(nn.Module):
 
     def forward(self, inputs, targets):
         logits = _logits(inputs)
+        _check_target(logits, targets, "CrossEntropyLoss2d")
         if targets.dtype != torch.int64:
             targets = targets.long()
         w = self.nll_loss.weight
@@ -169,6 +179,7 @@ class ProbCrossEntropyLoss2d(nn.Module):
 
     def forward(self, inputs, targets):
         p = inputs if inputs.dtype == F32 else inputs.float()
+        _check_target(p, targets, "ProbCrossEntropyLoss2d")
         if targets.dtype != torch.int64:
             targets = targets.long()
         w = self.nll_loss.weight

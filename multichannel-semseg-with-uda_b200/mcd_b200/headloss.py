@@ -186,8 +186,16 @@ class _HeadDiffFn(torch.autograd.Function):
         return (None,) + tuple(grads)
 
 
+def _check_target(inputs, target):
+    n, _, h, w = inputs[0].shape
+    if tuple(target.shape) != (n, 8 * h, 8 * w):
+        raise ValueError("CrossEntropyLoss2d: input and target batch or spatial sizes don't match: target %s, input %s"
+                         % (list(target.shape), [n, inputs[0].shape[1], 8 * h, 8 * w]))
+
+
 def head_ce2d(inputs, filters, target, weight=None, ignore_index=-100, size_average=True):
     """CrossEntropyLoss2d(weight, size_average, ignore_index)(head(inputs), target) without the logits tensor."""
+    _check_target(inputs, target)
     n_in = len(inputs)
     filters = [None] * n_in if filters is None else list(filters)
     xs = [_f32c(x) for x in inputs]
@@ -201,6 +209,7 @@ def head_ce2d(inputs, filters, target, weight=None, ignore_index=-100, size_aver
 def head_ce2d_pair(inputs, filters_a, filters_b, target, weight=None, ignore_index=-100, size_average=True):
     """CrossEntropyLoss2d(head_a(inputs), target) + CrossEntropyLoss2d(head_b(inputs), target): the supervised term of
     every MCD phase (adapt_trainer.py:171-175,191-194), one launch for both classifiers."""
+    _check_target(inputs, target)
     n_in = len(inputs)
     xs = [_f32c(x) for x in inputs]
     if target.dtype != torch.int64:

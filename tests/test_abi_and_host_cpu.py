@@ -162,3 +162,23 @@ def test_class_weights_and_lr_schedule():
     assert abs(util.adjust_learning_rate(opt, 1e-3, 0.1, 5, 10) - 1e-4) < 1e-12
     assert abs(util.adjust_learning_rate(opt, 1e-3, 0.1, 8, 10) - 1e-5) < 1e-12
     assert abs(opt.param_groups[0]["lr"] - 1e-5) < 1e-12
+
+
+def test_criteria_reject_mismatched_label_maps():
+    """torch's nll_loss raises when the label map does not have the logits' batch / spatial sizes (e.g. the source-only
+    MultiTaskDecoder of the reference, whose predictions stay at 1/8 resolution); the kernels index the labels with the
+    logits' geometry, so the check has to happen on the host - before anything touches the device."""
+    import torch
+    from loss import CrossEntropyLoss2d, ProbCrossEntropyLoss2d
+    from mcd_b200 import headloss
+    logits = torch.zeros(2, 41, 16, 24)
+    for crit in (CrossEntropyLoss2d(), ProbCrossEntropyLoss2d()):
+        for bad in (torch.zeros(2, 2, 3, dtype=torch.int64), torch.zeros(1, 16, 24, dtype=torch.int64),
+                    torch.zeros(2, 128, 192, dtype=torch.int64)):
+            with pytest.raises(ValueError, match="sizes don't match"):
+                crit(logits, bad)
+    with pytest.raises(ValueError, match="sizes don't match"):
+        headloss.head_ce2d([torch.zeros(2, 41, 2, 3)], None, torch.zeros(2, 2, 3, dtype=torch.int64))
+    with pytest.raises(ValueError, match="sizes don't match"):
+        headloss.head_ce2d_pair([torch.zeros(2, 41, 2, 3)], [torch.zeros(41, 1, 16, 16)], [torch.zeros(41, 1, 16, 16)],
+                                torch.zeros(2, 16, 25, dtype=torch.int64))
